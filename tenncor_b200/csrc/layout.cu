@@ -1,0 +1,366 @@
+// layout.cu — EXTEND / PERMUTE / SLICE / PAD / STRIDE / SCATTER / REVERSE / CONCAT.
+//
+// Replaces internal/eigen/operator.hpp:159-368. These are pure data movement and are
+// type-agnostic: kernels are instantiated per element size (1/2/4/8 bytes), results are
+// bit-exact. One coordinate-mapped copy kernel covers every op after the host collapses
+// the rank-8 description to its effective ranks; transposes of the two fastest ranks
+// go through a 32x32 shared-memory tile so that both the read and the write coalesce.
+#include <vector>
+
+#include "common.cuh"
+
+namespace tcr {
+
+template <int S> struct Elem;
+template <> struct Elem<1> { using type = uint8_t; };
+template <> struct Elem<2> { using type = uint16_t; };
+template <> struct Elem<4> { using type = uint32_t; };
+template <> struct Elem<8> { using type = uint64_t; };
+
+struct MapDim {
+  int64_t ext;        // output extent
+  int64_t mul, add, div;
+  int64_t in_dim;     // input extent of the mapped rank
+  int64_t in_stride;  // input stride (elements) of the mapped rank
+};
+
+struct MapPlan {
+  int nd;
+  int check;          // any rank needs a validity test
+  int64_t n_out;
+  int64_t base;       // constant input offset from collapsed extent-1 ranks
+  MapDim d[8];
+};
+
+template <typename E, typename I, bool CHECK>
+__global__ void __launch_bounds__(256) map_copy_kernel(const E* __restrict__ in, E* __restrict__ out, const __grid_constant__ MapPlan p) {
+  const I n = (I)p.n_out;
+  const I stride = (I)gridDim.x * blockDim.x;
+  for (I o = (I)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += stride) {
+    I t = o;
+    int64_t off = p.base;
+    bool valid = true;
+#pragma unroll 1
+    for (int k = 0; k < p.nd; ++k) {
+      const MapDim& d = p.d[k];
+      I c;
+      if (k == p.nd - 1) c = t;
+      else { c = t % (I)d.ext; t = t / (I)d.ext; }
+      int64_t q = (int64_t)c * d.mul + d.add;
+      if (CHECK) {
+        if (d.div != 1) {
+          if (q % d.div != 0) valid = false;
+          q /= d.div;
+        }
+        if (q < 0 || q >= d.in_dim) valid = false;
+      }
+      off += q * d.in_stride;
+    }
+    E v = E(0);
+    if (!CHECK || valid) v = in[off];
+    out[o] = v;
+  }
+}
+
+// out[j + B*(i + A*c)] = in[i + A*(j + B*c)]  (in is [A, B, C], out is [B, A, C])
+template <typename E>
+__global__ void __launch_bounds__(256) transpose_kernel(const E* __restrict__ in, E* __restrict__ out, int64_t A, int64_t B) {
+  __shared__ E tile[32][33];
+  const int64_t c = blockIdx.z;
+  const E* src = in + c * A * B;
+  E* dst = out + c * A * B;
+  const int64_t i0 = (int64_t)blockIdx.x * 32, j0 = (int64_t)blockIdx.y * 32;
+#pragma unroll
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int64_t i = i0 + threadIdx.x, j = j0 + y;
+    if (i < A && j < B) tile[y][threadIdx.x] = src[i + A * j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int64_t j = j0 + threadIdx.x, i = i0 + y;
+    if (i < A && j < B) dst[j + B * i] = tile[threadIdx.x][y];
+  }
+}
+
+// concat: copy one argument (shape [inner, ext, outer]) into out at axis offset `off`
+struct ConcatArgs {
+  const void* ptr[32];
+  int n;
+};
+
+template <typename E>
+__global__ void __launch_bounds__(256) concat_one_kernel(const E* __restrict__ in, E* __restrict__ out, int64_t inner,
+                                                         int64_t ext, int64_t outer, int64_t off, int64_t out_ext) {
+  const int64_t n = inner * ext * outer, stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t row = inner * ext;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t r = i % row, o = i / row;
+    out[r + inner * off + inner * out_ext * o] = in[i];
+  }
+}
+
+// n-ary concat: every argument has extent 1 along the axis; args k0..k0+n-1 of `total`
+template <typename E>
+__global__ void __launch_bounds__(256) concat_many_kernel(const __grid_constant__ ConcatArgs a, E* __restrict__ out,
+                                                          int64_t inner, int64_t outer, int k0, int total) {
+  const int64_t per = inner * outer, n = per * a.n, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t ii = i % inner, t = i / inner;
+    int k = (int)(t % a.n);
+    int64_t o = t / a.n;
+    const E* src = (const E*)a.ptr[k];
+    out[ii + inner * ((k0 + k) + (int64_t)total * o)] = src[ii + inner * o];
+  }
+}
+
+template <typename E>
+static int launch_map(const void* in, void* out, const MapPlan& p, int64_t n_in) {
+  int grid = wave_grid(p.n_out, 256, 8);
+  bool small = p.n_out < (1ll << 31) && n_in < (1ll << 31);
+  if (small) {
+    if (p.check) TCR_LAUNCH((map_copy_kernel<E, uint32_t, true>), grid, 256, 0, (const E*)in, (E*)out, p);
+    else TCR_LAUNCH((map_copy_kernel<E, uint32_t, false>), grid, 256, 0, (const E*)in, (E*)out, p);
+  } else {
+    if (p.check) TCR_LAUNCH((map_copy_kernel<E, int64_t, true>), grid, 256, 0, (const E*)in, (E*)out, p);
+    else TCR_LAUNCH((map_copy_kernel<E, int64_t, false>), grid, 256, 0, (const E*)in, (E*)out, p);
+  }
+  TCR_CHECK_LAUNCH();
+  return TCR_OK;
+}
+
+#define TCR_DISPATCH_ELEM(es, E, ...)                                           \
+  switch (es) {                                                                \
+    case 1: { using E = Elem<1>::type; __VA_ARGS__; } break;                   \
+    case 2: { using E = Elem<2>::type; __VA_ARGS__; } break;                   \
+    case 4: { using E = Elem<4>::type; __VA_ARGS__; } break;                   \
+    case 8: { using E = Elem<8>::type; __VA_ARGS__; } break;                   \
+    default: set_error("layout op: unsupported element size %d", (int)(es)); return TCR_ERR_ARG; \
+  }
+
+static void identity_desc(tcr_map_desc* d, const int64_t in_shape[8], const int64_t out_shape[8]) {
+  for (int k = 0; k < 8; ++k) {
+    d->in_shape[k] = in_shape[k];
+    d->out_shape[k] = out_shape[k];
+    d->perm[k] = k;
+    d->mul[k] = 1;
+    d->add[k] = 0;
+    d->div[k] = 1;
+  }
+}
+
+}  // namespace tcr
+
+using namespace tcr;
+
+extern "C" {
+
+int tcr_map_copy(const void* in, void* out, const tcr_map_desc* desc, int elem_size) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(in && out && desc, "tcr_map_copy: null argument");
+  int64_t in_stride[8], n_in = 1, n_out = 1;
+  bool seen[8] = {false};
+  for (int k = 0; k < 8; ++k) {
+    TCR_ARG(desc->in_shape[k] >= 0 && desc->out_shape[k] >= 0, "tcr_map_copy: negative extent");
+    TCR_ARG(desc->perm[k] >= 0 && desc->perm[k] < 8 && !seen[desc->perm[k]], "tcr_map_copy: perm is not a permutation");
+    TCR_ARG(desc->div[k] >= 1, "tcr_map_copy: div must be >= 1");
+    seen[desc->perm[k]] = true;
+    in_stride[k] = n_in;
+    n_in *= desc->in_shape[k];
+    n_out *= desc->out_shape[k];
+  }
+  if (n_out == 0) return TCR_OK;
+  if (n_in == 0) return tcr_memset(out, 0, (size_t)n_out * elem_size);
+
+  // collapse to effective ranks
+  MapPlan p;
+  memset(&p, 0, sizeof(p));
+  p.n_out = n_out;
+  bool dead = false;  // a collapsed extent-1 rank maps outside the input -> all zeros
+  for (int k = 0; k < 8; ++k) {
+    int r = desc->perm[k];
+    MapDim d{desc->out_shape[k], desc->mul[k], desc->add[k], desc->div[k], desc->in_shape[r], in_stride[r]};
+    if (d.ext == 1) {
+      int64_t q = d.add;
+      if (q % d.div != 0) { dead = true; continue; }
+      q /= d.div;
+      if (q < 0 || q >= d.in_dim) { dead = true; continue; }
+      p.base += q * d.in_stride;
+      continue;
+    }
+    bool need_check = d.div != 1 || d.add < 0 || ((d.ext - 1) * d.mul + d.add) / d.div >= d.in_dim ||
+                      (d.mul < 0 && (d.ext - 1) * d.mul + d.add < 0);
+    if (need_check) p.check = 1;
+    if (p.nd > 0) {
+      MapDim& prev = p.d[p.nd - 1];
+      // merge (prev, d) when both walk contiguous full input ranks in order
+      bool plain_prev = prev.mul == 1 && prev.add == 0 && prev.div == 1 && prev.in_dim == prev.ext;
+      bool plain_d = d.mul == 1 && d.add == 0 && d.div == 1;
+      if (plain_prev && plain_d && d.in_stride == prev.in_stride * prev.in_dim && !need_check) {
+        prev.ext *= d.ext;
+        prev.in_dim *= d.in_dim;
+        continue;
+      }
+      // merge broadcast ranks (mul == 0)
+      if (prev.mul == 0 && d.mul == 0 && prev.div == 1 && d.div == 1 && !need_check) {
+        p.base += 0;
+        int64_t q = d.add;  // constant coordinate
+        if (q < 0 || q >= d.in_dim) { dead = true; continue; }
+        p.base += q * d.in_stride;
+        prev.ext *= d.ext;
+        continue;
+      }
+    }
+    p.d[p.nd++] = d;
+  }
+  if (dead) return tcr_memset(out, 0, (size_t)n_out * elem_size);
+  if (p.nd == 0) {  // single element
+    return tcr_d2d(out, (const char*)in + p.base * elem_size, (size_t)elem_size);
+  }
+  // plain contiguous copy
+  if (p.nd == 1 && !p.check && p.d[0].mul == 1 && p.d[0].in_stride == 1)
+    return tcr_d2d(out, (const char*)in + (p.base + p.d[0].add) * elem_size, (size_t)n_out * elem_size);
+  // transpose of the two fastest effective ranks (optionally batched)
+  if (!p.check && (p.nd == 2 || p.nd == 3) && p.base == 0) {
+    const MapDim& d0 = p.d[0];
+    const MapDim& d1 = p.d[1];
+    bool t01 = d0.mul == 1 && d0.add == 0 && d1.mul == 1 && d1.add == 0 && d1.in_stride == 1 &&
+               d1.in_dim == d1.ext && d0.in_stride == d1.ext && d0.in_dim == d0.ext;
+    bool batch_ok = p.nd == 2 || (p.d[2].mul == 1 && p.d[2].add == 0 && p.d[2].in_stride == d0.ext * d1.ext &&
+                                  p.d[2].ext <= 65535);
+    if (t01 && batch_ok) {
+      int64_t A = d1.ext, B = d0.ext, C = p.nd == 3 ? p.d[2].ext : 1;  // in [A,B,C] -> out [B,A,C]
+      dim3 grid((unsigned)ceil_div(A, 32), (unsigned)ceil_div(B, 32), (unsigned)C);
+      if (grid.y <= 65535) {
+        TCR_DISPATCH_ELEM(elem_size, E, TCR_LAUNCH((transpose_kernel<E>), grid, dim3(32, 8), 0, (const E*)in, (E*)out, A, B));
+        TCR_CHECK_LAUNCH();
+        return TCR_OK;
+      }
+    }
+  }
+  TCR_DISPATCH_ELEM(elem_size, E, return launch_map<E>(in, out, p, n_in));
+  return TCR_OK;
+}
+
+int tcr_extend(const void* in, void* out, const int64_t in_shape[8], const int64_t bcast[8], int elem_size) {
+  tcr_map_desc d;
+  int64_t out_shape[8];
+  for (int k = 0; k < 8; ++k) {
+    TCR_ARG(bcast[k] >= 1, "tcr_extend: cannot extend using zero dimensions");
+    TCR_ARG(!(bcast[k] > 1 && in_shape[k] > 1), "tcr_extend: cannot extend non-singular dimension %d", k);
+    out_shape[k] = in_shape[k] * bcast[k];
+  }
+  identity_desc(&d, in_shape, out_shape);
+  for (int k = 0; k < 8; ++k)
+    if (bcast[k] > 1) d.mul[k] = 0;
+  return tcr_map_copy(in, out, &d, elem_size);
+}
+
+int tcr_permute(const void* in, void* out, const int64_t in_shape[8], const int32_t order[8], int elem_size) {
+  tcr_map_desc d;
+  int64_t out_shape[8];
+  for (int k = 0; k < 8; ++k) {
+    TCR_ARG(order[k] >= 0 && order[k] < 8, "tcr_permute: order[%d] out of range", k);
+    out_shape[k] = in_shape[order[k]];
+  }
+  identity_desc(&d, in_shape, out_shape);
+  for (int k = 0; k < 8; ++k) d.perm[k] = order[k];
+  return tcr_map_copy(in, out, &d, elem_size);
+}
+
+int tcr_slice(const void* in, void* out, const int64_t in_shape[8], const int64_t offsets[8], const int64_t extents[8], int elem_size) {
+  tcr_map_desc d;
+  for (int k = 0; k < 8; ++k)
+    TCR_ARG(offsets[k] >= 0 && extents[k] >= 1 && offsets[k] + extents[k] <= in_shape[k], "tcr_slice: box out of range at rank %d", k);
+  identity_desc(&d, in_shape, extents);
+  for (int k = 0; k < 8; ++k) d.add[k] = offsets[k];
+  return tcr_map_copy(in, out, &d, elem_size);
+}
+
+int tcr_pad(const void* in, void* out, const int64_t in_shape[8], const int64_t pad_lo[8], const int64_t pad_hi[8], int elem_size) {
+  tcr_map_desc d;
+  int64_t out_shape[8];
+  for (int k = 0; k < 8; ++k) {
+    TCR_ARG(pad_lo[k] >= 0 && pad_hi[k] >= 0, "tcr_pad: negative padding");
+    out_shape[k] = in_shape[k] + pad_lo[k] + pad_hi[k];
+  }
+  identity_desc(&d, in_shape, out_shape);
+  for (int k = 0; k < 8; ++k) d.add[k] = -pad_lo[k];
+  return tcr_map_copy(in, out, &d, elem_size);
+}
+
+int tcr_stride(const void* in, void* out, const int64_t in_shape[8], const int64_t incrs[8], int elem_size) {
+  tcr_map_desc d;
+  int64_t out_shape[8];
+  for (int k = 0; k < 8; ++k) {
+    TCR_ARG(incrs[k] >= 1, "tcr_stride: increments must be >= 1");
+    out_shape[k] = (in_shape[k] + incrs[k] - 1) / incrs[k];  // Eigen TensorStridingOp: ceil(dim / stride)
+  }
+  identity_desc(&d, in_shape, out_shape);
+  for (int k = 0; k < 8; ++k) d.mul[k] = incrs[k];
+  return tcr_map_copy(in, out, &d, elem_size);
+}
+
+int tcr_scatter(const void* in, void* out, const int64_t in_shape[8], const int64_t out_shape[8], const int64_t incrs[8], int elem_size) {
+  tcr_map_desc d;
+  identity_desc(&d, in_shape, out_shape);
+  for (int k = 0; k < 8; ++k) {
+    TCR_ARG(incrs[k] >= 1, "tcr_scatter: increments must be >= 1");
+    d.div[k] = incrs[k];
+  }
+  return tcr_map_copy(in, out, &d, elem_size);
+}
+
+int tcr_reverse(const void* in, void* out, const int64_t shape[8], uint32_t reverse_mask, int elem_size) {
+  tcr_map_desc d;
+  identity_desc(&d, shape, shape);
+  for (int k = 0; k < 8; ++k)
+    if ((reverse_mask >> k) & 1u) { d.mul[k] = -1; d.add[k] = shape[k] - 1; }
+  return tcr_map_copy(in, out, &d, elem_size);
+}
+
+int tcr_concat(const void* const* args, const int64_t* shapes, int nargs, void* out, int axis, int elem_size) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(args && shapes && out, "tcr_concat: null argument");
+  TCR_ARG(nargs >= 2, "tcr_concat: needs at least two arguments");
+  TCR_ARG(axis >= 0 && axis < 8, "tcr_concat: axis %d out of range", axis);
+  const int64_t* s0 = shapes;
+  int64_t inner = 1, outer = 1, out_ext = 0;
+  for (int k = 0; k < axis; ++k) inner *= s0[k];
+  for (int k = axis + 1; k < 8; ++k) outer *= s0[k];
+  for (int a = 0; a < nargs; ++a) {
+    const int64_t* s = shapes + 8 * a;
+    for (int k = 0; k < 8; ++k)
+      TCR_ARG(k == axis || s[k] == s0[k], "tcr_concat: argument %d shape mismatch at rank %d", a, k);
+    if (nargs > 2) TCR_ARG(s[axis] == 1, "tcr_concat: cannot group concat shapes with dimension that is not one");
+    out_ext += s[axis];
+  }
+  if (inner * outer * out_ext == 0) return TCR_OK;
+  if (nargs > 2) {
+    for (int k0 = 0; k0 < nargs; k0 += 32) {
+      ConcatArgs ca;
+      ca.n = nargs - k0 < 32 ? nargs - k0 : 32;
+      for (int k = 0; k < ca.n; ++k) ca.ptr[k] = args[k0 + k];
+      int grid = wave_grid(inner * outer * ca.n, 256, 8);
+      TCR_DISPATCH_ELEM(elem_size, E, TCR_LAUNCH((concat_many_kernel<E>), grid, 256, 0, ca, (E*)out, inner, outer, k0, nargs));
+    }
+    TCR_CHECK_LAUNCH();
+    return TCR_OK;
+  }
+  int64_t off = 0;
+  for (int a = 0; a < nargs; ++a) {
+    int64_t ext = shapes[8 * a + axis];
+    if (outer == 1) {  // contiguous block
+      int rc = tcr_d2d((char*)out + inner * off * elem_size, args[a], (size_t)(inner * ext) * elem_size);
+      if (rc) return rc;
+    } else {
+      int grid = wave_grid(inner * ext * outer, 256, 8);
+      TCR_DISPATCH_ELEM(elem_size, E, TCR_LAUNCH((concat_one_kernel<E>), grid, 256, 0, (const E*)args[a], (E*)out, inner, ext, outer, off, out_ext));
+    }
+    off += ext;
+  }
+  TCR_CHECK_LAUNCH();
+  return TCR_OK;
+}
+
+}  // extern "C"
