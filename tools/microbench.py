@@ -1,0 +1,122 @@
+"""Per-kernel micro-benchmarks (M-ew, M-red, M-lay, M-mm) through the C-ABI.
+Prints one JSON line per case: achieved GB/s (algorithmic bytes / CUDA-event time) or TFLOP/s.
+Inputs are larger than L2 (126 MB) for the HBM-bound cases so no flush is needed.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tenncor_b200 import cabi  # noqa: E402
+
+
+def timeit(fn, warmup=3, iters=10):
+    lib = cabi.lib()
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    cabi.check(lib.tcr_event_create(C.byref(e0)))
+    cabi.check(lib.tcr_event_create(C.byref(e1)))
+    for _ in range(warmup):
+        fn()
+    cabi.sync()
+    cabi.check(lib.tcr_event_record(e0))
+    for _ in range(iters):
+        fn()
+    cabi.check(lib.tcr_event_record(e1))
+    ms = C.c_float()
+    cabi.check(lib.tcr_event_elapsed_ms(e0, e1, C.byref(ms)))
+    return ms.value / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--log2n", type=int, default=26)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--peaks", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))
+    args = ap.parse_args()
+    peak = 6547.8
+    if os.path.exists(args.peaks):
+        peak = json.load(open(args.peaks)).get("hbm_gbs", peak)
+    cabi.init(0)
+    lib = cabi.lib()
+    n = 1 << args.log2n
+    rng = np.random.default_rng(5)
+    host = rng.uniform(-4, 4, n).astype(np.float32)
+    a, b, c = cabi.to_device(host), cabi.to_device(host[::-1].copy()), cabi.to_device(np.abs(host))
+    out = cabi.empty(n, np.float32)
+    F = cabi.FLOAT
+    P = lambda x: C.c_void_p(x.ptr)  # noqa: E731
+    res = []
+
+    def rec(name, ms, nbytes=None, flops=None):
+        r = {"case": name, "ms": round(ms, 4)}
+        if nbytes is not None:
+            r["GBps"] = round(nbytes / ms / 1e6, 1)
+            r["frac_of_measured_hbm"] = round(r["GBps"] / peak, 3)
+        if flops is not None:
+            r["TFLOPs"] = round(flops / ms / 1e9, 2)
+        res.append(r)
+        print(json.dumps(r), flush=True)
+
+    def want(name):
+        return not args.only or any(name.startswith(p) for p in args.only.split(","))
+
+    if want("ew"):
+        for op in ["EXP", "SIGMOID", "TANH", "NEG"]:
+            rec("ew_unary_%s_2^%d" % (op, args.log2n), timeit(lambda: cabi.check(lib.tcr_unary(cabi.OP[op], P(a), P(out), C.c_int64(n), F))), 8 * n)
+        for op in ["ADD", "MUL"]:
+            rec("ew_binary_%s_2^%d" % (op, args.log2n), timeit(lambda: cabi.check(lib.tcr_binary(cabi.OP[op], P(a), P(b), P(out), C.c_int64(n), F))), 12 * n)
+        prog = cabi.make_program(F, (n, 1, 1), [(a.ptr, F, (0, 0, 0)), (b.ptr, F, (0, 0, 0)), (c.ptr, F, (0, 0, 0))], [(out.ptr, F, 0)],
+                                 [(cabi.OP["MUL"], 0, 0, 1), (cabi.OP["ADD"], 0, 0, 2), (cabi.OP["SIGMOID"], 0, 0)])
+        rec("ew_fused_sigmoid(a*b+c)_2^%d" % args.log2n, timeit(lambda: cabi.check(lib.tcr_elementwise(C.byref(prog)))), 16 * n)
+        rec("ew_assign_sub_2^%d" % args.log2n, timeit(lambda: cabi.check(lib.tcr_assign(cabi.OP["ASSIGN_SUB"], P(out), P(a), C.c_int64(n), F))), 12 * n)
+        H, B = 1024, n // 1024
+        bias = cabi.to_device(host[:H].copy())
+        prog2 = cabi.make_program(F, (H, B, 1), [(a.ptr, F, (0, 0, 0)), (bias.ptr, F, (0, 1, 0))], [(out.ptr, F, 0)],
+                                  [(cabi.OP["ADD"], 0, 0, 1), (cabi.OP["SIGMOID"], 0, 0)])
+        rec("ew_fused_bias_sigmoid_[1024,%d]" % B, timeit(lambda: cabi.check(lib.tcr_elementwise(C.byref(prog2)))), 8 * n + 4 * H)
+    if want("red"):
+        R0, R1 = 4096, n // 4096
+        shape = cabi.shape8([R0, R1])
+        small = cabi.empty(max(R0, R1), np.float32)
+        for op in ["REDUCE_SUM", "REDUCE_MAX"]:
+            for mask, nm, nout in [(1, "dim0", R1), (2, "dim1", R0), (3, "full", 1)]:
+                rec("red_%s_%s_[4096,%d]" % (op, nm, R1), timeit(lambda: cabi.check(lib.tcr_reduce(cabi.OP[op], P(a), P(small), shape, C.c_uint32(mask), F))), 4 * (n + nout))
+        for dim, nm, nout in [(0, "dim0", R1), (1, "dim1", R0), (8, "flat", 1)]:
+            rec("argmax_%s_[4096,%d]" % (nm, R1), timeit(lambda: cabi.check(lib.tcr_argmax(P(a), P(small), shape, dim, F))), 4 * (n + nout))
+    if want("lay"):
+        side = 1 << (args.log2n // 2)
+        m = side * side
+        order = (C.c_int32 * 8)(1, 0, 2, 3, 4, 5, 6, 7)
+        rec("lay_permute10_[%d,%d]" % (side, side), timeit(lambda: cabi.check(lib.tcr_permute(P(a), P(out), cabi.shape8([side, side]), order, 4))), 8 * m)
+        bc = (C.c_int64 * 8)(1, n // 1024, 1, 1, 1, 1, 1, 1)
+        rec("lay_extend_[1024]->[1024,%d]" % (n // 1024), timeit(lambda: cabi.check(lib.tcr_extend(P(a), P(out), cabi.shape8([1024]), bc, 4))), 4 * n + 4096)
+        s3 = [1024, 128, n // (1024 * 128)]
+        offs = (C.c_int64 * 8)(0, 32, 0, 0, 0, 0, 0, 0)
+        exts = (C.c_int64 * 8)(1024, 64, s3[2], 1, 1, 1, 1, 1)
+        rec("lay_slice_mid_[1024,128,%d]" % s3[2], timeit(lambda: cabi.check(lib.tcr_slice(P(a), P(out), cabi.shape8(s3), offs, exts, 4))), 8 * (n // 2))
+        lo = (C.c_int64 * 8)(0, 16, 0, 0, 0, 0, 0, 0)
+        hi = (C.c_int64 * 8)(0, 16, 0, 0, 0, 0, 0, 0)
+        s3h = [1024, 96, s3[2]]
+        rec("lay_pad_mid_[1024,96,%d]" % s3[2], timeit(lambda: cabi.check(lib.tcr_pad(P(a), P(out), cabi.shape8(s3h), lo, hi, 4))), 4 * (1024 * 96 * s3[2] + n))
+        half = [1024, 64, s3[2]]
+        tab = (C.c_void_p * 2)(a.ptr, b.ptr)
+        shp = (C.c_int64 * 16)(*(cabi.shape8(half)[:] + cabi.shape8(half)[:]))
+        rec("lay_concat_axis1_[1024,64,%d]x2" % s3[2], timeit(lambda: cabi.check(lib.tcr_concat(tab, shp, 2, P(out), 1, 4))), 8 * n)
+    if want("mm"):
+        for prec, nm in [(0, "exact_simt"), (1, "tf32"), (2, "3xtf32")]:
+            for s in [1024, 4096]:
+                if prec == 0 and s > 2048:
+                    continue
+                M = N = K = s
+                d = cabi.GemmDesc(m=M, n=N, k=K, batch=1, a_sm=K, a_sk=1, a_sb=0, b_sk=N, b_sn=1, b_sb=0, c_sm=N, c_sn=1, c_sb=0,
+                                  dtype=F, precision=prec)
+                rec("mm_%s_%d^3" % (nm, s), timeit(lambda: cabi.check(lib.tcr_gemm(P(a), P(b), P(out), C.byref(d))), iters=5), flops=2.0 * M * N * K)
+    return res
+
+
+if __name__ == "__main__":
+    main()
