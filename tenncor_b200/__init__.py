@@ -15,3 +15,11 @@ try:  # the host extension is optional at import time so that build() can import
 except ImportError as _e:  # pragma: no cover
     HAVE_HOST = False
     _HOST_IMPORT_ERROR = _e
+
+if HAVE_HOST:
+    layer_rnn = _tenncor.api.layer.rnn_on
+
+
+def require_host():
+    if not HAVE_HOST:
+        raise ImportError("tenncor_b200._tenncor is not built: run __graft_entry__.build() (%s)" % _HOST_IMPORT_ERROR)

@@ -282,129 +282,120 @@ __device__ __forceinline__ void store_any(void* p, int dtype, int64_t j, T v) {
 
 constexpr int VM_V = 4;  // elements per thread per iteration
 
-#define VM_REG_SWITCH(IDX, R, ...)                   \
-  switch (IDX) {                                     \
-    case 0: { auto& R = r0; __VA_ARGS__; } break;    \
-    case 1: { auto& R = r1; __VA_ARGS__; } break;    \
-    case 2: { auto& R = r2; __VA_ARGS__; } break;    \
-    case 3: { auto& R = r3; __VA_ARGS__; } break;    \
-    case 4: { auto& R = r4; __VA_ARGS__; } break;    \
-    case 5: { auto& R = r5; __VA_ARGS__; } break;    \
-    case 6: { auto& R = r6; __VA_ARGS__; } break;    \
-    default: { auto& R = r7; __VA_ARGS__; } break;   \
-  }
+template <typename T> struct alignas(16) V4 { T v[VM_V]; };
+template <typename T> struct VmCfg { static constexpr int THREADS = sizeof(T) == 4 ? 256 : 128; };
 
-template <typename T, bool ALIGNED>
-__global__ void __launch_bounds__(256) ew_vm_kernel(const __grid_constant__ VmParams p) {
-  const int64_t n = p.n;
-  const int64_t nchunks = (n + VM_V - 1) / VM_V;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += stride) {
-    const int64_t base = ch * VM_V;
+// The virtual registers live in shared memory, one 4-element slot per (register, thread):
+// operand fetch is an LDS.128 with a computed address instead of a branch tree over
+// hardware registers, which keeps the kernel at ~40 registers (full occupancy) and makes
+// the cost of a VM instruction two shared loads, one uniform opcode branch and one store.
+template <typename T, bool ALIGNED, typename I>
+__global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_constant__ VmParams p) {
+  constexpr int THREADS = VmCfg<T>::THREADS;
+  __shared__ V4<T> regs[TCR_EW_NREGS][THREADS];
+  const I n = (I)p.n;
+  const I nchunks = (n + VM_V - 1) / VM_V;
+  const I stride = (I)gridDim.x * THREADS;
+  const I d0 = (I)p.d0, d1 = (I)p.d1;
+  for (I ch = (I)blockIdx.x * THREADS + threadIdx.x; ch < nchunks; ch += stride) {
+    const I base = ch * VM_V;
     const bool full = base + VM_V <= n;
-    T r0[VM_V], r1[VM_V], r2[VM_V], r3[VM_V], r4[VM_V], r5[VM_V], r6[VM_V], r7[VM_V];
-#pragma unroll
-    for (int v = 0; v < VM_V; ++v) r0[v] = r1[v] = r2[v] = r3[v] = r4[v] = r5[v] = r6[v] = r7[v] = T(0);
-    // ---- load inputs
+    // ---- load inputs into registers 0..n_inputs-1
     for (int k = 0; k < p.n_inputs; ++k) {
-      T x[VM_V];
+      V4<T> x;
       const VmInput& in = p.in[k];
       if (in.mode == 1) {
         T s = load_any<T>(in.ptr, in.dtype, 0);
 #pragma unroll
-        for (int v = 0; v < VM_V; ++v) x[v] = s;
+        for (int v = 0; v < VM_V; ++v) x.v[v] = s;
       } else if (in.mode == 0) {
         if (ALIGNED && full && in.dtype == DTypeOf<T>::value) {
           const T* src = (const T*)in.ptr + base;
           if (sizeof(T) == 4) {
-            Vec<T> q = ld16(src);
-#pragma unroll
-            for (int v = 0; v < VM_V; ++v) x[v] = q.v[v];
+            *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
           } else {
-            Vec<T> q0 = ld16(src), q1 = ld16(src + 2);
-            x[0] = q0.v[0]; x[1] = q0.v[1]; x[2] = q1.v[0]; x[3] = q1.v[1];
+            *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
+            *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
           }
         } else {
 #pragma unroll
-          for (int v = 0; v < VM_V; ++v) x[v] = (base + v < n) ? load_any<T>(in.ptr, in.dtype, base + v) : T(0);
+          for (int v = 0; v < VM_V; ++v) x.v[v] = (base + v < n) ? load_any<T>(in.ptr, in.dtype, base + v) : T(0);
+        }
+      } else if (in.mode == 3) {
+        // 3-segment broadcast with D0 % 4 == 0: the chunk stays inside one run of segment 0
+        const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
+        I i0 = base % d0, t = base / d0, i1 = t % d1, i2 = t / d1;
+        I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
+        if (in.bcast[0]) {
+          T s = load_any<T>(in.ptr, in.dtype, j);
+#pragma unroll
+          for (int v = 0; v < VM_V; ++v) x.v[v] = s;
+        } else if (ALIGNED && in.dtype == DTypeOf<T>::value) {
+          const T* src = (const T*)in.ptr + j;
+          *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
+          if (sizeof(T) == 8) *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VM_V; ++v) x.v[v] = load_any<T>(in.ptr, in.dtype, j + v);
         }
       } else {
-        const int64_t e0 = in.bcast[0] ? 1 : p.d0, e1 = in.bcast[1] ? 1 : p.d1;
+        const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
 #pragma unroll
         for (int v = 0; v < VM_V; ++v) {
-          int64_t i = base + v;
-          if (i >= n) { x[v] = T(0); continue; }
-          int64_t i0 = i % p.d0, t = i / p.d0, i1 = t % p.d1, i2 = t / p.d1;
-          int64_t j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
-          x[v] = load_any<T>(in.ptr, in.dtype, j);
+          I i = base + v;
+          if (i >= n) { x.v[v] = T(0); continue; }
+          I i0 = i % d0, t = i / d0, i1 = t % d1, i2 = t / d1;
+          I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
+          x.v[v] = load_any<T>(in.ptr, in.dtype, j);
         }
       }
-      VM_REG_SWITCH(k, R, _Pragma("unroll") for (int v = 0; v < VM_V; ++v) R[v] = x[v]);
+      regs[k][threadIdx.x] = x;
     }
     // ---- execute
     for (int pc = 0; pc < p.n_instrs; ++pc) {
       const tcr_ew_instr& ins = p.ins[pc];
       const int op = ins.op;
-      T a[VM_V], b[VM_V], d[VM_V];
-      VM_REG_SWITCH(ins.a, R, _Pragma("unroll") for (int v = 0; v < VM_V; ++v) a[v] = R[v]);
-      VM_REG_SWITCH(ins.b, R, _Pragma("unroll") for (int v = 0; v < VM_V; ++v) b[v] = R[v]);
-      if (op == TCR_EW_CONST) {
-#pragma unroll
-        for (int v = 0; v < VM_V; ++v) d[v] = (T)ins.imm;
-      } else if (op == TCR_EW_MOV) {
-#pragma unroll
-        for (int v = 0; v < VM_V; ++v) d[v] = a[v];
-      } else if (op == TCR_EW_SELECT) {
-        T c[VM_V];
-        VM_REG_SWITCH(ins.c, R, _Pragma("unroll") for (int v = 0; v < VM_V; ++v) c[v] = R[v]);
-#pragma unroll
-        for (int v = 0; v < VM_V; ++v) d[v] = (a[v] != T(0)) ? b[v] : c[v];
-      } else if (op >= TCR_EW_POW) {
+      V4<T> a = regs[ins.a][threadIdx.x], d;
+      if (op >= TCR_EW_POW && op <= TCR_EW_GT) {
+        V4<T> b = regs[ins.b][threadIdx.x];
         switch (op) {
-#define VMB(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d[v] = Ops<T>::bin(OP, a[v], b[v]); break;
-          VMB(TCR_EW_POW) VMB(TCR_EW_ADD) VMB(TCR_EW_SUB) VMB(TCR_EW_MUL) VMB(TCR_EW_DIV) VMB(TCR_EW_MIN)
+#define VMB(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d.v[v] = Ops<T>::bin(OP, a.v[v], b.v[v]); break;
+          VMB(TCR_EW_ADD) VMB(TCR_EW_SUB) VMB(TCR_EW_MUL) VMB(TCR_EW_DIV) VMB(TCR_EW_POW) VMB(TCR_EW_MIN)
           VMB(TCR_EW_MAX) VMB(TCR_EW_EQ) VMB(TCR_EW_NEQ) VMB(TCR_EW_LT) VMB(TCR_EW_GT)
 #undef VMB
-          default:
-#pragma unroll
-            for (int v = 0; v < VM_V; ++v) d[v] = a[v];
+          default: d = a;
         }
+      } else if (op == TCR_EW_CONST) {
+#pragma unroll
+        for (int v = 0; v < VM_V; ++v) d.v[v] = (T)ins.imm;
+      } else if (op == TCR_EW_SELECT) {
+        V4<T> b = regs[ins.b][threadIdx.x], c = regs[ins.c][threadIdx.x];
+#pragma unroll
+        for (int v = 0; v < VM_V; ++v) d.v[v] = (a.v[v] != T(0)) ? b.v[v] : c.v[v];
       } else {
         switch (op) {
-#define VMU(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d[v] = Ops<T>::un(OP, a[v]); break;
-          VMU(TCR_EW_ABS) VMU(TCR_EW_NEG) VMU(TCR_EW_SIN) VMU(TCR_EW_COS) VMU(TCR_EW_TAN) VMU(TCR_EW_EXP)
-          VMU(TCR_EW_LOG) VMU(TCR_EW_SQRT) VMU(TCR_EW_ROUND) VMU(TCR_EW_SIGMOID) VMU(TCR_EW_TANH)
-          VMU(TCR_EW_SQUARE) VMU(TCR_EW_CUBE)
+#define VMU(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d.v[v] = Ops<T>::un(OP, a.v[v]); break;
+          VMU(TCR_EW_SIGMOID) VMU(TCR_EW_TANH) VMU(TCR_EW_EXP) VMU(TCR_EW_NEG) VMU(TCR_EW_SQUARE) VMU(TCR_EW_LOG)
+          VMU(TCR_EW_SQRT) VMU(TCR_EW_ABS) VMU(TCR_EW_SIN) VMU(TCR_EW_COS) VMU(TCR_EW_TAN) VMU(TCR_EW_ROUND)
+          VMU(TCR_EW_CUBE)
 #undef VMU
-          default:
-#pragma unroll
-            for (int v = 0; v < VM_V; ++v) d[v] = a[v];
+          default: d = a;  // MOV
         }
       }
-      VM_REG_SWITCH(ins.dst, R, _Pragma("unroll") for (int v = 0; v < VM_V; ++v) R[v] = d[v]);
+      regs[ins.dst][threadIdx.x] = d;
     }
     // ---- store outputs
     for (int k = 0; k < p.n_outputs; ++k) {
       const tcr_ew_output& o = p.out[k];
-      T y[VM_V];
-      VM_REG_SWITCH(o.reg, R, _Pragma("unroll") for (int v = 0; v < VM_V; ++v) y[v] = R[v]);
+      V4<T> y = regs[o.reg][threadIdx.x];
       if (ALIGNED && full && o.dtype == DTypeOf<T>::value) {
         T* dst = (T*)o.ptr + base;
-        if (sizeof(T) == 4) {
-          Vec<T> q;
-#pragma unroll
-          for (int v = 0; v < VM_V; ++v) q.v[v] = y[v];
-          st16(dst, q);
-        } else {
-          Vec<T> q0, q1;
-          q0.v[0] = y[0]; q0.v[1] = y[1]; q1.v[0] = y[2]; q1.v[1] = y[3];
-          st16(dst, q0);
-          st16(dst + 2, q1);
-        }
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(y.v);
+        if (sizeof(T) == 8) *reinterpret_cast<uint4*>(dst + 2) = *reinterpret_cast<const uint4*>(y.v + 2);
       } else {
 #pragma unroll
         for (int v = 0; v < VM_V; ++v)
-          if (base + v < n) store_any<T>(o.ptr, o.dtype, base + v, y[v]);
+          if (base + v < n) store_any<T>(o.ptr, o.dtype, base + v, y.v[v]);
       }
     }
   }
@@ -442,7 +433,8 @@ static int run_vm(const tcr_ew_program* prog) {
     bool all = (b0 || prog->dims[0] == 1) && (b1 || prog->dims[1] == 1) && (b2 || prog->dims[2] == 1);
     p.in[k].bcast[0] = b0; p.in[k].bcast[1] = b1; p.in[k].bcast[2] = b2;
     p.in[k].mode = (!b0 && !b1 && !b2) ? 0 : (all ? 1 : 2);
-    if (p.in[k].mode == 0 && !aligned16(in.ptr)) aligned = false;
+    if (p.in[k].mode == 2 && prog->dims[0] % VM_V == 0) p.in[k].mode = 3;
+    if ((p.in[k].mode == 0 || (p.in[k].mode == 3 && !b0)) && !aligned16(in.ptr)) aligned = false;
   }
   for (int k = 0; k < prog->n_outputs; ++k) {
     TCR_ARG(prog->outputs[k].ptr != nullptr, "tcr_elementwise: output %d is null", k);
@@ -459,9 +451,16 @@ static int run_vm(const tcr_ew_program* prog) {
     p.ins[k] = ins;
   }
   if (p.n == 0) return TCR_OK;
-  int grid = wave_grid(ceil_div(p.n, VM_V), 256, 4);
-  if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true>), grid, 256, 0, p);
-  else TCR_LAUNCH((ew_vm_kernel<T, false>), grid, 256, 0, p);
+  constexpr int THREADS = VmCfg<T>::THREADS;
+  int grid = wave_grid(ceil_div(p.n, VM_V), THREADS, sizeof(T) == 4 ? 6 : 6);
+  const bool small = p.n < (1ll << 31);
+  if (small) {
+    if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, uint32_t>), grid, THREADS, 0, p);
+    else TCR_LAUNCH((ew_vm_kernel<T, false, uint32_t>), grid, THREADS, 0, p);
+  } else {
+    if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, int64_t>), grid, THREADS, 0, p);
+    else TCR_LAUNCH((ew_vm_kernel<T, false, int64_t>), grid, THREADS, 0, p);
+  }
   TCR_CHECK_LAUNCH();
   return TCR_OK;
 }

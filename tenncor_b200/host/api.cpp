@@ -1,0 +1,652 @@
+// api.cpp — user API composites, initialisers, optimisers and trainers.
+// Each function cites the yaml block of the reference it restates.
+#include "api.hpp"
+
+#include <cmath>
+#include <random>
+
+#include "dp.hpp"
+
+namespace tenncor {
+
+using namespace teq;
+using namespace egen;
+using eteq::make_functor;
+using eteq::make_constant_like;
+using eteq::VarptrT;
+
+// ------------------------------------------------------------------ core.yml
+ETensor cast(const ETensor& input, _GENERATED_DTYPE dtype) {  // core.yml:94-118
+  marsh::Maps attrs;
+  eigen::pack_attr(attrs, dtype);
+  return eteq::make_tfuncattr(dtype, CAST, {input}, attrs);
+}
+ETensor assign(const VarptrT& t, const ETensor& s) { return make_functor(ASSIGN, {t, s}); }          // core.yml:119-128
+ETensor assign_add(const VarptrT& t, const ETensor& s) { return make_functor(ASSIGN_ADD, {t, s}); }  // :129-138
+ETensor assign_sub(const VarptrT& t, const ETensor& s) { return make_functor(ASSIGN_SUB, {t, s}); }  // :139-148
+ETensor assign_mul(const VarptrT& t, const ETensor& s) { return make_functor(ASSIGN_MUL, {t, s}); }  // :149-158
+ETensor assign_div(const VarptrT& t, const ETensor& s) { return make_functor(ASSIGN_DIV, {t, s}); }  // :159-170
+
+ETensor identity(const ETensor& input, const ETensorsT& execute_in_parallel) {  // core.yml:171-187
+  TensptrsT args = {input};
+  args.insert(args.end(), execute_in_parallel.begin(), execute_in_parallel.end());
+  return make_functor(IDENTITY, args);
+}
+
+ETensor unary(_GENERATED_OPCODE op, const ETensor& input) { return make_functor(op, {input}); }  // core.yml:188-278
+ETensor binary(_GENERATED_OPCODE op, const ETensor& a, const ETensor& b) { return make_functor(op, {a, b}); }  // :279-633
+ETensor binary(_GENERATED_OPCODE op, const ETensor& a, double scalar) { return make_functor(op, {a, make_constant_like(scalar, a)}); }
+ETensor binary(_GENERATED_OPCODE op, double scalar, const ETensor& b) { return make_functor(op, {make_constant_like(scalar, b), b}); }
+
+ETensor min(const ETensorsT& args) {  // core.yml:569-586
+  if (args.empty()) global::fatal("cannot min without arguments");
+  ETensor out = args[0];
+  for (size_t i = 1, n = args.size(); i < n; ++i) out = min(out, args[i]);
+  return out;
+}
+ETensor max(const ETensorsT& args) {  // core.yml:616-633
+  if (args.empty()) global::fatal("cannot max without arguments");
+  ETensor out = args[0];
+  for (size_t i = 1, n = args.size(); i < n; ++i) out = max(out, args[i]);
+  return out;
+}
+
+ETensor if_then_else(const ETensor& condition, const ETensor& then, const ETensor& otherwise) {  // core.yml:634-651
+  if (then.get() == otherwise.get()) return then;
+  return make_functor(SELECT, {condition, then, otherwise});
+}
+ETensor reverse(const ETensor& arg, const std::set<RankT>& dims) { return make_functor(REVERSE, {arg}, dims); }
+ETensor permute(const ETensor& arg, const RanksT& order) { return make_functor(PERMUTE, {arg}, order); }
+ETensor extend(const ETensor& arg, const DimsT& bcast) { return make_functor(EXTEND, {arg}, bcast); }
+ETensor extend(const ETensor& arg, RankT offset, const DimsT& xlist) {  // core.yml:679-693
+  DimsT bcast(offset, 1);
+  bcast.insert(bcast.end(), xlist.begin(), xlist.end());
+  return make_functor(EXTEND, {arg}, bcast);
+}
+ETensor extend_like(const ETensor& arg, const ETensor& like) { return make_functor(EXTEND, {arg}, like); }  // core.yml:714-723
+ETensor concat(const ETensor& left, const ETensor& right, RankT axis) { return make_functor(CONCAT, {left, right}, axis); }
+ETensor concat(const ETensorsT& args, RankT axis) { return make_functor(CONCAT, args, axis); }
+ETensor reshape(const ETensor& arg, Shape shape) { return make_functor(RESHAPE, {arg}, shape); }
+
+ETensor reduce(_GENERATED_OPCODE op, const ETensor& tens, std::set<RankT> dims) { return make_functor(op, {tens}, dims); }
+ETensor reduce(_GENERATED_OPCODE op, const ETensor& tens, RankT offset, RankT ndims) {  // core.yml:773-872
+  if (offset >= rank_cap) global::fatalf("cannot reduce dimensions [%d:]. Must be less than %d", (int)offset, (int)rank_cap);
+  RanksT dims(std::min(ndims, (RankT)(rank_cap - offset)));
+  std::iota(dims.begin(), dims.end(), offset);
+  return make_functor(op, {tens}, std::set<RankT>(dims.begin(), dims.end()));
+}
+ETensor reduce_1d(_GENERATED_OPCODE op, const ETensor& arg, RankT dimension) {  // core.yml:1007-1082
+  auto red = reduce(op, arg, dimension, 1);
+  RanksT indices(rank_cap);
+  auto bt = indices.begin();
+  auto it = bt + dimension;
+  std::iota(bt, it, 0);
+  std::iota(it, indices.end(), dimension + 1);
+  indices[rank_cap - 1] = dimension;
+  return permute(red, indices);
+}
+ETensor argmax(const ETensor& tens, RankT return_dim) { return make_functor(ARGMAX, {tens}, return_dim); }
+ETensor n_elems(const ETensor& arg) {  // core.yml:883-889: a scalar constant baked at build time
+  return eteq::make_constant_scalar((double)arg->shape().n_elems(), Shape(), (_GENERATED_DTYPE)arg->get_meta().type_code());
+}
+ETensor n_dims(const ETensor& arg, RankT rank) {
+  return eteq::make_constant_scalar((double)arg->shape().at(rank), Shape(), (_GENERATED_DTYPE)arg->get_meta().type_code());
+}
+ETensor slice(const ETensor& arg, eigen::PairVecT<DimT> extents) { return make_functor(SLICE, {arg}, extents); }
+ETensor slice(const ETensor& arg, DimT offset, DimT extent, RankT dimension) {  // core.yml:918-927
+  eigen::PairVecT<DimT> extents(std::max(rank_cap, dimension), {0, std::numeric_limits<DimT>::max()});
+  extents[dimension] = {offset, extent};
+  return slice(arg, extents);
+}
+ETensor pad(const ETensor& arg, eigen::PairVecT<DimT> paddings) { return make_functor(PAD, {arg}, paddings); }
+ETensor pad(const ETensor& arg, const DimPairsT& padding, RankT dimension) {  // core.yml:937-952
+  eigen::PairVecT<DimT> paddings(std::max(rank_cap, dimension), {0, 0});
+  paddings[dimension] = padding;
+  return pad(arg, paddings);
+}
+ETensor stride(const ETensor& arg, const DimsT& incrs) { return make_functor(STRIDE, {arg}, incrs); }
+ETensor scatter(const ETensor& arg, const Shape& outshape, const DimsT& incrs) { return make_functor(SCATTER, {arg}, outshape, incrs); }
+ETensor contract(const ETensor& a, const ETensor& b, eigen::PairVecT<RankT> dims) { return make_functor(CONTRACT, {a, b}, dims); }
+ETensor matmul(const ETensor& a, const ETensor& b) { return make_functor(MATMUL, {a, b}); }
+ETensor convolution(const ETensor& image, const ETensor& kernel, const RanksT& dims) { return make_functor(CONV, {image, kernel}, dims); }
+ETensor transpose(const ETensor& arg) { return permute(arg, {1, 0}); }
+ETensor reduce_mean(const ETensor& arg) { return div(reduce_sum(arg), n_elems(arg)); }  // core.yml:1090-1096
+ETensor reduce_mean_1d(const ETensor& arg, RankT dimension) {                            // core.yml:1097-1109
+  auto red = reduce_sum_1d(arg, dimension);
+  auto dim = make_constant_like((double)arg->shape().at(dimension), red);
+  return div(red, dim);
+}
+ETensor reduce_variance(const ETensor& arg) { return reduce_mean(square(sub(arg, extend_like(reduce_mean(arg), arg)))); }
+ETensor reduce_variance_1d(const ETensor& arg, RankT dimension) {
+  return reduce_mean_1d(square(sub(arg, extend_like(reduce_mean_1d(arg, dimension), arg))), dimension);
+}
+ETensor reduce_l2norm(const ETensor& arg, RankT offset, RankT ndims) { return sqrt(reduce_sum(square(arg), offset, ndims)); }
+ETensor reduce_l2norm_1d(const ETensor& arg, RankT dimension) { return sqrt(reduce_sum_1d(square(arg), dimension)); }
+ETensor clip_by_range(const ETensor& arg, double minval, double maxval) {  // core.yml:1147-1166
+  if (minval > maxval) global::fatal("min value is below max");
+  auto lo = make_constant_like(minval, arg), hi = make_constant_like(maxval, arg);
+  return max(min(arg, hi), lo);
+}
+ETensor clip_by_l2norm(const ETensor& arg, double upper) {  // core.yml:1167-1189
+  if (upper == 0) global::fatal("cannot clip_by_norm with a upper limit of 0");
+  auto norm = extend_like(reduce_l2norm(arg), arg);
+  auto limit = make_constant_like(upper, arg);
+  return if_then_else(lt(norm, limit), arg, div(mul(arg, limit), norm));
+}
+ETensor sum(const ETensorsT& args) {  // core.yml:1190-1211
+  switch (args.size()) {
+    case 0: global::fatal("cannot sum without arguments");
+    case 1: return args[0];
+    case 2: return add(args[0], args[1]);
+    default: break;
+  }
+  return make_functor(ADD, args);
+}
+ETensor prod(const ETensorsT& args) {  // core.yml:1212-1231
+  switch (args.size()) {
+    case 0: global::fatal("cannot prod without arguments");
+    case 1: return args[0];
+    default: break;
+  }
+  return make_functor(MUL, args);
+}
+ETensor softmax(const ETensor& arg, RankT offset, RankT ndims) {  // core.yml:1232-1260
+  if (offset + ndims > rank_cap) global::fatalf("cannot perform softmax on dimensions beyond %d", (int)rank_cap);
+  auto overflow_preventer = extend_like(reduce_max(arg, offset, ndims), arg);
+  auto exarg = exp(sub(arg, overflow_preventer));
+  return div(exarg, extend_like(add(reduce_sum(exarg, offset, ndims), (double)std::numeric_limits<float>::epsilon()), exarg));
+}
+ETensor relu(const ETensor& arg) { return max(arg, 0.0); }
+ETensor softplus(const ETensor& arg) { return log(add(1.0, exp(arg))); }
+ETensor sign(const ETensor& x) { return add(mul(-2.0, lt(x, 0.0)), 1.0); }
+
+// ------------------------------------------------------------------ random.yml
+namespace random {
+ETensor rand_unif(const ETensor& a, const ETensor& b) { return make_functor(RAND_UNIF, {a, b}); }
+ETensor rand_binom_one(const ETensor& arg) {  // random.yml:22-32
+  auto dtype = (_GENERATED_DTYPE)arg->get_meta().type_code();
+  auto trial = rand_unif(eteq::make_variable_scalar(0, arg->shape(), "0", dtype), eteq::make_variable_scalar(1, arg->shape(), "1", dtype));
+  return lt(trial, arg);
+}
+}  // namespace random
+
+// ------------------------------------------------------------------ init.yml
+static std::mt19937_64& host_rng() {
+  static std::mt19937_64 rng(0);
+  return rng;
+}
+
+void seed(uint64_t s) {
+  eteq::seed(s);
+  host_rng().seed(s);
+}
+
+static double fanio(Shape shape) {  // layr::fanio (tenncor/layr/init.hpp:24-29)
+  auto slist = narrow_shape(shape);
+  return (double)std::accumulate(slist.begin(), slist.end(), (DimT)0);
+}
+
+static VarptrT var_from(const std::vector<double>& vals, _GENERATED_DTYPE dtype, Shape shape, const std::string& label) {
+  std::vector<char> buf(vals.size() * type_size(dtype));
+  type_convert(buf.data(), dtype, vals.data(), DOUBLE, vals.size());
+  return eteq::make_variable(buf.data(), dtype, shape, label);
+}
+
+namespace init {
+layr::InitF random_normal(double mean, double stddev, _GENERATED_DTYPE dtype) {
+  return [=](Shape shape, std::string label) {
+    std::normal_distribution<double> dist(mean, stddev);
+    std::vector<double> vec(shape.n_elems());
+    for (auto& v : vec) v = dist(host_rng());
+    return var_from(vec, dtype, shape, label);
+  };
+}
+layr::InitF random_uniform(double minval, double maxval, _GENERATED_DTYPE dtype) {
+  return [=](Shape shape, std::string label) {
+    std::uniform_real_distribution<double> dist(minval, maxval);
+    std::vector<double> vec(shape.n_elems());
+    for (auto& v : vec) v = dist(host_rng());
+    return var_from(vec, dtype, shape, label);
+  };
+}
+layr::InitF constants(double value, _GENERATED_DTYPE dtype) {
+  return [=](Shape shape, std::string label) { return eteq::make_variable_scalar(value, shape, label, dtype); };
+}
+layr::InitF zeros(_GENERATED_DTYPE dtype) { return constants(0, dtype); }
+layr::InitF ones(_GENERATED_DTYPE dtype) { return constants(1, dtype); }
+layr::InitF xavier_uniform(double factor, _GENERATED_DTYPE dtype) {  // init.yml:147-169
+  return [=](Shape shape, std::string label) {
+    double bound = factor * std::sqrt(6. / fanio(shape));
+    std::uniform_real_distribution<double> dist(-bound, bound);
+    std::vector<double> vec(shape.n_elems());
+    for (auto& v : vec) v = dist(host_rng());
+    return var_from(vec, dtype, shape, label);
+  };
+}
+layr::InitF xavier_normal(double factor, _GENERATED_DTYPE dtype) {  // init.yml:115-136 (truncated at 2 sigma)
+  return [=](Shape shape, std::string label) {
+    double stdev = factor * std::sqrt(2. / fanio(shape));
+    std::normal_distribution<double> dist(0, stdev);
+    std::vector<double> vec(shape.n_elems());
+    for (auto& v : vec) {
+      v = dist(host_rng());
+      for (int retry = 0; std::abs(v) > 2 * stdev && retry < 5; ++retry) v = dist(host_rng());
+    }
+    return var_from(vec, dtype, shape, label);
+  };
+}
+}  // namespace init
+
+// ------------------------------------------------------------------ nn.yml
+namespace nn {
+ETensor fully_connect(const ETensorsT& lefts, const ETensorsT& rights, const ETensor& bias, eigen::PairVecT<RankT> dims) {  // nn.yml:14-47
+  size_t nlefts = lefts.size();
+  if (nlefts != rights.size())
+    global::fatalf("number of lefts (%d) must equal the number of rights (%d)", (int)nlefts, (int)rights.size());
+  auto out = contract(lefts[0], rights[0], dims);
+  for (size_t i = 1; i < nlefts; ++i) out = add(out, contract(lefts[i], rights[i], dims));
+  if (nullptr != bias) out = add(out, extend_like(bias, out));
+  return out;
+}
+
+ETensor conv2d(const ETensor& image, const ETensor& kernel, const ETensor& bias, const std::pair<DimPairsT, DimPairsT>& zp) {  // nn.yml:48-98
+  ETensor cimage = image;
+  if (zp.first.first > 0 || zp.first.second > 0 || zp.second.first > 0 || zp.second.second > 0)
+    cimage = pad(cimage, eigen::PairVecT<DimT>{{0, 0}, {zp.first.first, zp.first.second}, {zp.second.first, zp.second.second}});
+  DimT img_pad = kernel->shape().at(0) - 1;  // out
+  cimage = pad(cimage, DimPairsT{img_pad, img_pad}, 4);
+  auto out = permute(convolution(cimage, reverse(kernel, {0}), {4, 0, 1, 2}), {4, 1, 2, 3});
+  if (nullptr != bias) out = add(out, extend_like(bias, out));
+  return out;
+}
+
+ETensor dropout(const ETensor& input, const ETensor& drop_rate) {  // nn.yml:112-130
+  ETensor rate = sub(make_constant_like(1, drop_rate), drop_rate);
+  if (false == rate->shape().compatible_after(input->shape(), 0)) rate = extend_like(rate, input);
+  auto mask = random::rand_binom_one(rate);
+  auto denom = div(reduce_sum(mask), n_elems(mask));
+  return mul(input, div(mask, extend_like(denom, mask)));
+}
+}  // namespace nn
+
+// ------------------------------------------------------------------ layer.yml
+namespace layer {
+
+ETensor bind(layr::UnaryF unary, const Shape& inshape, _GENERATED_DTYPE dtype) {  // layer.yml:14-30
+  ETensor input = eteq::make_variable_scalar(0, inshape, layr::input_label, dtype);
+  auto output = unary(input);
+  return layr::make_layer(identity(output), layr::bind_name, input);
+}
+
+ETensor link(ETensorsT layers, ETensor input) {  // layer.yml:31-67
+  if (layers.empty()) global::fatal("cannot link without layers");
+  ETensor output = input;
+  if (nullptr == input) {
+    output = layers.front();
+    input = layr::get_input(output);
+    layers = ETensorsT(layers.begin() + 1, layers.end());
+  }
+  for (auto& layer : layers) {
+    if (layr::get_input(layer).get() == output.get()) output = layer;
+    else output = layr::connect(layer, output);
+  }
+  return layr::make_layer(identity(output), layr::link_name, input);
+}
+
+ETensor dense(const ETensor& input, const ETensor& kernel, const ETensor& bias, eigen::PairVecT<RankT> dims) {  // layer.yml:636-656
+  auto output = nn::fully_connect({input}, {kernel}, bias, dims);
+  return layr::make_layer(identity(output), layr::dense_name, input);
+}
+
+ETensor dense(const ETensor& input, const DimsT& hidden_dims, layr::InitF kernel_init, layr::InitF bias_init, bool with_bias,
+              const eigen::PairVecT<RankT>& dims) {  // layer.yml:89-129
+  auto dtype = (_GENERATED_DTYPE)input->get_meta().type_code();
+  if (!kernel_init) kernel_init = init::glorot_uniform(1, dtype);
+  VarptrT kernel = kernel_init(layr::gen_rshape(hidden_dims, input->shape(), dims), layr::weight_label);
+  VarptrT bias;
+  if (with_bias) {
+    if (!bias_init) bias_init = init::zeros(dtype);
+    bias = bias_init(Shape(hidden_dims), layr::bias_label);
+  }
+  return dense(input, kernel, bias, dims);
+}
+
+ETensor dense(const Shape& inshape, const DimsT& hidden_dims, layr::InitF kernel_init, layr::InitF bias_init, bool with_bias,
+              const eigen::PairVecT<RankT>& dims, _GENERATED_DTYPE dtype) {  // layer.yml:68-88
+  ETensor input = eteq::make_variable_scalar(0, inshape, layr::input_label, dtype);
+  return dense(input, hidden_dims, kernel_init, bias_init, with_bias, dims);
+}
+
+ETensor conv2d(const ETensor& input, const ETensor& kernel, const ETensor& bias, const std::pair<DimPairsT, DimPairsT>& zero_padding) {  // layer.yml:657-677
+  auto output = nn::conv2d(input, kernel, bias, zero_padding);
+  return layr::make_layer(identity(output), layr::conv_name, input);
+}
+
+ETensor conv2d(const DimPairsT& kernel_hw, DimT in_ncol, DimT out_ncol, layr::InitF kernel_init, layr::InitF bias_init,
+               const std::pair<DimPairsT, DimPairsT>& zero_padding, bool with_bias, _GENERATED_DTYPE dtype) {  // layer.yml:130-160,215-253
+  ETensor input = eteq::make_variable_scalar(0, Shape({in_ncol, kernel_hw.second, kernel_hw.first, 1}), layr::input_label, dtype);
+  if (!kernel_init) kernel_init = init::glorot_uniform(1, dtype);
+  VarptrT kernel = kernel_init(Shape({out_ncol, input->shape().at(0), kernel_hw.second, kernel_hw.first}), layr::weight_label);
+  VarptrT bias;
+  if (with_bias) {
+    if (!bias_init) bias_init = init::zeros(dtype);
+    bias = bias_init(Shape({out_ncol}), layr::bias_label);
+  }
+  return conv2d(input, kernel, bias, zero_padding);
+}
+
+static void check_seq_dim(RankT seq_dim) {
+  if (seq_dim == 0) global::fatal("spliting input across 0th dimension... dense connection will not match");
+}
+
+ETensor rnn(const ETensor& input, const ETensor& init_state, const ETensor& cell, const layr::UnaryF& activation, RankT seq_dim) {  // layer.yml:678-715
+  DimT nseq = input->shape().at(seq_dim);
+  check_seq_dim(seq_dim);
+  ETensor state = init_state;
+  ETensorsT states;
+  for (DimT i = 0; i < nseq; ++i) {
+    ETensor inslice = slice(input, i, 1, seq_dim);
+    state = activation(layr::connect(cell, concat(inslice, state, 0)));
+    states.push_back(state);
+  }
+  auto output = concat(states, seq_dim);
+  return layr::make_layer(identity(output), layr::rnn_name, input);
+}
+
+ETensor rnn(DimT indim, DimT hidden_dim, const layr::UnaryF& activation, DimT nseq, layr::InitF kernel_init, layr::InitF bias_init,
+            RankT seq_dim, bool with_bias, _GENERATED_DTYPE dtype) {  // layer.yml:254-297
+  DimsT inslist(rank_cap, 1);
+  inslist[0] = indim;
+  inslist[seq_dim] = nseq;
+  ETensor input = eteq::make_variable_scalar(0, Shape(inslist), layr::input_label, dtype);
+  auto cell = dense(Shape({(DimT)(hidden_dim + indim)}), {hidden_dim}, kernel_init, bias_init, with_bias, {{0, 1}}, dtype);
+  auto init_state = eteq::make_variable_scalar(0, Shape({hidden_dim}), "init_state", dtype);
+  ETensor state = extend_like(init_state, slice(input, 0, 1, seq_dim));
+  return rnn(input, state, cell, activation, seq_dim);
+}
+
+ETensor lstm(const ETensor& input, const ETensor& init_state, const ETensor& init_hidden, const ETensor& ggate, const ETensor& forgate,
+             const ETensor& ingate, const ETensor& outgate, RankT seq_dim) {  // layer.yml:716-768
+  DimT nseq = input->shape().at(seq_dim);
+  check_seq_dim(seq_dim);
+  ETensor state = init_state, hidden = init_hidden;
+  ETensorsT states;
+  for (DimT i = 0; i < nseq; ++i) {
+    ETensor inslice = slice(input, i, 1, seq_dim);
+    ETensor xc = concat(inslice, hidden, 0);
+    auto gate = tanh(layr::connect(ggate, xc));
+    auto in = sigmoid(layr::connect(ingate, xc));
+    auto forget = sigmoid(layr::connect(forgate, xc));
+    auto output = sigmoid(layr::connect(outgate, xc));
+    state = add(mul(gate, in), mul(state, forget));
+    hidden = mul(state, output);
+    states.push_back(hidden);
+  }
+  auto output = concat(states, seq_dim);
+  return layr::make_layer(identity(output), layr::lstm_name, input);
+}
+
+ETensor lstm(const Shape& inshape, DimT hidden_dim, DimT nseq, layr::InitF kernel_init, layr::InitF bias_init, RankT seq_dim, bool with_bias,
+             _GENERATED_DTYPE dtype) {  // layer.yml:298-345
+  DimsT inslist(inshape.begin(), inshape.end());
+  inslist[seq_dim] = nseq;
+  ETensor input = eteq::make_variable_scalar(0, Shape(inslist), layr::input_label, dtype);
+  DimsT inputlist(inshape.begin(), inshape.end()), statelist(inshape.begin(), inshape.end());
+  inputlist[0] += hidden_dim;
+  statelist[0] = hidden_dim;
+  inputlist[seq_dim] = statelist[seq_dim] = 1;
+  Shape inputshape(inputlist), stateshape(statelist);
+  DimsT hid_dims = {hidden_dim};
+  auto ggate = dense(inputshape, hid_dims, kernel_init, bias_init, with_bias, {{0, 1}}, dtype);
+  auto forgate = dense(inputshape, hid_dims, kernel_init, bias_init, with_bias, {{0, 1}}, dtype);
+  auto ingate = dense(inputshape, hid_dims, kernel_init, bias_init, with_bias, {{0, 1}}, dtype);
+  auto outgate = dense(inputshape, hid_dims, kernel_init, bias_init, with_bias, {{0, 1}}, dtype);
+  auto state = eteq::make_constant_scalar(0, stateshape, dtype);
+  auto hidden = eteq::make_constant_scalar(0, stateshape, dtype);
+  return lstm(input, state, hidden, ggate, forgate, ingate, outgate, seq_dim);
+}
+
+ETensor gru(const ETensor& input, const ETensor& init_state, const ETensor& ugate, const ETensor& rgate, const ETensor& hgate, RankT seq_dim) {  // layer.yml:769-813
+  DimT nseq = input->shape().at(seq_dim);
+  check_seq_dim(seq_dim);
+  ETensor state = init_state;
+  ETensorsT states;
+  for (DimT i = 0; i < nseq; ++i) {
+    ETensor inslice = slice(input, i, 1, seq_dim);
+    ETensor xc = concat(inslice, state, 0);
+    auto update = sigmoid(layr::connect(ugate, xc));
+    auto reset = sigmoid(layr::connect(rgate, xc));
+    auto hidden = tanh(layr::connect(hgate, concat(inslice, mul(reset, state), 0)));
+    state = add(mul(update, state), mul(sub(1.0, update), hidden));
+    states.push_back(state);
+  }
+  auto output = concat(states, seq_dim);
+  return layr::make_layer(identity(output), layr::gru_name, input);
+}
+
+ETensor gru(const Shape& inshape, DimT hidden_dim, DimT nseq, layr::InitF kernel_init, layr::InitF bias_init, RankT seq_dim, bool with_bias,
+            _GENERATED_DTYPE dtype) {  // layer.yml:346-390
+  DimsT inslist(inshape.begin(), inshape.end());
+  inslist[seq_dim] = nseq;
+  ETensor input = eteq::make_variable_scalar(0, Shape(inslist), layr::input_label, dtype);
+  DimsT inputlist(inshape.begin(), inshape.end()), statelist(inshape.begin(), inshape.end());
+  inputlist[0] += hidden_dim;
+  statelist[0] = hidden_dim;
+  inputlist[seq_dim] = statelist[seq_dim] = 1;
+  Shape inputshape(inputlist), stateshape(statelist);
+  DimsT hid_dims = {hidden_dim};
+  auto ugate = dense(inputshape, hid_dims, kernel_init, bias_init, with_bias, {{0, 1}}, dtype);
+  auto rgate = dense(inputshape, hid_dims, kernel_init, bias_init, with_bias, {{0, 1}}, dtype);
+  auto hgate = dense(inputshape, hid_dims, kernel_init, bias_init, with_bias, {{0, 1}}, dtype);
+  auto state = eteq::make_constant_scalar(0, stateshape, dtype);
+  return gru(input, state, ugate, rgate, hgate, seq_dim);
+}
+
+layr::RBMLayer rbm(DimT nvisible, DimT nhidden, layr::InitF kernel_init, layr::InitF bias_init, bool with_bias, _GENERATED_DTYPE dtype) {  // layer.yml:391-430
+  if (!kernel_init) kernel_init = init::glorot_uniform(1, dtype);
+  ETensor fwdinput = eteq::make_variable_scalar(0, Shape({nvisible}), layr::input_label, dtype);
+  ETensor bwdinput = eteq::make_variable_scalar(0, Shape({nhidden}), layr::input_label, dtype);
+  VarptrT kernel = kernel_init(Shape({nhidden, nvisible}), layr::weight_label);
+  VarptrT hbias, vbias;
+  if (with_bias) {
+    if (!bias_init) bias_init = init::zeros(dtype);
+    hbias = bias_init(Shape({nhidden}), "h" + layr::bias_label);
+    vbias = bias_init(Shape({nvisible}), "v" + layr::bias_label);
+  }
+  return layr::RBMLayer{dense(fwdinput, kernel, hbias, {{0, 1}}), dense(bwdinput, transpose(kernel), vbias, {{0, 1}})};
+}
+
+}  // namespace layer
+
+// ------------------------------------------------------------------ loss.yml
+namespace loss {
+ETensor sqr_diff(const ETensor& target, const ETensor& input) { return square(sub(target, input)); }
+ETensor mean_squared(const ETensor& target, const ETensor& input, RankT axis) {  // loss.yml:21-39
+  auto sd = square(sub(target, input));
+  if (axis >= rank_cap) return reduce_mean(sd);
+  return reduce_mean_1d(sd, axis);
+}
+ETensor cross_entropy(const ETensor& target, const ETensor& input, float eps) {  // loss.yml:40-59
+  auto in = add(input, (double)eps);
+  auto not_in = sub(1.0, in);
+  auto not_targ = sub(1.0, target);
+  return neg(add(mul(target, log(in)), mul(not_targ, log(not_in))));
+}
+}  // namespace loss
+
+ETensorsT derive(const ETensor& root, const ETensorsT& targets) {
+  return dp::wrap_gradients(eteq::derive(root, targets));
+}
+
+// ------------------------------------------------------------------ approx.yml
+namespace approx {
+
+static ETensorsT ders_of(const ETensor& error, const eteq::VarptrsT& variables) {
+  return tenncor::derive(error, ETensorsT(variables.begin(), variables.end()));
+}
+
+static _GENERATED_DTYPE dtype_of(const ETensor& t) { return (_GENERATED_DTYPE)t->get_meta().type_code(); }
+
+layr::VarErrsT sgd(const ETensor& error, const eteq::VarptrsT& variables, double learning_rate, layr::UnaryF apply) {  // approx.yml:12-55
+  layr::VarErrsT out;
+  auto ders = ders_of(error, variables);
+  for (size_t i = 0, n = variables.size(); i < n; ++i) {
+    auto der = ders[i];
+    if (apply) der = apply(der);
+    out.push_back({variables[i], assign_sub(variables[i], mul(der, learning_rate))});
+  }
+  return out;
+}
+
+layr::VarErrsT adagrad(const ETensor& error, const eteq::VarptrsT& variables, double learning_rate, double epsilon, layr::UnaryF apply) {  // approx.yml:56-95
+  layr::VarErrsT out;
+  auto ders = ders_of(error, variables);
+  for (size_t i = 0, n = variables.size(); i < n; ++i) {
+    auto der = ders[i];
+    if (apply) der = apply(der);
+    VarptrT momentum = eteq::make_variable_scalar(1, der->shape(), "momentum", dtype_of(der));
+    auto update = assign_add(momentum, square(der));
+    // assign momentums before leaves
+    out.push_back({variables[i], assign_sub(variables[i], div(mul(der, learning_rate), add(sqrt(update), epsilon)))});
+  }
+  return out;
+}
+
+layr::VarErrsT adam(const ETensor& error, const eteq::VarptrsT& variables, double step_rate, double decay1, double decay2, double epsilon) {  // approx.yml:96-170
+  double nodecay1 = 1. - decay1, nodecay2 = 1. - decay2;
+  layr::VarErrsT out;
+  auto ders = ders_of(error, variables);
+  for (size_t i = 0, n = variables.size(); i < n; ++i) {
+    auto der = ders[i];
+    auto dt = dtype_of(der);
+    auto m = eteq::make_variable_scalar(0, der->shape(), "moment1", dt);
+    auto v = eteq::make_variable_scalar(0, der->shape(), "moment2", dt);
+    auto t = eteq::make_variable_scalar(0, der->shape(), "t", dt);
+    auto one_t = make_constant_like(1, der);
+    auto next_m = assign(m, add(mul(decay1, ETensor(m)), mul(nodecay1, der)));
+    auto next_v = assign(v, add(mul(decay2, ETensor(v)), mul(nodecay2, square(der))));
+    auto incr = assign_add(t, one_t);
+    auto m_corr = div(next_m, sub(one_t, pow(decay1, incr)));
+    auto v_corr = div(next_v, sub(one_t, pow(decay2, incr)));
+    auto delta = mul(step_rate, div(m_corr, add(sqrt(v_corr), epsilon)));
+    out.push_back({variables[i], assign_sub(variables[i], delta)});
+  }
+  return out;
+}
+
+layr::VarErrsT adadelta(const ETensor& error, const eteq::VarptrsT& variables, double step_rate, double decay, double offset, double epsilon,
+                        layr::UnaryF apply) {  // approx.yml:171-245
+  layr::VarErrsT out;
+  auto ders = ders_of(error, variables);
+  for (size_t i = 0, n = variables.size(); i < n; ++i) {
+    auto der = ders[i];
+    if (apply) der = apply(der);
+    double nodecay = 1. - decay;
+    auto dt = dtype_of(der);
+    VarptrT msg = eteq::make_variable_scalar(0, der->shape(), "ex_sqr_grad", dt);
+    VarptrT msd = eteq::make_variable_scalar(0, der->shape(), "ex_sqr_delx", dt);
+    auto msg_next = assign(msg, add(mul(decay, ETensor(msg)), mul(nodecay, square(der))));
+    auto delta = mul(mul(step_rate, div(sqrt(add(ETensor(msd), offset)), add(sqrt(add(msg_next, offset)), epsilon))), der);
+    auto msd_next = assign(msd, add(mul(decay, ETensor(msd)), mul(nodecay, square(delta))));
+    out.push_back({variables[i], assign_sub(variables[i], identity(delta, {msd_next}))});
+  }
+  return out;
+}
+
+layr::VarErrsT rms_momentum(const ETensor& error, const eteq::VarptrsT& variables, double learning_rate, double discount_factor,
+                            double epsilon, layr::UnaryF apply) {  // approx.yml:246-322
+  layr::VarErrsT out;
+  auto ders = ders_of(error, variables);
+  for (size_t i = 0, n = variables.size(); i < n; ++i) {
+    auto der = ders[i];
+    if (apply) der = apply(der);
+    VarptrT momentum = eteq::make_variable_scalar(1, der->shape(), "momentum", dtype_of(der));
+    auto update = assign(momentum, add(mul(discount_factor, ETensor(momentum)), mul(1 - discount_factor, square(der))));
+    // assign momentums before leaves
+    out.push_back({variables[i], assign_sub(variables[i], div(mul(der, learning_rate), add(sqrt(update), epsilon)))});
+  }
+  return out;
+}
+
+}  // namespace approx
+
+}  // namespace tenncor
+
+// ======================================================================== trainer
+namespace trainer {
+
+using namespace tenncor;
+
+layr::ETensor apply_update(const layr::ETensorsT& models, layr::ApproxF update, layr::ErrorF err_func) {
+  auto error = err_func(models);
+  eteq::VarptrsT vars;
+  for (auto& model : models) {
+    auto temp_vars = layr::get_storage(model);
+    vars.insert(vars.end(), temp_vars.begin(), temp_vars.end());
+  }
+  auto updates = update(error, vars);
+  teq::OwnMapT umap;
+  layr::ETensorsT deps;
+  deps.reserve(updates.size());
+  for (auto& u : updates) {
+    umap.emplace(u.first.get(), u.second);
+    deps.push_back(u.second);
+  }
+  // depend on assigns for variables not trailed in error
+  return identity(layr::trail(error, umap), deps);
+}
+
+layr::ETensor sample_v2h(const layr::RBMLayer& model, layr::ETensor vis) { return random::rand_binom_one(sigmoid(model.connect(vis))); }
+layr::ETensor sample_h2v(const layr::RBMLayer& model, layr::ETensor hid) { return random::rand_binom_one(sigmoid(model.backward_connect(hid))); }
+layr::ETensor gibbs_hvh(const layr::RBMLayer& model, layr::ETensor hid) { return sample_v2h(model, sample_h2v(model, hid)); }
+
+layr::VarErrsT bbernoulli_approx(const layr::VarErrsT& assocs, double learning_rate, double discount_factor) {  // rbm.hpp:42-63
+  layr::VarErrsT assigns;
+  for (const auto& verrs : assocs) {
+    auto err = verrs.second;
+    auto slist = teq::narrow_shape(err->shape());
+    teq::DimT shape_factor = slist.empty() ? 1 : slist.back();
+    auto momentum = eteq::make_variable_scalar(0, err->shape(), "momentum", (egen::_GENERATED_DTYPE)err->get_meta().type_code());
+    auto momentum_next = add(mul(discount_factor, layr::ETensor(momentum)), mul(learning_rate * (1 - discount_factor) / shape_factor, err));
+    assigns.push_back({verrs.first, assign_add(verrs.first, assign(momentum, momentum_next))});
+  }
+  return assigns;
+}
+
+layr::ETensor rbm(const layr::RBMLayer& model, layr::ETensor visible, double learning_rate, double discount_factor, BErrorF err_func, size_t cdk) {  // rbm.hpp:85-165
+  if (nullptr == visible) global::fatal("cannot call cd_grad_approx with null visible");
+  if (!err_func) err_func = [](const layr::ETensor& a, const layr::ETensor& b) { return loss::mean_squared(a, b); };
+  layr::ETensor hidden = sample_v2h(model, visible);
+  layr::ETensor chain_it = hidden;
+  for (size_t i = 0; i + 1 < cdk; ++i) chain_it = gibbs_hvh(model, chain_it);
+  auto visible_mean = sigmoid(model.backward_connect(chain_it));
+  auto hidden_mean = sigmoid(model.connect(visible_mean));
+
+  std::map<std::string, eteq::VarptrT> vars;
+  for (auto& var : layr::get_storage(model.fwd_)) vars.emplace(var->to_string(), var);
+  for (auto& var : layr::get_storage(model.bwd_)) vars.emplace(var->to_string(), var);
+
+  // the exchanged "errors" of a data-parallel RBM are the CD statistics
+  auto grad_w = sub(matmul(transpose(visible), hidden), matmul(transpose(visible_mean), hidden_mean));
+  layr::ETensorsT errs = {grad_w};
+  std::vector<eteq::VarptrT> targets = {vars.at(layr::weight_label)};
+  std::string hid_key = "h" + layr::bias_label, vis_key = "v" + layr::bias_label;
+  if (vars.count(hid_key)) {
+    errs.push_back(reduce_mean_1d(sub(hidden, hidden_mean), 1));
+    targets.push_back(vars.at(hid_key));
+  }
+  if (vars.count(vis_key)) {
+    errs.push_back(reduce_mean_1d(sub(visible, visible_mean), 1));
+    targets.push_back(vars.at(vis_key));
+  }
+  errs = dp::wrap_gradients(errs);
+  layr::VarErrsT varerrs;
+  for (size_t i = 0; i < errs.size(); ++i) varerrs.push_back({targets[i], errs[i]});
+  auto updates = bbernoulli_approx(varerrs, learning_rate, discount_factor);
+  teq::OwnMapT umap;
+  for (auto& u : updates) umap.emplace(u.first.get(), u.second);
+  layr::ETensor error = err_func(visible, visible_mean);
+  return layr::trail(error, umap);
+}
+
+}  // namespace trainer

@@ -1,0 +1,502 @@
+// pymod.cpp — pybind11 module `_tenncor`: the python surface of the reference's `tenncor`
+// module (tenncor/python/eteq_ext.cpp:20-522, layr_ext.cpp, generated pyapi_tenncor.cpp)
+// over the B200 back end. numpy shapes are REVERSED into teq shapes exactly like the
+// reference (tenncor/pyutils/src/convert.cpp:8-37).
+#include <pybind11/functional.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "api.hpp"
+#include "dp.hpp"
+#include "planner.hpp"
+
+namespace py = pybind11;
+using namespace teq;
+using layr::ETensor;
+using layr::ETensorsT;
+
+static DimsT c2pshape(const Shape& cshape) {
+  DimsT fwd = narrow_shape(cshape);
+  return DimsT(fwd.rbegin(), fwd.rend());
+}
+
+static Shape p2cshape(const std::vector<size_t>& pyshape) {
+  DimsT slist(pyshape.rbegin(), pyshape.rend());
+  return Shape(slist);
+}
+
+static egen::_GENERATED_DTYPE np2dtype(const py::dtype& dt) {
+  if (dt.is(py::dtype::of<double>())) return egen::DOUBLE;
+  if (dt.is(py::dtype::of<float>())) return egen::FLOAT;
+  if (dt.is(py::dtype::of<int8_t>())) return egen::INT8;
+  if (dt.is(py::dtype::of<uint8_t>())) return egen::UINT8;
+  if (dt.is(py::dtype::of<int16_t>())) return egen::INT16;
+  if (dt.is(py::dtype::of<uint16_t>())) return egen::UINT16;
+  if (dt.is(py::dtype::of<int32_t>())) return egen::INT32;
+  if (dt.is(py::dtype::of<uint32_t>())) return egen::UINT32;
+  if (dt.is(py::dtype::of<int64_t>())) return egen::INT64;
+  if (dt.is(py::dtype::of<uint64_t>())) return egen::UINT64;
+  return egen::BAD_TYPE;
+}
+
+static py::dtype dtype2np(egen::_GENERATED_DTYPE t) {
+  switch (t) {
+    case egen::DOUBLE: return py::dtype::of<double>();
+    case egen::FLOAT: return py::dtype::of<float>();
+    case egen::INT8: return py::dtype::of<int8_t>();
+    case egen::UINT8: return py::dtype::of<uint8_t>();
+    case egen::INT16: return py::dtype::of<int16_t>();
+    case egen::UINT16: return py::dtype::of<uint16_t>();
+    case egen::INT32: return py::dtype::of<int32_t>();
+    case egen::UINT32: return py::dtype::of<uint32_t>();
+    case egen::INT64: return py::dtype::of<int64_t>();
+    case egen::UINT64: return py::dtype::of<uint64_t>();
+    default: global::fatal("bad dtype");
+  }
+}
+
+static egen::_GENERATED_DTYPE parse_dtype(const py::object& o) {
+  if (o.is_none()) return egen::default_dtype;
+  if (py::isinstance<py::str>(o)) {
+    std::string s = o.cast<std::string>();
+    auto t = egen::get_type(s);
+    if (t != egen::BAD_TYPE) return t;
+  }
+  auto t = np2dtype(py::dtype::from_args(o));
+  if (t == egen::BAD_TYPE) global::fatal("unsupported dtype");
+  return t;
+}
+
+/// numpy array -> (contiguous array of a supported dtype, teq shape); unsupported dtypes become FLOAT (PybindT)
+static py::array normalise(py::array data, Shape& shape, egen::_GENERATED_DTYPE& dtype) {
+  dtype = np2dtype(data.dtype());
+  if (dtype == egen::BAD_TYPE) {
+    data = py::array_t<float, py::array::c_style | py::array::forcecast>(data);
+    dtype = egen::FLOAT;
+  }
+  data = py::array::ensure(data, py::array::c_style);
+  std::vector<size_t> ps(data.shape(), data.shape() + data.ndim());
+  shape = p2cshape(ps);
+  return data;
+}
+
+static py::array to_array(iTensor& tens) {
+  auto dtype = (egen::_GENERATED_DTYPE)tens.get_meta().type_code();
+  const void* host = tens.device().data();
+  if (nullptr == host) global::fatalf("%s has no data: evaluate it first", tens.to_string().c_str());
+  DimsT ps = c2pshape(tens.shape());
+  std::vector<py::ssize_t> pshape(ps.begin(), ps.end());
+  py::array out(dtype2np(dtype), pshape);
+  std::memcpy(out.mutable_data(), host, tens.shape().n_elems() * egen::type_size(dtype));
+  return out;
+}
+
+static TensSetT to_set(const ETensorsT& ts) {
+  TensSetT out;
+  for (auto& t : ts) out.emplace(t.get());
+  return out;
+}
+
+static py::object attr_to_py(const marsh::iObject* obj) {
+  if (auto a = dynamic_cast<const marsh::IntArray*>(obj)) return py::cast(a->vals_);
+  if (auto a = dynamic_cast<const marsh::PairArray*>(obj)) return py::cast(a->vals_);
+  if (auto a = dynamic_cast<const marsh::Integer*>(obj)) return py::cast(a->val_);
+  if (auto a = dynamic_cast<const marsh::Float*>(obj)) return py::cast(a->val_);
+  if (auto a = dynamic_cast<const marsh::String*>(obj)) return py::cast(a->val_);
+  return py::none();
+}
+
+/// post-order description of the graph under `targets`, in the exact order the reference
+/// evaluator visits it; leaves carry a copy of their current data. Consumed by the CPU
+/// oracle (tests only) and by debugging tools — the analogue of the reference's dbg print.
+static py::list dump_graph(const ETensorsT& targets) {
+  py::list out;
+  std::unordered_map<iTensor*, size_t> ids;
+  std::function<void(const TensptrT&)> visit = [&](const TensptrT& t) {
+    if (ids.count(t.get())) return;
+    py::dict node;
+    if (auto f = dynamic_cast<iFunctor*>(t.get())) {
+      py::list args;
+      for (auto& a : f->args_ref()) {
+        visit(a);
+        args.append(ids.at(a.get()));
+      }
+      node["kind"] = "func";
+      node["op"] = f->get_opcode().name_;
+      node["args"] = args;
+      py::dict attrs;
+      for (auto& name : f->ls_attrs()) {
+        auto obj = f->get_attr(name);
+        if (auto ref = dynamic_cast<const TensorRef*>(obj)) {
+          if (name == eigen::tensor_key) {
+            Shape s = ref->get_tensor()->shape();
+            attrs["tensor_shape"] = std::vector<int64_t>(s.begin(), s.end());
+          }
+          continue;
+        }
+        attrs[py::str(name)] = attr_to_py(obj);
+      }
+      node["attrs"] = attrs;
+    } else {
+      auto leaf = static_cast<iLeaf*>(t.get());
+      node["kind"] = "leaf";
+      node["usage"] = (int)leaf->get_usage();
+      node["label"] = t->to_string();
+      node["data"] = to_array(*t).attr("reshape")(-1);
+    }
+    Shape s = t->shape();
+    node["id"] = ids.size();
+    node["shape"] = std::vector<int64_t>(s.begin(), s.end());
+    node["dtype"] = (int)t->get_meta().type_code();
+    ids.emplace(t.get(), ids.size());
+    out.append(node);
+  };
+  for (auto& t : targets) visit(t);
+  return out;
+}
+
+struct InitHolder {
+  layr::InitF f;
+};
+
+static eteq::VarptrT as_var(const ETensor& t) {
+  auto v = std::dynamic_pointer_cast<eteq::Variable>(t);
+  if (nullptr == v) global::fatalf("%s is not a variable", t->to_string().c_str());
+  return v;
+}
+
+#define UN(NAME, OP) api.def(NAME, [](const ETensor& x) { return tenncor::unary(egen::OP, x); }, py::arg("input"))
+#define BIN(NAME, OP)                                                                                               \
+  api.def(NAME, [](const ETensor& a, const ETensor& b) { return tenncor::binary(egen::OP, a, b); });                \
+  api.def(NAME, [](const ETensor& a, double b) { return tenncor::binary(egen::OP, a, b); });                        \
+  api.def(NAME, [](double a, const ETensor& b) { return tenncor::binary(egen::OP, a, b); })
+
+PYBIND11_MODULE(_tenncor, m) {
+  m.doc() = "tenncor_b200 host module: TEQ functor graphs evaluated on B200 (sm_100a)";
+  py::register_exception<global::FatalError>(m, "FatalError", PyExc_RuntimeError);
+
+  py::class_<iTensor, TensptrT> etens(m, "ETensor");
+  etens.def("__str__", [](const iTensor& self) { return self.to_string(); })
+      .def("__hash__", [](const iTensor& self) { return (size_t)&self; })
+      .def("__eq__", [](const iTensor& self, py::object other) {
+        return py::isinstance<iTensor>(other) && other.cast<iTensor*>() == &self;
+      })
+      .def("shape", [](const iTensor& self) {
+        DimsT ps = c2pshape(self.shape());
+        return std::vector<size_t>(ps.begin(), ps.end());
+      }, "Return this instance's (numpy-ordered) shape")
+      .def("teq_shape", [](const iTensor& self) { Shape s = self.shape(); return std::vector<size_t>(s.begin(), s.end()); })
+      .def("dtype", [](const iTensor& self) { return dtype2np((egen::_GENERATED_DTYPE)self.get_meta().type_code()); })
+      .def("data", [](iTensor& self) { return to_array(self); }, "Host copy of the current data (D2H sync point)")
+      .def("get", [](TensptrT self, ETensorsT ignored, size_t max_version) {
+        eteq::run({self}, to_set(ignored), max_version);
+        return to_array(*self);
+      }, py::arg("ignored") = ETensorsT{}, py::arg("max_version") = std::numeric_limits<size_t>::max(),
+      "Evaluate on the device and return the result as a numpy array")
+      .def("calc", [](TensptrT self, ETensorsT ignored, size_t max_version) {
+        eteq::run({self}, to_set(ignored), max_version);
+      }, py::arg("ignored") = ETensorsT{}, py::arg("max_version") = std::numeric_limits<size_t>::max(),
+      "Evaluate on the device; the result stays in HBM (no host copy)")
+      .def("device_ptr", [](iTensor& self) { return (uintptr_t)self.device().device_data(); })
+      .def("get_version", [](const iTensor& self) { return self.get_meta().state_version(); })
+      .def("opname", [](const iTensor& self) {
+        auto f = dynamic_cast<const iFunctor*>(&self);
+        return f ? f->get_opcode().name_ : std::string();
+      })
+      .def("args", [](const iTensor& self) {
+        auto f = dynamic_cast<const iFunctor*>(&self);
+        return f ? f->get_args() : TensptrsT{};
+      })
+      .def("get_input", [](TensptrT self) { return layr::get_input(self); })
+      .def("connect", [](TensptrT self, const ETensor& input) { return layr::connect(self, input); })
+      .def("deep_clone", [](TensptrT self) { return layr::deep_clone(self); })
+      .def("get_storage", [](TensptrT self) {
+        auto vars = layr::get_storage(self);
+        return ETensorsT(vars.begin(), vars.end());
+      })
+      .def("__neg__", [](TensptrT a) { return tenncor::neg(a); })
+      .def("__add__", [](TensptrT a, const ETensor& b) { return tenncor::add(a, b); })
+      .def("__add__", [](TensptrT a, double b) { return tenncor::add(a, b); })
+      .def("__radd__", [](TensptrT a, double b) { return tenncor::add(b, a); })
+      .def("__sub__", [](TensptrT a, const ETensor& b) { return tenncor::sub(a, b); })
+      .def("__sub__", [](TensptrT a, double b) { return tenncor::sub(a, b); })
+      .def("__rsub__", [](TensptrT a, double b) { return tenncor::sub(b, a); })
+      .def("__mul__", [](TensptrT a, const ETensor& b) { return tenncor::mul(a, b); })
+      .def("__mul__", [](TensptrT a, double b) { return tenncor::mul(a, b); })
+      .def("__rmul__", [](TensptrT a, double b) { return tenncor::mul(b, a); })
+      .def("__truediv__", [](TensptrT a, const ETensor& b) { return tenncor::div(a, b); })
+      .def("__truediv__", [](TensptrT a, double b) { return tenncor::div(a, b); })
+      .def("__rtruediv__", [](TensptrT a, double b) { return tenncor::div(b, a); })
+      .def("__lt__", [](TensptrT a, const ETensor& b) { return tenncor::lt(a, b); })
+      .def("__gt__", [](TensptrT a, const ETensor& b) { return tenncor::gt(a, b); });
+
+  py::class_<eteq::Variable, iTensor, eteq::VarptrT>(m, "EVariable")
+      .def(py::init([](std::vector<size_t> slist, double scalar, const std::string& label, py::object dtype) {
+        return eteq::make_variable_scalar(scalar, p2cshape(slist), label, parse_dtype(dtype));
+      }), py::arg("shape"), py::arg("scalar") = 0, py::arg("label") = "", py::arg("dtype") = py::none())
+      .def("assign", [](eteq::Variable& self, py::array data) {
+        Shape shape;
+        egen::_GENERATED_DTYPE dtype;
+        py::array arr = normalise(data, shape, dtype);
+        self.assign(arr.data(), dtype, shape);
+      }, py::arg("data"), "Assign numpy data array to variable (host -> HBM, asynchronous for pinned arrays)")
+      .def("assign_device", [](eteq::Variable& self, uintptr_t dev_ptr) { self.assign_device((const void*)dev_ptr); },
+           "Assign from a device pointer holding this variable's dtype and element count");
+
+  // ---- evaluation / creation
+  m.def("run", [](ETensorsT targets, ETensorsT ignored, size_t max_version) {
+    eteq::run(targets, to_set(ignored), max_version);
+    std::vector<py::array> out;
+    for (auto& t : targets) out.push_back(to_array(*t));
+    return out;
+  }, py::arg("targets"), py::arg("ignored") = ETensorsT{}, py::arg("max_version") = std::numeric_limits<size_t>::max());
+  m.def("scalar_constant", [](double scalar, std::vector<size_t> slist, py::object dtype) {
+    return eteq::make_constant_scalar(scalar, p2cshape(slist), parse_dtype(dtype));
+  }, py::arg("scalar"), py::arg("slist"), py::arg("dtype") = py::none(), "Return scalar constant etens");
+  m.def("constant", [](py::array data) {
+    Shape shape;
+    egen::_GENERATED_DTYPE dtype;
+    py::array arr = normalise(data, shape, dtype);
+    return eteq::make_constant_tensor(arr.data(), dtype, shape);
+  }, "Return constant etens with data");
+  m.def("scalar_variable", [](double scalar, std::vector<size_t> slist, const std::string& label, py::object dtype) {
+    return eteq::make_variable_scalar(scalar, p2cshape(slist), label, parse_dtype(dtype));
+  }, py::arg("scalar"), py::arg("slist"), py::arg("label") = "", py::arg("dtype") = py::none());
+  m.def("variable_like", [](double scalar, ETensor like, const std::string& label) {
+    return eteq::make_variable_scalar(scalar, like->shape(), label, (egen::_GENERATED_DTYPE)like->get_meta().type_code());
+  }, py::arg("scalar"), py::arg("like"), py::arg("label") = "");
+  m.def("variable", [](py::array data, const std::string& label) {
+    Shape shape;
+    egen::_GENERATED_DTYPE dtype;
+    py::array arr = normalise(data, shape, dtype);
+    return eteq::make_variable(arr.data(), dtype, shape, label);
+  }, py::arg("data"), py::arg("label") = "");
+  m.def("to_variable", [](const ETensor& tens) { return as_var(tens); });
+  m.def("derive", [](const ETensor& root, const ETensorsT& targets) { return tenncor::derive(root, targets); },
+        "Return derivative of first tensor with respect to each target");
+  m.def("trail", [](const ETensor& root, const std::vector<std::pair<ETensor, ETensor>>& inps) {
+    OwnMapT inputs;
+    for (auto& p : inps) inputs.emplace(p.first.get(), p.second);
+    return layr::trail(root, inputs);
+  });
+  m.def("seed", &tenncor::seed, "Seed internal RNG");
+  m.def("dump_graph", &dump_graph, "Post-order node list (evaluation order) of the graph under the targets");
+  m.def("dump_ids", [](const ETensorsT& targets, py::object) {
+    // ids of `targets` in the numbering dump_graph uses
+    std::unordered_map<iTensor*, size_t> ids;
+    std::function<void(const TensptrT&)> visit = [&](const TensptrT& t) {
+      if (ids.count(t.get())) return;
+      if (auto f = dynamic_cast<iFunctor*>(t.get()))
+        for (auto& a : f->args_ref()) visit(a);
+      ids.emplace(t.get(), ids.size());
+    };
+    py::dict out;
+    for (auto& t : targets) {
+      visit(t);
+      out[py::cast(t)] = ids.at(t.get());
+    }
+    return out;
+  });
+  m.def("apply_update", [](const ETensorsT& models, std::function<layr::VarErrsT(const ETensor&, const ETensorsT&)> update, layr::ErrorF err) {
+    layr::ApproxF approx = [update](const ETensor& e, const eteq::VarptrsT& vars) { return update(e, ETensorsT(vars.begin(), vars.end())); };
+    return trainer::apply_update(models, approx, err);
+  }, py::arg("models"), py::arg("update"), py::arg("err_func"));
+
+  // ---- back-end controls
+  m.def("sync", [] { cuda::sync(); }, "Wait for all queued device work");
+  m.def("launch_count", [] { return tcr_launch_count(); });
+  m.def("set_matmul_precision", [](const std::string& p) {
+    cuda::set_gemm_precision(p == "exact" ? TCR_GEMM_EXACT : p == "tf32" ? TCR_GEMM_TF32 : p == "3xtf32" ? TCR_GEMM_3XTF32 : -1);
+  }, "fp32 MATMUL/CONTRACT precision: 'exact' (SIMT FMA), 'tf32' or '3xtf32' (tcgen05)");
+  m.def("set_evaluator", [](const std::string& kind) {
+    if (kind == "plan") teq::set_eval(std::make_shared<cuda::PlanEvaluator>());
+    else if (kind == "node") teq::set_eval(std::make_shared<teq::Evaluator>());
+    else global::fatalf("unknown evaluator `%s` (plan | node)", kind.c_str());
+  }, "'plan': fused launch plan replayed as a CUDA graph (default); 'node': one kernel per functor like the reference");
+  m.def("plan_stats", [] {
+    auto s = cuda::last_plan_stats();
+    py::dict d;
+    d["nodes"] = s.nodes; d["steps"] = s.steps; d["launches_per_run"] = s.launches; d["graph"] = s.graph; d["plans_cached"] = s.cached;
+    return d;
+  });
+  m.def("arena_stats", [] {
+    size_t a = 0, b = 0, c = 0;
+    tcr_arena_stats(&a, &b, &c);
+    py::dict d;
+    d["bytes_in_use"] = a; d["bytes_reserved"] = b; d["device_mallocs"] = c;
+    return d;
+  });
+
+  // ---- api
+  auto api = m.def_submodule("api", "TenncorAPI (cfg/tenncor/core.yml)");
+  UN("abs", ABS); UN("neg", NEG); UN("sin", SIN); UN("cos", COS); UN("tan", TAN); UN("exp", EXP); UN("log", LOG);
+  UN("sqrt", SQRT); UN("round", ROUND); UN("sigmoid", SIGMOID); UN("tanh", TANH); UN("square", SQUARE); UN("cube", CUBE);
+  BIN("pow", POW); BIN("add", ADD); BIN("sub", SUB); BIN("mul", MUL); BIN("div", DIV); BIN("eq", EQ); BIN("neq", NEQ);
+  BIN("lt", LT); BIN("gt", GT); BIN("min", MIN); BIN("max", MAX);
+  api.def("cast", [](const ETensor& x, py::object dtype) { return tenncor::cast(x, parse_dtype(dtype)); });
+  api.def("assign", [](const ETensor& t, const ETensor& s) { return tenncor::assign(as_var(t), s); });
+  api.def("assign_add", [](const ETensor& t, const ETensor& s) { return tenncor::assign_add(as_var(t), s); });
+  api.def("assign_sub", [](const ETensor& t, const ETensor& s) { return tenncor::assign_sub(as_var(t), s); });
+  api.def("assign_mul", [](const ETensor& t, const ETensor& s) { return tenncor::assign_mul(as_var(t), s); });
+  api.def("assign_div", [](const ETensor& t, const ETensor& s) { return tenncor::assign_div(as_var(t), s); });
+  api.def("identity", &tenncor::identity, py::arg("input"), py::arg("execute_in_parallel") = ETensorsT{});
+  api.def("if_then_else", &tenncor::if_then_else);
+  api.def("reverse", &tenncor::reverse);
+  api.def("permute", &tenncor::permute);
+  api.def("extend", [](const ETensor& a, const DimsT& bcast) { return tenncor::extend(a, bcast); });
+  api.def("extend", [](const ETensor& a, RankT offset, const DimsT& xlist) { return tenncor::extend(a, offset, xlist); });
+  api.def("extend_like", &tenncor::extend_like);
+  api.def("concat", [](const ETensor& l, const ETensor& r, RankT axis) { return tenncor::concat(l, r, axis); });
+  api.def("concat", [](const ETensorsT& args, RankT axis) { return tenncor::concat(args, axis); });
+  api.def("reshape", [](const ETensor& a, std::vector<size_t> pyshape) { return tenncor::reshape(a, p2cshape(pyshape)); });
+#define RED(NAME, OP)                                                                                                          \
+  api.def(NAME, [](const ETensor& t, std::set<RankT> dims) { return tenncor::reduce(egen::OP, t, dims); });                   \
+  api.def(NAME, [](const ETensor& t, RankT offset, RankT ndims) { return tenncor::reduce(egen::OP, t, offset, ndims); },      \
+          py::arg("tens"), py::arg("offset") = 0, py::arg("ndims") = rank_cap);                                                \
+  api.def(NAME "_1d", [](const ETensor& t, RankT d) { return tenncor::reduce_1d(egen::OP, t, d); })
+  RED("reduce_sum", REDUCE_SUM); RED("reduce_prod", REDUCE_PROD); RED("reduce_min", REDUCE_MIN); RED("reduce_max", REDUCE_MAX);
+  api.def("argmax", &tenncor::argmax, py::arg("tens"), py::arg("return_dim") = 8);
+  api.def("n_elems", &tenncor::n_elems);
+  api.def("n_dims", &tenncor::n_dims);
+  api.def("slice", [](const ETensor& a, eigen::PairVecT<DimT> extents) { return tenncor::slice(a, extents); });
+  api.def("slice", [](const ETensor& a, DimT offset, DimT extent, RankT dim) { return tenncor::slice(a, offset, extent, dim); });
+  api.def("pad", [](const ETensor& a, eigen::PairVecT<DimT> p) { return tenncor::pad(a, p); });
+  api.def("pad", [](const ETensor& a, tenncor::DimPairsT p, RankT dim) { return tenncor::pad(a, p, dim); });
+  api.def("stride", &tenncor::stride);
+  api.def("scatter", [](const ETensor& a, std::vector<size_t> pyshape, const DimsT& incrs) { return tenncor::scatter(a, p2cshape(pyshape), incrs); });
+  api.def("contract", &tenncor::contract, py::arg("a"), py::arg("b"), py::arg("dims") = eigen::PairVecT<RankT>{{0, 1}});
+  api.def("matmul", &tenncor::matmul);
+  api.def("convolution", &tenncor::convolution);
+  api.def("transpose", &tenncor::transpose);
+  api.def("reduce_mean", &tenncor::reduce_mean);
+  api.def("reduce_mean_1d", &tenncor::reduce_mean_1d);
+  api.def("reduce_variance", &tenncor::reduce_variance);
+  api.def("reduce_variance_1d", &tenncor::reduce_variance_1d);
+  api.def("reduce_l2norm", &tenncor::reduce_l2norm, py::arg("arg"), py::arg("offset") = 0, py::arg("ndims") = rank_cap);
+  api.def("reduce_l2norm_1d", &tenncor::reduce_l2norm_1d);
+  api.def("clip_by_range", &tenncor::clip_by_range);
+  api.def("clip_by_l2norm", &tenncor::clip_by_l2norm);
+  api.def("sum", &tenncor::sum);
+  api.def("prod", &tenncor::prod);
+  api.def("softmax", &tenncor::softmax, py::arg("arg"), py::arg("offset") = 0, py::arg("ndims") = rank_cap);
+  api.def("relu", &tenncor::relu);
+  api.def("softplus", &tenncor::softplus);
+  api.def("sign", &tenncor::sign);
+
+  auto rnd = api.def_submodule("random");
+  rnd.def("rand_unif", &tenncor::random::rand_unif);
+  rnd.def("rand_binom_one", &tenncor::random::rand_binom_one);
+
+  py::class_<InitHolder>(m, "Initializer")
+      .def("__call__", [](InitHolder& self, std::vector<size_t> pyshape, const std::string& label) { return self.f(p2cshape(pyshape), label); },
+           py::arg("shape"), py::arg("label") = "");
+  auto ini = api.def_submodule("init");
+  ini.def("random_normal", [](double mean, double stddev) { return InitHolder{tenncor::init::random_normal(mean, stddev)}; }, py::arg("mean") = 0, py::arg("stddev") = 1);
+  ini.def("random_uniform", [](double lo, double hi) { return InitHolder{tenncor::init::random_uniform(lo, hi)}; }, py::arg("minval") = -0.05, py::arg("maxval") = 0.05);
+  ini.def("zeros", [] { return InitHolder{tenncor::init::zeros()}; });
+  ini.def("ones", [] { return InitHolder{tenncor::init::ones()}; });
+  ini.def("constants", [](double v) { return InitHolder{tenncor::init::constants(v)}; });
+  ini.def("xavier_uniform", [](double f) { return InitHolder{tenncor::init::xavier_uniform(f)}; }, py::arg("factor") = 1);
+  ini.def("xavier_normal", [](double f) { return InitHolder{tenncor::init::xavier_normal(f)}; }, py::arg("factor") = 1);
+  ini.def("glorot_uniform", [](double f) { return InitHolder{tenncor::init::xavier_uniform(f)}; }, py::arg("factor") = 1);
+  ini.def("glorot_normal", [](double f) { return InitHolder{tenncor::init::xavier_normal(f)}; }, py::arg("factor") = 1);
+
+  auto nn = api.def_submodule("nn");
+  nn.def("fully_connect", &tenncor::nn::fully_connect, py::arg("lefts"), py::arg("rights"), py::arg("bias") = ETensor(),
+         py::arg("dims") = eigen::PairVecT<RankT>{{0, 1}});
+  nn.def("conv2d", &tenncor::nn::conv2d, py::arg("image"), py::arg("kernel"), py::arg("bias") = ETensor(),
+         py::arg("zero_paddings") = std::pair<tenncor::DimPairsT, tenncor::DimPairsT>{{0, 0}, {0, 0}});
+  nn.def("dropout", &tenncor::nn::dropout);
+
+  auto wrap_init = [](py::object f) -> layr::InitF {
+    if (f.is_none()) return layr::InitF();
+    if (py::isinstance<InitHolder>(f)) return f.cast<InitHolder&>().f;
+    // a python callable (numpy_shape, label) -> EVariable
+    py::function pf = f.cast<py::function>();
+    return [pf](Shape shape, std::string label) {
+      DimsT ps = c2pshape(shape);
+      return as_var(pf(std::vector<size_t>(ps.begin(), ps.end()), label).cast<ETensor>());
+    };
+  };
+  auto lay = api.def_submodule("layer");
+  lay.def("bind", [](layr::UnaryF unary, std::vector<size_t> inshape) { return tenncor::layer::bind(unary, p2cshape(inshape)); },
+          py::arg("unary"), py::arg("inshape") = std::vector<size_t>{});
+  lay.def("link", &tenncor::layer::link, py::arg("layers"), py::arg("input") = ETensor());
+  lay.def("dense", [wrap_init](std::vector<size_t> inshape, std::vector<size_t> hidden_dims, py::object kinit, py::object binit, bool with_bias) {
+    DimsT hd(hidden_dims.rbegin(), hidden_dims.rend());
+    return tenncor::layer::dense(p2cshape(inshape), hd, wrap_init(kinit), wrap_init(binit), with_bias);
+  }, py::arg("inshape"), py::arg("hidden_dims"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none(), py::arg("with_bias") = true);
+  lay.def("dense_on", [](const ETensor& input, const ETensor& kernel, const ETensor& bias) { return tenncor::layer::dense(input, kernel, bias); },
+          py::arg("input"), py::arg("kernel"), py::arg("bias") = ETensor());
+  lay.def("conv2d", [wrap_init](tenncor::DimPairsT kernel_hw, DimT in_ncol, DimT out_ncol, py::object kinit, py::object binit) {
+    return tenncor::layer::conv2d(kernel_hw, in_ncol, out_ncol, wrap_init(kinit), wrap_init(binit));
+  }, py::arg("kernel_hw"), py::arg("in_ncol"), py::arg("out_ncol"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none());
+  lay.def("rnn", [wrap_init](DimT indim, DimT hidden_dim, layr::UnaryF activation, DimT nseq, py::object kinit, py::object binit, RankT seq_dim) {
+    return tenncor::layer::rnn(indim, hidden_dim, activation, nseq, wrap_init(kinit), wrap_init(binit), seq_dim);
+  }, py::arg("indim"), py::arg("hidden_dim"), py::arg("activation"), py::arg("nseq"), py::arg("kernel_init") = py::none(),
+          py::arg("bias_init") = py::none(), py::arg("seq_dim") = 1);
+  lay.def("lstm", [wrap_init](std::vector<size_t> inshape, DimT hidden_dim, DimT nseq, py::object kinit, py::object binit, RankT seq_dim) {
+    return tenncor::layer::lstm(p2cshape(inshape), hidden_dim, nseq, wrap_init(kinit), wrap_init(binit), seq_dim);
+  }, py::arg("inshape"), py::arg("hidden_dim"), py::arg("nseq"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none(),
+          py::arg("seq_dim") = 1);
+  lay.def("gru", [wrap_init](std::vector<size_t> inshape, DimT hidden_dim, DimT nseq, py::object kinit, py::object binit, RankT seq_dim) {
+    return tenncor::layer::gru(p2cshape(inshape), hidden_dim, nseq, wrap_init(kinit), wrap_init(binit), seq_dim);
+  }, py::arg("inshape"), py::arg("hidden_dim"), py::arg("nseq"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none(),
+          py::arg("seq_dim") = 1);
+  lay.def("rnn_on", [](const ETensor& input, const ETensor& init_state, const ETensor& cell, layr::UnaryF activation, RankT seq_dim) {
+    return tenncor::layer::rnn(input, init_state, cell, activation, seq_dim);
+  }, py::arg("input"), py::arg("init_state"), py::arg("cell"), py::arg("activation"), py::arg("seq_dim") = 1);
+  py::class_<layr::RBMLayer>(m, "RBMLayer")
+      .def("connect", &layr::RBMLayer::connect)
+      .def("backward_connect", &layr::RBMLayer::backward_connect)
+      .def("deep_clone", &layr::RBMLayer::deep_clone)
+      .def("fwd", [](layr::RBMLayer& self) { return self.fwd_; })
+      .def("bwd", [](layr::RBMLayer& self) { return self.bwd_; });
+  lay.def("rbm", [wrap_init](DimT nvisible, DimT nhidden, py::object kinit, py::object binit) {
+    return tenncor::layer::rbm(nvisible, nhidden, wrap_init(kinit), wrap_init(binit));
+  }, py::arg("nvisible"), py::arg("nhidden"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none());
+
+  auto los = api.def_submodule("loss");
+  los.def("sqr_diff", &tenncor::loss::sqr_diff);
+  los.def("mean_squared", &tenncor::loss::mean_squared, py::arg("target"), py::arg("input"), py::arg("axis") = rank_cap);
+  los.def("cross_entropy", &tenncor::loss::cross_entropy, py::arg("target"), py::arg("input"), py::arg("eps") = std::numeric_limits<float>::epsilon());
+
+  auto to_vars = [](const ETensorsT& ts) {
+    eteq::VarptrsT vars;
+    for (auto& t : ts) vars.push_back(as_var(t));
+    return vars;
+  };
+  auto apx = api.def_submodule("approx");
+  const double feps = std::numeric_limits<float>::epsilon();
+  apx.def("sgd", [to_vars](const ETensor& e, const ETensorsT& v, double lr) { return tenncor::approx::sgd(e, to_vars(v), lr); },
+          py::arg("error"), py::arg("variables"), py::arg("learning_rate") = 0.5);
+  apx.def("adagrad", [to_vars](const ETensor& e, const ETensorsT& v, double lr, double eps) { return tenncor::approx::adagrad(e, to_vars(v), lr, eps); },
+          py::arg("error"), py::arg("variables"), py::arg("learning_rate") = 0.5, py::arg("epsilon") = feps);
+  apx.def("adam", [to_vars](const ETensor& e, const ETensorsT& v, double sr, double d1, double d2, double eps) {
+    return tenncor::approx::adam(e, to_vars(v), sr, d1, d2, eps);
+  }, py::arg("error"), py::arg("variables"), py::arg("step_rate") = 0.001, py::arg("decay1") = 0.9, py::arg("decay2") = 0.999, py::arg("epsilon") = feps);
+  apx.def("adadelta", [to_vars](const ETensor& e, const ETensorsT& v, double sr, double decay, double offset, double eps) {
+    return tenncor::approx::adadelta(e, to_vars(v), sr, decay, offset, eps);
+  }, py::arg("error"), py::arg("variables"), py::arg("step_rate") = 1, py::arg("decay") = 0.9, py::arg("offset") = 0.0001, py::arg("epsilon") = feps);
+  apx.def("rms_momentum", [to_vars](const ETensor& e, const ETensorsT& v, double lr, double discount, double eps, py::object apply) {
+    layr::UnaryF f;
+    if (!apply.is_none()) f = apply.cast<layr::UnaryF>();
+    return tenncor::approx::rms_momentum(e, to_vars(v), lr, discount, eps, f);
+  }, py::arg("error"), py::arg("variables"), py::arg("learning_rate") = 0.5, py::arg("discount_factor") = 0.99, py::arg("epsilon") = feps,
+          py::arg("apply") = py::none());
+
+  m.def("rbm_train", [](const layr::RBMLayer& model, ETensor visible, double lr, double discount, size_t cdk) {
+    return trainer::rbm(model, visible, lr, discount, {}, cdk);
+  }, py::arg("model"), py::arg("visible"), py::arg("learning_rate"), py::arg("discount_factor"), py::arg("cdk") = 1);
+
+  // ---- data parallel
+  auto dpm = m.def_submodule("dp", "batch-sharded data parallelism over NCCL (dp.hpp)");
+  dpm.def("unique_id", [] { return py::bytes(dp::unique_id()); });
+  dpm.def("init", [](int rank, int nranks, py::bytes id, bool mean_reduce) { dp::init(rank, nranks, std::string(id), mean_reduce); },
+          py::arg("rank"), py::arg("nranks"), py::arg("id") = py::bytes(""), py::arg("mean_reduce") = true);
+  dpm.def("shutdown", &dp::shutdown);
+  dpm.def("rank", &dp::rank);
+  dpm.def("size", &dp::size);
+  dpm.def("shard", &dp::shard);
+}

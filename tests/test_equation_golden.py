@@ -1,0 +1,117 @@
+"""The reference's end-to-end equation goldens (tenncor/test/test_equation.cpp): forward
+values and full gradients of MatmulComplex, ContractEquivalent, Slow/Fast SigmoidMLP (the
+gd_demo topology 10-9-5, batch 3) and TanhRNN, asserted there with EXPECT_DOUBLE_EQ.
+
+ * CPU (no GPU): the graphs are built through our host API (eteq / derive / layr), dumped,
+   and evaluated by the oracle -> pins BOTH the gradient-graph builder and the oracle's
+   tape evaluator against the reference's own numbers.
+ * GPU: the same graphs evaluated by the CUDA back end, node-by-node and planned.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import tenncor_b200 as tc
+from oracle import tcr_oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "equation_goldens.json")) as f:
+    GOLD = json.load(f)
+
+DOUBLE_EQ = 1e-13  # EXPECT_DOUBLE_EQ is 4 ulp; allow a few more for a different summation order
+
+
+def var(g, data, shape, label=""):
+    arr = np.array(g["vectors"][data], dtype=np.float64).reshape(g["shapes"][shape][::-1])
+    return tc.variable(arr, label or data)
+
+
+def build_matmul_complex(g, contract=False):
+    a, b, c = var(g, "data", "alist"), var(g, "data2", "blist"), var(g, "data3", "clist")
+    mm = tc.api.contract if contract else tc.api.matmul
+    d = mm(a, b)
+    e = mm(c, d)
+    f = mm(tc.api.transpose(d), tc.api.transpose(c))
+    dest = mm(e, f)
+    ders = tc.derive(dest, [a, b, c])
+    return [dest] + ders, ["expect_dest", "expect_ga", "expect_gb", "expect_gc"]
+
+
+def build_mlp(g, fast):
+    x = var(g, "in_data", "in_shape")
+    w0, b0 = var(g, "w0_data", "weight0_shape"), var(g, "b0_data", "bias0_shape")
+    w1, b1 = var(g, "w1_data", "weight1_shape"), var(g, "b1_data", "bias1_shape")
+    out = var(g, "out_data", "out_shape")
+    layer0 = tc.api.matmul(x, w0) + tc.api.extend(b0, 1, [3])
+    sig0 = tc.api.sigmoid(layer0) if fast else 1. / (1. + tc.api.exp(-layer0))
+    layer1 = tc.api.matmul(sig0, w1) + tc.api.extend(b1, 1, [3])
+    sig1 = tc.api.sigmoid(layer1) if fast else 1. / (1. + tc.api.exp(-layer1))
+    err = tc.api.pow(out - sig1, 2.)
+    return tc.derive(err, [w0, b0, w1, b1]), ["expect_gw0", "expect_gb0", "expect_gw1", "expect_gb1"]
+
+
+def build_rnn(g, layer):
+    x = var(g, "in_data", "in_shape")
+    weight, bias = var(g, "weight_data", "weight_shape", "weight"), var(g, "bias_data", "bias_shape", "bias")
+    istate, out = var(g, "state_data", "state_shape"), var(g, "out_data", "out_shape")
+    seq_dim, nseq = 1, g["shapes"]["in_shape"][1]
+    if layer:
+        cell_in = tc.EVariable([10], 0, "input", dtype="DOUBLE")
+        cell = tc.api.layer.dense_on(cell_in, weight, bias)
+        state = tc.api.extend_like(istate, tc.api.slice(x, 0, 1, seq_dim))
+        output = tc.layer_rnn(x, state, cell, tc.api.tanh, seq_dim)
+    else:
+        state, states = istate, []
+        for i in range(nseq):
+            inslice = tc.api.slice(x, i, 1, seq_dim)
+            state = tc.api.tanh(tc.api.nn.fully_connect([tc.api.concat(inslice, state, 0)], [weight], bias))
+            states.append(state)
+        output = tc.api.concat(states, seq_dim)
+    err = tc.api.pow(out - output, 2.)
+    return tc.derive(err, [weight, bias, istate]), ["expect_gw", "expect_gb", "expect_gstate"]
+
+
+CASES = {
+    "matmul_complex": lambda g: build_matmul_complex(g),
+    "contract_equivalent": lambda g: build_matmul_complex(g, contract=True),
+    "sigmoid_MLP_slow": lambda g: build_mlp(g, fast=False),
+    "sigmoid_MLP_fast": lambda g: build_mlp(g, fast=True),
+    "tanh_RNN": lambda g: build_rnn(g, layer=False),
+    "tanh_RNN_layer": lambda g: build_rnn(g, layer=True),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_host_graph_plus_oracle_match_reference(built, name):
+    g = GOLD[name]
+    roots, expects = CASES[name](g)
+    tape = tc.dump_graph(roots)
+    vals = orc.eval_tape(tape)
+    ids = tc.dump_ids(roots, tape)
+    for root, key in zip(roots, expects):
+        want = np.array(g["vectors"][key])
+        got = np.asarray(vals[ids[root]], dtype=np.float64)
+        assert got.size == want.size, (key, got.size, want.size)
+        np.testing.assert_allclose(got, want, rtol=DOUBLE_EQ, atol=0, err_msg=key)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("evaluator", ["node", "plan"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_gpu_matches_reference(gpu, name, evaluator):
+    g = GOLD[name]
+    tc.set_evaluator(evaluator)
+    try:
+        roots, expects = CASES[name](g)
+        outs = tc.run(roots)
+        for got, key in zip(outs, expects):
+            want = np.array(g["vectors"][key])
+            np.testing.assert_allclose(got.reshape(-1), want, rtol=DOUBLE_EQ, atol=0, err_msg=key)
+        # idempotent: a second evaluation returns the same values (test_api.cpp evaluates twice)
+        outs2 = tc.run(roots)
+        for a, b in zip(outs, outs2):
+            np.testing.assert_array_equal(a, b)
+    finally:
+        tc.set_evaluator("plan")
