@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — train steps/sec of the TEQ-graph evaluation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c1w|c4|c4a|c2] [--impl reference]
+
+One JSON line on stdout (rank 0). A "step" is one evaluation of the `apply_update` root of a
+demo model: forward + derivative graph + optimiser ASSIGNs over one synthetic batch.
+
+  value      steps/s with the batch already resident in HBM (CUDA events on the library stream,
+             barrier + synchronize on both sides, max over ranks)
+  e2e        the same metric through the public API with HOST buffers: every step assigns the
+             batch from pinned host memory (H2D) and reads the loss back (D2H)
+  roofline   the dominant kernel of the step, timed live with CUDA events through the C-ABI
+  cpu_baseline / --impl reference
+             the CPU oracle (numpy restatement of the reference's Eigen path; the reference
+             itself cannot be built here) evaluating the same dumped graph node
+             by node on the host cores
+
+Default workload c3 = BASELINE.json configs[2] "MNIST-shaped MLP ... batch 65536 sharded over
+8xB200" = 8192 samples per GPU (weak scaling); configs[1] (RBM) is `--workload c2`.
+Inputs per step are larger than nothing cached: weights + activations exceed L2 only for c3/c4
+(activations 33.5 MB x ~10 live tensors); smaller workloads say "l2_resident" in config.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (builder kwargs, description)
+    "c1": dict(kind="mlp", ninput=10, nhidden=9, noutput=5, nbatch=3),
+    "c1w": dict(kind="mlp", ninput=1024, nhidden=1024, noutput=512, nbatch=8192),
+    "c3": dict(kind="mlp", ninput=784, nhidden=1024, noutput=10, nbatch=8192, one_hot=True),
+    "c2": dict(kind="rbm", nvisible=784, nhidden=64, nbatch=4096),
+    "c4a": dict(kind="lstm", vocab=128, hidden=1024, seq=128, batch=None),
+    "c4": dict(kind="lstm", vocab=128, hidden=1024, seq=128, batch=64),
+    "c4gru": dict(kind="gru", vocab=128, hidden=1024, seq=128, batch=64),
+}
+
+
+def build_config(name):
+    from tenncor_b200 import configs
+    w = dict(WORKLOADS[name])
+    kind = w.pop("kind")
+    one_hot = w.pop("one_hot", False)
+    if kind == "mlp":
+        cfg = configs.mlp(name=name, **w)
+        gen = lambda rng: configs.mlp_batch(rng, cfg.feeds, one_hot=one_hot)  # noqa: E731
+    elif kind == "rbm":
+        cfg = configs.rbm(name=name, **w)
+        gen = lambda rng: ((rng.random(cfg.feeds["x"].shape()) < 0.5).astype(np.float32),)  # noqa: E731
+    else:
+        cfg = configs.recurrent(kind, name=name, **w)
+        gen = lambda rng: configs.recurrent_batch(rng, cfg.feeds, w["vocab"])  # noqa: E731
+    return cfg, gen, w
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.rows, self.stop_flag = device, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][2]) if self.rows[0][2].replace(".", "").isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def pinned_array(cabi, shape, dtype=np.float32):
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    cabi.check(cabi.lib().tcr_host_alloc(C.byref(p), C.c_size_t(n * np.dtype(dtype).itemsize)))
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def event_timer(cabi):
+    lib = cabi.lib()
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    cabi.check(lib.tcr_event_create(C.byref(e0)))
+    cabi.check(lib.tcr_event_create(C.byref(e1)))
+
+    def start():
+        cabi.check(lib.tcr_event_record(e0))
+
+    def stop_ms():
+        cabi.check(lib.tcr_event_record(e1))
+        ms = C.c_float()
+        cabi.check(lib.tcr_event_elapsed_ms(e0, e1, C.byref(ms)))
+        return ms.value
+    return start, stop_ms
+
+
+def dominant_kernel_roofline(cabi, name, w, peaks):
+    """Time the step's dominant kernel alone, on the library stream, with the workload's shapes."""
+    lib = cabi.lib()
+    F = cabi.FLOAT
+    start, stop_ms = event_timer(cabi)
+    rng = np.random.default_rng(7)
+    if "ninput" in w or "vocab" in w:
+        if "ninput" in w:
+            M, K, N = w["nbatch"], w["ninput"], w["nhidden"]
+            label = "tcr_gemm fwd layer0 (B x in)(in x hid) 3xTF32"
+        else:
+            B = w["batch"] or 1
+            M, K, N = B, w["vocab"] + w["hidden"], w["hidden"]
+            label = "tcr_gemm gate (B x (N+H))((N+H) x H) 3xTF32"
+        a = cabi.to_device(rng.uniform(-1, 1, M * K).astype(np.float32))
+        b = cabi.to_device(rng.uniform(-1, 1, K * N).astype(np.float32))
+        c = cabi.empty(M * N, np.float32)
+        d = cabi.GemmDesc(m=M, n=N, k=K, batch=1, a_sm=K, a_sk=1, b_sk=N, b_sn=1, c_sm=N, c_sn=1, dtype=F, precision=cabi.GEMM_3XTF32)
+        call = lambda: cabi.check(lib.tcr_gemm(C.c_void_p(a.ptr), C.c_void_p(b.ptr), C.c_void_p(c.ptr), C.byref(d)))  # noqa: E731
+        for _ in range(3):
+            call()
+        cabi.sync()
+        iters = 20
+        start()
+        for _ in range(iters):
+            call()
+        ms = stop_ms() / iters
+        flops = 2.0 * M * N * K
+        # TF32 dense peak is not in MEASURED_PEAKS.json: half of the measured bf16 burst (B200_PROFILING.md table: tf32 = bf16 / 2)
+        peak = peaks.get("bf16_tflops", 1590.0) / 2
+        return {"bound": "tensor", "kernel": label, "achieved": round(flops / ms / 1e9, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
+                "frac": round(flops / ms / 1e9 / peak, 4), "traffic": None, "ms_per_launch": round(ms, 5),
+                "peak_source": "0.5 x measured bf16_tflops (MEASURED_PEAKS.json)" if "bf16_tflops" in peaks else "0.5 x fallback 1590"}
+    # RBM: HBM-bound elementwise/RNG over [784, B]
+    n = w["nvisible"] * w["nbatch"]
+    x = cabi.to_device(rng.uniform(-4, 4, n).astype(np.float32))
+    y = cabi.empty(n, np.float32)
+    call = lambda: cabi.check(lib.tcr_unary(cabi.OP["SIGMOID"], C.c_void_p(x.ptr), C.c_void_p(y.ptr), C.c_int64(n), F))  # noqa: E731
+    for _ in range(3):
+        call()
+    cabi.sync()
+    start()
+    for _ in range(50):
+        call()
+    ms = stop_ms() / 50
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"bound": "hbm", "kernel": "tcr_unary SIGMOID [784,B]", "achieved": round(8 * n / ms / 1e6, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(8 * n / ms / 1e6 / peak, 4), "traffic": None, "ms_per_launch": round(ms, 5),
+            "peak_source": "measured hbm_gbs (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650"}
+
+
+def cpu_reference_steps(cfg, gen, budget_s, max_steps):
+    """The oracle port of the reference's CPU path: node-by-node numpy evaluation of the dumped
+    graph (TravEvaluator order, one unfused op per functor, in-place ASSIGNs)."""
+    import tenncor_b200 as tc
+    from oracle import tcr_oracle as orc  # cpu_baseline leg only: never on the product path
+    orc.set_baseline_mode(True)
+    tape = tc.dump_graph([cfg.train])
+    for node in tape:
+        if node["kind"] == "leaf":
+            node["data"] = np.array(node["data"], copy=True)
+    feed_ids = tc.dump_ids([cfg.train] + list(cfg.feeds.values()), None)
+    rng = np.random.default_rng(0)
+    times = []
+    t_begin = time.perf_counter()
+    while len(times) < max_steps and (time.perf_counter() - t_begin < budget_s or len(times) < 2):
+        batch = gen(rng)
+        t0 = time.perf_counter()
+        for feed, arr in zip(cfg.feeds.values(), batch):
+            tape[feed_ids[feed]]["data"][...] = arr.reshape(-1)
+        orc.eval_tape(tape)
+        times.append(time.perf_counter() - t0)
+    steady = times[1:] if len(times) > 1 else times
+    return float(np.median(steady)), len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--evaluator", default="plan", choices=["plan", "node"])
+    ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "exact"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+
+    import __graft_entry__ as g
+    g.build()
+    import tenncor_b200 as tc
+    from tenncor_b200 import cabi
+
+    metric = "train steps/sec"
+    wdesc = {"workload": args.workload, **{k: v for k, v in WORKLOADS[args.workload].items()}}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cfg, gen, w = build_config(args.workload)
+        med, nsteps = cpu_reference_steps(cfg, gen, budget_s=max(args.cpu_seconds, 10.0) * 4, max_steps=args.steps + args.warmup)
+        cores = os.cpu_count()
+        line = {"impl": "reference", "metric": metric, "value": round(1.0 / med, 4), "unit": "steps/s", "n_gpus": 0, "steps": nsteps,
+                "warmup": 1, "ms_per_step": round(med * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": dict(wdesc, desc=cfg.desc, batch_per_gpu=w.get("nbatch", w.get("batch"))),
+                "cpu_baseline": {"value": round(1.0 / med, 4), "unit": "steps/s", "cores": cores, "kind": "port",
+                                 "sample": "%d full steps of the same graph (numpy oracle: 1 thread per elementwise op, BLAS threads in GEMM)" % nsteps},
+                "e2e": {"value": round(1.0 / med, 4), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo", rank=rank, world_size=world)  # host-side rendezvous only; data path is NCCL in libtcr_b200
+    os.environ["TCR_DEVICE"] = str(local_rank)
+    cabi.init(local_rank)
+    tc.set_evaluator(args.evaluator)
+    tc.set_matmul_precision(args.precision)
+    if world > 1:
+        ids = [tc.dp.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        mean_loss = WORKLOADS[args.workload]["kind"] in ("mlp", "rbm")  # reduce_mean losses; the LSTM's NLL is a sum
+        tc.dp.init(rank, world, ids[0], mean_reduce=mean_loss)
+
+    cfg, gen, w = build_config(args.workload)
+    rng = np.random.default_rng(1000 + rank)
+    feeds = list(cfg.feeds.values())
+    host = [pinned_array(cabi, f.shape()) for f in feeds]
+    for buf, arr in zip(host, gen(rng)):
+        buf[...] = arr
+    h2d = int(sum(b.nbytes for b in host))
+
+    def barrier():
+        tc.sync()
+        if dist is not None:
+            dist.barrier()
+
+    start, stop_ms = event_timer(cabi)
+
+    # resident: batch uploaded once, timed region = graph evaluation only
+    for f, buf in zip(feeds, host):
+        f.assign(buf)
+    for _ in range(args.warmup):
+        cfg.train.calc()
+        for f in feeds:
+            f.touch()  # new input version, data stays resident: the next step recomputes everything
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = cabi.lib().tcr_launch_count()
+    start()
+    for _ in range(args.steps):
+        for f in feeds:
+            f.touch()
+        cfg.train.calc()
+    ms_total = stop_ms()
+    launches = int(cabi.lib().tcr_launch_count() - launches0)
+    barrier()
+    plan = tc.plan_stats()
+
+    # end to end: pinned host batch -> H2D -> step -> D2H of the loss, every step
+    loss = None
+    for _ in range(args.warmup):
+        for f, buf in zip(feeds, host):
+            f.assign(buf)
+        loss = cfg.train.get()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for f, buf in zip(feeds, host):
+            f.assign(buf)
+        loss = cfg.train.get()
+    tc.sync()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.summary()
+    d2h = int(np.asarray(loss).nbytes)
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = float(t[0]), float(t[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        roof = dominant_kernel_roofline(cabi, args.workload, w, peaks)
+        med, nsteps = cpu_reference_steps(cfg, gen, budget_s=args.cpu_seconds, max_steps=20)
+        ms_step = ms_total / args.steps
+        line = {
+            "metric": metric, "value": round(world * 1e3 / ms_step, 3), "unit": "steps/s (sum over GPUs of per-GPU steps/s; each step = one local batch)",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(wdesc, desc=cfg.desc, batch_per_gpu=w.get("nbatch", w.get("batch")), global_batch=(w.get("nbatch") or w.get("batch") or 1) * world,
+                           evaluator=args.evaluator, matmul=args.precision, parallelism="dp%d" % world,
+                           cache="step working set %s L2 (126 MB); no flush" % ("exceeds" if args.workload in ("c3", "c1w", "c4", "c4gru", "c2") else "is resident in")),
+            "samples_per_s": round(world * (w.get("nbatch") or w.get("batch") or 1) * 1e3 / ms_step, 1),
+            "flops_per_step": cfg.flops_per_step, "tflops": round(cfg.flops_per_step / ms_step / 1e9, 2),
+            "clocks": clocks,
+            "e2e": {"value": round(world * args.steps * 1e3 / e2e_ms, 3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_ms / args.steps, 4)},
+            "gpu_launches": launches, "launches_per_step": round(launches / args.steps, 1), "plan": plan,
+            "roofline": roof,
+            "cpu_baseline": {"value": round(1.0 / med, 4), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "%d full steps of the same graph on the host (numpy oracle of the Eigen path)" % nsteps},
+            "final_loss": float(np.asarray(loss).reshape(-1)[0]),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        tc.dp.shutdown()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -25,6 +25,23 @@ import numpy as np
 
 RANK_CAP = 8  # internal/teq/shape.hpp:45
 
+# checker mode (default): fp32 contractions accumulate in double, so the oracle is the more
+# accurate side of every comparison. baseline mode: contractions stay in the tensor's own
+# dtype (sgemm), which is what the reference's Eigen path executes — used only when the
+# oracle is TIMED as the CPU baseline.
+_BASELINE_MODE = False
+
+
+def set_baseline_mode(on):
+    global _BASELINE_MODE
+    _BASELINE_MODE = bool(on)
+
+
+def _acc_dtype(dt):
+    if dt == np.float32 and not _BASELINE_MODE:
+        return np.dtype(np.float64)
+    return dt
+
 # egen::_GENERATED_OPCODE, cfg/ops.yml:63-711 in order (BAD_OP = 0)
 OPCODES = [
     "BAD_OP", "IDENTITY", "ABS", "NEG", "SIN", "COS", "TAN", "EXP", "LOG", "SQRT", "ROUND",
@@ -307,7 +324,7 @@ def contract(a, ashape, b, bshape, pairs):
     pairs = [(int(p), int(q)) for p, q in pairs if p < RANK_CAP and q < RANK_CAP]
     a_axes = [ax(p) for p, _ in pairs]
     b_axes = [ax(q) for _, q in pairs]
-    acc = np.float64 if A.dtype == np.float32 else A.dtype
+    acc = _acc_dtype(A.dtype)
     out = np.tensordot(A.astype(acc), B.astype(acc), axes=(a_axes, b_axes)).astype(A.dtype)
     # tensordot(A, B) axes: A-free (numpy order = teq ranks descending) then B-free (descending)
     # reading numpy axes right-to-left gives teq order: b-free ascending, then a-free ascending
@@ -325,7 +342,7 @@ def matmul(a, ashape, b, bshape):
     as_, bs_ = full_shape(ashape), full_shape(bshape)
     A = nd(a, ashape).reshape(-1, as_[1], as_[0])  # row-major (M x K) per batch
     B = nd(b, bshape).reshape(-1, bs_[1], bs_[0])  # row-major (K x N)
-    acc = np.float64 if A.dtype == np.float32 else A.dtype
+    acc = _acc_dtype(A.dtype)
     out = np.matmul(A.astype(acc), B.astype(acc)).astype(A.dtype)
     return flat(out), full_shape([bs_[0], as_[1]] + as_[2:])
 
@@ -339,7 +356,7 @@ def conv(img, ishape, kern, kshape, order):
     oshape = list(is_)
     for i in range(RANK_CAP):
         oshape[order[i]] = is_[order[i]] - ks_[i] + 1
-    acc = np.dtype(np.float64) if I.dtype == np.float32 else I.dtype
+    acc = _acc_dtype(I.dtype)
     out = np.zeros(oshape[::-1], dtype=acc)
     for kidx in np.ndindex(*ks_):  # kidx[i] = coordinate along kernel rank i
         sl = [None] * RANK_CAP

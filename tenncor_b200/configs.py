@@ -1,0 +1,105 @@
+"""The reference's demo models, built through the public API exactly like the demos do.
+
+Each builder returns a `Config` whose `train` node evaluates one full training step
+(forward + derivative graph + optimiser ASSIGNs, trainer::apply_update semantics) and whose
+`feeds` are the input variables a step assigns. Shapes follow SURVEY.md §8(d) / BASELINE.md §3.
+"""
+from collections import namedtuple
+
+import numpy as np
+
+import tenncor_b200 as tc
+
+Config = namedtuple("Config", "name train feeds model variables flops_per_step desc")
+
+
+def mlp(ninput=10, nhidden=9, noutput=5, nbatch=3, learning_rate=0.9, seed=0, name="C1"):
+    """dense -> sigmoid -> dense -> sigmoid, MSE, SGD (demo/gd_demo.py:55-71, demo/gd_demo.cpp:100-168)."""
+    tc.seed(seed)
+    train_input = tc.EVariable([nbatch, ninput], 0, "train_input")
+    train_exout = tc.EVariable([nbatch, noutput], 0, "train_exout")
+    model = tc.api.layer.link([
+        tc.api.layer.dense([ninput], [nhidden]),
+        tc.api.layer.bind(tc.api.sigmoid),
+        tc.api.layer.dense([nhidden], [noutput]),
+        tc.api.layer.bind(tc.api.sigmoid),
+    ], train_input)
+    train = tc.apply_update(
+        [model],
+        lambda err, leaves: tc.api.approx.sgd(err, leaves, learning_rate=learning_rate),
+        lambda models: tc.api.loss.mean_squared(train_exout, models[0].connect(train_input)))
+    # grad wrt the first layer's input is not built (internal/teq/src/derive.cpp:151-159)
+    flops = 4 * nbatch * ninput * nhidden + 6 * nbatch * nhidden * noutput
+    return Config(name, train, {"x": train_input, "y": train_exout}, model, model.get_storage(), flops,
+                  "MLP %d-%d-%d sigmoid, MSE, SGD %.2g, batch %d" % (ninput, nhidden, noutput, learning_rate, nbatch))
+
+
+def mlp_batch(rng, cfg_feeds, one_hot=False):
+    """synthetic batch: x ~ U[0,1); y = pairwise mean of x (gd_demo batch_generate) or one-hot."""
+    x_shape = cfg_feeds["x"].shape()
+    y_shape = cfg_feeds["y"].shape()
+    x = rng.random(x_shape, dtype=np.float32)
+    if one_hot or x_shape[1] != 2 * y_shape[1]:
+        y = np.zeros(y_shape, dtype=np.float32)
+        y[np.arange(y_shape[0]), rng.integers(0, y_shape[1], y_shape[0])] = 1
+    else:
+        y = ((x[:, 0::2] + x[:, 1::2]) / 2).astype(np.float32)
+    return x, y
+
+
+def encoded_loss(encoded_expect, encoded_result):
+    # demo/lstm/latin_demo.py:39-40
+    return tc.api.reduce_sum(-tc.api.log(tc.api.reduce_sum(encoded_result * encoded_expect, 0, 1)))
+
+
+def recurrent(kind="lstm", vocab=128, hidden=1024, seq=128, batch=None, learning_rate=0.1, seed=3, name="C4"):
+    """layer.lstm / layer.gru -> dense -> softmax(dim 0), summed NLL, adagrad
+    (demo/lstm/latin_demo.py:94-122; GRU twin demo/gru/latin_demo.py). batch=None is the demo's
+    literal un-batched form ([N, seq]); a batch puts B at rank 1 and the sequence at rank 2 so
+    that every per-step SLICE stays a zero-copy view."""
+    tc.seed(seed)
+    winit = tc.api.init.random_uniform(-0.05, 0.05)
+    make = tc.api.layer.lstm if kind == "lstm" else tc.api.layer.gru
+    if batch is None:
+        cell = make([vocab], hidden, seq, kernel_init=winit)
+        in_shape = [seq, vocab]
+    else:
+        cell = make([batch, vocab], hidden, seq, kernel_init=winit, seq_dim=2)
+        in_shape = [seq, batch, vocab]
+    model = tc.api.layer.link([
+        cell,
+        tc.api.layer.dense([hidden], [vocab], kernel_init=winit),
+        tc.api.layer.bind(lambda x: tc.api.softmax(x, 0, 1)),
+    ])
+    train_inps = tc.EVariable(in_shape, 0, "train_inps")
+    train_exout = tc.EVariable(in_shape, 0, "train_exout")
+    train = tc.apply_update(
+        [model],
+        lambda error, leaves: tc.api.approx.adagrad(error, leaves, learning_rate=learning_rate, epsilon=1e-8),
+        lambda models: encoded_loss(train_exout, models[0].connect(train_inps)))
+    B = batch or 1
+    ngates = 4 if kind == "lstm" else 3
+    flops = 3 * (seq * ngates * 2 * B * (vocab + hidden) * hidden + 2 * seq * B * hidden * vocab)
+    return Config(name, train, {"x": train_inps, "y": train_exout}, model, model.get_storage(), flops,
+                  "%s N=%d H=%d seq=%d batch=%s, softmax NLL, adagrad %.2g" % (kind, vocab, hidden, seq, batch, learning_rate))
+
+
+def recurrent_batch(rng, cfg_feeds, vocab):
+    """one-hot token ids ~ U{0..vocab-1}; the target is the input shifted by one step."""
+    shape = cfg_feeds["x"].shape()  # [seq, vocab] or [seq, batch, vocab]
+    lead = shape[:-1]
+    ids = rng.integers(0, vocab, [lead[0] + 1] + list(lead[1:]))
+    eye = np.eye(vocab, dtype=np.float32)
+    return eye[ids[:-1]], eye[ids[1:]]
+
+
+def rbm(nvisible=784, nhidden=64, nbatch=4096, learning_rate=0.01, discount=0.95, seed=1, name="C2"):
+    """Bernoulli RBM trained by CD-1 (demo/rbm_demo.py:63-88, tenncor/trainer/rbm.hpp:85-165)."""
+    tc.seed(seed)
+    model = tc.api.layer.rbm(nvisible, nhidden)
+    visible = tc.EVariable([nbatch, nvisible], 0, "visible")
+    train = tc.rbm_train(model, visible, learning_rate=learning_rate, discount_factor=discount)
+    flops = 5 * 2 * nbatch * nvisible * nhidden
+    variables = list({id(v): v for v in model.fwd().get_storage() + model.bwd().get_storage()}.values())
+    return Config(name, train, {"x": visible}, model, variables, flops,
+                  "RBM %d<->%d CD-1, batch %d" % (nvisible, nhidden, nbatch))

@@ -241,6 +241,8 @@ PYBIND11_MODULE(_tenncor, m) {
         py::array arr = normalise(data, shape, dtype);
         self.assign(arr.data(), dtype, shape);
       }, py::arg("data"), "Assign numpy data array to variable (host -> HBM, asynchronous for pinned arrays)")
+      .def("touch", [](eteq::Variable& self) { self.upversion(eteq::get_lastvers() + 1); },
+           "Bump the version as if new data had been assigned (the data already in HBM is kept)")
       .def("assign_device", [](eteq::Variable& self, uintptr_t dev_ptr) { self.assign_device((const void*)dev_ptr); },
            "Assign from a device pointer holding this variable's dtype and element count");
 
