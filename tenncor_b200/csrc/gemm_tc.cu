@@ -1,11 +1,398 @@
-// gemm_tc.cu — tcgen05 (5th-gen tensor core) fp32 GEMM: TF32 and 3xTF32, TMEM accumulators.
-// Placeholder dispatch until the UMMA kernel lands: reports "not handled" so tcr_gemm
-// runs the exact SIMT kernel (still on the device).
+// gemm_tc.cu — fp32 GEMM on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// MATMUL / CONTRACT of the reference (internal/eigen/operator.hpp:1069-1139) for FLOAT
+// operands, in two precisions (BASELINE.json north_star):
+//   TCR_GEMM_TF32    one tcgen05.mma.kind::tf32 pass (operands truncated to 10-bit mantissa)
+//   TCR_GEMM_3XTF32  a = hi + lo split, D += Ahi*Bhi + Ahi*Blo + Alo*Bhi: fp32-grade accuracy
+//                    (relative error ~2^-21 per product) at 3 MMAs per k-step
+//
+// Structure (one 128x128 output tile per CTA, BLOCK_K = 32 fp32 = one 128-byte swizzle row):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d into a ring of smem stages (SWIZZLE_128B),
+//               arming full[s] with the expected byte count
+//   warp 1      allocates TMEM (128 fp32 columns); one elected lane issues tcgen05.mma from
+//               shared-memory descriptors into the TMEM accumulator; tcgen05.commit frees the
+//               stage (empty[s]) and finally signals the epilogue (tmem_full)
+//   warps 2-5   3xTF32 only: split each landed tile into hi (in place) and lo (second buffer),
+//               fence.proxy.async, arrive on ready[s]; then all four run the epilogue:
+//               tcgen05.ld 32 lanes x 32 columns -> bias / activation -> global stores
+// Both operand majors are supported through the UMMA descriptors (K-major and MN-major), so
+// the NN / TN / NT / TT variants produced by the backward contractions
+// (tenncor/eteq/backprop.hpp:269-359) need no transposes.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace tcr {
-int gemm_tc_dispatch(const void*, const void*, void*, const tcr_gemm_desc*, bool* handled) {
-  *handled = false;
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int TILE_BYTES = BM * BK * 4;  // 16 KiB (A tile == B tile)
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 28;  // bounded waits: a protocol bug traps instead of hanging the GPU
+
+struct TcParams {
+  int64_t m, n, k;
+  int64_t c_sm, c_sn;
+  float* c;
+  const float* bias;
+  int epilogue, activation, accumulate;
+  int a_mn_major, b_mn_major;  // 0: K-major (K contiguous), 1: MN-major (M / N contiguous)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address [0,14), leading
+// byte offset [16,30), stride byte offset [32,46) — all >> 4 —, version = 1 at [46,48),
+// layout type SWIZZLE_128B = 2 at [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate
+__device__ __forceinline__ uint32_t make_idesc(int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                          // c_format = F32
+  d |= 2u << 7;                          // a_format = TF32
+  d |= 2u << 10;                         // b_format = TF32
+  d |= (uint32_t)(a_mn_major & 1) << 15; // a_major
+  d |= (uint32_t)(b_mn_major & 1) << 16; // b_major
+  d |= (uint32_t)(BN >> 3) << 17;        // n_dim
+  d |= (uint32_t)(BM >> 4) << 24;        // m_dim
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float act_f(int act, float x) {
+  if (act == TCR_EW_SIGMOID) return 1.0f / (1.0f + expf(-x));
+  if (act == TCR_EW_TANH) return tanhf(x);
+  return x;
+}
+
+// MODE 1: TF32 (STAGES x 32 KiB), MODE 2: 3xTF32 (STAGES x 64 KiB)
+template <int MODE, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024-byte alignment
+  constexpr int STAGE_BYTES = (MODE == 2 ? 4 : 2) * TILE_BYTES;
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* ready = bars + 2 * STAGES;
+  uint64_t* tmem_full = bars + 3 * STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const int num_kb = (int)((p.k + BK - 1) / BK);
+
+  auto tile_a = [&](int s) { return smem + s * STAGE_BYTES; };
+  auto tile_b = [&](int s) { return smem + s * STAGE_BYTES + TILE_BYTES; };
+  auto tile_a_lo = [&](int s) { return smem + s * STAGE_BYTES + 2 * TILE_BYTES; };
+  auto tile_b_lo = [&](int s) { return smem + s * STAGE_BYTES + 3 * TILE_BYTES; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&ready[s], 4);  // one arrival per converter warp
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t round = kb / STAGES;
+        if (kb >= STAGES) mbar_wait(&empty[s], (round - 1) & 1);
+        mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+        const int32_t k0 = kb * BK;
+        if (!p.a_mn_major) {
+          tma_load_2d(&map_a, &full[s], tile_a(s), k0, (int32_t)m0);  // [128 rows][32 k]
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_2d(&map_a, &full[s], tile_a(s) + j * 4096, (int32_t)m0 + 32 * j, k0);  // 4 x [32 k][32 m]
+        }
+        if (!p.b_mn_major) {
+          tma_load_2d(&map_b, &full[s], tile_b(s), k0, (int32_t)n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_2d(&map_b, &full[s], tile_b(s) + j * 4096, (int32_t)n0 + 32 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.a_mn_major, p.b_mn_major);
+      // K-major: rows of 128 B, 8-row groups 1024 B apart; one MMA consumes 8 k = 32 B of each row.
+      // MN-major: 32-element (128 B) chunks along M/N 4096 B apart (LBO), 8-k groups 1024 B apart (SBO);
+      //           one MMA consumes one 8-k group = 1024 B.
+      const uint32_t a_lbo = p.a_mn_major ? 4096 : 16, a_sbo = 1024, a_kstep = p.a_mn_major ? 1024 : 32;
+      const uint32_t b_lbo = p.b_mn_major ? 4096 : 16, b_sbo = 1024, b_kstep = p.b_mn_major ? 1024 : 32;
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t round = kb / STAGES;
+        mbar_wait(MODE == 2 ? &ready[s] : &full[s], round & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(tile_a(s)), b_addr = smem_u32(tile_b(s));
+#pragma unroll
+        for (int k8 = 0; k8 < BK / 8; ++k8) {
+          const uint64_t da = make_desc(a_addr + k8 * a_kstep, a_lbo, a_sbo);
+          const uint64_t db = make_desc(b_addr + k8 * b_kstep, b_lbo, b_sbo);
+          if (MODE == 2) {
+            const uint64_t da_lo = make_desc(a_addr + 2 * TILE_BYTES + k8 * a_kstep, a_lbo, a_sbo);
+            const uint64_t db_lo = make_desc(b_addr + 2 * TILE_BYTES + k8 * b_kstep, b_lbo, b_sbo);
+            umma_tf32(tmem_base, da_lo, db, idesc, accumulate);  // small terms first
+            umma_tf32(tmem_base, da, db_lo, idesc, 1);
+            umma_tf32(tmem_base, da, db, idesc, 1);
+          } else {
+            umma_tf32(tmem_base, da, db, idesc, accumulate);
+          }
+          accumulate = 1;
+        }
+        umma_commit(&empty[s]);  // stage is reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ================= converter (3xTF32) + epilogue: warps 2..5 =================
+    const int ct = threadIdx.x - 64;  // 0..127
+    if (MODE == 2) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t round = kb / STAGES;
+        mbar_wait(&full[s], round & 1);
+        // hi/lo split is elementwise, so the swizzle is irrelevant: A and B tiles are adjacent (32 KiB)
+        uint4* src = reinterpret_cast<uint4*>(tile_a(s));
+        uint4* dlo = reinterpret_cast<uint4*>(tile_a_lo(s));
+#pragma unroll 4
+        for (int i = ct; i < 2 * TILE_BYTES / 16; i += 128) {
+          uint4 v = src[i], hi, lo;
+          const uint32_t* x = reinterpret_cast<const uint32_t*>(&v);
+          uint32_t* h = reinterpret_cast<uint32_t*>(&hi);
+          uint32_t* l = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(__uint_as_float(x[e])));
+            h[e] = hb;
+            l[e] = __float_as_uint(__uint_as_float(x[e]) - __uint_as_float(hb));
+          }
+          src[i] = hi;
+          dlo[i] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);
+      }
+    }
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int64_t m = m0 + 32 * q + lane;
+    const bool m_ok = m < p.m;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores of the previous chunk
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int64_t nb = n0 + c * 32;
+      if (!m_ok || nb >= p.n) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]);
+        const int64_t n = nb + j;
+        if (n < p.n) {
+          if (p.accumulate) x += p.c[m * p.c_sm + n * p.c_sn];
+          if (p.epilogue == TCR_EPI_BIAS_N) x += p.bias[n];
+          else if (p.epilogue == TCR_EPI_BIAS_M) x += p.bias[m];
+          if (p.activation) x = act_f(p.activation, x);
+        }
+        v[j] = x;
+      }
+      float* row = p.c + m * p.c_sm + nb * p.c_sn;
+      if (p.c_sn == 1 && nb + 32 <= p.n && (((uintptr_t)row) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(row + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < p.n) row[j * p.c_sn] = v[j];
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    // resolved through the runtime so that the library loads on machines without libcuda.so
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: dim0 = contiguous extent, dim1 = strided extent (pitch in elements)
+int make_map(CUtensorMap* map, const float* base, int64_t dim0, int64_t dim1, int64_t pitch, uint32_t box0, uint32_t box1) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return TCR_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for dims %lld x %lld pitch %lld", (int)r, (long long)dim0, (long long)dim1, (long long)pitch);
+    return TCR_ERR_CUDA;
+  }
   return TCR_OK;
 }
+
+template <int MODE, int STAGES>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p) {
+  constexpr int STAGE_BYTES = (MODE == 2 ? 4 : 2) * TILE_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static bool configured = false;
+  if (!configured) {
+    TCR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(p.n, BN), (unsigned)ceil_div(p.m, BM));
+  TCR_LAUNCH((gemm_tc_kernel<MODE, STAGES>), grid, NUM_THREADS, SMEM, ma, mb, p);
+  TCR_CHECK_LAUNCH();
+  return TCR_OK;
+}
+
+}  // namespace
+
+int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc* d, bool* handled) {
+  *handled = false;
+  if (d->dtype != TCR_FLOAT || d->k <= 0) return TCR_OK;
+  // tiny problems do not fill a 128x128 tile: the SIMT kernel is faster and exact
+  if (d->m * d->n < 64 * 64 || d->k < 16 || d->m * d->n * d->k < (1ll << 20)) return TCR_OK;
+  if (d->batch > 16) return TCR_OK;
+  const bool a_k = d->a_sk == 1 || d->k == 1, a_m = d->a_sm == 1 || d->m == 1;
+  const bool b_k = d->b_sk == 1 || d->k == 1, b_n = d->b_sn == 1 || d->n == 1;
+  if (!(a_k || a_m) || !(b_k || b_n)) return TCR_OK;
+  const int a_mn = !(d->a_sk == 1) && a_m ? 1 : (a_k ? 0 : 1);
+  const int b_mn = !(d->b_sk == 1) && b_n ? 1 : (b_k ? 0 : 1);
+  const int64_t a_pitch = a_mn ? d->a_sk : d->a_sm, b_pitch = b_mn ? d->b_sk : d->b_sn;
+  // TMA: 16-byte aligned base and pitch
+  auto ok16 = [](const void* ptr, int64_t pitch) { return (((uintptr_t)ptr) & 15) == 0 && pitch > 0 && (pitch % 4) == 0; };
+  if (!ok16(a, a_pitch) || !ok16(b, b_pitch)) return TCR_OK;
+  if ((d->a_sb % 4) != 0 || (d->b_sb % 4) != 0) return TCR_OK;
+  if (a_pitch < (a_mn ? d->m : d->k) || b_pitch < (b_mn ? d->n : d->k)) return TCR_OK;
+
+  for (int64_t bi = 0; bi < d->batch; ++bi) {
+    const float* ap = (const float*)a + bi * d->a_sb;
+    const float* bp = (const float*)b + bi * d->b_sb;
+    CUtensorMap ma, mb;
+    int rc;
+    // K-major: dims {K, rows}, box {32 k, 128 rows};  MN-major: dims {cols, K}, box {32 cols, 32 k}
+    rc = a_mn ? make_map(&ma, ap, d->m, d->k, a_pitch, 32, 32) : make_map(&ma, ap, d->k, d->m, a_pitch, 32, 128);
+    if (rc) return rc;
+    rc = b_mn ? make_map(&mb, bp, d->n, d->k, b_pitch, 32, 32) : make_map(&mb, bp, d->k, d->n, b_pitch, 32, 128);
+    if (rc) return rc;
+    TcParams p;
+    p.m = d->m; p.n = d->n; p.k = d->k;
+    p.c_sm = d->c_sm; p.c_sn = d->c_sn;
+    p.c = (float*)c + bi * d->c_sb;
+    p.bias = (const float*)d->bias;
+    p.epilogue = d->epilogue; p.activation = d->activation; p.accumulate = d->accumulate;
+    p.a_mn_major = a_mn; p.b_mn_major = b_mn;
+    rc = d->precision == TCR_GEMM_TF32 ? launch_tc<1, 6>(ma, mb, p) : launch_tc<2, 3>(ma, mb, p);
+    if (rc) return rc;
+  }
+  *handled = true;
+  return TCR_OK;
+}
+
 }  // namespace tcr
