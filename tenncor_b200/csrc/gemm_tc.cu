@@ -76,14 +76,16 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address [0,14), leading
 // byte offset [16,30), stride byte offset [32,46) — all >> 4 —, version = 1 at [46,48),
-// layout type SWIZZLE_128B = 2 at [61,64)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout type at [61,64): SWIZZLE_128B = 2 (K-major tiles), SWIZZLE_128B_BASE32B = 1 (the only
+// swizzled layout the hardware accepts for MN-major tf32 operands; TMA writes it with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout_type & 7) << 61;
   return d;
 }
 
@@ -187,11 +189,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.a_mn_major, p.b_mn_major);
-      // K-major: rows of 128 B, 8-row groups 1024 B apart; one MMA consumes 8 k = 32 B of each row.
-      // MN-major: 32-element (128 B) chunks along M/N 4096 B apart (LBO), 8-k groups 1024 B apart (SBO);
-      //           one MMA consumes one 8-k group = 1024 B.
-      const uint32_t a_lbo = p.a_mn_major ? 4096 : 16, a_sbo = 1024, a_kstep = p.a_mn_major ? 1024 : 32;
-      const uint32_t b_lbo = p.b_mn_major ? 4096 : 16, b_sbo = 1024, b_kstep = p.b_mn_major ? 1024 : 32;
+      // K-major (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO); one MMA consumes
+      //   8 k = 32 B of each row.
+      // MN-major (SWIZZLE_128B_BASE32B): k-rows of 128 B holding 32 consecutive m/n; the swizzle atom is
+      //   4 k-rows (512 B, SBO); 32-element chunks along M/N are 4096 B apart (LBO); one MMA consumes
+      //   8 k-rows = 1024 B.
+      const uint32_t a_lbo = p.a_mn_major ? 4096 : 16, a_sbo = p.a_mn_major ? 512 : 1024, a_kstep = p.a_mn_major ? 1024 : 32;
+      const uint32_t b_lbo = p.b_mn_major ? 4096 : 16, b_sbo = p.b_mn_major ? 512 : 1024, b_kstep = p.b_mn_major ? 1024 : 32;
+      const uint32_t a_lt = p.a_mn_major ? 1 : 2, b_lt = p.b_mn_major ? 1 : 2;
       uint32_t accumulate = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
@@ -201,11 +206,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t a_addr = smem_u32(tile_a(s)), b_addr = smem_u32(tile_b(s));
 #pragma unroll
         for (int k8 = 0; k8 < BK / 8; ++k8) {
-          const uint64_t da = make_desc(a_addr + k8 * a_kstep, a_lbo, a_sbo);
-          const uint64_t db = make_desc(b_addr + k8 * b_kstep, b_lbo, b_sbo);
+          const uint64_t da = make_desc(a_addr + k8 * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t db = make_desc(b_addr + k8 * b_kstep, b_lbo, b_sbo, b_lt);
           if (MODE == 2) {
-            const uint64_t da_lo = make_desc(a_addr + 2 * TILE_BYTES + k8 * a_kstep, a_lbo, a_sbo);
-            const uint64_t db_lo = make_desc(b_addr + 2 * TILE_BYTES + k8 * b_kstep, b_lbo, b_sbo);
+            const uint64_t da_lo = make_desc(a_addr + 2 * TILE_BYTES + k8 * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t db_lo = make_desc(b_addr + 2 * TILE_BYTES + k8 * b_kstep, b_lbo, b_sbo, b_lt);
             umma_tf32(tmem_base, da_lo, db, idesc, accumulate);  // small terms first
             umma_tf32(tmem_base, da, db_lo, idesc, 1);
             umma_tf32(tmem_base, da, db, idesc, 1);
@@ -317,7 +322,7 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 tensor map: dim0 = contiguous extent, dim1 = strided extent (pitch in elements)
-int make_map(CUtensorMap* map, const float* base, int64_t dim0, int64_t dim1, int64_t pitch, uint32_t box0, uint32_t box1) {
+int make_map(CUtensorMap* map, const float* base, int64_t dim0, int64_t dim1, int64_t pitch, uint32_t box0, uint32_t box1, bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -328,7 +333,7 @@ int make_map(CUtensorMap* map, const float* base, int64_t dim0, int64_t dim1, in
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for dims %lld x %lld pitch %lld", (int)r, (long long)dim0, (long long)dim1, (long long)pitch);
     return TCR_ERR_CUDA;
@@ -377,9 +382,9 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
     CUtensorMap ma, mb;
     int rc;
     // K-major: dims {K, rows}, box {32 k, 128 rows};  MN-major: dims {cols, K}, box {32 cols, 32 k}
-    rc = a_mn ? make_map(&ma, ap, d->m, d->k, a_pitch, 32, 32) : make_map(&ma, ap, d->k, d->m, a_pitch, 32, 128);
+    rc = a_mn ? make_map(&ma, ap, d->m, d->k, a_pitch, 32, 32, true) : make_map(&ma, ap, d->k, d->m, a_pitch, 32, 128, false);
     if (rc) return rc;
-    rc = b_mn ? make_map(&mb, bp, d->n, d->k, b_pitch, 32, 32) : make_map(&mb, bp, d->k, d->n, b_pitch, 32, 128);
+    rc = b_mn ? make_map(&mb, bp, d->n, d->k, b_pitch, 32, 32, true) : make_map(&mb, bp, d->k, d->n, b_pitch, 32, 128, false);
     if (rc) return rc;
     TcParams p;
     p.m = d->m; p.n = d->n; p.k = d->k;

@@ -13,7 +13,11 @@ void* DeviceRuntimeMemory::allocate(size_t size) {
   return p;
 }
 
-void DeviceRuntimeMemory::deallocate(void* ptr, size_t) { cuda::check(tcr_free(ptr), "tcr_free"); }
+void DeviceRuntimeMemory::deallocate(void* ptr, size_t) {
+  // never throws: holders and plans are also destroyed during interpreter shutdown, after the
+  // library's arena bookkeeping may already be gone
+  tcr_free(ptr);
+}
 
 static RTMemptrT& runtime_slot() {
   static RTMemptrT slot = std::make_shared<DeviceRuntimeMemory>();

@@ -172,6 +172,9 @@ struct DevOp final : public eigen::iEigen {
   void mark_device_dirty() override { mirror_.invalidate(); }
   /// bind an externally produced result (used by the plan executor for target nodes)
   void* ensure_buffer(size_t ttl, eigen::RTMemptrT& runtime);
+  /// run this op's kernel(s) on explicit buffers (plan executor: buffers come from the plan)
+  void launch_with(void* out, const std::vector<const void*>& in) const { launch_(out, in); }
+  size_t out_bytes() const { return bytes_; }
 
  private:
   size_t bytes_;
@@ -218,6 +221,9 @@ struct DevAssign final : public eigen::iEigen {
   void assign(size_t ttl, eigen::RTMemptrT&) override;
   bool valid_for(size_t desired_ttl) const override { return desired_ttl <= ref_ttl_; }
   void extend_life(size_t ttl) override { if (ref_ttl_ < ttl) ref_ttl_ = ttl; }
+  egen::_GENERATED_OPCODE opcode() const { return op_; }
+  teq::iTensor* target() const { return ref_; }
+  const teq::iTensor* source() const { return arg_; }
 
  private:
   void tick() const {

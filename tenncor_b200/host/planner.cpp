@@ -1,19 +1,693 @@
-// planner.cpp — (stage 1) delegates to the node-by-node evaluator; the fused plan lands next.
+// planner.cpp — lowers a functor DAG to a fused launch plan and replays it as a CUDA graph.
+// See planner.hpp for the design; reference hot loop being replaced:
+// teq::TravEvaluator::visit_func (internal/teq/evaluator.hpp:34-43) + eigen::Device::calc
+// (internal/eigen/device.hpp:555-570) + TensOp::assign (device.hpp:304-328).
 #include "planner.hpp"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace cuda {
+
+using namespace teq;
+using namespace egen;
 
 static PlanStats g_stats;
 PlanStats last_plan_stats() { return g_stats; }
 
-struct PlanCache {};
+namespace {
+
+constexpr int MAX_IN = TCR_EW_MAX_INPUTS, MAX_INSTR = TCR_EW_MAX_INSTRS, NREGS = TCR_EW_NREGS;
+
+bool is_unary(int op) { return op >= ABS && op <= CUBE; }
+bool is_binary(int op) { return op == POW || op == SUB || op == DIV || op == MIN || op == MAX || op == EQ || op == NEQ || op == LT || op == GT; }
+bool is_assign(int op) { return op >= ASSIGN && op <= ASSIGN_DIV; }
+bool is_ew_op(int op) { return is_unary(op) || is_binary(op) || op == ADD || op == MUL || op == SELECT || op == CAST || is_assign(op); }
+bool has_compute_kernels(_GENERATED_DTYPE t) { return t == FLOAT || t == DOUBLE || t == INT32 || t == INT64; }
+
+struct PNode {
+  iTensor* tens = nullptr;
+  iFunctor* func = nullptr;  // null: leaf (or ignored functor treated as a leaf)
+  eigen::iEigen* holder = nullptr;
+  int op = 0;
+  _GENERATED_DTYPE dtype = BAD_TYPE;
+  Shape shape;
+  int64_t n = 1;
+  std::vector<int> args;
+  int root = -1;          // storage base node (self unless a view / assign alias)
+  size_t offset = 0;      // byte offset into the base node's buffer
+  std::vector<int> consumers;
+  bool exposed = false, inlined = false, is_view = false, is_ew = false, is_extend = false, needs_mat = false;
+  bool has_scalar = false;  // value is one scalar known at plan time (constant leaf / EXTEND of one)
+  double scalar = 0;
+  bool mutable_leaf = false;
+  void* ptr = nullptr;
+  int step = -1;
+  int region = -1;  // root node of the EW region this node is computed in
+};
+
+struct InputRef {
+  int node;       // base node whose buffer is read
+  size_t offset;  // byte offset
+  uint32_t mask;  // ranks (of the region root's shape) along which the input is broadcast
+  _GENERATED_DTYPE dtype;
+  bool operator==(const InputRef& o) const { return node == o.node && offset == o.offset && mask == o.mask; }
+};
+
+struct Expr {
+  int kind;  // 0 input, 1 const, 2 op
+  int op = 0, a = -1, b = -1, c = -1, input = -1;
+  double imm = 0;
+  int uses = 0, reg = -1;
+  bool emitted = false;
+};
+
+struct Step {
+  bool ew = false;
+  // ew
+  tcr_ew_program prog;
+  std::vector<InputRef> inputs;
+  int out_node = -1;
+  // launch
+  const DevOp* holder = nullptr;
+  void* out = nullptr;
+  std::vector<const void*> in;
+  std::vector<int> in_nodes;
+  std::vector<size_t> in_offsets;
+};
+
+}  // namespace
+
+struct Plan {
+  std::vector<PNode> nodes;
+  std::vector<Step> steps;
+  std::vector<std::weak_ptr<iTensor>> target_refs;
+  std::vector<iTensor*> target_keys;
+  std::vector<int> functor_order;  // indices of functor nodes in evaluation order
+  std::vector<std::pair<void*, size_t>> owned;  // plan-owned device buffers
+  std::vector<std::pair<int, void*>> bound;     // (node, pointer) of holder / leaf buffers baked into the plan
+  eigen::RTMemptrT memory;
+  void* graph = nullptr;
+  bool use_graph = false, has_run = false, always_run = false;
+  int precision = 0;
+  size_t n_launch_steps = 0;
+
+  ~Plan() {
+    if (graph) tcr_graph_destroy(graph);
+    for (auto& b : owned) memory->deallocate(b.first, b.second);
+  }
+
+  // ---------------------------------------------------------------- graph collection
+  std::unordered_map<iTensor*, int> index;
+
+  int collect(iTensor* t, const TensSetT& ignored) {
+    auto it = index.find(t);
+    if (it != index.end()) return it->second;
+    PNode n;
+    n.tens = t;
+    n.dtype = (_GENERATED_DTYPE)t->get_meta().type_code();
+    n.shape = t->shape();
+    n.n = (int64_t)n.shape.n_elems();
+    auto f = dynamic_cast<iFunctor*>(t);
+    if (f && !ignored.count(t)) {
+      for (auto& a : f->args_ref()) n.args.push_back(collect(a.get(), ignored));
+      n.func = f;
+      n.op = (int)f->get_opcode().code_;
+      n.holder = &static_cast<eigen::iEigen&>(f->device());
+    } else {
+      if (auto c = dynamic_cast<eteq::Constant*>(t)) {
+        n.has_scalar = c->is_scalar();
+        n.scalar = c->scalar_value();
+      }
+      n.mutable_leaf = nullptr != dynamic_cast<eigen::iMutableLeaf*>(t);
+    }
+    int id = (int)nodes.size();
+    n.root = id;
+    nodes.push_back(std::move(n));
+    index.emplace(t, id);
+    if (nodes[id].func) functor_order.push_back(id);
+    return id;
+  }
+
+  std::pair<int, size_t> base(int i) const { return {nodes[i].root, nodes[i].offset}; }
+
+  void resolve_views() {
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      PNode& n = nodes[i];
+      if (!n.func) continue;
+      if (auto ref = dynamic_cast<DevRef*>(n.holder)) {
+        int a = index.at(ref->referent());
+        n.is_view = true;
+        n.root = nodes[a].root;
+        n.offset = nodes[a].offset + ref->byte_offset();
+        if (nodes[a].has_scalar && ref->byte_offset() == 0) { n.has_scalar = true; n.scalar = nodes[a].scalar; }
+      } else if (dynamic_cast<DevAssign*>(n.holder)) {
+        n.is_ew = true;  // computed by an EW program writing the variable's storage; consumers read the variable
+      } else if (n.op == EXTEND) {
+        n.is_extend = true;
+        const PNode& src = nodes[n.args[0]];
+        if (src.has_scalar) { n.has_scalar = true; n.scalar = src.scalar; }
+      } else if (is_ew_op(n.op) && has_compute_kernels(n.dtype)) {
+        n.is_ew = true;
+        if (n.op == CAST && !has_compute_kernels(nodes[n.args[0]].dtype)) n.is_ew = false;
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- EW regions
+  std::unordered_map<int, std::vector<int>> members;       // region root -> member nodes (incl. root)
+  std::unordered_map<int, std::vector<int>> assign_pos;    // mutable leaf -> positions of ASSIGN nodes writing it
+
+  uint32_t bcast_mask(const Shape& src, const Shape& dst) const {
+    uint32_t m = 0;
+    for (int r = 0; r < rank_cap; ++r)
+      if (dst.at(r) > 1 && src.at(r) == 1) m |= 1u << r;
+    return m;
+  }
+
+  struct Gen {
+    std::vector<Expr> ex;
+    std::vector<InputRef> inputs;
+    std::unordered_map<int, int> memo;  // member node -> expr
+    bool ok = true;
+  };
+
+  int add_input(Gen& g, InputRef ref) {
+    for (size_t k = 0; k < g.inputs.size(); ++k)
+      if (g.inputs[k] == ref) { Expr e; e.kind = 0; e.input = (int)k; g.ex.push_back(e); return (int)g.ex.size() - 1; }
+    if ((int)g.inputs.size() >= MAX_IN) { g.ok = false; return -1; }
+    g.inputs.push_back(ref);
+    Expr e;
+    e.kind = 0;
+    e.input = (int)g.inputs.size() - 1;
+    g.ex.push_back(e);
+    return (int)g.ex.size() - 1;
+  }
+
+  int add_op(Gen& g, int op, int a, int b = -1, int c = -1) {
+    Expr e;
+    e.kind = 2; e.op = op; e.a = a; e.b = b; e.c = c;
+    g.ex.push_back(e);
+    return (int)g.ex.size() - 1;
+  }
+
+  // expression of node `i` as seen by region `root`
+  int build_expr(Gen& g, int root, int i) {
+    if (!g.ok) return -1;
+    const PNode& root_n = nodes[root];
+    const PNode& ni = nodes[i];
+    if (ni.has_scalar && !(i == root)) {
+      Expr e;
+      e.kind = 1;
+      e.imm = ni.scalar;
+      g.ex.push_back(e);
+      return (int)g.ex.size() - 1;
+    }
+    int r = ni.root;
+    size_t off = ni.offset;
+    const PNode& nr = nodes[r];
+    bool member = (r == root && i == root) || (off == 0 && nr.region == root && (nr.inlined || r == root) && !ni.is_view) ||
+                  (off == 0 && ni.is_view && nr.region == root && (nr.inlined));
+    if (r == root && i != root) member = false;  // a consumer inside the region cannot be upstream of the root
+    if (member) {
+      auto it = g.memo.find(r);
+      if (it != g.memo.end()) return it->second;
+      int e = -1;
+      int op = nr.op;
+      if (is_assign(op)) {
+        int var = build_input(g, root, nr.args[0]);
+        int src = build_expr(g, root, nr.args[1]);
+        if (op == ASSIGN) e = add_op(g, TCR_EW_MOV, src);
+        else e = add_op(g, op == ASSIGN_ADD ? ADD : op == ASSIGN_SUB ? SUB : op == ASSIGN_MUL ? MUL : DIV, var, src);
+      } else if (op == CAST) {
+        e = add_op(g, TCR_EW_MOV, build_input(g, root, nr.args[0]));  // conversion happens at load
+      } else if (op == ADD || op == MUL) {
+        e = build_expr(g, root, nr.args[0]);
+        for (size_t k = 1; k < nr.args.size() && g.ok; ++k) e = add_op(g, op, e, build_expr(g, root, nr.args[k]));
+      } else if (op == SELECT) {
+        int a = build_expr(g, root, nr.args[0]), b = build_expr(g, root, nr.args[1]), c = build_expr(g, root, nr.args[2]);
+        e = add_op(g, TCR_EW_SELECT, a, b, c);
+      } else if (is_unary(op)) {
+        e = add_op(g, op, build_expr(g, root, nr.args[0]));
+      } else {
+        int a = build_expr(g, root, nr.args[0]), b = build_expr(g, root, nr.args[1]);
+        e = add_op(g, op, a, b);
+      }
+      g.memo.emplace(r, e);
+      (void)root_n;
+      return e;
+    }
+    return build_input(g, root, i);
+  }
+
+  int build_input(Gen& g, int root, int i) {
+    const PNode& ni = nodes[i];
+    const PNode& root_n = nodes[root];
+    // broadcast read through an EXTEND that nobody needs materialised
+    if (ni.is_extend && !ni.needs_mat && ni.shape == root_n.shape) {
+      const PNode& src = nodes[ni.args[0]];
+      return add_input(g, InputRef{src.root, src.offset, bcast_mask(src.shape, root_n.shape), src.dtype});
+    }
+    if (ni.n != root_n.n) { g.ok = false; return -1; }
+    return add_input(g, InputRef{ni.root, ni.offset, 0, ni.dtype});
+  }
+
+  // register allocation + instruction emission; fills `step`
+  bool emit(Gen& g, int root, int root_expr, Step& step) {
+    if (!g.ok) return false;
+    const PNode& rn = nodes[root];
+    // iteration-space split shared by every broadcast input (<= 3 segments)
+    int64_t dims[3] = {1, 1, 1};
+    int seg_of_rank[rank_cap];
+    {
+      int seg = -1;
+      uint32_t prev_sig = 0;
+      bool first = true;
+      for (int r = 0; r < rank_cap; ++r) {
+        seg_of_rank[r] = seg < 0 ? 0 : seg;
+        if (rn.shape.at(r) == 1) continue;
+        uint32_t sig = 0;
+        for (size_t k = 0; k < g.inputs.size(); ++k) sig |= ((g.inputs[k].mask >> r) & 1u) << k;
+        if (first || sig != prev_sig) { ++seg; first = false; prev_sig = sig; }
+        if (seg >= 3) return false;
+        seg_of_rank[r] = seg;
+        dims[seg] *= rn.shape.at(r);
+      }
+    }
+    // use counts
+    std::vector<int> order;
+    std::function<void(int)> count = [&](int e) {
+      Expr& x = g.ex[e];
+      x.uses++;
+      if (x.uses > 1) return;
+      if (x.kind == 2) { count(x.a); if (x.b >= 0) count(x.b); if (x.c >= 0) count(x.c); }
+      order.push_back(e);
+    };
+    count(root_expr);
+    int owner[NREGS];
+    for (int r = 0; r < NREGS; ++r) owner[r] = -1;
+    // an input expr may appear several times (deduped inputs share a register)
+    std::vector<int> input_uses(g.inputs.size(), 0);
+    for (int e : order)
+      if (g.ex[e].kind == 0) input_uses[g.ex[e].input] += g.ex[e].uses;
+    for (size_t k = 0; k < g.inputs.size(); ++k) owner[k] = 1000 + (int)k;  // held by input k
+    std::memset(&step.prog, 0, sizeof(step.prog));
+    tcr_ew_program& p = step.prog;
+    int ninstr = 0;
+    auto release = [&](int e) {
+      Expr& x = g.ex[e];
+      if (x.kind == 0) {
+        if (--input_uses[x.input] == 0) owner[x.input] = -1;
+      } else if (--x.uses == 0) {
+        owner[x.reg] = -1;
+      }
+    };
+    auto reg_of = [&](int e) { return g.ex[e].kind == 0 ? g.ex[e].input : g.ex[e].reg; };
+    for (int e : order) {
+      Expr& x = g.ex[e];
+      if (x.kind == 0) continue;
+      int ra = 0, rb = 0, rc = 0;
+      if (x.kind == 2) {
+        ra = reg_of(x.a);
+        if (x.b >= 0) rb = reg_of(x.b);
+        if (x.c >= 0) rc = reg_of(x.c);
+        release(x.a);
+        if (x.b >= 0) release(x.b);
+        if (x.c >= 0) release(x.c);
+      }
+      int dst = -1;
+      for (int r = 0; r < NREGS; ++r)
+        if (owner[r] == -1) { dst = r; break; }
+      if (dst < 0 || ninstr >= MAX_INSTR) return false;
+      owner[dst] = e;
+      x.reg = dst;
+      tcr_ew_instr& ins = p.instrs[ninstr++];
+      ins.op = (uint8_t)(x.kind == 1 ? TCR_EW_CONST : x.op);
+      ins.dst = (uint8_t)dst;
+      ins.a = (uint8_t)ra; ins.b = (uint8_t)rb; ins.c = (uint8_t)rc;
+      ins.imm = x.imm;
+    }
+    p.dtype = rn.op == CAST ? nodes[rn.args[0]].dtype : rn.dtype;
+    if (is_assign(rn.op)) p.dtype = rn.dtype;
+    if (!has_compute_kernels((_GENERATED_DTYPE)p.dtype)) return false;
+    // a CAST root converts at load: compute in the OUTPUT type so that the store is a plain copy
+    if (rn.op == CAST) p.dtype = rn.dtype;
+    p.n_inputs = (int)g.inputs.size();
+    p.n_outputs = 1;
+    p.n_instrs = ninstr;
+    for (int k = 0; k < 3; ++k) p.dims[k] = dims[k];
+    for (size_t k = 0; k < g.inputs.size(); ++k) {
+      p.inputs[k].dtype = g.inputs[k].dtype;
+      for (int r = 0; r < rank_cap; ++r)
+        if (rn.shape.at(r) > 1 && ((g.inputs[k].mask >> r) & 1u)) p.inputs[k].bcast[seg_of_rank[r]] = 1;
+    }
+    p.outputs[0].dtype = rn.dtype;
+    p.outputs[0].reg = (uint8_t)reg_of(root_expr);
+    step.inputs = g.inputs;
+    step.out_node = root;
+    step.ew = true;
+    return true;
+  }
+
+  bool try_region(int root, Step& step) {
+    Gen g;
+    int e = build_expr(g, root, root);
+    return emit(g, root, e, step);
+  }
+
+  // would moving region `a` (first evaluated at first_pos) to position `to` cross an ASSIGN of a leaf it reads?
+  bool crosses_assign(int a_root, int to) {
+    int first_pos = a_root;
+    for (int m : members[a_root]) first_pos = std::min(first_pos, m);
+    for (int m : members[a_root]) {
+      for (int arg : nodes[m].args) {
+        int leaf = nodes[arg].root;
+        if (nodes[arg].is_extend) leaf = nodes[nodes[arg].args[0]].root;
+        auto it = assign_pos.find(leaf);
+        if (it == assign_pos.end()) continue;
+        for (int pos : it->second)
+          if (pos > first_pos && pos < to) return true;
+      }
+    }
+    return false;
+  }
+
+  void fuse() {
+    for (size_t i = 0; i < nodes.size(); ++i)
+      if (nodes[i].func && is_assign(nodes[i].op)) assign_pos[nodes[nodes[i].args[0]].root].push_back((int)i);
+    // consumers (on storage roots); EXTENDs are looked through later
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      PNode& n = nodes[i];
+      if (!n.func || n.is_view) continue;
+      for (int a : n.args) nodes[nodes[a].root].consumers.push_back((int)i);
+    }
+    // non-EW consumers need real buffers: EXTEND operands get materialised. An EW node that cannot
+    // be lowered on its own (too many operands / broadcast segments) is demoted to its holder's
+    // kernel, which changes what its operands need — iterate to a fixed point.
+    for (bool changed = true; changed;) {
+      changed = false;
+      for (auto& n : nodes) n.needs_mat = false;
+      for (size_t i = 0; i < nodes.size(); ++i) {
+        PNode& n = nodes[i];
+        if (!n.func || n.is_view) continue;
+        bool ew_consumer = n.is_ew;
+        for (size_t k = 0; k < n.args.size(); ++k) {
+          PNode& a = nodes[nodes[n.args[k]].root];
+          if (!a.is_extend) continue;
+          bool as_bcast = ew_consumer && a.shape == n.shape && nodes[n.args[k]].offset == 0 && !(is_assign(n.op) && k == 0);
+          if (!as_bcast && !a.has_scalar) a.needs_mat = true;
+          if (!as_bcast && a.has_scalar && !ew_consumer) a.needs_mat = true;
+        }
+      }
+      for (size_t i = 0; i < nodes.size(); ++i)
+        if (nodes[i].is_extend && nodes[i].exposed) nodes[i].needs_mat = true;
+      for (size_t i = 0; i < nodes.size(); ++i) {
+        PNode& x = nodes[i];
+        if (!x.is_ew || is_assign(x.op)) continue;
+        x.region = (int)i;
+        Step scratch;
+        bool ok = try_region((int)i, scratch);
+        x.region = -1;
+        if (!ok) {
+          x.is_ew = false;
+          changed = true;
+        }
+      }
+    }
+    // greedy inlining in evaluation order
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      PNode& x = nodes[i];
+      if (!x.is_ew) continue;
+      x.region = (int)i;
+      members[(int)i] = {(int)i};
+      Step scratch;
+      for (size_t k = 0; k < x.args.size(); ++k) {
+        if (is_assign(x.op) && k == 0) continue;  // the variable itself
+        if (x.op == CAST) continue;
+        int ai = x.args[k];
+        if (nodes[ai].offset != 0) continue;
+        int a = nodes[ai].root;
+        PNode& an = nodes[a];
+        if (!an.is_ew || an.inlined || an.exposed || is_assign(an.op) || an.region != a) continue;
+        if (an.consumers.size() != 1 || an.n != x.n || an.dtype != x.dtype) continue;
+        if (an.op == CAST) continue;
+        if (crosses_assign(a, (int)i)) continue;
+        // tentatively merge
+        std::vector<int> moved = members[a];
+        for (int m : moved) nodes[m].region = (int)i;
+        an.inlined = true;
+        if (try_region((int)i, scratch)) {
+          auto& mine = members[(int)i];
+          mine.insert(mine.end(), moved.begin(), moved.end());
+          members.erase(a);
+        } else {
+          for (int m : moved) nodes[m].region = a;
+          an.inlined = false;
+        }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- steps + buffers
+  void* alloc_owned(size_t bytes) {
+    void* p = memory->allocate(bytes);
+    owned.push_back({p, bytes});
+    return p;
+  }
+
+  void build_steps() {
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      PNode& n = nodes[i];
+      if (!n.func || n.is_view || n.inlined) continue;
+      if (n.is_extend && !n.needs_mat) continue;
+      Step st;
+      if (n.is_ew && try_region((int)i, st)) {
+        n.step = (int)steps.size();
+        steps.push_back(std::move(st));
+        continue;
+      }
+      if (is_assign(n.op)) global::fatalf("planner: cannot lower %s", n.tens->to_string().c_str());
+      auto op = dynamic_cast<DevOp*>(n.holder);
+      if (!op) global::fatalf("planner: %s has no launchable holder", n.tens->to_string().c_str());
+      st.ew = false;
+      st.holder = op;
+      st.out_node = (int)i;
+      for (int a : n.args) {
+        if (n.op == IDENTITY && !st.in_nodes.empty()) break;  // all-reduce marker: operational deps are not data
+        st.in_nodes.push_back(nodes[a].root);
+        st.in_offsets.push_back(nodes[a].offset);
+      }
+      n.step = (int)steps.size();
+      steps.push_back(std::move(st));
+    }
+  }
+
+  void* leaf_ptr(PNode& n) {
+    void* p = n.tens->device().device_data();
+    if (!p) global::fatalf("planner: %s has no data", n.tens->to_string().c_str());
+    bound.push_back({(int)(&n - nodes.data()), p});
+    return p;
+  }
+
+  void assign_buffers() {
+    // last step that reads each base node
+    std::vector<int> last_use(nodes.size(), -1);
+    for (size_t s = 0; s < steps.size(); ++s) {
+      Step& st = steps[s];
+      if (st.ew) for (auto& in : st.inputs) last_use[in.node] = (int)s;
+      else for (int in : st.in_nodes) last_use[in] = (int)s;
+    }
+    for (auto& n : nodes)
+      if (!n.func) n.ptr = leaf_ptr(n);
+    std::multimap<size_t, void*> pool;  // plan-local free list: buffers are reused once their last reader has run
+    std::vector<std::vector<int>> dying(steps.size());
+    for (size_t s = 0; s < steps.size(); ++s) {
+      Step& st = steps[s];
+      PNode& out = nodes[st.out_node];
+      if (is_assign(out.op)) {
+        out.ptr = nodes[nodes[out.args[0]].root].ptr;  // variable storage
+        out.root = nodes[out.args[0]].root;
+      } else if (out.exposed) {
+        auto op = dynamic_cast<DevOp*>(out.holder);
+        if (!op) global::fatalf("planner: target %s cannot hold data", out.tens->to_string().c_str());
+        out.ptr = op->ensure_buffer(1, memory);
+        bound.push_back({st.out_node, out.ptr});
+      } else {
+        size_t bytes = (size_t)out.n * type_size(out.dtype);
+        size_t bucket = bytes < 512 ? 512 : bytes;
+        auto it = pool.lower_bound(bucket);
+        if (it != pool.end() && it->first <= bucket * 2) {
+          out.ptr = it->second;
+          pool.erase(it);
+        } else {
+          out.ptr = alloc_owned(bucket);
+        }
+        int lu = last_use[st.out_node];
+        if (lu >= (int)s) dying[lu].push_back(st.out_node);
+        else dying[s].push_back(st.out_node);  // never read: reusable right after
+      }
+      for (int d : dying[s]) {
+        PNode& dn = nodes[d];
+        size_t bytes = (size_t)dn.n * type_size(dn.dtype);
+        for (auto& b : owned)
+          if (b.first == dn.ptr) { bytes = b.second; break; }
+        pool.emplace(bytes, dn.ptr);
+      }
+    }
+    // resolve pointers inside the steps
+    for (auto& st : steps) {
+      PNode& out = nodes[st.out_node];
+      if (st.ew) {
+        for (size_t k = 0; k < st.inputs.size(); ++k) {
+          PNode& in = nodes[st.inputs[k].node];
+          if (!in.ptr) global::fatalf("planner: input %s of %s was never materialised", in.tens->to_string().c_str(), out.tens->to_string().c_str());
+          st.prog.inputs[k].ptr = (const char*)in.ptr + st.inputs[k].offset;
+        }
+        st.prog.outputs[0].ptr = out.ptr;
+      } else {
+        st.out = out.ptr;
+        for (size_t k = 0; k < st.in_nodes.size(); ++k) {
+          PNode& in = nodes[st.in_nodes[k]];
+          if (!in.ptr) global::fatalf("planner: input %s of %s was never materialised", in.tens->to_string().c_str(), out.tens->to_string().c_str());
+          st.in.push_back((const char*)in.ptr + st.in_offsets[k]);
+        }
+      }
+    }
+  }
+
+  void launch_steps() {
+    for (auto& st : steps) {
+      if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
+      else st.holder->launch_with(st.out, st.in);
+    }
+  }
+
+  void build(const TensSetT& targets, const TensSetT& ignored, eigen::RTMemptrT mem) {
+    memory = std::move(mem);
+    precision = gemm_precision();
+    std::vector<iTensor*> ordered(targets.begin(), targets.end());
+    std::sort(ordered.begin(), ordered.end());
+    for (auto t : ordered) {
+      target_keys.push_back(t);
+      target_refs.push_back(t->weak_from_this());
+      collect(t, ignored);
+    }
+    resolve_views();
+    for (auto t : ordered) nodes[nodes[index.at(t)].root].exposed = true;
+    bool has_rand = false;
+    for (auto& n : nodes) {
+      if (!n.func) continue;
+      if (!is_idempotent((_GENERATED_OPCODE)n.op)) always_run = true;
+      if (n.op == RAND_UNIF) has_rand = true;
+    }
+    fuse();
+    build_steps();
+    assign_buffers();
+    n_launch_steps = steps.size();
+    // RAND_UNIF draws a fresh Philox offset at every launch: such plans are launched eagerly
+    use_graph = !has_rand && std::getenv("TCR_NO_GRAPH") == nullptr && !steps.empty();
+  }
+
+  bool still_valid() const {
+    if (precision != gemm_precision()) return false;
+    for (size_t k = 0; k < target_refs.size(); ++k) {
+      auto sp = target_refs[k].lock();
+      if (!sp || sp.get() != target_keys[k]) return false;
+    }
+    for (int i : functor_order)
+      if (&static_cast<eigen::iEigen&>(nodes[i].func->device()) != nodes[i].holder) return false;
+    for (auto& b : bound)
+      if (nodes[b.first].tens->device().device_data() != b.second) return false;
+    return true;
+  }
+
+  // replicate the reference's version bookkeeping (functor.hpp:246-269, device.hpp:527-531)
+  bool propagate_versions(size_t max_version) {
+    bool any = false;
+    for (int i : functor_order) {
+      PNode& n = nodes[i];
+      any |= static_cast<eigen::Observable*>(n.func)->prop_version(max_version);
+      if (is_assign(n.op)) {
+        auto target = static_cast<eigen::iMutableLeaf*>(nodes[nodes[n.args[0]].root].tens);
+        target->upversion(nodes[n.args[1]].tens->get_meta().state_version() + 1);
+        static_cast<eigen::iEigen&>(target->device()).mark_device_dirty();
+      }
+    }
+    return any;
+  }
+
+  void run(size_t max_version) {
+    bool changed = propagate_versions(max_version);
+    if (has_run && !changed && !always_run) return;
+    if (steps.empty()) { has_run = true; return; }
+    if (use_graph && has_run) {
+      if (!graph) {
+        check(tcr_graph_begin(), "tcr_graph_begin");
+        try {
+          launch_steps();
+        } catch (...) {
+          void* dead = nullptr;
+          tcr_graph_end(&dead);
+          if (dead) tcr_graph_destroy(dead);
+          throw;
+        }
+        check(tcr_graph_end(&graph), "tcr_graph_end");
+      }
+      check(tcr_graph_launch(graph), "tcr_graph_launch");
+    } else {
+      launch_steps();  // first run is eager: warms the arena and surfaces errors outside capture
+    }
+    for (auto& n : nodes)
+      if (n.exposed && n.holder) n.holder->mark_device_dirty();
+    has_run = true;
+  }
+};
+
+struct PlanCache {
+  struct Key {
+    std::vector<iTensor*> t, ig;
+    bool operator<(const Key& o) const { return t != o.t ? t < o.t : ig < o.ig; }
+  };
+  std::map<Key, std::unique_ptr<Plan>> plans;
+};
 
 PlanEvaluator::PlanEvaluator() : cache_(new PlanCache()) {}
 PlanEvaluator::~PlanEvaluator() = default;
 
-void PlanEvaluator::evaluate(teq::iDevice& device, const teq::TensSetT& targets, const teq::TensSetT& ignored) {
-  teq::Evaluator fallback;
-  fallback.evaluate(device, targets, ignored);
+void PlanEvaluator::evaluate(iDevice& device, const TensSetT& targets, const TensSetT& ignored) {
+  auto cdev = dynamic_cast<Device*>(&device);
+  if (!cdev) {  // a foreign device (mock, profiler): the reference traversal applies
+    Evaluator fallback;
+    fallback.evaluate(device, targets, ignored);
+    return;
+  }
+  for (auto ig : ignored)
+    if (nullptr != ig && nullptr == ig->device().device_data())
+      global::throw_errf("cannot ignore tensor %s without existing data", ig->to_string().c_str());
+  PlanCache::Key key;
+  key.t.assign(targets.begin(), targets.end());
+  key.ig.assign(ignored.begin(), ignored.end());
+  std::sort(key.t.begin(), key.t.end());
+  std::sort(key.ig.begin(), key.ig.end());
+  auto it = cache_->plans.find(key);
+  if (it != cache_->plans.end() && !it->second->still_valid()) {
+    cache_->plans.erase(it);
+    it = cache_->plans.end();
+  }
+  if (it == cache_->plans.end()) {
+    if (cache_->plans.size() >= 64) cache_->plans.clear();  // bounded: plans pin device buffers
+    ensure_device();
+    std::unique_ptr<Plan> plan(new Plan());
+    plan->build(targets, ignored, cdev->memory());
+    it = cache_->plans.emplace(key, std::move(plan)).first;
+  }
+  Plan& plan = *it->second;
+  plan.run(cdev->max_version_);
+  g_stats.nodes = plan.functor_order.size();
+  g_stats.steps = plan.steps.size();
+  g_stats.launches = plan.n_launch_steps;
+  g_stats.graph = plan.graph != nullptr;
+  g_stats.cached = cache_->plans.size();
 }
 
 }  // namespace cuda

@@ -273,7 +273,7 @@ struct iMetadata {
   virtual size_t state_version() const = 0;
 };
 
-struct iTensor {
+struct iTensor : public std::enable_shared_from_this<iTensor> {
   virtual ~iTensor() = default;
   iTensor* clone() const { return this->clone_impl(); }
   virtual void accept(iTraveler& visiter) = 0;
