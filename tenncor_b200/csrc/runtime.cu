@@ -21,8 +21,8 @@ namespace tcr {
 static thread_local std::string g_err;
 
 State& state() {
-  static State s;
-  return s;
+  static State* s = new State();  // leaked on purpose: holders may outlive static destruction at exit
+  return *s;
 }
 
 void set_error(const char* fmt, ...) {
@@ -51,6 +51,7 @@ struct Arena {
   bool capturing = false;
   std::multimap<size_t, void*> capture_pool;
   std::unordered_map<void*, std::vector<std::pair<size_t, void*>>> graph_blocks;
+  std::unordered_map<void*, uint64_t> graph_kernels;  // kernel nodes per instantiated graph
 
   static size_t bucket(size_t bytes) {
     if (bytes < 512) return 512;
@@ -65,8 +66,8 @@ struct Arena {
 };
 
 static Arena& arena() {
-  static Arena a;
-  return a;
+  static Arena* a = new Arena();  // leaked on purpose (see state())
+  return *a;
 }
 
 }  // namespace tcr
@@ -293,7 +294,17 @@ int tcr_graph_end(void** out_exec) {
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(state().stream, &graph);
   cudaGraphExec_t exec = nullptr;
+  uint64_t n_kernels = 0;
   if (e == cudaSuccess) {
+    size_t n_nodes = 0;
+    if (cudaGraphGetNodes(graph, nullptr, &n_nodes) == cudaSuccess && n_nodes > 0) {
+      std::vector<cudaGraphNode_t> gn(n_nodes);
+      if (cudaGraphGetNodes(graph, gn.data(), &n_nodes) == cudaSuccess)
+        for (auto node : gn) {
+          cudaGraphNodeType ty;
+          if (cudaGraphNodeGetType(node, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) ++n_kernels;
+        }
+    }
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
   }
@@ -303,6 +314,7 @@ int tcr_graph_end(void** out_exec) {
     return fail_cuda(e, "cudaStreamEndCapture/cudaGraphInstantiate", __FILE__, __LINE__);
   }
   a.graph_blocks[(void*)exec] = std::move(held);
+  a.graph_kernels[(void*)exec] = n_kernels;
   *out_exec = (void*)exec;
   return TCR_OK;
 }
@@ -310,6 +322,12 @@ int tcr_graph_end(void** out_exec) {
 int tcr_graph_launch(void* exec) {
   TCR_REQUIRE_DEVICE();
   TCR_CUDA(cudaGraphLaunch((cudaGraphExec_t)exec, state().stream));
+  {
+    Arena& a = arena();
+    std::lock_guard<std::mutex> lk(a.mu);
+    auto it = a.graph_kernels.find(exec);
+    if (it != a.graph_kernels.end()) state().launches.fetch_add(it->second, std::memory_order_relaxed);
+  }
   return TCR_OK;
 }
 
@@ -324,6 +342,7 @@ int tcr_graph_destroy(void* exec) {
     for (auto& kv : it->second) a.free_blocks.emplace(kv.first, kv.second);
     a.graph_blocks.erase(it);
   }
+  a.graph_kernels.erase(exec);
   return TCR_OK;
 }
 

@@ -14,6 +14,8 @@ using namespace egen;
 
 static PlanStats g_stats;
 PlanStats last_plan_stats() { return g_stats; }
+struct Plan;
+static Plan* g_last_plan = nullptr;
 
 namespace {
 
@@ -616,6 +618,46 @@ struct Plan {
     return any;
   }
 
+  std::vector<StepTiming> profile(int repeats) {
+    std::vector<StepTiming> out;
+    void *e0 = nullptr, *e1 = nullptr;
+    check(tcr_event_create(&e0), "tcr_event_create");
+    check(tcr_event_create(&e1), "tcr_event_create");
+    for (auto& st : steps) {
+      PNode& o = nodes[st.out_node];
+      StepTiming t;
+      t.what = o.tens->to_string();
+      if (st.ew) t.what += " fused(" + std::to_string(st.prog.n_instrs) + " instr, " + std::to_string(st.prog.n_inputs) + " in)";
+      t.shape = o.shape.to_string();
+      t.bytes = (size_t)o.n * type_size(o.dtype);
+      if (st.ew) {
+        for (auto& in : st.inputs) {
+          size_t n = 1;
+          for (int r = 0; r < rank_cap; ++r)
+            if (!((in.mask >> r) & 1u)) n *= o.shape.at(r);
+          t.bytes += n * type_size(in.dtype);
+        }
+      } else {
+        for (int in : st.in_nodes) t.bytes += (size_t)nodes[in].n * type_size(nodes[in].dtype);
+      }
+      auto once = [&] {
+        if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
+        else st.holder->launch_with(st.out, st.in);
+      };
+      once();
+      check(tcr_event_record(e0), "tcr_event_record");
+      for (int r = 0; r < repeats; ++r) once();
+      check(tcr_event_record(e1), "tcr_event_record");
+      float ms = 0;
+      check(tcr_event_elapsed_ms(e0, e1, &ms), "tcr_event_elapsed_ms");
+      t.ms = ms / repeats;
+      out.push_back(t);
+    }
+    tcr_event_destroy(e0);
+    tcr_event_destroy(e1);
+    return out;
+  }
+
   void run(size_t max_version) {
     bool changed = propagate_versions(max_version);
     if (has_run && !changed && !always_run) return;
@@ -652,7 +694,12 @@ struct PlanCache {
 };
 
 PlanEvaluator::PlanEvaluator() : cache_(new PlanCache()) {}
-PlanEvaluator::~PlanEvaluator() = default;
+PlanEvaluator::~PlanEvaluator() { g_last_plan = nullptr; }
+
+std::vector<StepTiming> profile_last_plan(int repeats) {
+  if (!g_last_plan) global::fatal("profile_last_plan: no plan has been evaluated yet");
+  return g_last_plan->profile(repeats);
+}
 
 void PlanEvaluator::evaluate(iDevice& device, const TensSetT& targets, const TensSetT& ignored) {
   auto cdev = dynamic_cast<Device*>(&device);
@@ -671,11 +718,15 @@ void PlanEvaluator::evaluate(iDevice& device, const TensSetT& targets, const Ten
   std::sort(key.ig.begin(), key.ig.end());
   auto it = cache_->plans.find(key);
   if (it != cache_->plans.end() && !it->second->still_valid()) {
+    if (g_last_plan == it->second.get()) g_last_plan = nullptr;
     cache_->plans.erase(it);
     it = cache_->plans.end();
   }
   if (it == cache_->plans.end()) {
-    if (cache_->plans.size() >= 64) cache_->plans.clear();  // bounded: plans pin device buffers
+    if (cache_->plans.size() >= 64) {  // bounded: plans pin device buffers
+      cache_->plans.clear();
+      g_last_plan = nullptr;
+    }
     ensure_device();
     std::unique_ptr<Plan> plan(new Plan());
     plan->build(targets, ignored, cdev->memory());
@@ -683,6 +734,7 @@ void PlanEvaluator::evaluate(iDevice& device, const TensSetT& targets, const Ten
   }
   Plan& plan = *it->second;
   plan.run(cdev->max_version_);
+  g_last_plan = &plan;
   g_stats.nodes = plan.functor_order.size();
   g_stats.steps = plan.steps.size();
   g_stats.launches = plan.n_launch_steps;

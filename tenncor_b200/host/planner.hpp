@@ -27,6 +27,16 @@ struct PlanStats {
 
 PlanStats last_plan_stats();
 
+/// per-step device timings of the most recently evaluated plan (steps launched one by one with
+/// CUDA events on the library stream; runs the step sequence once more, eagerly)
+struct StepTiming {
+  std::string what;   // opcode of the node the step produces (+ "fused(n)" for register-machine programs)
+  std::string shape;  // output shape
+  double ms = 0;
+  size_t bytes = 0;   // algorithmic bytes (inputs un-broadcast + output) for HBM-bound steps
+};
+std::vector<StepTiming> profile_last_plan(int repeats = 5);
+
 struct PlanCache;
 
 struct PlanEvaluator final : public teq::iEvaluator {

@@ -322,6 +322,15 @@ PYBIND11_MODULE(_tenncor, m) {
     d["nodes"] = s.nodes; d["steps"] = s.steps; d["launches_per_run"] = s.launches; d["graph"] = s.graph; d["plans_cached"] = s.cached;
     return d;
   });
+  m.def("profile_plan", [](int repeats) {
+    py::list out;
+    for (auto& t : cuda::profile_last_plan(repeats)) {
+      py::dict d;
+      d["what"] = t.what; d["shape"] = t.shape; d["ms"] = t.ms; d["bytes"] = t.bytes;
+      out.append(d);
+    }
+    return out;
+  }, py::arg("repeats") = 5, "Per-step CUDA-event timings of the last evaluated plan");
   m.def("arena_stats", [] {
     size_t a = 0, b = 0, c = 0;
     tcr_arena_stats(&a, &b, &c);
