@@ -10,7 +10,8 @@
 
 namespace tcr {
 
-int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc* d, bool* handled);  // gemm_tc.cu
+int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc* d, bool* handled);      // gemm_tc.cu
+int gemm_skinny_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc* d, bool* handled);  // gemm_skinny.cu
 
 template <typename T> __device__ __forceinline__ T act_apply(int act, T x) { return x; }
 template <> __device__ __forceinline__ float act_apply(int act, float x) {
@@ -163,6 +164,13 @@ int tcr_gemm(const void* a, const void* b, void* c, const tcr_gemm_desc* desc) {
   TCR_ARG(desc->epilogue == TCR_EPI_NONE || desc->bias != nullptr, "tcr_gemm: bias epilogue without bias pointer");
   if (desc->m == 0 || desc->n == 0 || desc->batch == 0) return TCR_OK;
   TCR_ARG(desc->batch <= 65535, "tcr_gemm: batch %lld exceeds grid.z", (long long)desc->batch);
+  {
+    // skinny products (an extent <= 16) are HBM-bound: streaming kernels, exact FMA in the element type
+    bool handled = false;
+    int rc = gemm_skinny_dispatch(a, b, c, desc, &handled);
+    if (rc) return rc;
+    if (handled) return TCR_OK;
+  }
   if (desc->precision != TCR_GEMM_EXACT) {
     TCR_ARG(desc->dtype == TCR_FLOAT, "tcr_gemm: tensor-core precisions are fp32 only");
     bool handled = false;

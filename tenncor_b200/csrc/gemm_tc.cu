@@ -38,6 +38,7 @@ struct TcParams {
   const float* bias;
   int epilogue, activation, accumulate;
   int a_mn_major, b_mn_major;  // 0: K-major (K contiguous), 1: MN-major (M / N contiguous)
+  int kb_per_split;            // k-blocks handled by one blockIdx.z (split-K); partial tiles go to `c` + z*m*n
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,7 +138,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
-  const int num_kb = (int)((p.k + BK - 1) / BK);
+  const int total_kb = (int)((p.k + BK - 1) / BK);
+  const int kb_begin = (int)blockIdx.z * p.kb_per_split;
+  const int num_kb = min(p.kb_per_split, total_kb - kb_begin);  // >= 1 by construction of the grid
+  float* const c_out = p.c + (gridDim.z > 1 ? (int64_t)blockIdx.z * p.m * p.n : 0);
 
   auto tile_a = [&](int s) { return smem + s * STAGE_BYTES; };
   auto tile_b = [&](int s) { return smem + s * STAGE_BYTES + TILE_BYTES; };
@@ -170,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t round = kb / STAGES;
         if (kb >= STAGES) mbar_wait(&empty[s], (round - 1) & 1);
         mbar_expect_tx(&full[s], 2 * TILE_BYTES);
-        const int32_t k0 = kb * BK;
+        const int32_t k0 = (kb_begin + kb) * BK;
         if (!p.a_mn_major) {
           tma_load_2d(&map_a, &full[s], tile_a(s), k0, (int32_t)m0);  // [128 rows][32 k]
         } else {
@@ -282,14 +286,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float x = __uint_as_float(r[j]);
         const int64_t n = nb + j;
         if (n < p.n) {
-          if (p.accumulate) x += p.c[m * p.c_sm + n * p.c_sn];
+          if (p.accumulate) x += c_out[m * p.c_sm + n * p.c_sn];
           if (p.epilogue == TCR_EPI_BIAS_N) x += p.bias[n];
           else if (p.epilogue == TCR_EPI_BIAS_M) x += p.bias[m];
           if (p.activation) x = act_f(p.activation, x);
         }
         v[j] = x;
       }
-      float* row = p.c + m * p.c_sm + nb * p.c_sn;
+      float* row = c_out + m * p.c_sm + nb * p.c_sn;
       if (p.c_sn == 1 && nb + 32 <= p.n && (((uintptr_t)row) & 15) == 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(row + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -303,6 +307,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+}
+
+// deterministic split-K: out(m,n) = epilogue(sum_z ws[z][m][n])
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, TcParams p) {
+  const int64_t total = p.m * p.n, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t m = i / p.n, n = i % p.n;
+    float x = 0.f;
+    for (int z = 0; z < splits; ++z) x += ws[(int64_t)z * total + i];
+    float* dst = p.c + m * p.c_sm + n * p.c_sn;
+    if (p.accumulate) x += *dst;
+    if (p.epilogue == TCR_EPI_BIAS_N) x += p.bias[n];
+    else if (p.epilogue == TCR_EPI_BIAS_M) x += p.bias[m];
+    if (p.activation) x = act_f(p.activation, x);
+    *dst = x;
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -342,7 +362,7 @@ int make_map(CUtensorMap* map, const float* base, int64_t dim0, int64_t dim1, in
 }
 
 template <int MODE, int STAGES>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p) {
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int splits) {
   constexpr int STAGE_BYTES = (MODE == 2 ? 4 : 2) * TILE_BYTES;
   constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool configured = false;
@@ -350,7 +370,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p) {
     TCR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(p.n, BN), (unsigned)ceil_div(p.m, BM));
+  dim3 grid((unsigned)ceil_div(p.n, BN), (unsigned)ceil_div(p.m, BM), (unsigned)splits);
   TCR_LAUNCH((gemm_tc_kernel<MODE, STAGES>), grid, NUM_THREADS, SMEM, ma, mb, p);
   TCR_CHECK_LAUNCH();
   return TCR_OK;
@@ -393,8 +413,37 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
     p.bias = (const float*)d->bias;
     p.epilogue = d->epilogue; p.activation = d->activation; p.accumulate = d->accumulate;
     p.a_mn_major = a_mn; p.b_mn_major = b_mn;
-    rc = d->precision == TCR_GEMM_TF32 ? launch_tc<1, 6>(ma, mb, p) : launch_tc<2, 3>(ma, mb, p);
+    // split-K when the output has fewer tiles than SMs (weight gradients: K = batch): pick the
+    // split count whose CTA count best fills whole waves of the machine
+    const int total_kb = (int)ceil_div(d->k, BK);
+    const int64_t tiles = ceil_div(d->m, BM) * ceil_div(d->n, BN);
+    const int sms = state().sm_count;
+    int splits = 1;
+    if (tiles * 2 <= sms && total_kb >= 16) {
+      double best = (double)tiles / (double)(ceil_div(tiles, sms) * sms);
+      for (int sp = 2; sp <= 32 && total_kb / sp >= 8; ++sp) {
+        double eff = (double)(tiles * sp) / (double)(ceil_div(tiles * sp, sms) * sms);
+        if (eff > best + 0.05) { best = eff; splits = sp; }
+      }
+    }
+    p.kb_per_split = (int)ceil_div(total_kb, splits);
+    splits = (int)ceil_div(total_kb, p.kb_per_split);
+    void* ws = nullptr;
+    TcParams pk = p;
+    if (splits > 1) {
+      rc = tcr_alloc(&ws, sizeof(float) * (size_t)splits * d->m * d->n);
+      if (rc) return rc;
+      pk.c = (float*)ws; pk.c_sm = d->n; pk.c_sn = 1;
+      pk.epilogue = TCR_EPI_NONE; pk.activation = 0; pk.accumulate = 0; pk.bias = nullptr;
+    }
+    rc = d->precision == TCR_GEMM_TF32 ? launch_tc<1, 6>(ma, mb, pk, splits) : launch_tc<2, 3>(ma, mb, pk, splits);
     if (rc) return rc;
+    if (splits > 1) {
+      int grid = wave_grid(d->m * d->n, 256, 8);
+      TCR_LAUNCH(splitk_reduce_kernel, grid, 256, 0, (const float*)ws, splits, p);
+      TCR_CHECK_LAUNCH();
+      tcr_free(ws);
+    }
   }
   *handled = true;
   return TCR_OK;

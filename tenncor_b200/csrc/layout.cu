@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) map_copy_kernel(const E* __restrict__ in,
       }
       off += q * d.in_stride;
     }
-    E v = E(0);
+    E v = E();  // zero fill (PAD / SCATTER holes)
     if (!CHECK || valid) v = in[off];
     out[o] = v;
   }
@@ -238,6 +238,23 @@ int tcr_map_copy(const void* in, void* out, const tcr_map_desc* desc, int elem_s
       }
     }
   }
+  // 16-byte path: when the fastest effective rank is contiguous on both sides and everything is
+  // 16-byte aligned, move uint4 "elements" — the coordinate arithmetic is amortised over 16 bytes
+  if (elem_size < 16) {
+    const int64_t f = 16 / elem_size;
+    const MapDim& d0 = p.d[0];
+    bool ok = d0.mul == 1 && d0.div == 1 && d0.in_stride == 1 && d0.ext % f == 0 && d0.add % f == 0 && d0.in_dim % f == 0 &&
+              p.base % f == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    for (int k = 1; ok && k < p.nd; ++k) ok = p.d[k].in_stride % f == 0;
+    if (ok) {
+      MapPlan q = p;
+      q.d[0].ext /= f; q.d[0].add /= f; q.d[0].in_dim /= f;
+      for (int k = 1; k < q.nd; ++k) q.d[k].in_stride /= f;
+      q.base /= f;
+      q.n_out /= f;
+      return launch_map<uint4>(in, out, q, n_in / f);
+    }
+  }
   TCR_DISPATCH_ELEM(elem_size, E, return launch_map<E>(in, out, p, n_in));
   return TCR_OK;
 }
@@ -354,8 +371,14 @@ int tcr_concat(const void* const* args, const int64_t* shapes, int nargs, void* 
       int rc = tcr_d2d((char*)out + inner * off * elem_size, args[a], (size_t)(inner * ext) * elem_size);
       if (rc) return rc;
     } else {
-      int grid = wave_grid(inner * ext * outer, 256, 8);
-      TCR_DISPATCH_ELEM(elem_size, E, TCR_LAUNCH((concat_one_kernel<E>), grid, 256, 0, (const E*)args[a], (E*)out, inner, ext, outer, off, out_ext));
+      const int64_t f = 16 / elem_size;
+      if (elem_size < 16 && inner % f == 0 && (((uintptr_t)args[a] | (uintptr_t)out) & 15) == 0) {
+        int grid = wave_grid(inner / f * ext * outer, 256, 8);
+        TCR_LAUNCH((concat_one_kernel<uint4>), grid, 256, 0, (const uint4*)args[a], (uint4*)out, inner / f, ext, outer, off, out_ext);
+      } else {
+        int grid = wave_grid(inner * ext * outer, 256, 8);
+        TCR_DISPATCH_ELEM(elem_size, E, TCR_LAUNCH((concat_one_kernel<E>), grid, 256, 0, (const E*)args[a], (E*)out, inner, ext, outer, off, out_ext));
+      }
     }
     off += ext;
   }
