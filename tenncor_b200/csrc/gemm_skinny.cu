@@ -48,30 +48,56 @@ __device__ __forceinline__ void sk_store(const SkinnyDesc& d, T* C, int64_t l, i
 template <typename T> __device__ __forceinline__ T sk_shfl_down(T v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
 template <> __device__ __forceinline__ int64_t sk_shfl_down(int64_t v, int o) { return (int64_t)__shfl_down_sync(0xffffffffu, (long long)v, o); }
 
-// X is K-major (x_sk == 1): one warp per row l, lanes stride over k
+// X is K-major (x_sk == 1): a block owns 32 rows (4 per warp); the small operand is staged in shared
+// memory 128 k at a time ([s][k]: lanes read consecutive k, conflict-free), lanes stride over k
 template <typename T>
 __global__ void __launch_bounds__(256) skinny_rk_kernel(const T* __restrict__ X, const T* __restrict__ Y, T* __restrict__ C,
                                                         const __grid_constant__ SkinnyDesc d) {
-  const int lane = threadIdx.x & 31;
-  const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t l = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); l < d.L; l += wpg) {
-    const T* row = X + l * d.x_sl;
-    T acc[SK_MAX];
+  constexpr int KC = 128, RPW = 4;
+  __shared__ T ysm[SK_MAX][KC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t row_base = (int64_t)blockIdx.x * 32; row_base < d.L; row_base += (int64_t)gridDim.x * 32) {
+    T acc[RPW][SK_MAX];
 #pragma unroll
-    for (int s = 0; s < SK_MAX; ++s) acc[s] = T(0);
-    for (int64_t k = lane; k < d.K; k += 32) {
-      const T x = row[k];
+    for (int r = 0; r < RPW; ++r)
 #pragma unroll
-      for (int s = 0; s < SK_MAX; ++s)
-        if (s < d.S) acc[s] += x * __ldg(Y + s * d.y_ss + k * d.y_sk);
+      for (int s = 0; s < SK_MAX; ++s) acc[r][s] = T(0);
+    for (int64_t kb = 0; kb < d.K; kb += KC) {
+      for (int e = threadIdx.x; e < SK_MAX * KC; e += 256) {
+        const int s = e / KC, kk = e % KC;
+        ysm[s][kk] = (s < d.S && kb + kk < d.K) ? Y[s * d.y_ss + (kb + kk) * d.y_sk] : T(0);
+      }
+      __syncthreads();
+      T x[RPW][KC / 32];
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        const int64_t l = row_base + warp * RPW + r;
+#pragma unroll
+        for (int i = 0; i < KC / 32; ++i) {
+          const int64_t k = kb + lane + 32 * i;
+          x[r][i] = (l < d.L && k < d.K) ? X[l * d.x_sl + k] : T(0);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < KC / 32; ++i)
+#pragma unroll
+        for (int s = 0; s < SK_MAX; ++s) {
+          const T y = ysm[s][lane + 32 * i];
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) acc[r][s] += x[r][i] * y;
+        }
+      __syncthreads();
     }
 #pragma unroll
-    for (int s = 0; s < SK_MAX; ++s) {
-      if (s >= d.S) break;
-      T v = acc[s];
+    for (int r = 0; r < RPW; ++r) {
+      const int64_t l = row_base + warp * RPW + r;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += sk_shfl_down(v, o);
-      if (lane == 0) sk_store<T>(d, C, l, s, v);
+      for (int s = 0; s < SK_MAX; ++s) {
+        T v = acc[r][s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += sk_shfl_down(v, o);
+        if (lane == 0 && l < d.L && s < d.S) sk_store<T>(d, C, l, s, v);
+      }
     }
   }
 }
@@ -128,39 +154,48 @@ __global__ void __launch_bounds__(256) skinny_rs_reduce_kernel(const T* __restri
   }
 }
 
-// K <= 16: C(m, n..n+3) = sum_k A(m,k) B(k, n..n+3); consecutive threads walk n (coalesced stores)
+// K <= 16: every output is a short dot product. A thread keeps its column B(:, n) in registers,
+// a block stages 64 rows of A in shared memory and streams them; consecutive threads walk n
+// (coalesced stores when c_sn == 1)
 template <typename T>
 __global__ void __launch_bounds__(256) small_k_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C,
                                                       const __grid_constant__ tcr_gemm_desc d) {
-  const int64_t nq = (d.n + 3) / 4, total = d.m * nq, stride = (int64_t)gridDim.x * blockDim.x;
+  __shared__ T a_sm[64][SK_MAX];
+  const int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool n_ok = n < d.n;
   const T* bias = (const T*)d.bias;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t m = i / nq, n0 = (i % nq) * 4;
-    T acc[4] = {T(0), T(0), T(0), T(0)};
-    for (int k = 0; k < (int)d.k; ++k) {
-      const T a = __ldg(A + m * d.a_sm + k * d.a_sk);
+  T b[SK_MAX];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (n0 + j < d.n) acc[j] += a * __ldg(B + k * d.b_sk + (n0 + j) * d.b_sn);
+  for (int k = 0; k < SK_MAX; ++k) b[k] = (n_ok && k < d.k) ? B[k * d.b_sk + n * d.b_sn] : T(0);
+  for (int64_t m0 = (int64_t)blockIdx.y * 64; m0 < d.m; m0 += (int64_t)gridDim.y * 64) {
+    for (int e = threadIdx.x; e < 64 * SK_MAX; e += 256) {
+      const int mm = e / SK_MAX, k = e % SK_MAX;
+      a_sm[mm][k] = (m0 + mm < d.m && k < d.k) ? A[(m0 + mm) * d.a_sm + k * d.a_sk] : T(0);
     }
+    __syncthreads();
+    if (n_ok) {
+      const int rows = d.m - m0 < 64 ? (int)(d.m - m0) : 64;
+      for (int mm = 0; mm < rows; ++mm) {
+        T v = T(0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (n0 + j >= d.n) break;
-      T v = acc[j];
-      T* dst = C + m * d.c_sm + (n0 + j) * d.c_sn;
-      if (d.accumulate) v += *dst;
-      if (d.epilogue == TCR_EPI_BIAS_N) v += bias[n0 + j];
-      else if (d.epilogue == TCR_EPI_BIAS_M) v += bias[m];
-      if (d.activation) v = sk_act<T>(d.activation, v);
-      *dst = v;
+        for (int k = 0; k < SK_MAX; ++k) v += a_sm[mm][k] * b[k];
+        const int64_t m = m0 + mm;
+        T* dst = C + m * d.c_sm + n * d.c_sn;
+        if (d.accumulate) v += *dst;
+        if (d.epilogue == TCR_EPI_BIAS_N) v += bias[n];
+        else if (d.epilogue == TCR_EPI_BIAS_M) v += bias[m];
+        if (d.activation) v = sk_act<T>(d.activation, v);
+        *dst = v;
+      }
     }
+    __syncthreads();
   }
 }
 
 template <typename T>
 static int run_skinny(const T* X, const T* Y, T* C, const SkinnyDesc& d) {
   if (d.x_sk == 1 || d.K == 1) {
-    int grid = wave_grid(d.L, 8, 8);
+    int grid = wave_grid(d.L, 32, 4);
     TCR_LAUNCH((skinny_rk_kernel<T>), grid, 256, 0, X, Y, C, d);
     TCR_CHECK_LAUNCH();
     return TCR_OK;
@@ -196,7 +231,9 @@ int gemm_skinny_dispatch(const void* a, const void* b, void* c, const tcr_gemm_d
   const bool big = d->m * d->n * d->k >= (1ll << 16);
   if (!big) return TCR_OK;
   if (d->k <= SK_MAX && d->m * d->n >= 4096) {
-    int grid = wave_grid(d->m * ((d->n + 3) / 4), 256, 8);
+    int64_t gy = ceil_div(d->m, 64);
+    if (gy > 4096) gy = 4096;
+    dim3 grid((unsigned)ceil_div(d->n, 256), (unsigned)gy);
     TCR_DISPATCH_COMPUTE(d->dtype, T, TCR_LAUNCH((small_k_kernel<T>), grid, 256, 0, (const T*)a, (const T*)b, (T*)c, *d));
     TCR_CHECK_LAUNCH();
     *handled = true;

@@ -20,6 +20,8 @@
 // (tenncor/eteq/backprop.hpp:269-359) need no transposes.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tcr {
@@ -39,6 +41,7 @@ struct TcParams {
   int epilogue, activation, accumulate;
   int a_mn_major, b_mn_major;  // 0: K-major (K contiguous), 1: MN-major (M / N contiguous)
   int kb_per_split;            // k-blocks handled by one blockIdx.z (split-K); partial tiles go to `c` + z*m*n
+  int raw_hi;                  // 3xTF32: leave the landed tile untouched (the tensor core truncates it to tf32 = hi) and only write lo
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -247,11 +250,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             uint32_t hb;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(__uint_as_float(x[e])));
+            if (p.raw_hi) hb = x[e] & 0xFFFFE000u;  // what the tensor core keeps of the raw fp32 word
+            else asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(__uint_as_float(x[e])));
             h[e] = hb;
             l[e] = __float_as_uint(__uint_as_float(x[e]) - __uint_as_float(hb));
           }
-          src[i] = hi;
+          if (!p.raw_hi) src[i] = hi;
           dlo[i] = lo;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
@@ -413,6 +417,10 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
     p.bias = (const float*)d->bias;
     p.epilogue = d->epilogue; p.activation = d->activation; p.accumulate = d->accumulate;
     p.a_mn_major = a_mn; p.b_mn_major = b_mn;
+    {
+      static const int raw_hi = std::getenv("TCR_3X_RAWHI") ? std::atoi(std::getenv("TCR_3X_RAWHI")) : 0;
+      p.raw_hi = raw_hi;
+    }
     // split-K when the output has fewer tiles than SMs (weight gradients: K = batch): pick the
     // split count whose CTA count best fills whole waves of the machine
     const int total_kb = (int)ceil_div(d->k, BK);

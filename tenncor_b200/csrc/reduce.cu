@@ -353,6 +353,39 @@ __global__ void __launch_bounds__(256) argmax_cols(const T* __restrict__ in, T* 
   }
 }
 
+// columns with few outputs and a long reduced rank: block = (32 lanes along ki, 8 along r),
+// grid = (ceil(Kin/32), S, Kout). Pass 1 (pidx == nullptr) scans `in` and emits per-split winners
+// (value, original r); pass 2 merges the S winners. Ties resolve to the lowest r in both passes.
+template <typename T>
+__global__ void __launch_bounds__(256) argmax_cols_split(const T* __restrict__ in, const int64_t* __restrict__ pidx, T* __restrict__ out_val,
+                                                         int64_t* __restrict__ out_idx, T* __restrict__ out_final, int64_t Kin, int64_t R,
+                                                         int64_t chunk, int S) {
+  __shared__ T sv[8][33];
+  __shared__ int64_t si[8][33];
+  const int64_t ki = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  const int s = blockIdx.y;
+  const int64_t ko = blockIdx.z;
+  const int64_t lo = (int64_t)s * chunk, hi = lo + chunk < R ? lo + chunk : R;
+  ValIdx<T> best{Lim<T>::lo(), INT64_MAX};
+  if (ki < Kin) {
+    const int64_t base = ki + Kin * (R * ko);
+    for (int64_t r = lo + threadIdx.y; r < hi; r += 8) {
+      const int64_t at = base + Kin * r;
+      best = vi_better(best, ValIdx<T>{in[at], pidx ? pidx[at] : r});
+    }
+  }
+  sv[threadIdx.y][threadIdx.x] = best.v;
+  si[threadIdx.y][threadIdx.x] = best.i;
+  __syncthreads();
+  if (threadIdx.y == 0 && ki < Kin) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y) best = vi_better(best, ValIdx<T>{sv[y][threadIdx.x], si[y][threadIdx.x]});
+    const int64_t o = ki + Kin * ((int64_t)s + (int64_t)S * ko);
+    if (out_final) out_final[ki + Kin * ko] = (T)(best.i == INT64_MAX ? 0 : best.i);
+    else { out_val[o] = best.v; out_idx[o] = best.i; }
+  }
+}
+
 // flat: pass 1 -> per-block (val, idx); pass 2 (single block) -> out
 template <typename T>
 __global__ void __launch_bounds__(256) argmax_flat1(const T* __restrict__ in, int64_t n, T* __restrict__ pv, int64_t* __restrict__ pi) {
@@ -413,9 +446,32 @@ static int run_argmax(const void* in, void* out, const int64_t shape[8], int ret
   if (Kin == 1) {
     int grid = wave_grid(Kout, 8, 8);
     TCR_LAUNCH((argmax_warp<T>), grid, 256, 0, (const T*)in, (T*)out, R, Kout);
-  } else {
+  } else if (Kin * Kout >= (int64_t)state().sm_count * 512 || R < 64 || Kout > 65535) {
     int grid = wave_grid(Kin * Kout, 256, 8);
     TCR_LAUNCH((argmax_cols<T>), grid, 256, 0, (const T*)in, (T*)out, Kin, R, Kout);
+  } else {
+    const int64_t bx = ceil_div(Kin, 32);
+    int64_t S = ceil_div((int64_t)state().sm_count * 8, bx * Kout);
+    if (S > ceil_div(R, 64)) S = ceil_div(R, 64);
+    if (S < 1) S = 1;
+    if (S > 65535) S = 65535;
+    int64_t chunk = ceil_div(R, S);
+    S = ceil_div(R, chunk);
+    if (S == 1) {
+      TCR_LAUNCH((argmax_cols_split<T>), dim3((unsigned)bx, 1, (unsigned)Kout), dim3(32, 8), 0, (const T*)in, (const int64_t*)nullptr,
+                 (T*)nullptr, (int64_t*)nullptr, (T*)out, Kin, R, chunk, 1);
+    } else {
+      void* pv = nullptr; void* pi = nullptr;
+      int rc = tcr_alloc(&pv, sizeof(T) * (size_t)(Kin * S * Kout));
+      if (rc) return rc;
+      rc = tcr_alloc(&pi, sizeof(int64_t) * (size_t)(Kin * S * Kout));
+      if (rc) { tcr_free(pv); return rc; }
+      TCR_LAUNCH((argmax_cols_split<T>), dim3((unsigned)bx, (unsigned)S, (unsigned)Kout), dim3(32, 8), 0, (const T*)in,
+                 (const int64_t*)nullptr, (T*)pv, (int64_t*)pi, (T*)nullptr, Kin, R, chunk, (int)S);
+      TCR_LAUNCH((argmax_cols_split<T>), dim3((unsigned)bx, 1, (unsigned)Kout), dim3(32, 8), 0, (const T*)pv, (const int64_t*)pi,
+                 (T*)nullptr, (int64_t*)nullptr, (T*)out, Kin, S, S, 1);
+      tcr_free(pv); tcr_free(pi);
+    }
   }
   TCR_CHECK_LAUNCH();
   return TCR_OK;

@@ -115,6 +115,16 @@ def main():
                 d = cabi.GemmDesc(m=M, n=N, k=K, batch=1, a_sm=K, a_sk=1, a_sb=0, b_sk=N, b_sn=1, b_sb=0, c_sm=N, c_sn=1, c_sb=0,
                                   dtype=F, precision=prec)
                 rec("mm_%s_%d^3" % (nm, s), timeit(lambda: cabi.check(lib.tcr_gemm(P(a), P(b), P(out), C.byref(d))), iters=5), flops=2.0 * M * N * K)
+        # operand majors (the backward contractions are the TN / NT forms) and the c3 training shapes
+        for prec, nm in [(1, "tf32"), (2, "3xtf32")]:
+            for tag, (M, N, K), ta, tb in [("NN_4096^3", (4096, 4096, 4096), 0, 0), ("TN_4096^3", (4096, 4096, 4096), 1, 0),
+                                           ("NT_4096^3", (4096, 4096, 4096), 0, 1), ("TT_4096^3", (4096, 4096, 4096), 1, 1),
+                                           ("c3_fwd_NN_8192x1024x784", (8192, 1024, 784), 0, 0),
+                                           ("c3_dW_TN_1024x784x8192", (1024, 784, 8192), 1, 0),
+                                           ("c4_gate_NN_64x4096x1152", (64, 4096, 1152), 0, 0)]:
+                d = cabi.GemmDesc(m=M, n=N, k=K, batch=1, a_sm=1 if ta else K, a_sk=M if ta else 1, b_sk=1 if tb else N, b_sn=K if tb else 1,
+                                  c_sm=N, c_sn=1, dtype=F, precision=prec)
+                rec("mm_%s_%s" % (nm, tag), timeit(lambda: cabi.check(lib.tcr_gemm(P(a), P(b), P(out), C.byref(d))), iters=5), flops=2.0 * M * N * K)
     return res
 
 
