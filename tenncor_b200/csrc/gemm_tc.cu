@@ -418,7 +418,9 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
     p.epilogue = d->epilogue; p.activation = d->activation; p.accumulate = d->accumulate;
     p.a_mn_major = a_mn; p.b_mn_major = b_mn;
     {
-      static const int raw_hi = std::getenv("TCR_3X_RAWHI") ? std::atoi(std::getenv("TCR_3X_RAWHI")) : 0;
+      // measured on B200: the tensor core truncates fp32 words to tf32, so the raw tile IS the hi part
+      // (3xTF32 error unchanged: 5.7e-5 vs 4.9e-5 abs at K = 256); TCR_3X_RAWHI=0 restores the explicit rna split
+      static const int raw_hi = std::getenv("TCR_3X_RAWHI") ? std::atoi(std::getenv("TCR_3X_RAWHI")) : 1;
       p.raw_hi = raw_hi;
     }
     // split-K when the output has fewer tiles than SMs (weight gradients: K = batch): pick the
