@@ -349,10 +349,29 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
+        dist.barrier()  # rank 0 may still be in its CPU-baseline leg: leave together
         tc.dp.shutdown()
         dist.destroy_process_group()
     return 0
 
 
+def _watchdog(seconds):
+    """A bench that wedges (a peer died, a collective never completes) must end, not hold the box."""
+    import threading
+
+    def fire():
+        sys.stderr.write("bench.py: watchdog expired after %ds, aborting\n" % seconds)
+        sys.stderr.flush()
+        os._exit(3)
+
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    _watchdog(int(os.environ.get("TCR_BENCH_WATCHDOG_S", "900")))
+    rc = main()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(rc)  # skip interpreter teardown: nothing after the JSON line may block the launcher

@@ -382,6 +382,12 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, i
 
 }  // namespace
 
+int make_tf32_map(CUtensorMap* map, const float* base, int64_t dim0, int64_t dim1, int64_t pitch, uint32_t box0, uint32_t box1, bool mn_major) {
+  return make_map(map, base, dim0, dim1, pitch, box0, box1, mn_major);
+}
+
+int gemm_tc2_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc* d, int a_mn, int b_mn, int64_t a_pitch, int64_t b_pitch, bool* handled);  // gemm_tc2.cu
+
 int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc* d, bool* handled) {
   *handled = false;
   if (d->dtype != TCR_FLOAT || d->k <= 0) return TCR_OK;
@@ -400,6 +406,11 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
   if ((d->a_sb % 4) != 0 || (d->b_sb % 4) != 0) return TCR_OK;
   if (a_pitch < (a_mn ? d->m : d->k) || b_pitch < (b_mn ? d->n : d->k)) return TCR_OK;
 
+  {
+    // large outputs: persistent CTA-pair kernel (256x256 tiles, cta_group::2)
+    int rc2 = gemm_tc2_dispatch(a, b, c, d, a_mn, b_mn, a_pitch, b_pitch, handled);
+    if (rc2 || *handled) return rc2;
+  }
   for (int64_t bi = 0; bi < d->batch; ++bi) {
     const float* ap = (const float*)a + bi * d->a_sb;
     const float* bp = (const float*)b + bi * d->b_sb;

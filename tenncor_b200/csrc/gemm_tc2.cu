@@ -1,0 +1,472 @@
+// gemm_tc2.cu — persistent CTA-pair fp32 GEMM on tcgen05 (cta_group::2), TF32 and 3xTF32.
+//
+// Why a second kernel: ncu on the single-CTA 128x128 kernel (profiles/r1_ncu_gemm_tc_tf32_4096.md)
+// shows tensor pipe 27 %, DRAM 14 %, L2 27 % — it is bound by shared-memory bandwidth (fp32
+// operands: per k-block the MMA reads 32 KiB while TMA writes 32 KiB in the 256 cycles the MMAs
+// take) and pays a fixed prologue/epilogue bubble per tile. This kernel
+//   * pairs two SMs on one 256x256 output tile (tcgen05.mma.cta_group::2, M = 256, N = 256): each
+//     CTA stages only its 128 rows of A and its 128 columns of B, halving smem traffic per flop;
+//   * is persistent: one CTA pair per SM pair walks a static tile schedule, the accumulator is
+//     double-buffered in TMEM (2 x 256 columns = all 512) so the epilogue of tile i overlaps the
+//     main loop of tile i+1, and barrier setup / TMEM allocation happen once per launch;
+//   * keeps the 3xTF32 hi/lo split in shared memory (converter warps write only `lo`; the tensor core
+//     truncates the raw tile to its `hi` part), 3 MMAs per k-step;
+//   * supports split-K work items (weight gradients: K = batch) with a deterministic second pass.
+//
+// Warp roles (per CTA):  w0 TMA producer | w1 MMA issuer (leader CTA only) | w2 TMEM alloc + TF32
+// forwarder | w3 idle | 3xTF32: w4-7 converters, w8-11 epilogue | TF32: w4-7 epilogue.
+// Barrier protocol (s = smem stage, b = TMEM buffer):
+//   full[s]   local, 1 arrival + 32 KiB tx : this CTA's A/B tiles landed
+//   ready[s]  leader, 2 (TF32) or 8 (3x) arrivals from both CTAs : stage may be consumed by the MMA
+//   empty[s]  local, tcgen05.commit multicast to both CTAs : stage may be refilled
+//   tfull[b]  local, commit multicast : accumulator b complete
+//   tempty[b] leader, 8 arrivals (4 epilogue warps x 2 CTAs) : accumulator b drained
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace tcr {
+
+namespace {
+
+constexpr int BM_CTA = 128, BN_CTA = 128, BN = 256, BK = 32;
+constexpr int TILE_BYTES = 128 * BK * 4;  // 16 KiB per operand tile per CTA
+constexpr uint32_t SPIN_LIMIT = 1u << 28;
+
+struct Tc2Params {
+  int64_t m, n, k;
+  int64_t c_sm, c_sn;
+  float* c;
+  const float* bias;
+  int epilogue, activation, accumulate;
+  int a_mn_major, b_mn_major;
+  int tiles_m, tiles_n, splits, kb_per_split;  // work item = (tile_m, tile_n, split); split-K partials go to c + split*m*n
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;   // c_format F32
+  d |= 2u << 7;   // a_format TF32
+  d |= 2u << 10;  // b_format TF32
+  d |= (uint32_t)(a_mn_major & 1) << 15;
+  d |= (uint32_t)(b_mn_major & 1) << 16;
+  d |= (uint32_t)(BN >> 3) << 17;   // N = 256
+  d |= (uint32_t)(256 >> 4) << 24;  // M = 256 across the CTA pair
+  return d;
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit to the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ float act_f(int act, float x) {
+  if (act == TCR_EW_SIGMOID) return 1.0f / (1.0f + expf(-x));
+  if (act == TCR_EW_TANH) return tanhf(x);
+  return x;
+}
+
+template <int MODE> struct Cfg {
+  static constexpr int STAGES = MODE == 2 ? 3 : 6;
+  static constexpr int STAGE_BYTES = (MODE == 2 ? 4 : 2) * TILE_BYTES;
+  static constexpr int CONV_WARP0 = 4;                       // 3xTF32 converters: warps 4..7
+  static constexpr int EPI_WARP0 = MODE == 2 ? 8 : 4;        // epilogue: 4 warps
+  static constexpr int THREADS = (EPI_WARP0 + 4) * 32;
+  static constexpr int READY_COUNT = MODE == 2 ? 8 : 2;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 512;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(Cfg<MODE>::THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Tc2Params p) {
+  using C = Cfg<MODE>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* ready = bars + STAGES;
+  uint64_t* empty = bars + 2 * STAGES;
+  uint64_t* tfull = bars + 3 * STAGES;
+  uint64_t* tempty = bars + 3 * STAGES + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int total_kb = (int)((p.k + BK - 1) / BK);
+  const int num_items = p.tiles_m * p.tiles_n * p.splits;
+
+  auto tile_a = [&](int s) { return smem + s * C::STAGE_BYTES; };
+  auto tile_b = [&](int s) { return smem + s * C::STAGE_BYTES + TILE_BYTES; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], C::READY_COUNT);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();  // the peer's barriers exist before anyone arrives on them remotely
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> tile coordinates and k range
+  auto decode = [&](int item, int64_t& m0, int64_t& n0, int& kb0, int& nkb, int& split) {
+    split = item % p.splits;
+    int t = item / p.splits;
+    const int tn = t % p.tiles_n, tm = t / p.tiles_n;
+    m0 = (int64_t)tm * 256;
+    n0 = (int64_t)tn * 256;
+    kb0 = split * p.kb_per_split;
+    nkb = min(p.kb_per_split, total_kb - kb0);
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      uint32_t it = 0;  // global k-block counter -> stage / phase
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        int64_t m0, n0; int kb0, nkb, split;
+        decode(item, m0, n0, kb0, nkb, split);
+        const int32_t am = (int32_t)(m0 + 128 * rank), bn = (int32_t)(n0 + 128 * rank);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t use = it / STAGES;
+          mbar_wait(&empty[s], (use & 1) ^ 1);  // passes immediately on the first use of a stage
+          mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+          const int32_t k0 = (kb0 + kb) * BK;
+          if (!p.a_mn_major) tma_load_2d(&map_a, &full[s], tile_a(s), k0, am);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d(&map_a, &full[s], tile_a(s) + j * 4096, am + 32 * j, k0);
+          }
+          if (!p.b_mn_major) tma_load_2d(&map_b, &full[s], tile_b(s), k0, bn);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d(&map_b, &full[s], tile_b(s) + j * 4096, bn + 32 * j, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA, one thread) =================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc(p.a_mn_major, p.b_mn_major);
+      const uint32_t a_lbo = p.a_mn_major ? 4096 : 16, a_sbo = p.a_mn_major ? 512 : 1024, a_kstep = p.a_mn_major ? 1024 : 32;
+      const uint32_t b_lbo = p.b_mn_major ? 4096 : 16, b_sbo = p.b_mn_major ? 512 : 1024, b_kstep = p.b_mn_major ? 1024 : 32;
+      const uint32_t a_lt = p.a_mn_major ? 1 : 2, b_lt = p.b_mn_major ? 1 : 2;
+      uint32_t it = 0, tile_it = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters, ++tile_it) {
+        int64_t m0, n0; int kb0, nkb, split;
+        decode(item, m0, n0, kb0, nkb, split);
+        const uint32_t b = tile_it & 1, buse = tile_it >> 1;
+        mbar_wait(&tempty[b], (buse & 1) ^ 1);  // epilogues of both CTAs drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + b * BN;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t use = it / STAGES;
+          mbar_wait(&ready[s], use & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_u32(tile_a(s)), b_addr = smem_u32(tile_b(s));
+#pragma unroll
+          for (int k8 = 0; k8 < BK / 8; ++k8) {
+            const uint64_t da = make_desc(a_addr + k8 * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t db = make_desc(b_addr + k8 * b_kstep, b_lbo, b_sbo, b_lt);
+            if (MODE == 2) {
+              const uint64_t da_lo = make_desc(a_addr + 2 * TILE_BYTES + k8 * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t db_lo = make_desc(b_addr + 2 * TILE_BYTES + k8 * b_kstep, b_lbo, b_sbo, b_lt);
+              umma2_tf32(tmem_d, da_lo, db, idesc, accumulate);
+              umma2_tf32(tmem_d, da, db_lo, idesc, 1);
+              umma2_tf32(tmem_d, da, db, idesc, 1);
+            } else {
+              umma2_tf32(tmem_d, da, db, idesc, accumulate);
+            }
+            accumulate = 1;
+          }
+          umma2_commit(&empty[s]);
+        }
+        umma2_commit(&tfull[b]);
+      }
+    }
+  } else if (warp == 2 && MODE == 1) {
+    // ================= TF32 forwarder: local "tiles landed" -> leader's ready barrier =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        int64_t m0, n0; int kb0, nkb, split;
+        decode(item, m0, n0, kb0, nkb, split);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          mbar_arrive_cluster(&ready[s], 0);
+        }
+      }
+    }
+  } else if (MODE == 2 && warp >= C::CONV_WARP0 && warp < C::CONV_WARP0 + 4) {
+    // ================= 3xTF32 converters: lo = x - trunc_tf32(x) =================
+    const int ct = threadIdx.x - C::CONV_WARP0 * 32;  // 0..127
+    uint32_t it = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      int64_t m0, n0; int kb0, nkb, split;
+      decode(item, m0, n0, kb0, nkb, split);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        const uint4* src = reinterpret_cast<const uint4*>(tile_a(s));
+        uint4* dlo = reinterpret_cast<uint4*>(tile_a(s) + 2 * TILE_BYTES);
+#pragma unroll 4
+        for (int i = ct; i < 2 * TILE_BYTES / 16; i += 128) {
+          const uint4 v = src[i];
+          uint4 lo;
+          lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+          lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+          lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+          lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
+          dlo[i] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&ready[s], 0);
+      }
+    }
+  } else if (warp >= C::EPI_WARP0) {
+    // ================= epilogue: TMEM -> registers -> global (both CTAs, own 128 rows) =================
+    const int q = warp & 3;
+    uint32_t tile_it = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters, ++tile_it) {
+      int64_t m0, n0; int kb0, nkb, split;
+      decode(item, m0, n0, kb0, nkb, split);
+      const uint32_t b = tile_it & 1, buse = tile_it >> 1;
+      mbar_wait(&tfull[b], buse & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* c_out = p.c + (p.splits > 1 ? (int64_t)split * p.m * p.n : 0);
+      const int64_t m = m0 + 128 * rank + 32 * q + lane;
+      const bool m_ok = m < p.m;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        __syncwarp();
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * BN + c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int64_t nb = n0 + c * 32;
+        if (m_ok && nb < p.n) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]);
+            const int64_t n = nb + j;
+            if (n < p.n) {
+              if (p.accumulate) x += c_out[m * p.c_sm + n * p.c_sn];
+              if (p.epilogue == TCR_EPI_BIAS_N) x += p.bias[n];
+              else if (p.epilogue == TCR_EPI_BIAS_M) x += p.bias[m];
+              if (p.activation) x = act_f(p.activation, x);
+            }
+            v[j] = x;
+          }
+          float* row = c_out + m * p.c_sm + nb * p.c_sn;
+          if (p.c_sn == 1 && nb + 32 <= p.n && (((uintptr_t)row) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(row + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.n) row[j * p.c_sn] = v[j];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty[b], 0);  // this warp's quarter of accumulator b is free
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+__global__ void __launch_bounds__(256) splitk2_reduce_kernel(const float* __restrict__ ws, int splits, Tc2Params p) {
+  const int64_t total = p.m * p.n, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t m = i / p.n, n = i % p.n;
+    float x = 0.f;
+    for (int z = 0; z < splits; ++z) x += ws[(int64_t)z * total + i];
+    float* dst = p.c + m * p.c_sm + n * p.c_sn;
+    if (p.accumulate) x += *dst;
+    if (p.epilogue == TCR_EPI_BIAS_N) x += p.bias[n];
+    else if (p.epilogue == TCR_EPI_BIAS_M) x += p.bias[m];
+    if (p.activation) x = act_f(p.activation, x);
+    *dst = x;
+  }
+}
+
+template <int MODE>
+int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Params& p, int num_clusters) {
+  using C = Cfg<MODE>;
+  static bool configured = false;
+  if (!configured) {
+    TCR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * num_clusters);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = state().stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TCR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<MODE>, ma, mb, p));
+  state().launches.fetch_add(1, std::memory_order_relaxed);
+  return TCR_OK;
+}
+
+}  // namespace
+
+int make_tf32_map(CUtensorMap* map, const float* base, int64_t dim0, int64_t dim1, int64_t pitch, uint32_t box0, uint32_t box1, bool mn_major);  // gemm_tc.cu
+
+// 2-CTA path: returns handled = false when the problem should go to the single-CTA kernel
+int gemm_tc2_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc* d, int a_mn, int b_mn, int64_t a_pitch, int64_t b_pitch, bool* handled) {
+  *handled = false;
+  static const int enabled = std::getenv("TCR_GEMM_2CTA") ? std::atoi(std::getenv("TCR_GEMM_2CTA")) : 1;
+  if (!enabled || d->batch != 1) return TCR_OK;
+  if (d->m <= 128 || d->n <= 128) return TCR_OK;  // a 256x256 pair tile would be mostly padding
+  CUtensorMap ma, mb;
+  int rc = a_mn ? make_tf32_map(&ma, (const float*)a, d->m, d->k, a_pitch, 32, 32, true) : make_tf32_map(&ma, (const float*)a, d->k, d->m, a_pitch, 32, 128, false);
+  if (rc) return rc;
+  rc = b_mn ? make_tf32_map(&mb, (const float*)b, d->n, d->k, b_pitch, 32, 32, true) : make_tf32_map(&mb, (const float*)b, d->k, d->n, b_pitch, 32, 128, false);
+  if (rc) return rc;
+  Tc2Params p;
+  p.m = d->m; p.n = d->n; p.k = d->k;
+  p.c_sm = d->c_sm; p.c_sn = d->c_sn;
+  p.c = (float*)c;
+  p.bias = (const float*)d->bias;
+  p.epilogue = d->epilogue; p.activation = d->activation; p.accumulate = d->accumulate;
+  p.a_mn_major = a_mn; p.b_mn_major = b_mn;
+  p.tiles_m = (int)ceil_div(d->m, 256);
+  p.tiles_n = (int)ceil_div(d->n, 256);
+  const int total_kb = (int)ceil_div(d->k, BK);
+  const int pairs = state().sm_count / 2;
+  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+  int splits = 1;
+  if (tiles * 2 <= pairs && total_kb >= 16) {
+    double best = (double)tiles / (double)(ceil_div(tiles, pairs) * pairs);
+    for (int sp = 2; sp <= 64 && total_kb / sp >= 8; ++sp) {
+      double eff = (double)(tiles * sp) / (double)(ceil_div(tiles * sp, pairs) * pairs);
+      if (eff > best + 0.05) { best = eff; splits = sp; }
+    }
+  }
+  p.kb_per_split = (int)ceil_div(total_kb, splits);
+  splits = (int)ceil_div(total_kb, p.kb_per_split);
+  p.splits = splits;
+  void* ws = nullptr;
+  Tc2Params pk = p;
+  if (splits > 1) {
+    rc = tcr_alloc(&ws, sizeof(float) * (size_t)splits * d->m * d->n);
+    if (rc) return rc;
+    pk.c = (float*)ws; pk.c_sm = d->n; pk.c_sn = 1;
+    pk.epilogue = TCR_EPI_NONE; pk.activation = 0; pk.accumulate = 0; pk.bias = nullptr;
+  }
+  const int64_t items = tiles * splits;
+  const int num_clusters = (int)(items < pairs ? items : pairs);
+  rc = d->precision == TCR_GEMM_TF32 ? launch_tc2<1>(ma, mb, pk, num_clusters) : launch_tc2<2>(ma, mb, pk, num_clusters);
+  if (rc) return rc;
+  if (splits > 1) {
+    int grid = wave_grid(d->m * d->n, 256, 8);
+    TCR_LAUNCH(splitk2_reduce_kernel, grid, 256, 0, (const float*)ws, splits, p);
+    TCR_CHECK_LAUNCH();
+    tcr_free(ws);
+  }
+  *handled = true;
+  return TCR_OK;
+}
+
+}  // namespace tcr

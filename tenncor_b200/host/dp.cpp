@@ -1,5 +1,6 @@
 // dp.cpp — data-parallel group state and gradient marking.
 #include "dp.hpp"
+#include "planner.hpp"
 
 namespace dp {
 
@@ -25,6 +26,8 @@ void init(int rank, int nranks, const std::string& id, bool mean_reduce) {
 }
 
 void shutdown() {
+  cuda::drop_all_plans();  // captured graphs hold references on the communicator
+  tcr_sync();
   tcr_comm_destroy();
   g_rank = 0;
   g_size = 1;

@@ -3,6 +3,7 @@
 // teq::TravEvaluator::visit_func (internal/teq/evaluator.hpp:34-43) + eigen::Device::calc
 // (internal/eigen/device.hpp:555-570) + TensOp::assign (device.hpp:304-328).
 #include "planner.hpp"
+#include <set>
 
 #include <cstdlib>
 #include <cstring>
@@ -693,8 +694,25 @@ struct PlanCache {
   std::map<Key, std::unique_ptr<Plan>> plans;
 };
 
-PlanEvaluator::PlanEvaluator() : cache_(new PlanCache()) {}
-PlanEvaluator::~PlanEvaluator() { g_last_plan = nullptr; }
+static std::set<PlanEvaluator*>& live_evaluators() {
+  static auto* s = new std::set<PlanEvaluator*>();
+  return *s;
+}
+
+PlanEvaluator::PlanEvaluator() : cache_(new PlanCache()) { live_evaluators().insert(this); }
+PlanEvaluator::~PlanEvaluator() {
+  live_evaluators().erase(this);
+  g_last_plan = nullptr;
+}
+
+void PlanEvaluator::drop_plans() {
+  cache_->plans.clear();
+  g_last_plan = nullptr;
+}
+
+void drop_all_plans() {
+  for (auto e : live_evaluators()) e->drop_plans();
+}
 
 std::vector<StepTiming> profile_last_plan(int repeats) {
   if (!g_last_plan) global::fatal("profile_last_plan: no plan has been evaluated yet");

@@ -43,10 +43,15 @@ struct PlanEvaluator final : public teq::iEvaluator {
   PlanEvaluator();
   ~PlanEvaluator();
   void evaluate(teq::iDevice& device, const teq::TensSetT& targets, const teq::TensSetT& ignored = {}) override;
+  void drop_plans();
 
  private:
   std::unique_ptr<PlanCache> cache_;
 };
+
+/// destroy every cached plan (and its captured CUDA graph) of every live PlanEvaluator.  Must
+/// precede tcr_comm_destroy: NCCL waits for graphs holding captured collectives to be destroyed.
+void drop_all_plans();
 
 }  // namespace cuda
 

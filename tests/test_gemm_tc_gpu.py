@@ -77,3 +77,30 @@ def test_unaligned_operands_take_exact_path(gpu):
     got = run_gemm(gpu, A, B, 0, 0, 2)
     want = A.astype(np.float64) @ B.astype(np.float64)
     assert np.abs(got - want).max() < K * 1e-6
+
+
+def test_single_cta_kernel_still_correct_in_subprocess(gpu):
+    """TCR_GEMM_2CTA=0 forces the single-CTA 128x128 tcgen05 kernel (the dispatch reads the variable once,
+    so the check runs in a fresh interpreter)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from tenncor_b200 import cabi\n"
+        "from tests.test_gemm_tc_gpu import run_gemm\n"
+        "cabi.init(0)\n"
+        "rng = np.random.default_rng(0)\n"
+        "for (M, N, K, ta, tb) in [(256, 384, 96, 0, 0), (300, 200, 100, 1, 0), (512, 256, 4096, 1, 1), (1024, 784, 8192, 1, 0)]:\n"
+        "    A = rng.uniform(-1, 1, (M, K)).astype(np.float32); B = rng.uniform(-1, 1, (K, N)).astype(np.float32)\n"
+        "    want = A.astype(np.float64) @ B.astype(np.float64)\n"
+        "    S = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)\n"
+        "    for prec, tol in ((1, 2.0 ** -10), (2, 2.0 ** -19 + K * 2.0 ** -23)):\n"
+        "        got = run_gemm(cabi, A, B, ta, tb, prec)\n"
+        "        assert np.all(np.abs(got - want) <= S * tol), (M, N, K, prec)\n"
+        "print('OK')\n" % root)
+    env = dict(os.environ, TCR_GEMM_2CTA="0")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
