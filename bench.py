@@ -44,6 +44,7 @@ WORKLOADS = {
     "c4a": dict(kind="lstm", vocab=128, hidden=1024, seq=128, batch=None),
     "c4": dict(kind="lstm", vocab=128, hidden=1024, seq=128, batch=64),
     "c4gru": dict(kind="gru", vocab=128, hidden=1024, seq=128, batch=64),
+    "c5": dict(kind="dqn", nobs=10, nunits=9, nactions=9, nbatch=4096),
 }
 
 
@@ -58,6 +59,9 @@ def build_config(name):
     elif kind == "rbm":
         cfg = configs.rbm(name=name, **w)
         gen = lambda rng: ((rng.random(cfg.feeds["x"].shape()) < 0.5).astype(np.float32),)  # noqa: E731
+    elif kind == "dqn":
+        cfg = configs.dqn(name=name, **w)
+        gen = lambda rng: tuple(configs.dqn_batch(rng, cfg.feeds)[k] for k in cfg.feeds)  # noqa: E731
     else:
         cfg = configs.recurrent(kind, name=name, **w)
         gen = lambda rng: configs.recurrent_batch(rng, cfg.feeds, w["vocab"])  # noqa: E731
@@ -143,22 +147,31 @@ def dominant_kernel_roofline(cabi, name, w, peaks):
         c = cabi.empty(M * N, np.float32)
         d = cabi.GemmDesc(m=M, n=N, k=K, batch=1, a_sm=K, a_sk=1, b_sk=N, b_sn=1, c_sm=N, c_sn=1, dtype=F, precision=cabi.GEMM_3XTF32)
         call = lambda: cabi.check(lib.tcr_gemm(C.c_void_p(a.ptr), C.c_void_p(b.ptr), C.c_void_p(c.ptr), C.byref(d)))  # noqa: E731
-        for _ in range(3):
-            call()
-        cabi.sync()
-        iters = 20
-        start()
-        for _ in range(iters):
-            call()
-        ms = stop_ms() / iters
+
+        def timed(iters=20):
+            for _ in range(3):
+                call()
+            cabi.sync()
+            start()
+            for _ in range(iters):
+                call()
+            return stop_ms() / iters
+
+        ms = timed()
+        d.precision = cabi.GEMM_TF32  # the plain-TF32 variant of the same launch, reported beside the 3xTF32 product path
+        ms_tf32 = timed()
+        d.precision = cabi.GEMM_3XTF32
         flops = 2.0 * M * N * K
         # TF32 dense peak is not in MEASURED_PEAKS.json: half of the measured bf16 burst (B200_PROFILING.md table: tf32 = bf16 / 2)
         peak = peaks.get("bf16_tflops", 1590.0) / 2
         return {"bound": "tensor", "kernel": label, "achieved": round(flops / ms / 1e9, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
                 "frac": round(flops / ms / 1e9 / peak, 4), "traffic": None, "ms_per_launch": round(ms, 5),
+                "issued_mma_frac": round(3 * flops / ms / 1e9 / peak, 4),  # 3xTF32 issues 3 TF32 MMAs per algorithmic MMA
+                "tf32_variant": {"achieved": round(flops / ms_tf32 / 1e9, 2), "frac": round(flops / ms_tf32 / 1e9 / peak, 4), "ms_per_launch": round(ms_tf32, 5)},
                 "peak_source": "0.5 x measured bf16_tflops (MEASURED_PEAKS.json)" if "bf16_tflops" in peaks else "0.5 x fallback 1590"}
-    # RBM: HBM-bound elementwise/RNG over [784, B]
-    n = w["nvisible"] * w["nbatch"]
+    # RBM: HBM-bound elementwise/RNG over [784, B]; DQN: the same kernel over [nobs, B] (latency-bound at that size)
+    width = w.get("nvisible", w.get("nobs", 1))
+    n = width * w["nbatch"]
     x = cabi.to_device(rng.uniform(-4, 4, n).astype(np.float32))
     y = cabi.empty(n, np.float32)
     call = lambda: cabi.check(lib.tcr_unary(cabi.OP["SIGMOID"], C.c_void_p(x.ptr), C.c_void_p(y.ptr), C.c_int64(n), F))  # noqa: E731
@@ -170,7 +183,7 @@ def dominant_kernel_roofline(cabi, name, w, peaks):
         call()
     ms = stop_ms() / 50
     peak = peaks.get("hbm_gbs", 6650.0)
-    return {"bound": "hbm", "kernel": "tcr_unary SIGMOID [784,B]", "achieved": round(8 * n / ms / 1e6, 1), "peak": peak, "unit": "GB/s",
+    return {"bound": "hbm", "kernel": "tcr_unary SIGMOID [%d,B]" % width, "achieved": round(8 * n / ms / 1e6, 1), "peak": peak, "unit": "GB/s",
             "frac": round(8 * n / ms / 1e6 / peak, 4), "traffic": None, "ms_per_launch": round(ms, 5),
             "peak_source": "measured hbm_gbs (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650"}
 
@@ -256,7 +269,7 @@ def main():
     if world > 1:
         ids = [tc.dp.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
-        mean_loss = WORKLOADS[args.workload]["kind"] in ("mlp", "rbm")  # reduce_mean losses; the LSTM's NLL is a sum
+        mean_loss = WORKLOADS[args.workload]["kind"] in ("mlp", "rbm", "dqn")  # reduce_mean losses; the LSTM's NLL is a sum
         tc.dp.init(rank, world, ids[0], mean_reduce=mean_loss)
 
     cfg, gen, w = build_config(args.workload)

@@ -113,6 +113,14 @@ int tcr_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on
 /* CUDA-graph capture of a launch sequence (replaces the per-node host traversal of
  * teq::TravEvaluator::visit_func, internal/teq/evaluator.hpp:34-43, on replay). */
 int tcr_graph_begin(void);
+/* Capture lanes. Between tcr_graph_begin and tcr_graph_end the launcher may route launches to
+ * side lanes (lane 0 = the library stream) and order lanes with marks; independent steps then
+ * become parallel branches of the instantiated graph. tcr_graph_end joins every lane. Scratch
+ * memory obtained with tcr_alloc during capture is recycled per lane only. */
+#define TCR_GRAPH_LANES 8
+int tcr_graph_lane(int lane);
+int tcr_graph_record(int* mark_id);
+int tcr_graph_wait(int mark_id);
 int tcr_graph_end(void** out_exec);
 int tcr_graph_launch(void* exec);
 int tcr_graph_destroy(void* exec);

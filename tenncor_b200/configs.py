@@ -103,3 +103,67 @@ def rbm(nvisible=784, nhidden=64, nbatch=4096, learning_rate=0.01, discount=0.95
     variables = list({id(v): v for v in model.fwd().get_storage() + model.bwd().get_storage()}.values())
     return Config(name, train, {"x": visible}, model, variables, flops,
                   "RBM %d<->%d CD-1, batch %d" % (nvisible, nhidden, nbatch))
+
+
+def dqn(nobs=10, nunits=9, nactions=9, nbatch=4096, discount_rate=0.99, target_update_rate=0.01,
+        learning_rate=0.1, rms_discount=0.5, clip=5.0, seed=4, name="C5"):
+    """DQN training step: source + target copies of dense-sigmoid-dense-sigmoid, masked TD error,
+    rms_momentum with l2-norm clipping on the source net, soft update of the target net
+    (demo/dqn_demo.py:70-93, extenncor/dqn_trainer.py:15-48,72-92)."""
+    tc.seed(seed)
+    src_model = tc.api.layer.link([
+        tc.api.layer.dense([nobs], [nunits]),
+        tc.api.layer.bind(tc.api.sigmoid),
+        tc.api.layer.dense([nunits], [nactions]),
+        tc.api.layer.bind(tc.api.sigmoid),
+    ])
+    nxt_model = src_model.deep_clone()
+    src_obs = tc.EVariable([nbatch, nobs], 0, "src_obs")
+    nxt_obs = tc.EVariable([nbatch, nobs], 0, "nxt_obs")
+    src_outmask = tc.EVariable([nbatch, nactions], 1, "src_outmask")
+    nxt_outmask = tc.EVariable([nbatch], 1, "nxt_outmask")
+    rewards = tc.EVariable([nbatch], 0, "rewards")
+
+    def update(err, variables):
+        half = len(variables) // 2
+        src_vars, nxt_vars = variables[:half], variables[half:]
+        src_updates = tc.api.approx.rms_momentum(err, src_vars, learning_rate=learning_rate, discount_factor=rms_discount,
+                                                 apply=lambda x: tc.api.clip_by_l2norm(x, clip))
+        assigns = []
+        for nxt_var, (src_var, updated) in zip(nxt_vars, src_updates):
+            diff = nxt_var - updated
+            assigns.append((nxt_var, tc.api.assign_sub(nxt_var, target_update_rate * diff)))
+        return assigns
+
+    def error(models):
+        src_act = models[0].connect(src_obs)
+        nxt_act = models[1].connect(nxt_obs)
+        target_vals = nxt_outmask * tc.api.reduce_max_1d(nxt_act, 0)
+        future_reward = rewards + discount_rate * target_vals
+        masked = tc.api.reduce_sum_1d(src_act * src_outmask, 0)
+        return tc.api.reduce_mean(tc.api.square(masked - future_reward))
+
+    train = tc.apply_update([src_model, nxt_model], update, error)
+    # two forwards (source, target) + source backward without the input gradient
+    flops = 2 * (2 * nbatch * nobs * nunits + 2 * nbatch * nunits * nactions) + 2 * nbatch * nobs * nunits + 4 * nbatch * nunits * nactions
+    feeds = {"src_obs": src_obs, "nxt_obs": nxt_obs, "src_outmask": src_outmask, "nxt_outmask": nxt_outmask, "rewards": rewards}
+    variables = src_model.get_storage() + nxt_model.get_storage()
+    return Config(name, train, feeds, src_model, variables, flops,
+                  "DQN %d-%d-%d x2 (source/target), rms_momentum + clip, replay batch %d" % (nobs, nunits, nactions, nbatch))
+
+
+def dqn_batch(rng, cfg_feeds):
+    """observations ~ U[0,1), one-hot action mask, rewards ~ U[-1,1]."""
+    # shapes come back trimmed of trailing 1s (batch 1): recover the sizes from element counts
+    nb = int(np.prod(cfg_feeds["rewards"].shape()))
+    nobs = int(np.prod(cfg_feeds["src_obs"].shape())) // nb
+    nact = int(np.prod(cfg_feeds["src_outmask"].shape())) // nb
+    mask = np.zeros((nb, nact), dtype=np.float32)
+    mask[np.arange(nb), rng.integers(0, nact, nb)] = 1
+    return {
+        "src_obs": rng.random((nb, nobs), dtype=np.float32),
+        "nxt_obs": rng.random((nb, nobs), dtype=np.float32),
+        "src_outmask": mask,
+        "nxt_outmask": (rng.random(nb) < 0.95).astype(np.float32),
+        "rewards": rng.uniform(-1, 1, nb).astype(np.float32),
+    }

@@ -32,6 +32,7 @@ constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int TILE_BYTES = BM * BK * 4;  // 16 KiB (A tile == B tile)
 constexpr int NUM_THREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 28;  // bounded waits: a protocol bug traps instead of hanging the GPU
+constexpr int EPI_PITCH = 36;  // floats per staged epilogue row: 16-byte aligned, conflict-free for 128-bit accesses
 
 struct TcParams {
   int64_t m, n, k;
@@ -283,28 +284,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const int64_t nb = n0 + c * 32;
-      if (!m_ok || nb >= p.n) continue;
+      if (nb >= p.n) continue;  // warp-uniform
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]);
-        const int64_t n = nb + j;
-        if (n < p.n) {
-          if (p.accumulate) x += c_out[m * p.c_sm + n * p.c_sn];
-          if (p.epilogue == TCR_EPI_BIAS_N) x += p.bias[n];
-          else if (p.epilogue == TCR_EPI_BIAS_M) x += p.bias[m];
-          if (p.activation) x = act_f(p.activation, x);
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      // fast path (warp-uniform): rows go through shared memory (the pipeline stages are idle once
+      // tmem_full fired) so each store instruction writes four full 128-byte row segments
+      const bool fast = p.c_sn == 1 && nb + 32 <= p.n && (p.c_sm & 3) == 0 && ((((uintptr_t)c_out) & 15) == 0) && ((nb & 3) == 0) &&
+                        !(p.accumulate && (p.epilogue != TCR_EPI_NONE || p.activation));
+      if (fast) {
+        if (m_ok && (p.epilogue != TCR_EPI_NONE || p.activation)) {
+          const float bm = p.epilogue == TCR_EPI_BIAS_M ? p.bias[m] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j] + bm;
+            if (p.epilogue == TCR_EPI_BIAS_N) x += p.bias[nb + j];
+            if (p.activation) x = act_f(p.activation, x);
+            v[j] = x;
+          }
         }
-        v[j] = x;
-      }
-      float* row = c_out + m * p.c_sm + nb * p.c_sn;
-      if (p.c_sn == 1 && nb + 32 <= p.n && (((uintptr_t)row) & 15) == 0) {
+        float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * EPI_PITCH);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(row + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const int sub = lane >> 3, col = (lane & 7) * 4;
+        const int64_t mw = m0 + 32 * q;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nb + j < p.n) row[j * p.c_sn] = v[j];
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int row = rr + sub;
+          const int64_t gm = mw + row;
+          if (gm < p.m) {
+            float4 x = *reinterpret_cast<const float4*>(stage + row * EPI_PITCH + col);
+            float* dst = c_out + gm * p.c_sm + nb + col;
+            if (p.accumulate) {
+              const float4 o = *reinterpret_cast<const float4*>(dst);
+              x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+            }
+            *reinterpret_cast<float4*>(dst) = x;
+          }
+        }
+      } else if (m_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int64_t n = nb + j;
+          if (n < p.n) {
+            float x = v[j];
+            float* dst = c_out + m * p.c_sm + n * p.c_sn;
+            if (p.accumulate) x += *dst;
+            if (p.epilogue == TCR_EPI_BIAS_N) x += p.bias[n];
+            else if (p.epilogue == TCR_EPI_BIAS_M) x += p.bias[m];
+            if (p.activation) x = act_f(p.activation, x);
+            *dst = x;
+          }
+        }
       }
     }
   }

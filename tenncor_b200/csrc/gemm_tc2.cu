@@ -34,6 +34,7 @@ namespace {
 constexpr int BM_CTA = 128, BN_CTA = 128, BN = 256, BK = 32;
 constexpr int TILE_BYTES = 128 * BK * 4;  // 16 KiB per operand tile per CTA
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
+constexpr int EPI_PITCH = 36;  // floats per staged row: 16-byte aligned, conflict-free for 128-bit accesses
 
 struct Tc2Params {
   int64_t m, n, k;
@@ -62,7 +63,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
@@ -134,7 +135,7 @@ template <int MODE> struct Cfg {
   static constexpr int EPI_WARP0 = MODE == 2 ? 8 : 4;        // epilogue: 4 warps
   static constexpr int THREADS = (EPI_WARP0 + 4) * 32;
   static constexpr int READY_COUNT = MODE == 2 ? 8 : 2;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 512;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 512 + 4 * 32 * EPI_PITCH * 4;
 };
 
 template <int MODE>
@@ -151,6 +152,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* tfull = bars + 3 * STAGES;
   uint64_t* tempty = bars + 3 * STAGES + 2;
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4);
+  float* epi_stage = (float*)(smem + STAGES * C::STAGE_BYTES + 512);  // 4 warps x 32 rows x EPI_PITCH
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
@@ -333,28 +335,60 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int64_t nb = n0 + c * 32;
-        if (m_ok && nb < p.n) {
-          float v[32];
+        if (nb >= p.n) continue;  // warp-uniform
+        const int64_t mw = m0 + 128 * rank + 32 * q;  // first row of this warp
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        // fast path (warp-uniform): unit-stride, 16-byte aligned rows, whole 32-column chunk inside C.
+        // Rows are exchanged through shared memory so every store instruction writes four full
+        // 128-byte row segments instead of 32 scattered 16-byte pieces.
+        const bool fast = p.c_sn == 1 && nb + 32 <= p.n && (p.c_sm & 3) == 0 && ((((uintptr_t)c_out) & 15) == 0) && ((nb & 3) == 0) &&
+                          !(p.accumulate && (p.epilogue != TCR_EPI_NONE || p.activation));  // that mix keeps the scalar order: (x + C) + bias, then activation
+        if (fast) {
+          if (m_ok && (p.epilogue == TCR_EPI_BIAS_M || p.activation || p.epilogue == TCR_EPI_BIAS_N)) {
+            const float bm = p.epilogue == TCR_EPI_BIAS_M ? p.bias[m] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = v[j] + bm;
+              if (p.epilogue == TCR_EPI_BIAS_N) x += p.bias[nb + j];
+              if (p.activation) x = act_f(p.activation, x);
+              v[j] = x;
+            }
+          }
+          float* stage = epi_stage + (warp - C::EPI_WARP0) * (32 * EPI_PITCH);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+          const int sub = lane >> 3, col = (lane & 7) * 4;
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 4) {
+            const int row = rr + sub;
+            const int64_t gm = mw + row;
+            if (gm < p.m) {
+              float4 x = *reinterpret_cast<const float4*>(stage + row * EPI_PITCH + col);
+              float* dst = c_out + gm * p.c_sm + nb + col;
+              if (p.accumulate) {
+                const float4 o = *reinterpret_cast<const float4*>(dst);
+                x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+              }
+              *reinterpret_cast<float4*>(dst) = x;
+            }
+          }
+        } else if (m_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]);
             const int64_t n = nb + j;
             if (n < p.n) {
-              if (p.accumulate) x += c_out[m * p.c_sm + n * p.c_sn];
+              float x = v[j];
+              float* dst = c_out + m * p.c_sm + n * p.c_sn;
+              if (p.accumulate) x += *dst;
               if (p.epilogue == TCR_EPI_BIAS_N) x += p.bias[n];
               else if (p.epilogue == TCR_EPI_BIAS_M) x += p.bias[m];
               if (p.activation) x = act_f(p.activation, x);
+              *dst = x;
             }
-            v[j] = x;
-          }
-          float* row = c_out + m * p.c_sm + nb * p.c_sn;
-          if (p.c_sn == 1 && nb + 32 <= p.n && (((uintptr_t)row) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(row + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.n) row[j * p.c_sn] = v[j];
           }
         }
       }
@@ -456,7 +490,9 @@ int gemm_tc2_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc
     pk.epilogue = TCR_EPI_NONE; pk.activation = 0; pk.accumulate = 0; pk.bias = nullptr;
   }
   const int64_t items = tiles * splits;
-  const int num_clusters = (int)(items < pairs ? items : pairs);
+  int num_clusters = (int)(items < pairs ? items : pairs);
+  static const int cap = std::getenv("TCR_TC2_CLUSTERS") ? std::atoi(std::getenv("TCR_TC2_CLUSTERS")) : 0;  // experiment knob
+  if (cap > 0 && num_clusters > cap) num_clusters = cap;
   rc = d->precision == TCR_GEMM_TF32 ? launch_tc2<1>(ma, mb, pk, num_clusters) : launch_tc2<2>(ma, mb, pk, num_clusters);
   if (rc) return rc;
   if (splits > 1) {

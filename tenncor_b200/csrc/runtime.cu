@@ -49,7 +49,11 @@ struct Arena {
   // (its kernels keep their addresses): they are recycled only inside the capture and
   // return to the global pool when the graph is destroyed.
   bool capturing = false;
-  std::multimap<size_t, void*> capture_pool;
+  // one pool per capture lane: two lanes may run concurrently inside the graph, so a scratch
+  // block freed on one lane must not be handed to a kernel on another
+  std::multimap<size_t, void*> capture_pools[TCR_GRAPH_LANES];
+  int lane = 0;
+  std::multimap<size_t, void*>& capture_pool() { return capture_pools[lane]; }
   std::unordered_map<void*, std::vector<std::pair<size_t, void*>>> graph_blocks;
   std::unordered_map<void*, uint64_t> graph_kernels;  // kernel nodes per instantiated graph
 
@@ -140,11 +144,12 @@ int tcr_alloc(void** out, size_t bytes) {
   size_t b = Arena::bucket(bytes);
   std::lock_guard<std::mutex> lk(a.mu);
   void* p = nullptr;
-  auto cit = a.capturing ? a.capture_pool.find(b) : a.capture_pool.end();
+  auto& cpool = a.capture_pool();
+  auto cit = a.capturing ? cpool.find(b) : cpool.end();
   auto it = a.free_blocks.find(b);
-  if (cit != a.capture_pool.end()) {
+  if (cit != cpool.end()) {
     p = cit->second;
-    a.capture_pool.erase(cit);
+    cpool.erase(cit);
   } else if (it != a.free_blocks.end()) {
     p = it->second;
     a.free_blocks.erase(it);
@@ -177,7 +182,7 @@ int tcr_free(void* ptr) {
   std::lock_guard<std::mutex> lk(a.mu);
   auto it = a.live.find(ptr);
   TCR_ARG(it != a.live.end(), "tcr_free: pointer %p was not allocated by tcr_alloc", ptr);
-  if (a.capturing) a.capture_pool.emplace(it->second, ptr);
+  if (a.capturing) a.capture_pool().emplace(it->second, ptr);
   else a.free_blocks.emplace(it->second, ptr);
   a.in_use -= it->second;
   a.live.erase(it);
@@ -271,13 +276,81 @@ int tcr_event_elapsed_ms(void* start, void* stop, float* ms) {
 }
 
 // ---------------------------------------------------------------- graphs
+struct Lanes {
+  cudaStream_t origin = nullptr;
+  cudaStream_t side[TCR_GRAPH_LANES] = {};
+  bool forked[TCR_GRAPH_LANES] = {};
+  cudaEvent_t root = nullptr;
+  std::vector<cudaEvent_t> events;
+};
+static Lanes& lanes() {
+  static Lanes* l = new Lanes();
+  return *l;
+}
+
 int tcr_graph_begin(void) {
   TCR_REQUIRE_DEVICE();
   Arena& a = arena();
   TCR_ARG(!a.capturing, "tcr_graph_begin: a capture is already in progress");
-  TCR_CUDA(cudaStreamBeginCapture(state().stream, cudaStreamCaptureModeRelaxed));
+  Lanes& l = lanes();
+  l.origin = state().stream;
+  TCR_CUDA(cudaStreamBeginCapture(l.origin, cudaStreamCaptureModeRelaxed));
+  for (int i = 0; i < TCR_GRAPH_LANES; ++i) l.forked[i] = false;
+  l.forked[0] = true;
+  l.root = nullptr;
+  {  // side lanes join the capture by waiting on this mark of the origin stream
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+      l.events.push_back(ev);
+      if (cudaEventRecord(ev, l.origin) == cudaSuccess) l.root = ev;
+    }
+  }
   std::lock_guard<std::mutex> lk(a.mu);
   a.capturing = true;
+  a.lane = 0;
+  return TCR_OK;
+}
+
+// ---- capture lanes: independent steps of one plan are captured on side streams so the
+// instantiated graph has parallel branches (kernels that fill a fraction of the SMs overlap)
+int tcr_graph_lane(int lane) {
+  TCR_REQUIRE_DEVICE();
+  Arena& a = arena();
+  Lanes& l = lanes();
+  TCR_ARG(a.capturing, "tcr_graph_lane: no capture in progress");
+  TCR_ARG(lane >= 0 && lane < TCR_GRAPH_LANES, "tcr_graph_lane: lane %d out of range [0,%d)", lane, TCR_GRAPH_LANES);
+  if (lane > 0) {
+    if (l.side[lane] == nullptr) TCR_CUDA(cudaStreamCreateWithFlags(&l.side[lane], cudaStreamNonBlocking));
+    if (!l.forked[lane]) {
+      TCR_ARG(l.root != nullptr, "tcr_graph_lane: the capture has no root mark");
+      TCR_CUDA(cudaStreamWaitEvent(l.side[lane], l.root, 0));
+      l.forked[lane] = true;
+    }
+  }
+  state().stream = lane == 0 ? l.origin : l.side[lane];
+  std::lock_guard<std::mutex> lk(a.mu);
+  a.lane = lane;
+  return TCR_OK;
+}
+
+int tcr_graph_record(int* event_id) {
+  TCR_REQUIRE_DEVICE();
+  Lanes& l = lanes();
+  TCR_ARG(arena().capturing && event_id != nullptr, "tcr_graph_record: no capture in progress");
+  cudaEvent_t ev;
+  TCR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  l.events.push_back(ev);
+  TCR_CUDA(cudaEventRecord(ev, state().stream));
+  *event_id = (int)l.events.size() - 1;
+  return TCR_OK;
+}
+
+int tcr_graph_wait(int event_id) {
+  TCR_REQUIRE_DEVICE();
+  Lanes& l = lanes();
+  TCR_ARG(arena().capturing, "tcr_graph_wait: no capture in progress");
+  TCR_ARG(event_id >= 0 && event_id < (int)l.events.size(), "tcr_graph_wait: unknown mark %d", event_id);
+  TCR_CUDA(cudaStreamWaitEvent(state().stream, l.events[event_id], 0));
   return TCR_OK;
 }
 
@@ -285,14 +358,43 @@ int tcr_graph_end(void** out_exec) {
   TCR_REQUIRE_DEVICE();
   Arena& a = arena();
   std::vector<std::pair<size_t, void*>> held;
+  Lanes& l = lanes();
+  cudaError_t join_err = cudaSuccess;
+  if (l.origin != nullptr) {
+    // every side lane rejoins the origin stream before the capture ends
+    for (int i = 1; i < TCR_GRAPH_LANES; ++i) {
+      if (!l.forked[i]) continue;
+      cudaEvent_t ev;
+      cudaError_t je = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (je == cudaSuccess) {
+        l.events.push_back(ev);
+        je = cudaEventRecord(ev, l.side[i]);
+        if (je == cudaSuccess) je = cudaStreamWaitEvent(l.origin, ev, 0);
+      }
+      if (je != cudaSuccess) join_err = je;
+      l.forked[i] = false;
+    }
+    state().stream = l.origin;
+  }
   {
     std::lock_guard<std::mutex> lk(a.mu);
     a.capturing = false;
-    for (auto& kv : a.capture_pool) held.push_back({kv.first, kv.second});
-    a.capture_pool.clear();
+    a.lane = 0;
+    for (auto& pool : a.capture_pools) {
+      for (auto& kv : pool) held.push_back({kv.first, kv.second});
+      pool.clear();
+    }
   }
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(state().stream, &graph);
+  for (auto ev : l.events) cudaEventDestroy(ev);
+  l.events.clear();
+  l.root = nullptr;
+  if (e == cudaSuccess && join_err != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    graph = nullptr;
+    e = join_err;
+  }
   cudaGraphExec_t exec = nullptr;
   uint64_t n_kernels = 0;
   if (e == cudaSuccess) {

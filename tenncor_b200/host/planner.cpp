@@ -558,11 +558,104 @@ struct Plan {
     }
   }
 
+  void launch_one(Step& st) {
+    if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
+    else st.holder->launch_with(st.out, st.in);
+  }
+
   void launch_steps() {
-    for (auto& st : steps) {
-      if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
-      else st.holder->launch_with(st.out, st.in);
+    for (auto& st : steps) launch_one(st);
+  }
+
+  // ---------------------------------------------------------------- capture lanes
+  // Steps are ordered by the buffers they touch (read-after-write on producers, write-after-read
+  // and write-after-write on recycled buffers and on variables updated in place). Independent
+  // steps are captured on different lanes, so the graph runs them concurrently.
+  std::vector<int> step_lane;
+  std::vector<std::vector<int>> step_waits;  // cross-lane producers each step waits for
+  std::vector<char> step_marks;              // step is awaited from another lane
+  int lanes_used = 1;
+
+  void schedule_lanes(int n_lanes) {
+    const int ns = (int)steps.size();
+    step_lane.assign(ns, 0);
+    step_waits.assign(ns, {});
+    step_marks.assign(ns, 0);
+    lanes_used = 1;
+    if (n_lanes <= 1 || ns < 3) return;
+    std::unordered_map<const void*, int> last_writer;
+    std::unordered_map<const void*, std::vector<int>> readers;
+    std::vector<std::vector<int>> deps(ns);
+    int last_comm = -1;
+    for (int s = 0; s < ns; ++s) {
+      Step& st = steps[s];
+      std::vector<int>& d = deps[s];
+      auto read = [&](const void* base) {
+        auto w = last_writer.find(base);
+        if (w != last_writer.end()) d.push_back(w->second);
+        readers[base].push_back(s);
+      };
+      if (st.ew) for (auto& in : st.inputs) read(nodes[in.node].ptr);
+      else for (int in : st.in_nodes) read(nodes[in].ptr);
+      const void* out = nodes[st.out_node].ptr;
+      auto w = last_writer.find(out);
+      if (w != last_writer.end()) d.push_back(w->second);
+      auto r = readers.find(out);
+      if (r != readers.end()) {
+        for (int x : r->second)
+          if (x != s) d.push_back(x);
+        r->second.clear();
+      }
+      last_writer[out] = s;
+      if (!st.ew && nodes[st.out_node].op == IDENTITY) {  // collective: one communicator, program order
+        if (last_comm >= 0) d.push_back(last_comm);
+        last_comm = s;
+      }
+      std::sort(d.begin(), d.end());
+      d.erase(std::unique(d.begin(), d.end()), d.end());
     }
+    std::vector<int> lane_tail(n_lanes, -1);  // last step captured on each lane
+    for (int s = 0; s < ns; ++s) {
+      Step& st = steps[s];
+      int lane = -1;
+      if (!st.ew && nodes[st.out_node].op == IDENTITY) lane = 0;
+      if (lane < 0) {  // continue the lane of the latest producer when this step directly follows it there
+        for (auto it = deps[s].rbegin(); it != deps[s].rend(); ++it)
+          if (lane_tail[step_lane[*it]] == *it) { lane = step_lane[*it]; break; }
+      }
+      if (lane < 0) {  // otherwise the lane that has been idle longest
+        lane = 0;
+        for (int l = 1; l < n_lanes; ++l)
+          if (lane_tail[l] < lane_tail[lane]) lane = l;
+      }
+      step_lane[s] = lane;
+      lane_tail[lane] = s;
+      if (lane + 1 > lanes_used) lanes_used = lane + 1;
+      // one wait per foreign lane: its latest producer orders all earlier ones on that lane
+      std::vector<int> latest(n_lanes, -1);
+      for (int dstep : deps[s])
+        if (step_lane[dstep] != lane && dstep > latest[step_lane[dstep]]) latest[step_lane[dstep]] = dstep;
+      for (int l = 0; l < n_lanes; ++l)
+        if (latest[l] >= 0) {
+          step_waits[s].push_back(latest[l]);
+          step_marks[latest[l]] = 1;
+        }
+    }
+  }
+
+  void capture_steps_on_lanes() {
+    std::vector<int> mark(steps.size(), -1);
+    int current = 0;
+    for (size_t s = 0; s < steps.size(); ++s) {
+      if (step_lane[s] != current) {
+        check(tcr_graph_lane(step_lane[s]), "tcr_graph_lane");
+        current = step_lane[s];
+      }
+      for (int w : step_waits[s]) check(tcr_graph_wait(mark[w]), "tcr_graph_wait");
+      launch_one(steps[s]);
+      if (step_marks[s]) check(tcr_graph_record(&mark[s]), "tcr_graph_record");
+    }
+    if (current != 0) check(tcr_graph_lane(0), "tcr_graph_lane");
   }
 
   void build(const TensSetT& targets, const TensSetT& ignored, eigen::RTMemptrT mem) {
@@ -589,6 +682,10 @@ struct Plan {
     n_launch_steps = steps.size();
     // RAND_UNIF draws a fresh Philox offset at every launch: such plans are launched eagerly
     use_graph = !has_rand && std::getenv("TCR_NO_GRAPH") == nullptr && !steps.empty();
+    const char* lanes_env = std::getenv("TCR_GRAPH_LANES");
+    int n_lanes = lanes_env ? std::atoi(lanes_env) : TCR_GRAPH_LANES;
+    if (n_lanes > TCR_GRAPH_LANES) n_lanes = TCR_GRAPH_LANES;
+    if (use_graph) schedule_lanes(n_lanes);
   }
 
   bool still_valid() const {
@@ -667,7 +764,8 @@ struct Plan {
       if (!graph) {
         check(tcr_graph_begin(), "tcr_graph_begin");
         try {
-          launch_steps();
+          if (lanes_used > 1) capture_steps_on_lanes();
+          else launch_steps();
         } catch (...) {
           void* dead = nullptr;
           tcr_graph_end(&dead);

@@ -126,3 +126,27 @@ def test_version_gating_and_repeat_get(gpu):
     w1 = cfg.variables[0].data().copy()
     assert np.isfinite([e0, e1]).all() and e1 < e0  # second SGD step on the same batch lowers the error
     assert not np.array_equal(w0, w1)
+
+
+@pytest.mark.parametrize("evaluator", ["node", "plan"])
+@pytest.mark.parametrize("nbatch", [1, 32, 257])
+def test_dqn_training_matches_oracle(gpu, nbatch, evaluator):
+    """C5: source/target nets, masked TD error, rms_momentum + clip_by_l2norm, soft target update
+    (extenncor/dqn_trainer.py:15-48)."""
+    tc.set_evaluator(evaluator)
+    try:
+        cfg = configs.dqn(nbatch=nbatch)
+        sess = OracleSession([cfg.train])
+        rng = np.random.default_rng(4)
+        for step in range(4):
+            batch = configs.dqn_batch(rng, cfg.feeds)
+            for k, f in cfg.feeds.items():
+                f.assign(batch[k])
+                sess.assign(f, batch[k])
+            err = cfg.train.get()
+            want = sess.run()[0]
+            assert rel_err(err, want) < 1e-4, (step, err, want)
+        for v in cfg.variables:
+            assert rel_err(v.data(), sess.leaf_value(v)) < 1e-4
+    finally:
+        tc.set_evaluator("plan")
