@@ -453,6 +453,7 @@ int gemm_tc2_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc
   static const int enabled = std::getenv("TCR_GEMM_2CTA") ? std::atoi(std::getenv("TCR_GEMM_2CTA")) : 1;
   if (!enabled || d->batch != 1) return TCR_OK;
   if (d->m <= 128 || d->n <= 128) return TCR_OK;  // a 256x256 pair tile would be mostly padding
+  if (d->k < 8 * BK) return TCR_OK;                // too few k-blocks to amortise the persistent prologue (measured: 1152x1024x64)
   CUtensorMap ma, mb;
   int rc = a_mn ? make_tf32_map(&ma, (const float*)a, d->m, d->k, a_pitch, 32, 32, true) : make_tf32_map(&ma, (const float*)a, d->k, d->m, a_pitch, 32, 128, false);
   if (rc) return rc;

@@ -444,6 +444,7 @@ void typed_exec(egen::_GENERATED_OPCODE opcode, egen::_GENERATED_DTYPE dtype, ei
         dd.precision = dtype == FLOAT ? gemm_precision() : TCR_GEMM_EXACT;
         check(tcr_gemm(a[0], a[1], o, &dd), "tcr_gemm");
       });
+      static_cast<DevOp*>(out.get())->set_gemm(d);
     } break;
     case CONTRACT: {
       auto pairs = eigen::unpack_rankpairs(attrib);
@@ -456,6 +457,7 @@ void typed_exec(egen::_GENERATED_OPCODE opcode, egen::_GENERATED_DTYPE dtype, ei
           dd.precision = dtype == FLOAT ? gemm_precision() : TCR_GEMM_EXACT;
           check(tcr_gemm(a[0], a[1], o, &dd), "tcr_gemm");
         });
+        static_cast<DevOp*>(out.get())->set_gemm(d);
       } else {
         std::vector<int32_t> flat;
         for (auto& p : pairs) { flat.push_back(p.first); flat.push_back(p.second); }

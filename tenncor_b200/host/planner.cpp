@@ -47,6 +47,10 @@ struct PNode {
   void* ptr = nullptr;
   int step = -1;
   int region = -1;  // root node of the EW region this node is computed in
+  // GEMM with fused epilogue: this node (ADD of a bias, optionally through SIGMOID / TANH) is
+  // produced by the GEMM kernel of node `gemm_src`
+  int gemm_src = -1, gemm_bias = -1, gemm_epi = 0, gemm_act = 0;
+  bool gemm_transposed = false;  // PERMUTE{1,0} of a GEMM: computed as (B^T A^T), no copy
 };
 
 struct InputRef {
@@ -77,6 +81,9 @@ struct Step {
   std::vector<const void*> in;
   std::vector<int> in_nodes;
   std::vector<size_t> in_offsets;
+  // fused GEMM epilogue (in[2] = bias)
+  bool gemm_fused = false;
+  tcr_gemm_desc gemm;
 };
 
 }  // namespace
@@ -375,6 +382,114 @@ struct Plan {
     return false;
   }
 
+  // dense layers: act(CONTRACT(x, W) + EXTEND(b)) becomes one GEMM launch with a bias (+ activation)
+  // epilogue when the product and the sum have no other reader (cfg/tenncor/layer.yml:636-656,
+  // nn.yml:14-47: the backward pass reads the activation's output, not the pre-activation)
+  void fuse_gemm_epilogues() {
+    if (std::getenv("TCR_NO_GEMM_EPILOGUE")) return;
+    // weight gradients: PERMUTE{1,0}(CONTRACT(sup, x)) (backprop.hpp:269-359) = the product with
+    // its operands swapped; both operand majors are native to the GEMM kernels
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      PNode& n = nodes[i];
+      if (!n.func || n.is_view || n.op != PERMUTE || n.args.size() != 1) continue;
+      const int gi = nodes[n.args[0]].root;
+      PNode& g = nodes[gi];
+      if (nodes[n.args[0]].offset != 0 || !g.func || (g.op != CONTRACT && g.op != MATMUL) || g.exposed || g.inlined || g.consumers.size() != 1) continue;
+      auto gop = dynamic_cast<DevOp*>(g.holder);
+      if (!gop || !gop->gemm() || gop->gemm()->batch != 1) continue;
+      const tcr_gemm_desc& d = *gop->gemm();
+      if (d.c_sn != 1 || d.c_sm != d.n) continue;
+      RanksT order = eigen::unpack_ranks(*n.func);
+      if (order.size() < 2 || order[0] != 1 || order[1] != 0) continue;
+      bool rest_identity = true;
+      for (size_t r = 2; r < order.size() && r < rank_cap; ++r)
+        if (order[r] != r) rest_identity = false;
+      bool two_d = (int64_t)g.shape.at(0) == d.n && (int64_t)g.shape.at(1) == d.m;
+      for (int r = 2; r < rank_cap; ++r)
+        if (g.shape.at(r) != 1) two_d = false;
+      if (!rest_identity || !two_d) continue;
+      bool crosses = false;
+      for (int arg : g.args) {
+        auto it = assign_pos.find(nodes[arg].root);
+        if (it == assign_pos.end()) continue;
+        for (int pos : it->second)
+          if (pos > gi && pos < (int)i) crosses = true;
+      }
+      if (crosses) continue;
+      n.gemm_src = gi;
+      n.gemm_transposed = true;
+      g.inlined = true;
+    }
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      PNode& n = nodes[i];
+      if (!n.func || n.is_view || n.op != ADD || n.args.size() != 2 || n.dtype != FLOAT) continue;
+      for (int k = 0; k < 2; ++k) {
+        const int gi = nodes[n.args[k]].root, oi = nodes[n.args[1 - k]].root;
+        PNode& g = nodes[gi];
+        PNode& o = nodes[oi];
+        if (!g.func || (g.op != CONTRACT && g.op != MATMUL) || g.exposed || g.inlined || g.consumers.size() != 1) continue;
+        if (nodes[n.args[k]].offset != 0 || nodes[n.args[1 - k]].offset != 0 || !(g.shape == n.shape)) continue;
+        auto gop = dynamic_cast<DevOp*>(g.holder);
+        if (!gop || !gop->gemm() || gop->gemm()->batch != 1) continue;
+        if (!o.is_extend || o.has_scalar || o.exposed || !(o.shape == n.shape) || o.consumers.size() != 1) continue;
+        const PNode& b = nodes[o.args[0]];
+        // which GEMM index does the bias follow? C is row-major [m][n]: n spans the leading ranks
+        const tcr_gemm_desc& d = *gop->gemm();
+        if (d.c_sn != 1 || d.c_sm != d.n) continue;
+        int epi = 0;
+        {
+          int64_t lead = 1;
+          int r = 0;
+          for (; r < rank_cap && lead < d.n; ++r) lead *= n.shape.at(r);
+          if (lead != d.n) continue;
+          bool n_only = true, m_only = true;  // bias extents only inside / only outside the n ranks
+          for (int q = 0; q < rank_cap; ++q) {
+            const auto e = b.shape.at(q);
+            if (q < r) { if (e != n.shape.at(q)) n_only = false; if (e != 1) m_only = false; }
+            else { if (e != 1) n_only = false; if (e != n.shape.at(q)) m_only = false; }
+          }
+          if (n_only && b.n == d.n) epi = TCR_EPI_BIAS_N;
+          else if (m_only && b.n == d.m) epi = TCR_EPI_BIAS_M;
+          else continue;
+        }
+        // the GEMM moves to the position of the fused node: it must not cross an update of what it reads
+        int final_node = (int)i, act = 0;
+        if (!n.exposed && n.consumers.size() == 1) {
+          PNode& c = nodes[n.consumers[0]];
+          if ((c.op == SIGMOID || c.op == TANH) && c.args.size() == 1 && nodes[c.args[0]].root == (int)i && nodes[c.args[0]].offset == 0 &&
+              c.dtype == FLOAT && !c.is_view) {
+            final_node = n.consumers[0];
+            act = c.op;
+          }
+        }
+        bool crosses = false;
+        for (int arg : g.args) {
+          auto it = assign_pos.find(nodes[arg].root);
+          if (it == assign_pos.end()) continue;
+          for (int pos : it->second)
+            if (pos > gi && pos < final_node) crosses = true;
+        }
+        {
+          auto it = assign_pos.find(nodes[o.args[0]].root);
+          if (it != assign_pos.end())
+            for (int pos : it->second)
+              if (pos > oi && pos < final_node) crosses = true;
+        }
+        if (crosses) continue;
+        PNode& f = nodes[final_node];
+        f.gemm_src = gi;
+        f.gemm_bias = o.args[0];
+        f.gemm_epi = epi;
+        f.gemm_act = act;
+        f.is_ew = false;
+        g.inlined = true;
+        o.inlined = true;
+        if (final_node != (int)i) n.inlined = true;
+        break;
+      }
+    }
+  }
+
   void fuse() {
     for (size_t i = 0; i < nodes.size(); ++i)
       if (nodes[i].func && is_assign(nodes[i].op)) assign_pos[nodes[nodes[i].args[0]].root].push_back((int)i);
@@ -384,6 +499,7 @@ struct Plan {
       if (!n.func || n.is_view) continue;
       for (int a : n.args) nodes[nodes[a].root].consumers.push_back((int)i);
     }
+    fuse_gemm_epilogues();
     // non-EW consumers need real buffers: EXTEND operands get materialised. An EW node that cannot
     // be lowered on its own (too many operands / broadcast segments) is demoted to its holder's
     // kernel, which changes what its operands need — iterate to a fixed point.
@@ -393,6 +509,7 @@ struct Plan {
       for (size_t i = 0; i < nodes.size(); ++i) {
         PNode& n = nodes[i];
         if (!n.func || n.is_view) continue;
+        if (n.inlined || n.gemm_src >= 0) continue;  // absorbed into a GEMM epilogue: reads nothing itself
         bool ew_consumer = n.is_ew;
         for (size_t k = 0; k < n.args.size(); ++k) {
           PNode& a = nodes[nodes[n.args[k]].root];
@@ -464,6 +581,36 @@ struct Plan {
       if (!n.func || n.is_view || n.inlined) continue;
       if (n.is_extend && !n.needs_mat) continue;
       Step st;
+      if (n.gemm_src >= 0) {
+        PNode& g = nodes[n.gemm_src];
+        auto gop = dynamic_cast<DevOp*>(g.holder);
+        st.ew = false;
+        st.holder = gop;
+        st.out_node = (int)i;
+        st.gemm_fused = true;
+        st.gemm = *gop->gemm();
+        st.gemm.epilogue = n.gemm_epi;
+        st.gemm.activation = n.gemm_act;
+        if (n.gemm_transposed) {
+          // C^T (n x m, row-major) = B^T (n x k) * A^T (k x m)
+          const tcr_gemm_desc d = st.gemm;
+          st.gemm.m = d.n; st.gemm.n = d.m;
+          st.gemm.a_sm = d.b_sn; st.gemm.a_sk = d.b_sk;
+          st.gemm.b_sk = d.a_sk; st.gemm.b_sn = d.a_sm;
+          st.gemm.c_sm = d.m; st.gemm.c_sn = 1;
+          for (int a : {g.args[1], g.args[0]}) {
+            st.in_nodes.push_back(nodes[a].root);
+            st.in_offsets.push_back(nodes[a].offset);
+          }
+        } else
+        for (int a : {g.args[0], g.args[1], n.gemm_bias}) {
+          st.in_nodes.push_back(nodes[a].root);
+          st.in_offsets.push_back(nodes[a].offset);
+        }
+        n.step = (int)steps.size();
+        steps.push_back(std::move(st));
+        continue;
+      }
       if (n.is_ew && try_region((int)i, st)) {
         n.step = (int)steps.size();
         steps.push_back(std::move(st));
@@ -560,7 +707,12 @@ struct Plan {
 
   void launch_one(Step& st) {
     if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
-    else st.holder->launch_with(st.out, st.in);
+    else if (st.gemm_fused) {
+      tcr_gemm_desc d = st.gemm;
+      d.precision = d.dtype == FLOAT ? gemm_precision() : TCR_GEMM_EXACT;
+      d.bias = st.in.size() > 2 ? st.in[2] : nullptr;
+      check(tcr_gemm(st.in[0], st.in[1], st.out, &d), "tcr_gemm");
+    } else st.holder->launch_with(st.out, st.in);
   }
 
   void launch_steps() {
@@ -737,11 +889,13 @@ struct Plan {
         }
       } else {
         for (int in : st.in_nodes) t.bytes += (size_t)nodes[in].n * type_size(nodes[in].dtype);
+        if (st.gemm_fused && st.in.size() == 2) t.what = "GEMM^T m" + std::to_string(st.gemm.m) + " n" + std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
+        else if (st.gemm_fused) t.what = "GEMM+bias" + std::string(st.gemm.activation ? "+act" : "") + " m" + std::to_string(st.gemm.m) + " n" +
+                                    std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
+        else if (o.op == CONTRACT || o.op == MATMUL || o.op == CONV)
+          for (int a : o.args) t.what += " " + nodes[a].shape.to_string();
       }
-      auto once = [&] {
-        if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
-        else st.holder->launch_with(st.out, st.in);
-      };
+      auto once = [&] { launch_one(st); };
       once();
       check(tcr_event_record(e0), "tcr_event_record");
       for (int r = 0; r < repeats; ++r) once();

@@ -17,6 +17,8 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--precision", default="3xtf32")
     ap.add_argument("--json", default="")
+    ap.add_argument("--aggregate", action="store_true", help="group identical (step, shape) rows: for plans with thousands of steps")
+    ap.add_argument("--repeats", type=int, default=5)
     args = ap.parse_args()
     import tenncor_b200 as tc
     tc.set_evaluator("plan")
@@ -30,12 +32,28 @@ def main():
         for f in cfg.feeds.values():
             f.touch()
     tc.sync()
-    steps = tc.profile_plan(5)
+    import re
+    steps = tc.profile_plan(args.repeats)
+    for s in steps:  # compact shapes: drop trailing unit ranks
+        s["what"] = re.sub(r"(\\1)+\]", "]", s["what"])
+        s["shape"] = re.sub(r"(\\1)+\]", "]", s["shape"])
     total = sum(s["ms"] for s in steps)
     print("plan: %s" % tc.plan_stats())
     print("%-48s %-28s %9s %6s %9s" % ("step", "shape", "us", "%", "GB/s"))
-    for s in steps:
-        print("%-48s %-28s %9.1f %6.1f %9.1f" % (s["what"][:48], s["shape"][:28], s["ms"] * 1e3, 100 * s["ms"] / total, s["bytes"] / s["ms"] / 1e6))
+    if args.aggregate:
+        groups = {}
+        for s in steps:
+            g = groups.setdefault((s["what"], s["shape"]), {"n": 0, "ms": 0.0, "bytes": 0})
+            g["n"] += 1
+            g["ms"] += s["ms"]
+            g["bytes"] += s["bytes"]
+        print("%-5s %-44s %-24s %10s %6s %8s %9s" % ("count", "step", "shape", "total us", "%", "us each", "GB/s"))
+        for (what, shape), g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
+            print("%-5d %-44s %-24s %10.1f %6.1f %8.2f %9.1f" % (g["n"], what[:44], shape[:24], g["ms"] * 1e3, 100 * g["ms"] / total,
+                                                              g["ms"] * 1e3 / g["n"], g["bytes"] / g["ms"] / 1e6))
+    else:
+        for s in steps:
+            print("%-48s %-28s %9.1f %6.1f %9.1f" % (s["what"][:48], s["shape"][:28], s["ms"] * 1e3, 100 * s["ms"] / total, s["bytes"] / s["ms"] / 1e6))
     print("sum of steps: %.1f us" % (total * 1e3))
     if args.json:
         json.dump({"workload": args.workload, "steps": steps, "sum_ms": total}, open(args.json, "w"), indent=1)
