@@ -244,8 +244,12 @@ struct VmParams {
   int64_t d0, d1;  // segment extents (d2 implied)
   VmInput in[TCR_EW_MAX_INPUTS];
   tcr_ew_output out[TCR_EW_MAX_OUTPUTS];
-  tcr_ew_instr ins[TCR_EW_MAX_INSTRS];
+  tcr_ew_instr ins[TCR_EW_MAX_INSTRS];  // _pad[0] = VM_FWD_* flags computed by run_vm
+  uint8_t out_fwd[TCR_EW_MAX_OUTPUTS];  // output k is the value of the last instruction
 };
+// result forwarding: the value an instruction produces stays in hardware registers for the next
+// instruction; it is written to its shared-memory slot only when something later still reads it
+enum { VM_FWD_A = 1, VM_FWD_B = 2, VM_FWD_C = 4, VM_STORE = 8 };
 
 template <typename T>
 __device__ __forceinline__ T load_any(const void* p, int dtype, int64_t j) {
@@ -352,12 +356,20 @@ __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_c
       regs[k][threadIdx.x] = x;
     }
     // ---- execute
+    V4<T> last;
+#pragma unroll
+    for (int v = 0; v < VM_V; ++v) last.v[v] = T(0);
     for (int pc = 0; pc < p.n_instrs; ++pc) {
       const tcr_ew_instr& ins = p.ins[pc];
       const int op = ins.op;
-      V4<T> a = regs[ins.a][threadIdx.x], d;
+      const int fl = ins._pad[0];
+      V4<T> a, d;
+      if (fl & VM_FWD_A) a = last;
+      else if (op != TCR_EW_CONST) a = regs[ins.a][threadIdx.x];
       if (op >= TCR_EW_POW && op <= TCR_EW_GT) {
-        V4<T> b = regs[ins.b][threadIdx.x];
+        V4<T> b;
+        if (fl & VM_FWD_B) b = last;
+        else b = regs[ins.b][threadIdx.x];
         switch (op) {
 #define VMB(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d.v[v] = Ops<T>::bin(OP, a.v[v], b.v[v]); break;
           VMB(TCR_EW_ADD) VMB(TCR_EW_SUB) VMB(TCR_EW_MUL) VMB(TCR_EW_DIV) VMB(TCR_EW_POW) VMB(TCR_EW_MIN)
@@ -369,7 +381,11 @@ __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_c
 #pragma unroll
         for (int v = 0; v < VM_V; ++v) d.v[v] = (T)ins.imm;
       } else if (op == TCR_EW_SELECT) {
-        V4<T> b = regs[ins.b][threadIdx.x], c = regs[ins.c][threadIdx.x];
+        V4<T> b, c;
+        if (fl & VM_FWD_B) b = last;
+        else b = regs[ins.b][threadIdx.x];
+        if (fl & VM_FWD_C) c = last;
+        else c = regs[ins.c][threadIdx.x];
 #pragma unroll
         for (int v = 0; v < VM_V; ++v) d.v[v] = (a.v[v] != T(0)) ? b.v[v] : c.v[v];
       } else {
@@ -382,12 +398,15 @@ __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_c
           default: d = a;  // MOV
         }
       }
-      regs[ins.dst][threadIdx.x] = d;
+      if (fl & VM_STORE) regs[ins.dst][threadIdx.x] = d;
+      last = d;
     }
     // ---- store outputs
     for (int k = 0; k < p.n_outputs; ++k) {
       const tcr_ew_output& o = p.out[k];
-      V4<T> y = regs[o.reg][threadIdx.x];
+      V4<T> y;
+      if (p.out_fwd[k]) y = last;
+      else y = regs[o.reg][threadIdx.x];
       if (ALIGNED && full && o.dtype == DTypeOf<T>::value) {
         T* dst = (T*)o.ptr + base;
         *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(y.v);
@@ -450,6 +469,33 @@ static int run_vm(const tcr_ew_program* prog) {
             "tcr_elementwise: instr %d register out of range", k);
     p.ins[k] = ins;
   }
+  // forwarding flags
+  for (int i = 0; i < prog->n_instrs; ++i) {
+    tcr_ew_instr& ins = p.ins[i];
+    const int ar = op_arity(ins.op);
+    uint8_t fl = 0;
+    if (i > 0) {
+      const uint8_t prev = p.ins[i - 1].dst;
+      if (ar >= 1 && ins.a == prev) fl |= VM_FWD_A;
+      if (ar >= 2 && ins.b == prev) fl |= VM_FWD_B;
+      if (ar >= 3 && ins.c == prev) fl |= VM_FWD_C;
+    }
+    bool need = false, overwritten = false;
+    for (int j = i + 1; j < prog->n_instrs && !overwritten; ++j) {
+      const tcr_ew_instr& u = p.ins[j];
+      const int aj = op_arity(u.op);
+      const bool reads = (aj >= 1 && u.a == ins.dst) || (aj >= 2 && u.b == ins.dst) || (aj >= 3 && u.c == ins.dst);
+      if (reads && j != i + 1) need = true;  // j == i + 1 takes the forwarded copy
+      if (u.dst == ins.dst) overwritten = true;
+    }
+    if (!overwritten)
+      for (int k = 0; k < prog->n_outputs; ++k)
+        if (prog->outputs[k].reg == ins.dst && i != prog->n_instrs - 1) need = true;
+    if (need) fl |= VM_STORE;
+    ins._pad[0] = fl;
+  }
+  for (int k = 0; k < prog->n_outputs; ++k)
+    p.out_fwd[k] = prog->n_instrs > 0 && prog->outputs[k].reg == p.ins[prog->n_instrs - 1].dst;
   if (p.n == 0) return TCR_OK;
   constexpr int THREADS = VmCfg<T>::THREADS;
   int grid = wave_grid(ceil_div(p.n, VM_V), THREADS, sizeof(T) == 4 ? 6 : 6);

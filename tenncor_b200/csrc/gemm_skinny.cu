@@ -232,9 +232,11 @@ __global__ void __launch_bounds__(256, (SP * sizeof(T) <= 48 ? 2 : 1)) skinny_rk
   const bool single = d.K <= kc;
   auto stage = [&](int64_t kb) {
     const int64_t kw = d.K - kb < kc ? d.K - kb : kc;
-    for (int e = threadIdx.x; e < SP * kc; e += 256) {
-      const int s = e / kc, kk = e % kc;
-      ysm[e] = (s < d.S && kk < kw) ? Y[s * d.y_ss + (kb + kk) * d.y_sk] : T(0);
+    // (no div/mod by the run-time chunk length: this loop runs SP*kc/256 times per thread)
+#pragma unroll 1
+    for (int s = 0; s < SP; ++s) {
+      const T* yrow = Y + s * d.y_ss + kb * d.y_sk;
+      for (int kk = threadIdx.x; kk < kc; kk += 256) ysm[s * kc + kk] = (s < d.S && kk < kw) ? yrow[kk * d.y_sk] : T(0);
     }
   };
   if (single) {
@@ -392,6 +394,40 @@ __global__ void __launch_bounds__(256) small_k2_kernel(const T* __restrict__ A, 
   }
 }
 
+
+// K <= 16 and a narrow output (n <= 16, e.g. the 10-9-9 DQN layers at replay batch 4096): a thread
+// owns one row m; B (k x n) sits in shared memory and is read by broadcast
+template <typename T, int KP>
+__global__ void __launch_bounds__(256) small_kn_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C,
+                                                       const __grid_constant__ tcr_gemm_desc d) {
+  __shared__ T b_sm[KP][SK_MAX];
+  for (int e = threadIdx.x; e < KP * SK_MAX; e += 256) {
+    const int k = e / SK_MAX, n = e % SK_MAX;
+    b_sm[k][n] = (k < d.k && n < d.n) ? B[k * d.b_sk + n * d.b_sn] : T(0);
+  }
+  __syncthreads();
+  const T* bias = (const T*)d.bias;
+  for (int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x; m < d.m; m += (int64_t)gridDim.x * 256) {
+    T a[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) a[k] = k < d.k ? A[m * d.a_sm + k * d.a_sk] : T(0);
+#pragma unroll
+    for (int n = 0; n < SK_MAX; ++n) {
+      if (n < d.n) {
+        T v = T(0);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) v += a[k] * b_sm[k][n];
+        T* dst = C + m * d.c_sm + n * d.c_sn;
+        if (d.accumulate) v += *dst;
+        if (d.epilogue == TCR_EPI_BIAS_N) v += bias[n];
+        else if (d.epilogue == TCR_EPI_BIAS_M) v += bias[m];
+        if (d.activation) v = sk_act<T>(d.activation, v);
+        *dst = v;
+      }
+    }
+  }
+}
+
 template <typename T, int SP>
 static int launch_rk2(const T* X, const T* Y, T* C, const SkinnyDesc& d) {
   constexpr int V = 16 / sizeof(T), KSTEP = 32 * V;
@@ -507,7 +543,15 @@ int gemm_skinny_dispatch(const void* a, const void* b, void* c, const tcr_gemm_d
     if (gy > 4096) gy = 4096;
     dim3 grid((unsigned)ceil_div(d->n, 256), (unsigned)gy);
     static const int vec = std::getenv("TCR_SKINNY_VEC") ? std::atoi(std::getenv("TCR_SKINNY_VEC")) : 1;
-    if (vec) {
+    if (vec && d->n <= SK_MAX && d->m >= 256) {
+      int g1 = wave_grid(d->m, 256, 4);
+      TCR_DISPATCH_COMPUTE(d->dtype, T, {
+        if (d->k <= 4) TCR_LAUNCH((small_kn_kernel<T, 4>), g1, 256, 0, (const T*)a, (const T*)b, (T*)c, *d);
+        else if (d->k <= 8) TCR_LAUNCH((small_kn_kernel<T, 8>), g1, 256, 0, (const T*)a, (const T*)b, (T*)c, *d);
+        else if (d->k <= 12) TCR_LAUNCH((small_kn_kernel<T, 12>), g1, 256, 0, (const T*)a, (const T*)b, (T*)c, *d);
+        else TCR_LAUNCH((small_kn_kernel<T, 16>), g1, 256, 0, (const T*)a, (const T*)b, (T*)c, *d);
+      });
+    } else if (vec) {
       TCR_DISPATCH_COMPUTE(d->dtype, T, {
         if (d->k <= 4) TCR_LAUNCH((small_k2_kernel<T, 4>), grid, 256, 0, (const T*)a, (const T*)b, (T*)c, *d);
         else if (d->k <= 8) TCR_LAUNCH((small_k2_kernel<T, 8>), grid, 256, 0, (const T*)a, (const T*)b, (T*)c, *d);

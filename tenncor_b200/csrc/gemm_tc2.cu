@@ -348,12 +348,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (fast) {
           if (m_ok && (p.epilogue == TCR_EPI_BIAS_M || p.activation || p.epilogue == TCR_EPI_BIAS_N)) {
             const float bm = p.epilogue == TCR_EPI_BIAS_M ? p.bias[m] : 0.f;
+            // the opcode tests sit outside the element loops: 32 independent chains per lane
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = v[j] + bm;
-              if (p.epilogue == TCR_EPI_BIAS_N) x += p.bias[nb + j];
-              if (p.activation) x = act_f(p.activation, x);
-              v[j] = x;
+            for (int j = 0; j < 32; ++j) v[j] += bm;
+            if (p.epilogue == TCR_EPI_BIAS_N) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + nb);
+              if ((((uintptr_t)b4) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 t = __ldg(b4 + j);
+                  v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += p.bias[nb + j];
+              }
+            }
+            if (p.activation == TCR_EW_SIGMOID) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __frcp_rn(1.0f + expf(-v[j]));
+            } else if (p.activation == TCR_EW_TANH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
             }
           }
           float* stage = epi_stage + (warp - C::EPI_WARP0) * (32 * EPI_PITCH);

@@ -100,6 +100,17 @@ __global__ void __launch_bounds__(256) concat_one_kernel(const E* __restrict__ i
   }
 }
 
+// binary concat in one launch: rows of the output are [inner*ext0 from a | inner*ext1 from b]
+template <typename E>
+__global__ void __launch_bounds__(256) concat_pair_kernel(const E* __restrict__ a, const E* __restrict__ b, E* __restrict__ out,
+                                                          int64_t row0, int64_t row1, int64_t outer) {
+  const int64_t row = row0 + row1, n = row * outer, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i % row, o = i / row;
+    out[i] = r < row0 ? a[o * row0 + r] : b[o * row1 + (r - row0)];
+  }
+}
+
 // n-ary concat: every argument has extent 1 along the axis; args k0..k0+n-1 of `total`
 template <typename E>
 __global__ void __launch_bounds__(256) concat_many_kernel(const __grid_constant__ ConcatArgs a, E* __restrict__ out,
@@ -360,6 +371,19 @@ int tcr_concat(const void* const* args, const int64_t* shapes, int nargs, void* 
       for (int k = 0; k < ca.n; ++k) ca.ptr[k] = args[k0 + k];
       int grid = wave_grid(inner * outer * ca.n, 256, 8);
       TCR_DISPATCH_ELEM(elem_size, E, TCR_LAUNCH((concat_many_kernel<E>), grid, 256, 0, ca, (E*)out, inner, outer, k0, nargs));
+    }
+    TCR_CHECK_LAUNCH();
+    return TCR_OK;
+  }
+  if (nargs == 2 && outer > 1) {  // the recurrent cells' [x_t | h] input: one launch instead of one per argument
+    const int64_t row0 = inner * shapes[axis], row1 = inner * shapes[8 + axis];
+    const int64_t f = 16 / elem_size;
+    if (elem_size < 16 && row0 % f == 0 && row1 % f == 0 && (((uintptr_t)args[0] | (uintptr_t)args[1] | (uintptr_t)out) & 15) == 0) {
+      int grid = wave_grid((row0 + row1) / f * outer, 256, 8);
+      TCR_LAUNCH((concat_pair_kernel<uint4>), grid, 256, 0, (const uint4*)args[0], (const uint4*)args[1], (uint4*)out, row0 / f, row1 / f, outer);
+    } else {
+      int grid = wave_grid((row0 + row1) * outer, 256, 8);
+      TCR_DISPATCH_ELEM(elem_size, E, TCR_LAUNCH((concat_pair_kernel<E>), grid, 256, 0, (const E*)args[0], (const E*)args[1], (E*)out, row0, row1, outer));
     }
     TCR_CHECK_LAUNCH();
     return TCR_OK;
