@@ -244,7 +244,9 @@ struct VmParams {
   int64_t d0, d1;  // segment extents (d2 implied)
   VmInput in[TCR_EW_MAX_INPUTS];
   tcr_ew_output out[TCR_EW_MAX_OUTPUTS];
-  tcr_ew_instr ins[TCR_EW_MAX_INSTRS];  // _pad[0] = VM_FWD_* flags computed by run_vm
+  // packed instruction: op [0,8) | VM_* flags [8,16) | dst [16,20) | a [20,24) | b [24,28) | c [28,32)
+  uint32_t insw[TCR_EW_MAX_INSTRS];
+  double imm[TCR_EW_MAX_INSTRS];
   uint8_t out_fwd[TCR_EW_MAX_OUTPUTS];  // output k is the value of the last instruction
 };
 // result forwarding: the value an instruction produces stays in hardware registers for the next
@@ -289,132 +291,183 @@ constexpr int VM_V = 4;  // elements per thread per iteration
 template <typename T> struct alignas(16) V4 { T v[VM_V]; };
 template <typename T> struct VmCfg { static constexpr int THREADS = sizeof(T) == 4 ? 256 : 128; };
 
-// The virtual registers live in shared memory, one 4-element slot per (register, thread):
-// operand fetch is an LDS.128 with a computed address instead of a branch tree over
-// hardware registers, which keeps the kernel at ~40 registers (full occupancy) and makes
-// the cost of a VM instruction two shared loads, one uniform opcode branch and one store.
+// The virtual registers live in shared memory, one 4-element slot per (register, chunk, thread):
+// operand fetch is an LDS.128 with a computed address instead of a branch tree over hardware
+// registers. ncu (profiles/r1_ncu_ew_vm.md) showed the first version issue-bound (72 % issue
+// slots, ~410 instructions per 4 elements, 85 % of them decode / address arithmetic / branches),
+// so: (1) an instruction is one packed 32-bit word (op, flags, register numbers) fetched with a
+// single constant load; (2) each thread runs the program over VM_CH chunks per decode, halving
+// the per-element cost of decode, dispatch and loop control; (3) the value an instruction
+// produces is forwarded in hardware registers to the next instruction and only written to its
+// shared-memory slot when something later reads it.
+template <typename T> struct VmChunks { static constexpr int N = sizeof(T) == 4 ? 2 : 1; };
+
+template <typename T, typename I>
+__device__ __forceinline__ V4<T> vm_load_input(const VmInput& in, I base, I n, I d0, I d1, bool full, bool aligned) {
+  V4<T> x;
+  if (in.mode == 1) {
+    const T s = load_any<T>(in.ptr, in.dtype, 0);
+#pragma unroll
+    for (int v = 0; v < VM_V; ++v) x.v[v] = s;
+  } else if (in.mode == 0) {
+    if (aligned && full && in.dtype == DTypeOf<T>::value) {
+      const T* src = (const T*)in.ptr + base;
+      *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
+      if (sizeof(T) == 8) *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) x.v[v] = (base + v < n) ? load_any<T>(in.ptr, in.dtype, base + v) : T(0);
+    }
+  } else if (in.mode == 3) {
+    // 3-segment broadcast with D0 % 4 == 0: the chunk stays inside one run of segment 0
+    const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
+    const I i0 = base % d0, t = base / d0, i1 = t % d1, i2 = t / d1;
+    const I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
+    if (base >= n) {
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) x.v[v] = T(0);
+    } else if (in.bcast[0]) {
+      const T s = load_any<T>(in.ptr, in.dtype, j);
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) x.v[v] = s;
+    } else if (aligned && in.dtype == DTypeOf<T>::value) {
+      const T* src = (const T*)in.ptr + j;
+      *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
+      if (sizeof(T) == 8) *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) x.v[v] = load_any<T>(in.ptr, in.dtype, j + v);
+    }
+  } else {
+    const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
+#pragma unroll
+    for (int v = 0; v < VM_V; ++v) {
+      const I i = base + v;
+      if (i >= n) { x.v[v] = T(0); continue; }
+      const I i0 = i % d0, t = i / d0, i1 = t % d1, i2 = t / d1;
+      const I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
+      x.v[v] = load_any<T>(in.ptr, in.dtype, j);
+    }
+  }
+  return x;
+}
+
 template <typename T, bool ALIGNED, typename I>
 __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_constant__ VmParams p) {
-  constexpr int THREADS = VmCfg<T>::THREADS;
-  __shared__ V4<T> regs[TCR_EW_NREGS][THREADS];
+  constexpr int THREADS = VmCfg<T>::THREADS, CH = VmChunks<T>::N;
+  extern __shared__ __align__(16) unsigned char vm_smem[];
+  // slot of (register r, chunk c, thread t) = ((r * CH + c) * THREADS + t)
+  V4<T>* const mine = reinterpret_cast<V4<T>*>(vm_smem) + threadIdx.x;
+  constexpr int RSTRIDE = CH * THREADS;  // slots between consecutive registers
   const I n = (I)p.n;
   const I nchunks = (n + VM_V - 1) / VM_V;
-  const I stride = (I)gridDim.x * THREADS;
+  const I stride = (I)gridDim.x * (THREADS * CH);
   const I d0 = (I)p.d0, d1 = (I)p.d1;
-  for (I ch = (I)blockIdx.x * THREADS + threadIdx.x; ch < nchunks; ch += stride) {
-    const I base = ch * VM_V;
-    const bool full = base + VM_V <= n;
-    // ---- load inputs into registers 0..n_inputs-1
-    for (int k = 0; k < p.n_inputs; ++k) {
-      V4<T> x;
+  const int n_inputs = p.n_inputs, n_instrs = p.n_instrs, n_outputs = p.n_outputs;
+  for (I ch0 = (I)blockIdx.x * (THREADS * CH) + threadIdx.x; ch0 < nchunks; ch0 += stride) {
+    // ---- load inputs into registers 0..n_inputs-1 (all global loads are issued before the first use)
+    for (int k = 0; k < n_inputs; ++k) {
       const VmInput& in = p.in[k];
-      if (in.mode == 1) {
-        T s = load_any<T>(in.ptr, in.dtype, 0);
+      V4<T> x[CH];
 #pragma unroll
-        for (int v = 0; v < VM_V; ++v) x.v[v] = s;
-      } else if (in.mode == 0) {
-        if (ALIGNED && full && in.dtype == DTypeOf<T>::value) {
-          const T* src = (const T*)in.ptr + base;
-          if (sizeof(T) == 4) {
-            *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
-          } else {
-            *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
-            *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
-          }
-        } else {
-#pragma unroll
-          for (int v = 0; v < VM_V; ++v) x.v[v] = (base + v < n) ? load_any<T>(in.ptr, in.dtype, base + v) : T(0);
-        }
-      } else if (in.mode == 3) {
-        // 3-segment broadcast with D0 % 4 == 0: the chunk stays inside one run of segment 0
-        const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
-        I i0 = base % d0, t = base / d0, i1 = t % d1, i2 = t / d1;
-        I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
-        if (in.bcast[0]) {
-          T s = load_any<T>(in.ptr, in.dtype, j);
-#pragma unroll
-          for (int v = 0; v < VM_V; ++v) x.v[v] = s;
-        } else if (ALIGNED && in.dtype == DTypeOf<T>::value) {
-          const T* src = (const T*)in.ptr + j;
-          *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
-          if (sizeof(T) == 8) *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
-        } else {
-#pragma unroll
-          for (int v = 0; v < VM_V; ++v) x.v[v] = load_any<T>(in.ptr, in.dtype, j + v);
-        }
-      } else {
-        const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
-#pragma unroll
-        for (int v = 0; v < VM_V; ++v) {
-          I i = base + v;
-          if (i >= n) { x.v[v] = T(0); continue; }
-          I i0 = i % d0, t = i / d0, i1 = t % d1, i2 = t / d1;
-          I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
-          x.v[v] = load_any<T>(in.ptr, in.dtype, j);
-        }
+      for (int c = 0; c < CH; ++c) {
+        const I base = (ch0 + (I)c * THREADS) * VM_V;
+        x[c] = vm_load_input<T, I>(in, base, n, d0, d1, base + VM_V <= n, ALIGNED);
       }
-      regs[k][threadIdx.x] = x;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) mine[(k * CH + c) * THREADS] = x[c];
     }
     // ---- execute
-    V4<T> last;
+    V4<T> last[CH];
 #pragma unroll
-    for (int v = 0; v < VM_V; ++v) last.v[v] = T(0);
-    for (int pc = 0; pc < p.n_instrs; ++pc) {
-      const tcr_ew_instr& ins = p.ins[pc];
-      const int op = ins.op;
-      const int fl = ins._pad[0];
-      V4<T> a, d;
-      if (fl & VM_FWD_A) a = last;
-      else if (op != TCR_EW_CONST) a = regs[ins.a][threadIdx.x];
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) last[c].v[v] = T(0);
+    for (int pc = 0; pc < n_instrs; ++pc) {
+      const uint32_t w = p.insw[pc];
+      const int op = w & 0xff, fl = (w >> 8) & 0xff;
+      const V4<T>* ra = mine + ((w >> 20) & 0xf) * RSTRIDE;
+      const V4<T>* rb = mine + ((w >> 24) & 0xf) * RSTRIDE;
+      V4<T> a[CH], d[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        if (fl & VM_FWD_A) a[c] = last[c];
+        else a[c] = ra[c * THREADS];  // (CONST reads a slot it ignores: cheaper than another branch)
+      }
       if (op >= TCR_EW_POW && op <= TCR_EW_GT) {
-        V4<T> b;
-        if (fl & VM_FWD_B) b = last;
-        else b = regs[ins.b][threadIdx.x];
+        V4<T> b[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          if (fl & VM_FWD_B) b[c] = last[c];
+          else b[c] = rb[c * THREADS];
+        }
         switch (op) {
-#define VMB(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d.v[v] = Ops<T>::bin(OP, a.v[v], b.v[v]); break;
+#define VMB(OP) case OP: _Pragma("unroll") for (int c = 0; c < CH; ++c) _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d[c].v[v] = Ops<T>::bin(OP, a[c].v[v], b[c].v[v]); break;
           VMB(TCR_EW_ADD) VMB(TCR_EW_SUB) VMB(TCR_EW_MUL) VMB(TCR_EW_DIV) VMB(TCR_EW_POW) VMB(TCR_EW_MIN)
           VMB(TCR_EW_MAX) VMB(TCR_EW_EQ) VMB(TCR_EW_NEQ) VMB(TCR_EW_LT) VMB(TCR_EW_GT)
 #undef VMB
-          default: d = a;
+          default:
+#pragma unroll
+            for (int c = 0; c < CH; ++c) d[c] = a[c];
         }
       } else if (op == TCR_EW_CONST) {
+        const T imm = (T)p.imm[pc];
 #pragma unroll
-        for (int v = 0; v < VM_V; ++v) d.v[v] = (T)ins.imm;
+        for (int c = 0; c < CH; ++c)
+#pragma unroll
+          for (int v = 0; v < VM_V; ++v) d[c].v[v] = imm;
       } else if (op == TCR_EW_SELECT) {
-        V4<T> b, c;
-        if (fl & VM_FWD_B) b = last;
-        else b = regs[ins.b][threadIdx.x];
-        if (fl & VM_FWD_C) c = last;
-        else c = regs[ins.c][threadIdx.x];
+        const V4<T>* rc = mine + ((w >> 28) & 0xf) * RSTRIDE;
 #pragma unroll
-        for (int v = 0; v < VM_V; ++v) d.v[v] = (a.v[v] != T(0)) ? b.v[v] : c.v[v];
+        for (int c = 0; c < CH; ++c) {
+          V4<T> b, cc;
+          if (fl & VM_FWD_B) b = last[c];
+          else b = rb[c * THREADS];
+          if (fl & VM_FWD_C) cc = last[c];
+          else cc = rc[c * THREADS];
+#pragma unroll
+          for (int v = 0; v < VM_V; ++v) d[c].v[v] = (a[c].v[v] != T(0)) ? b.v[v] : cc.v[v];
+        }
       } else {
         switch (op) {
-#define VMU(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d.v[v] = Ops<T>::un(OP, a.v[v]); break;
+#define VMU(OP) case OP: _Pragma("unroll") for (int c = 0; c < CH; ++c) _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d[c].v[v] = Ops<T>::un(OP, a[c].v[v]); break;
           VMU(TCR_EW_SIGMOID) VMU(TCR_EW_TANH) VMU(TCR_EW_EXP) VMU(TCR_EW_NEG) VMU(TCR_EW_SQUARE) VMU(TCR_EW_LOG)
           VMU(TCR_EW_SQRT) VMU(TCR_EW_ABS) VMU(TCR_EW_SIN) VMU(TCR_EW_COS) VMU(TCR_EW_TAN) VMU(TCR_EW_ROUND)
           VMU(TCR_EW_CUBE)
 #undef VMU
-          default: d = a;  // MOV
+          default:  // MOV
+#pragma unroll
+            for (int c = 0; c < CH; ++c) d[c] = a[c];
         }
       }
-      if (fl & VM_STORE) regs[ins.dst][threadIdx.x] = d;
-      last = d;
+      if (fl & VM_STORE) {
+        V4<T>* rd = mine + ((w >> 16) & 0xf) * RSTRIDE;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) rd[c * THREADS] = d[c];
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) last[c] = d[c];
     }
     // ---- store outputs
-    for (int k = 0; k < p.n_outputs; ++k) {
+    for (int k = 0; k < n_outputs; ++k) {
       const tcr_ew_output& o = p.out[k];
-      V4<T> y;
-      if (p.out_fwd[k]) y = last;
-      else y = regs[o.reg][threadIdx.x];
-      if (ALIGNED && full && o.dtype == DTypeOf<T>::value) {
-        T* dst = (T*)o.ptr + base;
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(y.v);
-        if (sizeof(T) == 8) *reinterpret_cast<uint4*>(dst + 2) = *reinterpret_cast<const uint4*>(y.v + 2);
-      } else {
+      const bool fwd = p.out_fwd[k];
 #pragma unroll
-        for (int v = 0; v < VM_V; ++v)
-          if (base + v < n) store_any<T>(o.ptr, o.dtype, base + v, y.v[v]);
+      for (int c = 0; c < CH; ++c) {
+        const I base = (ch0 + (I)c * THREADS) * VM_V;
+        if (base >= n) continue;
+        V4<T> y;
+        if (fwd) y = last[c];
+        else y = mine[(o.reg * CH + c) * THREADS];
+        if (ALIGNED && base + VM_V <= n && o.dtype == DTypeOf<T>::value) {
+          T* dst = (T*)o.ptr + base;
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(y.v);
+          if (sizeof(T) == 8) *reinterpret_cast<uint4*>(dst + 2) = *reinterpret_cast<const uint4*>(y.v + 2);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VM_V; ++v)
+            if (base + v < n) store_any<T>(o.ptr, o.dtype, base + v, y.v[v]);
+        }
       }
     }
   }
@@ -467,45 +520,56 @@ static int run_vm(const tcr_ew_program* prog) {
     TCR_ARG(op_arity(ins.op) >= 0, "tcr_elementwise: instr %d has bad opcode %d", k, (int)ins.op);
     TCR_ARG(ins.dst < TCR_EW_NREGS && ins.a < TCR_EW_NREGS && ins.b < TCR_EW_NREGS && ins.c < TCR_EW_NREGS,
             "tcr_elementwise: instr %d register out of range", k);
-    p.ins[k] = ins;
   }
-  // forwarding flags
+  // pack the instructions and compute the forwarding flags
+  const tcr_ew_instr* ins = prog->instrs;
   for (int i = 0; i < prog->n_instrs; ++i) {
-    tcr_ew_instr& ins = p.ins[i];
-    const int ar = op_arity(ins.op);
-    uint8_t fl = 0;
+    const int ar = op_arity(ins[i].op);
+    uint32_t fl = 0;
     if (i > 0) {
-      const uint8_t prev = p.ins[i - 1].dst;
-      if (ar >= 1 && ins.a == prev) fl |= VM_FWD_A;
-      if (ar >= 2 && ins.b == prev) fl |= VM_FWD_B;
-      if (ar >= 3 && ins.c == prev) fl |= VM_FWD_C;
+      const uint8_t prev = ins[i - 1].dst;
+      if (ar >= 1 && ins[i].a == prev) fl |= VM_FWD_A;
+      if (ar >= 2 && ins[i].b == prev) fl |= VM_FWD_B;
+      if (ar >= 3 && ins[i].c == prev) fl |= VM_FWD_C;
     }
     bool need = false, overwritten = false;
     for (int j = i + 1; j < prog->n_instrs && !overwritten; ++j) {
-      const tcr_ew_instr& u = p.ins[j];
+      const tcr_ew_instr& u = ins[j];
       const int aj = op_arity(u.op);
-      const bool reads = (aj >= 1 && u.a == ins.dst) || (aj >= 2 && u.b == ins.dst) || (aj >= 3 && u.c == ins.dst);
+      const bool reads = (aj >= 1 && u.a == ins[i].dst) || (aj >= 2 && u.b == ins[i].dst) || (aj >= 3 && u.c == ins[i].dst);
       if (reads && j != i + 1) need = true;  // j == i + 1 takes the forwarded copy
-      if (u.dst == ins.dst) overwritten = true;
+      if (u.dst == ins[i].dst) overwritten = true;
     }
     if (!overwritten)
       for (int k = 0; k < prog->n_outputs; ++k)
-        if (prog->outputs[k].reg == ins.dst && i != prog->n_instrs - 1) need = true;
+        if (prog->outputs[k].reg == ins[i].dst && i != prog->n_instrs - 1) need = true;
     if (need) fl |= VM_STORE;
-    ins._pad[0] = fl;
+    p.insw[i] = (uint32_t)ins[i].op | (fl << 8) | ((uint32_t)ins[i].dst << 16) | ((uint32_t)ins[i].a << 20) |
+                ((uint32_t)ins[i].b << 24) | ((uint32_t)ins[i].c << 28);
+    p.imm[i] = ins[i].imm;
   }
   for (int k = 0; k < prog->n_outputs; ++k)
-    p.out_fwd[k] = prog->n_instrs > 0 && prog->outputs[k].reg == p.ins[prog->n_instrs - 1].dst;
+    p.out_fwd[k] = prog->n_instrs > 0 && prog->outputs[k].reg == ins[prog->n_instrs - 1].dst;
   if (p.n == 0) return TCR_OK;
-  constexpr int THREADS = VmCfg<T>::THREADS;
-  int grid = wave_grid(ceil_div(p.n, VM_V), THREADS, sizeof(T) == 4 ? 6 : 6);
-  const bool small = p.n < (1ll << 31);
+  constexpr int THREADS = VmCfg<T>::THREADS, CH = VmChunks<T>::N;
+  constexpr size_t SMEM = (size_t)TCR_EW_NREGS * CH * THREADS * sizeof(V4<T>);
+  static bool configured = false;
+  if (!configured) {
+    TCR_CUDA(cudaFuncSetAttribute(ew_vm_kernel<T, true, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    TCR_CUDA(cudaFuncSetAttribute(ew_vm_kernel<T, false, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    TCR_CUDA(cudaFuncSetAttribute(ew_vm_kernel<T, true, int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    TCR_CUDA(cudaFuncSetAttribute(ew_vm_kernel<T, false, int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    configured = true;
+  }
+  const int per_sm = (int)(220 * 1024 / SMEM) < 6 ? (int)(220 * 1024 / SMEM) : 6;
+  int grid = wave_grid(ceil_div(p.n, VM_V), THREADS * CH, per_sm);
+  const bool small = p.n < (1ll << 31) - (int64_t)4 * THREADS * CH * 148 * 8;
   if (small) {
-    if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, uint32_t>), grid, THREADS, 0, p);
-    else TCR_LAUNCH((ew_vm_kernel<T, false, uint32_t>), grid, THREADS, 0, p);
+    if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, uint32_t>), grid, THREADS, SMEM, p);
+    else TCR_LAUNCH((ew_vm_kernel<T, false, uint32_t>), grid, THREADS, SMEM, p);
   } else {
-    if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, int64_t>), grid, THREADS, 0, p);
-    else TCR_LAUNCH((ew_vm_kernel<T, false, int64_t>), grid, THREADS, 0, p);
+    if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, int64_t>), grid, THREADS, SMEM, p);
+    else TCR_LAUNCH((ew_vm_kernel<T, false, int64_t>), grid, THREADS, SMEM, p);
   }
   TCR_CHECK_LAUNCH();
   return TCR_OK;

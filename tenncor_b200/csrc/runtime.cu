@@ -14,6 +14,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cmath>
+
 #include "common.cuh"
 
 namespace tcr {
@@ -552,8 +554,11 @@ int tcr_allreduce_sum(void* buf, int64_t n, int dtype, double scale) {
       case TCR_INT64: nccl_type = 4; break;
       default: set_error("tcr_allreduce_sum: unsupported dtype %d", dtype); return TCR_ERR_DTYPE;
     }
-    int e = g_nccl.allreduce(buf, buf, (size_t)n, nccl_type, /*ncclSum*/ 0, g_nccl.comm, state().stream);
+    // mean over ranks (batch-normalised losses): NCCL's own averaging op, no second kernel
+    const bool avg = (dtype == TCR_FLOAT || dtype == TCR_DOUBLE) && fabs(scale * g_nccl.size - 1.0) < 1e-12;
+    int e = g_nccl.allreduce(buf, buf, (size_t)n, nccl_type, avg ? /*ncclAvg*/ 4 : /*ncclSum*/ 0, g_nccl.comm, state().stream);
     if (e) return nccl_fail(e, "ncclAllReduce");
+    if (avg) return TCR_OK;
   }
   if (scale != 1.0) return tcr_scale_inplace(buf, n, dtype, scale);
   return TCR_OK;

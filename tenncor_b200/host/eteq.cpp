@@ -291,7 +291,7 @@ void typed_exec(egen::_GENERATED_OPCODE opcode, egen::_GENERATED_DTYPE dtype, ei
         double scale = red->val_;
         args.resize(1);
         op([=](void* o, const std::vector<const void*>& a) {
-          check(tcr_d2d(o, a[0], out_bytes), "tcr_d2d");
+          if (o != a[0]) check(tcr_d2d(o, a[0], out_bytes), "tcr_d2d");  // the planner may run the exchange in place
           check(tcr_allreduce_sum(o, n_out, dtype, scale), "tcr_allreduce_sum");
         });
         break;

@@ -4,6 +4,7 @@
 // (internal/eigen/device.hpp:555-570) + TensOp::assign (device.hpp:304-328).
 #include "planner.hpp"
 #include <set>
+#include <algorithm>
 
 #include <cstdlib>
 #include <cstring>
@@ -662,6 +663,18 @@ struct Plan {
         if (!op) global::fatalf("planner: target %s cannot hold data", out.tens->to_string().c_str());
         out.ptr = op->ensure_buffer(1, memory);
         bound.push_back({st.out_node, out.ptr});
+      } else if (!st.ew && !st.gemm_fused && out.op == IDENTITY && st.in_nodes.size() == 1 && st.in_offsets[0] == 0 &&
+                 nodes[st.in_nodes[0]].func && nodes[st.in_nodes[0]].step >= 0 && !nodes[st.in_nodes[0]].exposed &&
+                 !is_assign(nodes[st.in_nodes[0]].op) && last_use[st.in_nodes[0]] == (int)s &&
+                 nodes[st.in_nodes[0]].n == out.n && nodes[st.in_nodes[0]].dtype == out.dtype) {
+        // gradient exchange in place: the all-reduce takes over its only producer's buffer (no copy)
+        const int in = st.in_nodes[0];
+        out.ptr = nodes[in].ptr;
+        auto& dl = dying[s];
+        dl.erase(std::remove(dl.begin(), dl.end(), in), dl.end());
+        int lu = last_use[st.out_node];
+        if (lu >= (int)s) dying[lu].push_back(st.out_node);
+        else dying[s].push_back(st.out_node);
       } else {
         size_t bytes = (size_t)out.n * type_size(out.dtype);
         size_t bucket = bytes < 512 ? 512 : bytes;
