@@ -10,6 +10,9 @@
 //     (scalar / leading block / trailing block) so EXTEND never materialises.
 #include <math.h>
 
+#include <cstdlib>
+#include <vector>
+
 #include "common.cuh"
 
 namespace tcr {
@@ -51,6 +54,17 @@ template <> __device__ __forceinline__ float m_abs(float x) { return fabsf(x); }
 template <> __device__ __forceinline__ double m_abs(double x) { return fabs(x); }
 // Eigen scalar_sigmoid_op: 1 / (1 + exp(-x))
 template <typename T> __device__ __forceinline__ T m_sigmoid(T x) { return T(1) / (T(1) + m_exp<T>(-x)); }
+// fp32: the denominator is >= 1, so the approximate reciprocal (<= 2 ulp, no slow path) is safe;
+// 1 / inf = 0 is the correct limit for x -> -inf
+template <> __device__ __forceinline__ float m_sigmoid(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
+
+// Heavy libm bodies (Payne-Hanek range reduction, pow) are kept out of line in the multi-opcode
+// kernels: inlined once per element per opcode case they made those kernels > 150 KB of SASS and
+// the instruction cache, not HBM, set their speed. The single-op direct kernels inline them.
+template <typename T> __device__ __noinline__ T m_sin_ool(T x) { return m_sin<T>(x); }
+template <typename T> __device__ __noinline__ T m_cos_ool(T x) { return m_cos<T>(x); }
+template <typename T> __device__ __noinline__ T m_tan_ool(T x) { return m_tan<T>(x); }
+template <typename T> __device__ __noinline__ T m_pow_ool(T x, T y) { return m_pow<T>(x, y); }
 
 template <typename T, bool IsFloat = (sizeof(typename Compute<T>::type) == sizeof(T) && !std::is_integral<T>::value)>
 struct Ops;
@@ -231,6 +245,20 @@ static int direct_binary(int op, const void* a, const void* b, void* out, int64_
   }
 }
 
+// opcode known at compile time inside a `case`: heavy bodies go out of line (see m_*_ool)
+template <typename T, int OP> __device__ __forceinline__ T vm_un(T a) {
+  using C = typename Compute<T>::type;
+  if (OP == TCR_EW_SIN) return T(m_sin_ool<C>((C)a));
+  if (OP == TCR_EW_COS) return T(m_cos_ool<C>((C)a));
+  if (OP == TCR_EW_TAN) return T(m_tan_ool<C>((C)a));
+  return Ops<T>::un(OP, a);
+}
+template <typename T, int OP> __device__ __forceinline__ T vm_bin(T a, T b) {
+  using C = typename Compute<T>::type;
+  if (OP == TCR_EW_POW) return T(m_pow_ool<C>((C)a, (C)b));
+  return Ops<T>::bin(OP, a, b);
+}
+
 // ------------------------------------------------------------------ register machine
 struct VmInput {
   const void* ptr;
@@ -244,14 +272,8 @@ struct VmParams {
   int64_t d0, d1;  // segment extents (d2 implied)
   VmInput in[TCR_EW_MAX_INPUTS];
   tcr_ew_output out[TCR_EW_MAX_OUTPUTS];
-  // packed instruction: op [0,8) | VM_* flags [8,16) | dst [16,20) | a [20,24) | b [24,28) | c [28,32)
-  uint32_t insw[TCR_EW_MAX_INSTRS];
-  double imm[TCR_EW_MAX_INSTRS];
-  uint8_t out_fwd[TCR_EW_MAX_OUTPUTS];  // output k is the value of the last instruction
+  tcr_ew_instr ins[TCR_EW_MAX_INSTRS];
 };
-// result forwarding: the value an instruction produces stays in hardware registers for the next
-// instruction; it is written to its shared-memory slot only when something later still reads it
-enum { VM_FWD_A = 1, VM_FWD_B = 2, VM_FWD_C = 4, VM_STORE = 8 };
 
 template <typename T>
 __device__ __forceinline__ T load_any(const void* p, int dtype, int64_t j) {
@@ -291,183 +313,117 @@ constexpr int VM_V = 4;  // elements per thread per iteration
 template <typename T> struct alignas(16) V4 { T v[VM_V]; };
 template <typename T> struct VmCfg { static constexpr int THREADS = sizeof(T) == 4 ? 256 : 128; };
 
-// The virtual registers live in shared memory, one 4-element slot per (register, chunk, thread):
-// operand fetch is an LDS.128 with a computed address instead of a branch tree over hardware
-// registers. ncu (profiles/r1_ncu_ew_vm.md) showed the first version issue-bound (72 % issue
-// slots, ~410 instructions per 4 elements, 85 % of them decode / address arithmetic / branches),
-// so: (1) an instruction is one packed 32-bit word (op, flags, register numbers) fetched with a
-// single constant load; (2) each thread runs the program over VM_CH chunks per decode, halving
-// the per-element cost of decode, dispatch and loop control; (3) the value an instruction
-// produces is forwarded in hardware registers to the next instruction and only written to its
-// shared-memory slot when something later reads it.
-template <typename T> struct VmChunks { static constexpr int N = sizeof(T) == 4 ? 2 : 1; };
-
-template <typename T, typename I>
-__device__ __forceinline__ V4<T> vm_load_input(const VmInput& in, I base, I n, I d0, I d1, bool full, bool aligned) {
-  V4<T> x;
-  if (in.mode == 1) {
-    const T s = load_any<T>(in.ptr, in.dtype, 0);
-#pragma unroll
-    for (int v = 0; v < VM_V; ++v) x.v[v] = s;
-  } else if (in.mode == 0) {
-    if (aligned && full && in.dtype == DTypeOf<T>::value) {
-      const T* src = (const T*)in.ptr + base;
-      *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
-      if (sizeof(T) == 8) *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
-    } else {
-#pragma unroll
-      for (int v = 0; v < VM_V; ++v) x.v[v] = (base + v < n) ? load_any<T>(in.ptr, in.dtype, base + v) : T(0);
-    }
-  } else if (in.mode == 3) {
-    // 3-segment broadcast with D0 % 4 == 0: the chunk stays inside one run of segment 0
-    const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
-    const I i0 = base % d0, t = base / d0, i1 = t % d1, i2 = t / d1;
-    const I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
-    if (base >= n) {
-#pragma unroll
-      for (int v = 0; v < VM_V; ++v) x.v[v] = T(0);
-    } else if (in.bcast[0]) {
-      const T s = load_any<T>(in.ptr, in.dtype, j);
-#pragma unroll
-      for (int v = 0; v < VM_V; ++v) x.v[v] = s;
-    } else if (aligned && in.dtype == DTypeOf<T>::value) {
-      const T* src = (const T*)in.ptr + j;
-      *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
-      if (sizeof(T) == 8) *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
-    } else {
-#pragma unroll
-      for (int v = 0; v < VM_V; ++v) x.v[v] = load_any<T>(in.ptr, in.dtype, j + v);
-    }
-  } else {
-    const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
-#pragma unroll
-    for (int v = 0; v < VM_V; ++v) {
-      const I i = base + v;
-      if (i >= n) { x.v[v] = T(0); continue; }
-      const I i0 = i % d0, t = i / d0, i1 = t % d1, i2 = t / d1;
-      const I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
-      x.v[v] = load_any<T>(in.ptr, in.dtype, j);
-    }
-  }
-  return x;
-}
-
+// The virtual registers live in shared memory, one 4-element slot per (register, thread):
+// operand fetch is an LDS.128 with a computed address instead of a branch tree over
+// hardware registers, which keeps the kernel at ~40 registers (full occupancy) and makes
+// the cost of a VM instruction two shared loads, one uniform opcode branch and one store.
 template <typename T, bool ALIGNED, typename I>
 __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_constant__ VmParams p) {
-  constexpr int THREADS = VmCfg<T>::THREADS, CH = VmChunks<T>::N;
-  extern __shared__ __align__(16) unsigned char vm_smem[];
-  // slot of (register r, chunk c, thread t) = ((r * CH + c) * THREADS + t)
-  V4<T>* const mine = reinterpret_cast<V4<T>*>(vm_smem) + threadIdx.x;
-  constexpr int RSTRIDE = CH * THREADS;  // slots between consecutive registers
+  constexpr int THREADS = VmCfg<T>::THREADS;
+  __shared__ V4<T> regs[TCR_EW_NREGS][THREADS];
   const I n = (I)p.n;
   const I nchunks = (n + VM_V - 1) / VM_V;
-  const I stride = (I)gridDim.x * (THREADS * CH);
+  const I stride = (I)gridDim.x * THREADS;
   const I d0 = (I)p.d0, d1 = (I)p.d1;
-  const int n_inputs = p.n_inputs, n_instrs = p.n_instrs, n_outputs = p.n_outputs;
-  for (I ch0 = (I)blockIdx.x * (THREADS * CH) + threadIdx.x; ch0 < nchunks; ch0 += stride) {
-    // ---- load inputs into registers 0..n_inputs-1 (all global loads are issued before the first use)
-    for (int k = 0; k < n_inputs; ++k) {
+  for (I ch = (I)blockIdx.x * THREADS + threadIdx.x; ch < nchunks; ch += stride) {
+    const I base = ch * VM_V;
+    const bool full = base + VM_V <= n;
+    // ---- load inputs into registers 0..n_inputs-1
+    for (int k = 0; k < p.n_inputs; ++k) {
+      V4<T> x;
       const VmInput& in = p.in[k];
-      V4<T> x[CH];
+      if (in.mode == 1) {
+        T s = load_any<T>(in.ptr, in.dtype, 0);
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const I base = (ch0 + (I)c * THREADS) * VM_V;
-        x[c] = vm_load_input<T, I>(in, base, n, d0, d1, base + VM_V <= n, ALIGNED);
+        for (int v = 0; v < VM_V; ++v) x.v[v] = s;
+      } else if (in.mode == 0) {
+        if (ALIGNED && full && in.dtype == DTypeOf<T>::value) {
+          const T* src = (const T*)in.ptr + base;
+          if (sizeof(T) == 4) {
+            *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
+          } else {
+            *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
+            *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < VM_V; ++v) x.v[v] = (base + v < n) ? load_any<T>(in.ptr, in.dtype, base + v) : T(0);
+        }
+      } else if (in.mode == 3) {
+        // 3-segment broadcast with D0 % 4 == 0: the chunk stays inside one run of segment 0
+        const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
+        I i0 = base % d0, t = base / d0, i1 = t % d1, i2 = t / d1;
+        I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
+        if (in.bcast[0]) {
+          T s = load_any<T>(in.ptr, in.dtype, j);
+#pragma unroll
+          for (int v = 0; v < VM_V; ++v) x.v[v] = s;
+        } else if (ALIGNED && in.dtype == DTypeOf<T>::value) {
+          const T* src = (const T*)in.ptr + j;
+          *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
+          if (sizeof(T) == 8) *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VM_V; ++v) x.v[v] = load_any<T>(in.ptr, in.dtype, j + v);
+        }
+      } else {
+        const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
+#pragma unroll
+        for (int v = 0; v < VM_V; ++v) {
+          I i = base + v;
+          if (i >= n) { x.v[v] = T(0); continue; }
+          I i0 = i % d0, t = i / d0, i1 = t % d1, i2 = t / d1;
+          I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
+          x.v[v] = load_any<T>(in.ptr, in.dtype, j);
+        }
       }
-#pragma unroll
-      for (int c = 0; c < CH; ++c) mine[(k * CH + c) * THREADS] = x[c];
+      regs[k][threadIdx.x] = x;
     }
     // ---- execute
-    V4<T> last[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c)
-#pragma unroll
-      for (int v = 0; v < VM_V; ++v) last[c].v[v] = T(0);
-    for (int pc = 0; pc < n_instrs; ++pc) {
-      const uint32_t w = p.insw[pc];
-      const int op = w & 0xff, fl = (w >> 8) & 0xff;
-      const V4<T>* ra = mine + ((w >> 20) & 0xf) * RSTRIDE;
-      const V4<T>* rb = mine + ((w >> 24) & 0xf) * RSTRIDE;
-      V4<T> a[CH], d[CH];
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        if (fl & VM_FWD_A) a[c] = last[c];
-        else a[c] = ra[c * THREADS];  // (CONST reads a slot it ignores: cheaper than another branch)
-      }
+    for (int pc = 0; pc < p.n_instrs; ++pc) {
+      const tcr_ew_instr& ins = p.ins[pc];
+      const int op = ins.op;
+      V4<T> a = regs[ins.a][threadIdx.x], d;
       if (op >= TCR_EW_POW && op <= TCR_EW_GT) {
-        V4<T> b[CH];
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          if (fl & VM_FWD_B) b[c] = last[c];
-          else b[c] = rb[c * THREADS];
-        }
+        V4<T> b = regs[ins.b][threadIdx.x];
         switch (op) {
-#define VMB(OP) case OP: _Pragma("unroll") for (int c = 0; c < CH; ++c) _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d[c].v[v] = Ops<T>::bin(OP, a[c].v[v], b[c].v[v]); break;
+#define VMB(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d.v[v] = vm_bin<T, OP>(a.v[v], b.v[v]); break;
           VMB(TCR_EW_ADD) VMB(TCR_EW_SUB) VMB(TCR_EW_MUL) VMB(TCR_EW_DIV) VMB(TCR_EW_POW) VMB(TCR_EW_MIN)
           VMB(TCR_EW_MAX) VMB(TCR_EW_EQ) VMB(TCR_EW_NEQ) VMB(TCR_EW_LT) VMB(TCR_EW_GT)
 #undef VMB
-          default:
-#pragma unroll
-            for (int c = 0; c < CH; ++c) d[c] = a[c];
+          default: d = a;
         }
       } else if (op == TCR_EW_CONST) {
-        const T imm = (T)p.imm[pc];
 #pragma unroll
-        for (int c = 0; c < CH; ++c)
-#pragma unroll
-          for (int v = 0; v < VM_V; ++v) d[c].v[v] = imm;
+        for (int v = 0; v < VM_V; ++v) d.v[v] = (T)ins.imm;
       } else if (op == TCR_EW_SELECT) {
-        const V4<T>* rc = mine + ((w >> 28) & 0xf) * RSTRIDE;
+        V4<T> b = regs[ins.b][threadIdx.x], c = regs[ins.c][threadIdx.x];
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          V4<T> b, cc;
-          if (fl & VM_FWD_B) b = last[c];
-          else b = rb[c * THREADS];
-          if (fl & VM_FWD_C) cc = last[c];
-          else cc = rc[c * THREADS];
-#pragma unroll
-          for (int v = 0; v < VM_V; ++v) d[c].v[v] = (a[c].v[v] != T(0)) ? b.v[v] : cc.v[v];
-        }
+        for (int v = 0; v < VM_V; ++v) d.v[v] = (a.v[v] != T(0)) ? b.v[v] : c.v[v];
       } else {
         switch (op) {
-#define VMU(OP) case OP: _Pragma("unroll") for (int c = 0; c < CH; ++c) _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d[c].v[v] = Ops<T>::un(OP, a[c].v[v]); break;
+#define VMU(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d.v[v] = vm_un<T, OP>(a.v[v]); break;
           VMU(TCR_EW_SIGMOID) VMU(TCR_EW_TANH) VMU(TCR_EW_EXP) VMU(TCR_EW_NEG) VMU(TCR_EW_SQUARE) VMU(TCR_EW_LOG)
           VMU(TCR_EW_SQRT) VMU(TCR_EW_ABS) VMU(TCR_EW_SIN) VMU(TCR_EW_COS) VMU(TCR_EW_TAN) VMU(TCR_EW_ROUND)
           VMU(TCR_EW_CUBE)
 #undef VMU
-          default:  // MOV
-#pragma unroll
-            for (int c = 0; c < CH; ++c) d[c] = a[c];
+          default: d = a;  // MOV
         }
       }
-      if (fl & VM_STORE) {
-        V4<T>* rd = mine + ((w >> 16) & 0xf) * RSTRIDE;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) rd[c * THREADS] = d[c];
-      }
-#pragma unroll
-      for (int c = 0; c < CH; ++c) last[c] = d[c];
+      regs[ins.dst][threadIdx.x] = d;
     }
     // ---- store outputs
-    for (int k = 0; k < n_outputs; ++k) {
+    for (int k = 0; k < p.n_outputs; ++k) {
       const tcr_ew_output& o = p.out[k];
-      const bool fwd = p.out_fwd[k];
+      V4<T> y = regs[o.reg][threadIdx.x];
+      if (ALIGNED && full && o.dtype == DTypeOf<T>::value) {
+        T* dst = (T*)o.ptr + base;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(y.v);
+        if (sizeof(T) == 8) *reinterpret_cast<uint4*>(dst + 2) = *reinterpret_cast<const uint4*>(y.v + 2);
+      } else {
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const I base = (ch0 + (I)c * THREADS) * VM_V;
-        if (base >= n) continue;
-        V4<T> y;
-        if (fwd) y = last[c];
-        else y = mine[(o.reg * CH + c) * THREADS];
-        if (ALIGNED && base + VM_V <= n && o.dtype == DTypeOf<T>::value) {
-          T* dst = (T*)o.ptr + base;
-          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(y.v);
-          if (sizeof(T) == 8) *reinterpret_cast<uint4*>(dst + 2) = *reinterpret_cast<const uint4*>(y.v + 2);
-        } else {
-#pragma unroll
-          for (int v = 0; v < VM_V; ++v)
-            if (base + v < n) store_any<T>(o.ptr, o.dtype, base + v, y.v[v]);
-        }
+        for (int v = 0; v < VM_V; ++v)
+          if (base + v < n) store_any<T>(o.ptr, o.dtype, base + v, y.v[v]);
       }
     }
   }
@@ -520,59 +476,378 @@ static int run_vm(const tcr_ew_program* prog) {
     TCR_ARG(op_arity(ins.op) >= 0, "tcr_elementwise: instr %d has bad opcode %d", k, (int)ins.op);
     TCR_ARG(ins.dst < TCR_EW_NREGS && ins.a < TCR_EW_NREGS && ins.b < TCR_EW_NREGS && ins.c < TCR_EW_NREGS,
             "tcr_elementwise: instr %d register out of range", k);
+    p.ins[k] = ins;
   }
-  // pack the instructions and compute the forwarding flags
-  const tcr_ew_instr* ins = prog->instrs;
-  for (int i = 0; i < prog->n_instrs; ++i) {
-    const int ar = op_arity(ins[i].op);
-    uint32_t fl = 0;
-    if (i > 0) {
-      const uint8_t prev = ins[i - 1].dst;
-      if (ar >= 1 && ins[i].a == prev) fl |= VM_FWD_A;
-      if (ar >= 2 && ins[i].b == prev) fl |= VM_FWD_B;
-      if (ar >= 3 && ins[i].c == prev) fl |= VM_FWD_C;
-    }
-    bool need = false, overwritten = false;
-    for (int j = i + 1; j < prog->n_instrs && !overwritten; ++j) {
-      const tcr_ew_instr& u = ins[j];
-      const int aj = op_arity(u.op);
-      const bool reads = (aj >= 1 && u.a == ins[i].dst) || (aj >= 2 && u.b == ins[i].dst) || (aj >= 3 && u.c == ins[i].dst);
-      if (reads && j != i + 1) need = true;  // j == i + 1 takes the forwarded copy
-      if (u.dst == ins[i].dst) overwritten = true;
-    }
-    if (!overwritten)
-      for (int k = 0; k < prog->n_outputs; ++k)
-        if (prog->outputs[k].reg == ins[i].dst && i != prog->n_instrs - 1) need = true;
-    if (need) fl |= VM_STORE;
-    p.insw[i] = (uint32_t)ins[i].op | (fl << 8) | ((uint32_t)ins[i].dst << 16) | ((uint32_t)ins[i].a << 20) |
-                ((uint32_t)ins[i].b << 24) | ((uint32_t)ins[i].c << 28);
-    p.imm[i] = ins[i].imm;
-  }
-  for (int k = 0; k < prog->n_outputs; ++k)
-    p.out_fwd[k] = prog->n_instrs > 0 && prog->outputs[k].reg == ins[prog->n_instrs - 1].dst;
   if (p.n == 0) return TCR_OK;
-  constexpr int THREADS = VmCfg<T>::THREADS, CH = VmChunks<T>::N;
-  constexpr size_t SMEM = (size_t)TCR_EW_NREGS * CH * THREADS * sizeof(V4<T>);
-  static bool configured = false;
-  if (!configured) {
-    TCR_CUDA(cudaFuncSetAttribute(ew_vm_kernel<T, true, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    TCR_CUDA(cudaFuncSetAttribute(ew_vm_kernel<T, false, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    TCR_CUDA(cudaFuncSetAttribute(ew_vm_kernel<T, true, int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    TCR_CUDA(cudaFuncSetAttribute(ew_vm_kernel<T, false, int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    configured = true;
-  }
-  const int per_sm = (int)(220 * 1024 / SMEM) < 6 ? (int)(220 * 1024 / SMEM) : 6;
-  int grid = wave_grid(ceil_div(p.n, VM_V), THREADS * CH, per_sm);
-  const bool small = p.n < (1ll << 31) - (int64_t)4 * THREADS * CH * 148 * 8;
+  constexpr int THREADS = VmCfg<T>::THREADS;
+  int grid = wave_grid(ceil_div(p.n, VM_V), THREADS, sizeof(T) == 4 ? 6 : 6);
+  const bool small = p.n < (1ll << 31);
   if (small) {
-    if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, uint32_t>), grid, THREADS, SMEM, p);
-    else TCR_LAUNCH((ew_vm_kernel<T, false, uint32_t>), grid, THREADS, SMEM, p);
+    if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, uint32_t>), grid, THREADS, 0, p);
+    else TCR_LAUNCH((ew_vm_kernel<T, false, uint32_t>), grid, THREADS, 0, p);
   } else {
-    if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, int64_t>), grid, THREADS, SMEM, p);
-    else TCR_LAUNCH((ew_vm_kernel<T, false, int64_t>), grid, THREADS, SMEM, p);
+    if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, int64_t>), grid, THREADS, 0, p);
+    else TCR_LAUNCH((ew_vm_kernel<T, false, int64_t>), grid, THREADS, 0, p);
   }
   TCR_CHECK_LAUNCH();
   return TCR_OK;
+}
+
+// ------------------------------------------------------------------ chain kernel
+// ncu showed the register machine above bound by instruction issue (72 % of issue slots, ~410
+// instructions per 4 elements, 85 % of them decode / address arithmetic / branches, see
+// profiles/r1_ncu_ew_vm.md). Most fused regions the planner emits are expression trees that a
+// two-deep stack evaluates (Strahler number <= 2: activations, their gradients, optimiser updates,
+// LSTM cell updates). Those run here: the program is re-coded on the host as <= 8 straight-line
+// steps over an accumulator `acc` and one temporary `tmp`; a step may consume one leaf.
+//   * intermediate values never leave hardware registers (no shared-memory register file);
+//   * leaves are staged global -> shared with cp.async into thread-private 16-byte slots, double
+//     buffered: the loads of iteration i+1 are in flight while iteration i computes, so bytes in
+//     flight per SM (~100 KB at 1024 threads x 96 B) are not capped by the register file — a first
+//     version that staged leaves in registers ran at 50 % of HBM with 16 warps per SM;
+//   * one non-unrolled step loop = one copy of the opcode switch (an unrolled loop was 360 KB of SASS).
+enum { CH_NONE = 0, CH_INIT, CH_PUSH, CH_UN, CH_AL, CH_LA, CH_TA, CH_AT };       // step forms
+enum { SL_NONE = 0, SL_FULL, SL_CONSTANT, SL_CHUNK, SL_GENERAL };                  // leaf kinds
+constexpr int CHAIN_MAXN = 8;
+
+struct ChainParams {
+  int32_t n_steps, n_staged;
+  int64_t n, d0, d1;
+  uint8_t form[CHAIN_MAXN], op[CHAIN_MAXN], kind[CHAIN_MAXN];
+  uint8_t stage[CHAIN_MAXN];  // staging slot of the leaf of step i (kinds FULL / CHUNK)
+  uint8_t bcast[CHAIN_MAXN][3];
+  int32_t dtype[CHAIN_MAXN];
+  const void* ptr[CHAIN_MAXN];
+  double imm[CHAIN_MAXN];
+  void* out;
+  int32_t out_dtype;
+};
+
+template <typename T, int CH>
+__device__ __forceinline__ void chain_apply(int op, bool unary, const V4<T> (&l)[CH], const V4<T> (&r)[CH], V4<T> (&d)[CH]) {
+  if (unary) {
+    switch (op) {
+#define CHU(OP) case OP: _Pragma("unroll") for (int c = 0; c < CH; ++c) _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d[c].v[v] = vm_un<T, OP>(l[c].v[v]); break;
+      CHU(TCR_EW_SIGMOID) CHU(TCR_EW_TANH) CHU(TCR_EW_EXP) CHU(TCR_EW_NEG) CHU(TCR_EW_SQUARE) CHU(TCR_EW_LOG)
+      CHU(TCR_EW_SQRT) CHU(TCR_EW_ABS) CHU(TCR_EW_SIN) CHU(TCR_EW_COS) CHU(TCR_EW_TAN) CHU(TCR_EW_ROUND) CHU(TCR_EW_CUBE)
+#undef CHU
+      default:
+#pragma unroll
+        for (int c = 0; c < CH; ++c) d[c] = l[c];
+    }
+  } else {
+    switch (op) {
+#define CHB(OP) case OP: _Pragma("unroll") for (int c = 0; c < CH; ++c) _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d[c].v[v] = vm_bin<T, OP>(l[c].v[v], r[c].v[v]); break;
+      CHB(TCR_EW_ADD) CHB(TCR_EW_SUB) CHB(TCR_EW_MUL) CHB(TCR_EW_DIV) CHB(TCR_EW_POW) CHB(TCR_EW_MIN)
+      CHB(TCR_EW_MAX) CHB(TCR_EW_EQ) CHB(TCR_EW_NEQ) CHB(TCR_EW_LT) CHB(TCR_EW_GT)
+#undef CHB
+      default:
+#pragma unroll
+        for (int c = 0; c < CH; ++c) d[c] = l[c];
+    }
+  }
+}
+
+// rare paths (mixed-type or unaligned leaves, ragged tail), out of line to keep the hot loop small
+template <typename T>
+__device__ __noinline__ V4<T> chain_load_general(const void* ptr, int dtype, bool b0, bool b1, bool b2, uint32_t base, uint32_t n,
+                                                 uint32_t d0, uint32_t d1) {
+  V4<T> x;
+  const uint32_t e0 = b0 ? 1 : d0, e1 = b1 ? 1 : d1;
+#pragma unroll 1
+  for (int v = 0; v < VM_V; ++v) {
+    const uint32_t e = base + v;
+    T val = T(0);
+    if (e < n) {
+      const uint32_t i0 = e % d0, t = e / d0, i1 = t % d1, i2 = t / d1;
+      val = load_any<T>(ptr, dtype, (b0 ? 0 : i0) + e0 * ((b1 ? 0 : i1) + e1 * (b2 ? 0 : i2)));
+    }
+    x.v[v] = val;
+  }
+  return x;
+}
+template <typename T>
+__device__ __noinline__ void chain_store_general(void* out, int dtype, uint32_t base, uint32_t n, V4<T> y) {
+#pragma unroll 1
+  for (int v = 0; v < VM_V; ++v)
+    if (base + v < n) store_any<T>(out, dtype, base + v, y.v[v]);
+}
+
+template <typename T, int CH>
+__global__ void __launch_bounds__(256, 3) ew_chain_kernel(const __grid_constant__ ChainParams p) {
+  constexpr int THREADS = 256;
+  using I = uint32_t;
+  extern __shared__ __align__(16) unsigned char chain_smem[];
+  // stage[buf][slot][chunk][thread]
+  V4<T>* const mine = reinterpret_cast<V4<T>*>(chain_smem) + threadIdx.x;
+  const int n_staged = p.n_staged;
+  const int buf_stride = n_staged * CH * THREADS;
+  const I n = (I)p.n, nchunks = (n + VM_V - 1) / VM_V;
+  const I stride = (I)gridDim.x * (THREADS * CH);
+  const I d0 = (I)p.d0, d1 = (I)p.d1;
+
+  // issue the asynchronous copies of one iteration into buffer `buf`
+  auto prefetch = [&](I ch0, int buf) {
+    if (ch0 < nchunks) {
+#pragma unroll 1
+      for (int i = 0; i < p.n_steps; ++i) {
+        const int kind = p.kind[i];
+        if (kind != SL_FULL && kind != SL_CHUNK) continue;
+        V4<T>* slot = mine + buf * buf_stride + p.stage[i] * (CH * THREADS);
+        const bool b0 = p.bcast[i][0], b1 = p.bcast[i][1], b2 = p.bcast[i][2];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const I base = (ch0 + (I)c * THREADS) * VM_V;
+          if (base + VM_V > n) continue;  // ragged tail: loaded at use
+          I j = base;
+          if (kind == SL_CHUNK) {
+            const I e0 = b0 ? 1 : d0, e1 = b1 ? 1 : d1;
+            const I i0 = base % d0, t = base / d0, i1 = t % d1, i2 = t / d1;
+            j = (b0 ? 0 : i0) + e0 * ((b1 ? 0 : i1) + e1 * (b2 ? 0 : i2));
+          }
+          const T* src = (const T*)p.ptr[i] + j;
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + c * THREADS);
+          if (kind == SL_CHUNK && b0) {
+            if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+            else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+          } else {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            if (sizeof(T) == 8) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 2) : "memory");
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  I ch0 = (I)blockIdx.x * (THREADS * CH) + threadIdx.x;
+  int buf = 0;
+  prefetch(ch0, 0);
+  for (; ch0 < nchunks; ch0 += stride, buf ^= 1) {
+    prefetch(ch0 + stride, buf ^ 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the newest group has landed
+    V4<T> acc[CH], tmp[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) { acc[c].v[v] = T(0); tmp[c].v[v] = T(0); }
+#pragma unroll 1
+    for (int i = 0; i < p.n_steps; ++i) {
+      const int form = p.form[i], kind = p.kind[i];
+      V4<T> leaf[CH];
+      if (kind == SL_FULL || kind == SL_CHUNK) {
+        const V4<T>* slot = mine + buf * buf_stride + p.stage[i] * (CH * THREADS);
+        const bool splat = kind == SL_CHUNK && p.bcast[i][0];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const I base = (ch0 + (I)c * THREADS) * VM_V;
+          if (base + VM_V <= n) {
+            leaf[c] = slot[c * THREADS];
+            if (splat) {
+#pragma unroll
+              for (int v = 1; v < VM_V; ++v) leaf[c].v[v] = leaf[c].v[0];
+            }
+          } else {
+            leaf[c] = chain_load_general<T>(p.ptr[i], p.dtype[i], p.bcast[i][0], p.bcast[i][1], p.bcast[i][2], base, n, d0, d1);
+          }
+        }
+      } else if (kind == SL_CONSTANT) {
+        const T s = p.ptr[i] ? load_any<T>(p.ptr[i], p.dtype[i], 0) : (T)p.imm[i];
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+#pragma unroll
+          for (int v = 0; v < VM_V; ++v) leaf[c].v[v] = s;
+      } else if (kind == SL_GENERAL) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          leaf[c] = chain_load_general<T>(p.ptr[i], p.dtype[i], p.bcast[i][0], p.bcast[i][1], p.bcast[i][2],
+                                          (ch0 + (I)c * THREADS) * VM_V, n, d0, d1);
+      }
+      if (form == CH_INIT) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] = leaf[c];
+      } else if (form == CH_PUSH) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { tmp[c] = acc[c]; acc[c] = leaf[c]; }
+      } else {
+        V4<T> l[CH], r[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          l[c] = form == CH_LA ? leaf[c] : (form == CH_TA ? tmp[c] : acc[c]);
+          r[c] = form == CH_AL ? leaf[c] : (form == CH_AT ? tmp[c] : acc[c]);
+        }
+        chain_apply<T, CH>(p.op[i], form == CH_UN, l, r, acc);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const I base = (ch0 + (I)c * THREADS) * VM_V;
+      if (base >= n) continue;
+      if (base + VM_V <= n && p.out_dtype == DTypeOf<T>::value) {
+        T* dst = (T*)p.out + base;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(acc[c].v);
+        if (sizeof(T) == 8) *reinterpret_cast<uint4*>(dst + 2) = *reinterpret_cast<const uint4*>(acc[c].v + 2);
+      } else {
+        chain_store_general<T>(p.out, p.out_dtype, base, n, acc[c]);
+      }
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// Host: re-code a tcr_ew_program as a chain. Returns false when the program is not a depth-2 tree.
+namespace {
+struct ChainExpr {
+  int kind;  // 0 input, 1 imm, 2 op
+  int op = 0, a = -1, b = -1, input = -1, uses = 0;
+  double imm = 0;
+};
+struct ChainCode {
+  int n = 0;
+  uint8_t form[8], op[8];
+  int leaf[8];  // expr id of the leaf consumed by step i, or -1
+};
+struct ChainGen {
+  std::vector<ChainExpr> ex;
+  ChainCode code;
+  bool emit(int form, int op, int leaf) {
+    if (code.n >= 8) return false;
+    code.form[code.n] = (uint8_t)form;
+    code.op[code.n] = (uint8_t)op;
+    code.leaf[code.n] = leaf;
+    ++code.n;
+    return true;
+  }
+  bool is_leaf(int e) const { return ex[e].kind != 2; }
+  // depth 0: acc free; depth 1: acc holds a live value that must survive in tmp
+  bool gen(int e, int depth) {
+    const ChainExpr& x = ex[e];
+    if (x.kind != 2) return emit(depth == 0 ? CH_INIT : CH_PUSH, 0, e);
+    if (x.uses > 1) return false;  // shared interior value: needs a named register
+    if (x.b < 0) return gen(x.a, depth) && emit(CH_UN, x.op, -1);
+    if (is_leaf(x.b)) return gen(x.a, depth) && emit(CH_AL, x.op, x.b);
+    if (is_leaf(x.a)) return gen(x.b, depth) && emit(CH_LA, x.op, x.a);
+    if (depth != 0) return false;
+    return gen(x.a, 0) && gen(x.b, 1) && emit(CH_TA, x.op, -1);
+  }
+};
+}  // namespace
+
+template <typename T, int CH>
+static int launch_chain(const ChainParams& p) {
+  const size_t smem = (size_t)2 * (p.n_staged > 0 ? p.n_staged : 1) * CH * 256 * sizeof(V4<T>);
+  static size_t configured = 0;
+  if (smem > configured) {
+    TCR_CUDA(cudaFuncSetAttribute(ew_chain_kernel<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  int per_sm = (int)(220 * 1024 / (smem + 1024));
+  if (per_sm > 3) per_sm = 3;
+  if (per_sm < 1) per_sm = 1;
+  int grid = wave_grid(ceil_div(p.n, VM_V), 256 * CH, per_sm);
+  TCR_LAUNCH((ew_chain_kernel<T, CH>), grid, 256, smem, p);
+  TCR_CHECK_LAUNCH();
+  return TCR_OK;
+}
+
+template <typename T>
+static bool try_chain(const tcr_ew_program* prog, int* rc) {
+  static const int enabled = std::getenv("TCR_EW_CHAIN") ? std::atoi(std::getenv("TCR_EW_CHAIN")) : 1;
+  if (!enabled || prog->n_outputs != 1 || prog->n_instrs < 1) return false;
+  const int64_t n = prog->dims[0] * prog->dims[1] * prog->dims[2];
+  if (n <= 0 || n >= (1ll << 31) - (1 << 22)) return false;
+  if (!aligned16(prog->outputs[0].ptr)) return false;
+  // registers -> expressions
+  ChainGen g;
+  int reg[TCR_EW_NREGS];
+  for (int r = 0; r < TCR_EW_NREGS; ++r) reg[r] = -1;
+  for (int k = 0; k < prog->n_inputs; ++k) {
+    ChainExpr e;
+    e.kind = 0;
+    e.input = k;
+    g.ex.push_back(e);
+    reg[k] = (int)g.ex.size() - 1;
+  }
+  for (int i = 0; i < prog->n_instrs; ++i) {
+    const tcr_ew_instr& ins = prog->instrs[i];
+    const int ar = op_arity(ins.op);
+    ChainExpr e;
+    if (ins.op == TCR_EW_CONST) {
+      e.kind = 1;
+      e.imm = ins.imm;
+    } else if (ins.op == TCR_EW_MOV) {
+      if (reg[ins.a] < 0) return false;
+      reg[ins.dst] = reg[ins.a];
+      continue;
+    } else if (ar == 1 || ar == 2) {
+      e.kind = 2;
+      e.op = ins.op;
+      e.a = reg[ins.a];
+      e.b = ar == 2 ? reg[ins.b] : -1;
+      if (e.a < 0 || (ar == 2 && e.b < 0)) return false;
+    } else {
+      return false;  // SELECT
+    }
+    g.ex.push_back(e);
+    reg[ins.dst] = (int)g.ex.size() - 1;
+  }
+  const int root = reg[prog->outputs[0].reg];
+  if (root < 0 || g.ex[root].kind != 2) return false;
+  // use counts over the tree reachable from the root
+  std::vector<int> stack{root};
+  g.ex[root].uses = 1;
+  while (!stack.empty()) {
+    const int e = stack.back();
+    stack.pop_back();
+    for (int child : {g.ex[e].a, g.ex[e].b}) {
+      if (child < 0) continue;
+      if (++g.ex[child].uses == 1 && g.ex[child].kind == 2) stack.push_back(child);
+    }
+  }
+  if (!g.gen(root, 0)) return false;
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_steps = g.code.n;
+  p.n = n;
+  p.d0 = prog->dims[0];
+  p.d1 = prog->dims[1];
+  p.out = prog->outputs[0].ptr;
+  p.out_dtype = prog->outputs[0].dtype;
+  int staged_of_input[TCR_EW_MAX_INPUTS];
+  for (int k = 0; k < TCR_EW_MAX_INPUTS; ++k) staged_of_input[k] = -1;
+  for (int i = 0; i < g.code.n; ++i) {
+    p.form[i] = g.code.form[i];
+    p.op[i] = g.code.op[i];
+    p.kind[i] = SL_NONE;
+    const int leaf = g.code.leaf[i];
+    if (leaf < 0) continue;
+    const ChainExpr& e = g.ex[leaf];
+    if (e.kind == 1) {
+      p.kind[i] = SL_CONSTANT;
+      p.imm[i] = e.imm;
+      continue;
+    }
+    const tcr_ew_input& in = prog->inputs[e.input];
+    if (in.ptr == nullptr || dtype_size(in.dtype) == 0) return false;
+    const bool b0 = in.bcast[0] && prog->dims[0] > 1, b1 = in.bcast[1] && prog->dims[1] > 1, b2 = in.bcast[2] && prog->dims[2] > 1;
+    const bool all = (b0 || prog->dims[0] == 1) && (b1 || prog->dims[1] == 1) && (b2 || prog->dims[2] == 1);
+    p.ptr[i] = in.ptr;
+    p.dtype[i] = in.dtype;
+    p.bcast[i][0] = b0; p.bcast[i][1] = b1; p.bcast[i][2] = b2;
+    const bool same = in.dtype == DTypeOf<T>::value;
+    if (all) p.kind[i] = SL_CONSTANT;
+    else if (!b0 && !b1 && !b2) p.kind[i] = (same && aligned16(in.ptr)) ? SL_FULL : SL_GENERAL;
+    else if (same && prog->dims[0] % VM_V == 0 && (b0 || aligned16(in.ptr))) p.kind[i] = SL_CHUNK;
+    else p.kind[i] = SL_GENERAL;
+    if (p.kind[i] == SL_FULL || p.kind[i] == SL_CHUNK) {
+      // an input read by several steps is staged once
+      if (staged_of_input[e.input] < 0) staged_of_input[e.input] = p.n_staged++;
+      p.stage[i] = (uint8_t)staged_of_input[e.input];
+    }
+  }
+  if (sizeof(T) == 4 && p.n_staged <= 4) *rc = launch_chain<T, 2>(p);
+  else *rc = launch_chain<T, 1>(p);
+  return true;
 }
 
 // ------------------------------------------------------------------ rand (Philox4x32-10)
@@ -671,7 +946,11 @@ int tcr_elementwise(const tcr_ew_program* prog) {
       });
     }
   }
-  TCR_DISPATCH_COMPUTE(prog->dtype, T, return run_vm<T>(prog));
+  TCR_DISPATCH_COMPUTE(prog->dtype, T, {
+    int rc = TCR_OK;
+    if (try_chain<T>(prog, &rc)) return rc;
+    return run_vm<T>(prog);
+  });
   return TCR_OK;
 }
 

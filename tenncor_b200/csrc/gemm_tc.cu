@@ -313,7 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (p.activation == TCR_EW_SIGMOID) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __frcp_rn(1.0f + expf(-v[j]));
+            for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.0f, 1.0f + expf(-v[j]));
           } else if (p.activation == TCR_EW_TANH) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);

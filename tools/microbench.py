@@ -72,6 +72,9 @@ def main():
         prog = cabi.make_program(F, (n, 1, 1), [(a.ptr, F, (0, 0, 0)), (b.ptr, F, (0, 0, 0)), (c.ptr, F, (0, 0, 0))], [(out.ptr, F, 0)],
                                  [(cabi.OP["MUL"], 0, 0, 1), (cabi.OP["ADD"], 0, 0, 2), (cabi.OP["SIGMOID"], 0, 0)])
         rec("ew_fused_sigmoid(a*b+c)_2^%d" % args.log2n, timeit(lambda: cabi.check(lib.tcr_elementwise(C.byref(prog)))), 16 * n)
+        prog3 = cabi.make_program(F, (n, 1, 1), [(a.ptr, F, (0, 0, 0)), (b.ptr, F, (0, 0, 0)), (c.ptr, F, (0, 0, 0))], [(out.ptr, F, 0)],
+                                  [(cabi.OP["MUL"], 0, 0, 1), (cabi.OP["ADD"], 0, 0, 2)])
+        rec("ew_fused_a*b+c_2^%d" % args.log2n, timeit(lambda: cabi.check(lib.tcr_elementwise(C.byref(prog3)))), 16 * n)
         rec("ew_assign_sub_2^%d" % args.log2n, timeit(lambda: cabi.check(lib.tcr_assign(cabi.OP["ASSIGN_SUB"], P(out), P(a), C.c_int64(n), F))), 12 * n)
         H, B = 1024, n // 1024
         bias = cabi.to_device(host[:H].copy())
