@@ -506,12 +506,17 @@ static int run_vm(const tcr_ew_program* prog) {
 //     flight per SM (~100 KB at 1024 threads x 96 B) are not capped by the register file — a first
 //     version that staged leaves in registers ran at 50 % of HBM with 16 warps per SM;
 //   * one non-unrolled step loop = one copy of the opcode switch (an unrolled loop was 360 KB of SASS).
-enum { CH_NONE = 0, CH_INIT, CH_PUSH, CH_UN, CH_AL, CH_LA, CH_TA, CH_AT };       // step forms
+// step forms: every binary step is acc = op(acc, leaf); a swapped operand order is folded into the
+// opcode (TCR_CH_REV bit); PUSH parks acc in a thread-private shared slot that a later POP reads back
+// as its leaf, so there is no second live register array and no operand select
+enum { CH_NONE = 0, CH_INIT, CH_PUSH, CH_UN, CH_BIN, CH_POP };
+constexpr int TCR_CH_REV = 0x80;
 enum { SL_NONE = 0, SL_FULL, SL_CONSTANT, SL_CHUNK, SL_GENERAL };                  // leaf kinds
 constexpr int CHAIN_MAXN = 8;
 
 struct ChainParams {
-  int32_t n_steps, n_staged;
+  int32_t n_steps, n_staged, n_buf;  // n_buf staging buffers: loads run n_buf - 1 iterations ahead
+  int32_t has_chunk;                 // some leaf is a partial broadcast: track the split index
   int64_t n, d0, d1;
   uint8_t form[CHAIN_MAXN], op[CHAIN_MAXN], kind[CHAIN_MAXN];
   uint8_t stage[CHAIN_MAXN];  // staging slot of the leaf of step i (kinds FULL / CHUNK)
@@ -524,26 +529,25 @@ struct ChainParams {
 };
 
 template <typename T, int CH>
-__device__ __forceinline__ void chain_apply(int op, bool unary, const V4<T> (&l)[CH], const V4<T> (&r)[CH], V4<T> (&d)[CH]) {
+__device__ __forceinline__ void chain_apply(int op, bool unary, V4<T> (&acc)[CH], const V4<T> (&r)[CH]) {
   if (unary) {
     switch (op) {
-#define CHU(OP) case OP: _Pragma("unroll") for (int c = 0; c < CH; ++c) _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d[c].v[v] = vm_un<T, OP>(l[c].v[v]); break;
+#define CHU(OP) case OP: _Pragma("unroll") for (int c = 0; c < CH; ++c) _Pragma("unroll") for (int v = 0; v < VM_V; ++v) acc[c].v[v] = vm_un<T, OP>(acc[c].v[v]); break;
       CHU(TCR_EW_SIGMOID) CHU(TCR_EW_TANH) CHU(TCR_EW_EXP) CHU(TCR_EW_NEG) CHU(TCR_EW_SQUARE) CHU(TCR_EW_LOG)
       CHU(TCR_EW_SQRT) CHU(TCR_EW_ABS) CHU(TCR_EW_SIN) CHU(TCR_EW_COS) CHU(TCR_EW_TAN) CHU(TCR_EW_ROUND) CHU(TCR_EW_CUBE)
 #undef CHU
-      default:
-#pragma unroll
-        for (int c = 0; c < CH; ++c) d[c] = l[c];
+      default: break;
     }
   } else {
     switch (op) {
-#define CHB(OP) case OP: _Pragma("unroll") for (int c = 0; c < CH; ++c) _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d[c].v[v] = vm_bin<T, OP>(l[c].v[v], r[c].v[v]); break;
+#define CHB(OP) case OP: _Pragma("unroll") for (int c = 0; c < CH; ++c) _Pragma("unroll") for (int v = 0; v < VM_V; ++v) acc[c].v[v] = vm_bin<T, OP>(acc[c].v[v], r[c].v[v]); break;
+#define CHR(OP) case (OP | TCR_CH_REV): _Pragma("unroll") for (int c = 0; c < CH; ++c) _Pragma("unroll") for (int v = 0; v < VM_V; ++v) acc[c].v[v] = vm_bin<T, OP>(r[c].v[v], acc[c].v[v]); break;
       CHB(TCR_EW_ADD) CHB(TCR_EW_SUB) CHB(TCR_EW_MUL) CHB(TCR_EW_DIV) CHB(TCR_EW_POW) CHB(TCR_EW_MIN)
       CHB(TCR_EW_MAX) CHB(TCR_EW_EQ) CHB(TCR_EW_NEQ) CHB(TCR_EW_LT) CHB(TCR_EW_GT)
+      CHR(TCR_EW_SUB) CHR(TCR_EW_DIV) CHR(TCR_EW_POW) CHR(TCR_EW_LT) CHR(TCR_EW_GT)
 #undef CHB
-      default:
-#pragma unroll
-        for (int c = 0; c < CH; ++c) d[c] = l[c];
+#undef CHR
+      default: break;
     }
   }
 }
@@ -574,7 +578,7 @@ __device__ __noinline__ void chain_store_general(void* out, int dtype, uint32_t 
 }
 
 template <typename T, int CH>
-__global__ void __launch_bounds__(256, 3) ew_chain_kernel(const __grid_constant__ ChainParams p) {
+__global__ void __launch_bounds__(256, 4) ew_chain_kernel(const __grid_constant__ ChainParams p) {
   constexpr int THREADS = 256;
   using I = uint32_t;
   extern __shared__ __align__(16) unsigned char chain_smem[];
@@ -586,7 +590,30 @@ __global__ void __launch_bounds__(256, 3) ew_chain_kernel(const __grid_constant_
   const I stride = (I)gridDim.x * (THREADS * CH);
   const I d0 = (I)p.d0, d1 = (I)p.d1;
 
-  // issue the asynchronous copies of one iteration into buffer `buf`
+  // (i0, i1, i2) of each chunk at the prefetch position, advanced by mixed-radix addition every
+  // iteration: broadcast leaves need the split index, and three integer divisions per chunk per
+  // iteration were 40 % of the instructions of a bias + sigmoid kernel
+  I pi0[CH], pi1[CH], pi2[CH];
+  I step0 = 0, step1 = 0, step2 = 0;  // the iteration stride, split the same way
+#pragma unroll
+  for (int c = 0; c < CH; ++c) pi0[c] = pi1[c] = pi2[c] = 0;
+  const bool has_chunk = p.has_chunk != 0;
+  if (has_chunk) {
+    const I se = stride * VM_V;
+    step0 = se % d0;
+    const I t = se / d0;
+    step1 = t % d1;
+    step2 = t / d1;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const I base = ((I)blockIdx.x * (THREADS * CH) + threadIdx.x + (I)c * THREADS) * VM_V;
+      pi0[c] = base % d0;
+      const I u = base / d0;
+      pi1[c] = u % d1;
+      pi2[c] = u / d1;
+    }
+  }
+  // issue the asynchronous copies of one iteration into buffer `buf` (called for consecutive iterations)
   auto prefetch = [&](I ch0, int buf) {
     if (ch0 < nchunks) {
 #pragma unroll 1
@@ -602,14 +629,16 @@ __global__ void __launch_bounds__(256, 3) ew_chain_kernel(const __grid_constant_
           I j = base;
           if (kind == SL_CHUNK) {
             const I e0 = b0 ? 1 : d0, e1 = b1 ? 1 : d1;
-            const I i0 = base % d0, t = base / d0, i1 = t % d1, i2 = t / d1;
-            j = (b0 ? 0 : i0) + e0 * ((b1 ? 0 : i1) + e1 * (b2 ? 0 : i2));
+            j = (b0 ? 0 : pi0[c]) + e0 * ((b1 ? 0 : pi1[c]) + e1 * (b2 ? 0 : pi2[c]));
           }
           const T* src = (const T*)p.ptr[i] + j;
           const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + c * THREADS);
           if (kind == SL_CHUNK && b0) {
             if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
             else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+          } else if (kind == SL_CHUNK) {  // re-read by many threads: keep it in L1
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 2) : "memory");
           } else {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
             if (sizeof(T) == 8) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 2) : "memory");
@@ -618,24 +647,43 @@ __global__ void __launch_bounds__(256, 3) ew_chain_kernel(const __grid_constant_
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    if (has_chunk)
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {  // advance to the next iteration's chunk
+      pi0[c] += step0;
+      I carry = 0;
+      if (pi0[c] >= d0) { pi0[c] -= d0; carry = 1; }
+      pi1[c] += step1 + carry;
+      carry = 0;
+      if (pi1[c] >= d1) { pi1[c] -= d1; carry = 1; }
+      pi2[c] += step2 + carry;
+    }
   };
 
   I ch0 = (I)blockIdx.x * (THREADS * CH) + threadIdx.x;
-  int buf = 0;
-  prefetch(ch0, 0);
-  for (; ch0 < nchunks; ch0 += stride, buf ^= 1) {
-    prefetch(ch0 + stride, buf ^ 1);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the newest group has landed
-    V4<T> acc[CH], tmp[CH];
+  const int n_buf = p.n_buf;
+  for (int k = 0; k < n_buf - 1; ++k) prefetch(ch0 + (I)k * stride, k);
+  int buf = 0, ahead = n_buf - 1;  // buffer of the current iteration / buffer the next prefetch fills
+  for (; ch0 < nchunks; ch0 += stride) {
+    prefetch(ch0 + (I)(n_buf - 1) * stride, ahead);
+    // everything but the newest n_buf - 1 groups has landed
+    if (n_buf == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else if (n_buf == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else asm volatile("cp.async.wait_group 3;" ::: "memory");
+    V4<T> acc[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c)
 #pragma unroll
-      for (int v = 0; v < VM_V; ++v) { acc[c].v[v] = T(0); tmp[c].v[v] = T(0); }
+      for (int v = 0; v < VM_V; ++v) acc[c].v[v] = T(0);
+    V4<T>* const park = mine + n_buf * buf_stride;  // PUSH / POP slot (one pending value: depth-2 trees)
 #pragma unroll 1
     for (int i = 0; i < p.n_steps; ++i) {
       const int form = p.form[i], kind = p.kind[i];
       V4<T> leaf[CH];
-      if (kind == SL_FULL || kind == SL_CHUNK) {
+      if (form == CH_POP) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) leaf[c] = park[c * THREADS];
+      } else if (kind == SL_FULL || kind == SL_CHUNK) {
         const V4<T>* slot = mine + buf * buf_stride + p.stage[i] * (CH * THREADS);
         const bool splat = kind == SL_CHUNK && p.bcast[i][0];
 #pragma unroll
@@ -668,15 +716,9 @@ __global__ void __launch_bounds__(256, 3) ew_chain_kernel(const __grid_constant_
         for (int c = 0; c < CH; ++c) acc[c] = leaf[c];
       } else if (form == CH_PUSH) {
 #pragma unroll
-        for (int c = 0; c < CH; ++c) { tmp[c] = acc[c]; acc[c] = leaf[c]; }
+        for (int c = 0; c < CH; ++c) { park[c * THREADS] = acc[c]; acc[c] = leaf[c]; }
       } else {
-        V4<T> l[CH], r[CH];
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          l[c] = form == CH_LA ? leaf[c] : (form == CH_TA ? tmp[c] : acc[c]);
-          r[c] = form == CH_AL ? leaf[c] : (form == CH_AT ? tmp[c] : acc[c]);
-        }
-        chain_apply<T, CH>(p.op[i], form == CH_UN, l, r, acc);
+        chain_apply<T, CH>(p.op[i], form == CH_UN, acc, leaf);
       }
     }
 #pragma unroll
@@ -691,6 +733,8 @@ __global__ void __launch_bounds__(256, 3) ew_chain_kernel(const __grid_constant_
         chain_store_general<T>(p.out, p.out_dtype, base, n, acc[c]);
       }
     }
+    buf = buf + 1 == n_buf ? 0 : buf + 1;
+    ahead = ahead + 1 == n_buf ? 0 : ahead + 1;
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
@@ -719,30 +763,38 @@ struct ChainGen {
     return true;
   }
   bool is_leaf(int e) const { return ex[e].kind != 2; }
-  // depth 0: acc free; depth 1: acc holds a live value that must survive in tmp
+  static bool commutes(int op) {
+    return op == TCR_EW_ADD || op == TCR_EW_MUL || op == TCR_EW_MIN || op == TCR_EW_MAX || op == TCR_EW_EQ || op == TCR_EW_NEQ;
+  }
+  // depth 0: acc free; depth 1: acc holds a live value that PUSH parks until the matching POP
   bool gen(int e, int depth) {
     const ChainExpr& x = ex[e];
     if (x.kind != 2) return emit(depth == 0 ? CH_INIT : CH_PUSH, 0, e);
     if (x.uses > 1) return false;  // shared interior value: needs a named register
     if (x.b < 0) return gen(x.a, depth) && emit(CH_UN, x.op, -1);
-    if (is_leaf(x.b)) return gen(x.a, depth) && emit(CH_AL, x.op, x.b);
-    if (is_leaf(x.a)) return gen(x.b, depth) && emit(CH_LA, x.op, x.a);
+    if (is_leaf(x.b)) return gen(x.a, depth) && emit(CH_BIN, x.op, x.b);                                  // acc op leaf
+    if (is_leaf(x.a)) return gen(x.b, depth) && emit(CH_BIN, commutes(x.op) ? x.op : (x.op | TCR_CH_REV), x.a);  // leaf op acc
     if (depth != 0) return false;
-    return gen(x.a, 0) && gen(x.b, 1) && emit(CH_TA, x.op, -1);
+    // acc = a; PUSH: park a, acc = b; POP: acc = parked(a) op acc(b) -> reversed
+    return gen(x.a, 0) && gen(x.b, 1) && emit(CH_POP, commutes(x.op) ? x.op : (x.op | TCR_CH_REV), -1);
   }
 };
 }  // namespace
 
 template <typename T, int CH>
 static int launch_chain(const ChainParams& p) {
-  const size_t smem = (size_t)2 * (p.n_staged > 0 ? p.n_staged : 1) * CH * 256 * sizeof(V4<T>);
+  bool parks = false;
+  for (int i = 0; i < p.n_steps; ++i) parks |= p.form[i] == CH_PUSH;
+  size_t slots = (size_t)p.n_buf * p.n_staged + (parks ? 1 : 0);  // staging ring (+ the PUSH/POP slot)
+  if (slots == 0) slots = 1;
+  const size_t smem = slots * CH * 256 * sizeof(V4<T>);
   static size_t configured = 0;
   if (smem > configured) {
     TCR_CUDA(cudaFuncSetAttribute(ew_chain_kernel<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = 200 * 1024;
   }
   int per_sm = (int)(220 * 1024 / (smem + 1024));
-  if (per_sm > 3) per_sm = 3;
+  if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
   int grid = wave_grid(ceil_div(p.n, VM_V), 256 * CH, per_sm);
   TCR_LAUNCH((ew_chain_kernel<T, CH>), grid, 256, smem, p);
@@ -755,7 +807,7 @@ static bool try_chain(const tcr_ew_program* prog, int* rc) {
   static const int enabled = std::getenv("TCR_EW_CHAIN") ? std::atoi(std::getenv("TCR_EW_CHAIN")) : 1;
   if (!enabled || prog->n_outputs != 1 || prog->n_instrs < 1) return false;
   const int64_t n = prog->dims[0] * prog->dims[1] * prog->dims[2];
-  if (n <= 0 || n >= (1ll << 31) - (1 << 22)) return false;
+  if (n < (1 << 15) || n >= (1ll << 31) - (1 << 22)) return false;  // small tensors: the register machine has the shorter prologue
   if (!aligned16(prog->outputs[0].ptr)) return false;
   // registers -> expressions
   ChainGen g;
@@ -845,7 +897,21 @@ static bool try_chain(const tcr_ew_program* prog, int* rc) {
       p.stage[i] = (uint8_t)staged_of_input[e.input];
     }
   }
-  if (sizeof(T) == 4 && p.n_staged <= 4) *rc = launch_chain<T, 2>(p);
+  // enough 16-byte loads in flight per thread (~6) whatever the number of streamed inputs
+  const int ch = (sizeof(T) == 4 && p.n_staged <= 4) ? 2 : 1;
+  int n_full = 0;  // streamed from HBM (broadcast leaves hit in cache)
+  {
+    bool seen[CHAIN_MAXN] = {false};
+    for (int i = 0; i < p.n_steps; ++i) {
+      if (p.kind[i] == SL_CHUNK) p.has_chunk = 1;
+      if (p.kind[i] == SL_FULL && !seen[p.stage[i]]) { seen[p.stage[i]] = true; ++n_full; }
+    }
+  }
+  const int per_iter = ch * (n_full > 0 ? n_full : 1) * (sizeof(T) == 8 ? 2 : 1);
+  p.n_buf = 1 + (6 + per_iter - 1) / per_iter;
+  if (p.n_buf < 2) p.n_buf = 2;
+  if (p.n_buf > 4) p.n_buf = 4;
+  if (ch == 2) *rc = launch_chain<T, 2>(p);
   else *rc = launch_chain<T, 1>(p);
   return true;
 }
