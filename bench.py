@@ -340,6 +340,13 @@ def main():
         if os.path.exists(pk):
             peaks = json.load(open(pk))
         roof = dominant_kernel_roofline(cabi, args.workload, w, peaks)
+        try:  # DRAM traffic of the dominant kernel from the committed ncu capture (null when none was taken)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
+            if tr:
+                roof["traffic"] = tr["bytes"]
+                roof["traffic_source"] = tr["source"]
+        except Exception:
+            pass
         med, nsteps = cpu_reference_steps(cfg, gen, budget_s=args.cpu_seconds, max_steps=20)
         ms_step = ms_total / args.steps
         line = {
