@@ -43,6 +43,13 @@ struct TcParams {
   int a_mn_major, b_mn_major;  // 0: K-major (K contiguous), 1: MN-major (M / N contiguous)
   int kb_per_split;            // k-blocks handled by one blockIdx.z (split-K); partial tiles go to `c` + z*m*n
   int raw_hi;                  // 3xTF32: leave the landed tile untouched (the tensor core truncates it to tf32 = hi) and only write lo
+  // fused split-K reduction: the last CTA of a tile to finish (ticket counter) sums the partial tiles
+  // in split order and applies the epilogue — deterministic, and no second launch
+  int* counters;               // one per output tile, zero between launches (self-resetting); null = separate reduce kernel
+  float* fin_c;
+  int64_t fin_sm, fin_sn;
+  const float* fin_bias;
+  int fin_epilogue, fin_activation, fin_accumulate;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -357,9 +364,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   }
+  if (gridDim.z > 1 && p.counters != nullptr) __threadfence();  // partial tile visible device-wide before the ticket
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+  if (gridDim.z > 1 && p.counters != nullptr) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+      int* ctr = p.counters + blockIdx.y * gridDim.x + blockIdx.x;
+      const int ticket = atomicAdd(ctr, 1);
+      s_last = ticket == (int)gridDim.z - 1;
+      if (s_last) *ctr = 0;  // every split has arrived: ready for the next launch that is handed this counter
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int64_t plane = p.m * p.n;
+      const int splits = (int)gridDim.z;
+      const bool vec = (p.n & 3) == 0;
+      for (int idx = threadIdx.x; idx < BM * (BN / 4); idx += NUM_THREADS) {
+        const int64_t m = m0 + idx / (BN / 4), n = n0 + (idx % (BN / 4)) * 4;
+        if (m >= p.m || n >= p.n) continue;
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* src = p.c + m * p.n + n;  // p.c = workspace, partial z at + z * plane
+        if (vec) {  // n + 4 <= p.n follows from n % 4 == 0 and p.n % 4 == 0
+          for (int z = 0; z < splits; ++z) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)z * plane));
+            x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
+          }
+        } else {
+          for (int z = 0; z < splits; ++z)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < p.n) x[j] += __ldcg(src + (int64_t)z * plane + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (n + j >= p.n) continue;
+          float v = x[j];
+          float* dst = p.fin_c + m * p.fin_sm + (n + j) * p.fin_sn;
+          if (p.fin_accumulate) v += *dst;
+          if (p.fin_epilogue == TCR_EPI_BIAS_N) v += p.fin_bias[n + j];
+          else if (p.fin_epilogue == TCR_EPI_BIAS_M) v += p.fin_bias[m];
+          if (p.fin_activation) v = act_f(p.fin_activation, v);
+          *dst = v;
+        }
+      }
+    }
+  }
 }
 
 // deterministic split-K: out(m,n) = epilogue(sum_z ws[z][m][n])
@@ -436,6 +488,7 @@ int make_tf32_map(CUtensorMap* map, const float* base, int64_t dim0, int64_t dim
 }
 
 int gemm_tc2_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc* d, int a_mn, int b_mn, int64_t a_pitch, int64_t b_pitch, bool* handled);  // gemm_tc2.cu
+int* counter_ring_take(int n);  // runtime.cu
 
 int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc* d, bool* handled) {
   *handled = false;
@@ -489,9 +542,10 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
     const int64_t tiles = ceil_div(d->m, BM) * ceil_div(d->n, BN);
     const int sms = state().sm_count;
     int splits = 1;
-    if (tiles * 2 <= sms && total_kb >= 16) {
+    static const int min_kb = std::getenv("TCR_GEMM_SPLIT_MIN_KB") ? std::atoi(std::getenv("TCR_GEMM_SPLIT_MIN_KB")) : 8;  // experiment knob; 0 = never split
+    if (min_kb > 0 && tiles * 2 <= sms && total_kb >= 16) {
       double best = (double)tiles / (double)(ceil_div(tiles, sms) * sms);
-      for (int sp = 2; sp <= 32 && total_kb / sp >= 8; ++sp) {
+      for (int sp = 2; sp <= 32 && total_kb / sp >= min_kb; ++sp) {
         double eff = (double)(tiles * sp) / (double)(ceil_div(tiles * sp, sms) * sms);
         if (eff > best + 0.05) { best = eff; splits = sp; }
       }
@@ -500,18 +554,29 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
     splits = (int)ceil_div(total_kb, p.kb_per_split);
     void* ws = nullptr;
     TcParams pk = p;
+    pk.counters = nullptr;
+    // measured in a CUDA graph on the LSTM gate product (64 x 1024 x 1152, 4 splits): fused 22.1 us vs separate reduce 13.0 us —
+    // one CTA per tile summing the partials has too little parallelism, so the fused form stays opt-in
+    static const int fused_reduce = std::getenv("TCR_GEMM_FUSED_REDUCE") ? std::atoi(std::getenv("TCR_GEMM_FUSED_REDUCE")) : 0;
     if (splits > 1) {
       rc = tcr_alloc(&ws, sizeof(float) * (size_t)splits * d->m * d->n);
       if (rc) return rc;
       pk.c = (float*)ws; pk.c_sm = d->n; pk.c_sn = 1;
       pk.epilogue = TCR_EPI_NONE; pk.activation = 0; pk.accumulate = 0; pk.bias = nullptr;
+      if (fused_reduce) {
+        pk.counters = counter_ring_take((int)tiles);
+        pk.fin_c = p.c; pk.fin_sm = p.c_sm; pk.fin_sn = p.c_sn; pk.fin_bias = p.bias;
+        pk.fin_epilogue = p.epilogue; pk.fin_activation = p.activation; pk.fin_accumulate = p.accumulate;
+      }
     }
     rc = d->precision == TCR_GEMM_TF32 ? launch_tc<1, 6>(ma, mb, pk, splits) : launch_tc<2, 3>(ma, mb, pk, splits);
     if (rc) return rc;
     if (splits > 1) {
-      int grid = wave_grid(d->m * d->n, 256, 8);
-      TCR_LAUNCH(splitk_reduce_kernel, grid, 256, 0, (const float*)ws, splits, p);
-      TCR_CHECK_LAUNCH();
+      if (pk.counters == nullptr) {
+        int grid = wave_grid(d->m * d->n, 256, 8);
+        TCR_LAUNCH(splitk_reduce_kernel, grid, 256, 0, (const float*)ws, splits, p);
+        TCR_CHECK_LAUNCH();
+      }
       tcr_free(ws);
     }
   }

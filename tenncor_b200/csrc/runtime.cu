@@ -41,6 +41,24 @@ int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
   return TCR_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------- ticket counters
+// Self-resetting per-tile arrival counters for kernels that finish a split reduction in their last
+// CTA. A launch takes a fresh range of a zero-initialised ring; ranges baked into captured graphs stay
+// valid because every user leaves its counters at zero. Two launches share a range only after the
+// ring wraps (2^20 counters), and launches of different plans are ordered on the library stream.
+static int* g_counter_ring = nullptr;
+static size_t g_counter_pos = 0;
+constexpr size_t COUNTER_RING = 1u << 20;
+
+int* counter_ring_take(int n) {
+  if (g_counter_ring == nullptr) return nullptr;
+  if (n < 1) n = 1;
+  if (g_counter_pos + (size_t)n > COUNTER_RING) g_counter_pos = 0;
+  int* p = g_counter_ring + g_counter_pos;
+  g_counter_pos += (size_t)n;
+  return p;
+}
+
 // ---------------------------------------------------------------- arena
 struct Arena {
   std::mutex mu;
@@ -111,6 +129,10 @@ int tcr_init(int device) {
     return TCR_ERR_NODEVICE;
   }
   if (s.stream == nullptr) TCR_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  if (g_counter_ring == nullptr) {
+    TCR_CUDA(cudaMalloc(&g_counter_ring, COUNTER_RING * sizeof(int)));
+    TCR_CUDA(cudaMemset(g_counter_ring, 0, COUNTER_RING * sizeof(int)));
+  }
   s.device = device;
   s.sm_count = prop.multiProcessorCount;
   s.ready = true;

@@ -412,6 +412,42 @@ def test_graph_capture_replay_and_arena(gpu):
     gpu.check(lib.tcr_graph_destroy(exe))
 
 
+def test_graph_capture_lanes(gpu):
+    """Two independent chains captured on different lanes, joined by a mark: the replayed graph
+    computes z = exp(x) + tanh(y) (lane 1 and lane 2 feed lane 0). Lane calls outside a capture fail."""
+    lib = gpu.lib()
+    n = 1 << 15
+    rng = np.random.default_rng(1)
+    x, y = rng.uniform(-1, 1, n).astype(np.float32), rng.uniform(-1, 1, n).astype(np.float32)
+    dx, dy = gpu.to_device(x), gpu.to_device(y)
+    ex, ty, dz = gpu.empty(n, np.float32), gpu.empty(n, np.float32), gpu.empty(n, np.float32)
+    assert lib.tcr_graph_lane(1) != 0  # no capture in progress
+    gpu.check(lib.tcr_graph_begin())
+    m1, m2 = C.c_int(-1), C.c_int(-1)
+    gpu.check(lib.tcr_graph_lane(1))
+    gpu.check(lib.tcr_unary(gpu.OP["EXP"], C.c_void_p(dx.ptr), C.c_void_p(ex.ptr), C.c_int64(n), gpu.FLOAT))
+    gpu.check(lib.tcr_graph_record(C.byref(m1)))
+    gpu.check(lib.tcr_graph_lane(2))
+    gpu.check(lib.tcr_unary(gpu.OP["TANH"], C.c_void_p(dy.ptr), C.c_void_p(ty.ptr), C.c_int64(n), gpu.FLOAT))
+    gpu.check(lib.tcr_graph_record(C.byref(m2)))
+    gpu.check(lib.tcr_graph_lane(0))
+    gpu.check(lib.tcr_graph_wait(m1.value))
+    gpu.check(lib.tcr_graph_wait(m2.value))
+    gpu.check(lib.tcr_binary(gpu.OP["ADD"], C.c_void_p(ex.ptr), C.c_void_p(ty.ptr), C.c_void_p(dz.ptr), C.c_int64(n), gpu.FLOAT))
+    exe = C.c_void_p()
+    gpu.check(lib.tcr_graph_end(C.byref(exe)))  # joins lanes 1 and 2
+    assert lib.tcr_graph_wait(m1.value) != 0  # marks die with the capture
+    for scale in (1.0, -0.5):
+        x2, y2 = (x * scale).astype(np.float32), (y * scale).astype(np.float32)
+        gpu.check(lib.tcr_h2d(C.c_void_p(dx.ptr), x2.ctypes.data_as(C.c_void_p), C.c_size_t(x2.nbytes)))
+        gpu.check(lib.tcr_h2d(C.c_void_p(dy.ptr), y2.ctypes.data_as(C.c_void_p), C.c_size_t(y2.nbytes)))
+        gpu.check(lib.tcr_graph_launch(exe))
+        got = gpu.to_host(dz, n, np.float32)
+        want = np.exp(x2.astype(np.float64)) + np.tanh(y2.astype(np.float64))
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+    gpu.check(lib.tcr_graph_destroy(exe))
+
+
 def test_errors_are_loud(gpu):
     lib = gpu.lib()
     buf = gpu.empty(16, np.float32)

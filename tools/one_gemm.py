@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--tb", type=int, default=0)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--graph", action="store_true", help="capture the launches in one CUDA graph and time its replay (GPU-side cost without CPU launch overhead)")
     args = ap.parse_args()
     cabi.init(0)
     lib = cabi.lib()
@@ -41,10 +42,22 @@ def main():
     for _ in range(args.warmup):
         cabi.check(lib.tcr_gemm(P(a), P(b), P(out), C.byref(d)))
     cabi.sync()
-    cabi.check(lib.tcr_event_record(e0))
-    for _ in range(args.iters):
-        cabi.check(lib.tcr_gemm(P(a), P(b), P(out), C.byref(d)))
-    cabi.check(lib.tcr_event_record(e1))
+    if args.graph:
+        g = C.c_void_p()
+        cabi.check(lib.tcr_graph_begin())
+        for _ in range(args.iters):
+            cabi.check(lib.tcr_gemm(P(a), P(b), P(out), C.byref(d)))
+        cabi.check(lib.tcr_graph_end(C.byref(g)))
+        cabi.check(lib.tcr_graph_launch(g))
+        cabi.sync()
+        cabi.check(lib.tcr_event_record(e0))
+        cabi.check(lib.tcr_graph_launch(g))
+        cabi.check(lib.tcr_event_record(e1))
+    else:
+        cabi.check(lib.tcr_event_record(e0))
+        for _ in range(args.iters):
+            cabi.check(lib.tcr_gemm(P(a), P(b), P(out), C.byref(d)))
+        cabi.check(lib.tcr_event_record(e1))
     ms = C.c_float()
     cabi.check(lib.tcr_event_elapsed_ms(e0, e1, C.byref(ms)))
     per = ms.value / args.iters
