@@ -67,9 +67,10 @@ __device__ __forceinline__ T block_reduce(T v) {
 // ---- rows: out[ko*S + s] = reduce in[ko*R + chunk_s]; grid = (S, Kout)
 template <typename T, int OP>
 __global__ void __launch_bounds__(256) reduce_rows_block(const T* __restrict__ in, T* __restrict__ out, int64_t R,
-                                                         int64_t chunk, int S) {
-  const int64_t ko = blockIdx.y;
+                                                         int64_t chunk, int S, int64_t Kout) {
   const int s = blockIdx.x;
+  // grid.y walks the kept rows (any count: 65536 rows of 4096 is a SURVEY §8d case)
+  for (int64_t ko = blockIdx.y; ko < Kout; ko += gridDim.y) {
   const T* row = in + ko * R;
   int64_t lo = (int64_t)s * chunk, hi = lo + chunk < R ? lo + chunk : R;
   T acc = Red<T, OP>::init();
@@ -102,6 +103,8 @@ __global__ void __launch_bounds__(256) reduce_rows_block(const T* __restrict__ i
   for (int64_t t = vlo + nvec * N + threadIdx.x; t < hi; t += blockDim.x) acc = Red<T, OP>::op(acc, row[t]);
   acc = block_reduce<T, OP>(acc);
   if (threadIdx.x == 0) out[ko * S + s] = acc;
+  __syncthreads();  // block_reduce's scratch is reused by the next row
+  }
 }
 
 // ---- rows, one warp per row (short rows, many rows)
@@ -203,19 +206,19 @@ static int run_rows(const T* in, T* out, int64_t R, int64_t Kout) {
     if (S > maxS) S = maxS;
     if (S < 1) S = 1;
   }
-  TCR_ARG(Kout <= 65535, "tcr_reduce: too many rows for block-per-row kernel");
+  const unsigned gy = (unsigned)(Kout < 65535 ? Kout : 65535);
   int64_t chunk = ceil_div(R, S);
   chunk = (chunk + 3) / 4 * 4;
   S = ceil_div(R, chunk);
   if (S == 1) {
-    TCR_LAUNCH((reduce_rows_block<T, OP>), dim3(1, (unsigned)Kout), 256, 0, in, out, R, chunk, 1);
+    TCR_LAUNCH((reduce_rows_block<T, OP>), dim3(1, gy), 256, 0, in, out, R, chunk, 1, Kout);
     TCR_CHECK_LAUNCH();
     return TCR_OK;
   }
   void* part = nullptr;
   int rc = tcr_alloc(&part, sizeof(T) * (size_t)(Kout * S));
   if (rc) return rc;
-  TCR_LAUNCH((reduce_rows_block<T, OP>), dim3((unsigned)S, (unsigned)Kout), 256, 0, in, (T*)part, R, chunk, (int)S);
+  TCR_LAUNCH((reduce_rows_block<T, OP>), dim3((unsigned)S, gy), 256, 0, in, (T*)part, R, chunk, (int)S, Kout);
   TCR_CHECK_LAUNCH();
   rc = run_rows<T, OP>((const T*)part, out, S, Kout);
   tcr_free(part);
@@ -277,10 +280,8 @@ static int run_reduce(const void* in, void* out, const int64_t shape[8], uint32_
   else if (seg.size() == 2) { Kin = seg[0].first; R = seg[1].first; }
   else if (seg.size() == 3 && !seg[0].second) { Kin = seg[0].first; R = seg[1].first; Kout = seg[2].first; }
   else simple = false;
-  if (simple && Kout <= 65535) {
-    if (Kin == 1) return run_rows<T, OP>((const T*)in, (T*)out, R, Kout);
-    return run_cols<T, OP>((const T*)in, (T*)out, Kin, R, Kout);
-  }
+  if (simple && Kin == 1) return run_rows<T, OP>((const T*)in, (T*)out, R, Kout);
+  if (simple && Kout <= 65535) return run_cols<T, OP>((const T*)in, (T*)out, Kin, R, Kout);
   GenericDesc d;
   memset(&d, 0, sizeof(d));
   int64_t stride = 1;

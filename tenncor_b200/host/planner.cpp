@@ -3,6 +3,8 @@
 // teq::TravEvaluator::visit_func (internal/teq/evaluator.hpp:34-43) + eigen::Device::calc
 // (internal/eigen/device.hpp:555-570) + TensOp::assign (device.hpp:304-328).
 #include "planner.hpp"
+#include "dp.hpp"
+#include <queue>
 #include <set>
 #include <algorithm>
 
@@ -52,6 +54,7 @@ struct PNode {
   // produced by the GEMM kernel of node `gemm_src`
   int gemm_src = -1, gemm_bias = -1, gemm_epi = 0, gemm_act = 0;
   bool gemm_transposed = false;  // PERMUTE{1,0} of a GEMM: computed as (B^T A^T), no copy
+  int64_t bucket_slot = -1;      // >= 0: this node's buffer is the gradient bucket at this byte offset
 };
 
 struct InputRef {
@@ -85,6 +88,12 @@ struct Step {
   // fused GEMM epilogue (in[2] = bias)
   bool gemm_fused = false;
   tcr_gemm_desc gemm;
+  // data-parallel gradient bucket: member = a gradient placed in the bucket (copy, or nothing when
+  // its producer already wrote there); flush = ONE all-reduce over the whole bucket
+  enum Kind { NORMAL = 0, BUCKET_MEMBER, BUCKET_FLUSH } kind = NORMAL;
+  bool member_in_place = false;
+  size_t bucket_offset = 0;         // member: byte offset of its slot
+  std::vector<int> bucket_members;  // flush: member step indices
 };
 
 }  // namespace
@@ -102,6 +111,11 @@ struct Plan {
   bool use_graph = false, has_run = false, always_run = false;
   int precision = 0;
   size_t n_launch_steps = 0;
+  // gradient bucket (data parallel): one flat buffer, one collective per step
+  void* bucket = nullptr;
+  size_t bucket_bytes = 0;
+  int bucket_dtype = 0;
+  double bucket_scale = 1.0;
 
   ~Plan() {
     if (graph) tcr_graph_destroy(graph);
@@ -633,6 +647,126 @@ struct Plan {
     }
   }
 
+  // Reads / write of a step in terms of storage roots (before buffers exist)
+  void step_access(const Step& st, std::vector<int>& reads, std::vector<int>& writes) const {
+    reads.clear();
+    writes.clear();
+    if (st.ew) for (auto& in : st.inputs) reads.push_back(in.node);
+    else for (int in : st.in_nodes) reads.push_back(in);
+    const PNode& out = nodes[st.out_node];
+    writes.push_back(st.out_node);
+    // an ASSIGN updates the variable's storage AND is what readers of the updated value name
+    if (is_assign(out.op)) writes.push_back(nodes[out.args[0]].root);
+  }
+
+  // Data-parallel plans: put every all-reduced gradient in one flat bucket and exchange it with ONE
+  // collective. The steps are re-ordered by a stable topological sort in which every reader of a
+  // reduced gradient waits for the flush, so all gradients are produced first, then the exchange,
+  // then the optimiser updates and whatever reads the updated variables.
+  void bucket_gradients() {
+    if (std::getenv("TCR_NO_BUCKET")) return;
+    std::vector<int> comm;
+    for (size_t s = 0; s < steps.size(); ++s) {
+      const Step& st = steps[s];
+      if (!st.ew && !st.gemm_fused && nodes[st.out_node].op == IDENTITY && st.in_nodes.size() == 1) comm.push_back((int)s);
+    }
+    if (comm.size() < 2) return;
+    const auto dt = nodes[steps[comm[0]].out_node].dtype;
+    const double scale = dp::allreduce_scale(*nodes[steps[comm[0]].out_node].func);
+    for (int c : comm) {
+      const PNode& o = nodes[steps[c].out_node];
+      if (o.dtype != dt || dp::allreduce_scale(*o.func) != scale || o.exposed || steps[c].in_offsets[0] != 0) return;
+    }
+    const int ns = (int)steps.size();
+    // dependencies in the current order
+    std::vector<std::vector<int>> deps(ns + 1);
+    {
+      std::unordered_map<int, int> last_writer;
+      std::unordered_map<int, std::vector<int>> readers;
+      std::vector<int> reads, writes;
+      for (int s = 0; s < ns; ++s) {
+        step_access(steps[s], reads, writes);
+        for (int r : reads) {
+          auto w = last_writer.find(r);
+          if (w != last_writer.end()) deps[s].push_back(w->second);
+          readers[r].push_back(s);
+        }
+        for (int write : writes) {
+          auto w = last_writer.find(write);
+          if (w != last_writer.end()) deps[s].push_back(w->second);
+          auto rd = readers.find(write);
+          if (rd != readers.end()) {
+            for (int x : rd->second)
+              if (x != s) deps[s].push_back(x);
+            rd->second.clear();
+          }
+          last_writer[write] = s;
+        }
+      }
+    }
+    // the flush (index ns) waits for every member; whoever waited for a member waits for the flush
+    std::set<int> is_comm(comm.begin(), comm.end());
+    for (int s = 0; s < ns; ++s) {
+      if (is_comm.count(s)) continue;
+      bool reads_member = false;
+      for (int d : deps[s]) reads_member |= is_comm.count(d) > 0;
+      if (reads_member) deps[s].push_back(ns);
+    }
+    deps[ns] = comm;
+    // stable topological order: smallest original index first; the flush sorts right after the last member
+    std::vector<int> indeg(ns + 1, 0);
+    std::vector<std::vector<int>> users(ns + 1);
+    for (int s = 0; s <= ns; ++s) {
+      std::sort(deps[s].begin(), deps[s].end());
+      deps[s].erase(std::unique(deps[s].begin(), deps[s].end()), deps[s].end());
+      for (int d : deps[s]) { users[d].push_back(s); ++indeg[s]; }
+    }
+    auto key = [&](int s) { return s == ns ? 2 * comm.back() + 1 : 2 * s; };
+    auto cmp = [&](int a, int b) { return key(a) > key(b); };
+    std::priority_queue<int, std::vector<int>, decltype(cmp)> ready(cmp);
+    for (int s = 0; s <= ns; ++s)
+      if (indeg[s] == 0) ready.push(s);
+    std::vector<int> order;
+    while (!ready.empty()) {
+      int s = ready.top();
+      ready.pop();
+      order.push_back(s);
+      for (int u : users[s])
+        if (--indeg[u] == 0) ready.push(u);
+    }
+    if ((int)order.size() != ns + 1) return;  // cycle: keep the per-gradient exchange
+    // slots
+    size_t off = 0;
+    std::vector<size_t> slot(ns, 0);
+    for (int c : comm) {
+      slot[c] = off;
+      size_t bytes = (size_t)nodes[steps[c].out_node].n * type_size(dt);
+      off += (bytes + 15) / 16 * 16;
+    }
+    bucket_bytes = off;
+    bucket_dtype = dt;
+    bucket_scale = scale;
+    std::vector<Step> reordered;
+    std::vector<int> new_index(ns + 1, -1);
+    Step flush;
+    flush.kind = Step::BUCKET_FLUSH;
+    flush.out_node = steps[comm.back()].out_node;
+    for (int s : order) {
+      new_index[s] = (int)reordered.size();
+      if (s == ns) { reordered.push_back(flush); continue; }
+      Step st = std::move(steps[s]);
+      if (is_comm.count(s)) {
+        st.kind = Step::BUCKET_MEMBER;
+        st.bucket_offset = slot[s];
+      }
+      reordered.push_back(std::move(st));
+    }
+    for (int c : comm) reordered[new_index[ns]].bucket_members.push_back(new_index[c]);
+    steps = std::move(reordered);
+    for (size_t s = 0; s < steps.size(); ++s)
+      if (steps[s].kind != Step::BUCKET_FLUSH) nodes[steps[s].out_node].step = (int)s;
+  }
+
   void* leaf_ptr(PNode& n) {
     void* p = n.tens->device().device_data();
     if (!p) global::fatalf("planner: %s has no data", n.tens->to_string().c_str());
@@ -650,12 +784,34 @@ struct Plan {
     }
     for (auto& n : nodes)
       if (!n.func) n.ptr = leaf_ptr(n);
+    if (bucket_bytes > 0) {
+      bucket = alloc_owned(bucket_bytes);
+      check(tcr_memset(bucket, 0, bucket_bytes), "tcr_memset");  // the 16-byte padding between slots stays zero
+      // a gradient read only by its exchange is produced straight into its slot
+      for (size_t s = 0; s < steps.size(); ++s) {
+        Step& st = steps[s];
+        if (st.kind != Step::BUCKET_MEMBER) continue;
+        PNode& in = nodes[st.in_nodes[0]];
+        PNode& out = nodes[st.out_node];
+        if (in.func && in.step >= 0 && !in.exposed && !is_assign(in.op) && last_use[st.in_nodes[0]] == (int)s &&
+            steps[in.step].kind == Step::NORMAL && in.n == out.n && in.dtype == out.dtype) {
+          in.bucket_slot = (int64_t)st.bucket_offset;
+          st.member_in_place = true;
+        }
+      }
+    }
     std::multimap<size_t, void*> pool;  // plan-local free list: buffers are reused once their last reader has run
     std::vector<std::vector<int>> dying(steps.size());
     for (size_t s = 0; s < steps.size(); ++s) {
       Step& st = steps[s];
       PNode& out = nodes[st.out_node];
-      if (is_assign(out.op)) {
+      if (st.kind == Step::BUCKET_FLUSH) {
+        continue;  // owns nothing
+      } else if (st.kind == Step::BUCKET_MEMBER) {
+        out.ptr = (char*)bucket + st.bucket_offset;  // lives for the whole plan, never pooled
+      } else if (out.bucket_slot >= 0) {
+        out.ptr = (char*)bucket + out.bucket_slot;
+      } else if (is_assign(out.op)) {
         out.ptr = nodes[nodes[out.args[0]].root].ptr;  // variable storage
         out.root = nodes[out.args[0]].root;
       } else if (out.exposed) {
@@ -699,6 +855,7 @@ struct Plan {
     }
     // resolve pointers inside the steps
     for (auto& st : steps) {
+      if (st.kind == Step::BUCKET_FLUSH) continue;
       PNode& out = nodes[st.out_node];
       if (st.ew) {
         for (size_t k = 0; k < st.inputs.size(); ++k) {
@@ -719,7 +876,12 @@ struct Plan {
   }
 
   void launch_one(Step& st) {
-    if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
+    if (st.kind == Step::BUCKET_FLUSH) {
+      check(tcr_allreduce_sum(bucket, (int64_t)(bucket_bytes / type_size((_GENERATED_DTYPE)bucket_dtype)), bucket_dtype, bucket_scale),
+            "tcr_allreduce_sum");
+    } else if (st.kind == Step::BUCKET_MEMBER) {
+      if (!st.member_in_place) check(tcr_d2d(st.out, st.in[0], (size_t)nodes[st.out_node].n * type_size(nodes[st.out_node].dtype)), "tcr_d2d");
+    } else if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
     else if (st.gemm_fused) {
       tcr_gemm_desc d = st.gemm;
       d.precision = d.dtype == FLOAT ? gemm_precision() : TCR_GEMM_EXACT;
@@ -762,17 +924,24 @@ struct Plan {
       };
       if (st.ew) for (auto& in : st.inputs) read(nodes[in.node].ptr);
       else for (int in : st.in_nodes) read(nodes[in].ptr);
-      const void* out = nodes[st.out_node].ptr;
-      auto w = last_writer.find(out);
-      if (w != last_writer.end()) d.push_back(w->second);
-      auto r = readers.find(out);
-      if (r != readers.end()) {
-        for (int x : r->second)
-          if (x != s) d.push_back(x);
-        r->second.clear();
+      auto write = [&](const void* out) {
+        auto w = last_writer.find(out);
+        if (w != last_writer.end()) d.push_back(w->second);
+        auto r = readers.find(out);
+        if (r != readers.end()) {
+          for (int x : r->second)
+            if (x != s) d.push_back(x);
+          r->second.clear();
+        }
+        last_writer[out] = s;
+      };
+      if (st.kind == Step::BUCKET_FLUSH) {  // reduces every slot of the bucket in place
+        for (int m : st.bucket_members) write(nodes[steps[m].out_node].ptr);
+      } else {
+        write(nodes[st.out_node].ptr);
       }
-      last_writer[out] = s;
-      if (!st.ew && nodes[st.out_node].op == IDENTITY) {  // collective: one communicator, program order
+      const bool collective = st.kind == Step::BUCKET_FLUSH || (st.kind == Step::NORMAL && !st.ew && !st.gemm_fused && nodes[st.out_node].op == IDENTITY);
+      if (collective) {  // one communicator, program order
         if (last_comm >= 0) d.push_back(last_comm);
         last_comm = s;
       }
@@ -783,7 +952,7 @@ struct Plan {
     for (int s = 0; s < ns; ++s) {
       Step& st = steps[s];
       int lane = -1;
-      if (!st.ew && nodes[st.out_node].op == IDENTITY) lane = 0;
+      if (st.kind == Step::BUCKET_FLUSH || (st.kind == Step::NORMAL && !st.ew && !st.gemm_fused && nodes[st.out_node].op == IDENTITY)) lane = 0;
       if (lane < 0) {  // continue the lane of the latest producer when this step directly follows it there
         for (auto it = deps[s].rbegin(); it != deps[s].rend(); ++it)
           if (lane_tail[step_lane[*it]] == *it) { lane = step_lane[*it]; break; }
@@ -843,6 +1012,7 @@ struct Plan {
     }
     fuse();
     build_steps();
+    bucket_gradients();
     assign_buffers();
     n_launch_steps = steps.size();
     // RAND_UNIF draws a fresh Philox offset at every launch: such plans are launched eagerly

@@ -412,6 +412,24 @@ def test_graph_capture_replay_and_arena(gpu):
     gpu.check(lib.tcr_graph_destroy(exe))
 
 
+@pytest.mark.parametrize("op", ["REDUCE_SUM", "REDUCE_MAX"])
+def test_reduce_more_rows_than_a_grid_dimension(gpu, op):
+    """[1100, 66000] reduced over the fast rank: 66000 kept rows (> 65535, the SURVEY §8d
+    [4096, 65536] case scaled down) must take the row kernel, not the one-thread-per-output fallback."""
+    rng = np.random.default_rng(11)
+    shape = [1100, 66000]
+    x = rng.uniform(-1, 1, shape[0] * shape[1]).astype(np.float32)
+    s8 = orc.full_shape(shape)
+    got, oshape = opcheck.gpu_run(gpu, op, [x], [s8], {"rank_set": [0]})
+    rows = x.reshape(shape[1], shape[0]).astype(np.float64)
+    want = rows.sum(axis=1) if op == "REDUCE_SUM" else rows.max(axis=1)
+    assert list(oshape)[:2] == [1, 66000]
+    if op == "REDUCE_MAX":
+        np.testing.assert_array_equal(got.reshape(-1), want.astype(np.float32))
+    else:
+        assert np.all(np.abs(got.reshape(-1) - want) <= FP32_RTOL * np.abs(rows).sum(axis=1))
+
+
 def test_graph_capture_lanes(gpu):
     """Two independent chains captured on different lanes, joined by a mark: the replayed graph
     computes z = exp(x) + tanh(y) (lane 1 and lane 2 feed lane 0). Lane calls outside a capture fail."""

@@ -109,6 +109,45 @@ def main():
         tab = (C.c_void_p * 2)(a.ptr, b.ptr)
         shp = (C.c_int64 * 16)(*(cabi.shape8(half)[:] + cabi.shape8(half)[:]))
         rec("lay_concat_axis1_[1024,64,%d]x2" % s3[2], timeit(lambda: cabi.check(lib.tcr_concat(tab, shp, 2, P(out), 1, 4))), 8 * n)
+    if want("survey"):
+        # the exact shapes SURVEY.md §8(d) lists that the n-derived cases above do not hit
+        R0, R1 = 4096, 65536
+        big = cabi.to_device(rng.uniform(0.9, 1.1, R0 * R1).astype(np.float32))
+        small2 = cabi.empty(R1, np.float32)
+        shp = cabi.shape8([R0, R1])
+        nn = R0 * R1
+        for op in ["REDUCE_SUM", "REDUCE_MAX", "REDUCE_MIN", "REDUCE_PROD"]:
+            for mask, nm, nout in [(1, "dim0", R1), (2, "dim1", R0), (3, "full", 1)]:
+                rec("red_%s_%s_[4096,65536]" % (op, nm), timeit(lambda: cabi.check(lib.tcr_reduce(cabi.OP[op], P(big), P(small2), shp, C.c_uint32(mask), F)), iters=5), 4 * (nn + nout))
+        for dim, nm, nout in [(0, "dim0", R1), (1, "dim1", R0), (8, "flat", 1)]:
+            rec("argmax_%s_[4096,65536]" % nm, timeit(lambda: cabi.check(lib.tcr_argmax(P(big), P(small2), shp, dim, F)), iters=5), 4 * (nn + nout))
+        big2 = cabi.empty(nn, np.float32)
+        for op in ["EXP", "SIGMOID", "TANH"]:
+            rec("ew_unary_%s_2^28" % op, timeit(lambda: cabi.check(lib.tcr_unary(cabi.OP[op], P(big), P(big2), C.c_int64(nn), F)), iters=5), 8 * nn)
+        big3 = cabi.to_device(rng.uniform(-1, 1, nn).astype(np.float32))
+        big4 = cabi.to_device(rng.uniform(-1, 1, nn).astype(np.float32))
+        for op in ["ADD", "MUL"]:
+            rec("ew_binary_%s_2^28" % op, timeit(lambda: cabi.check(lib.tcr_binary(cabi.OP[op], P(big), P(big3), P(big2), C.c_int64(nn), F)), iters=5), 12 * nn)
+        progb = cabi.make_program(F, (nn, 1, 1), [(big.ptr, F, (0, 0, 0)), (big3.ptr, F, (0, 0, 0)), (big4.ptr, F, (0, 0, 0))], [(big2.ptr, F, 0)],
+                                  [(cabi.OP["MUL"], 0, 0, 1), (cabi.OP["ADD"], 0, 0, 2), (cabi.OP["SIGMOID"], 0, 0)])
+        rec("ew_fused_sigmoid(a*b+c)_2^28", timeit(lambda: cabi.check(lib.tcr_elementwise(C.byref(progb))), iters=5), 16 * nn)
+        rec("ew_assign_sub_2^28", timeit(lambda: cabi.check(lib.tcr_assign(cabi.OP["ASSIGN_SUB"], P(big2), P(big), C.c_int64(nn), F)), iters=5), 12 * nn)
+        bc = (C.c_int64 * 8)(1, 65536, 1, 1, 1, 1, 1, 1)
+        rec("lay_extend_[1024]->[1024,65536]", timeit(lambda: cabi.check(lib.tcr_extend(P(big), P(big2), cabi.shape8([1024]), bc, 4))), 4 * 1024 * 65536 + 4096)
+        s3 = [1024, 128, 64]
+        m3 = 1024 * 128 * 64
+        offs = (C.c_int64 * 8)(0, 32, 0, 0, 0, 0, 0, 0)
+        exts = (C.c_int64 * 8)(1024, 64, 64, 1, 1, 1, 1, 1)
+        rec("lay_slice_mid_[1024,128,64] (L2-resident)", timeit(lambda: cabi.check(lib.tcr_slice(P(big), P(big2), cabi.shape8(s3), offs, exts, 4))), 8 * (m3 // 2))
+        lo = (C.c_int64 * 8)(0, 16, 0, 0, 0, 0, 0, 0)
+        rec("lay_pad_mid_[1024,128,64] (L2-resident)", timeit(lambda: cabi.check(lib.tcr_pad(P(big), P(big2), cabi.shape8(s3), lo, lo, 4))), 4 * (m3 + 1024 * 160 * 64))
+        tab = (C.c_void_p * 2)(big.ptr, big.ptr)
+        shp2 = (C.c_int64 * 16)(*(cabi.shape8(s3)[:] + cabi.shape8(s3)[:]))
+        rec("lay_concat_axis1_[1024,128,64]x2 (L2-resident)", timeit(lambda: cabi.check(lib.tcr_concat(tab, shp2, 2, P(big2), 1, 4))), 16 * m3)
+        for prec, nm in [(1, "tf32"), (2, "3xtf32")]:
+            M = N = K = 8192
+            d = cabi.GemmDesc(m=M, n=N, k=K, batch=1, a_sm=K, a_sk=1, a_sb=0, b_sk=N, b_sn=1, b_sb=0, c_sm=N, c_sn=1, c_sb=0, dtype=F, precision=prec)
+            rec("mm_%s_8192^3" % nm, timeit(lambda: cabi.check(lib.tcr_gemm(P(big), P(big), P(big2), C.byref(d))), iters=3), flops=2.0 * M * N * K)
     if want("mm"):
         for prec, nm in [(0, "exact_simt"), (1, "tf32"), (2, "3xtf32")]:
             for s in [1024, 4096]:
