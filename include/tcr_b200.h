@@ -217,6 +217,12 @@ int tcr_assign(int opcode, void* dst, const void* src, int64_t n, int dtype);
  * (seed, offset + i). Integer dtypes draw from the closed range [lo, hi]. */
 int tcr_rand_unif(const void* lo, const void* hi, void* out, int64_t n, int dtype,
                   uint64_t seed, uint64_t offset);
+/* The same generator with its (seed, offset) state resident on the device — the stand-in for the
+ * reference's process-wide engine (internal/global/random.hpp:78-146). Each call draws n numbers at
+ * the current offset and advances it by n on the stream, so a captured CUDA graph produces new
+ * numbers at every replay and the sequence equals that of eager calls in the same order. */
+int tcr_rand_seed(uint64_t seed, uint64_t offset);
+int tcr_rand_unif_stream(const void* lo, const void* hi, void* out, int64_t n, int dtype);
 
 /* ---------------------------------------------------------------- reductions */
 

@@ -926,10 +926,21 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2])
   k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
 }
 
-template <typename T>
+// Device-resident generator state for tcr_rand_unif_stream: {seed, offset}. Keeping the offset on the
+// device lets a captured CUDA graph draw fresh numbers at every replay (the kernel reads the offset,
+// a one-thread kernel behind it advances it), in the same sequence an eager run produces.
+__device__ uint64_t g_rand_state[2];
+__global__ void rand_seed_kernel(uint64_t seed, uint64_t offset) { g_rand_state[0] = seed; g_rand_state[1] = offset; }
+__global__ void rand_advance_kernel(uint64_t n) { g_rand_state[1] += n; }
+
+template <typename T, bool STREAM = false>
 __global__ void __launch_bounds__(256) rand_unif_kernel(const T* __restrict__ lo, const T* __restrict__ hi,
                                                         T* __restrict__ out, int64_t n, uint64_t seed,
                                                         uint64_t offset) {
+  if (STREAM) {
+    seed = g_rand_state[0];
+    offset = g_rand_state[1];
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint64_t ctr = offset + (uint64_t)i;
@@ -1115,6 +1126,25 @@ int tcr_rand_unif(const void* lo, const void* hi, void* out, int64_t n, int dtyp
   if (n == 0) return TCR_OK;
   int grid = wave_grid(n, 256, 8);
   TCR_DISPATCH_COMPUTE(dtype, T, TCR_LAUNCH((rand_unif_kernel<T>), grid, 256, 0, (const T*)lo, (const T*)hi, (T*)out, n, seed, offset));
+  TCR_CHECK_LAUNCH();
+  return TCR_OK;
+}
+
+int tcr_rand_seed(uint64_t seed, uint64_t offset) {
+  TCR_REQUIRE_DEVICE();
+  TCR_LAUNCH(rand_seed_kernel, 1, 1, 0, seed, offset);
+  TCR_CHECK_LAUNCH();
+  return TCR_OK;
+}
+
+int tcr_rand_unif_stream(const void* lo, const void* hi, void* out, int64_t n, int dtype) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(lo && hi && out, "tcr_rand_unif_stream: null argument");
+  TCR_ARG(n >= 0, "tcr_rand_unif_stream: negative size");
+  if (n == 0) return TCR_OK;
+  int grid = wave_grid(n, 256, 8);
+  TCR_DISPATCH_COMPUTE(dtype, T, TCR_LAUNCH((rand_unif_kernel<T, true>), grid, 256, 0, (const T*)lo, (const T*)hi, (T*)out, n, 0ull, 0ull));
+  TCR_LAUNCH(rand_advance_kernel, 1, 1, 0, (uint64_t)n);
   TCR_CHECK_LAUNCH();
   return TCR_OK;
 }

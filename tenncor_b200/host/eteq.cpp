@@ -307,8 +307,9 @@ void typed_exec(egen::_GENERATED_OPCODE opcode, egen::_GENERATED_DTYPE dtype, ei
       break;
     case RAND_UNIF:
       op([=](void* o, const std::vector<const void*>& a) {
-        uint64_t offset = eteq::rng_advance((uint64_t)n_out);
-        check(tcr_rand_unif(a[0], a[1], o, n_out, dtype, eteq::rng_seed(), offset), "tcr_rand_unif");
+        eteq::rng_flush();  // (seed, offset) live on the device: graph replays draw fresh numbers
+        eteq::rng_advance((uint64_t)n_out);
+        check(tcr_rand_unif_stream(a[0], a[1], o, n_out, dtype), "tcr_rand_unif_stream");
       });
       break;
     case REVERSE: {
@@ -536,7 +537,13 @@ size_t get_lastvers() { return g_lastvers; }
 void note_version(size_t v) { if (v > g_lastvers) g_lastvers = v; }
 
 static uint64_t g_seed = 0x5eed5eedULL, g_rng_counter = 0;
-void seed(uint64_t s) { g_seed = s; g_rng_counter = 0; }
+static bool g_rng_dirty = true;  // host (seed, offset) not yet pushed to the device generator
+void seed(uint64_t s) { g_seed = s; g_rng_counter = 0; g_rng_dirty = true; }
+void rng_flush() {
+  if (!g_rng_dirty) return;
+  cuda::check(tcr_rand_seed(g_seed, g_rng_counter), "tcr_rand_seed");
+  g_rng_dirty = false;
+}
 uint64_t rng_seed() { return g_seed; }
 uint64_t rng_advance(uint64_t n) {
   uint64_t off = g_rng_counter;

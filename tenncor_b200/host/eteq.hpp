@@ -276,6 +276,7 @@ void note_version(size_t v);
 void seed(uint64_t s);
 uint64_t rng_seed();
 uint64_t rng_advance(uint64_t n);  // returns the offset to use, then advances by n
+void rng_flush();                  // push a pending seed() to the device-resident generator
 
 struct Variable final : public eigen::iMutableLeaf {
   static Variable* get(const void* host_data, egen::_GENERATED_DTYPE dtype, teq::Shape shape, std::string label = "",

@@ -112,6 +112,7 @@ struct Plan {
   int precision = 0;
   size_t n_launch_steps = 0;
   // gradient bucket (data parallel): one flat buffer, one collective per step
+  bool uses_rand = false;
   void* bucket = nullptr;
   size_t bucket_bytes = 0;
   int bucket_dtype = 0;
@@ -940,8 +941,10 @@ struct Plan {
       } else {
         write(nodes[st.out_node].ptr);
       }
-      const bool collective = st.kind == Step::BUCKET_FLUSH || (st.kind == Step::NORMAL && !st.ew && !st.gemm_fused && nodes[st.out_node].op == IDENTITY);
-      if (collective) {  // one communicator, program order
+      // collectives (one communicator) and RAND_UNIF (one generator state) keep program order on lane 0
+      const bool collective = st.kind == Step::BUCKET_FLUSH ||
+                              (st.kind == Step::NORMAL && !st.ew && !st.gemm_fused && (nodes[st.out_node].op == IDENTITY || nodes[st.out_node].op == RAND_UNIF));
+      if (collective) {
         if (last_comm >= 0) d.push_back(last_comm);
         last_comm = s;
       }
@@ -952,7 +955,9 @@ struct Plan {
     for (int s = 0; s < ns; ++s) {
       Step& st = steps[s];
       int lane = -1;
-      if (st.kind == Step::BUCKET_FLUSH || (st.kind == Step::NORMAL && !st.ew && !st.gemm_fused && nodes[st.out_node].op == IDENTITY)) lane = 0;
+      if (st.kind == Step::BUCKET_FLUSH ||
+          (st.kind == Step::NORMAL && !st.ew && !st.gemm_fused && (nodes[st.out_node].op == IDENTITY || nodes[st.out_node].op == RAND_UNIF)))
+        lane = 0;
       if (lane < 0) {  // continue the lane of the latest producer when this step directly follows it there
         for (auto it = deps[s].rbegin(); it != deps[s].rend(); ++it)
           if (lane_tail[step_lane[*it]] == *it) { lane = step_lane[*it]; break; }
@@ -1015,8 +1020,9 @@ struct Plan {
     bucket_gradients();
     assign_buffers();
     n_launch_steps = steps.size();
-    // RAND_UNIF draws a fresh Philox offset at every launch: such plans are launched eagerly
-    use_graph = !has_rand && std::getenv("TCR_NO_GRAPH") == nullptr && !steps.empty();
+    // RAND_UNIF reads and advances the device-resident generator state: graph replays draw fresh numbers
+    use_graph = std::getenv("TCR_NO_GRAPH") == nullptr && !steps.empty();
+    uses_rand = has_rand;
     const char* lanes_env = std::getenv("TCR_GRAPH_LANES");
     int n_lanes = lanes_env ? std::atoi(lanes_env) : TCR_GRAPH_LANES;
     if (n_lanes > TCR_GRAPH_LANES) n_lanes = TCR_GRAPH_LANES;
@@ -1097,6 +1103,7 @@ struct Plan {
     bool changed = propagate_versions(max_version);
     if (has_run && !changed && !always_run) return;
     if (steps.empty()) { has_run = true; return; }
+    if (uses_rand) eteq::rng_flush();  // a seed() since the last run must reach the device before a replay
     if (use_graph && has_run) {
       if (!graph) {
         check(tcr_graph_begin(), "tcr_graph_begin");
