@@ -45,6 +45,9 @@ WORKLOADS = {
     "c4": dict(kind="lstm", vocab=128, hidden=1024, seq=128, batch=64),
     "c4gru": dict(kind="gru", vocab=128, hidden=1024, seq=128, batch=64),
     "c5": dict(kind="dqn", nobs=10, nunits=9, nactions=9, nbatch=4096),
+    # SURVEY §8a row a12 (CONV; not one of BASELINE's configs): one conv2d layer + sigmoid trained like gd_demo. The CPU oracle of the
+    # reference's padded-rank formulation needs minutes per step at this size: run with --cpu-seconds 0 to skip that leg.
+    "conv": dict(kind="conv", in_ch=32, out_ch=64, width=34, height=34, nbatch=64),
 }
 
 
@@ -59,6 +62,9 @@ def build_config(name):
     elif kind == "rbm":
         cfg = configs.rbm(name=name, **w)
         gen = lambda rng: ((rng.random(cfg.feeds["x"].shape()) < 0.5).astype(np.float32),)  # noqa: E731
+    elif kind == "conv":
+        cfg = configs.conv_layer(name=name, **w)
+        gen = lambda rng: configs.cnn_batch(rng, cfg.feeds)  # noqa: E731
     elif kind == "dqn":
         cfg = configs.dqn(name=name, **w)
         gen = lambda rng: tuple(configs.dqn_batch(rng, cfg.feeds)[k] for k in cfg.feeds)  # noqa: E731
@@ -134,8 +140,11 @@ def dominant_kernel_roofline(cabi, name, w, peaks):
     F = cabi.FLOAT
     start, stop_ms = event_timer(cabi)
     rng = np.random.default_rng(7)
-    if "ninput" in w or "vocab" in w:
-        if "ninput" in w:
+    if "ninput" in w or "vocab" in w or "in_ch" in w:
+        if "in_ch" in w:
+            M, K, N = (w["width"] - 2) * (w["height"] - 2) * w["nbatch"], 9 * w["in_ch"], w["out_ch"]
+            label = "tcr_gemm conv2d forward (positions x patch)(patch x out) 3xTF32"
+        elif "ninput" in w:
             M, K, N = w["nbatch"], w["ninput"], w["nhidden"]
             label = "tcr_gemm fwd layer0 (B x in)(in x hid) 3xTF32"
         else:
@@ -269,7 +278,7 @@ def main():
     if world > 1:
         ids = [tc.dp.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
-        mean_loss = WORKLOADS[args.workload]["kind"] in ("mlp", "rbm", "dqn")  # reduce_mean losses; the LSTM's NLL is a sum
+        mean_loss = WORKLOADS[args.workload]["kind"] in ("mlp", "rbm", "dqn", "conv")  # reduce_mean losses; the LSTM's NLL is a sum
         tc.dp.init(rank, world, ids[0], mean_reduce=mean_loss)
 
     cfg, gen, w = build_config(args.workload)
@@ -347,7 +356,12 @@ def main():
                 roof["traffic_source"] = tr["source"]
         except Exception:
             pass
-        med, nsteps = cpu_reference_steps(cfg, gen, budget_s=args.cpu_seconds, max_steps=20)
+        if args.cpu_seconds > 0:
+            med, nsteps = cpu_reference_steps(cfg, gen, budget_s=args.cpu_seconds, max_steps=20)
+            cpu_baseline = {"value": round(1.0 / med, 4), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+                            "sample": "%d full steps of the same graph on the host (numpy oracle of the Eigen path)" % nsteps}
+        else:
+            cpu_baseline = None  # --cpu-seconds 0: the CPU leg was skipped on request
         ms_step = ms_total / args.steps
         line = {
             "metric": metric, "value": round(world * 1e3 / ms_step, 3), "unit": "steps/s (sum over GPUs of per-GPU steps/s; each step = one local batch)",
@@ -355,7 +369,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(wdesc, desc=cfg.desc, batch_per_gpu=w.get("nbatch", w.get("batch")), global_batch=(w.get("nbatch") or w.get("batch") or 1) * world,
                            evaluator=args.evaluator, matmul=args.precision, parallelism="dp%d" % world,
-                           cache="step working set %s L2 (126 MB); no flush" % ("exceeds" if args.workload in ("c3", "c1w", "c4", "c4gru", "c2") else "is resident in")),
+                           cache="step working set %s L2 (126 MB); no flush" % ("exceeds" if args.workload in ("c3", "c1w", "c4", "c4gru", "c2", "conv") else "is resident in")),
             "samples_per_s": round(world * (w.get("nbatch") or w.get("batch") or 1) * 1e3 / ms_step, 1),
             "flops_per_step": cfg.flops_per_step, "tflops": round(cfg.flops_per_step / ms_step / 1e9, 2),
             "clocks": clocks,
@@ -363,8 +377,7 @@ def main():
                     "ms_per_step": round(e2e_ms / args.steps, 4)},
             "gpu_launches": launches, "launches_per_step": round(launches / args.steps, 1), "plan": plan,
             "roofline": roof,
-            "cpu_baseline": {"value": round(1.0 / med, 4), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": "%d full steps of the same graph on the host (numpy oracle of the Eigen path)" % nsteps},
+            "cpu_baseline": cpu_baseline,
             "final_loss": float(np.asarray(loss).reshape(-1)[0]),
         }
         print(json.dumps(line), flush=True)

@@ -315,6 +315,15 @@ int tcr_contract(const void* a, const void* b, void* out, const int64_t a_shape[
 int tcr_conv(const void* image, const void* kernel, void* out, const int64_t img_shape[8],
              const int64_t kern_shape[8], const int32_t order[8], int dtype);
 
+/* Patch gather for the conv2d composite (cfg/tenncor/nn.yml:48-98 = PAD along a fresh rank +
+ * REVERSE(kernel) + CONV + PERMUTE): cols[pos][win] = image[pos + win], where `pos` runs over the
+ * valid positions (img_shape - win_shape + 1 per rank, rank 0 fastest) and `win` over the window
+ * coordinates (rank 0 fastest); each row is zero-filled up to `row_pitch` elements (a multiple
+ * of 4). The multi-filter correlation is then ONE tcr_gemm over `cols` on the tensor cores
+ * instead of operator.hpp:1143-1187's scalar slide over a mostly-zero rank. 4-byte elements. */
+int tcr_im2col(const void* image, void* cols, const int64_t img_shape[8], const int64_t win_shape[8],
+               int64_t row_pitch, int elem_size);
+
 /* --------------------------------------------------------------- collectives */
 
 /* NCCL data-parallel gradient exchange (replaces tenncor/distr's gRPC/consul path for

@@ -167,3 +167,54 @@ def dqn_batch(rng, cfg_feeds):
         "nxt_outmask": (rng.random(nb) < 0.95).astype(np.float32),
         "rewards": rng.uniform(-1, 1, nb).astype(np.float32),
     }
+
+
+def cnn(in_ch=3, mid_ch=8, out_ch=4, width=12, height=10, nbatch=4, kernel_hw=(3, 3), learning_rate=0.5, seed=6, name="CNN"):
+    """layer.conv2d -> sigmoid -> layer.conv2d -> sigmoid, MSE, SGD: the conv2d layer
+    (cfg/tenncor/layer.yml:130-160,657-677 over nn.yml:48-98) driven like the gd_demo MLP. The reference
+    ships no conv demo; this is the smallest model that exercises CONV forward,
+    its kernel gradient (tensor-core GEMMs over a patch gather) and its image gradient."""
+    tc.seed(seed)
+    kh, kw = kernel_hw
+    oh, ow = height - 2 * (kh - 1), width - 2 * (kw - 1)
+    train_input = tc.EVariable([nbatch, height, width, in_ch], 0, "train_input")
+    train_exout = tc.EVariable([nbatch, oh, ow, out_ch], 0, "train_exout")
+    model = tc.api.layer.link([
+        tc.api.layer.conv2d((kh, kw), in_ch, mid_ch),
+        tc.api.layer.bind(tc.api.sigmoid),
+        tc.api.layer.conv2d((kh, kw), mid_ch, out_ch),
+        tc.api.layer.bind(tc.api.sigmoid),
+    ], train_input)
+    train = tc.apply_update(
+        [model],
+        lambda err, leaves: tc.api.approx.sgd(err, leaves, learning_rate=learning_rate),
+        lambda models: tc.api.loss.mean_squared(train_exout, models[0].connect(train_input)))
+    mh, mw = height - kh + 1, width - kw + 1
+    # forward + kernel gradient of both layers, image gradient of the second; the post-update forward again
+    flops = 2 * nbatch * kh * kw * (3 * mh * mw * in_ch * mid_ch + 4 * oh * ow * mid_ch * out_ch)
+    return Config(name, train, {"x": train_input, "y": train_exout}, model, model.get_storage(), flops,
+                  "CNN conv%dx%d %d-%d-%d sigmoid on %dx%d, MSE, SGD %.2g, batch %d" % (kh, kw, in_ch, mid_ch, out_ch, width, height, learning_rate, nbatch))
+
+
+def conv_layer(in_ch=32, out_ch=64, width=34, height=34, nbatch=64, kernel_hw=(3, 3), learning_rate=0.5, seed=7, name="CONV"):
+    """One layer.conv2d + sigmoid, MSE, SGD. No image gradient is built for the first layer's input
+    (internal/teq/src/derive.cpp:151-159), so every CONV in the step lowers to patch gather + GEMM."""
+    tc.seed(seed)
+    kh, kw = kernel_hw
+    oh, ow = height - kh + 1, width - kw + 1
+    train_input = tc.EVariable([nbatch, height, width, in_ch], 0, "train_input")
+    train_exout = tc.EVariable([nbatch, oh, ow, out_ch], 0, "train_exout")
+    model = tc.api.layer.link([tc.api.layer.conv2d((kh, kw), in_ch, out_ch), tc.api.layer.bind(tc.api.sigmoid)], train_input)
+    train = tc.apply_update(
+        [model],
+        lambda err, leaves: tc.api.approx.sgd(err, leaves, learning_rate=learning_rate),
+        lambda models: tc.api.loss.mean_squared(train_exout, models[0].connect(train_input)))
+    flops = 3 * 2 * nbatch * oh * ow * kh * kw * in_ch * out_ch  # forward, kernel gradient, post-update forward
+    return Config(name, train, {"x": train_input, "y": train_exout}, model, model.get_storage(), flops,
+                  "conv%dx%d %d->%d sigmoid on %dx%d, MSE, SGD %.2g, batch %d" % (kh, kw, in_ch, out_ch, width, height, learning_rate, nbatch))
+
+
+def cnn_batch(rng, cfg_feeds):
+    x = rng.random(cfg_feeds["x"].shape(), dtype=np.float32)
+    y = rng.random(cfg_feeds["y"].shape(), dtype=np.float32)
+    return x, y

@@ -1,0 +1,94 @@
+// im2col.cu — patch gather that turns the reference's conv2d composite into a GEMM operand.
+//
+// The reference has no multi-filter convolution opcode: nn.conv2d (cfg/tenncor/nn.yml:48-98)
+// zero-pads the image along a fresh rank by (out-1, out-1) and runs the single-kernel N-d valid
+// correlation CONV (internal/eigen/operator.hpp:1143-1187) with the reversed kernel sliding along
+// that rank, so every output channel is one position of the slide and (2*out-1)/1 of the products
+// multiply a zero. The planner recognises the composite (planner.cpp, fuse_convs) and computes
+//     out[(x,y,b), o] = sum_{c,i,j} img[c, x+i, y+j, b] * k[o, c, i, j]
+// as cols[(x,y,b), (c,i,j)] . k[(c,i,j), o] on the tcgen05 GEMM. This file produces `cols`.
+//
+// HBM-bound: algorithmic bytes = 4 * (rows * pitch written + image read once).
+#include <cstring>
+
+#include "common.cuh"
+
+namespace tcr {
+
+struct Im2colDesc {
+  int n_pos, n_win;
+  int64_t rows, k, pitch4;       // pitch4 = row pitch in 16-byte groups
+  int64_t pos_ext[8], pos_stride[8];
+  int64_t win_ext[8], win_stride[8];
+};
+
+// one thread per 16-byte group of a row: 4 consecutive window elements
+__global__ void __launch_bounds__(256) im2col_kernel(const uint32_t* __restrict__ img, uint4* __restrict__ cols, Im2colDesc d) {
+  const int64_t total = d.rows * d.pitch4;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = t / d.pitch4, g = t - row * d.pitch4;
+    int64_t base = 0, r = row;
+#pragma unroll 1
+    for (int q = 0; q < d.n_pos; ++q) {
+      const int64_t c = r % d.pos_ext[q];
+      r /= d.pos_ext[q];
+      base += c * d.pos_stride[q];
+    }
+    uint32_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int64_t kk = g * 4 + e;
+      v[e] = 0u;
+      if (kk < d.k) {
+        int64_t off = base;
+#pragma unroll 1
+        for (int q = 0; q < d.n_win; ++q) {
+          const int64_t c = kk % d.win_ext[q];
+          kk /= d.win_ext[q];
+          off += c * d.win_stride[q];
+        }
+        v[e] = __ldg(img + off);
+      }
+    }
+    cols[t] = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+}  // namespace tcr
+
+using namespace tcr;
+
+extern "C" {
+
+int tcr_im2col(const void* image, void* cols, const int64_t img_shape[8], const int64_t win_shape[8], int64_t row_pitch, int elem_size) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(image && cols && img_shape && win_shape, "tcr_im2col: null argument");
+  TCR_ARG(elem_size == 4, "tcr_im2col: 4-byte elements only (got %d)", elem_size);
+  TCR_ARG((((uintptr_t)cols) & 15) == 0, "tcr_im2col: cols must be 16-byte aligned");
+  Im2colDesc d;
+  memset(&d, 0, sizeof(d));
+  d.rows = 1;
+  d.k = 1;
+  int64_t stride = 1;
+  for (int r = 0; r < 8; ++r) {
+    TCR_ARG(img_shape[r] >= 1 && win_shape[r] >= 1 && win_shape[r] <= img_shape[r], "tcr_im2col: window %lld does not fit image extent %lld at rank %d",
+            (long long)win_shape[r], (long long)img_shape[r], r);
+    const int64_t pos = img_shape[r] - win_shape[r] + 1;
+    if (pos > 1) { d.pos_ext[d.n_pos] = pos; d.pos_stride[d.n_pos] = stride; d.n_pos++; d.rows *= pos; }
+    if (win_shape[r] > 1) {
+      // a window that covers a whole rank continues the run of the rank below it
+      if (d.n_win > 0 && d.win_stride[d.n_win - 1] * d.win_ext[d.n_win - 1] == stride) d.win_ext[d.n_win - 1] *= win_shape[r];
+      else { d.win_ext[d.n_win] = win_shape[r]; d.win_stride[d.n_win] = stride; d.n_win++; }
+      d.k *= win_shape[r];
+    }
+    stride *= img_shape[r];
+  }
+  TCR_ARG(row_pitch >= d.k && row_pitch % 4 == 0, "tcr_im2col: row pitch %lld must be a multiple of 4 and at least %lld", (long long)row_pitch, (long long)d.k);
+  d.pitch4 = row_pitch / 4;
+  int grid = wave_grid(d.rows * d.pitch4, 256, 8);
+  TCR_LAUNCH(im2col_kernel, grid, 256, 0, (const uint32_t*)image, (uint4*)cols, d);
+  TCR_CHECK_LAUNCH();
+  return TCR_OK;
+}
+
+}  // extern "C"

@@ -55,6 +55,7 @@ struct PNode {
   int gemm_src = -1, gemm_bias = -1, gemm_epi = 0, gemm_act = 0;
   bool gemm_transposed = false;  // PERMUTE{1,0} of a GEMM: computed as (B^T A^T), no copy
   int64_t bucket_slot = -1;      // >= 0: this node's buffer is the gradient bucket at this byte offset
+  int conv = -1;                 // >= 0: produced by the patch-gather + GEMM step `convs[conv]` (fuse_convs)
 };
 
 struct InputRef {
@@ -88,12 +89,26 @@ struct Step {
   // fused GEMM epilogue (in[2] = bias)
   bool gemm_fused = false;
   tcr_gemm_desc gemm;
+  // conv2d composite as patch gather + GEMM (fuse_convs): in = {image, kernel | upstream gradient, [bias]}
+  bool conv_fused = false, conv_grad = false;
+  int64_t conv_img[8], conv_win[8], conv_pitch = 0, conv_rows = 0;
+  void* conv_cols = nullptr;
   // data-parallel gradient bucket: member = a gradient placed in the bucket (copy, or nothing when
   // its producer already wrote there); flush = ONE all-reduce over the whole bucket
   enum Kind { NORMAL = 0, BUCKET_MEMBER, BUCKET_FLUSH } kind = NORMAL;
   bool member_in_place = false;
   size_t bucket_offset = 0;         // member: byte offset of its slot
   std::vector<int> bucket_members;  // flush: member step indices
+};
+
+// One recognised conv2d composite (cfg/tenncor/nn.yml:48-98) or its kernel gradient
+// (tenncor/eteq/backprop.hpp CONV rule, arg 1): see Plan::fuse_convs.
+struct ConvFuse {
+  bool grad = false;
+  int img = -1, other = -1;  // arg nodes read directly: the un-padded image; the kernel (forward) / upstream gradient (grad)
+  int first = 0;             // earliest node position whose read moves to the fused step
+  int64_t img_shape[8], win[8], rows = 1, k = 1, pitch = 0;
+  tcr_gemm_desc gemm;
 };
 
 }  // namespace
@@ -183,6 +198,7 @@ struct Plan {
   // ---------------------------------------------------------------- EW regions
   std::unordered_map<int, std::vector<int>> members;       // region root -> member nodes (incl. root)
   std::unordered_map<int, std::vector<int>> assign_pos;    // mutable leaf -> positions of ASSIGN nodes writing it
+  std::vector<ConvFuse> convs;
 
   uint32_t bcast_mask(const Shape& src, const Shape& dst) const {
     uint32_t m = 0;
@@ -398,6 +414,245 @@ struct Plan {
     return false;
   }
 
+
+  // ---------------------------------------------------------------- conv2d composite -> patch gather + GEMM
+  // The reference has no multi-filter convolution opcode. nn.conv2d (cfg/tenncor/nn.yml:48-98) is
+  //   PERMUTE(CONV(PAD(img, fresh rank d by (out-1, out-1)), REVERSE(kernel, {0}), {d, 0, 1, 2}), {d, 1, 2, 3})
+  // i.e. the single-kernel N-d valid correlation (operator.hpp:1143-1187) slides the reversed kernel along a
+  // zero-padded rank so that each of its `out` positions meets exactly one filter. Seen whole it is
+  //   out[(x,y,b), o] = sum_{c,i,j} img[c, x+i, y+j, b] * kernel[o, c, i, j]
+  // = cols[(x,y,b), (c,i,j)] . kernel[(c,i,j), o]: a patch gather (tcr_im2col) and ONE tensor-core GEMM whose
+  // row-major output already has the PERMUTE's layout. Its kernel gradient (backprop.hpp CONV rule, arg 1, followed
+  // by the PERMUTE / REVERSE rules) REVERSE(PERMUTE(CONV(PAD(img), sup', identity))) is cols^T . sup in the kernel's
+  // own layout. Anything that does not match keeps the generic CONV kernel.
+  static RanksT full_order(const iFunctor& f) {
+    RanksT order = eigen::unpack_ranks(f);
+    if (order.size() > rank_cap) order.resize(rank_cap);
+    bool visited[rank_cap] = {false};
+    for (auto r : order) {
+      if (r >= rank_cap || visited[r]) return {};
+      visited[r] = true;
+    }
+    for (RankT i = 0; i < rank_cap; ++i)
+      if (!visited[i]) order.push_back(i);
+    return order;
+  }
+
+  // the node whose buffer `arg` names element for element (looks through IDENTITY-like views), or -1
+  int solid(int arg) const {
+    const PNode& a = nodes[arg];
+    if (a.offset != 0 || !(nodes[a.root].shape == a.shape)) return -1;
+    return a.root;
+  }
+
+  struct PadTrick {
+    int pad = -1, img = -1, d = -1;
+    int64_t p = 0;
+  };
+
+  // PAD of one singular trailing rank d by (p, p), p >= 1
+  bool pad_trick(int arg, PadTrick& t) const {
+    const int xi = solid(arg);
+    if (xi < 0) return false;
+    const PNode& x = nodes[xi];
+    if (!x.func || x.op != PAD || x.dtype != FLOAT || x.args.size() != 1) return false;
+    auto pads = eigen::unpack_dimpairs(*x.func);
+    int d = -1;
+    int64_t p = 0;
+    for (size_t r = 0; r < pads.size() && r < rank_cap; ++r) {
+      if (pads[r].first == 0 && pads[r].second == 0) continue;
+      if (d >= 0 || pads[r].first != pads[r].second) return false;
+      d = (int)r;
+      p = pads[r].first;
+    }
+    if (d < 0 || p < 1) return false;
+    const PNode& img = nodes[x.args[0]];
+    if (img.dtype != FLOAT) return false;
+    for (int r = d; r < rank_cap; ++r)
+      if (img.shape.at(r) != 1) return false;
+    t.pad = xi; t.img = x.args[0]; t.d = d; t.p = p;
+    return true;
+  }
+
+  // in the memory order of PERMUTE(src, perm): is d the fastest non-singular rank and are the others ascending?
+  static bool d_first(const Shape& src, const RanksT& perm, int d) {
+    int prev = -1;
+    bool first = true;
+    for (int q = 0; q < rank_cap; ++q) {
+      const int r = perm[q];
+      if (src.at(r) == 1) continue;
+      if (first) {
+        if (r != d) return false;
+        first = false;
+        continue;
+      }
+      if (r <= prev) return false;
+      prev = r;
+    }
+    return !first;
+  }
+
+  bool assigned_between(std::initializer_list<int> arg_nodes, int lo, int hi) const {
+    for (int a : arg_nodes) {
+      auto it = assign_pos.find(nodes[a].root);
+      if (it == assign_pos.end()) continue;
+      for (int pos : it->second)
+        if (pos > lo && pos < hi) return true;
+    }
+    return false;
+  }
+
+  void fuse_convs() {
+    if (std::getenv("TCR_NO_CONV_GEMM")) return;
+    std::unordered_map<int, size_t> skipped;  // helper node (PAD / REVERSE / PERMUTE) -> consumers that now read through it
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      PNode& n = nodes[i];
+      if (!n.func || n.is_view || n.dtype != FLOAT || n.args.size() != 1) continue;
+      if (n.op == PERMUTE) {
+        // ---- forward
+        const int ci = solid(n.args[0]);
+        if (ci < 0) continue;
+        PNode& c = nodes[ci];
+        if (!c.func || c.op != CONV || c.dtype != FLOAT || c.exposed || c.inlined || c.consumers.size() != 1 || c.args.size() != 2) continue;
+        const RanksT order = full_order(*c.func), perm = full_order(*n.func);
+        if (order.empty() || perm.empty()) continue;
+        PadTrick t;
+        if (!pad_trick(c.args[0], t) || order[0] != t.d) continue;
+        const int ki = solid(c.args[1]);
+        if (ki < 0) continue;
+        const PNode& kr = nodes[ki];
+        if (!kr.func || kr.op != REVERSE || kr.dtype != FLOAT || kr.args.size() != 1) continue;
+        auto rset = eigen::unpack_rankset(*kr.func);
+        if (rset.size() != 1 || *rset.begin() != 0 || (int64_t)kr.shape.at(0) != t.p + 1) continue;
+        ConvFuse cf;
+        const PNode& img = nodes[t.img];
+        for (int r = 0; r < rank_cap; ++r) { cf.img_shape[r] = img.shape.at(r); cf.win[r] = 1; }
+        bool ok = true;
+        int prev = -1;
+        for (int q = 1; q < rank_cap; ++q) {  // kernel rank q slides along image rank order[q]
+          if (kr.shape.at(q) == 1) continue;
+          const int r = order[q];
+          if (r <= prev || r >= t.d) ok = false;  // window coordinates must enumerate in the kernel's memory order
+          prev = r;
+          if (ok) cf.win[r] = kr.shape.at(q);
+        }
+        for (int r = 0; r < rank_cap && ok; ++r) {
+          const int64_t e = r == t.d ? t.p + 1 : cf.img_shape[r] - cf.win[r] + 1;
+          if (e < 1 || (int64_t)c.shape.at(r) != e) ok = false;
+          if (r != t.d) { cf.rows *= e; cf.k *= cf.win[r]; }
+        }
+        if (!ok || !d_first(c.shape, perm, t.d)) continue;
+        cf.pitch = (cf.k + 3) / 4 * 4;
+        cf.img = t.img;
+        cf.other = kr.args[0];
+        cf.first = std::min({t.pad, ki, ci});
+        if (assigned_between({cf.img, cf.other}, cf.first, (int)i)) continue;
+        tcr_gemm_desc& g = cf.gemm;
+        std::memset(&g, 0, sizeof(g));
+        g.m = cf.rows; g.n = t.p + 1; g.k = cf.k; g.batch = 1;
+        g.a_sm = cf.pitch; g.a_sk = 1;
+        g.b_sk = g.n; g.b_sn = 1;
+        g.c_sm = g.n; g.c_sn = 1;
+        g.dtype = FLOAT;
+        n.conv = (int)convs.size();
+        convs.push_back(cf);
+        c.inlined = true;
+        ++skipped[t.pad];
+        ++skipped[ki];
+      } else if (n.op == REVERSE) {
+        // ---- kernel gradient
+        auto rset = eigen::unpack_rankset(*n.func);
+        if (rset.size() != 1 || *rset.begin() != 0) continue;
+        const int pi = solid(n.args[0]);
+        if (pi < 0) continue;
+        PNode& p2 = nodes[pi];
+        if (!p2.func || p2.op != PERMUTE || p2.dtype != FLOAT || p2.exposed || p2.inlined || p2.conv >= 0 || p2.consumers.size() != 1 || p2.args.size() != 1) continue;
+        const int ci = solid(p2.args[0]);
+        if (ci < 0) continue;
+        PNode& c = nodes[ci];
+        if (!c.func || c.op != CONV || c.dtype != FLOAT || c.exposed || c.inlined || c.consumers.size() != 1 || c.args.size() != 2) continue;
+        const RanksT order = full_order(*c.func), perm = full_order(*p2.func);
+        if (order.empty() || perm.empty()) continue;
+        PadTrick t;
+        if (!pad_trick(c.args[0], t)) continue;
+        const Shape ss = nodes[c.args[1]].shape;  // the upstream gradient in the CONV's output layout
+        if (nodes[c.args[1]].dtype != FLOAT) continue;
+        bool ok = (int64_t)ss.at(t.d) == t.p + 1 && (int64_t)n.shape.at(0) == t.p + 1;
+        for (int q = 0; q < rank_cap; ++q)
+          if (ss.at(q) > 1 && order[q] != q) ok = false;
+        ConvFuse cf;
+        cf.grad = true;
+        const PNode& img = nodes[t.img];
+        for (int r = 0; r < rank_cap && ok; ++r) {
+          cf.img_shape[r] = img.shape.at(r);
+          cf.win[r] = 1;
+          if (r == t.d) { ok = (int64_t)c.shape.at(r) == t.p + 1; continue; }
+          cf.win[r] = cf.img_shape[r] - (int64_t)ss.at(r) + 1;
+          if (cf.win[r] < 1 || (int64_t)c.shape.at(r) != cf.win[r]) ok = false;
+          cf.rows *= ss.at(r);
+          cf.k *= cf.win[r];
+        }
+        if (!ok || !d_first(c.shape, perm, t.d)) continue;
+        cf.pitch = (cf.k + 3) / 4 * 4;
+        cf.img = t.img;
+        cf.other = c.args[1];
+        cf.first = std::min({t.pad, ci, pi});
+        tcr_gemm_desc& g = cf.gemm;
+        std::memset(&g, 0, sizeof(g));
+        g.m = cf.k; g.n = t.p + 1; g.k = cf.rows; g.batch = 1;
+        g.a_sm = 1; g.a_sk = cf.pitch;      // cols^T
+        g.b_sk = 1; g.b_sn = cf.rows;       // sup' [positions..., out]: out slowest
+        g.c_sm = g.n; g.c_sn = 1;
+        g.dtype = FLOAT;
+        // sup' is normally PERMUTE(sup) of a gradient laid out [out, positions...] (the PERMUTE rule): read that instead
+        int through = -1;
+        const int si = solid(c.args[1]);
+        if (si >= 0 && nodes[si].func && nodes[si].op == PERMUTE && nodes[si].args.size() == 1 && nodes[nodes[si].args[0]].dtype == FLOAT) {
+          const RanksT sperm = full_order(*nodes[si].func);
+          if (!sperm.empty()) {
+            RanksT inv(rank_cap);
+            for (int q = 0; q < rank_cap; ++q) inv[sperm[q]] = (RankT)q;
+            if (d_first(ss, inv, t.d)) through = si;
+          }
+        }
+        if (through >= 0) {
+          cf.other = nodes[through].args[0];
+          cf.first = std::min(cf.first, through);
+          g.b_sk = g.n; g.b_sn = 1;
+        }
+        if (assigned_between({cf.img, cf.other}, cf.first, (int)i)) continue;
+        n.conv = (int)convs.size();
+        convs.push_back(cf);
+        c.inlined = true;
+        p2.inlined = true;
+        ++skipped[t.pad];
+        if (through >= 0) ++skipped[through];
+      }
+    }
+    for (auto& kv : skipped) {
+      PNode& x = nodes[kv.first];
+      if (!x.exposed && !x.inlined && kv.second == x.consumers.size()) x.inlined = true;
+    }
+  }
+
+  void conv_step(Step& st, const ConvFuse& cf, int out_node, int bias_node, int epi, int act) {
+    st.ew = false;
+    st.conv_fused = true;
+    st.conv_grad = cf.grad;
+    st.out_node = out_node;
+    st.gemm = cf.gemm;
+    st.gemm.epilogue = epi;
+    st.gemm.activation = act;
+    for (int r = 0; r < rank_cap; ++r) { st.conv_img[r] = cf.img_shape[r]; st.conv_win[r] = cf.win[r]; }
+    st.conv_pitch = cf.pitch;
+    st.conv_rows = cf.rows;
+    for (int a : {cf.img, cf.other, bias_node}) {
+      if (a < 0) continue;
+      st.in_nodes.push_back(nodes[a].root);
+      st.in_offsets.push_back(nodes[a].offset);
+    }
+  }
+
   // dense layers: act(CONTRACT(x, W) + EXTEND(b)) becomes one GEMM launch with a bias (+ activation)
   // epilogue when the product and the sum have no other reader (cfg/tenncor/layer.yml:636-656,
   // nn.yml:14-47: the backward pass reads the activation's output, not the pre-activation)
@@ -443,14 +698,15 @@ struct Plan {
         const int gi = nodes[n.args[k]].root, oi = nodes[n.args[1 - k]].root;
         PNode& g = nodes[gi];
         PNode& o = nodes[oi];
-        if (!g.func || (g.op != CONTRACT && g.op != MATMUL) || g.exposed || g.inlined || g.consumers.size() != 1) continue;
+        const bool from_conv = g.conv >= 0 && !convs[g.conv].grad;  // conv2d composite: same epilogue on its GEMM
+        if (!g.func || (!from_conv && g.op != CONTRACT && g.op != MATMUL) || g.exposed || g.inlined || g.consumers.size() != 1) continue;
         if (nodes[n.args[k]].offset != 0 || nodes[n.args[1 - k]].offset != 0 || !(g.shape == n.shape)) continue;
         auto gop = dynamic_cast<DevOp*>(g.holder);
-        if (!gop || !gop->gemm() || gop->gemm()->batch != 1) continue;
+        if (!from_conv && (!gop || !gop->gemm() || gop->gemm()->batch != 1)) continue;
         if (!o.is_extend || o.has_scalar || o.exposed || !(o.shape == n.shape) || o.consumers.size() != 1) continue;
         const PNode& b = nodes[o.args[0]];
         // which GEMM index does the bias follow? C is row-major [m][n]: n spans the leading ranks
-        const tcr_gemm_desc& d = *gop->gemm();
+        const tcr_gemm_desc& d = from_conv ? convs[g.conv].gemm : *gop->gemm();
         if (d.c_sn != 1 || d.c_sm != d.n) continue;
         int epi = 0;
         {
@@ -479,6 +735,8 @@ struct Plan {
           }
         }
         bool crosses = false;
+        if (from_conv) crosses = assigned_between({convs[g.conv].img, convs[g.conv].other}, convs[g.conv].first, final_node);
+        else
         for (int arg : g.args) {
           auto it = assign_pos.find(nodes[arg].root);
           if (it == assign_pos.end()) continue;
@@ -515,6 +773,7 @@ struct Plan {
       if (!n.func || n.is_view) continue;
       for (int a : n.args) nodes[nodes[a].root].consumers.push_back((int)i);
     }
+    fuse_convs();
     fuse_gemm_epilogues();
     // non-EW consumers need real buffers: EXTEND operands get materialised. An EW node that cannot
     // be lowered on its own (too many operands / broadcast segments) is demoted to its holder's
@@ -522,6 +781,11 @@ struct Plan {
     for (bool changed = true; changed;) {
       changed = false;
       for (auto& n : nodes) n.needs_mat = false;
+      for (auto& cf : convs)
+        for (int a : {cf.img, cf.other}) {
+          PNode& r = nodes[nodes[a].root];
+          if (r.is_extend) r.needs_mat = true;
+        }
       for (size_t i = 0; i < nodes.size(); ++i) {
         PNode& n = nodes[i];
         if (!n.func || n.is_view) continue;
@@ -597,6 +861,18 @@ struct Plan {
       if (!n.func || n.is_view || n.inlined) continue;
       if (n.is_extend && !n.needs_mat) continue;
       Step st;
+      if (n.gemm_src >= 0 && nodes[n.gemm_src].conv >= 0) {
+        conv_step(st, convs[nodes[n.gemm_src].conv], (int)i, n.gemm_bias, n.gemm_epi, n.gemm_act);
+        n.step = (int)steps.size();
+        steps.push_back(std::move(st));
+        continue;
+      }
+      if (n.conv >= 0) {
+        conv_step(st, convs[n.conv], (int)i, -1, TCR_EPI_NONE, 0);
+        n.step = (int)steps.size();
+        steps.push_back(std::move(st));
+        continue;
+      }
       if (n.gemm_src >= 0) {
         PNode& g = nodes[n.gemm_src];
         auto gop = dynamic_cast<DevOp*>(g.holder);
@@ -867,6 +1143,7 @@ struct Plan {
         st.prog.outputs[0].ptr = out.ptr;
       } else {
         st.out = out.ptr;
+        if (st.conv_fused) st.conv_cols = alloc_owned((size_t)st.conv_rows * (size_t)st.conv_pitch * sizeof(float));
         for (size_t k = 0; k < st.in_nodes.size(); ++k) {
           PNode& in = nodes[st.in_nodes[k]];
           if (!in.ptr) global::fatalf("planner: input %s of %s was never materialised", in.tens->to_string().c_str(), out.tens->to_string().c_str());
@@ -883,7 +1160,13 @@ struct Plan {
     } else if (st.kind == Step::BUCKET_MEMBER) {
       if (!st.member_in_place) check(tcr_d2d(st.out, st.in[0], (size_t)nodes[st.out_node].n * type_size(nodes[st.out_node].dtype)), "tcr_d2d");
     } else if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
-    else if (st.gemm_fused) {
+    else if (st.conv_fused) {
+      check(tcr_im2col(st.in[0], st.conv_cols, st.conv_img, st.conv_win, st.conv_pitch, (int)sizeof(float)), "tcr_im2col");
+      tcr_gemm_desc d = st.gemm;
+      d.precision = gemm_precision();
+      d.bias = st.in.size() > 2 ? st.in[2] : nullptr;
+      check(tcr_gemm(st.conv_cols, st.in[1], st.out, &d), "tcr_gemm");
+    } else if (st.gemm_fused) {
       tcr_gemm_desc d = st.gemm;
       d.precision = d.dtype == FLOAT ? gemm_precision() : TCR_GEMM_EXACT;
       d.bias = st.in.size() > 2 ? st.in[2] : nullptr;
@@ -997,7 +1280,7 @@ struct Plan {
     if (current != 0) check(tcr_graph_lane(0), "tcr_graph_lane");
   }
 
-  void build(const TensSetT& targets, const TensSetT& ignored, eigen::RTMemptrT mem) {
+  void build(const TensSetT& targets, const TensSetT& ignored, eigen::RTMemptrT mem, bool lower_only = false) {
     memory = std::move(mem);
     precision = gemm_precision();
     std::vector<iTensor*> ordered(targets.begin(), targets.end());
@@ -1018,6 +1301,7 @@ struct Plan {
     fuse();
     build_steps();
     bucket_gradients();
+    if (lower_only) return;
     assign_buffers();
     n_launch_steps = steps.size();
     // RAND_UNIF reads and advances the device-resident generator state: graph replays draw fresh numbers
@@ -1057,6 +1341,20 @@ struct Plan {
     return any;
   }
 
+  std::string step_name(const Step& st) const {
+    if (st.kind == Step::BUCKET_FLUSH) return "ALLREDUCE bucket";
+    const PNode& o = nodes[st.out_node];
+    std::string what = egen::name_op((_GENERATED_OPCODE)o.op);
+    if (st.kind == Step::BUCKET_MEMBER) return what + " -> bucket";
+    if (st.ew) return what + " fused(" + std::to_string(st.prog.n_instrs) + " instr, " + std::to_string(st.prog.n_inputs) + " in)";
+    const std::string mnk = " m" + std::to_string(st.gemm.m) + " n" + std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
+    if (st.conv_fused)
+      return std::string(st.conv_grad ? "CONV2D-dK" : "CONV2D") + " im2col+GEMM" + (st.gemm.epilogue ? "+bias" : "") + (st.gemm.activation ? "+act" : "") + mnk;
+    if (st.gemm_fused && st.in_nodes.size() == 2) return "GEMM^T" + mnk;
+    if (st.gemm_fused) return "GEMM+bias" + std::string(st.gemm.activation ? "+act" : "") + mnk;
+    return what;
+  }
+
   std::vector<StepTiming> profile(int repeats) {
     std::vector<StepTiming> out;
     void *e0 = nullptr, *e1 = nullptr;
@@ -1078,7 +1376,9 @@ struct Plan {
         }
       } else {
         for (int in : st.in_nodes) t.bytes += (size_t)nodes[in].n * type_size(nodes[in].dtype);
-        if (st.gemm_fused && st.in.size() == 2) t.what = "GEMM^T m" + std::to_string(st.gemm.m) + " n" + std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
+        if (st.conv_fused) t.what = std::string(st.conv_grad ? "CONV2D-dK" : "CONV2D") + " im2col+GEMM" + (st.gemm.epilogue ? "+bias" : "") + (st.gemm.activation ? "+act" : "") +
+                                    " m" + std::to_string(st.gemm.m) + " n" + std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
+        else if (st.gemm_fused && st.in.size() == 2) t.what = "GEMM^T m" + std::to_string(st.gemm.m) + " n" + std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
         else if (st.gemm_fused) t.what = "GEMM+bias" + std::string(st.gemm.activation ? "+act" : "") + " m" + std::to_string(st.gemm.m) + " n" +
                                     std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
         else if (o.op == CONTRACT || o.op == MATMUL || o.op == CONV)
@@ -1154,6 +1454,14 @@ void PlanEvaluator::drop_plans() {
 
 void drop_all_plans() {
   for (auto e : live_evaluators()) e->drop_plans();
+}
+
+std::vector<std::string> describe_plan(const TensSetT& targets) {
+  Plan plan;
+  plan.build(targets, {}, nullptr, true);
+  std::vector<std::string> out;
+  for (auto& st : plan.steps) out.push_back(plan.step_name(st) + " " + (st.kind == Step::BUCKET_FLUSH ? std::string() : plan.nodes[st.out_node].shape.to_string()));
+  return out;
 }
 
 std::vector<StepTiming> profile_last_plan(int repeats) {

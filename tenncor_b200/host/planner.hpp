@@ -37,6 +37,9 @@ struct StepTiming {
 };
 std::vector<StepTiming> profile_last_plan(int repeats = 5);
 
+/// lowering only (no device needed): the launch steps a plan for `targets` would consist of, in order
+std::vector<std::string> describe_plan(const teq::TensSetT& targets);
+
 struct PlanCache;
 
 struct PlanEvaluator final : public teq::iEvaluator {

@@ -322,6 +322,11 @@ PYBIND11_MODULE(_tenncor, m) {
     d["nodes"] = s.nodes; d["steps"] = s.steps; d["launches_per_run"] = s.launches; d["graph"] = s.graph; d["plans_cached"] = s.cached;
     return d;
   });
+  m.def("describe_plan", [](const ETensorsT& targets) {
+    teq::TensSetT set;
+    for (auto& t : targets) set.insert(t.get());
+    return cuda::describe_plan(set);
+  }, "Launch steps the planned evaluator lowers `targets` to (host-side lowering only; needs no device)");
   m.def("profile_plan", [](int repeats) {
     py::list out;
     for (auto& t : cuda::profile_last_plan(repeats)) {

@@ -167,6 +167,38 @@ def main():
                 d = cabi.GemmDesc(m=M, n=N, k=K, batch=1, a_sm=1 if ta else K, a_sk=M if ta else 1, b_sk=1 if tb else N, b_sn=K if tb else 1,
                                   c_sm=N, c_sn=1, dtype=F, precision=prec)
                 rec("mm_%s_%s" % (nm, tag), timeit(lambda: cabi.check(lib.tcr_gemm(P(a), P(b), P(out), C.byref(d))), iters=5), flops=2.0 * M * N * K)
+    if want("conv"):
+        # conv2d composite as the planner lowers it (fuse_convs): patch gather (HBM-bound) + GEMM (tensor-bound), and the
+        # generic CONV kernel running the reference's padded-rank formulation of the same layer for contrast (small case only)
+        for tag, (inc, outc, W, Hh, B, kw, kh) in [("3x3_64->64_34x34_B64", (64, 64, 34, 34, 64, 3, 3)), ("3x3_3->64_66x66_B64", (3, 64, 66, 66, 64, 3, 3)),
+                                                   ("5x5_32->128_20x20_B128", (32, 128, 20, 20, 128, 5, 5))]:
+            img_shape, win = [inc, W, Hh, B], [inc, kw, kh, 1]
+            rows, k = (W - kw + 1) * (Hh - kh + 1) * B, inc * kw * kh
+            pitch = (k + 3) // 4 * 4
+            img = cabi.to_device(rng.uniform(-1, 1, inc * W * Hh * B).astype(np.float32))
+            ker = cabi.to_device(rng.uniform(-1, 1, k * outc).astype(np.float32))
+            sup = cabi.to_device(rng.uniform(-1, 1, rows * outc).astype(np.float32))
+            cols = cabi.empty(rows * pitch, np.float32)
+            o = cabi.empty(rows * outc, np.float32)
+            dk = cabi.empty(k * outc, np.float32)
+            s8, w8 = cabi.shape8(img_shape), cabi.shape8(win)
+            gather = lambda: cabi.check(lib.tcr_im2col(P(img), P(cols), s8, w8, C.c_int64(pitch), 4))  # noqa: E731
+            rec("conv_im2col_%s" % tag, timeit(gather), 4 * (rows * pitch + inc * W * Hh * B))
+            for prec, nm in [(1, "tf32"), (2, "3xtf32")]:
+                d = cabi.GemmDesc(m=rows, n=outc, k=k, batch=1, a_sm=pitch, a_sk=1, b_sk=outc, b_sn=1, c_sm=outc, c_sn=1, dtype=F, precision=prec)
+                fwd = lambda: cabi.check(lib.tcr_gemm(P(cols), P(ker), P(o), C.byref(d)))  # noqa: E731
+                rec("conv_fwd_gemm_%s_%s" % (nm, tag), timeit(fwd), flops=2.0 * rows * outc * k)
+                rec("conv_fwd_total_%s_%s" % (nm, tag), timeit(lambda: (gather(), fwd())), flops=2.0 * rows * outc * k)
+                g = cabi.GemmDesc(m=k, n=outc, k=rows, batch=1, a_sm=1, a_sk=pitch, b_sk=outc, b_sn=1, c_sm=outc, c_sn=1, dtype=F, precision=prec)
+                rec("conv_dK_gemm_%s_%s" % (nm, tag), timeit(lambda: cabi.check(lib.tcr_gemm(P(cols), P(sup), P(dk), C.byref(g)))), flops=2.0 * rows * outc * k)
+        inc, outc, W, Hh, B, kw, kh = 8, 16, 18, 18, 8, 3, 3
+        padded = cabi.to_device(np.zeros(inc * W * Hh * B * (2 * outc - 1), np.float32))
+        kr = cabi.to_device(rng.uniform(-1, 1, outc * inc * kw * kh).astype(np.float32))
+        og = cabi.empty((W - kw + 1) * (Hh - kh + 1) * B * outc, np.float32)
+        order = (C.c_int32 * 8)(4, 0, 1, 2, 3, 5, 6, 7)
+        rec("conv_generic_padded_rank_3x3_8->16_18x18_B8",
+            timeit(lambda: cabi.check(lib.tcr_conv(P(padded), P(kr), P(og), cabi.shape8([inc, W, Hh, B, 2 * outc - 1]), cabi.shape8([outc, inc, kw, kh]), order, F))),
+            flops=2.0 * (W - kw + 1) * (Hh - kh + 1) * B * outc * inc * kw * kh)
     return res
 
 
