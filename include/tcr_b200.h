@@ -100,6 +100,14 @@ int tcr_arena_trim(void); /* return cached blocks to the driver */
 int tcr_host_alloc(void** out, size_t bytes); /* pinned */
 int tcr_host_free(void* ptr);
 int tcr_h2d(void* dst, const void* host_src, size_t bytes);
+/* Input prefetch (extension; the reference's Variable::assign is a synchronous memcpy,
+ * tenncor/eteq/variable.hpp:55-90): `tcr_h2d_prefetch` copies a pinned host batch into a device
+ * staging buffer on a dedicated copy stream, so it overlaps the step that is computing;
+ * `tcr_prefetch_commit` makes the library stream wait for that copy and moves staging -> dst
+ * (HBM -> HBM). A later prefetch into the same staging buffer waits for the commit that read it. */
+int tcr_h2d_prefetch(void* staging, const void* host_src, size_t bytes);
+int tcr_prefetch_commit(void* dst, const void* staging, size_t bytes);
+int tcr_prefetch_sync(void); /* wait for the copy stream (tcr_sync covers the library stream only) */
 int tcr_d2h(void* host_dst, const void* src, size_t bytes); /* async; tcr_sync() before reading */
 int tcr_d2d(void* dst, const void* src, size_t bytes);
 int tcr_memset(void* dst, int byte, size_t bytes);

@@ -494,7 +494,10 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
   *handled = false;
   if (d->dtype != TCR_FLOAT || d->k <= 0) return TCR_OK;
   // tiny problems do not fill a 128x128 tile: the SIMT kernel is faster and exact
-  if (d->m * d->n < 64 * 64 || d->k < 16 || d->m * d->n * d->k < (1ll << 20)) return TCR_OK;
+  // ... unless the reduction is long (conv kernel gradients: K = positions x batch): split-K over many CTAs then
+  // gives the parallelism one SIMT tile cannot (measured: 27 x 64 x 262144 took 21 ms on the SIMT kernel)
+  const bool deep = d->k >= 4096 && d->m * d->n >= 256;
+  if ((d->m * d->n < 64 * 64 && !deep) || d->k < 16 || d->m * d->n * d->k < (1ll << 20)) return TCR_OK;
   if (d->batch > 16) return TCR_OK;
   const bool a_k = d->a_sk == 1 || d->k == 1, a_m = d->a_sm == 1 || d->m == 1;
   const bool b_k = d->b_sk == 1 || d->k == 1, b_n = d->b_sn == 1 || d->n == 1;
@@ -545,7 +548,8 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
     static const int min_kb = std::getenv("TCR_GEMM_SPLIT_MIN_KB") ? std::atoi(std::getenv("TCR_GEMM_SPLIT_MIN_KB")) : 8;  // experiment knob; 0 = never split
     if (min_kb > 0 && tiles * 2 <= sms && total_kb >= 16) {
       double best = (double)tiles / (double)(ceil_div(tiles, sms) * sms);
-      for (int sp = 2; sp <= 32 && total_kb / sp >= min_kb; ++sp) {
+      const int sp_cap = total_kb >= sms * 16 ? sms : 32;  // very long reductions may use every SM for one output tile
+      for (int sp = 2; sp <= sp_cap && total_kb / sp >= min_kb; ++sp) {
         double eff = (double)(tiles * sp) / (double)(ceil_div(tiles * sp, sms) * sms);
         if (eff > best + 0.05) { best = eff; splits = sp; }
       }

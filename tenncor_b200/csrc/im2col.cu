@@ -22,7 +22,7 @@ struct Im2colDesc {
   int64_t win_ext[8], win_stride[8];
 };
 
-// one thread per 16-byte group of a row: 4 consecutive window elements
+// generic form: one thread per 16-byte group of a row, 64-bit coordinate arithmetic (any size)
 __global__ void __launch_bounds__(256) im2col_kernel(const uint32_t* __restrict__ img, uint4* __restrict__ cols, Im2colDesc d) {
   const int64_t total = d.rows * d.pitch4;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -54,6 +54,69 @@ __global__ void __launch_bounds__(256) im2col_kernel(const uint32_t* __restrict_
   }
 }
 
+// Tiled form (image < 2^31 elements, window offsets fit shared memory). A block owns IM_ROWS consecutive rows
+// per iteration: the window offsets of a row are the same for every row (computed once per block into shared
+// memory), the row bases once per tile, so the copy loop is one shared-memory lookup, the loads and one 16-byte
+// store per thread with no division chains. VEC: every run of the window is a multiple of 4 elements and
+// 16-byte aligned in the image, so the four elements of a group are one 16-byte load.
+constexpr int IM_ROWS = 32;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) im2col_tiled_kernel(const uint32_t* __restrict__ img, uint4* __restrict__ cols, Im2colDesc d) {
+  extern __shared__ int32_t woff[];  // [pitch4 * 4] window offsets (-1: zero fill), then IM_ROWS row bases
+  const int pitch4 = (int)d.pitch4;
+  int32_t* base = woff + pitch4 * 4;
+  for (int kk = threadIdx.x; kk < pitch4 * 4; kk += blockDim.x) {
+    int32_t off = -1;
+    if (kk < (int)d.k) {
+      int rem = kk;
+      off = 0;
+      for (int q = 0; q < d.n_win; ++q) {
+        const int e = (int)d.win_ext[q];
+        off += (rem % e) * (int32_t)d.win_stride[q];
+        rem /= e;
+      }
+    }
+    woff[kk] = off;
+  }
+  const int64_t n_tiles = (d.rows + IM_ROWS - 1) / IM_ROWS;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();  // woff ready (first pass) / previous tile done with `base`
+    const int64_t row0 = tile * IM_ROWS;
+    if (threadIdx.x < IM_ROWS) {
+      int64_t r = row0 + threadIdx.x;
+      int32_t b = 0;
+      if (r < d.rows) {
+        for (int q = 0; q < d.n_pos; ++q) {
+          const int64_t e = d.pos_ext[q];
+          b += (int32_t)(r % e) * (int32_t)d.pos_stride[q];
+          r /= e;
+        }
+      }
+      base[threadIdx.x] = b;
+    }
+    __syncthreads();
+    const int rows_here = (int)(d.rows - row0 < IM_ROWS ? d.rows - row0 : IM_ROWS);
+    const int work = rows_here * pitch4;
+    uint4* out = cols + row0 * pitch4;
+    for (int t = threadIdx.x; t < work; t += blockDim.x) {
+      const int rr = t / pitch4, g = t - rr * pitch4;
+      const int32_t b = base[rr];
+      const int4 o = *reinterpret_cast<const int4*>(woff + 4 * g);
+      uint4 v;
+      if (VEC) {
+        v = o.x >= 0 ? __ldg(reinterpret_cast<const uint4*>(img + b + o.x)) : make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        v.x = o.x >= 0 ? __ldg(img + b + o.x) : 0u;
+        v.y = o.y >= 0 ? __ldg(img + b + o.y) : 0u;
+        v.z = o.z >= 0 ? __ldg(img + b + o.z) : 0u;
+        v.w = o.w >= 0 ? __ldg(img + b + o.w) : 0u;
+      }
+      out[t] = v;
+    }
+  }
+}
+
 }  // namespace tcr
 
 using namespace tcr;
@@ -70,11 +133,15 @@ int tcr_im2col(const void* image, void* cols, const int64_t img_shape[8], const 
   d.rows = 1;
   d.k = 1;
   int64_t stride = 1;
+  bool vec = (((uintptr_t)image) & 15) == 0;
   for (int r = 0; r < 8; ++r) {
     TCR_ARG(img_shape[r] >= 1 && win_shape[r] >= 1 && win_shape[r] <= img_shape[r], "tcr_im2col: window %lld does not fit image extent %lld at rank %d",
             (long long)win_shape[r], (long long)img_shape[r], r);
     const int64_t pos = img_shape[r] - win_shape[r] + 1;
-    if (pos > 1) { d.pos_ext[d.n_pos] = pos; d.pos_stride[d.n_pos] = stride; d.n_pos++; d.rows *= pos; }
+    if (pos > 1) {
+      d.pos_ext[d.n_pos] = pos; d.pos_stride[d.n_pos] = stride; d.n_pos++; d.rows *= pos;
+      if (stride % 4 != 0) vec = false;
+    }
     if (win_shape[r] > 1) {
       // a window that covers a whole rank continues the run of the rank below it
       if (d.n_win > 0 && d.win_stride[d.n_win - 1] * d.win_ext[d.n_win - 1] == stride) d.win_ext[d.n_win - 1] *= win_shape[r];
@@ -85,8 +152,29 @@ int tcr_im2col(const void* image, void* cols, const int64_t img_shape[8], const 
   }
   TCR_ARG(row_pitch >= d.k && row_pitch % 4 == 0, "tcr_im2col: row pitch %lld must be a multiple of 4 and at least %lld", (long long)row_pitch, (long long)d.k);
   d.pitch4 = row_pitch / 4;
-  int grid = wave_grid(d.rows * d.pitch4, 256, 8);
-  TCR_LAUNCH(im2col_kernel, grid, 256, 0, (const uint32_t*)image, (uint4*)cols, d);
+  // 16-byte loads: the fastest run starts at stride 1, is a multiple of 4 long, and every other run starts 16-byte aligned
+  if (d.n_win == 0 || d.win_stride[0] != 1 || d.win_ext[0] % 4 != 0) vec = false;
+  for (int q = 1; q < d.n_win; ++q)
+    if (d.win_stride[q] % 4 != 0) vec = false;
+  const size_t smem = (size_t)(row_pitch + IM_ROWS) * sizeof(int32_t);
+  if (stride < (1ll << 31) && smem <= 96 * 1024) {
+    const int64_t n_tiles = ceil_div(d.rows, IM_ROWS);
+    const int64_t cap = (int64_t)state().sm_count * 8;
+    const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+    if (smem > 48 * 1024) {
+      static bool raised = false;
+      if (!raised) {
+        TCR_CUDA(cudaFuncSetAttribute(im2col_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        TCR_CUDA(cudaFuncSetAttribute(im2col_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        raised = true;
+      }
+    }
+    if (vec) TCR_LAUNCH((im2col_tiled_kernel<true>), grid, 256, smem, (const uint32_t*)image, (uint4*)cols, d);
+    else TCR_LAUNCH((im2col_tiled_kernel<false>), grid, 256, smem, (const uint32_t*)image, (uint4*)cols, d);
+  } else {
+    int grid = wave_grid(d.rows * d.pitch4, 256, 8);
+    TCR_LAUNCH(im2col_kernel, grid, 256, 0, (const uint32_t*)image, (uint4*)cols, d);
+  }
   TCR_CHECK_LAUNCH();
   return TCR_OK;
 }

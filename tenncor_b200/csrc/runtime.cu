@@ -139,11 +139,24 @@ int tcr_init(int device) {
   return TCR_OK;
 }
 
+// input prefetch state (tcr_h2d_prefetch / tcr_prefetch_commit below)
+static cudaStream_t g_copy_stream = nullptr;
+static cudaEvent_t g_copy_done = nullptr, g_commit_done = nullptr;
+static bool g_copy_pending = false, g_commit_recorded = false;
+
 int tcr_shutdown(void) {
   State& s = state();
   if (!s.ready) return TCR_OK;
   tcr_comm_destroy();
   cudaStreamSynchronize(s.stream);
+  if (g_copy_stream) {
+    cudaStreamSynchronize(g_copy_stream);
+    cudaStreamDestroy(g_copy_stream);
+    cudaEventDestroy(g_copy_done);
+    cudaEventDestroy(g_commit_done);
+    g_copy_stream = nullptr;
+    g_copy_pending = g_commit_recorded = false;
+  }
   tcr_arena_trim();
   cudaStreamDestroy(s.stream);
   s.stream = nullptr;
@@ -249,6 +262,41 @@ int tcr_h2d(void* dst, const void* host_src, size_t bytes) {
   TCR_REQUIRE_DEVICE();
   if (bytes == 0) return TCR_OK;
   TCR_CUDA(cudaMemcpyAsync(dst, host_src, bytes, cudaMemcpyHostToDevice, state().stream));
+  return TCR_OK;
+}
+
+// ---- input prefetch: the next batch crosses PCIe on a copy stream while the current step computes
+
+int tcr_h2d_prefetch(void* staging, const void* host_src, size_t bytes) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(staging && host_src, "tcr_h2d_prefetch: null argument");
+  if (g_copy_stream == nullptr) {
+    TCR_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+    TCR_CUDA(cudaEventCreateWithFlags(&g_copy_done, cudaEventDisableTiming));
+    TCR_CUDA(cudaEventCreateWithFlags(&g_commit_done, cudaEventDisableTiming));
+  }
+  // the staging buffer may still be the source of the previous commit's device copy
+  if (g_commit_recorded) TCR_CUDA(cudaStreamWaitEvent(g_copy_stream, g_commit_done, 0));
+  if (bytes) TCR_CUDA(cudaMemcpyAsync(staging, host_src, bytes, cudaMemcpyHostToDevice, g_copy_stream));
+  TCR_CUDA(cudaEventRecord(g_copy_done, g_copy_stream));
+  g_copy_pending = true;
+  return TCR_OK;
+}
+
+int tcr_prefetch_sync(void) {
+  TCR_REQUIRE_DEVICE();
+  if (g_copy_stream) TCR_CUDA(cudaStreamSynchronize(g_copy_stream));
+  return TCR_OK;
+}
+
+int tcr_prefetch_commit(void* dst, const void* staging, size_t bytes) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(dst && staging, "tcr_prefetch_commit: null argument");
+  TCR_ARG(g_copy_pending, "tcr_prefetch_commit: nothing was prefetched");
+  TCR_CUDA(cudaStreamWaitEvent(state().stream, g_copy_done, 0));
+  if (bytes) TCR_CUDA(cudaMemcpyAsync(dst, staging, bytes, cudaMemcpyDeviceToDevice, state().stream));
+  TCR_CUDA(cudaEventRecord(g_commit_done, state().stream));
+  g_commit_recorded = true;
   return TCR_OK;
 }
 

@@ -107,6 +107,24 @@ DevSrc::DevSrc(const void* host_data, egen::_GENERATED_DTYPE dtype, Shape shape,
 
 DevSrc::~DevSrc() {
   if (dev_) tcr_free(dev_);
+  if (staging_) tcr_free(staging_);
+}
+
+void DevSrc::prefetch_host(const void* host_data) {
+  if (staging_ == nullptr) {
+    device_data();
+    check(tcr_alloc(&staging_, bytes_), "tcr_alloc");
+    sync();  // the block may be recycled from work still queued on the library stream; the copy stream is not ordered with it
+  }
+  check(tcr_h2d_prefetch(staging_, host_data, bytes_), "tcr_h2d_prefetch");
+  staged_ = true;
+}
+
+void DevSrc::commit_prefetch() {
+  if (!staged_) global::fatal("commit without a prefetched batch");
+  check(tcr_prefetch_commit(dev_, staging_, bytes_), "tcr_prefetch_commit");
+  staged_ = false;
+  mirror_.invalidate();
 }
 
 void* DevSrc::data() {
@@ -581,6 +599,20 @@ void Variable::assign(const void* input, egen::_GENERATED_DTYPE dtype, Shape sha
   egen::type_convert(tmp.data(), meta_.dtype_, input, dtype, n);
   ref_->assign_host(tmp.data());
   if (ref_->resident()) cuda::sync();  // tmp goes out of scope
+}
+
+void Variable::prefetch(const void* input, egen::_GENERATED_DTYPE dtype, Shape shape) {
+  if (false == shape.compatible_after(shape_, 0))
+    global::fatalf("assigning data shaped %s to tensor %s", shape.to_string().c_str(), shape_.to_string().c_str());
+  if (dtype != meta_.dtype_)
+    global::fatalf("prefetch needs %s data (got %s): the copy is asynchronous, no conversion buffer outlives the call",
+                   egen::name_type(meta_.dtype_).c_str(), egen::name_type(dtype).c_str());
+  ref_->prefetch_host(input);
+}
+
+void Variable::commit() {
+  upversion(get_lastvers() + 1);
+  ref_->commit_prefetch();
 }
 
 void Variable::assign_device(const void* dev_input) {

@@ -146,10 +146,16 @@ struct DevSrc final : public eigen::iEigen {
   void assign_host(const void* host_data);
   /// HBM -> HBM
   void assign_device(const void* dev_data);
+  /// pinned host -> device staging buffer on the copy stream (overlaps the running step); `commit_prefetch`
+  /// makes the staged batch this leaf's data (stream-ordered HBM -> HBM copy)
+  void prefetch_host(const void* host_data);
+  void commit_prefetch();
   size_t bytes() const { return bytes_; }
 
  private:
   void* dev_ = nullptr;
+  void* staging_ = nullptr;
+  bool staged_ = false;
   size_t bytes_;
   bool keep_host_;  // constants keep their host copy (is_scalar / const folding read it)
   mutable HostMirror mirror_;
@@ -286,6 +292,11 @@ struct Variable final : public eigen::iMutableLeaf {
   void assign(const void* input, egen::_GENERATED_DTYPE dtype, teq::Shape shape);
   /// device pointer of this variable's own dtype (stays on HBM)
   void assign_device(const void* dev_input);
+  /// double-buffered input: `prefetch` starts the host -> HBM copy of the NEXT batch (pinned memory, this variable's
+  /// dtype) on the copy stream while the current step computes; `commit` makes it the variable's data and bumps the
+  /// version exactly like `assign`. Extension of Variable<T>::assign (tenncor/eteq/variable.hpp:55-90).
+  void prefetch(const void* input, egen::_GENERATED_DTYPE dtype, teq::Shape shape);
+  void commit();
   teq::Shape shape() const override { return shape_; }
   teq::iDeviceRef& device() override { return *ref_; }
   const teq::iDeviceRef& device() const override { return *ref_; }

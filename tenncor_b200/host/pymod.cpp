@@ -241,6 +241,14 @@ PYBIND11_MODULE(_tenncor, m) {
         py::array arr = normalise(data, shape, dtype);
         self.assign(arr.data(), dtype, shape);
       }, py::arg("data"), "Assign numpy data array to variable (host -> HBM, asynchronous for pinned arrays)")
+      .def("prefetch", [](eteq::Variable& self, py::array data) {
+        Shape shape;
+        egen::_GENERATED_DTYPE dtype;
+        py::array arr = normalise(data, shape, dtype);
+        if (arr.data() != data.data()) global::fatal("prefetch needs a C-contiguous array that stays alive until commit (pinned for overlap)");
+        self.prefetch(arr.data(), dtype, shape);
+      }, py::arg("data"), "Start copying the NEXT batch host -> HBM on the copy stream; overlaps the step being evaluated")
+      .def("commit", [](eteq::Variable& self) { self.commit(); }, "Make the prefetched batch this variable's data (version bump like assign)")
       .def("touch", [](eteq::Variable& self) { self.upversion(eteq::get_lastvers() + 1); },
            "Bump the version as if new data had been assigned (the data already in HBM is kept)")
       .def("assign_device", [](eteq::Variable& self, uintptr_t dev_ptr) { self.assign_device((const void*)dev_ptr); },
@@ -308,6 +316,7 @@ PYBIND11_MODULE(_tenncor, m) {
   // ---- back-end controls
   m.def("sync", [] { cuda::sync(); }, "Wait for all queued device work");
   m.def("launch_count", [] { return tcr_launch_count(); });
+  m.def("sync_prefetch", [] { cuda::check(tcr_prefetch_sync(), "tcr_prefetch_sync"); }, "Wait for input copies started by EVariable.prefetch");
   m.def("set_matmul_precision", [](const std::string& p) {
     cuda::set_gemm_precision(p == "exact" ? TCR_GEMM_EXACT : p == "tf32" ? TCR_GEMM_TF32 : p == "3xtf32" ? TCR_GEMM_3XTF32 : -1);
   }, "fp32 MATMUL/CONTRACT precision: 'exact' (SIMT FMA), 'tf32' or '3xtf32' (tcgen05)");

@@ -41,7 +41,8 @@ def test_skinny_epilogue_and_perm(gpu):
 
 
 @pytest.mark.parametrize("precision", [1, 2], ids=["tf32", "3xtf32"])
-@pytest.mark.parametrize("M,N,K,ta,tb", [(1024, 784, 8192, 1, 0), (256, 128, 4096, 0, 0), (128, 128, 32768, 0, 1), (384, 640, 2048, 1, 1)])
+@pytest.mark.parametrize("M,N,K,ta,tb", [(1024, 784, 8192, 1, 0), (256, 128, 4096, 0, 0), (128, 128, 32768, 0, 1), (384, 640, 2048, 1, 1),
+                                         (28, 64, 65536, 1, 0), (48, 40, 20000, 0, 0), (288, 64, 65536, 1, 0)])  # few outputs, long reduction: conv kernel gradients
 def test_split_k_is_deterministic_and_accurate(gpu, M, N, K, ta, tb, precision):
     rng = np.random.default_rng(K)
     A, B = rng.uniform(-1, 1, (M, K)).astype(np.float32), rng.uniform(-1, 1, (K, N)).astype(np.float32)

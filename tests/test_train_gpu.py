@@ -150,3 +150,44 @@ def test_dqn_training_matches_oracle(gpu, nbatch, evaluator):
             assert rel_err(v.data(), sess.leaf_value(v)) < 1e-4
     finally:
         tc.set_evaluator("plan")
+
+
+def test_prefetch_commit_matches_assign(gpu):
+    """EVariable.prefetch / commit (copy-stream H2D one step ahead) trains exactly like assign."""
+    rng = np.random.default_rng(5)
+    batches = [configs.mlp_batch(rng, configs.mlp(64, 48, 16, 33).feeds) for _ in range(5)]
+
+    def losses(pipelined):
+        cfg = configs.mlp(64, 48, 16, 33)
+        out = []
+        if pipelined:
+            for f, arr in zip(cfg.feeds.values(), batches[0]):
+                f.prefetch(arr)
+        for i in range(len(batches)):
+            if pipelined:
+                for f in cfg.feeds.values():
+                    f.commit()
+                if i + 1 < len(batches):
+                    for f, arr in zip(cfg.feeds.values(), batches[i + 1]):
+                        f.prefetch(arr)
+            else:
+                for f, arr in zip(cfg.feeds.values(), batches[i]):
+                    f.assign(arr)
+            out.append(float(cfg.train.get()))
+        tc.sync_prefetch()
+        return out, [v.data().copy() for v in cfg.variables]
+
+    want, wvars = losses(False)
+    got, gvars = losses(True)
+    assert got == want
+    for g, w in zip(gvars, wvars):
+        np.testing.assert_array_equal(g, w)
+    x = cfgx = configs.mlp(10, 9, 5, 3).feeds["x"]
+    arr = rng.random(x.shape(), dtype=np.float32)
+    x.prefetch(arr)
+    x.commit()
+    np.testing.assert_array_equal(x.data(), arr)
+    with pytest.raises(Exception):
+        x.commit()  # nothing staged
+    with pytest.raises(Exception):
+        x.prefetch(arr.astype(np.float64))  # asynchronous copies do not convert
