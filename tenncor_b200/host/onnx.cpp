@@ -794,7 +794,7 @@ TensptrsT load_model(TensIds& identified, const ModelProto& pb_model) { return l
 
 bool save_to_file(const std::string& filename, const TensptrsT& models, const std::vector<std::pair<std::string, TensptrT>>& keys) {  // eteq_ext.cpp:461-487
   if (models.empty()) {
-    global::warnf("attempting to save to file `%s` without specifying models", filename.c_str());
+    std::fprintf(stderr, "[warn] attempting to save to file `%s` without specifying models\n", filename.c_str());
     return false;
   }
   std::ofstream output(filename, std::ios::binary);

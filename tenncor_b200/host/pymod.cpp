@@ -9,6 +9,7 @@
 
 #include "api.hpp"
 #include "dp.hpp"
+#include "onnx.hpp"
 #include "planner.hpp"
 
 namespace py = pybind11;
@@ -312,6 +313,15 @@ PYBIND11_MODULE(_tenncor, m) {
     layr::ApproxF approx = [update](const ETensor& e, const eteq::VarptrsT& vars) { return update(e, ETensorsT(vars.begin(), vars.end())); };
     return trainer::apply_update(models, approx, err);
   }, py::arg("models"), py::arg("update"), py::arg("err_func"));
+
+  // ---- serialization (tenncor/python/eteq_ext.cpp:408-487)
+  m.def("load_from_file", [](const std::string& filename, const std::unordered_map<std::string, size_t>& key_prec) {
+    return onnx::load_from_file(filename, key_prec);
+  }, py::arg("filename"), py::arg("key_prec") = std::unordered_map<std::string, size_t>{});
+  m.def("save_to_file", [](const std::string& filename, const ETensorsT& models, const std::map<std::string, ETensor>& keys) {
+    std::vector<std::pair<std::string, ETensor>> k(keys.begin(), keys.end());
+    return onnx::save_to_file(filename, models, k);
+  }, py::arg("filename"), py::arg("models"), py::arg("keys") = std::map<std::string, ETensor>{});
 
   // ---- back-end controls
   m.def("sync", [] { cuda::sync(); }, "Wait for all queued device work");
