@@ -9,6 +9,7 @@
 
 #include "api.hpp"
 #include "dp.hpp"
+#include "hone.hpp"
 #include "onnx.hpp"
 #include "planner.hpp"
 
@@ -322,6 +323,21 @@ PYBIND11_MODULE(_tenncor, m) {
     std::vector<std::pair<std::string, ETensor>> k(keys.begin(), keys.end());
     return onnx::save_to_file(filename, models, k);
   }, py::arg("filename"), py::arg("models"), py::arg("keys") = std::map<std::string, ETensor>{});
+
+  // ---- hone: pre-evaluation rewrites (tenncor/hone/src/optimize.cpp)
+  m.def("optimize", [](ETensorsT roots, bool fold_constants) {
+    hone::Stats st;
+    ETensorsT out = hone::optimize(std::move(roots), &st, fold_constants);
+    py::dict d;
+    d["functors_before"] = st.functors_before; d["functors_after"] = st.functors_after; d["merged"] = st.merged; d["folded"] = st.folded; d["rounds"] = st.rounds;
+    return py::make_tuple(out, d);
+  }, py::arg("roots"), py::arg("fold_constants") = true,
+  "Merge structurally equal sub-graphs and fold constant functors (evaluated on the device); returns (new roots, stats)");
+  m.def("merge_dups", [](ETensorsT roots) {
+    size_t n = 0;
+    ETensorsT out = hone::merge_dups(std::move(roots), &n);
+    return py::make_tuple(out, n);
+  }, py::arg("roots"));
 
   // ---- back-end controls
   m.def("sync", [] { cuda::sync(); }, "Wait for all queued device work");

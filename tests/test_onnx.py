@@ -212,3 +212,16 @@ def test_errors():
     with pytest.raises(Exception, match="not found"):
         tc.load_from_file("/nonexistent/model.onnx")
     assert tc.save_to_file("/tmp/_tcr_never_written.onnx", []) is False
+
+
+def test_pretrained_gd_model_solves_the_gd_demo_task():
+    """models/gd.onnx is the trained gd_demo MLP (demo/gd_demo.py:76,99-118 'pretrained mlp error rate'): connected
+    to fresh inputs it must reproduce y = pairwise mean of x far better than an untrained model of the same shape."""
+    rng = np.random.default_rng(0)
+    x = rng.random((200, 10)).astype(np.float32)
+    y = (x[:, 0::2] + x[:, 1::2]) / 2
+    testin = tc.variable(x, "testin")
+    pretrained = tc.load_from_file(os.path.join(GOLDEN, "gd.onnx"))[0].connect(testin)
+    untrained = configs.mlp(10, 9, 5, 3).model.connect(testin)
+    err = [float(np.mean(np.abs(o.reshape(200, 5) - y))) for o in _oracle_eval([pretrained, untrained])]
+    assert err[0] < 0.05 and err[1] > 3 * err[0], err

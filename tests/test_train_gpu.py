@@ -191,3 +191,38 @@ def test_prefetch_commit_matches_assign(gpu):
         x.commit()  # nothing staged
     with pytest.raises(Exception):
         x.prefetch(arr.astype(np.float64))  # asynchronous copies do not convert
+
+
+@pytest.mark.parametrize("evaluator", ["node", "plan"])
+def test_pretrained_onnx_model_runs_and_keeps_training(gpu, evaluator):
+    """BASELINE config 1 names models/gd.onnx: the file the reference's serializer wrote loads, evaluates on the device
+    like the oracle, solves the gd_demo task, and trains on from its weights (demo/gd_demo.py:72-96)."""
+    import os
+    tc.set_evaluator(evaluator)
+    try:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "onnx", "gd.onnx")
+        model = tc.load_from_file(path)[0]
+        rng = np.random.default_rng(0)
+        x = rng.random((200, 10)).astype(np.float32)
+        y = (x[:, 0::2] + x[:, 1::2]) / 2
+        testin = tc.variable(x, "testin")
+        out = model.connect(testin)
+        got = out.get()
+        want = OracleSession([out]).run()[0]
+        assert rel_err(got, want) < 1e-5
+        assert float(np.mean(np.abs(got.reshape(200, 5) - y))) < 0.05
+        train_input = tc.EVariable([3, 10], 0, "train_input")
+        train_exout = tc.EVariable([3, 5], 0, "train_exout")
+        train = tc.apply_update([model], lambda err, leaves: tc.api.approx.sgd(err, leaves, learning_rate=0.9),
+                                lambda models: tc.api.loss.mean_squared(train_exout, models[0].connect(train_input)))
+        sess = OracleSession([train])
+        for step in range(4):
+            bx = rng.random((3, 10)).astype(np.float32)
+            by = ((bx[:, 0::2] + bx[:, 1::2]) / 2).astype(np.float32)
+            train_input.assign(bx)
+            train_exout.assign(by)
+            sess.assign(train_input, bx)
+            sess.assign(train_exout, by)
+            assert rel_err(train.get(), sess.run()[0]) < 1e-4
+    finally:
+        tc.set_evaluator("plan")
