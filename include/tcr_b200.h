@@ -331,6 +331,11 @@ int tcr_conv(const void* image, const void* kernel, void* out, const int64_t img
  * instead of operator.hpp:1143-1187's scalar slide over a mostly-zero rank. 4-byte elements. */
 int tcr_im2col(const void* image, void* cols, const int64_t img_shape[8], const int64_t win_shape[8],
                int64_t row_pitch, int elem_size);
+/* Adjoint of tcr_im2col (the conv2d image gradient: cols = upstream . kernel^T on the tensor cores, then this):
+ * image[u] = sum over window coordinates w with a valid position u - w of cols[position(u - w)][w]. Every image
+ * element is written (zero where no window reaches). Terms are added in a fixed order: deterministic. FLOAT only. */
+int tcr_col2im(const void* cols, void* image, const int64_t img_shape[8], const int64_t win_shape[8],
+               int64_t row_pitch, int dtype);
 
 /* --------------------------------------------------------------- collectives */
 

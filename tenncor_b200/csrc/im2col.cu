@@ -117,6 +117,51 @@ __global__ void __launch_bounds__(256) im2col_tiled_kernel(const uint32_t* __res
   }
 }
 
+// col2im: the adjoint of the patch gather. image[u] = sum over window coordinates w with a valid position u - w of
+// cols[position(u - w)][w]. One thread per image element; the terms are added in a fixed order (deterministic, no
+// atomics). Ranks whose window covers the whole rank have one position (w = u), ranks with a unit window have w = 0:
+// only the sliding ranks (kernel width / height) are looped over.
+struct Col2imDesc {
+  int nd;                       // non-singular image ranks, ascending
+  int n_slide;
+  int64_t n_img, pitch, n_combo;
+  int32_t ext[8], pos[8], win[8];
+  int64_t row_stride[8], col_stride[8];
+  int32_t slide[8];             // indices (into the nd ranks) of the sliding ranks
+};
+
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ cols, float* __restrict__ img, Col2imDesc d) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < d.n_img; t += (int64_t)gridDim.x * blockDim.x) {
+    int32_t u[8];
+    int64_t rem = t, row0 = 0, col0 = 0;
+#pragma unroll 1
+    for (int q = 0; q < d.nd; ++q) {
+      u[q] = (int32_t)(rem % d.ext[q]);
+      rem /= d.ext[q];
+      if (d.pos[q] == 1) col0 += (int64_t)u[q] * d.col_stride[q];        // the window spans the rank: w = u
+      else if (d.win[q] == 1) row0 += (int64_t)u[q] * d.row_stride[q];   // unit window: w = 0
+    }
+    float acc = 0.f;
+#pragma unroll 1
+    for (int64_t combo = 0; combo < d.n_combo; ++combo) {
+      int64_t c = combo, row = row0, col = col0;
+      bool ok = true;
+#pragma unroll 1
+      for (int k = 0; k < d.n_slide; ++k) {
+        const int q = d.slide[k];
+        const int32_t w = (int32_t)(c % d.win[q]);
+        c /= d.win[q];
+        const int32_t p = u[q] - w;
+        ok = ok && p >= 0 && p < d.pos[q];
+        row += (int64_t)p * d.row_stride[q];
+        col += (int64_t)w * d.col_stride[q];
+      }
+      if (ok) acc += __ldg(cols + row * d.pitch + col);
+    }
+    img[t] = acc;
+  }
+}
+
 }  // namespace tcr
 
 using namespace tcr;
@@ -175,6 +220,38 @@ int tcr_im2col(const void* image, void* cols, const int64_t img_shape[8], const 
     int grid = wave_grid(d.rows * d.pitch4, 256, 8);
     TCR_LAUNCH(im2col_kernel, grid, 256, 0, (const uint32_t*)image, (uint4*)cols, d);
   }
+  TCR_CHECK_LAUNCH();
+  return TCR_OK;
+}
+
+int tcr_col2im(const void* cols, void* image, const int64_t img_shape[8], const int64_t win_shape[8], int64_t row_pitch, int dtype) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(cols && image && img_shape && win_shape, "tcr_col2im: null argument");
+  TCR_ARG(dtype == TCR_FLOAT, "tcr_col2im: FLOAT only (got dtype %d)", dtype);
+  Col2imDesc d;
+  memset(&d, 0, sizeof(d));
+  d.n_img = 1;
+  d.n_combo = 1;
+  d.pitch = row_pitch;
+  int64_t rows = 1, k = 1;
+  for (int r = 0; r < 8; ++r) {
+    TCR_ARG(img_shape[r] >= 1 && win_shape[r] >= 1 && win_shape[r] <= img_shape[r], "tcr_col2im: window %lld does not fit image extent %lld at rank %d",
+            (long long)win_shape[r], (long long)img_shape[r], r);
+    TCR_ARG(img_shape[r] < (1ll << 31), "tcr_col2im: extent too large");
+    const int64_t pos = img_shape[r] - win_shape[r] + 1;
+    if (img_shape[r] > 1) {
+      const int q = d.nd++;
+      d.ext[q] = (int32_t)img_shape[r]; d.pos[q] = (int32_t)pos; d.win[q] = (int32_t)win_shape[r];
+      d.row_stride[q] = rows; d.col_stride[q] = k;
+      if (pos > 1 && win_shape[r] > 1) { d.slide[d.n_slide++] = q; d.n_combo *= win_shape[r]; }
+    }
+    rows *= pos;
+    k *= win_shape[r];
+    d.n_img *= img_shape[r];
+  }
+  TCR_ARG(row_pitch >= k, "tcr_col2im: row pitch %lld is smaller than the window (%lld elements)", (long long)row_pitch, (long long)k);
+  int grid = wave_grid(d.n_img, 256, 8);
+  TCR_LAUNCH(col2im_kernel, grid, 256, 0, (const float*)cols, (float*)image, d);
   TCR_CHECK_LAUNCH();
   return TCR_OK;
 }

@@ -90,7 +90,8 @@ struct Step {
   bool gemm_fused = false;
   tcr_gemm_desc gemm;
   // conv2d composite as patch gather + GEMM (fuse_convs): in = {image, kernel | upstream gradient, [bias]}
-  bool conv_fused = false, conv_grad = false;
+  bool conv_fused = false, conv_grad = false, conv_dimg = false;
+  size_t conv_out_offset = 0;
   int64_t conv_img[8], conv_win[8], conv_pitch = 0, conv_rows = 0;
   void* conv_cols = nullptr;
   // data-parallel gradient bucket: member = a gradient placed in the bucket (copy, or nothing when
@@ -105,6 +106,9 @@ struct Step {
 // (tenncor/eteq/backprop.hpp CONV rule, arg 1): see Plan::fuse_convs.
 struct ConvFuse {
   bool grad = false;
+  bool dimg = false;         // image gradient: GEMM into the patch matrix, then col2im into one slice of the CONV's output
+  size_t out_offset = 0;     // dimg: byte offset of that slice (the only part of the output any reader touches)
+  int64_t out_n = 0;         // dimg: elements of the slice
   int img = -1, other = -1;  // arg nodes read directly: the un-padded image; the kernel (forward) / upstream gradient (grad)
   int first = 0;             // earliest node position whose read moves to the fused step
   int64_t img_shape[8], win[8], rows = 1, k = 1, pitch = 0;
@@ -505,9 +509,15 @@ struct Plan {
   void fuse_convs() {
     if (std::getenv("TCR_NO_CONV_GEMM")) return;
     std::unordered_map<int, size_t> skipped;  // helper node (PAD / REVERSE / PERMUTE) -> consumers that now read through it
+    std::vector<std::pair<int, int>> chains;  // (helper, its helper argument): once the first is inlined the second lost a consumer
     for (size_t i = 0; i < nodes.size(); ++i) {
       PNode& n = nodes[i];
-      if (!n.func || n.is_view || n.dtype != FLOAT || n.args.size() != 1) continue;
+      if (!n.func || n.is_view || n.dtype != FLOAT) continue;
+      if (n.op == CONV && n.args.size() == 2) {
+        fuse_conv_image_gradient((int)i, skipped, chains);
+        continue;
+      }
+      if (n.args.size() != 1) continue;
       if (n.op == PERMUTE) {
         // ---- forward
         const int ci = solid(n.args[0]);
@@ -629,10 +639,131 @@ struct Plan {
         if (through >= 0) ++skipped[through];
       }
     }
-    for (auto& kv : skipped) {
-      PNode& x = nodes[kv.first];
-      if (!x.exposed && !x.inlined && kv.second == x.consumers.size()) x.inlined = true;
+    std::vector<char> chain_done(chains.size(), 0);
+    for (bool changed = true; changed;) {
+      changed = false;
+      for (auto& kv : skipped) {
+        PNode& x = nodes[kv.first];
+        if (!x.exposed && !x.inlined && kv.second == x.consumers.size()) { x.inlined = true; changed = true; }
+      }
+      for (size_t c = 0; c < chains.size(); ++c)
+        if (!chain_done[c] && nodes[chains[c].first].inlined) { ++skipped[chains[c].second]; chain_done[c] = 1; changed = true; }
     }
+  }
+
+  // Image gradient of the conv2d composite (backprop.hpp CONV rule, arg 0): CONV(PAD(sup', kernel extents - 1 on every
+  // slid rank), REVERSE(REVERSE(kernel, {0}), all ranks), same order), of which the PAD rule's SLICE keeps only position
+  // p of rank d. That slice is dimg[c,x,y,b] = sum_{o,i,j} sup[o, x-i, y-j, b] * kernel[o,c,i,j]: one GEMM
+  // cols[(x',y',b), (c,i,j)] = sup[(x',y',b), o] . kernel[o, (c,i,j)] and the adjoint of the patch gather (tcr_col2im).
+  // The other 2p positions of rank d — (2*out - 1)/1 of the reference's work — are never read and never computed.
+  void fuse_conv_image_gradient(int i, std::unordered_map<int, size_t>& skipped, std::vector<std::pair<int, int>>& chains) {
+    PNode& n = nodes[i];
+    if (n.inlined || n.conv >= 0) return;
+    const RanksT order = full_order(*n.func);
+    if (order.empty()) return;
+    const int d = order[0];
+    // kernel operand: REVERSE over every non-singular rank of REVERSE(kernel, {0})
+    const int ra = solid(n.args[1]);
+    if (ra < 0) return;
+    const PNode& rev_all = nodes[ra];
+    if (!rev_all.func || rev_all.op != REVERSE || rev_all.dtype != FLOAT || rev_all.args.size() != 1) return;
+    const Shape ks = rev_all.shape;
+    auto rs = eigen::unpack_rankset(*rev_all.func);
+    for (int q = 0; q < rank_cap; ++q)
+      if (ks.at(q) > 1 && !rs.count((RankT)q)) return;
+    const int kr = solid(rev_all.args[0]);
+    if (kr < 0) return;
+    const PNode& rev0 = nodes[kr];
+    if (!rev0.func || rev0.op != REVERSE || rev0.dtype != FLOAT || rev0.args.size() != 1) return;
+    auto rs0 = eigen::unpack_rankset(*rev0.func);
+    if (rs0.size() != 1 || *rs0.begin() != 0) return;
+    const int64_t nout = ks.at(0), p = nout - 1;
+    if (p < 1) return;
+    // image operand: PAD of the upstream gradient by (extent - 1) on every rank a non-singular kernel rank slides along
+    const int pd = solid(n.args[0]);
+    if (pd < 0) return;
+    const PNode& pad = nodes[pd];
+    if (!pad.func || pad.op != PAD || pad.dtype != FLOAT || pad.args.size() != 1) return;
+    int64_t want_pad[rank_cap] = {0};
+    ConvFuse cf;
+    cf.dimg = true;
+    for (int r = 0; r < rank_cap; ++r) cf.win[r] = 1;
+    int prev = -1;
+    for (int q = 0; q < rank_cap; ++q) {
+      if (ks.at(q) == 1) continue;
+      const int r = order[q];
+      want_pad[r] = (int64_t)ks.at(q) - 1;
+      if (q == 0) continue;
+      if (r <= prev || r >= d) return;  // window coordinates must enumerate in the kernel's memory order
+      prev = r;
+      cf.win[r] = ks.at(q);
+    }
+    auto pads = eigen::unpack_dimpairs(*pad.func);
+    for (int r = 0; r < rank_cap; ++r) {
+      const int64_t lo = r < (int)pads.size() ? pads[r].first : 0, hi = r < (int)pads.size() ? pads[r].second : 0;
+      if (lo != want_pad[r] || hi != want_pad[r]) return;
+    }
+    const PNode& sup = nodes[pad.args[0]];
+    if (sup.dtype != FLOAT) return;
+    const Shape ss = sup.shape;
+    if ((int64_t)ss.at(d) != nout || (int64_t)n.shape.at(d) != 2 * p + 1) return;
+    int64_t slice_n = 1;
+    for (int r = 0; r < rank_cap; ++r) {
+      if (r > d && (ss.at(r) != 1 || n.shape.at(r) != 1)) return;
+      if (r >= d) { cf.img_shape[r] = 1; continue; }
+      cf.img_shape[r] = (int64_t)ss.at(r) + cf.win[r] - 1;
+      if ((int64_t)n.shape.at(r) != cf.img_shape[r]) return;
+      cf.rows *= ss.at(r);
+      cf.k *= cf.win[r];
+      slice_n *= cf.img_shape[r];
+    }
+    cf.out_n = slice_n;
+    cf.out_offset = (size_t)p * (size_t)slice_n * sizeof(float);
+    // every reader — and every target, when the node is exposed through a view — must name exactly that slice
+    if (n.exposed)
+      for (iTensor* t : target_keys) {
+        const PNode& tn = nodes[index.at(t)];
+        if (tn.root == i && (tn.offset != cf.out_offset || tn.n != slice_n)) return;
+      }
+    for (size_t m = 0; m < nodes.size(); ++m) {
+      const PNode& reader = nodes[m];
+      if (!reader.func || reader.is_view) continue;
+      for (int a : reader.args)
+        if (nodes[a].root == i && (nodes[a].offset != cf.out_offset || nodes[a].n != slice_n)) return;
+    }
+    cf.pitch = (cf.k + 3) / 4 * 4;
+    cf.img = rev0.args[0];  // the kernel itself
+    cf.other = pad.args[0];
+    cf.first = std::min({pd, ra, kr, i});
+    tcr_gemm_desc& g = cf.gemm;
+    std::memset(&g, 0, sizeof(g));
+    g.m = cf.rows; g.n = cf.k; g.k = nout; g.batch = 1;
+    g.a_sm = 1; g.a_sk = cf.rows;     // sup' [positions..., out]: out slowest
+    g.b_sk = 1; g.b_sn = nout;        // kernel [out, (c,i,j)]: out fastest
+    g.c_sm = cf.pitch; g.c_sn = 1;
+    g.dtype = FLOAT;
+    int through = -1;
+    const int si = solid(pad.args[0]);
+    if (si >= 0 && nodes[si].func && nodes[si].op == PERMUTE && nodes[si].args.size() == 1 && nodes[nodes[si].args[0]].dtype == FLOAT) {
+      const RanksT sperm = full_order(*nodes[si].func);
+      if (!sperm.empty()) {
+        RanksT inv(rank_cap);
+        for (int q = 0; q < rank_cap; ++q) inv[sperm[q]] = (RankT)q;
+        if (d_first(ss, inv, d)) through = si;
+      }
+    }
+    if (through >= 0) {
+      cf.other = nodes[through].args[0];
+      cf.first = std::min(cf.first, through);
+      g.a_sm = nout; g.a_sk = 1;
+    }
+    if (assigned_between({cf.img, cf.other}, cf.first, i)) return;
+    n.conv = (int)convs.size();
+    convs.push_back(cf);
+    ++skipped[pd];
+    ++skipped[ra];
+    chains.push_back({ra, kr});
+    if (through >= 0) chains.push_back({pd, through});
   }
 
   void conv_step(Step& st, const ConvFuse& cf, int out_node, int bias_node, int epi, int act) {
@@ -646,7 +777,9 @@ struct Plan {
     for (int r = 0; r < rank_cap; ++r) { st.conv_img[r] = cf.img_shape[r]; st.conv_win[r] = cf.win[r]; }
     st.conv_pitch = cf.pitch;
     st.conv_rows = cf.rows;
-    for (int a : {cf.img, cf.other, bias_node}) {
+    st.conv_dimg = cf.dimg;
+    st.conv_out_offset = cf.out_offset;
+    for (int a : {cf.dimg ? cf.other : cf.img, cf.dimg ? cf.img : cf.other, bias_node}) {
       if (a < 0) continue;
       st.in_nodes.push_back(nodes[a].root);
       st.in_offsets.push_back(nodes[a].offset);
@@ -698,7 +831,7 @@ struct Plan {
         const int gi = nodes[n.args[k]].root, oi = nodes[n.args[1 - k]].root;
         PNode& g = nodes[gi];
         PNode& o = nodes[oi];
-        const bool from_conv = g.conv >= 0 && !convs[g.conv].grad;  // conv2d composite: same epilogue on its GEMM
+        const bool from_conv = g.conv >= 0 && !convs[g.conv].grad && !convs[g.conv].dimg;  // conv2d composite: same epilogue on its GEMM
         if (!g.func || (!from_conv && g.op != CONTRACT && g.op != MATMUL) || g.exposed || g.inlined || g.consumers.size() != 1) continue;
         if (nodes[n.args[k]].offset != 0 || nodes[n.args[1 - k]].offset != 0 || !(g.shape == n.shape)) continue;
         auto gop = dynamic_cast<DevOp*>(g.holder);
@@ -1088,6 +1221,16 @@ struct Plan {
         out.ptr = (char*)bucket + st.bucket_offset;  // lives for the whole plan, never pooled
       } else if (out.bucket_slot >= 0) {
         out.ptr = (char*)bucket + out.bucket_slot;
+      } else if (st.conv_dimg && out.exposed) {
+        // a target reads the slice through the CONV holder's own (full-size) buffer: only the slice is written
+        auto op = dynamic_cast<DevOp*>(out.holder);
+        if (!op) global::fatalf("planner: target %s cannot hold data", out.tens->to_string().c_str());
+        out.ptr = op->ensure_buffer(1, memory);
+        bound.push_back({st.out_node, out.ptr});
+      } else if (st.conv_dimg) {
+        // only one slice of this node's output is ever read (checked in fuse_conv_image_gradient): allocate that slice and
+        // hand out the base it would have inside the full tensor. Plan-owned, never recycled.
+        out.ptr = (char*)alloc_owned((size_t)convs[out.conv].out_n * sizeof(float)) - st.conv_out_offset;
       } else if (is_assign(out.op)) {
         out.ptr = nodes[nodes[out.args[0]].root].ptr;  // variable storage
         out.root = nodes[out.args[0]].root;
@@ -1160,7 +1303,12 @@ struct Plan {
     } else if (st.kind == Step::BUCKET_MEMBER) {
       if (!st.member_in_place) check(tcr_d2d(st.out, st.in[0], (size_t)nodes[st.out_node].n * type_size(nodes[st.out_node].dtype)), "tcr_d2d");
     } else if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
-    else if (st.conv_fused) {
+    else if (st.conv_dimg) {
+      tcr_gemm_desc d = st.gemm;
+      d.precision = gemm_precision();
+      check(tcr_gemm(st.in[0], st.in[1], st.conv_cols, &d), "tcr_gemm");
+      check(tcr_col2im(st.conv_cols, (char*)st.out + st.conv_out_offset, st.conv_img, st.conv_win, st.conv_pitch, FLOAT), "tcr_col2im");
+    } else if (st.conv_fused) {
       check(tcr_im2col(st.in[0], st.conv_cols, st.conv_img, st.conv_win, st.conv_pitch, (int)sizeof(float)), "tcr_im2col");
       tcr_gemm_desc d = st.gemm;
       d.precision = gemm_precision();
@@ -1349,7 +1497,7 @@ struct Plan {
     if (st.ew) return what + " fused(" + std::to_string(st.prog.n_instrs) + " instr, " + std::to_string(st.prog.n_inputs) + " in)";
     const std::string mnk = " m" + std::to_string(st.gemm.m) + " n" + std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
     if (st.conv_fused)
-      return std::string(st.conv_grad ? "CONV2D-dK" : "CONV2D") + " im2col+GEMM" + (st.gemm.epilogue ? "+bias" : "") + (st.gemm.activation ? "+act" : "") + mnk;
+      return st.conv_dimg ? "CONV2D-dX GEMM+col2im" + mnk : std::string(st.conv_grad ? "CONV2D-dK" : "CONV2D") + " im2col+GEMM" + (st.gemm.epilogue ? "+bias" : "") + (st.gemm.activation ? "+act" : "") + mnk;
     if (st.gemm_fused && st.in_nodes.size() == 2) return "GEMM^T" + mnk;
     if (st.gemm_fused) return "GEMM+bias" + std::string(st.gemm.activation ? "+act" : "") + mnk;
     return what;
@@ -1376,7 +1524,8 @@ struct Plan {
         }
       } else {
         for (int in : st.in_nodes) t.bytes += (size_t)nodes[in].n * type_size(nodes[in].dtype);
-        if (st.conv_fused) t.what = std::string(st.conv_grad ? "CONV2D-dK" : "CONV2D") + " im2col+GEMM" + (st.gemm.epilogue ? "+bias" : "") + (st.gemm.activation ? "+act" : "") +
+        if (st.conv_dimg) t.what = "CONV2D-dX GEMM+col2im m" + std::to_string(st.gemm.m) + " n" + std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
+        else if (st.conv_fused) t.what = std::string(st.conv_grad ? "CONV2D-dK" : "CONV2D") + " im2col+GEMM" + (st.gemm.epilogue ? "+bias" : "") + (st.gemm.activation ? "+act" : "") +
                                     " m" + std::to_string(st.gemm.m) + " n" + std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
         else if (st.gemm_fused && st.in.size() == 2) t.what = "GEMM^T m" + std::to_string(st.gemm.m) + " n" + std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
         else if (st.gemm_fused) t.what = "GEMM+bias" + std::string(st.gemm.activation ? "+act" : "") + " m" + std::to_string(st.gemm.m) + " n" +

@@ -12,7 +12,7 @@ import pytest
 import tenncor_b200 as tc
 from oracle import tcr_oracle as orc
 from tenncor_b200 import configs
-from tests.test_conv_plan import _im2col
+from tests.test_conv_plan import _col2im, _im2col
 from tests.test_train_gpu import OracleSession, rel_err
 
 pytestmark = pytest.mark.gpu
@@ -43,6 +43,28 @@ def test_im2col_bit_exact(gpu, img_shape, win):
     assert not got[:, k:].any()  # the tail of each row is zero-filled
 
 
+@pytest.mark.parametrize("img_shape,win", [([3, 10, 9, 4], [3, 3, 2, 1]), ([16, 18, 18, 8], [16, 3, 3, 1]), ([1, 7, 5, 1], [1, 2, 2, 1]),
+                                           ([5, 6, 7, 2], [2, 1, 3, 2]), ([4, 4, 4, 4], [4, 4, 4, 4]), ([8, 9, 1, 3], [8, 1, 1, 1])])
+def test_col2im_is_the_adjoint_of_im2col(gpu, img_shape, win):
+    rng = np.random.default_rng(14)
+    s8 = list(img_shape) + [1] * (8 - len(img_shape))
+    w8 = list(win) + [1] * (8 - len(win))
+    rows = int(np.prod([a - b + 1 for a, b in zip(s8, w8)]))
+    k = int(np.prod(w8))
+    pitch = (k + 3) // 4 * 4
+    cols = rng.integers(-4, 5, (rows, pitch)).astype(np.float32)  # small integers: every sum is exact in fp32
+    want = _col2im(cols.astype(np.float64), s8, w8)
+    dcols = gpu.to_device(cols)
+    n_img = int(np.prod(s8))
+    dimg = gpu.empty(n_img, np.float32)
+    gpu.check(gpu.lib().tcr_memset(C.c_void_p(dimg.ptr), 0xFF, C.c_size_t(n_img * 4)))
+    gpu.check(gpu.lib().tcr_col2im(C.c_void_p(dcols.ptr), C.c_void_p(dimg.ptr), gpu.shape8(s8), gpu.shape8(w8), C.c_int64(pitch), gpu.FLOAT))
+    np.testing.assert_array_equal(gpu.to_host(dimg, n_img, np.float32), want.astype(np.float32))
+    # <im2col(x), y> == <x, col2im(y)>
+    x = rng.integers(-4, 5, n_img).astype(np.float64)
+    assert np.sum(_im2col(x, s8, w8) * cols[:, :k]) == np.sum(x * want)
+
+
 def test_im2col_rejects_bad_arguments(gpu):
     dimg = gpu.to_device(np.zeros(64, np.float32))
     dcols = gpu.empty(64, np.float32)
@@ -59,6 +81,7 @@ CONV_CASES = [
     (1, 3, 5, 5, 1, 2, 2, False, None, True),
     (5, 2, 7, 4, 3, 1, 3, True, ((1, 1), (2, 0)), True),
     (7, 5, 9, 8, 3, 2, 3, True, None, True),           # k = 42: padded row pitch, n not a multiple of 4
+    (16, 20, 14, 12, 6, 3, 3, True, None, True),       # image-gradient GEMM (720 x 144 x 20) on the tcgen05 kernel
     (16, 32, 18, 18, 8, 3, 3, True, None, False),      # forward and kernel-gradient GEMMs large enough for the tcgen05 kernels
     (8, 32, 34, 20, 4, 3, 3, True, ((1, 1), (1, 1)), False),
 ]
@@ -128,3 +151,4 @@ def test_conv_plan_is_fused_and_graph_replayed(gpu):
     names = [t["what"] for t in tc.profile_plan(1)]
     assert sum(n.startswith("CONV2D im2col+GEMM") for n in names) == 4, names
     assert sum(n.startswith("CONV2D-dK") for n in names) == 2, names
+    assert sum(n.startswith("CONV2D-dX") for n in names) == 1, names

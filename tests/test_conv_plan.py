@@ -61,7 +61,25 @@ def test_cnn_training_plan():
     steps = tc.describe_plan([cfg.train])
     assert sum(s.startswith("CONV2D im2col+GEMM+bias+act") for s in steps) == 4  # two layers, before and after the update
     assert sum(s.startswith("CONV2D-dK") for s in steps) == 2
-    assert sum(s.startswith("CONV ") for s in steps) == 1  # the image gradient of layer 2 stays generic
+    assert sum(s.startswith("CONV2D-dX GEMM+col2im m192 n72 k4") for s in steps) == 1  # image gradient of layer 2
+    # nothing of the composites is left to the generic kernels
+    assert not any(s.split()[0] in ("CONV", "PAD", "PERMUTE", "REVERSE", "SLICE") for s in steps), steps
+
+
+def test_image_gradient_falls_back_when_the_whole_padded_output_is_read():
+    """the fused step computes only the slice the PAD rule keeps; a reader of the full tensor keeps the generic CONV"""
+    rng = np.random.default_rng(0)
+    img, ker, b, out = _conv_graph(rng, 3, 4, 6, 5, 2, 3, 2)
+    loss = tc.api.reduce_sum(tc.api.square(out))
+    gi = tc.derive(loss, [img])[0]
+    steps = tc.describe_plan([gi])
+    assert any(s.startswith("CONV2D-dX") for s in steps), steps
+    # walk down to the CONV under the gradient's SLICE and expose it as a second target
+    node = gi
+    while node.opname() != "CONV":
+        node = node.args()[0]
+    steps = tc.describe_plan([gi, node])
+    assert not any(s.startswith("CONV2D-dX") for s in steps) and any(s.startswith("CONV ") for s in steps), steps
 
 
 def _im2col(flat, img_shape, win):
@@ -72,6 +90,35 @@ def _im2col(flat, img_shape, win):
     pos_idx = np.stack(np.unravel_index(np.arange(rows), pos, order="F"), 1)
     win_idx = np.stack(np.unravel_index(np.arange(k), win, order="F"), 1)
     return flat[(pos_idx @ strides)[:, None] + (win_idx @ strides)[None, :]]
+
+
+def _col2im(cols, img_shape, win):
+    """numpy replay of tcr_col2im (tenncor_b200/csrc/im2col.cu): the adjoint of `_im2col`."""
+    pos = [s - w + 1 for s, w in zip(img_shape, win)]
+    strides = np.cumprod([1] + list(img_shape[:-1]))
+    rows, k = int(np.prod(pos)), int(np.prod(win))
+    pos_idx = np.stack(np.unravel_index(np.arange(rows), pos, order="F"), 1)
+    win_idx = np.stack(np.unravel_index(np.arange(k), win, order="F"), 1)
+    img = np.zeros(int(np.prod(img_shape)))
+    np.add.at(img, (pos_idx @ strides)[:, None] + (win_idx @ strides)[None, :], cols[:, :k])
+    return img
+
+
+@pytest.mark.parametrize("inc,outc,W,H,B,kw,kh", [(3, 8, 10, 9, 4, 3, 2), (1, 3, 5, 5, 1, 2, 2), (5, 2, 7, 4, 3, 1, 3), (2, 5, 6, 6, 2, 6, 6)])
+def test_image_gradient_algebra_matches_oracle(inc, outc, W, H, B, kw, kh):
+    rng = np.random.default_rng(2)
+    # small integers in float32: the fused lowering is FLOAT-only and every sum stays exact
+    img_np, ker_np = (rng.integers(-3, 4, s).astype(np.float32) for s in ((B, H, W, inc), (kh, kw, inc, outc)))
+    g_np = rng.integers(-3, 4, (B, H - kh + 1, W - kw + 1, outc)).astype(np.float32)
+    img, ker, g = (tc.variable(a, n) for a, n in ((img_np, "img"), (ker_np, "ker"), (g_np, "g")))
+    gi = tc.derive(tc.api.reduce_sum(tc.api.nn.conv2d(img, ker) * g), [img])[0]
+    assert any(s.startswith("CONV2D-dX") for s in tc.describe_plan([gi]))
+    tape = tc.dump_graph([gi])
+    want = np.asarray(orc.eval_tape(tape)[tc.dump_ids([gi], tape)[gi]]).reshape(-1)
+    k = inc * kw * kh
+    cols = g_np.reshape(-1, outc).astype(np.float64) @ ker_np.reshape(k, outc).T  # a = sup [rows, out]; b(kk = o, n = (c,i,j)) = kernel[o + out * n]
+    got = _col2im(cols, [inc, W, H, B, 1, 1, 1, 1], [inc, kw, kh, 1, 1, 1, 1, 1])
+    np.testing.assert_array_equal(got, want)
 
 
 @pytest.mark.parametrize("inc,outc,W,H,B,kw,kh", [(3, 8, 10, 9, 4, 3, 2), (1, 3, 5, 5, 1, 2, 2), (5, 2, 7, 4, 3, 1, 3), (2, 5, 6, 6, 2, 6, 6)])

@@ -191,6 +191,11 @@ def main():
                 rec("conv_fwd_total_%s_%s" % (nm, tag), timeit(lambda: (gather(), fwd())), flops=2.0 * rows * outc * k)
                 g = cabi.GemmDesc(m=k, n=outc, k=rows, batch=1, a_sm=1, a_sk=pitch, b_sk=outc, b_sn=1, c_sm=outc, c_sn=1, dtype=F, precision=prec)
                 rec("conv_dK_gemm_%s_%s" % (nm, tag), timeit(lambda: cabi.check(lib.tcr_gemm(P(cols), P(sup), P(dk), C.byref(g)))), flops=2.0 * rows * outc * k)
+                x = cabi.GemmDesc(m=rows, n=k, k=outc, batch=1, a_sm=outc, a_sk=1, b_sk=1, b_sn=outc, c_sm=pitch, c_sn=1, dtype=F, precision=prec)
+                dx_gemm = lambda: cabi.check(lib.tcr_gemm(P(sup), P(ker), P(cols), C.byref(x)))  # noqa: E731
+                rec("conv_dX_gemm_%s_%s" % (nm, tag), timeit(dx_gemm), flops=2.0 * rows * outc * k)
+            scatter = lambda: cabi.check(lib.tcr_col2im(P(cols), P(img), s8, w8, C.c_int64(pitch), F))  # noqa: E731
+            rec("conv_col2im_%s" % tag, timeit(scatter), 4 * (rows * pitch + inc * W * Hh * B))
         inc, outc, W, Hh, B, kw, kh = 8, 16, 18, 18, 8, 3, 3
         padded = cabi.to_device(np.zeros(inc * W * Hh * B * (2 * outc - 1), np.float32))
         kr = cabi.to_device(rng.uniform(-1, 1, outc * inc * kw * kh).astype(np.float32))
