@@ -120,43 +120,79 @@ __global__ void __launch_bounds__(256) im2col_tiled_kernel(const uint32_t* __res
 // col2im: the adjoint of the patch gather. image[u] = sum over window coordinates w with a valid position u - w of
 // cols[position(u - w)][w]. One thread per image element; the terms are added in a fixed order (deterministic, no
 // atomics). Ranks whose window covers the whole rank have one position (w = u), ranks with a unit window have w = 0:
-// only the sliding ranks (kernel width / height) are looped over.
+// only the sliding ranks (kernel width / height) are looped over. The window offsets of the sliding ranks are the
+// same for every element: a per-block table in shared memory (w per sliding rank + column offset), so the inner loop
+// is a range test, one multiply-add per sliding rank and the load. 32-bit coordinates (image and rows < 2^31).
 struct Col2imDesc {
   int nd;                       // non-singular image ranks, ascending
   int n_slide;
-  int64_t n_img, pitch, n_combo;
+  int64_t n_img, pitch;
+  int32_t n_combo;
   int32_t ext[8], pos[8], win[8];
-  int64_t row_stride[8], col_stride[8];
+  int32_t row_stride[8], col_stride[8];
   int32_t slide[8];             // indices (into the nd ranks) of the sliding ranks
 };
 
+constexpr int C2I_MAX_SLIDE = 4;
+
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ cols, float* __restrict__ img, Col2imDesc d) {
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < d.n_img; t += (int64_t)gridDim.x * blockDim.x) {
-    int32_t u[8];
-    int64_t rem = t, row0 = 0, col0 = 0;
+  extern __shared__ int32_t table[];  // n_combo x (C2I_MAX_SLIDE window coordinates + column offset)
+  constexpr int TW = C2I_MAX_SLIDE + 1;
+  for (int c = threadIdx.x; c < d.n_combo; c += blockDim.x) {
+    int rem = c;
+    int32_t col = 0;
+    for (int k = 0; k < C2I_MAX_SLIDE; ++k) {
+      int32_t w = 0;
+      if (k < d.n_slide) {
+        const int q = d.slide[k];
+        w = rem % d.win[q];
+        rem /= d.win[q];
+        col += w * d.col_stride[q];
+      }
+      table[c * TW + k] = w;
+    }
+    table[c * TW + C2I_MAX_SLIDE] = col;
+  }
+  __syncthreads();
+  int32_t s_pos[C2I_MAX_SLIDE], s_rs[C2I_MAX_SLIDE];
+  int s_q[C2I_MAX_SLIDE];
+#pragma unroll
+  for (int k = 0; k < C2I_MAX_SLIDE; ++k) {
+    s_q[k] = k < d.n_slide ? d.slide[k] : 0;
+    s_pos[k] = k < d.n_slide ? d.pos[s_q[k]] : 1;
+    s_rs[k] = k < d.n_slide ? d.row_stride[s_q[k]] : 0;
+  }
+  const uint32_t n_img = (uint32_t)d.n_img;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_img; t += gridDim.x * blockDim.x) {
+    uint32_t rem = t;
+    int32_t row0 = 0, col0 = 0, us[C2I_MAX_SLIDE] = {0, 0, 0, 0};
 #pragma unroll 1
     for (int q = 0; q < d.nd; ++q) {
-      u[q] = (int32_t)(rem % d.ext[q]);
-      rem /= d.ext[q];
-      if (d.pos[q] == 1) col0 += (int64_t)u[q] * d.col_stride[q];        // the window spans the rank: w = u
-      else if (d.win[q] == 1) row0 += (int64_t)u[q] * d.row_stride[q];   // unit window: w = 0
-    }
-    float acc = 0.f;
-#pragma unroll 1
-    for (int64_t combo = 0; combo < d.n_combo; ++combo) {
-      int64_t c = combo, row = row0, col = col0;
-      bool ok = true;
-#pragma unroll 1
-      for (int k = 0; k < d.n_slide; ++k) {
-        const int q = d.slide[k];
-        const int32_t w = (int32_t)(c % d.win[q]);
-        c /= d.win[q];
-        const int32_t p = u[q] - w;
-        ok = ok && p >= 0 && p < d.pos[q];
-        row += (int64_t)p * d.row_stride[q];
-        col += (int64_t)w * d.col_stride[q];
+      const uint32_t e = (uint32_t)d.ext[q];
+      const int32_t u = (int32_t)(rem % e);
+      rem /= e;
+      if (d.pos[q] == 1) col0 += u * d.col_stride[q];        // the window spans the rank: w = u
+      else if (d.win[q] == 1) row0 += u * d.row_stride[q];   // unit window: w = 0
+      else {
+#pragma unroll
+        for (int k = 0; k < C2I_MAX_SLIDE; ++k)
+          if (k < d.n_slide && s_q[k] == q) us[k] = u;
       }
-      if (ok) acc += __ldg(cols + row * d.pitch + col);
+    }
+    const float* base = cols + col0;
+    float acc = 0.f;
+#pragma unroll 2
+    for (int c = 0; c < d.n_combo; ++c) {
+      const int32_t* e = table + c * TW;
+      int32_t row = row0;
+      bool ok = true;
+#pragma unroll
+      for (int k = 0; k < C2I_MAX_SLIDE; ++k) {
+        const int32_t p = us[k] - e[k];
+        ok = ok && (uint32_t)p < (uint32_t)s_pos[k];
+        row += p * s_rs[k];
+      }
+      if (ok) acc += __ldg(base + (int64_t)row * d.pitch + e[C2I_MAX_SLIDE]);
     }
     img[t] = acc;
   }
@@ -231,27 +267,34 @@ int tcr_col2im(const void* cols, void* image, const int64_t img_shape[8], const 
   Col2imDesc d;
   memset(&d, 0, sizeof(d));
   d.n_img = 1;
-  d.n_combo = 1;
   d.pitch = row_pitch;
-  int64_t rows = 1, k = 1;
+  int64_t rows = 1, k = 1, n_combo = 1;
   for (int r = 0; r < 8; ++r) {
     TCR_ARG(img_shape[r] >= 1 && win_shape[r] >= 1 && win_shape[r] <= img_shape[r], "tcr_col2im: window %lld does not fit image extent %lld at rank %d",
             (long long)win_shape[r], (long long)img_shape[r], r);
-    TCR_ARG(img_shape[r] < (1ll << 31), "tcr_col2im: extent too large");
     const int64_t pos = img_shape[r] - win_shape[r] + 1;
     if (img_shape[r] > 1) {
       const int q = d.nd++;
+      TCR_ARG(rows < (1ll << 31) && k < (1ll << 31), "tcr_col2im: patch matrix too large for 32-bit coordinates");
       d.ext[q] = (int32_t)img_shape[r]; d.pos[q] = (int32_t)pos; d.win[q] = (int32_t)win_shape[r];
-      d.row_stride[q] = rows; d.col_stride[q] = k;
-      if (pos > 1 && win_shape[r] > 1) { d.slide[d.n_slide++] = q; d.n_combo *= win_shape[r]; }
+      d.row_stride[q] = (int32_t)rows; d.col_stride[q] = (int32_t)k;
+      if (pos > 1 && win_shape[r] > 1) {
+        TCR_ARG(d.n_slide < C2I_MAX_SLIDE, "tcr_col2im: more than %d sliding ranks", C2I_MAX_SLIDE);
+        d.slide[d.n_slide++] = q;
+        n_combo *= win_shape[r];
+      }
     }
     rows *= pos;
     k *= win_shape[r];
     d.n_img *= img_shape[r];
   }
   TCR_ARG(row_pitch >= k, "tcr_col2im: row pitch %lld is smaller than the window (%lld elements)", (long long)row_pitch, (long long)k);
+  TCR_ARG(d.n_img < (1ll << 31) && rows < (1ll << 31), "tcr_col2im: image or patch matrix too large for 32-bit coordinates");
+  TCR_ARG(n_combo <= 2048, "tcr_col2im: %lld window positions per element exceed the shared-memory table", (long long)n_combo);
+  d.n_combo = (int32_t)n_combo;
+  const size_t smem = (size_t)n_combo * (C2I_MAX_SLIDE + 1) * sizeof(int32_t);
   int grid = wave_grid(d.n_img, 256, 8);
-  TCR_LAUNCH(col2im_kernel, grid, 256, 0, (const float*)cols, (float*)image, d);
+  TCR_LAUNCH(col2im_kernel, grid, 256, smem, (const float*)cols, (float*)image, d);
   TCR_CHECK_LAUNCH();
   return TCR_OK;
 }

@@ -8,6 +8,7 @@
 #include <pybind11/stl.h>
 
 #include "api.hpp"
+#include "dbg.hpp"
 #include "dp.hpp"
 #include "hone.hpp"
 #include "onnx.hpp"
@@ -201,6 +202,24 @@ PYBIND11_MODULE(_tenncor, m) {
       }, py::arg("ignored") = ETensorsT{}, py::arg("max_version") = std::numeric_limits<size_t>::max(),
       "Evaluate on the device; the result stays in HBM (no host copy)")
       .def("device_ptr", [](iTensor& self) { return (uintptr_t)self.device().device_data(); })
+      .def_property_readonly("__cuda_array_interface__", [](iTensor& self) {
+        // zero-copy view of the resident HBM buffer for torch.as_tensor / cupy.asarray (CUDA Array Interface v3);
+        // `stream` names the library stream so that consumers order themselves after the producing kernels
+        void* ptr = self.device().device_data();
+        if (nullptr == ptr) global::fatalf("%s has no device data: evaluate it first (calc / get)", self.to_string().c_str());
+        DimsT ps = c2pshape(self.shape());
+        py::tuple shape(ps.size());
+        for (size_t i = 0; i < ps.size(); ++i) shape[i] = (size_t)ps[i];
+        py::dict d;
+        d["shape"] = shape;
+        d["typestr"] = dtype2np((egen::_GENERATED_DTYPE)self.get_meta().type_code()).attr("str");
+        d["data"] = py::make_tuple((uintptr_t)ptr, false);
+        d["strides"] = py::none();
+        d["version"] = 3;
+        uintptr_t stream = (uintptr_t)tcr_stream();
+        d["stream"] = stream ? py::cast(stream) : py::cast(1);
+        return d;
+      })
       .def("get_version", [](const iTensor& self) { return self.get_meta().state_version(); })
       .def("opname", [](const iTensor& self) {
         auto f = dynamic_cast<const iFunctor*>(&self);
@@ -237,12 +256,30 @@ PYBIND11_MODULE(_tenncor, m) {
       .def(py::init([](std::vector<size_t> slist, double scalar, const std::string& label, py::object dtype) {
         return eteq::make_variable_scalar(scalar, p2cshape(slist), label, parse_dtype(dtype));
       }), py::arg("shape"), py::arg("scalar") = 0, py::arg("label") = "", py::arg("dtype") = py::none())
-      .def("assign", [](eteq::Variable& self, py::array data) {
+      .def("assign", [](eteq::Variable& self, py::object obj) {
+        if (py::hasattr(obj, "__cuda_array_interface__")) {
+          // a device array (torch / cupy / another tensor of this module): HBM -> HBM, no host round trip. The producer's
+          // stream must already be synchronised with the library stream (tc.sync() / torch.cuda.synchronize()).
+          py::dict cai = obj.attr("__cuda_array_interface__");
+          if (!cai["strides"].is_none()) global::fatal("assign from a device array needs a C-contiguous array");
+          std::vector<size_t> ps = cai["shape"].cast<std::vector<size_t>>();
+          Shape shape = p2cshape(ps);
+          if (false == shape.compatible_after(self.shape(), 0))
+            global::fatalf("assigning data shaped %s to tensor %s", shape.to_string().c_str(), self.shape().to_string().c_str());
+          py::dtype want = dtype2np((egen::_GENERATED_DTYPE)self.get_meta().type_code());
+          if (cai["typestr"].cast<std::string>() != want.attr("str").cast<std::string>())
+            global::fatalf("assign from a device array needs dtype %s (got %s): conversions happen on the host path only",
+                           want.attr("str").cast<std::string>().c_str(), cai["typestr"].cast<std::string>().c_str());
+          self.assign_device((const void*)cai["data"].cast<py::tuple>()[0].cast<uintptr_t>());
+          return;
+        }
+        py::array data = py::array::ensure(obj);
+        if (!data) global::fatal("assign needs a numpy-convertible array or a device array");
         Shape shape;
         egen::_GENERATED_DTYPE dtype;
         py::array arr = normalise(data, shape, dtype);
         self.assign(arr.data(), dtype, shape);
-      }, py::arg("data"), "Assign numpy data array to variable (host -> HBM, asynchronous for pinned arrays)")
+      }, py::arg("data"), "Assign a numpy array (host -> HBM, asynchronous for pinned arrays) or any object exposing __cuda_array_interface__ (HBM -> HBM)")
       .def("prefetch", [](eteq::Variable& self, py::array data) {
         Shape shape;
         egen::_GENERATED_DTYPE dtype;
@@ -323,6 +360,35 @@ PYBIND11_MODULE(_tenncor, m) {
     std::vector<std::pair<std::string, ETensor>> k(keys.begin(), keys.end());
     return onnx::save_to_file(filename, models, k);
   }, py::arg("filename"), py::arg("models"), py::arg("keys") = std::map<std::string, ETensor>{});
+
+  // ---- evaluator plugins (dbg/python/peval.cpp:9-80) + per-opcode profiler
+  py::class_<teq::iEvaluator, std::shared_ptr<teq::iEvaluator>>(m, "iEvaluator");
+  py::class_<dbg::iPlugin, std::shared_ptr<dbg::iPlugin>>(m, "Plugin");
+  py::class_<dbg::PlugableEvaluator, teq::iEvaluator, std::shared_ptr<dbg::PlugableEvaluator>>(m, "PlugableEvaluator")
+      .def(py::init<>())
+      .def("add_plugin", &dbg::PlugableEvaluator::add_plugin);
+  py::class_<dbg::Inspector, dbg::iPlugin, std::shared_ptr<dbg::Inspector>>(m, "Inspector")
+      .def(py::init<>())
+      .def("add", &dbg::Inspector::add, py::arg("target"), py::arg("label") = "")
+      .def("last", [](dbg::Inspector& self) { return self.last_; }, "label -> (min, max) seen by the latest evaluation");
+  py::class_<dbg::OpProfiler, teq::iEvaluator, std::shared_ptr<dbg::OpProfiler>>(m, "OpProfiler")
+      .def(py::init<>())
+      .def("reset", &dbg::OpProfiler::reset)
+      .def("report", [](dbg::OpProfiler& self) {
+        py::list out;
+        double total = 0;
+        for (auto& kv : self.stats_) total += kv.second.ms;
+        for (auto& kv : self.stats_) {
+          py::dict d;
+          d["opcode"] = kv.first; d["calls"] = kv.second.calls; d["ms"] = kv.second.ms; d["bytes"] = kv.second.bytes;
+          d["share"] = total > 0 ? kv.second.ms / total : 0.0;
+          d["GBps"] = kv.second.ms > 0 ? kv.second.bytes / kv.second.ms / 1e6 : 0.0;
+          out.append(d);
+        }
+        return out;
+      }, "Per-opcode calls, device ms (CUDA events), algorithmic bytes, time share and GB/s since the last reset");
+  m.def("set_eval", [](std::shared_ptr<teq::iEvaluator> eval) { teq::set_eval(std::move(eval)); },
+        "Install an evaluator object in the context slot (teq::set_eval, internal/teq/evaluator.hpp:65)");
 
   // ---- hone: pre-evaluation rewrites (tenncor/hone/src/optimize.cpp)
   m.def("optimize", [](ETensorsT roots, bool fold_constants) {

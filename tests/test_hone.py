@@ -91,7 +91,7 @@ def test_constant_folding_on_device(gpu):
     x = tc.variable(rng.random((4, 5), dtype=np.float32), "x")
     c1 = tc.constant(np.arange(20, dtype=np.float32).reshape(4, 5))
     c2 = tc.constant(np.full((4, 5), 0.5, dtype=np.float32))
-    folded_part = tc.api.exp(c2) * c1 + tc.api.reduce_sum(c1)  # constants only: becomes one constant leaf
+    folded_part = tc.api.exp(c2) * c1 + tc.api.extend_like(tc.api.reduce_sum(c1), c1)  # constants only: becomes one constant leaf
     lo, hi = tc.scalar_constant(0, [4, 5]), tc.scalar_constant(1, [4, 5])
     noise = tc.api.random.rand_unif(lo, hi)                            # constant arguments, but not foldable
     root = x * folded_part + noise * 0.0

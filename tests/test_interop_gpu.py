@@ -1,0 +1,46 @@
+"""Zero-copy interop: every tensor exposes __cuda_array_interface__ over its resident HBM buffer, and
+EVariable.assign takes device arrays (HBM -> HBM) — the python demos keep their numpy flow, GPU pipelines skip the host."""
+import numpy as np
+import pytest
+
+import tenncor_b200 as tc
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def test_results_are_visible_to_torch_without_a_copy(gpu):
+    rng = np.random.default_rng(0)
+    a = tc.variable(rng.uniform(-1, 1, (6, 5, 4)).astype(np.float32), "a")
+    out = tc.api.tanh(a) * 2.0
+    with pytest.raises(Exception, match="no device data"):
+        tc.api.exp(a).__cuda_array_interface__  # never evaluated
+    out.calc()
+    tc.sync()
+    cai = out.__cuda_array_interface__
+    assert cai["shape"] == (6, 5, 4) and cai["typestr"] == "<f4" and cai["data"][0] == out.device_ptr() and cai["version"] == 3
+    t = torch.as_tensor(out, device="cuda")
+    assert t.data_ptr() == out.device_ptr() and tuple(t.shape) == (6, 5, 4)
+    np.testing.assert_array_equal(t.cpu().numpy(), out.data())
+
+
+def test_assign_from_a_device_array(gpu):
+    rng = np.random.default_rng(1)
+    x = tc.EVariable([4, 7], 0, "x")
+    y = tc.api.square(x)
+    src = torch.as_tensor(rng.uniform(-3, 3, (4, 7)).astype(np.float32)).cuda()
+    torch.cuda.synchronize()
+    v0 = x.get_version()
+    x.assign(src)
+    assert x.get_version() > v0
+    np.testing.assert_allclose(y.get(), src.cpu().numpy() ** 2, rtol=1e-6)
+    other = tc.variable(rng.uniform(-1, 1, (4, 7)).astype(np.float32), "other")
+    z = other + 1.0
+    z.calc()
+    tc.sync()
+    x.assign(z)  # another tensor of this module is a device array too
+    np.testing.assert_array_equal(x.data(), z.data())
+    with pytest.raises(Exception, match="dtype"):
+        x.assign(src.double())
+    with pytest.raises(Exception, match="shaped"):
+        x.assign(src[:2].contiguous())
