@@ -29,7 +29,9 @@ def test_plugable_evaluator_runs_plugins_after_the_traversal(gpu):
     ev = tc.PlugableEvaluator()
     ev.add_plugin(insp)
     tc.set_eval(ev)
-    got = out.get()
+    # an intermediate's buffer expires with its last consumer (device.hpp:555-570): to be inspected it must be a target,
+    # exactly as with the reference's Inspector
+    got = tc.run([out, hidden])[0]
     want = OracleSession([out, hidden]).run()
     np.testing.assert_allclose(got.reshape(-1), want[0], rtol=1e-5)
     last = insp.last()
