@@ -197,17 +197,18 @@ def dominant_kernel_roofline(cabi, name, w, peaks):
             "peak_source": "measured hbm_gbs (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650"}
 
 
-def cpu_reference_steps(cfg, gen, budget_s, max_steps):
+def cpu_reference_steps(cfg, gen, budget_s, max_steps, target=None):
     """The oracle port of the reference's CPU path: node-by-node numpy evaluation of the dumped
     graph (TravEvaluator order, one unfused op per functor, in-place ASSIGNs)."""
     import tenncor_b200 as tc
     from oracle import tcr_oracle as orc  # cpu_baseline leg only: never on the product path
     orc.set_baseline_mode(True)
-    tape = tc.dump_graph([cfg.train])
+    target = cfg.train if target is None else target
+    tape = tc.dump_graph([target])
     for node in tape:
         if node["kind"] == "leaf":
             node["data"] = np.array(node["data"], copy=True)
-    feed_ids = tc.dump_ids([cfg.train] + list(cfg.feeds.values()), None)
+    feed_ids = tc.dump_ids([target] + list(cfg.feeds.values()), None)
     rng = np.random.default_rng(0)
     times = []
     t_begin = time.perf_counter()
@@ -215,11 +216,20 @@ def cpu_reference_steps(cfg, gen, budget_s, max_steps):
         batch = gen(rng)
         t0 = time.perf_counter()
         for feed, arr in zip(cfg.feeds.values(), batch):
-            tape[feed_ids[feed]]["data"][...] = arr.reshape(-1)
+            if feed_ids[feed] < len(tape) and tape[feed_ids[feed]]["kind"] == "leaf":  # inference does not read the labels
+                tape[feed_ids[feed]]["data"][...] = arr.reshape(-1)
         orc.eval_tape(tape)
         times.append(time.perf_counter() - t0)
     steady = times[1:] if len(times) > 1 else times
     return float(np.median(steady)), len(times)
+
+
+def pick_target(cfg, mode):
+    if mode == "train":
+        return cfg.train
+    if "x" not in cfg.feeds or not hasattr(cfg.model, "get") or cfg.name.startswith("c4"):
+        raise SystemExit("--mode inference is defined for the models linked to their input variable: mlp (c1, c1w, c3) and conv")
+    return cfg.model
 
 
 def main():
@@ -232,6 +242,8 @@ def main():
     ap.add_argument("--evaluator", default="plan", choices=["plan", "node"])
     ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "exact"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--mode", default="train", choices=["train", "inference"],
+                    help="train: one apply_update step (the metric); inference: forward pass of the model only (BASELINE config 3 'inference+training')")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -246,7 +258,7 @@ def main():
     import tenncor_b200 as tc
     from tenncor_b200 import cabi
 
-    metric = "train steps/sec"
+    metric = "train steps/sec" if args.mode == "train" else "inference steps/sec"
     wdesc = {"workload": args.workload, **{k: v for k, v in WORKLOADS[args.workload].items()}}
 
     # ------------------------------------------------------------------ reference arm
@@ -254,7 +266,8 @@ def main():
         if rank != 0:
             return 0
         cfg, gen, w = build_config(args.workload)
-        med, nsteps = cpu_reference_steps(cfg, gen, budget_s=max(args.cpu_seconds, 10.0) * 4, max_steps=args.steps + args.warmup)
+        target = pick_target(cfg, args.mode)
+        med, nsteps = cpu_reference_steps(cfg, gen, budget_s=max(args.cpu_seconds, 10.0) * 4, max_steps=args.steps + args.warmup, target=target)
         cores = os.cpu_count()
         line = {"impl": "reference", "metric": metric, "value": round(1.0 / med, 4), "unit": "steps/s", "n_gpus": 0, "steps": nsteps,
                 "warmup": 1, "ms_per_step": round(med * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -282,8 +295,9 @@ def main():
         tc.dp.init(rank, world, ids[0], mean_reduce=mean_loss)
 
     cfg, gen, w = build_config(args.workload)
+    target = pick_target(cfg, args.mode)
     rng = np.random.default_rng(1000 + rank)
-    feeds = list(cfg.feeds.values())
+    feeds = list(cfg.feeds.values()) if args.mode == "train" else [cfg.feeds["x"]]  # inference reads no labels
     host = [pinned_array(cabi, f.shape()) for f in feeds]
     for buf, arr in zip(host, gen(rng)):
         buf[...] = arr
@@ -300,7 +314,7 @@ def main():
     for f, buf in zip(feeds, host):
         f.assign(buf)
     for _ in range(args.warmup):
-        cfg.train.calc()
+        target.calc()
         for f in feeds:
             f.touch()  # new input version, data stays resident: the next step recomputes everything
     barrier()
@@ -311,7 +325,7 @@ def main():
     for _ in range(args.steps):
         for f in feeds:
             f.touch()
-        cfg.train.calc()
+        target.calc()
     ms_total = stop_ms()
     launches = int(cabi.lib().tcr_launch_count() - launches0)
     barrier()
@@ -322,13 +336,13 @@ def main():
     for _ in range(args.warmup):
         for f, buf in zip(feeds, host):
             f.assign(buf)
-        loss = cfg.train.get()
+        loss = target.get()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for f, buf in zip(feeds, host):
             f.assign(buf)
-        loss = cfg.train.get()
+        loss = target.get()
     tc.sync()
     e2e_serial_s = time.perf_counter() - t0
     barrier()
@@ -341,7 +355,7 @@ def main():
             f.commit()
         for f, buf in zip(feeds, host):
             f.prefetch(buf)
-        loss = cfg.train.get()
+        loss = target.get()
     tc.sync()
     tc.sync_prefetch()
     barrier()
@@ -351,7 +365,7 @@ def main():
             f.commit()
         for f, buf in zip(feeds, host):
             f.prefetch(buf)
-        loss = cfg.train.get()
+        loss = target.get()
     tc.sync()
     tc.sync_prefetch()  # K copies were issued inside the timed region: all of them must have landed
     e2e_s = time.perf_counter() - t0
@@ -381,21 +395,24 @@ def main():
         except Exception:
             pass
         if args.cpu_seconds > 0:
-            med, nsteps = cpu_reference_steps(cfg, gen, budget_s=args.cpu_seconds, max_steps=20)
+            med, nsteps = cpu_reference_steps(cfg, gen, budget_s=args.cpu_seconds, max_steps=20, target=target)
             cpu_baseline = {"value": round(1.0 / med, 4), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
                             "sample": "%d full steps of the same graph on the host (numpy oracle of the Eigen path)" % nsteps}
         else:
             cpu_baseline = None  # --cpu-seconds 0: the CPU leg was skipped on request
         ms_step = ms_total / args.steps
+        # inference = forward only: a third of forward + both gradients for the GEMM-dominated models (approximate for c3, whose
+        # first layer has no input gradient: 2*B*(in*hid + hid*out) exactly)
+        flops_step = cfg.flops_per_step if args.mode == "train" else (2 * w["nbatch"] * (w["ninput"] * w["nhidden"] + w["nhidden"] * w["noutput"]) if "ninput" in w else cfg.flops_per_step // 3)
         line = {
             "metric": metric, "value": round(world * 1e3 / ms_step, 3), "unit": "steps/s (sum over GPUs of per-GPU steps/s; each step = one local batch)",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(wdesc, desc=cfg.desc, batch_per_gpu=w.get("nbatch", w.get("batch")), global_batch=(w.get("nbatch") or w.get("batch") or 1) * world,
-                           evaluator=args.evaluator, matmul=args.precision, parallelism="dp%d" % world,
+                           evaluator=args.evaluator, matmul=args.precision, parallelism="dp%d" % world, mode=args.mode,
                            cache="step working set %s L2 (126 MB); no flush" % ("exceeds" if args.workload in ("c3", "c1w", "c4", "c4gru", "c2", "conv") else "is resident in")),
             "samples_per_s": round(world * (w.get("nbatch") or w.get("batch") or 1) * 1e3 / ms_step, 1),
-            "flops_per_step": cfg.flops_per_step, "tflops": round(cfg.flops_per_step / ms_step / 1e9, 2),
+            "flops_per_step": flops_step, "tflops": round(flops_step / ms_step / 1e9, 2),
             "clocks": clocks,
             "e2e": {"value": round(world * args.steps * 1e3 / e2e_ms, 3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms / args.steps, 4), "input": "prefetched one step ahead on a copy stream (EVariable.prefetch / commit)",
