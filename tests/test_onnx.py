@@ -1,8 +1,8 @@
 """ONNX-dialect model files: tc.load_from_file / tc.save_to_file mirror
 tenncor/python/eteq_ext.cpp:408-487 over internal/onnx + tenncor/serial.
 
-Pinned against the reference: tests/golden/onnx/*.onnx were written by the reference's serializer
-(its shipped demo models). Each is decoded twice — by the host's loader and by the small independent
+Pinned against the reference: tests/golden/reference_models.json holds files written by the reference's
+serializer (its shipped demo models gd / dqn / dbn / rnn). Each is decoded twice — by the host's loader and by the small independent
 wire-format reader below — and the forward pass the loaded graph defines (evaluated by the CPU oracle)
 must equal the one recomputed in numpy from the independently decoded weights. No device needed."""
 import os
@@ -15,7 +15,23 @@ import tenncor_b200 as tc
 from oracle import tcr_oracle as orc
 from tenncor_b200 import configs
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "onnx")
+GOLDEN_JSON = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_models.json")
+
+
+def golden_model(name, tmp_dir=None):
+    """path of the reference's models/<name>.onnx, materialised from the committed fixture (tests/golden/make_model_goldens.py)"""
+    import base64
+    import hashlib
+    import json
+    import tempfile
+    entry = json.load(open(GOLDEN_JSON))["models"][name]
+    data = base64.b64decode(entry["base64"])
+    assert len(data) == entry["bytes"] and hashlib.sha256(data).hexdigest() == entry["sha256"]
+    d = tmp_dir or tempfile.mkdtemp(prefix="tcr_golden_")
+    path = os.path.join(str(d), name + ".onnx")
+    with open(path, "wb") as f:
+        f.write(data)
+    return path
 
 
 @pytest.fixture(autouse=True)
@@ -104,7 +120,7 @@ def _sigmoid(x):
 # ---------------------------------------------------------------- the reference's own files
 @pytest.mark.parametrize("name,widths", [("gd", [10, 9, 5]), ("dqn", [10, 9, 9])])
 def test_reference_dense_models_load_and_evaluate(name, widths):
-    path = os.path.join(GOLDEN, name + ".onnx")
+    path = golden_model(name)
     model = tc.load_from_file(path)
     assert len(model) == 1
     got = _oracle_eval(model)[0]
@@ -125,7 +141,7 @@ def test_reference_dense_models_load_and_evaluate(name, widths):
 
 @pytest.mark.parametrize("name", ["gd", "dqn", "dbn", "rnn"])
 def test_reference_files_survive_a_round_trip(name, tmp_path):
-    path = os.path.join(GOLDEN, name + ".onnx")
+    path = golden_model(name)
     first = tc.load_from_file(path)
     want = _oracle_eval(first)
     again_path = str(tmp_path / (name + "_again.onnx"))
@@ -221,7 +237,7 @@ def test_pretrained_gd_model_solves_the_gd_demo_task():
     x = rng.random((200, 10)).astype(np.float32)
     y = (x[:, 0::2] + x[:, 1::2]) / 2
     testin = tc.variable(x, "testin")
-    pretrained = tc.load_from_file(os.path.join(GOLDEN, "gd.onnx"))[0].connect(testin)
+    pretrained = tc.load_from_file(golden_model("gd"))[0].connect(testin)
     untrained = configs.mlp(10, 9, 5, 3).model.connect(testin)
     err = [float(np.mean(np.abs(o.reshape(200, 5) - y))) for o in _oracle_eval([pretrained, untrained])]
     assert err[0] < 0.05 and err[1] > 3 * err[0], err

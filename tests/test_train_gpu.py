@@ -200,8 +200,8 @@ def test_pretrained_onnx_model_runs_and_keeps_training(gpu, evaluator):
     import os
     tc.set_evaluator(evaluator)
     try:
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "onnx", "gd.onnx")
-        model = tc.load_from_file(path)[0]
+        from tests.test_onnx import golden_model
+        model = tc.load_from_file(golden_model("gd"))[0]
         rng = np.random.default_rng(0)
         x = rng.random((200, 10)).astype(np.float32)
         y = (x[:, 0::2] + x[:, 1::2]) / 2
