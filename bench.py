@@ -224,6 +224,18 @@ def cpu_reference_steps(cfg, gen, budget_s, max_steps, target=None):
     return float(np.median(steady)), len(times)
 
 
+def e2e_entry(world, steps, pipelined_ms, serial_ms, h2d, d2h):
+    """Both loops go through the public API with the same per-step H2D + D2H; the headline is the faster one (prefetching pays
+    when the copy is long enough to hide: c3 1.7x; for the latency-bound toy sizes its extra device copy costs ~10 %)."""
+    pipe = {"value": round(world * steps * 1e3 / pipelined_ms, 3), "ms_per_step": round(pipelined_ms / steps, 4),
+            "input": "prefetched one step ahead on a copy stream (EVariable.prefetch / commit)"}
+    serial = {"value": round(world * steps * 1e3 / serial_ms, 3), "ms_per_step": round(serial_ms / steps, 4),
+              "input": "EVariable.assign then get(), no overlap"}
+    best = pipe if pipelined_ms <= serial_ms else serial
+    return {"value": best["value"], "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": best["ms_per_step"],
+            "input": best["input"], "pipelined": pipe, "serial": serial}
+
+
 def pick_target(cfg, mode):
     if mode == "train":
         return cfg.train
@@ -414,10 +426,7 @@ def main():
             "samples_per_s": round(world * (w.get("nbatch") or w.get("batch") or 1) * 1e3 / ms_step, 1),
             "flops_per_step": flops_step, "tflops": round(flops_step / ms_step / 1e9, 2),
             "clocks": clocks,
-            "e2e": {"value": round(world * args.steps * 1e3 / e2e_ms, 3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_ms / args.steps, 4), "input": "prefetched one step ahead on a copy stream (EVariable.prefetch / commit)",
-                    "serial": {"value": round(world * args.steps * 1e3 / e2e_serial_ms, 3), "ms_per_step": round(e2e_serial_ms / args.steps, 4),
-                               "input": "EVariable.assign then get(), no overlap"}},
+            "e2e": e2e_entry(world, args.steps, e2e_ms, e2e_serial_ms, h2d, d2h),
             "gpu_launches": launches, "launches_per_step": round(launches / args.steps, 1), "plan": plan,
             "roofline": roof,
             "cpu_baseline": cpu_baseline,

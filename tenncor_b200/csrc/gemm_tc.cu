@@ -549,14 +549,11 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
     if (min_kb > 0 && tiles * 2 <= sms && total_kb >= 16) {
       double best = (double)tiles / (double)(ceil_div(tiles, sms) * sms);
       const int sp_cap = total_kb >= sms * 16 ? sms : 32;  // very long reductions may use every SM for one output tile
-      // Small outputs (the LSTM's 64 x 1024 x 1152 gate products) are latency-bound: splits down to 2 k-blocks pay as long as
-      // the partials stay a few MB (profiles/r1_sweep_c4_gemm.txt: 13.1 -> 9.7 us per launch in a graph; 64 x 4096 x 1152,
-      // whose partials would reach 9 MB, gets slower and keeps the 8-block floor)
-      const bool default_floor = std::getenv("TCR_GEMM_SPLIT_MIN_KB") == nullptr;
-      for (int sp = 2; sp <= sp_cap; ++sp) {
-        const int kb = total_kb / sp;
-        const bool small_partials = (int64_t)sp * d->m * d->n * (int64_t)sizeof(float) <= (6ll << 20);
-        if (!(kb >= min_kb || (default_floor && kb >= 2 && small_partials))) break;
+      // The floor of 8 k-blocks per split stays even for small latency-bound outputs. Alone in a graph the LSTM's 64 x 1024 x 1152
+      // gate product gets faster with more splits (13.1 us at >= 8 k-blocks, 9.7 us at >= 2, profiles/r1_sweep_c4_gemm.txt), but the
+      // step runs four of them on concurrent lanes: 4 x 144 CTAs no longer fit one wave and the whole C4 step went from 15.7 ms to
+      // 20.2 ms (>= 4 k-blocks: 16.4 ms). Measured with TCR_GEMM_SPLIT_MIN_KB, profiles/r1_bench_c4_split_floor.md.
+      for (int sp = 2; sp <= sp_cap && total_kb / sp >= min_kb; ++sp) {
         double eff = (double)(tiles * sp) / (double)(ceil_div(tiles * sp, sms) * sms);
         if (eff > best + 0.05) { best = eff; splits = sp; }
       }
