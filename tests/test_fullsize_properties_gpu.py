@@ -181,3 +181,37 @@ def test_c4_lstm_step_is_finite_and_deterministic(gpu):
     assert runs[0][0] == runs[1][0]
     np.testing.assert_array_equal(runs[0][1], runs[1][1])
     assert rng is not None
+
+
+def test_conv2d_adjoint_identities_at_bench_size(gpu):
+    """conv2d 3x3, 32 -> 64 channels, 34x34, batch 64 (bench.py --workload conv): the oracle's padded-rank formulation needs
+    minutes there, so forward, kernel gradient and image gradient — three different lowerings (patch gather + GEMM, gather +
+    transposed split-K GEMM, GEMM + patch scatter) — are tied together by the bilinear form they all evaluate:
+        <conv(x, k), g>  ==  <k, dL/dk>  ==  <x, dL/dx>      for L = sum(conv(x, k) * g),
+    and the planned evaluator must agree with itself under linearity in x. fp32 / 3xTF32: 1e-4 relative."""
+    tc.set_evaluator("plan")
+    tc.set_matmul_precision("3xtf32")
+    rng = np.random.default_rng(21)
+    B, H, W, cin, cout = 64, 34, 34, 32, 64
+    x_np = rng.uniform(-1, 1, (B, H, W, cin)).astype(np.float32)
+    k_np = rng.uniform(-1, 1, (3, 3, cin, cout)).astype(np.float32)
+    g_np = rng.uniform(-1, 1, (B, H - 2, W - 2, cout)).astype(np.float32)
+    x, k, g = tc.variable(x_np, "x"), tc.variable(k_np, "k"), tc.variable(g_np, "g")
+    out = tc.api.nn.conv2d(x, k)
+    loss = tc.api.reduce_sum(out * g)
+    dk, dx = tc.derive(loss, [k, x])
+    steps = tc.describe_plan([out, dk, dx])
+    assert any(s.startswith("CONV2D im2col+GEMM") for s in steps) and any(s.startswith("CONV2D-dK") for s in steps)
+    assert any(s.startswith("CONV2D-dX") for s in steps) and not any(s.startswith("CONV ") for s in steps), steps
+    out_v, dk_v, dx_v = (a.astype(np.float64) for a in tc.run([out, dk, dx]))
+    form = float(np.sum(out_v * g_np))
+    scale = float(np.sum(np.abs(out_v) * np.abs(g_np)))
+    assert abs(float(np.sum(dk_v * k_np)) - form) <= 1e-4 * scale
+    assert abs(float(np.sum(dx_v * x_np)) - form) <= 1e-4 * scale
+    # spot values against a direct evaluation of the definition at a few output positions
+    for (b, y, xx, o) in [(0, 0, 0, 0), (63, 31, 31, 63), (17, 5, 29, 40), (40, 30, 2, 7)]:
+        want = float(np.sum(x_np[b, y:y + 3, xx:xx + 3, :].astype(np.float64) * k_np[:, :, :, o]))
+        assert abs(out_v[b, y, xx, o] - want) <= 1e-4 * float(np.sum(np.abs(x_np[b, y:y + 3, xx:xx + 3, :]) * np.abs(k_np[:, :, :, o])))
+    # linearity in the image: conv(2x, k) == 2 conv(x, k) bit for bit (a power-of-two scale commutes with every rounding)
+    x.assign(2 * x_np)
+    np.testing.assert_array_equal(out.get().astype(np.float64), 2 * out_v)
