@@ -15,6 +15,10 @@ import os
 import re
 
 REF = "/root/reference/tenncor/test/test_equation.cpp"
+# one more golden of the same kind from the API tests: forward and both gradients of CONV
+# (tenncor/test/test_api.cpp:2265-2361, asserted there with ASSERT_VECEQ on doubles)
+API_REF = "/root/reference/tenncor/test/test_api.cpp"
+API_FUNCS = {"api_convolution": (2265, 2361)}
 FUNCS = {"matmul_complex": (26, 136), "contract_equivalent": (139, 250), "sigmoid_MLP_slow": (252, 480),
          "sigmoid_MLP_fast": (482, 707), "tanh_RNN": (709, 840), "tanh_RNN_layer": (842, 970)}
 
@@ -32,6 +36,12 @@ def main():
         shapes = {m.group(1): [int(v) for v in numbers(m.group(2))] for m in re.finditer(r"teq::Shape\s+(\w+)\(\{([^}]*)\}\)", text)}
         shapes.update({m.group(1): [int(v) for v in numbers(m.group(2))] for m in re.finditer(r"teq::DimsT\s+(\w+)\s*=\s*\{([^}]*)\};", text)})
         out[name] = {"cite": "tenncor/test/test_equation.cpp:%d-%d" % (lo, hi), "vectors": vecs, "shapes": shapes}
+    api_lines = open(API_REF).read().split("\n")
+    for name, (lo, hi) in API_FUNCS.items():
+        text = "\n".join(api_lines[lo - 1:hi])
+        vecs = {m.group(1): numbers(m.group(2)) for m in re.finditer(r"std::vector<double>\s+(\w+)\s*=\s*\{([^}]*)\};", text, re.S)}
+        shapes = {m.group(1): [int(v) for v in numbers(m.group(2))] for m in re.finditer(r"teq::DimsT\s+(\w+)\s*=\s*\{([^}]*)\};", text, re.S)}
+        out[name] = {"cite": "tenncor/test/test_api.cpp:%d-%d" % (lo, hi), "vectors": vecs, "shapes": shapes}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "equation_goldens.json")
     with open(path, "w") as f:
         json.dump(out, f)

@@ -73,7 +73,18 @@ def build_rnn(g, layer):
     return tc.derive(err, [weight, bias, istate]), ["expect_gw", "expect_gb", "expect_gstate"]
 
 
+def build_api_convolution(g):
+    """API.Convolution (tenncor/test/test_api.cpp:2265-2361): an image [2,4,3,3] correlated with a [1,2,2,1] kernel over all
+    ranks in order, and the gradients of the result w.r.t. image and kernel (CONV rules of backprop.hpp, through PAD /
+    REVERSE / PERMUTE). The reference builds both operands as constants; the values do not depend on that."""
+    img, kernel = var(g, "data", "alist"), var(g, "data2", "blist")
+    dest = tc.api.convolution(img, kernel, list(range(8)))
+    assert dest.teq_shape() == g["shapes"]["expectslist"]
+    return [dest] + tc.derive(dest, [img, kernel]), ["expect_out", "expect_ga", "expect_gb"]
+
+
 CASES = {
+    "api_convolution": build_api_convolution,
     "matmul_complex": lambda g: build_matmul_complex(g),
     "contract_equivalent": lambda g: build_matmul_complex(g, contract=True),
     "sigmoid_MLP_slow": lambda g: build_mlp(g, fast=False),

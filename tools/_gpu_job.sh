@@ -1,13 +1,15 @@
 set +e
 mkdir -p gpurun_out
 date +%s > gpurun_out/t0
-timeout 700 python -m pytest tests -m gpu -q -x 2>&1 | tail -6 > gpurun_out/r1_gpu_tests.log; tail -6 gpurun_out/r1_gpu_tests.log
-echo "all tests done $(( $(date +%s) - $(cat gpurun_out/t0) ))s"
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-for wl in c3 c1 c2 c5 conv; do
-  extra="--cpu-seconds 3"; [ $wl = conv ] && extra="--cpu-seconds 0"; [ $wl = c3 ] && extra="--cpu-seconds 10"
-  timeout 300 python bench.py --workload $wl --steps 30 $extra > gpurun_out/r1_bench_final_$wl.log 2> gpurun_out/r1_bench_final_$wl.err; tail -1 gpurun_out/r1_bench_final_$wl.log | cut -c1-200; tail -2 gpurun_out/r1_bench_final_$wl.err
-  echo "bench $wl done $(( $(date +%s) - $(cat gpurun_out/t0) ))s"
-done
-timeout 200 python bench.py --impl reference --steps 3 --warmup 1 --cpu-seconds 3 2>&1 | tail -1 | cut -c1-300
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel" -s 1 -c 1 -o gpurun_out/r1_ncu_conv_gemm python tools/one_gemm.py --m 65536 --n 64 --k 288 --prec 2 --iters 2 --warmup 1 > gpurun_out/r1_ncu_conv_gemm.log 2>&1
+python tools/ncu_summary.py gpurun_out/r1_ncu_conv_gemm.ncu-rep > gpurun_out/r1_ncu_conv_gemm_summary.txt 2>&1; cat gpurun_out/r1_ncu_conv_gemm_summary.txt | head -30
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel" -s 1 -c 1 -o gpurun_out/r1_ncu_conv_gemm_tf32 python tools/one_gemm.py --m 65536 --n 64 --k 288 --prec 1 --iters 2 --warmup 1 > gpurun_out/r1_ncu_conv_gemm_tf32.log 2>&1
+python tools/ncu_summary.py gpurun_out/r1_ncu_conv_gemm_tf32.ncu-rep > gpurun_out/r1_ncu_conv_gemm_tf32_summary.txt 2>&1; cat gpurun_out/r1_ncu_conv_gemm_tf32_summary.txt | head -30
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"col2im" -c 1 -o gpurun_out/r1_ncu_col2im_vec python tools/microbench.py --only conv > gpurun_out/r1_ncu_col2im_vec.log 2>&1
+python tools/ncu_summary.py gpurun_out/r1_ncu_col2im_vec.ncu-rep > gpurun_out/r1_ncu_col2im_vec_summary.txt 2>&1; cat gpurun_out/r1_ncu_col2im_vec_summary.txt | head -30
+python tools/one_gemm.py --m 65536 --n 64 --k 288 --prec 2 --iters 20 --warmup 2 --graph
+python tools/one_gemm.py --m 65536 --n 64 --k 288 --prec 1 --iters 20 --warmup 2 --graph
+python tools/one_gemm.py --m 65536 --n 128 --k 288 --prec 2 --iters 20 --warmup 2 --graph
+python tools/one_gemm.py --m 65536 --n 256 --k 288 --prec 2 --iters 20 --warmup 2 --graph
+python tools/one_gemm.py --m 32768 --n 128 --k 576 --prec 2 --iters 20 --warmup 2 --graph
 echo "done $(( $(date +%s) - $(cat gpurun_out/t0) ))s"
