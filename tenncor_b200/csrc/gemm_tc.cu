@@ -577,6 +577,15 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
         pk.fin_epilogue = p.epilogue; pk.fin_activation = p.activation; pk.fin_accumulate = p.accumulate;
       }
     }
+    // Few k-blocks per CTA and many CTAs (conv2d patch products, K = 9 x channels): the 6-stage ring never fills, and with 198 KB
+    // of stages only one CTA fits an SM, so nothing hides its prologue and epilogue (profiles/r1_ncu_conv.md). In TF32 a 3-stage ring
+    // (97 KB, two CTAs per SM) is 1.37x faster there (65536 x 64 x 288: 25.3 -> 18.5 us). The 3xTF32 ring is already 3 stages; a
+    // single-stage variant that would fit two CTAs was slower everywhere (41.7 -> 46.8 us; LSTM gate product 13.9 -> 19.5 us;
+    // profiles/r1_sweep_shortk.txt) and is not built. TCR_GEMM_SHORTK=0 disables the shallow ring.
+    static const int shortk = std::getenv("TCR_GEMM_SHORTK") ? std::atoi(std::getenv("TCR_GEMM_SHORTK")) : 1;
+    if (shortk && d->precision == TCR_GEMM_TF32 && p.kb_per_split <= 12 && tiles * splits >= 2 * sms)
+      rc = launch_tc<1, 3>(ma, mb, pk, splits);
+    else
     rc = d->precision == TCR_GEMM_TF32 ? launch_tc<1, 6>(ma, mb, pk, splits) : launch_tc<2, 3>(ma, mb, pk, splits);
     if (rc) return rc;
     if (splits > 1) {

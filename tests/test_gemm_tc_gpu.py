@@ -33,7 +33,8 @@ def run_gemm(gpu, A, B, ta, tb, precision, perm_c=False, bias=None, epi=0, act=0
     return out.reshape(N, M).T if perm_c else out.reshape(M, N)
 
 
-SHAPES = [(128, 128, 32), (128, 128, 256), (256, 384, 96), (300, 200, 100), (1000, 72, 520), (64, 4096, 64), (8192, 1024, 784), (129, 257, 36)]
+SHAPES = [(128, 128, 32), (128, 128, 256), (256, 384, 96), (300, 200, 100), (1000, 72, 520), (64, 4096, 64), (8192, 1024, 784), (129, 257, 36),
+          (40000, 64, 288)]  # many tiles x few k-blocks (conv2d patch product): the shallow-ring TF32 variant
 
 
 @pytest.mark.parametrize("precision", [1, 2], ids=["tf32", "3xtf32"])

@@ -1,15 +1,16 @@
 set +e
 mkdir -p gpurun_out
 date +%s > gpurun_out/t0
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel" -s 1 -c 1 -o gpurun_out/r1_ncu_conv_gemm python tools/one_gemm.py --m 65536 --n 64 --k 288 --prec 2 --iters 2 --warmup 1 > gpurun_out/r1_ncu_conv_gemm.log 2>&1
-python tools/ncu_summary.py gpurun_out/r1_ncu_conv_gemm.ncu-rep > gpurun_out/r1_ncu_conv_gemm_summary.txt 2>&1; cat gpurun_out/r1_ncu_conv_gemm_summary.txt | head -30
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel" -s 1 -c 1 -o gpurun_out/r1_ncu_conv_gemm_tf32 python tools/one_gemm.py --m 65536 --n 64 --k 288 --prec 1 --iters 2 --warmup 1 > gpurun_out/r1_ncu_conv_gemm_tf32.log 2>&1
-python tools/ncu_summary.py gpurun_out/r1_ncu_conv_gemm_tf32.ncu-rep > gpurun_out/r1_ncu_conv_gemm_tf32_summary.txt 2>&1; cat gpurun_out/r1_ncu_conv_gemm_tf32_summary.txt | head -30
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:"col2im" -c 1 -o gpurun_out/r1_ncu_col2im_vec python tools/microbench.py --only conv > gpurun_out/r1_ncu_col2im_vec.log 2>&1
-python tools/ncu_summary.py gpurun_out/r1_ncu_col2im_vec.ncu-rep > gpurun_out/r1_ncu_col2im_vec_summary.txt 2>&1; cat gpurun_out/r1_ncu_col2im_vec_summary.txt | head -30
-python tools/one_gemm.py --m 65536 --n 64 --k 288 --prec 2 --iters 20 --warmup 2 --graph
-python tools/one_gemm.py --m 65536 --n 64 --k 288 --prec 1 --iters 20 --warmup 2 --graph
-python tools/one_gemm.py --m 65536 --n 128 --k 288 --prec 2 --iters 20 --warmup 2 --graph
-python tools/one_gemm.py --m 65536 --n 256 --k 288 --prec 2 --iters 20 --warmup 2 --graph
-python tools/one_gemm.py --m 32768 --n 128 --k 576 --prec 2 --iters 20 --warmup 2 --graph
+TCR_GEMM_SHORTK=1 timeout 300 python -m pytest tests/test_gemm_tc_gpu.py tests/test_gemm_shapes_gpu.py tests/test_conv_gpu.py -m gpu -q -x 2>&1 | tail -4
+echo "tests done $(( $(date +%s) - $(cat gpurun_out/t0) ))s"
+for knob in 0 1; do
+  for shape in "65536 64 288 2" "65536 64 288 1" "65536 64 576 2" "16384 128 800 2" "64 1024 1152 2" "8192 128 256 2"; do
+    set -- $shape
+    echo -n "shortk=$knob "
+    TCR_GEMM_SHORTK=$knob python tools/one_gemm.py --m $1 --n $2 --k $3 --prec $4 --iters 20 --warmup 2 --graph
+  done
+done > gpurun_out/r1_sweep_shortk.txt 2>&1; cat gpurun_out/r1_sweep_shortk.txt
+echo "sweep done $(( $(date +%s) - $(cat gpurun_out/t0) ))s"
+TCR_GEMM_SHORTK=1 timeout 200 python bench.py --workload conv --steps 20 --cpu-seconds 0 2>/dev/null | tail -1 | cut -c1-220
+TCR_GEMM_SHORTK=1 timeout 300 python bench.py --workload c4 --steps 20 --cpu-seconds 0 2>/dev/null | tail -1 | cut -c1-220
 echo "done $(( $(date +%s) - $(cat gpurun_out/t0) ))s"
