@@ -41,13 +41,14 @@ ETensor binary(_GENERATED_OPCODE op, double scalar, const ETensor& b) { return m
 ETensor min(const ETensorsT& args) {  // core.yml:569-586
   if (args.empty()) global::fatal("cannot min without arguments");
   ETensor out = args[0];
-  for (size_t i = 1, n = args.size(); i < n; ++i) out = min(out, args[i]);
+  // binary() by name: an unqualified min(ETensor, ETensor) finds std::min through ADL (shared_ptr lives in std) and would compare pointers
+  for (size_t i = 1, n = args.size(); i < n; ++i) out = binary(MIN, out, args[i]);
   return out;
 }
 ETensor max(const ETensorsT& args) {  // core.yml:616-633
   if (args.empty()) global::fatal("cannot max without arguments");
   ETensor out = args[0];
-  for (size_t i = 1, n = args.size(); i < n; ++i) out = max(out, args[i]);
+  for (size_t i = 1, n = args.size(); i < n; ++i) out = binary(MAX, out, args[i]);
   return out;
 }
 
@@ -125,7 +126,7 @@ ETensor reduce_l2norm_1d(const ETensor& arg, RankT dimension) { return sqrt(redu
 ETensor clip_by_range(const ETensor& arg, double minval, double maxval) {  // core.yml:1147-1166
   if (minval > maxval) global::fatal("min value is below max");
   auto lo = make_constant_like(minval, arg), hi = make_constant_like(maxval, arg);
-  return max(min(arg, hi), lo);
+  return binary(MAX, binary(MIN, arg, hi), lo);  // not min()/max(): ADL would pick std::min / std::max on the shared_ptrs
 }
 ETensor clip_by_l2norm(const ETensor& arg, double upper) {  // core.yml:1167-1189
   if (upper == 0) global::fatal("cannot clip_by_norm with a upper limit of 0");
@@ -235,6 +236,39 @@ layr::InitF xavier_normal(double factor, _GENERATED_DTYPE dtype) {  // init.yml:
     return var_from(vec, dtype, shape, label);
   };
 }
+static void truncated_fill(std::vector<double>& vec, double mean, double stdev) {  // layr::truncated_normal, init.hpp:40-72
+  std::normal_distribution<double> dist(mean, stdev);
+  const double upper = mean + 2 * stdev, lower = mean - 2 * stdev;
+  for (auto& v : vec) {
+    v = dist(host_rng());
+    for (int retry = 0; (v > upper || v < lower) && retry < 5; ++retry) v = dist(host_rng());
+    v = std::min(std::max(v, lower), upper);
+  }
+}
+layr::InitF truncated_normal(double mean, double stddev, _GENERATED_DTYPE dtype) {  // init.yml:54-74
+  return [=](Shape shape, std::string label) {
+    std::vector<double> vec(shape.n_elems());
+    truncated_fill(vec, mean, stddev);
+    return var_from(vec, dtype, shape, label);
+  };
+}
+layr::InitF identity(double gain, _GENERATED_DTYPE dtype) {  // init.yml:170-195
+  return [=](Shape shape, std::string label) {
+    if (false == shape.compatible_after(Shape(), 2)) global::fatal("identity initialization can only be used for to 2D tensors");
+    std::vector<double> vec(shape.n_elems(), 0);
+    const DimT x = shape.at(0), y = shape.at(1);
+    for (DimT diag = 0, n = std::min(x, y); diag < n; ++diag) vec[diag + diag * x] = gain;
+    return var_from(vec, dtype, shape, label);
+  };
+}
+layr::InitF variance_scaling(double factor, std::function<double(Shape)> shape_factor, _GENERATED_DTYPE dtype) {  // init.yml:196-219
+  if (!shape_factor) shape_factor = [](Shape shape) { return fanio(shape) / 2; };  // layr::fanavg
+  return [=](Shape shape, std::string label) {
+    std::vector<double> vec(shape.n_elems());
+    truncated_fill(vec, 0, std::sqrt(factor / shape_factor(shape)));
+    return var_from(vec, dtype, shape, label);
+  };
+}
 }  // namespace init
 
 // ------------------------------------------------------------------ nn.yml
@@ -267,10 +301,87 @@ ETensor dropout(const ETensor& input, const ETensor& drop_rate) {  // nn.yml:112
   auto denom = div(reduce_sum(mask), n_elems(mask));
   return mul(input, div(mask, extend_like(denom, mask)));
 }
+
+ETensor batch_normalization(const ETensor& input, ETensor offset, ETensor scale, ETensor eps, layr::UnaryF get_mean, layr::UnaryF get_variance) {  // nn.yml:158-208
+  if (!get_mean) get_mean = [](const ETensor& in) { return extend_like(reduce_mean(in), in); };
+  if (!get_variance) get_variance = [](const ETensor& in) { return extend_like(reduce_variance(in), in); };
+  if (false == offset->shape().compatible_after(input->shape(), 0)) offset = extend_like(offset, input);
+  if (false == scale->shape().compatible_after(input->shape(), 0)) scale = extend_like(scale, input);
+  if (false == eps->shape().compatible_after(input->shape(), 0)) eps = extend_like(eps, input);
+  auto norm = div(sub(input, get_mean(input)), sqrt(add(get_variance(input), eps)));
+  return add(mul(norm, scale), offset);
+}
+
+static double type_epsilon(const ETensor& t) {  // std::numeric_limits<T>::epsilon() of the input's element type
+  return (_GENERATED_DTYPE)t->get_meta().type_code() == DOUBLE ? std::numeric_limits<double>::epsilon() : std::numeric_limits<float>::epsilon();
+}
+
+ETensor batch_normalization(const ETensor& input, double offset, double scale, double eps, layr::UnaryF get_mean, layr::UnaryF get_variance) {  // nn.yml:128-157
+  if (eps < 0) eps = type_epsilon(input);
+  return batch_normalization(input, eteq::make_constant_like(offset, input), eteq::make_constant_like(scale, input),
+                             eteq::make_constant_like(eps, input), get_mean, get_variance);
+}
+
+static ETensor pool2d(const ETensor& arg, std::pair<RankT, RankT> dims, bool take_max) {  // nn.yml:209-268
+  Shape shape = arg->shape();
+  DimT xextent = shape.at(dims.first) - 1, yextent = shape.at(dims.second) - 1;
+  DimsT strider(rank_cap, 1);
+  strider[dims.first] = strider[dims.second] = 2;
+  auto top_left = stride(arg, strider);
+  auto top_right = stride(slice(arg, 1, xextent, dims.first), strider);
+  auto bot_left = stride(slice(arg, 1, yextent, dims.second), strider);
+  eigen::PairVecT<DimT> pvec(rank_cap, {0, std::numeric_limits<DimT>::max()});
+  pvec[dims.first] = {1, xextent};
+  pvec[dims.second] = {1, yextent};
+  auto bot_right = stride(slice(arg, pvec), strider);
+  ETensorsT corners = {top_left, top_right, bot_left, bot_right};
+  return take_max ? max(corners) : div(sum(corners), 4.);
+}
+ETensor mean_pool2d(const ETensor& arg, std::pair<RankT, RankT> dims) { return pool2d(arg, dims, false); }
+ETensor max_pool2d(const ETensor& arg, std::pair<RankT, RankT> dims) { return pool2d(arg, dims, true); }
 }  // namespace nn
 
 // ------------------------------------------------------------------ layer.yml
 namespace layer {
+
+ETensor dropout(const ETensor& input, const ETensor& drop_rate, ETensor training) {  // layer.yml:455-478
+  auto out = nn::dropout(input, drop_rate);
+  if (nullptr != training) {
+    if (false == training->shape().compatible_after(input->shape(), 0)) training = extend_like(training, input);
+    out = if_then_else(training, out, input);
+  }
+  return out;
+}
+
+ETensor batch_normalization(ETensor input, ETensor offset, ETensor scale, ETensor eps, ETensor training, ETensor momentum,
+                            layr::InitF moving_mean_init, layr::InitF moving_var_init, RankT axis) {  // layer.yml:523-633
+  layr::UnaryF get_mean, get_var;
+  const bool whole = axis >= rank_cap;
+  auto batch_mean = [whole, axis](const ETensor& in) { return extend_like(whole ? reduce_mean(in) : reduce_mean_1d(in, axis), in); };
+  auto batch_var = [whole, axis](const ETensor& in) { return extend_like(whole ? reduce_variance(in) : reduce_variance_1d(in, axis), in); };
+  if (nullptr == training) {
+    get_mean = batch_mean;
+    get_var = batch_var;
+  } else {
+    const auto dtype = (_GENERATED_DTYPE)input->get_meta().type_code();
+    if (nullptr == momentum) momentum = eteq::make_constant_like(0.99, input);
+    if (!moving_mean_init) moving_mean_init = init::zeros(dtype);
+    if (!moving_var_init) moving_var_init = init::ones(dtype);
+    VarptrT moving_mean = moving_mean_init(input->shape(), "moving_mean");
+    VarptrT moving_var = moving_var_init(input->shape(), "moving_var");
+    if (false == training->shape().compatible_after(input->shape(), 0)) training = extend_like(training, input);
+    auto moving = [training, momentum](const VarptrT& state, std::function<ETensor(const ETensor&)> batch_stat) {
+      return [=](const ETensor& in) {
+        auto stat = batch_stat(in);
+        auto blended = add(mul(ETensor(state), momentum), mul(stat, sub(1., momentum)));
+        return if_then_else(training, stat, assign(state, blended));
+      };
+    };
+    get_mean = moving(moving_mean, batch_mean);
+    get_var = moving(moving_var, batch_var);
+  }
+  return nn::batch_normalization(input, offset, scale, eps, get_mean, get_var);
+}
 
 ETensor bind(layr::UnaryF unary, const Shape& inshape, _GENERATED_DTYPE dtype) {  // layer.yml:14-30
   ETensor input = eteq::make_variable_scalar(0, inshape, layr::input_label, dtype);

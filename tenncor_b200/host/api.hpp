@@ -116,6 +116,12 @@ layr::InitF xavier_uniform(double factor = 1, egen::_GENERATED_DTYPE dtype = ege
 layr::InitF xavier_normal(double factor = 1, egen::_GENERATED_DTYPE dtype = egen::default_dtype);
 inline layr::InitF glorot_uniform(double factor = 1, egen::_GENERATED_DTYPE dtype = egen::default_dtype) { return xavier_uniform(factor, dtype); }
 inline layr::InitF glorot_normal(double factor = 1, egen::_GENERATED_DTYPE dtype = egen::default_dtype) { return xavier_normal(factor, dtype); }
+/// normal values re-drawn (up to 5 times, then clipped) when further than 2 stddev from the mean (tenncor/layr/init.hpp:40-72)
+layr::InitF truncated_normal(double mean = 0, double stddev = 1, egen::_GENERATED_DTYPE dtype = egen::default_dtype);
+/// `gain` on the diagonal of a 2-D shape (init.yml:170-195)
+layr::InitF identity(double gain = 1, egen::_GENERATED_DTYPE dtype = egen::default_dtype);
+/// truncated normal with stddev = sqrt(factor / shape_factor(shape)); default shape factor = fanavg (init.yml:196-219)
+layr::InitF variance_scaling(double factor, std::function<double(teq::Shape)> shape_factor = {}, egen::_GENERATED_DTYPE dtype = egen::default_dtype);
 }  // namespace init
 
 // ---- nn (cfg/tenncor/nn.yml)
@@ -125,6 +131,13 @@ ETensor fully_connect(const ETensorsT& lefts, const ETensorsT& rights, const ETe
 ETensor conv2d(const ETensor& image, const ETensor& kernel, const ETensor& bias = nullptr,
                const std::pair<DimPairsT, DimPairsT>& zero_paddings = {{0, 0}, {0, 0}});
 ETensor dropout(const ETensor& input, const ETensor& drop_rate);
+/// (input - mean) / sqrt(variance + eps) * scale + offset; mean / variance default to the whole-tensor statistics (nn.yml:128-208)
+ETensor batch_normalization(const ETensor& input, ETensor offset, ETensor scale, ETensor eps, layr::UnaryF get_mean = {}, layr::UnaryF get_variance = {});
+ETensor batch_normalization(const ETensor& input, double offset = 0, double scale = 1, double eps = -1, layr::UnaryF get_mean = {},
+                            layr::UnaryF get_variance = {});
+/// 2x2 mean / max over the two ranks `dims`, stride 2, built from STRIDE + SLICE (nn.yml:209-268)
+ETensor mean_pool2d(const ETensor& arg, std::pair<teq::RankT, teq::RankT> dims = {0, 1});
+ETensor max_pool2d(const ETensor& arg, std::pair<teq::RankT, teq::RankT> dims = {0, 1});
 }  // namespace nn
 
 // ---- layer (cfg/tenncor/layer.yml)
@@ -152,6 +165,12 @@ ETensor gru(const ETensor& input, const ETensor& init_state, const ETensor& ugat
             teq::RankT seq_dim = 1);
 ETensor gru(const teq::Shape& inshape, teq::DimT hidden_dim, teq::DimT nseq, layr::InitF kernel_init = {}, layr::InitF bias_init = {},
             teq::RankT seq_dim = 1, bool with_bias = true, egen::_GENERATED_DTYPE dtype = egen::default_dtype);
+/// nn.dropout, bypassed where `training` is 0 (layer.yml:441-478)
+ETensor dropout(const ETensor& input, const ETensor& drop_rate, ETensor training = nullptr);
+/// batch normalization with optional moving statistics: with `training` given, mean / variance are the batch statistics where
+/// training != 0 and the momentum-updated moving statistics (ASSIGNed in place) elsewhere (layer.yml:479-633)
+ETensor batch_normalization(ETensor input, ETensor offset, ETensor scale, ETensor eps, ETensor training = nullptr, ETensor momentum = nullptr,
+                            layr::InitF moving_mean_init = {}, layr::InitF moving_var_init = {}, teq::RankT axis = teq::rank_cap);
 layr::RBMLayer rbm(teq::DimT nvisible, teq::DimT nhidden, layr::InitF kernel_init = {}, layr::InitF bias_init = {}, bool with_bias = true,
                    egen::_GENERATED_DTYPE dtype = egen::default_dtype);
 }  // namespace layer

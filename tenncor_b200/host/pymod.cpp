@@ -517,6 +517,16 @@ PYBIND11_MODULE(_tenncor, m) {
   ini.def("xavier_uniform", [](double f) { return InitHolder{tenncor::init::xavier_uniform(f)}; }, py::arg("factor") = 1);
   ini.def("xavier_normal", [](double f) { return InitHolder{tenncor::init::xavier_normal(f)}; }, py::arg("factor") = 1);
   ini.def("glorot_uniform", [](double f) { return InitHolder{tenncor::init::xavier_uniform(f)}; }, py::arg("factor") = 1);
+  ini.def("truncated_normal", [](double mean, double stddev) { return InitHolder{tenncor::init::truncated_normal(mean, stddev)}; }, py::arg("mean") = 0, py::arg("stddev") = 1);
+  ini.def("identity", [](double gain) { return InitHolder{tenncor::init::identity(gain)}; }, py::arg("gain") = 1);
+  ini.def("variance_scaling", [](double factor, py::object sfactor) {
+    std::function<double(Shape)> f;
+    if (!sfactor.is_none()) {
+      py::function pf = sfactor.cast<py::function>();
+      f = [pf](Shape shape) { DimsT ps = c2pshape(shape); return pf(std::vector<size_t>(ps.begin(), ps.end())).cast<double>(); };
+    }
+    return InitHolder{tenncor::init::variance_scaling(factor, f)};
+  }, py::arg("factor"), py::arg("shape_factor") = py::none());
   ini.def("glorot_normal", [](double f) { return InitHolder{tenncor::init::xavier_normal(f)}; }, py::arg("factor") = 1);
 
   auto nn = api.def_submodule("nn");
@@ -525,6 +535,15 @@ PYBIND11_MODULE(_tenncor, m) {
   nn.def("conv2d", &tenncor::nn::conv2d, py::arg("image"), py::arg("kernel"), py::arg("bias") = ETensor(),
          py::arg("zero_paddings") = std::pair<tenncor::DimPairsT, tenncor::DimPairsT>{{0, 0}, {0, 0}});
   nn.def("dropout", &tenncor::nn::dropout);
+  nn.def("batch_normalization", [](const ETensor& input, py::object offset, py::object scale, py::object eps, py::object get_mean, py::object get_variance) {
+    auto unary = [](py::object f) { return f.is_none() ? layr::UnaryF() : f.cast<layr::UnaryF>(); };
+    if (py::isinstance<py::float_>(offset) || py::isinstance<py::int_>(offset))
+      return tenncor::nn::batch_normalization(input, offset.cast<double>(), scale.cast<double>(), eps.is_none() ? -1. : eps.cast<double>(), unary(get_mean), unary(get_variance));
+    ETensor e = eps.is_none() ? eteq::make_constant_like(1e-7, input) : eps.cast<ETensor>();
+    return tenncor::nn::batch_normalization(input, offset.cast<ETensor>(), scale.cast<ETensor>(), e, unary(get_mean), unary(get_variance));
+  }, py::arg("input"), py::arg("offset") = 0., py::arg("scale") = 1., py::arg("eps") = py::none(), py::arg("get_mean") = py::none(), py::arg("get_variance") = py::none());
+  nn.def("mean_pool2d", &tenncor::nn::mean_pool2d, py::arg("arg"), py::arg("dims") = std::pair<RankT, RankT>{0, 1});
+  nn.def("max_pool2d", &tenncor::nn::max_pool2d, py::arg("arg"), py::arg("dims") = std::pair<RankT, RankT>{0, 1});
 
   auto wrap_init = [](py::object f) -> layr::InitF {
     if (f.is_none()) return layr::InitF();
@@ -570,6 +589,26 @@ PYBIND11_MODULE(_tenncor, m) {
       .def("deep_clone", &layr::RBMLayer::deep_clone)
       .def("fwd", [](layr::RBMLayer& self) { return self.fwd_; })
       .def("bwd", [](layr::RBMLayer& self) { return self.bwd_; });
+  lay.def("dropout", [](const ETensor& input, py::object drop_rate, ETensor training) {
+    ETensor rate = (py::isinstance<py::float_>(drop_rate) || py::isinstance<py::int_>(drop_rate))
+                       ? ETensor(eteq::make_variable_scalar(drop_rate.cast<double>(), Shape(), "drop_rate", (egen::_GENERATED_DTYPE)input->get_meta().type_code()))
+                       : drop_rate.cast<ETensor>();
+    return tenncor::layer::dropout(input, rate, training);
+  }, py::arg("input"), py::arg("drop_rate"), py::arg("training") = ETensor());
+  lay.def("batch_normalization", [wrap_init](ETensor input, py::object offset, py::object scale, py::object eps, ETensor training, py::object momentum,
+                                            py::object moving_mean_init, py::object moving_var_init, RankT axis) {
+    auto as_tensor = [&input](py::object o, double dflt) -> ETensor {
+      if (o.is_none()) return eteq::make_constant_like(dflt, input);
+      if (py::isinstance<py::float_>(o) || py::isinstance<py::int_>(o)) return eteq::make_constant_like(o.cast<double>(), input);
+      return o.cast<ETensor>();
+    };
+    const bool is_double = (egen::_GENERATED_DTYPE)input->get_meta().type_code() == egen::DOUBLE;
+    ETensor m = momentum.is_none() ? ETensor() : as_tensor(momentum, 0.99);
+    return tenncor::layer::batch_normalization(input, as_tensor(offset, 0), as_tensor(scale, 1),
+                                               as_tensor(eps, is_double ? std::numeric_limits<double>::epsilon() : std::numeric_limits<float>::epsilon()),
+                                               training, m, wrap_init(moving_mean_init), wrap_init(moving_var_init), axis);
+  }, py::arg("input"), py::arg("offset") = 0., py::arg("scale") = 1., py::arg("eps") = py::none(), py::arg("training") = ETensor(),
+          py::arg("momentum") = py::none(), py::arg("moving_mean_init") = py::none(), py::arg("moving_var_init") = py::none(), py::arg("axis") = teq::rank_cap);
   lay.def("rbm", [wrap_init](DimT nvisible, DimT nhidden, py::object kinit, py::object binit) {
     return tenncor::layer::rbm(nvisible, nhidden, wrap_init(kinit), wrap_init(binit));
   }, py::arg("nvisible"), py::arg("nhidden"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none());
