@@ -172,7 +172,7 @@ ETensor rand_binom_one(const ETensor& arg) {  // random.yml:22-32
 }  // namespace random
 
 // ------------------------------------------------------------------ init.yml
-static std::mt19937_64& host_rng() {
+std::mt19937_64& host_rng() {
   static std::mt19937_64 rng(0);
   return rng;
 }

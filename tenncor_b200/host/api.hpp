@@ -5,6 +5,8 @@
 #ifndef TCR_HOST_API_HPP
 #define TCR_HOST_API_HPP
 
+#include <random>
+
 #include "layr.hpp"
 
 namespace tenncor {
@@ -104,6 +106,9 @@ namespace random {
 ETensor rand_unif(const ETensor& a, const ETensor& b);
 ETensor rand_binom_one(const ETensor& arg);
 }  // namespace random
+
+/// the host generator behind the initialisers and tc.unif_gen / tc.norm_gen (global::get_generator(), seeded by tenncor::seed)
+std::mt19937_64& host_rng();
 
 // ---- init (cfg/tenncor/init.yml); host RNG = std::mt19937_64 seeded by tenncor::seed
 namespace init {

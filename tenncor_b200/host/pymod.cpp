@@ -169,6 +169,22 @@ static eteq::VarptrT as_var(const ETensor& t) {
   return v;
 }
 
+// an api.init.* initializer object or a python callable (numpy_shape, label) -> EVariable
+static layr::InitF to_initf(py::object f) {
+  if (f.is_none()) return layr::InitF();
+  if (py::isinstance<InitHolder>(f)) return f.cast<InitHolder&>().f;
+  py::function pf = f.cast<py::function>();
+  return [pf](Shape shape, std::string label) {
+    DimsT ps = c2pshape(shape);
+    return as_var(pf(std::vector<size_t>(ps.begin(), ps.end()), label).cast<ETensor>());
+  };
+}
+
+static std::string& log_level() {
+  static std::string level = "info";
+  return level;
+}
+
 #define UN(NAME, OP) api.def(NAME, [](const ETensor& x) { return tenncor::unary(egen::OP, x); }, py::arg("input"))
 #define BIN(NAME, OP)                                                                                               \
   api.def(NAME, [](const ETensor& a, const ETensor& b) { return tenncor::binary(egen::OP, a, b); });                \
@@ -352,6 +368,19 @@ PYBIND11_MODULE(_tenncor, m) {
     return trainer::apply_update(models, approx, err);
   }, py::arg("models"), py::arg("update"), py::arg("err_func"));
 
+  // ---- host random generators and logging level (eteq_ext.cpp:383-405)
+  m.def("unif_gen", [](double lower, double upper) {
+    return py::cpp_function([lower, upper]() { return std::uniform_real_distribution<double>(lower, upper)(tenncor::host_rng()); });
+  }, py::arg("lower") = 0, py::arg("upper") = 1, "Return a generator function drawing U[lower, upper) from the seeded host generator");
+  m.def("norm_gen", [](double mean, double stdev) {
+    return py::cpp_function([mean, stdev]() { return std::normal_distribution<double>(mean, stdev)(tenncor::host_rng()); });
+  }, py::arg("mean") = 0, py::arg("stdev") = 1);
+  m.def("set_log_level", [](const std::string& level) { log_level() = level; }, py::arg("level"), "Set log level (recorded; the host reports errors as exceptions)");
+  m.def("get_log_level", [] { return log_level(); });
+  m.def("variable_from_init", [](py::object init, std::vector<size_t> slist, const std::string& label) {
+    return to_initf(init)(p2cshape(slist), label);
+  }, py::arg("init"), py::arg("slist"), py::arg("label") = "", "Return labelled variable containing data created from initializer");
+
   // ---- serialization (tenncor/python/eteq_ext.cpp:408-487)
   m.def("load_from_file", [](const std::string& filename, const std::unordered_map<std::string, size_t>& key_prec) {
     return onnx::load_from_file(filename, key_prec);
@@ -387,6 +416,12 @@ PYBIND11_MODULE(_tenncor, m) {
         }
         return out;
       }, "Per-opcode calls, device ms (CUDA events), algorithmic bytes, time share and GB/s since the last reset");
+  py::class_<teq::Evaluator, teq::iEvaluator, std::shared_ptr<teq::Evaluator>>(m, "Evaluator").def(py::init<>());  // eteq_ext.cpp:205
+  py::class_<cuda::PlanEvaluator, teq::iEvaluator, std::shared_ptr<cuda::PlanEvaluator>>(m, "PlanEvaluator").def(py::init<>());
+  m.def("evaluate", [](std::shared_ptr<teq::iEvaluator> self, ETensorsT targeted, size_t max_version, ETensorsT ignored) {
+    cuda::Device device(max_version);  // iEvaluator.evaluate (eteq_ext.cpp:208-225), as a function taking the evaluator
+    self->evaluate(device, to_set(targeted), to_set(ignored));
+  }, py::arg("evaluator"), py::arg("targeted"), py::arg("max_version") = std::numeric_limits<size_t>::max(), py::arg("ignored") = ETensorsT{});
   m.def("set_eval", [](std::shared_ptr<teq::iEvaluator> eval) { teq::set_eval(std::move(eval)); },
         "Install an evaluator object in the context slot (teq::set_eval, internal/teq/evaluator.hpp:65)");
 

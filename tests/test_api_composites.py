@@ -138,3 +138,22 @@ def _accepts_list(fn, vs):
         return True
     except TypeError:
         return False
+
+
+def test_module_level_helpers():
+    """tc.unif_gen / norm_gen / variable_from_init / set_log_level / Evaluator (tenncor/python/eteq_ext.cpp:205-405, layr_ext.cpp:74-80)"""
+    tc.seed(11)
+    gen = tc.unif_gen(2.0, 3.0)
+    draws = [gen() for _ in range(200)]
+    assert min(draws) >= 2.0 and max(draws) < 3.0 and abs(np.mean(draws) - 2.5) < 0.1
+    norm = tc.norm_gen(1.0, 0.1)
+    assert abs(np.mean([norm() for _ in range(500)]) - 1.0) < 0.02
+    tc.seed(11)
+    assert [tc.unif_gen(2.0, 3.0)() for _ in range(1)] == draws[:1]  # seeded with the rest of the host state
+    v = tc.variable_from_init(tc.api.init.constants(3.5), [2, 3], "w")
+    assert v.shape() == [2, 3] and np.all(v.data() == 3.5)
+    w = tc.variable_from_init(lambda shape, label: tc.variable(np.ones(shape, dtype=np.float32) * 2, label), [4], "mine")
+    assert np.all(w.data() == 2)
+    tc.set_log_level("warn")
+    assert tc.get_log_level() == "warn"
+    assert isinstance(tc.Evaluator(), tc.iEvaluator) and isinstance(tc.PlanEvaluator(), tc.iEvaluator)
