@@ -724,40 +724,134 @@ layr::VarErrsT bbernoulli_approx(const layr::VarErrsT& assocs, double learning_r
   return assigns;
 }
 
-layr::ETensor rbm(const layr::RBMLayer& model, layr::ETensor visible, double learning_rate, double discount_factor, BErrorF err_func, size_t cdk) {  // rbm.hpp:85-165
-  if (nullptr == visible) global::fatal("cannot call cd_grad_approx with null visible");
-  if (!err_func) err_func = [](const layr::ETensor& a, const layr::ETensor& b) { return loss::mean_squared(a, b); };
-  layr::ETensor hidden = sample_v2h(model, visible);
-  layr::ETensor chain_it = hidden;
+layr::VarErrsT cd_grad_approx(CDChainIO& io, const layr::RBMLayer& model, size_t cdk, eteq::VarptrT persistent) {  // rbm.hpp:83-146
+  if (nullptr == io.visible_) global::fatal("cannot call cd_grad_approx with null visible");
+  if (nullptr == io.hidden_) io.hidden_ = sample_v2h(model, io.visible_);
+  layr::ETensor chain_it = nullptr == persistent ? io.hidden_ : layr::ETensor(persistent);
   for (size_t i = 0; i + 1 < cdk; ++i) chain_it = gibbs_hvh(model, chain_it);
-  auto visible_mean = sigmoid(model.backward_connect(chain_it));
-  auto hidden_mean = sigmoid(model.connect(visible_mean));
+  io.visible_mean_ = sigmoid(model.backward_connect(chain_it));
+  io.hidden_mean_ = sigmoid(model.connect(io.visible_mean_));
 
   std::map<std::string, eteq::VarptrT> vars;
   for (auto& var : layr::get_storage(model.fwd_)) vars.emplace(var->to_string(), var);
   for (auto& var : layr::get_storage(model.bwd_)) vars.emplace(var->to_string(), var);
 
+  auto grad_w = sub(matmul(transpose(io.visible_), io.hidden_), matmul(transpose(io.visible_mean_), io.hidden_mean_));
+  layr::VarErrsT varerrs = {{vars.at(layr::weight_label), grad_w}};
+  const std::string hid_key = "h" + layr::bias_label, vis_key = "v" + layr::bias_label;
+  if (vars.count(hid_key)) varerrs.push_back({vars.at(hid_key), reduce_mean_1d(sub(io.hidden_, io.hidden_mean_), 1)});
+  if (vars.count(vis_key)) varerrs.push_back({vars.at(vis_key), reduce_mean_1d(sub(io.visible_, io.visible_mean_), 1)});
+  if (nullptr != persistent) varerrs.push_back({persistent, gibbs_hvh(model, chain_it)});
+  return varerrs;
+}
+
+layr::ETensor rbm(const layr::RBMLayer& model, layr::ETensor visible, double learning_rate, double discount_factor, BErrorF err_func, size_t cdk) {  // rbm.hpp:148-165
+  if (!err_func) err_func = [](const layr::ETensor& a, const layr::ETensor& b) { return loss::mean_squared(a, b); };
+  CDChainIO io(visible);
+  layr::VarErrsT varerrs = cd_grad_approx(io, model, cdk);
   // the exchanged "errors" of a data-parallel RBM are the CD statistics
-  auto grad_w = sub(matmul(transpose(visible), hidden), matmul(transpose(visible_mean), hidden_mean));
-  layr::ETensorsT errs = {grad_w};
-  std::vector<eteq::VarptrT> targets = {vars.at(layr::weight_label)};
-  std::string hid_key = "h" + layr::bias_label, vis_key = "v" + layr::bias_label;
-  if (vars.count(hid_key)) {
-    errs.push_back(reduce_mean_1d(sub(hidden, hidden_mean), 1));
-    targets.push_back(vars.at(hid_key));
-  }
-  if (vars.count(vis_key)) {
-    errs.push_back(reduce_mean_1d(sub(visible, visible_mean), 1));
-    targets.push_back(vars.at(vis_key));
-  }
+  layr::ETensorsT errs;
+  for (auto& ve : varerrs) errs.push_back(ve.second);
   errs = dp::wrap_gradients(errs);
-  layr::VarErrsT varerrs;
-  for (size_t i = 0; i < errs.size(); ++i) varerrs.push_back({targets[i], errs[i]});
+  for (size_t i = 0; i < errs.size(); ++i) varerrs[i].second = errs[i];
   auto updates = bbernoulli_approx(varerrs, learning_rate, discount_factor);
   teq::OwnMapT umap;
   for (auto& u : updates) umap.emplace(u.first.get(), u.second);
-  layr::ETensor error = err_func(visible, visible_mean);
+  layr::ETensor error = err_func(io.visible_, io.visible_mean_);
   return layr::trail(error, umap);
+}
+
+// ---------------------------------------------------------------- DBN (tenncor/trainer/dbn.hpp)
+static double scalar_of(const layr::ETensor& t) {
+  const void* data = t->device().data();
+  if (nullptr == data) global::fatalf("%s has no data", t->to_string().c_str());
+  double out = 0;
+  type_convert(&out, DOUBLE, data, (_GENERATED_DTYPE)t->get_meta().type_code(), 1);
+  return out;
+}
+
+DBNTrainer::DBNTrainer(const std::vector<layr::RBMLayer>& rbms, layr::ETensor dense, RankT softmax_dim, DimT batch_size, double pretrain_lr,
+                       double train_lr, size_t cdk, double l2_reg, double lr_scaling)
+    : nlayers_(rbms.size()), batch_size_(batch_size) {
+  if (rbms.empty()) global::fatal("cannot train a deep belief network without rbm layers");
+  input_size_ = layr::get_input(rbms.front().fwd_)->shape().at(0);
+  output_size_ = dense->shape().at(0);
+  const auto dtype = (_GENERATED_DTYPE)dense->get_meta().type_code();
+  trainx_ = eteq::make_variable_scalar(0, Shape({(DimT)input_size_, batch_size}), "trainx", dtype);
+  trainy_ = eteq::make_variable_scalar(0, Shape({(DimT)output_size_, batch_size}), "trainy", dtype);
+
+  // general rbm sampling: every layer feeds on a sample of the one below
+  sample_pipes_.push_back(trainx_);
+  for (size_t i = 0; i < nlayers_; ++i) sample_pipes_.push_back(sample_v2h(rbms[i], sample_pipes_[i]));
+
+  // layer-wise rbm reconstruction
+  for (size_t i = 0; i < nlayers_; ++i) {
+    const layr::RBMLayer& layer = rbms[i];
+    const layr::ETensor& rx = sample_pipes_[i];
+    teq::TensSetT to_learn;
+    for (auto& var : layr::get_storage(layer.fwd_)) to_learn.emplace(var.get());
+    for (auto& var : layr::get_storage(layer.bwd_)) to_learn.emplace(var.get());
+    CDChainIO io(rx, sample_pipes_[i + 1]);
+    layr::VarErrsT varerrs = cd_grad_approx(io, layer, cdk);
+    layr::ETensorsT assigns;
+    for (auto& varerr : varerrs)  // weights and biases move by the learning rate; anything else (a persistent chain) is replaced
+      assigns.push_back(to_learn.count(varerr.first.get()) ? assign_add(varerr.first, mul(pretrain_lr, varerr.second)) : assign(varerr.first, varerr.second));
+    rupdates_.push_back(assigns);
+    auto vhv = sigmoid(layer.backward_connect(sigmoid(layer.connect(rx))));
+    rcosts_.push_back(neg(reduce_mean(reduce_sum_1d(add(mul(rx, log(vhv)), mul(sub(1., rx), log(sub(1., vhv)))), 0))));
+  }
+
+  // logistic layer on the top-level samples
+  auto contents = layr::get_storage(dense);
+  if (contents.size() < 2) global::fatal("the dbn's dense layer needs a weight and a bias");
+  eteq::VarptrT w = contents[0], b = contents[1];
+  auto final_out = softmax(layr::connect(dense, sample_pipes_.back()), softmax_dim, 1);
+  auto diff = sub(layr::ETensor(trainy_), final_out);
+  auto l2_regularized = sub(matmul(transpose(sample_pipes_.back()), diff), mul(l2_reg, layr::ETensor(w)));
+  Shape wshape = w->shape(), bshape = b->shape();
+  auto tlr = eteq::make_variable_scalar(train_lr, Shape(), "learning_rate", dtype);
+  auto dw = mul(extend(layr::ETensor(tlr), 0, DimsT(wshape.begin(), wshape.end())), l2_regularized);
+  auto db = mul(extend(layr::ETensor(tlr), 0, DimsT(bshape.begin(), bshape.end())), reduce_mean_1d(diff, 1));
+  auto dtrain_lr = mul(layr::ETensor(tlr), lr_scaling);
+  tupdate_ = assign(tlr, identity(dtrain_lr, {assign_add(w, dw), assign_add(b, db)}));
+  tcost_ = neg(reduce_mean(reduce_sum_1d(add(mul(layr::ETensor(trainy_), log(final_out)), mul(sub(1., layr::ETensor(trainy_)), log(sub(1., final_out)))), 0)));
+}
+
+void DBNTrainer::pretrain(const void* train_in, _GENERATED_DTYPE dtype, size_t nepochs, std::function<void(size_t, size_t)> logger) {
+  trainx_->assign(train_in, dtype, trainx_->shape());
+  for (size_t i = 0; i < nlayers_; ++i) {
+    // the layer's input sample is frozen (ignored = read as data) while its RBM learns to reconstruct it
+    teq::TensSetT ignore = {sample_pipes_[i].get()};
+    for (size_t epoch = 0; epoch < nepochs; ++epoch) {
+      eteq::run(rupdates_[i], ignore);
+      if (logger) logger(epoch, i);
+    }
+    if (i + 1 < nlayers_) eteq::run({sample_pipes_[i + 1]}, ignore);
+  }
+}
+
+void DBNTrainer::finetune(const void* train_in, const void* train_out, _GENERATED_DTYPE dtype, size_t nepochs, std::function<void(size_t)> logger) {
+  trainx_->assign(train_in, dtype, trainx_->shape());
+  trainy_->assign(train_out, dtype, trainy_->shape());
+  layr::ETensor top = sample_pipes_.back();
+  if (nullptr == sample_pipes_[nlayers_ - 1]->device().device_data() && nlayers_ > 1)
+    global::fatal("finetune needs the samples pretrain leaves behind: call pretrain first");
+  eteq::run({top}, nlayers_ > 1 ? teq::TensSetT{sample_pipes_[nlayers_ - 1].get()} : teq::TensSetT{});
+  for (size_t epoch = 0; epoch < nepochs; ++epoch) {
+    eteq::run({tupdate_}, {top.get()});  // train the logistic layer on the frozen top-level sample
+    if (logger) logger(epoch);
+  }
+}
+
+double DBNTrainer::reconstruction_cost(size_t layer) {
+  if (layer >= rcosts_.size()) global::fatalf("layer %d out of range (%d rbm layers)", (int)layer, (int)rcosts_.size());
+  eteq::run({rcosts_[layer]});
+  return scalar_of(rcosts_[layer]);
+}
+
+double DBNTrainer::training_cost() {
+  eteq::run({tcost_});
+  return scalar_of(tcost_);
 }
 
 }  // namespace trainer

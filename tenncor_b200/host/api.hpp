@@ -219,9 +219,38 @@ layr::VarErrsT bbernoulli_approx(const layr::VarErrsT& assocs, double learning_r
 layr::ETensor sample_v2h(const layr::RBMLayer& model, layr::ETensor vis);
 layr::ETensor sample_h2v(const layr::RBMLayer& model, layr::ETensor hid);
 layr::ETensor gibbs_hvh(const layr::RBMLayer& model, layr::ETensor hid);
+/// contrastive-divergence chain: visible (given) -> hidden sample -> k-1 Gibbs steps -> visible / hidden means (rbm.hpp:65-81)
+struct CDChainIO final {
+  explicit CDChainIO(layr::ETensor visible, layr::ETensor hidden = nullptr) : visible_(std::move(visible)), hidden_(std::move(hidden)) {}
+  layr::ETensor visible_, hidden_, visible_mean_, hidden_mean_;
+};
+/// CD-k statistics standing in for back-propagated gradients: (weight, <v h> - <v' h'>), (hbias, mean(h - h')), (vbias, mean(v - v'))
+/// and, with a persistent chain, (persistent, next chain state) (rbm.hpp:83-146)
+layr::VarErrsT cd_grad_approx(CDChainIO& io, const layr::RBMLayer& model, size_t cdk = 1, eteq::VarptrT persistent = nullptr);
 using BErrorF = std::function<layr::ETensor(const layr::ETensor&, const layr::ETensor&)>;
 layr::ETensor rbm(const layr::RBMLayer& model, layr::ETensor visible, double learning_rate, double discount_factor,
                   BErrorF err_func = {}, size_t cdk = 1);
+
+
+/// Deep belief network: greedy layer-wise CD-k pre-training of a stack of RBMs, then a softmax (logistic) layer trained on the
+/// top-level samples with a decaying learning rate (tenncor/trainer/dbn.hpp:13-229; demo/dbn_demo.py:60-118).
+struct DBNTrainer final {
+  DBNTrainer(const std::vector<layr::RBMLayer>& rbms, layr::ETensor dense, teq::RankT softmax_dim, teq::DimT batch_size, double pretrain_lr = 0.1,
+             double train_lr = 0.1, size_t cdk = 10, double l2_reg = 0., double lr_scaling = 0.95);
+  /// `train_in`: batch_size x input_size elements of `dtype`, row-major (the reference's ShapedArr)
+  void pretrain(const void* train_in, egen::_GENERATED_DTYPE dtype, size_t nepochs = 100, std::function<void(size_t, size_t)> logger = {});
+  void finetune(const void* train_in, const void* train_out, egen::_GENERATED_DTYPE dtype, size_t nepochs = 100, std::function<void(size_t)> logger = {});
+  double reconstruction_cost(size_t layer);
+  double training_cost();
+
+  size_t nlayers_, input_size_, output_size_, batch_size_;
+  eteq::VarptrT trainx_, trainy_;
+  layr::ETensorsT sample_pipes_;
+  std::vector<layr::ETensorsT> rupdates_;
+  layr::ETensor tupdate_;
+  layr::ETensorsT rcosts_;
+  layr::ETensor tcost_;
+};
 
 }  // namespace trainer
 

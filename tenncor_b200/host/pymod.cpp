@@ -619,6 +619,7 @@ PYBIND11_MODULE(_tenncor, m) {
     return tenncor::layer::rnn(input, init_state, cell, activation, seq_dim);
   }, py::arg("input"), py::arg("init_state"), py::arg("cell"), py::arg("activation"), py::arg("seq_dim") = 1);
   py::class_<layr::RBMLayer>(m, "RBMLayer")
+      .def(py::init([](ETensor fwd, ETensor bwd) { return layr::RBMLayer{fwd, bwd}; }), py::arg("fwd"), py::arg("bwd"))
       .def("connect", &layr::RBMLayer::connect)
       .def("backward_connect", &layr::RBMLayer::backward_connect)
       .def("deep_clone", &layr::RBMLayer::deep_clone)
@@ -676,6 +677,40 @@ PYBIND11_MODULE(_tenncor, m) {
     return tenncor::approx::rms_momentum(e, to_vars(v), lr, discount, eps, f);
   }, py::arg("error"), py::arg("variables"), py::arg("learning_rate") = 0.5, py::arg("discount_factor") = 0.99, py::arg("epsilon") = feps,
           py::arg("apply") = py::none());
+
+  // trainer::DBNTrainer (tenncor/python/layr_ext.cpp:30-70)
+  py::class_<trainer::DBNTrainer>(m, "DBNTrainer")
+      .def(py::init<const std::vector<layr::RBMLayer>&, ETensor, RankT, DimT, double, double, size_t, double, double>(), py::arg("rbms"), py::arg("dense"),
+           py::arg("softmax_dim"), py::arg("batch_size"), py::arg("pretrain_lr") = 0.1, py::arg("train_lr") = 0.1, py::arg("cdk") = 10,
+           py::arg("l2_reg") = 0., py::arg("lr_scaling") = 0.95)
+      .def("pretrain", [](trainer::DBNTrainer& self, py::array x, size_t nepochs, py::object logger) {
+        Shape shape;
+        egen::_GENERATED_DTYPE dtype;
+        py::array arr = normalise(x, shape, dtype);
+        if (shape.n_elems() != self.trainx_->shape().n_elems()) global::fatalf("pretrain input has %d elements, the trainer expects %d", (int)shape.n_elems(), (int)self.trainx_->shape().n_elems());
+        std::function<void(size_t, size_t)> log;
+        if (!logger.is_none()) log = [logger](size_t epoch, size_t layer) { logger(epoch, layer); };
+        self.pretrain(arr.data(), dtype, nepochs, log);
+      }, py::arg("x"), py::arg("nepochs") = 100, py::arg("logger") = py::none())
+      .def("finetune", [](trainer::DBNTrainer& self, py::array x, py::array y, size_t nepochs, py::object logger) {
+        Shape xs, ys;
+        egen::_GENERATED_DTYPE xd, yd;
+        py::array xa = normalise(x, xs, xd), ya = normalise(y, ys, yd);
+        if (xd != yd) global::fatal("finetune input and labels need the same dtype");
+        if (xs.n_elems() != self.trainx_->shape().n_elems() || ys.n_elems() != self.trainy_->shape().n_elems()) global::fatal("finetune data does not match the trainer's batch shape");
+        std::function<void(size_t)> log;
+        if (!logger.is_none()) log = [logger](size_t epoch) { logger(epoch); };
+        self.finetune(xa.data(), ya.data(), xd, nepochs, log);
+      }, py::arg("x"), py::arg("y"), py::arg("nepochs") = 100, py::arg("logger") = py::none())
+      .def("reconstruction_cost", &trainer::DBNTrainer::reconstruction_cost)
+      .def("training_cost", &trainer::DBNTrainer::training_cost)
+      .def("sample_pipes", [](trainer::DBNTrainer& self) { return self.sample_pipes_; })
+      .def("update_graphs", [](trainer::DBNTrainer& self) {
+        ETensorsT out;
+        for (auto& layer : self.rupdates_) out.insert(out.end(), layer.begin(), layer.end());
+        out.push_back(self.tupdate_);
+        return out;
+      }, "every per-layer CD update followed by the logistic-layer update (for inspection / describe_plan)");
 
   m.def("rbm_train", [](const layr::RBMLayer& model, ETensor visible, double lr, double discount, size_t cdk) {
     return trainer::rbm(model, visible, lr, discount, {}, cdk);
