@@ -45,8 +45,8 @@ def test_dbn_demo_learns_its_toy_problem(gpu):
     rbms, dense, model, trainer = build(cdk=1)
     seen = []
     c0 = [trainer.reconstruction_cost(0), trainer.reconstruction_cost(1)]
-    trainer.pretrain(X, nepochs=300, logger=lambda epoch, layer: seen.append((layer, epoch)))
-    assert seen[0] == (0, 0) and seen[-1] == (1, 299) and len(seen) == 600
+    trainer.pretrain(X, nepochs=1000, logger=lambda epoch, layer: seen.append((layer, epoch)))  # the demo's defaults: 1000 / 200 epochs, CD-1
+    assert seen[0] == (0, 0) and seen[-1] == (1, 999) and len(seen) == 2000
     c1 = [trainer.reconstruction_cost(0), trainer.reconstruction_cost(1)]
     assert np.isfinite(c0 + c1).all() and c1[0] < c0[0], (c0, c1)  # the first RBM reconstructs its input better than at the start
     t0 = trainer.training_cost()
