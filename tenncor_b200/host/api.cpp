@@ -783,6 +783,10 @@ DBNTrainer::DBNTrainer(const std::vector<layr::RBMLayer>& rbms, layr::ETensor de
   // general rbm sampling: every layer feeds on a sample of the one below
   sample_pipes_.push_back(trainx_);
   for (size_t i = 0; i < nlayers_; ++i) sample_pipes_.push_back(sample_v2h(rbms[i], sample_pipes_[i]));
+  // the samples are evaluated once and then read as data by many later evaluations (pretrain / finetune name them in `ignored`):
+  // their buffers must not expire with their consumers' reads — the reference's cache_init() (dbn.hpp:138-144,188-191)
+  for (size_t i = 1; i < sample_pipes_.size(); ++i)
+    if (auto op = dynamic_cast<cuda::DevOp*>(&sample_pipes_[i]->device())) op->pin();
 
   // layer-wise rbm reconstruction
   for (size_t i = 0; i < nlayers_; ++i) {

@@ -41,7 +41,10 @@ RTMemptrT get_runtime();
 struct Expirable final {
   ~Expirable() { expire(); }
   void expire();
-  void tick() { if (ttl_ > 0 && 0 == (--ttl_)) expire(); }
+  void tick() { if (!pinned_ && ttl_ > 0 && 0 == (--ttl_)) expire(); }
+  /// keep the buffer for the holder's lifetime once it exists (the reference's Functor::cache_init swaps in a permanent holder,
+  /// tenncor/eteq/functor.hpp:231-243, internal/eigen/device.hpp:41-101): consumer reads no longer count it down
+  void pin() { pinned_ = true; }
   bool is_expired() const { return 0 == ttl_; }
   size_t get_ttl() const { return ttl_; }
   void* get() { return ptr_; }
@@ -51,6 +54,7 @@ struct Expirable final {
 
  private:
   size_t ttl_ = 0;
+  bool pinned_ = false;
   void* ptr_ = nullptr;
   size_t size_ = 0;
   RTMemptrT allocator_ = nullptr;
@@ -178,6 +182,8 @@ struct DevOp final : public eigen::iEigen {
   void mark_device_dirty() override { mirror_.invalidate(); }
   /// bind an externally produced result (used by the plan executor for target nodes)
   void* ensure_buffer(size_t ttl, eigen::RTMemptrT& runtime);
+  /// Functor::cache_init: the result outlives its consumers' reads (evaluations that name this node in their `ignored` set read it as data)
+  void pin() { data_.pin(); }
   /// run this op's kernel(s) on explicit buffers (plan executor: buffers come from the plan)
   void launch_with(void* out, const std::vector<const void*>& in) const { launch_(out, in); }
   size_t out_bytes() const { return bytes_; }

@@ -40,8 +40,16 @@ def test_trainer_graphs(built):
     assert again.connect(pipes[0]).shape() == [7, 3] and again.backward_connect(pipes[1]).shape() == [7, 6]
 
 
+@pytest.fixture
+def evaluator(request):
+    tc.set_evaluator(request.param)
+    yield request.param
+    tc.set_evaluator("plan")
+
+
 @pytest.mark.gpu
-def test_dbn_demo_learns_its_toy_problem(gpu):
+@pytest.mark.parametrize("evaluator", ["node", "plan"], indirect=True)
+def test_dbn_demo_learns_its_toy_problem(gpu, evaluator):
     rbms, dense, model, trainer = build(cdk=1)
     seen = []
     c0 = [trainer.reconstruction_cost(0), trainer.reconstruction_cost(1)]
