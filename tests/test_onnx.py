@@ -241,3 +241,35 @@ def test_pretrained_gd_model_solves_the_gd_demo_task():
     untrained = configs.mlp(10, 9, 5, 3).model.connect(testin)
     err = [float(np.mean(np.abs(o.reshape(200, 5) - y))) for o in _oracle_eval([pretrained, untrained])]
     assert err[0] < 0.05 and err[1] > 3 * err[0], err
+
+
+def test_conv_and_rbm_models_round_trip(tmp_path):
+    """the other layer kinds the demos save: a conv2d stack (_CONV_LAYER) and an RBM's two halves saved together under keys and
+    rebuilt as tc.RBMLayer(*tc.load_from_file(...)) (demo/rbm_demo.py:75-78,177-180)"""
+    cfg = configs.cnn()
+    rng = np.random.default_rng(4)
+    probe = tc.variable(rng.random(cfg.feeds["x"].shape(), dtype=np.float32), "probe")
+    want = _oracle_eval([cfg.model.connect(probe)])[0]
+    path = str(tmp_path / "cnn.onnx")
+    assert tc.save_to_file(path, [cfg.model])
+    loaded = tc.load_from_file(path)[0]
+    np.testing.assert_array_equal(_oracle_eval([loaded.connect(probe)])[0], want)
+    assert len(loaded.get_storage()) == 4  # two kernels, two biases
+    # the reloaded conv2d still lowers to the tensor-core form: the composite's structure survived the file
+    assert sum(s.startswith("CONV2D im2col+GEMM") for s in tc.describe_plan([loaded.connect(probe)])) == 2
+
+    rbm = tc.api.layer.rbm(12, 5)
+    vis = tc.variable((rng.random((3, 12)) < 0.5).astype(np.float32), "vis")
+    hid = tc.variable((rng.random((3, 5)) < 0.5).astype(np.float32), "hid")
+    want_f, want_b = _oracle_eval([rbm.connect(vis), rbm.backward_connect(hid)])
+    path = str(tmp_path / "rbm.onnx")
+    assert tc.save_to_file(path, [rbm.fwd(), rbm.bwd()], keys={"fwd": rbm.fwd(), "bwd": rbm.bwd()})
+    again = tc.RBMLayer(*tc.load_from_file(path, key_prec={"fwd": 0, "bwd": 1}))
+    got_f, got_b = _oracle_eval([again.connect(vis), again.backward_connect(hid)])
+    np.testing.assert_array_equal(got_f, want_f)
+    np.testing.assert_array_equal(got_b, want_b)
+    # the weight is ONE variable shared by both halves, in the file as in memory
+    assert len(again.fwd().get_storage()) == len(rbm.fwd().get_storage())
+    weight = [v for v in again.fwd().get_storage() if v.shape() == [12, 5]][0]
+    weight.assign(np.zeros((12, 5), dtype=np.float32))
+    np.testing.assert_array_equal(_oracle_eval([again.backward_connect(hid)])[0], np.zeros(3 * 12))  # bwd sees fwd's zeroed weight (vbias starts at 0)
