@@ -1,2 +1,4 @@
+# the round's validation recipe on a GPU box: /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/_gpu_job.sh'
 set +e
-timeout 200 python -m pytest tests/test_dbn.py -m gpu -q 2>&1 | tail -30
+mkdir -p gpurun_out
+timeout 700 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/r1_gpu_tests.log
