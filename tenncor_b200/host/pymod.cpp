@@ -368,6 +368,52 @@ PYBIND11_MODULE(_tenncor, m) {
     return trainer::apply_update(models, approx, err);
   }, py::arg("models"), py::arg("update"), py::arg("err_func"));
 
+  // ---- the generated egen surface, for the host-logic tests that mirror internal/eigen/test/test_shaper.cpp / test_funcopt.cpp
+  auto eg = m.def_submodule("egen", "ShapeParser / TypeParser / FuncOpt of the opcode table (cfg/ops.yml)");
+  auto to_maps = [](const py::dict& d) {
+    // values are packed the way eigen::Packer packs them (internal/eigen/packattr.hpp): the key decides the attribute kind
+    marsh::Maps attrs;
+    for (auto kv : d) {
+      const std::string key = kv.first.cast<std::string>();
+      py::handle v = kv.second;
+      if (key == eigen::dimpairs_key) eigen::pack_attr(attrs, v.cast<eigen::PairVecT<DimT>>());
+      else if (key == eigen::rankpairs_key) eigen::pack_attr(attrs, v.cast<eigen::PairVecT<RankT>>());
+      else if (key == eigen::dims_key) eigen::pack_attr(attrs, v.cast<DimsT>());
+      else if (key == eigen::ranks_key) eigen::pack_attr(attrs, v.cast<teq::RanksT>());
+      else if (key == eigen::rankset_key) eigen::pack_attr(attrs, v.cast<std::set<RankT>>());
+      else if (key == eigen::rank_key) eigen::pack_attr(attrs, v.cast<RankT>());
+      else if (key == eigen::shape_key) eigen::pack_attr(attrs, Shape(v.cast<DimsT>()));
+      else if (key == eigen::dtype_key) eigen::pack_attr(attrs, egen::get_type(v.cast<std::string>()));
+      else if (key == eigen::tensor_key) eigen::pack_attr(attrs, v.cast<ETensor>());
+      else global::fatalf("unknown attribute key `%s`", key.c_str());
+    }
+    return attrs;
+  };
+  eg.def("shape_parse", [to_maps](const std::string& opname, const py::dict& attrs, const std::vector<DimsT>& shapes) {
+    teq::ShapesT ss;
+    for (auto& sh : shapes) ss.push_back(Shape(sh));
+    marsh::Maps m = to_maps(attrs);
+    Shape out = eigen::shape_parse(egen::get_op(opname), m, ss);
+    return std::vector<size_t>(out.begin(), out.end());
+  }, py::arg("opname"), py::arg("attrs"), py::arg("shapes"), "teq shape (rank 0 first, padded to 8) the opcode's shape rule gives");
+  eg.def("type_parse", [to_maps](const std::string& opname, const py::dict& attrs, const std::vector<std::string>& dtypes) {
+    eigen::DTypesT ds;
+    for (auto& d : dtypes) ds.push_back(egen::get_type(d));
+    marsh::Maps m = to_maps(attrs);
+    return egen::name_type(eigen::type_parse(egen::get_op(opname), m, ds));
+  }, py::arg("opname"), py::arg("attrs"), py::arg("dtypes"));
+  eg.def("func_opt", [to_maps](const std::string& opname, const py::dict& attrs, const ETensorsT& args, const std::string& out_dtype) {
+    marsh::Maps m = to_maps(attrs);
+    return eigen::func_opt(egen::get_op(opname), egen::get_type(out_dtype), m, args);
+  }, py::arg("opname"), py::arg("attrs"), py::arg("args"), py::arg("out_dtype") = "DOUBLE", "true when the functor would be redundant (make_funcattr returns its first argument)");
+  eg.def("is_commutative", [](const std::string& opname) { return egen::is_commutative(egen::get_op(opname)); });
+  eg.def("is_idempotent", [](const std::string& opname) { return egen::is_idempotent(egen::get_op(opname)); });
+  eg.def("opcodes", [] {
+    std::vector<std::string> out;
+    for (int op = 1; op < egen::_N_GENERATED_OPCODES; ++op) out.push_back(egen::name_op((egen::_GENERATED_OPCODE)op));
+    return out;
+  });
+
   // ---- host random generators and logging level (eteq_ext.cpp:383-405)
   m.def("unif_gen", [](double lower, double upper) {
     return py::cpp_function([lower, upper]() { return std::uniform_real_distribution<double>(lower, upper)(tenncor::host_rng()); });
