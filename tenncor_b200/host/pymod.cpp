@@ -217,6 +217,8 @@ PYBIND11_MODULE(_tenncor, m) {
         eteq::run({self}, to_set(ignored), max_version);
       }, py::arg("ignored") = ETensorsT{}, py::arg("max_version") = std::numeric_limits<size_t>::max(),
       "Evaluate on the device; the result stays in HBM (no host copy)")
+      .def("label", [](const iTensor& self) { return self.to_string(); }, "iTensor::to_string: a leaf's label / constant value, a functor's opcode name")
+      .def("is_leaf", [](const iTensor& self) { return nullptr == dynamic_cast<const iFunctor*>(&self); })
       .def("device_ptr", [](iTensor& self) { return (uintptr_t)self.device().device_data(); })
       .def_property_readonly("__cuda_array_interface__", [](iTensor& self) {
         // zero-copy view of the resident HBM buffer for torch.as_tensor / cupy.asarray (CUDA Array Interface v3);
@@ -406,6 +408,18 @@ PYBIND11_MODULE(_tenncor, m) {
     marsh::Maps m = to_maps(attrs);
     return eigen::func_opt(egen::get_op(opname), egen::get_type(out_dtype), m, args);
   }, py::arg("opname"), py::arg("attrs"), py::arg("args"), py::arg("out_dtype") = "DOUBLE", "true when the functor would be redundant (make_funcattr returns its first argument)");
+  eg.def("make_functor", [to_maps](const std::string& opname, const ETensorsT& args, const py::dict& attrs) {
+    marsh::Maps m = to_maps(attrs);
+    return eteq::make_funcattr(egen::get_op(opname), args, m);  // eteq::make_functor with the attributes eigen::Packer would pack
+  }, py::arg("opname"), py::arg("args"), py::arg("attrs") = py::dict());
+  eg.def("lderive", [](const ETensor& op, const ETensor& supgrad, size_t arg_idx) {
+    auto f = std::dynamic_pointer_cast<teq::iFunctor>(op);
+    if (nullptr == f) global::fatalf("%s is not a functor", op->to_string().c_str());
+    return eteq::DerivativeFuncs().lderive(f, supgrad, arg_idx);
+  }, py::arg("op"), py::arg("supgrad"), py::arg("arg_idx"), "DerivativeFuncs::lderive (tenncor/eteq/backprop.hpp:58-545): the local gradient rule of one functor");
+  eg.def("const_zero", [](ETensor like) { return eteq::DerivativeFuncs().get_const_zero(*like); });
+  eg.def("const_one", [](ETensor like) { return eteq::DerivativeFuncs().get_const_one(*like); });
+  eg.def("grad_add", [](const ETensorsT& elems) { return eteq::DerivativeFuncs().add(elems); });
   eg.def("is_commutative", [](const std::string& opname) { return egen::is_commutative(egen::get_op(opname)); });
   eg.def("is_idempotent", [](const std::string& opname) { return egen::is_idempotent(egen::get_op(opname)); });
   eg.def("opcodes", [] {

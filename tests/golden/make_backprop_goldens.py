@@ -1,0 +1,42 @@
+"""Extracts the expected derivative graphs of tenncor/eteq/test/test_backprop.cpp (EXPECT_GRAPHEQ string literals, one per
+TEST(BACKPROP, Name)) into tests/golden/backprop_goldens.json. Only the literals are copied; tests/test_backprop_golden.py
+rebuilds each operand set through our own host and prints our graph in the same PrettyEquation format.
+Run in the build container:  python tests/golden/make_backprop_goldens.py"""
+import json
+import os
+import re
+
+REF = "/root/reference/tenncor/eteq/test/test_backprop.cpp"
+
+
+def main():
+    src = open(REF).read()
+    out = {}
+    for m in re.finditer(r"TEST\(BACKPROP, (\w+)\)\n\{(.*?)\n\}\n", src, re.S):
+        name, body = m.group(1), m.group(2)
+        graphs = []
+        # runs of adjacent C string literals (only whitespace between them); a run that starts with "(" is one expected graph
+        lits = [(l.start(), l.end(), l.group(1)) for l in re.finditer(r'"((?:[^"\\]|\\.)*)"', body)]
+        run = []
+        for i, (a, b, text) in enumerate(lits):
+            if run and body[lits[i - 1][1]:a].strip() == "":
+                run.append(text)
+            else:
+                if run:
+                    graphs.append(run)
+                run = [text]
+        if run:
+            graphs.append(run)
+        graphs = ["".join(r).replace("\\\\", "\\").replace("\\n", "\n") for r in graphs]
+        graphs = [g for g in graphs if g.startswith("(") and g.endswith("\n")]
+        if graphs:
+            line = src[:m.start()].count("\n") + 1
+            out[name] = {"cite": "tenncor/eteq/test/test_backprop.cpp:%d" % line, "graphs": graphs}
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "backprop_goldens.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+    print({k: len(v["graphs"]) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
