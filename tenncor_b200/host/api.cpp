@@ -598,6 +598,12 @@ static ETensorsT ders_of(const ETensor& error, const eteq::VarptrsT& variables) 
 
 static _GENERATED_DTYPE dtype_of(const ETensor& t) { return (_GENERATED_DTYPE)t->get_meta().type_code(); }
 
+// The reference's optimizers are templates on the element type T and their hyper-parameters are of type T: a float model holds
+// decay = 0.999f, and `T nodecay = 1. - decay` is 0.000999987, not 0.001 (tenncor/test/test_approx.cpp:388-482 prints it). Scalar
+// arithmetic on hyper-parameters therefore happens here in the element type too.
+static double in_elem(double v, _GENERATED_DTYPE dt) { return dt == FLOAT ? (double)(float)v : v; }
+static double one_minus(double v, _GENERATED_DTYPE dt) { return in_elem(1. - in_elem(v, dt), dt); }
+
 layr::VarErrsT sgd(const ETensor& error, const eteq::VarptrsT& variables, double learning_rate, layr::UnaryF apply) {  // approx.yml:12-55
   layr::VarErrsT out;
   auto ders = ders_of(error, variables);
@@ -624,12 +630,12 @@ layr::VarErrsT adagrad(const ETensor& error, const eteq::VarptrsT& variables, do
 }
 
 layr::VarErrsT adam(const ETensor& error, const eteq::VarptrsT& variables, double step_rate, double decay1, double decay2, double epsilon) {  // approx.yml:96-170
-  double nodecay1 = 1. - decay1, nodecay2 = 1. - decay2;
   layr::VarErrsT out;
   auto ders = ders_of(error, variables);
   for (size_t i = 0, n = variables.size(); i < n; ++i) {
     auto der = ders[i];
     auto dt = dtype_of(der);
+    const double nodecay1 = one_minus(decay1, dt), nodecay2 = one_minus(decay2, dt);  // T nodecay = 1. - decay
     auto m = eteq::make_variable_scalar(0, der->shape(), "moment1", dt);
     auto v = eteq::make_variable_scalar(0, der->shape(), "moment2", dt);
     auto t = eteq::make_variable_scalar(0, der->shape(), "t", dt);
@@ -652,8 +658,8 @@ layr::VarErrsT adadelta(const ETensor& error, const eteq::VarptrsT& variables, d
   for (size_t i = 0, n = variables.size(); i < n; ++i) {
     auto der = ders[i];
     if (apply) der = apply(der);
-    double nodecay = 1. - decay;
     auto dt = dtype_of(der);
+    const double nodecay = one_minus(decay, dt);  // T nodecay = 1. - decay (approx.yml:233)
     VarptrT msg = eteq::make_variable_scalar(0, der->shape(), "ex_sqr_grad", dt);
     VarptrT msd = eteq::make_variable_scalar(0, der->shape(), "ex_sqr_delx", dt);
     auto msg_next = assign(msg, add(mul(decay, ETensor(msg)), mul(nodecay, square(der))));
@@ -672,7 +678,7 @@ layr::VarErrsT rms_momentum(const ETensor& error, const eteq::VarptrsT& variable
     auto der = ders[i];
     if (apply) der = apply(der);
     VarptrT momentum = eteq::make_variable_scalar(1, der->shape(), "momentum", dtype_of(der));
-    auto update = assign(momentum, add(mul(discount_factor, ETensor(momentum)), mul(1 - discount_factor, square(der))));
+    auto update = assign(momentum, add(mul(discount_factor, ETensor(momentum)), mul(one_minus(discount_factor, dtype_of(der)), square(der))));
     // assign momentums before leaves
     out.push_back({variables[i], assign_sub(variables[i], div(mul(der, learning_rate), add(sqrt(update), epsilon)))});
   }
@@ -717,8 +723,13 @@ layr::VarErrsT bbernoulli_approx(const layr::VarErrsT& assocs, double learning_r
     auto err = verrs.second;
     auto slist = teq::narrow_shape(err->shape());
     teq::DimT shape_factor = slist.empty() ? 1 : slist.back();
-    auto momentum = eteq::make_variable_scalar(0, err->shape(), "momentum", (egen::_GENERATED_DTYPE)err->get_meta().type_code());
-    auto momentum_next = add(mul(discount_factor, layr::ETensor(momentum)), mul(learning_rate * (1 - discount_factor) / shape_factor, err));
+    const auto dt = (egen::_GENERATED_DTYPE)err->get_meta().type_code();
+    auto momentum = eteq::make_variable_scalar(0, err->shape(), "momentum", dt);
+    // (learning_rate * (1 - discount_factor) / shape_factor) with T-typed hyper-parameters: every step rounds to T (rbm.hpp:55-56)
+    using tenncor::approx::in_elem;
+    using tenncor::approx::one_minus;
+    const double step = in_elem(in_elem(in_elem(learning_rate, dt) * one_minus(discount_factor, dt), dt) / in_elem((double)shape_factor, dt), dt);
+    auto momentum_next = add(mul(discount_factor, layr::ETensor(momentum)), mul(step, err));
     assigns.push_back({verrs.first, assign_add(verrs.first, assign(momentum, momentum_next))});
   }
   return assigns;

@@ -219,6 +219,16 @@ PYBIND11_MODULE(_tenncor, m) {
       "Evaluate on the device; the result stays in HBM (no host copy)")
       .def("label", [](const iTensor& self) { return self.to_string(); }, "iTensor::to_string: a leaf's label / constant value, a functor's opcode name")
       .def("is_leaf", [](const iTensor& self) { return nullptr == dynamic_cast<const iFunctor*>(&self); })
+      .def("usage", [](const iTensor& self) -> std::string {  // teq::get_usage_name (internal/teq/src/ileaf.cpp:12-35); "" for functors
+        auto leaf = dynamic_cast<const teq::iLeaf*>(&self);
+        if (nullptr == leaf) return "";
+        switch (leaf->get_usage()) {
+          case teq::IMMUTABLE: return "constant";
+          case teq::VARUSAGE: return "variable";
+          case teq::PLACEHOLDER: return "placeholder";
+          default: return "unknown";
+        }
+      })
       .def("device_ptr", [](iTensor& self) { return (uintptr_t)self.device().device_data(); })
       .def_property_readonly("__cuda_array_interface__", [](iTensor& self) {
         // zero-copy view of the resident HBM buffer for torch.as_tensor / cupy.asarray (CUDA Array Interface v3);

@@ -7,13 +7,14 @@ import os
 import re
 
 REF = "/root/reference/tenncor/eteq/test/test_backprop.cpp"
+# the optimizer update graphs asserted the same way (EXPECT_GRAPHEQ) by tenncor/test/test_approx.cpp
+APPROX_REF = "/root/reference/tenncor/test/test_approx.cpp"
 
 
-def main():
-    src = open(REF).read()
-    out = {}
-    for m in re.finditer(r"TEST\(BACKPROP, (\w+)\)\n\{(.*?)\n\}\n", src, re.S):
-        name, body = m.group(1), m.group(2)
+def extract(path, suite, out, prefix=""):
+    src = open(path).read()
+    for m in re.finditer(r"TEST\(%s, (\w+)\)\n\{(.*?)\n\}\n" % suite, src, re.S):
+        name, body = prefix + m.group(1), m.group(2)
         graphs = []
         # runs of adjacent C string literals (only whitespace between them); a run that starts with "(" is one expected graph
         lits = [(l.start(), l.end(), l.group(1)) for l in re.finditer(r'"((?:[^"\\]|\\.)*)"', body)]
@@ -28,10 +29,16 @@ def main():
         if run:
             graphs.append(run)
         graphs = ["".join(r).replace("\\\\", "\\").replace("\\n", "\n") for r in graphs]
-        graphs = [g for g in graphs if g.startswith("(") and g.endswith("\n")]
+        graphs = [g for g in graphs if g.startswith("(") and "\n" in g]
         if graphs:
             line = src[:m.start()].count("\n") + 1
-            out[name] = {"cite": "tenncor/eteq/test/test_backprop.cpp:%d" % line, "graphs": graphs}
+            out[name] = {"cite": "%s:%d" % (path.replace("/root/reference/", ""), line), "graphs": graphs}
+
+
+def main():
+    out = {}
+    extract(REF, "BACKPROP", out)
+    extract(APPROX_REF, "APPROX", out, prefix="Approx")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "backprop_goldens.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)

@@ -136,3 +136,78 @@ def test_assign_has_no_derivative():  # BACKPROP.Fatals :684-721
     sup, a1, a2 = std_operands()
     with pytest.raises(Exception, match="cannot derive"):
         tc.egen.lderive(F("ASSIGN", [a1, a2]), sup, 1)
+
+
+# ---------------------------------------------------------------- optimizer update graphs (tenncor/test/test_approx.cpp)
+def render_typed(root):
+    """like render(), with each leaf's real usage (variable / constant), as the reference prints real leaves"""
+    out = []
+
+    def text(t):
+        shape = "\\".join(str(d) for d in t.teq_shape())
+        dtype = {"float64": "DOUBLE", "float32": "FLOAT", "int32": "INT32"}[str(t.dtype())]
+        name = (t.usage() + ":" + t.label()) if t.is_leaf() else t.opname()
+        return "(%s<%s>[%s])" % (name, dtype, shape)
+
+    def rec(t, ancestors_last):
+        if not ancestors_last:
+            out.append(text(t))
+        else:
+            out.append("_" + "".join("____" if last else "|___" for last in ancestors_last[:-1]) + "`--" + text(t))
+        if not t.is_leaf():
+            kids = t.args()
+            for i, k in enumerate(kids):
+                rec(k, ancestors_last + [i == len(kids) - 1])
+
+    rec(root, [])
+    return "\n".join(out)
+
+
+def _leaf(shape):
+    return tc.EVariable(shape[::-1], 0, "leaf")  # FLOAT by default, like make_variable_scalar<float>
+
+
+def _golden(name):
+    return GOLD[name]["graphs"][0].rstrip("\n")
+
+
+def same_graph(got, want):
+    """tutil::compare_graph (testutil/src/graph_comp.cpp:14-56): lines are compared after stripping '_', blanks and newlines from
+    both ends — the reference's hand-written goldens are not exact about leading indentation (Adadelta's has a line one short)"""
+    strip = lambda text: [l.strip("_ \t") for l in text.split("\n") if l.strip("_ \t")]  # noqa: E731
+    return strip(got) == strip(want)
+
+
+def test_sgd_graph():  # APPROX.StochasticGD :21-45
+    leaf = _leaf([18, 9, 3])
+    groups = tc.api.approx.sgd(tc.api.abs(leaf), [leaf], learning_rate=0.67)
+    assert len(groups) == 1
+    assert render_typed(groups[0][1]) == _golden("ApproxStochasticGD")
+
+
+def test_adagrad_graph():  # APPROX.Adagrad :48-86
+    leaf = _leaf([18, 9, 3])
+    groups = tc.api.approx.adagrad(tc.api.abs(leaf), [leaf], learning_rate=0.67)
+    assert len(groups) == 1
+    assert render_typed(groups[0][1]) == _golden("ApproxAdagrad")
+
+
+def test_adadelta_graph():  # APPROX.Adadelta :89-195 (the golden is a format string: %s = fmts::to_string(float epsilon))
+    leaf = _leaf([18, 9, 3])
+    groups = tc.api.approx.adadelta(tc.api.sin(leaf), [leaf], 1.0, 0.91, 0.16)
+    assert len(groups) == 1
+    assert same_graph(render_typed(groups[0][1]), _golden("ApproxAdadelta").replace("%s", "1.19209e-07"))
+
+
+def test_rms_momentum_graph():  # APPROX.RmsMomentum :289-341
+    leaf = _leaf([5])
+    groups = tc.api.approx.rms_momentum(tc.api.sin(leaf) / 2.0, [leaf], 1.0, 0.52, float(np.finfo(np.float32).eps))
+    assert len(groups) == 1
+    assert render_typed(groups[0][1]) == _golden("ApproxRmsMomentum")
+
+
+def test_adam_graph():  # APPROX.Adam :388-482
+    x = tc.EVariable([], 0, "x")
+    loss = tc.api.square(x) - 2.0 * x + 1.0
+    step = tc.api.approx.adam(loss, [x], 0.01, 0.9, 0.999, 1e-8)[0][1]
+    assert render_typed(step) == _golden("ApproxAdam")
