@@ -664,19 +664,20 @@ PYBIND11_MODULE(_tenncor, m) {
   lay.def("bind", [](layr::UnaryF unary, std::vector<size_t> inshape) { return tenncor::layer::bind(unary, p2cshape(inshape)); },
           py::arg("unary"), py::arg("inshape") = std::vector<size_t>{});
   lay.def("link", &tenncor::layer::link, py::arg("layers"), py::arg("input") = ETensor());
-  lay.def("dense", [wrap_init](std::vector<size_t> inshape, std::vector<size_t> hidden_dims, py::object kinit, py::object binit, bool with_bias) {
+  lay.def("dense", [wrap_init](std::vector<size_t> inshape, std::vector<size_t> hidden_dims, py::object kinit, py::object binit, bool with_bias, py::object dtype) {
     DimsT hd(hidden_dims.rbegin(), hidden_dims.rend());
-    return tenncor::layer::dense(p2cshape(inshape), hd, wrap_init(kinit), wrap_init(binit), with_bias);
-  }, py::arg("inshape"), py::arg("hidden_dims"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none(), py::arg("with_bias") = true);
+    return tenncor::layer::dense(p2cshape(inshape), hd, wrap_init(kinit), wrap_init(binit), with_bias, {{0, 1}}, parse_dtype(dtype));
+  }, py::arg("inshape"), py::arg("hidden_dims"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none(), py::arg("with_bias") = true,
+          py::arg("dtype") = py::none());
   lay.def("dense_on", [](const ETensor& input, const ETensor& kernel, const ETensor& bias) { return tenncor::layer::dense(input, kernel, bias); },
           py::arg("input"), py::arg("kernel"), py::arg("bias") = ETensor());
   lay.def("conv2d", [wrap_init](tenncor::DimPairsT kernel_hw, DimT in_ncol, DimT out_ncol, py::object kinit, py::object binit) {
     return tenncor::layer::conv2d(kernel_hw, in_ncol, out_ncol, wrap_init(kinit), wrap_init(binit));
   }, py::arg("kernel_hw"), py::arg("in_ncol"), py::arg("out_ncol"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none());
-  lay.def("rnn", [wrap_init](DimT indim, DimT hidden_dim, layr::UnaryF activation, DimT nseq, py::object kinit, py::object binit, RankT seq_dim) {
-    return tenncor::layer::rnn(indim, hidden_dim, activation, nseq, wrap_init(kinit), wrap_init(binit), seq_dim);
+  lay.def("rnn", [wrap_init](DimT indim, DimT hidden_dim, layr::UnaryF activation, DimT nseq, py::object kinit, py::object binit, RankT seq_dim, py::object dtype) {
+    return tenncor::layer::rnn(indim, hidden_dim, activation, nseq, wrap_init(kinit), wrap_init(binit), seq_dim, true, parse_dtype(dtype));
   }, py::arg("indim"), py::arg("hidden_dim"), py::arg("activation"), py::arg("nseq"), py::arg("kernel_init") = py::none(),
-          py::arg("bias_init") = py::none(), py::arg("seq_dim") = 1);
+          py::arg("bias_init") = py::none(), py::arg("seq_dim") = 1, py::arg("dtype") = py::none());
   lay.def("lstm", [wrap_init](std::vector<size_t> inshape, DimT hidden_dim, DimT nseq, py::object kinit, py::object binit, RankT seq_dim) {
     return tenncor::layer::lstm(p2cshape(inshape), hidden_dim, nseq, wrap_init(kinit), wrap_init(binit), seq_dim);
   }, py::arg("inshape"), py::arg("hidden_dim"), py::arg("nseq"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none(),
@@ -715,9 +716,9 @@ PYBIND11_MODULE(_tenncor, m) {
                                                training, m, wrap_init(moving_mean_init), wrap_init(moving_var_init), axis);
   }, py::arg("input"), py::arg("offset") = 0., py::arg("scale") = 1., py::arg("eps") = py::none(), py::arg("training") = ETensor(),
           py::arg("momentum") = py::none(), py::arg("moving_mean_init") = py::none(), py::arg("moving_var_init") = py::none(), py::arg("axis") = teq::rank_cap);
-  lay.def("rbm", [wrap_init](DimT nvisible, DimT nhidden, py::object kinit, py::object binit) {
-    return tenncor::layer::rbm(nvisible, nhidden, wrap_init(kinit), wrap_init(binit));
-  }, py::arg("nvisible"), py::arg("nhidden"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none());
+  lay.def("rbm", [wrap_init](DimT nvisible, DimT nhidden, py::object kinit, py::object binit, bool with_bias) {
+    return tenncor::layer::rbm(nvisible, nhidden, wrap_init(kinit), wrap_init(binit), with_bias);
+  }, py::arg("nvisible"), py::arg("nhidden"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none(), py::arg("with_bias") = true);
 
   auto los = api.def_submodule("loss");
   los.def("sqr_diff", &tenncor::loss::sqr_diff);

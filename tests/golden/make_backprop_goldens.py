@@ -9,6 +9,7 @@ import re
 REF = "/root/reference/tenncor/eteq/test/test_backprop.cpp"
 # the optimizer update graphs asserted the same way (EXPECT_GRAPHEQ) by tenncor/test/test_approx.cpp
 APPROX_REF = "/root/reference/tenncor/test/test_approx.cpp"
+LAYER_REF = "/root/reference/tenncor/test/test_layer.cpp"
 
 
 def extract(path, suite, out, prefix=""):
@@ -39,6 +40,9 @@ def main():
     out = {}
     extract(REF, "BACKPROP", out)
     extract(APPROX_REF, "APPROX", out, prefix="Approx")
+    # layer connection graphs (tenncor/test/test_layer.cpp:36-262): dense / conv2d / rbm (both directions) / bind
+    for suite in ("DENSE", "CONV", "RBM", "BIND"):
+        extract(LAYER_REF, suite, out, prefix="Layer" + suite.capitalize())
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "backprop_goldens.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)

@@ -19,6 +19,10 @@ REF = "/root/reference/tenncor/test/test_equation.cpp"
 # (tenncor/test/test_api.cpp:2265-2361, asserted there with ASSERT_VECEQ on doubles)
 API_REF = "/root/reference/tenncor/test/test_api.cpp"
 API_FUNCS = {"api_convolution": (2265, 2361)}
+# layer-level goldens: rnn / dense stacks connected through layer.link, full gradients (tenncor/test/test_layer.cpp CONNECT.*)
+LAYER_REF = "/root/reference/tenncor/test/test_layer.cpp"
+LAYER_FUNCS = {"layer_tanh_rnn": (264, 388), "layer_dense_tanh_rnn": (390, 572), "layer_tanh_rnn_full": (574, 814),
+               "layer_tanh_rnn_cross_entropy": (816, 1059)}
 FUNCS = {"matmul_complex": (26, 136), "contract_equivalent": (139, 250), "sigmoid_MLP_slow": (252, 480),
          "sigmoid_MLP_fast": (482, 707), "tanh_RNN": (709, 840), "tanh_RNN_layer": (842, 970)}
 
@@ -42,6 +46,12 @@ def main():
         vecs = {m.group(1): numbers(m.group(2)) for m in re.finditer(r"std::vector<double>\s+(\w+)\s*=\s*\{([^}]*)\};", text, re.S)}
         shapes = {m.group(1): [int(v) for v in numbers(m.group(2))] for m in re.finditer(r"teq::DimsT\s+(\w+)\s*=\s*\{([^}]*)\};", text, re.S)}
         out[name] = {"cite": "tenncor/test/test_api.cpp:%d-%d" % (lo, hi), "vectors": vecs, "shapes": shapes}
+    layer_lines = open(LAYER_REF).read().split("\n")
+    for name, (lo, hi) in LAYER_FUNCS.items():
+        text = "\n".join(layer_lines[lo - 1:hi])
+        vecs = {m.group(1): numbers(m.group(2)) for m in re.finditer(r"std::vector<double>\s+(\w+)\s*=\s*\{([^}]*)\};", text, re.S)}
+        dims = {m.group(1): int(m.group(2)) for m in re.finditer(r"teq::(?:DimT|RankT)\s+(\w+)\s*=\s*(\d+);", text)}
+        out[name] = {"cite": "tenncor/test/test_layer.cpp:%d-%d" % (lo, hi), "vectors": vecs, "shapes": {}, "dims": dims}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "equation_goldens.json")
     with open(path, "w") as f:
         json.dump(out, f)

@@ -211,3 +211,45 @@ def test_adam_graph():  # APPROX.Adam :388-482
     loss = tc.api.square(x) - 2.0 * x + 1.0
     step = tc.api.approx.adam(loss, [x], 0.01, 0.9, 0.999, 1e-8)[0][1]
     assert render_typed(step) == _golden("ApproxAdam")
+
+
+# ---------------------------------------------------------------- layer connection graphs (tenncor/test/test_layer.cpp:36-262)
+def _x(teq_shape, label):
+    return tc.EVariable(teq_shape[::-1], 0, label)
+
+
+def _graphs(name):
+    return [g.rstrip("\n").replace("%s", "1.19209e-07") for g in GOLD[name]["graphs"]]
+
+
+def test_dense_connection():
+    xu = tc.api.init.xavier_uniform
+    biased = tc.api.layer.dense([6], [5], xu(2), xu(4))
+    plain = tc.api.layer.dense([7], [6], xu(3), None, with_bias=False)
+    want = _graphs("LayerDenseConnection")
+    assert same_graph(render_typed(biased.connect(_x([6, 2], "x"))), want[0])
+    assert same_graph(render_typed(plain.connect(_x([7, 2], "x2"))), want[1])
+
+
+def test_conv_connection():
+    conv = tc.api.layer.conv2d((6, 5), 4, 3, tc.api.init.xavier_uniform(1), tc.api.init.zeros())
+    assert same_graph(render_typed(conv.connect(_x([4, 10, 9, 2], "x"))), _graphs("LayerConvConnection")[0])
+
+
+def test_rbm_connections():
+    xu = tc.api.init.xavier_uniform
+    rbm, nobias = tc.api.layer.rbm(6, 5, xu(2), xu(4)), tc.api.layer.rbm(7, 6, xu(3), None, with_bias=False)
+    fwd = _graphs("LayerRbmConnection")
+    assert same_graph(render_typed(rbm.connect(_x([6, 2], "x"))), fwd[0])
+    assert same_graph(render_typed(nobias.connect(_x([7, 2], "x2"))), fwd[1])
+    bwd = _graphs("LayerRbmBackwardConnection")
+    assert same_graph(render_typed(rbm.backward_connect(_x([5, 2], "y"))), bwd[0])
+    assert same_graph(render_typed(nobias.backward_connect(_x([6, 2], "y2"))), bwd[1])
+
+
+def test_bind_layers():
+    x = _x([6, 2], "x")
+    assert same_graph(render_typed(tc.api.layer.bind(tc.api.sigmoid).connect(x)), _graphs("LayerBindSigmoid")[0])
+    soft = _graphs("LayerBindSoftmax")
+    assert same_graph(render_typed(tc.api.layer.bind(lambda e: tc.api.softmax(e, 0, 1)).connect(x)), soft[0])
+    assert same_graph(render_typed(tc.api.layer.bind(lambda e: tc.api.softmax(e, 1, 1)).connect(x)), soft[1])
