@@ -168,3 +168,42 @@ def test_opcode_properties():
     assert len(ops) == 50 and ops[0] == "IDENTITY" and ops[-1] == "CAST"
     assert {o for o in ops if tc.egen.is_commutative(o)} == {"ADD", "MUL", "MIN", "MAX", "EQ", "NEQ"}
     assert {o for o in ops if not tc.egen.is_idempotent(o)} == {"RAND_UNIF", "ASSIGN_ADD", "ASSIGN_SUB", "ASSIGN_MUL", "ASSIGN_DIV", "CAST"}
+
+
+# ---------------------------------------------------------------- test_typer.cpp (TypeParser<OP>)
+def dtype(opname, attrs, dtypes):
+    return tc.egen.type_parse(opname, attrs, dtypes)
+
+
+def test_type_rules():  # internal/eigen/test/test_typer.cpp:13-87
+    with pytest.raises(Exception, match=NO_ARGS):
+        dtype("ADD", {}, [])
+    # the result has the highest precision among the arguments, whatever their order
+    assert dtype("ADD", {}, ["DOUBLE", "FLOAT"]) == "DOUBLE" and dtype("ADD", {}, ["FLOAT", "DOUBLE"]) == "DOUBLE"
+    assert dtype("ADD", {}, ["FLOAT", "INT32"]) == "FLOAT" and dtype("ADD", {}, ["INT32", "FLOAT"]) == "FLOAT"
+    # ASSIGN takes the destination's type
+    with pytest.raises(Exception, match=NO_ARGS):
+        dtype("ASSIGN", {}, [])
+    assert dtype("ASSIGN", {}, ["DOUBLE", "FLOAT"]) == "DOUBLE" and dtype("ASSIGN", {}, ["FLOAT", "DOUBLE"]) == "FLOAT"
+    assert dtype("ASSIGN", {}, ["INT32", "DOUBLE"]) == "INT32" and dtype("ASSIGN", {}, ["INT32", "FLOAT"]) == "INT32"
+    # CAST: identity without the dtype attribute, the attribute's type with it
+    with pytest.raises(Exception, match=NO_ARGS):
+        dtype("CAST", {}, [])
+    assert [dtype("CAST", {}, [t]) for t in ("DOUBLE", "FLOAT", "INT32")] == ["DOUBLE", "FLOAT", "INT32"]
+    assert [dtype("CAST", {"dtype": "INT32"}, [t]) for t in ("DOUBLE", "FLOAT", "INT32")] == ["INT32"] * 3
+
+
+# ---------------------------------------------------------------- test_packer.cpp (attribute packers' error behaviour)
+def test_attribute_packers():  # internal/eigen/test/test_packer.cpp:116-300
+    """a rule that needs an attribute names the missing key; packers refuse ranks beyond rank_cap with the reference's texts"""
+    for opname, key in [("REDUCE_SUM", "rank_set"), ("PERMUTE", "ranks"), ("CONTRACT", "rank_pairs"), ("PAD", "dimension_pairs"),
+                        ("ARGMAX", "rank"), ("RESHAPE", "shape"), ("STRIDE", "dimensions")]:
+        shapes = [[3, 4], [3, 4]] if opname == "CONTRACT" else [[3, 4]]
+        fails(opname, {}, shapes, "cannot find `%s` attribute" % key)
+    fails("PERMUTE", {"ranks": [8, 3, 4, 10]}, [[3, 4]], "cannot reference ranks beyond rank_cap 8: [8\\3\\4\\10]")
+    fails("CONTRACT", {"rank_pairs": [(8, 3), (4, 10)]}, [[3, 4], [3, 4]], "cannot reference ranks beyond rank_cap 8: [8:3\\4:10]")
+    fails("REDUCE_SUM", {"rank_set": {3, 4, 8, 10}}, [[3, 4]], "cannot reference ranks beyond rank_cap 8: [3\\4\\8\\10]")
+    fails("REDUCE_SUM", {"rank_set": set(range(9))}, [[3, 4]], "cannot specify 9 ranks when 8 (rank_cap) are available")
+    # values survive the round trip through the attribute map
+    assert shape("PAD", {"dimension_pairs": [(2, 1), (0, 3)]}, [[3, 4]]) == [6, 7]
+    assert shape("REDUCE_SUM", {"rank_set": {1, 8}}, [[3, 4]]) == [3]  # rank_cap itself is accepted and names no rank
