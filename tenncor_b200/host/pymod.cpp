@@ -169,6 +169,14 @@ static eteq::VarptrT as_var(const ETensor& t) {
   return v;
 }
 
+// a teq::iDevice that computes nothing and records the calc() calls an evaluator makes (the role of MockDevice in
+// internal/teq/test/test_evaluator.cpp): the evaluators' traversal order, target flags and `ignored` handling become testable
+// without a GPU
+struct RecordingDevice final : public teq::iDevice {
+  void calc(iTensor& tens, size_t cache_ttl) override { calls_.push_back({tens.shared_from_this(), cache_ttl}); }
+  std::vector<std::pair<TensptrT, size_t>> calls_;
+};
+
 // an api.init.* initializer object or a python callable (numpy_shape, label) -> EVariable
 static layr::InitF to_initf(py::object f) {
   if (f.is_none()) return layr::InitF();
@@ -492,6 +500,28 @@ PYBIND11_MODULE(_tenncor, m) {
     cuda::Device device(max_version);  // iEvaluator.evaluate (eteq_ext.cpp:208-225), as a function taking the evaluator
     self->evaluate(device, to_set(targeted), to_set(ignored));
   }, py::arg("evaluator"), py::arg("targeted"), py::arg("max_version") = std::numeric_limits<size_t>::max(), py::arg("ignored") = ETensorsT{});
+  py::class_<RecordingDevice>(m, "RecordingDevice")
+      .def(py::init<>())
+      .def("calls", [](RecordingDevice& self) { return self.calls_; }, "(tensor, cache_ttl) of every calc() so far, in order")
+      .def("clear", [](RecordingDevice& self) { self.calls_.clear(); });
+  m.def("evaluate_on", [](std::shared_ptr<teq::iEvaluator> self, RecordingDevice& device, ETensorsT targeted, ETensorsT ignored) {
+    self->evaluate(device, to_set(targeted), to_set(ignored));
+  }, py::arg("evaluator"), py::arg("device"), py::arg("targeted"), py::arg("ignored") = ETensorsT{},
+  "iEvaluator::evaluate on a recording device (no computation): which functors are visited, in what order");
+  // test support only (the counterpart of the reference tests' MockDeviceRef): hands a functor's holder a small HOST block so that
+  // device_data() is non-null and the evaluators' "cannot ignore tensor without existing data" precondition can be met on a
+  // machine without a GPU. Nothing ever reads the block; never call this on a graph that will be evaluated on the device.
+  auto testing = m.def_submodule("testing", "hooks for the CPU-side mirrors of the reference's unit tests");
+  testing.def("mock_data", [](ETensor t) {
+    struct HostMemory final : public eigen::iRuntimeMemory {
+      void* allocate(size_t size) override { return std::malloc(size ? size : 1); }
+      void deallocate(void* ptr, size_t) override { std::free(ptr); }
+    };
+    static eigen::RTMemptrT host = std::make_shared<HostMemory>();
+    auto op = dynamic_cast<cuda::DevOp*>(&t->device());
+    if (nullptr == op) global::fatalf("%s has no temporary holder to mock", t->to_string().c_str());
+    op->ensure_buffer(1, host);
+  }, py::arg("tensor"));
   m.def("set_eval", [](std::shared_ptr<teq::iEvaluator> eval) { teq::set_eval(std::move(eval)); },
         "Install an evaluator object in the context slot (teq::set_eval, internal/teq/evaluator.hpp:65)");
 
