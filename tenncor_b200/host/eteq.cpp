@@ -571,7 +571,9 @@ uint64_t rng_advance(uint64_t n) {
 
 // ---------------------------------------------------------------- Variable
 Variable::Variable(const void* host_data, egen::_GENERATED_DTYPE dtype, Shape shape, std::string label, Usage usage)
-    : ref_(std::make_shared<cuda::DevSrc>(host_data, dtype, shape, false)), shape_(shape), label_(std::move(label)), meta_(dtype), usage_(usage) {}
+    : ref_(std::make_shared<cuda::DevSrc>(host_data, dtype, shape, false)), shape_(shape), label_(std::move(label)), meta_(dtype, 1), usage_(usage) {
+  note_version(1);  // leaves are born at version 1 (variable.hpp:153, constant.hpp:102): a fresh functor (version 0) is stale against them
+}
 
 Variable::Variable(const Variable& other)
     : ref_(std::make_shared<cuda::DevSrc>(const_cast<Variable&>(other).ref_->data(), other.meta_.dtype_, other.shape_, false)),
@@ -622,7 +624,8 @@ void Variable::assign_device(const void* dev_input) {
 
 // ---------------------------------------------------------------- Constant
 Constant::Constant(const void* host_data, egen::_GENERATED_DTYPE dtype, Shape shape)
-    : ref_(std::make_shared<cuda::DevSrc>(host_data, dtype, shape, true)), shape_(shape), meta_(dtype) {
+    : ref_(std::make_shared<cuda::DevSrc>(host_data, dtype, shape, true)), shape_(shape), meta_(dtype, 1) {
+  note_version(1);
   size_t n = shape.n_elems();
   std::vector<double> d(n);
   egen::type_convert(d.data(), egen::DOUBLE, host_data, dtype, n);

@@ -187,6 +187,8 @@ struct DevOp final : public eigen::iEigen {
   /// run this op's kernel(s) on explicit buffers (plan executor: buffers come from the plan)
   void launch_with(void* out, const std::vector<const void*>& in) const { launch_(out, in); }
   size_t out_bytes() const { return bytes_; }
+  /// test support: swap the kernel launcher (the role of the op lambda handed to TensOp in internal/eigen/test/test_device.cpp)
+  void set_launch(LaunchF launch) { launch_ = std::move(launch); }
   /// MATMUL / CONTRACT lowered to one tcr_gemm: the descriptor, so a launcher may add an epilogue
   void set_gemm(const tcr_gemm_desc& d) { gemm_ = std::make_shared<tcr_gemm_desc>(d); }
   const tcr_gemm_desc* gemm() const { return gemm_.get(); }

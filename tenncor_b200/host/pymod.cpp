@@ -177,6 +177,24 @@ struct RecordingDevice final : public teq::iDevice {
   std::vector<std::pair<TensptrT, size_t>> calls_;
 };
 
+// MockRuntimeMemory of internal/eigen/mock/memory.hpp as a recorder: host blocks, every call logged
+struct CountingMemory final : public eigen::iRuntimeMemory {
+  void* allocate(size_t size) override {
+    void* p = std::malloc(size ? size : 1);
+    log_.push_back({"allocate", size, (uintptr_t)p});
+    return p;
+  }
+  void deallocate(void* ptr, size_t size) override {
+    log_.push_back({"deallocate", size, (uintptr_t)ptr});
+    std::free(ptr);
+  }
+  std::vector<std::tuple<std::string, size_t, uintptr_t>> log_;
+};
+
+struct LaunchLog {
+  std::vector<std::pair<uintptr_t, std::vector<uintptr_t>>> calls_;
+};
+
 // an api.init.* initializer object or a python callable (numpy_shape, label) -> EVariable
 static layr::InitF to_initf(py::object f) {
   if (f.is_none()) return layr::InitF();
@@ -257,6 +275,25 @@ PYBIND11_MODULE(_tenncor, m) {
         return d;
       })
       .def("get_version", [](const iTensor& self) { return self.get_meta().state_version(); })
+      .def("type_label", [](const iTensor& self) { return self.get_meta().type_label(); })
+      .def("type_size", [](const iTensor& self) { return self.get_meta().type_size(); })
+      // eigen::Observable (internal/eigen/observable.hpp) / eteq::Functor (tenncor/eteq/functor.hpp:106-269) as the reference's
+      // tests drive them (tenncor/eteq/test/test_functor.cpp)
+      .def("has_data", [](const iTensor& self) { auto f = dynamic_cast<const eigen::Observable*>(&self); return f ? f->has_data() : true; })
+      .def("must_initialize", [](iTensor& self) { if (auto f = dynamic_cast<eigen::Observable*>(&self)) f->must_initialize(); })
+      .def("uninitialize", [](iTensor& self) { if (auto f = dynamic_cast<eigen::Observable*>(&self)) f->uninitialize(); })
+      .def("prop_version", [](iTensor& self, size_t max_version) {
+        auto f = dynamic_cast<eigen::Observable*>(&self);
+        if (nullptr == f) global::fatalf("%s is not a functor", self.to_string().c_str());
+        return f->prop_version(max_version);
+      }, py::arg("max_version") = std::numeric_limits<size_t>::max())
+      .def("update_child", [](iTensor& self, TensptrT arg, size_t index) {
+        auto f = dynamic_cast<iFunctor*>(&self);
+        if (nullptr == f) global::fatalf("%s is not a functor", self.to_string().c_str());
+        f->update_child(arg, index);
+      }, py::arg("arg"), py::arg("index"))
+      .def("nsubs", [](const iTensor& self) { auto f = dynamic_cast<const eigen::Observable*>(&self); return f ? f->nsubs() : (size_t)0; })
+      .def("clone", [](const iTensor& self) { return TensptrT(self.clone()); })
       .def("opname", [](const iTensor& self) {
         auto f = dynamic_cast<const iFunctor*>(&self);
         return f ? f->get_opcode().name_ : std::string();
@@ -430,6 +467,11 @@ PYBIND11_MODULE(_tenncor, m) {
     marsh::Maps m = to_maps(attrs);
     return eteq::make_funcattr(egen::get_op(opname), args, m);  // eteq::make_functor with the attributes eigen::Packer would pack
   }, py::arg("opname"), py::arg("args"), py::arg("attrs") = py::dict());
+  eg.def("make_tfunctor", [to_maps](const std::string& dtype, const std::string& opname, ETensorsT args, const py::dict& attrs) {
+    marsh::Maps m = to_maps(attrs);
+    return eteq::make_tfuncattr(egen::get_type(dtype), egen::get_op(opname), std::move(args), m);  // make_tfuncattr<T>, make.hpp:66-84
+  }, py::arg("dtype"), py::arg("opname"), py::arg("args"), py::arg("attrs") = py::dict(),
+  "eteq::make_tfunctor<T>: the functor in an explicit element type; TypeCaster (caster.hpp:10-44) wraps arguments of another type in CAST");
   eg.def("lderive", [](const ETensor& op, const ETensor& supgrad, size_t arg_idx) {
     auto f = std::dynamic_pointer_cast<teq::iFunctor>(op);
     if (nullptr == f) global::fatalf("%s is not a functor", op->to_string().c_str());
@@ -512,7 +554,7 @@ PYBIND11_MODULE(_tenncor, m) {
   // device_data() is non-null and the evaluators' "cannot ignore tensor without existing data" precondition can be met on a
   // machine without a GPU. Nothing ever reads the block; never call this on a graph that will be evaluated on the device.
   auto testing = m.def_submodule("testing", "hooks for the CPU-side mirrors of the reference's unit tests");
-  testing.def("mock_data", [](ETensor t) {
+  testing.def("mock_data", [](ETensor t, size_t ttl) {
     struct HostMemory final : public eigen::iRuntimeMemory {
       void* allocate(size_t size) override { return std::malloc(size ? size : 1); }
       void deallocate(void* ptr, size_t) override { std::free(ptr); }
@@ -520,8 +562,57 @@ PYBIND11_MODULE(_tenncor, m) {
     static eigen::RTMemptrT host = std::make_shared<HostMemory>();
     auto op = dynamic_cast<cuda::DevOp*>(&t->device());
     if (nullptr == op) global::fatalf("%s has no temporary holder to mock", t->to_string().c_str());
-    op->ensure_buffer(1, host);
-  }, py::arg("tensor"));
+    op->ensure_buffer(ttl, host);
+  }, py::arg("tensor"), py::arg("ttl") = 1);
+  // The holder contract of SURVEY §8 rows a2-a7 / a16 (iEigen: data / odata / assign / valid_for / extend_life, Expirable TTL,
+  // iRuntimeMemory) exercised the way internal/eigen/test/test_device.cpp and tenncor/eteq/test/test_functor.cpp do: a recording
+  // allocator stands in for MockRuntimeMemory and a recording launcher for the op lambda, so no kernel runs.
+  py::class_<CountingMemory, std::shared_ptr<CountingMemory>>(testing, "CountingMemory")
+      .def(py::init<>())
+      .def("log", [](CountingMemory& self) { return self.log_; }, "('allocate' | 'deallocate', bytes, pointer) in call order")
+      .def("clear", [](CountingMemory& self) { self.log_.clear(); });
+  py::class_<LaunchLog, std::shared_ptr<LaunchLog>>(testing, "LaunchLog")
+      .def("calls", [](LaunchLog& self) { return self.calls_; }, "(out pointer, [argument pointers]) of every launch so far");
+  testing.def("stub_launch", [](ETensor t) {
+    auto op = dynamic_cast<cuda::DevOp*>(&t->device());
+    if (nullptr == op) global::fatalf("%s has no temporary holder to stub", t->to_string().c_str());
+    auto log = std::make_shared<LaunchLog>();
+    op->set_launch([log](void* out, const std::vector<const void*>& in) {
+      std::vector<uintptr_t> args;
+      for (auto p : in) args.push_back((uintptr_t)p);
+      log->calls_.push_back({(uintptr_t)out, args});
+    });
+    return log;
+  }, py::arg("tensor"), "Replace the functor's kernel launcher by a recorder (never call on a graph that will be evaluated on the device)");
+  testing.def("holder_kind", [](ETensor t) -> std::string {
+    auto& dev = t->device();
+    if (dynamic_cast<cuda::DevOp*>(&dev)) return "DevOp";
+    if (dynamic_cast<cuda::DevRef*>(&dev)) return "DevRef";
+    if (dynamic_cast<cuda::DevSrc*>(&dev)) return "DevSrc";
+    if (dynamic_cast<cuda::DevAssign*>(&dev)) return "DevAssign";
+    return "other";
+  });
+  testing.def("cache_init", [](ETensor t) {  // Functor::cache_init (functor.hpp:229-243): CacheEigen keeps the result across reads
+    auto op = dynamic_cast<cuda::DevOp*>(&t->device());
+    if (nullptr == op) global::fatalf("%s has no temporary holder to cache", t->to_string().c_str());
+    op->pin();
+  });
+  testing.def("holder_ptr", [](ETensor t) { return (uintptr_t)t->device().device_data(); }, "device_data() of the holder: 0 before the first assign");
+  testing.def("holder_assign", [](ETensor t, size_t ttl, std::shared_ptr<CountingMemory> memory) {
+    eigen::RTMemptrT mem = memory;
+    static_cast<eigen::iEigen&>(t->device()).assign(ttl, mem);
+  }, py::arg("tensor"), py::arg("ttl"), py::arg("memory"));
+  testing.def("holder_read", [](ETensor t) {
+    uintptr_t p;
+    { auto once = t->device().odata(); p = (uintptr_t)once.get(); }  // the Once's destructor is "one consumer done"
+    return p;
+  }, py::arg("tensor"), "Take odata() and release it: one consumer read (ticks the TTL)");
+  testing.def("holder_valid_for", [](ETensor t, size_t ttl) { return static_cast<eigen::iEigen&>(t->device()).valid_for(ttl); });
+  testing.def("holder_extend_life", [](ETensor t, size_t ttl) { static_cast<eigen::iEigen&>(t->device()).extend_life(ttl); });
+  testing.def("device_calc", [](ETensor t, size_t cache_ttl, std::shared_ptr<CountingMemory> memory, size_t max_version) {
+    cuda::Device dev(memory, max_version);  // eigen::Device::calc, internal/eigen/device.hpp:555-570
+    dev.calc(*t, cache_ttl);
+  }, py::arg("tensor"), py::arg("cache_ttl"), py::arg("memory"), py::arg("max_version") = std::numeric_limits<size_t>::max());
   m.def("set_eval", [](std::shared_ptr<teq::iEvaluator> eval) { teq::set_eval(std::move(eval)); },
         "Install an evaluator object in the context slot (teq::set_eval, internal/teq/evaluator.hpp:65)");
 
