@@ -488,6 +488,55 @@ PYBIND11_MODULE(_tenncor, m) {
     return out;
   });
 
+  // ---- teq: shapes and the graph travelers the derivative builder and the evaluators stand on (internal/teq/shape.hpp, traveler.hpp)
+  auto tq = m.def_submodule("teq", "teq::Shape and travelers, as internal/teq/test/test_shape.cpp / test_traveler.cpp drive them");
+  py::class_<Shape>(tq, "Shape")
+      .def(py::init<>())
+      .def(py::init([](const DimsT& dims) { return Shape(dims); }))
+      .def("at", [](const Shape& self, size_t idx) { return (size_t)self.at((RankT)std::min<size_t>(idx, 255)); })
+      .def("n_elems", [](const Shape& self) { return (uint64_t)self.n_elems(); })
+      .def("compatible_before", [](const Shape& self, const Shape& other, size_t idx) { return self.compatible_before(other, (RankT)idx); })
+      .def("compatible_after", [](const Shape& self, const Shape& other, size_t idx) { return self.compatible_after(other, (RankT)idx); })
+      .def("to_list", [](const Shape& self) { return std::vector<size_t>(self.begin(), self.end()); })
+      .def("narrow", [](const Shape& self) { DimsT d = teq::narrow_shape(self); return std::vector<size_t>(d.begin(), d.end()); })
+      .def("__len__", [](const Shape&) { return (size_t)rank_cap; })
+      .def("__eq__", [](const Shape& a, const Shape& b) { return a == b; })
+      .def("__str__", [](const Shape& self) { return self.to_string(); });
+  tq.attr("rank_cap") = (size_t)rank_cap;
+  tq.def("graph_stat", [](const ETensor& root) {
+    teq::GraphStat stat;
+    root->accept(stat);
+    std::vector<std::pair<ETensor, size_t>> out;
+    for (auto& kv : stat.height_) out.push_back({kv.first->shared_from_this(), kv.second});
+    return out;
+  }, "GraphStat (traveler.hpp:51-110): (tensor, longest distance to a leaf) for every node under root");
+  tq.def("graph_index", [](const ETensor& root) {
+    teq::GraphIndex index;
+    root->accept(index);
+    std::vector<std::pair<ETensor, size_t>> out;
+    for (auto& kv : index.indices_) out.push_back({kv.first->shared_from_this(), kv.second});
+    return out;
+  }, "GraphIndex (traveler.hpp:112-148): post-order index of every node under root");
+  tq.def("path_finder", [](const ETensor& root, const ETensorsT& targets, bool follow_attrs) {
+    teq::PathFinder finder(to_set(targets), follow_attrs);
+    root->accept(finder);
+    std::vector<std::tuple<ETensor, std::vector<size_t>, std::vector<std::string>>> out;
+    for (auto& kv : finder.roadmap_) out.push_back({kv.first->shared_from_this(), kv.second.args_, kv.second.attrs_});
+    return out;
+  }, py::arg("root"), py::arg("targets"), py::arg("follow_attrs") = true,
+  "PathFinder (traveler.hpp:200-300): the functors under root that lead to a target, with the argument indices and attribute names to follow");
+  tq.def("copy_graph", [](const ETensor& root, const ETensorsT& ignores) {
+    teq::Copier copier(to_set(ignores));
+    root->accept(copier);
+    std::vector<std::pair<ETensor, ETensor>> out;
+    for (auto& kv : copier.clones_) out.push_back({kv.first->shared_from_this(), kv.second});
+    return out;
+  }, py::arg("root"), py::arg("ignores") = ETensorsT{}, "Copier (traveler.hpp:378-432): (original, clone) pairs; ignored nodes are shared, not cloned");
+  tq.def("attr_tensors", [](const ETensor& func) {
+    auto f = dynamic_cast<iFunctor*>(func.get());
+    return f ? teq::attr_tensors(*f) : TensptrsT{};
+  }, "FindTensAttr (objs.hpp): tensors referenced by a functor's attributes");
+
   // ---- host random generators and logging level (eteq_ext.cpp:383-405)
   m.def("unif_gen", [](double lower, double upper) {
     return py::cpp_function([lower, upper]() { return std::uniform_real_distribution<double>(lower, upper)(tenncor::host_rng()); });
