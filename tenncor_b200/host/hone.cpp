@@ -136,12 +136,12 @@ TensptrsT merge_dups(TensptrsT roots, size_t* merged) {
   return apply(graph, converts, std::move(roots));
 }
 
-TensptrsT fold_constants(TensptrsT roots, size_t* folded) {
-  Collector graph;
-  for (auto& r : roots) graph.visit(r);
-  OwnMapT converts;
-  // post-order: a functor is constant when every argument is a constant leaf or was just folded. Only the top-most
-  // constant functor of each chain is evaluated (its constant children are evaluated on the way, on the device).
+// Which functors constant folding evaluates: post-order, a functor is constant when every argument is a constant leaf or was
+// itself found constant; only the top-most constant functor of each chain is evaluated (its constant children are evaluated
+// on the way, on the device). The reference reaches the same fixed point one level per round (generate_cstrules,
+// tenncor/hone/src/cstrules.cpp:8-37: one source pattern "op over constant leaves" per opcode and branching factor) and, like it,
+// never folds an IDENTITY: an identity is structure (a layer root, a dependency carrier), so nothing above one folds either.
+static std::vector<iTensor*> fold_tops(const Collector& graph) {
   std::unordered_set<iTensor*> constant;
   std::vector<iTensor*> tops;
   for (iTensor* t : graph.order) {
@@ -151,7 +151,7 @@ TensptrsT fold_constants(TensptrsT roots, size_t* folded) {
       continue;
     }
     if (!egen::is_idempotent((egen::_GENERATED_OPCODE)f->get_opcode().code_)) continue;
-    if (f->get_attr(layer_attr)) continue;  // a layer root is structure, not a value
+    if (egen::IDENTITY == (egen::_GENERATED_OPCODE)f->get_opcode().code_) continue;
     bool all = !f->args_ref().empty();
     for (auto& a : f->args_ref()) all &= constant.count(a.get()) > 0;
     if (all) constant.insert(t);
@@ -164,6 +164,22 @@ TensptrsT fold_constants(TensptrsT roots, size_t* folded) {
         for (auto& a : f->args_ref()) has_const_parent.insert(a.get());
   for (iTensor* t : graph.order)
     if (dynamic_cast<iFunctor*>(t) && constant.count(t) && !has_const_parent.count(t)) tops.push_back(t);
+  return tops;
+}
+
+TensptrsT fold_candidates(const TensptrsT& roots) {
+  Collector graph;
+  for (auto& r : roots) graph.visit(r);
+  TensptrsT out;
+  for (iTensor* t : fold_tops(graph)) out.push_back(graph.owners.at(t));
+  return out;
+}
+
+TensptrsT fold_constants(TensptrsT roots, size_t* folded) {
+  Collector graph;
+  for (auto& r : roots) graph.visit(r);
+  OwnMapT converts;
+  std::vector<iTensor*> tops = fold_tops(graph);
   if (!tops.empty()) {
     TensptrsT targets;
     for (iTensor* t : tops) targets.push_back(graph.owners.at(t));

@@ -30,6 +30,8 @@ teq::TensptrsT merge_dups(teq::TensptrsT roots, size_t* merged = nullptr);
 
 /// functors over constants only -> constants (needs a device: the value is computed by the evaluator)
 teq::TensptrsT fold_constants(teq::TensptrsT roots, size_t* folded = nullptr);
+/// the functors `fold_constants` would evaluate and replace by constant leaves (host-side decision only; needs no device)
+teq::TensptrsT fold_candidates(const teq::TensptrsT& roots);
 
 /// hone::optimize without a rule file: merge_dups, then constant folding + merging to a fixed point
 teq::TensptrsT optimize(teq::TensptrsT roots, Stats* stats = nullptr, bool fold = true);

@@ -674,6 +674,8 @@ PYBIND11_MODULE(_tenncor, m) {
     return py::make_tuple(out, d);
   }, py::arg("roots"), py::arg("fold_constants") = true,
   "Merge structurally equal sub-graphs and fold constant functors (evaluated on the device); returns (new roots, stats)");
+  m.def("fold_candidates", [](const ETensorsT& roots) { return hone::fold_candidates(roots); }, py::arg("roots"),
+        "The functors constant folding would evaluate and replace by constants (top-most constant functors; IDENTITY never folds)");
   m.def("merge_dups", [](ETensorsT roots) {
     size_t n = 0;
     ETensorsT out = hone::merge_dups(std::move(roots), &n);

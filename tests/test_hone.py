@@ -85,6 +85,57 @@ def test_training_graphs_keep_their_values(build):
     assert len(tc.describe_plan([root])) <= len(tc.describe_plan([build().train]))
 
 
+CST_A = np.array([59, 10, 28, 10, 67, 62, 23, 4, 55, 77, 28, 16, 82, 52, 47, 16, 7, 85, 37, 2, 8, 52, 62, 43], dtype=np.float64).reshape(4, 3, 2)
+CST_B = np.array([22, 15, 74, 38, 61, 95, 62, 81, 99, 76, 7, 22, 56, 50, 19, 13, 12, 10, 31, 40, 60, 54, 6, 83], dtype=np.float64).reshape(4, 3, 2)
+
+
+def _cstrules_graphs():
+    """the three graphs of tenncor/hone/test/test_cstrules.cpp (Typical :12-48, StopAtVar :51-90, IdentityDependency :93-130)"""
+    a, b = tc.constant(CST_A), tc.constant(CST_B)
+    c = tc.scalar_constant(4, [4, 3, 2], "DOUBLE")
+    var = tc.variable(CST_A, "a")
+    lhs = b + c
+    typical = lhs + (a + b)
+    stop_at_var = lhs + (var + b)
+    identity = tc.egen.make_functor("IDENTITY", [lhs, a + b])
+    return lhs, typical, stop_at_var, identity
+
+
+def test_which_functors_fold():
+    """the host-side half of constant folding, no device: WHICH functors get evaluated and replaced"""
+    lhs, typical, stop_at_var, identity = _cstrules_graphs()
+    assert tc.fold_candidates([typical]) == [typical]              # constants all the way down: the root itself becomes the constant
+    assert tc.fold_candidates([stop_at_var]) == [lhs]              # a variable below stops the chain: only the constant side folds
+    # IDENTITY is never a folding candidate (tenncor/hone/src/cstrules.cpp:26): its arguments fold, it stays, and so does its reader
+    assert tc.fold_candidates([identity]) == identity.args()
+    assert tc.fold_candidates([tc.api.sin(identity)]) == identity.args()
+    lo, hi = tc.scalar_constant(0, [2, 2]), tc.scalar_constant(1, [2, 2])
+    noise = tc.api.random.rand_unif(lo, hi)
+    # deviation kept on purpose: a random draw is not a constant (only the broadcast of the scalar 2 folds here)
+    assert [t.opname() for t in tc.fold_candidates([noise * 2.0])] == ["EXTEND"]
+
+
+@pytest.mark.gpu
+def test_cstrules_goldens(gpu):
+    from tests.test_backprop_golden import render_typed, same_graph
+    lhs, typical, stop_at_var, identity = _cstrules_graphs()
+    (got,), _ = tc.optimize([typical])
+    assert same_graph(render_typed(got), "(constant:[107\\44\\180\\90\\193\\...]<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"), render_typed(got)
+    np.testing.assert_array_equal(got.data(), CST_B + 4 + CST_A + CST_B)
+    (got,), _ = tc.optimize([stop_at_var])
+    assert same_graph(render_typed(got),
+                      "(ADD<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
+                      "_`--(constant:[26\\19\\78\\42\\65\\...]<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
+                      "_`--(ADD<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
+                      "_____`--(variable:a<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
+                      "_____`--(constant:[22\\15\\74\\38\\61\\...]<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"), render_typed(got)
+    (got,), _ = tc.optimize([identity])
+    assert same_graph(render_typed(got),
+                      "(IDENTITY<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
+                      "_`--(constant:[26\\19\\78\\42\\65\\...]<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
+                      "_`--(constant:[81\\25\\102\\48\\128\\...]<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"), render_typed(got)
+
+
 @pytest.mark.gpu
 def test_constant_folding_on_device(gpu):
     rng = np.random.default_rng(3)
