@@ -811,7 +811,10 @@ PYBIND11_MODULE(_tenncor, m) {
          py::arg("dims") = eigen::PairVecT<RankT>{{0, 1}});
   nn.def("conv2d", &tenncor::nn::conv2d, py::arg("image"), py::arg("kernel"), py::arg("bias") = ETensor(),
          py::arg("zero_paddings") = std::pair<tenncor::DimPairsT, tenncor::DimPairsT>{{0, 0}, {0, 0}});
-  nn.def("dropout", &tenncor::nn::dropout);
+  nn.def("dropout", &tenncor::nn::dropout, py::arg("input"), py::arg("drop_rate"));
+  nn.def("dropout", [](const ETensor& input, double drop_rate) {  // nn.yml:99-109: the rate becomes a scalar variable of the input's type
+    return tenncor::nn::dropout(input, eteq::make_variable_scalar(drop_rate, Shape(), "drop_rate", (egen::_GENERATED_DTYPE)input->get_meta().type_code()));
+  }, py::arg("input"), py::arg("drop_rate"));
   nn.def("batch_normalization", [](const ETensor& input, py::object offset, py::object scale, py::object eps, py::object get_mean, py::object get_variance) {
     auto unary = [](py::object f) { return f.is_none() ? layr::UnaryF() : f.cast<layr::UnaryF>(); };
     if (py::isinstance<py::float_>(offset) || py::isinstance<py::int_>(offset))

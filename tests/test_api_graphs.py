@@ -58,3 +58,58 @@ def test_cast_is_not_doubled():
             "_________`--(constant:2<INT32>)\n")
     got = "\n".join(line[:line.rindex("[")] + ")" for line in render_typed(out).split("\n"))  # EXPECT_GRAPH_STRUCTEQ prints no shapes
     assert same_graph(got, want), got
+
+
+def test_nn_dropout_graph():  # NN.Dropout (tenncor/test/test_nn.cpp:15-49): the graph, verbatim; the values are a GPU matter
+    x = tc.scalar_constant(1, [5, 2], "FLOAT")
+    f = tc.api.nn.dropout(x, 0.1)
+    mask = ("(LT<FLOAT>[2\\5\\1\\1\\1\\1\\1\\1])\n"
+            "`--(RAND_UNIF<FLOAT>[2\\5\\1\\1\\1\\1\\1\\1])\n"
+            "|___`--(variable:0<FLOAT>[2\\5\\1\\1\\1\\1\\1\\1])\n"
+            "|___`--(variable:1<FLOAT>[2\\5\\1\\1\\1\\1\\1\\1])\n"
+            "`--(EXTEND<FLOAT>[2\\5\\1\\1\\1\\1\\1\\1])\n"
+            "____`--(SUB<FLOAT>[1\\1\\1\\1\\1\\1\\1\\1])\n"
+            "________`--(EXTEND<FLOAT>[1\\1\\1\\1\\1\\1\\1\\1])\n"
+            "________|___`--(constant:1<FLOAT>[1\\1\\1\\1\\1\\1\\1\\1])\n"
+            "________`--(variable:drop_rate<FLOAT>[1\\1\\1\\1\\1\\1\\1\\1])\n")
+    indent = lambda text, pre: "".join(pre + line + "\n" for line in text.rstrip("\n").split("\n"))  # noqa: E731
+    want = ("(MUL<FLOAT>[2\\5\\1\\1\\1\\1\\1\\1])\n"
+            "_`--(constant:1<FLOAT>[2\\5\\1\\1\\1\\1\\1\\1])\n"
+            "_`--(DIV<FLOAT>[2\\5\\1\\1\\1\\1\\1\\1])\n"
+            + "_____`--" + indent(mask, "_____|___")[len("_____|___"):]
+            + "_____`--(EXTEND<FLOAT>[2\\5\\1\\1\\1\\1\\1\\1])\n"
+            "_________`--(DIV<FLOAT>[1\\1\\1\\1\\1\\1\\1\\1])\n"
+            "_____________`--(REDUCE_SUM<FLOAT>[1\\1\\1\\1\\1\\1\\1\\1])\n"
+            + "_____________|___`--" + indent(mask, "_____________|_______")[len("_____________|_______"):]
+            + "_____________`--(constant:10<FLOAT>[1\\1\\1\\1\\1\\1\\1\\1])")
+    assert same_graph(render_typed(f), want), render_typed(f)
+    # the mask is ONE node read twice (one draw per evaluation), not two independent draws
+    div = f.args()[1]
+    assert div.args()[0] == div.args()[1].args()[0].args()[0].args()[0]
+    assert f.teq_shape() == [2, 5, 1, 1, 1, 1, 1, 1]
+
+
+# ---------------------------------------------------------------- initialisers (tenncor/test/test_init.cpp)
+def test_init_zero():  # INIT.Zero :12-28
+    z = tc.variable_from_init(tc.api.init.zeros(), [9, 18], "abc")
+    assert z.teq_shape()[:2] == [18, 9] and str(z) == "abc"
+    assert not z.data().any()
+
+
+def test_init_variance_scaling():  # INIT.VarianceScaling :31-75 — truncated at two standard deviations
+    factor = 0.425
+    v1 = tc.variable_from_init(tc.api.init.variance_scaling(factor), [3, 9, 18], "def")
+    v2 = tc.variable_from_init(tc.api.init.variance_scaling(factor, shape_factor=lambda shape: float(shape[0])), [3, 9, 18], "def")
+    assert v1.teq_shape()[:3] == [18, 9, 3] and str(v1) == "def"
+    bound1 = 2 * np.sqrt(factor / ((18 + 9) / 2))            # default fan: mean of the two fastest dimensions
+    assert np.abs(v1.data()).max() < bound1 and v1.data().std() > bound1 / 8
+    bound2 = 2 * np.sqrt(factor / 3)                         # shape.at(2): numpy lists it first
+    assert np.abs(v2.data()).max() < bound2 and v2.data().std() > bound2 / 8
+
+
+def test_init_xavier_uniform():  # INIT.UniformXavier :78-96
+    factor = 0.712
+    x = tc.variable_from_init(tc.api.init.xavier_uniform(factor), [3, 9, 18], "ghi")
+    bound = factor * np.sqrt(6.0 / (18 + 9))
+    assert x.teq_shape()[:3] == [18, 9, 3] and str(x) == "ghi"
+    assert np.abs(x.data()).max() < bound and np.abs(x.data()).max() > 0.8 * bound
