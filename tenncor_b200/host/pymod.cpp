@@ -2,6 +2,9 @@
 // module (tenncor/python/eteq_ext.cpp:20-522, layr_ext.cpp, generated pyapi_tenncor.cpp)
 // over the B200 back end. numpy shapes are REVERSED into teq shapes exactly like the
 // reference (tenncor/pyutils/src/convert.cpp:8-37).
+#include <fstream>
+#include <iterator>
+
 #include <pybind11/functional.h>
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
@@ -554,6 +557,60 @@ PYBIND11_MODULE(_tenncor, m) {
   m.def("load_from_file", [](const std::string& filename, const std::unordered_map<std::string, size_t>& key_prec) {
     return onnx::load_from_file(filename, key_prec);
   }, py::arg("filename"), py::arg("key_prec") = std::unordered_map<std::string, size_t>{});
+  m.def("onnx_describe", [](const py::bytes& data) {
+    // the parsed ModelProto as plain python objects: lets a test compare two files message by message (the role of
+    // google::protobuf::util::MessageDifferencer in tenncor/test/test_serialize.cpp SaveGraph)
+    onnx::ModelProto pb;
+    onnx::parse(pb, std::string(data));
+    std::function<py::dict(const onnx::TensorProto&)> tensor = [](const onnx::TensorProto& t) {
+      py::dict d;
+      d["dims"] = t.dims; d["data_type"] = t.data_type; d["name"] = t.name; d["float_data"] = t.float_data; d["int32_data"] = t.int32_data;
+      d["int64_data"] = t.int64_data; d["double_data"] = t.double_data; d["uint64_data"] = t.uint64_data; d["raw_data"] = py::bytes(t.raw_data);
+      return d;
+    };
+    std::function<py::dict(const onnx::GraphProto&)> graph = [&](const onnx::GraphProto& g) {
+      py::list nodes, inits, ins, outs, annos;
+      for (auto& n : g.node) {
+        py::list attrs;
+        for (auto& a : n.attribute) {
+          py::dict d;
+          d["name"] = a.name; d["type"] = a.type; d["f"] = a.f; d["i"] = a.i; d["s"] = py::bytes(a.s); d["floats"] = a.floats; d["ints"] = a.ints;
+          py::list strs, tens;
+          for (auto& st : a.strings) strs.append(py::bytes(st));
+          for (auto& t : a.tensors) tens.append(tensor(t));
+          d["strings"] = strs; d["tensors"] = tens; d["t"] = tensor(a.t);
+          d["g"] = a.g ? py::object(graph(*a.g)) : py::object(py::none());
+          attrs.append(d);
+        }
+        py::dict d;
+        d["input"] = n.input; d["output"] = n.output; d["name"] = n.name; d["op_type"] = n.op_type; d["attribute"] = attrs;
+        nodes.append(d);
+      }
+      for (auto& t : g.initializer) inits.append(tensor(t));
+      auto vinfo = [](const onnx::ValueInfoProto& v) { py::dict d; d["name"] = v.name; d["elem_type"] = v.elem_type; d["dims"] = v.dims; return d; };
+      for (auto& v : g.input) ins.append(vinfo(v));
+      for (auto& v : g.output) outs.append(vinfo(v));
+      for (auto& a : g.quantization_annotation) { py::dict d; d["tensor_name"] = a.tensor_name; d["params"] = a.quant_parameter_tensor_names; annos.append(d); }
+      py::dict d;
+      d["node"] = nodes; d["name"] = g.name; d["initializer"] = inits; d["input"] = ins; d["output"] = outs; d["quantization_annotation"] = annos;
+      return d;
+    };
+    py::dict d;
+    d["ir_version"] = pb.ir_version; d["model_version"] = pb.model_version; d["producer_name"] = pb.producer_name;
+    d["producer_version"] = pb.producer_version; d["domain"] = pb.domain; d["graph"] = graph(pb.graph);
+    return d;
+  }, py::arg("data"));
+  m.def("load_model_ids", [](const std::string& filename) {
+    std::ifstream in(filename, std::ios::binary);
+    if (!in.is_open()) global::fatalf("failed to read file `%s`", filename.c_str());
+    std::string bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    onnx::ModelProto pb;
+    onnx::parse(pb, bytes);
+    onnx::TensIds ids;
+    ETensorsT roots = onnx::load_model(ids, pb);  // tcr::load_model(ids, model), tenncor/src/serial.cpp:53-85
+    std::map<std::string, ETensor> named(ids.by_id.begin(), ids.by_id.end());
+    return py::make_tuple(roots, named);
+  }, py::arg("filename"), "tcr::load_model with its id map: (graph outputs in file order, {id: tensor})");
   m.def("save_to_file", [](const std::string& filename, const ETensorsT& models, const std::map<std::string, ETensor>& keys) {
     std::vector<std::pair<std::string, ETensor>> k(keys.begin(), keys.end());
     return onnx::save_to_file(filename, models, k);

@@ -13,6 +13,9 @@ import os
 REF = "/root/reference/models"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_models.json")
 NAMES = ["gd", "dqn", "dbn", "rnn"]
+# models/test/<name>.onnx + <name>.txt: the file and the PrettyEquation rendering the reference's own serializer tests compare
+# against (tenncor/test/test_serialize.cpp SaveGraph / LoadGraph)
+TEST_NAMES = ["eteq"]
 
 
 def main():
@@ -20,6 +23,11 @@ def main():
     for name in NAMES:
         data = open(os.path.join(REF, name + ".onnx"), "rb").read()
         out["models"][name] = {"bytes": len(data), "sha256": hashlib.sha256(data).hexdigest(), "base64": base64.b64encode(data).decode()}
+    out["test_models"] = {}
+    for name in TEST_NAMES:
+        data = open(os.path.join(REF, "test", name + ".onnx"), "rb").read()
+        out["test_models"][name] = {"bytes": len(data), "sha256": hashlib.sha256(data).hexdigest(), "base64": base64.b64encode(data).decode(),
+                                    "txt": open(os.path.join(REF, "test", name + ".txt")).read()}
     with open(OUT, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", OUT)
