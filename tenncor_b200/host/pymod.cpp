@@ -397,6 +397,12 @@ PYBIND11_MODULE(_tenncor, m) {
     py::array arr = normalise(data, shape, dtype);
     return eteq::make_variable(arr.data(), dtype, shape, label);
   }, py::arg("data"), py::arg("label") = "");
+  m.def("placeholder", [](py::array data, const std::string& label) {
+    Shape shape;
+    egen::_GENERATED_DTYPE dtype;
+    py::array arr = normalise(data, shape, dtype);
+    return eteq::VarptrT(eteq::Variable::get(arr.data(), dtype, shape, label, teq::PLACEHOLDER));  // Variable<T>::get(..., teq::PLACEHOLDER)
+  }, py::arg("data"), py::arg("label") = "", "A variable with PLACEHOLDER usage: saved as a graph input instead of an initializer");
   m.def("to_variable", [](const ETensor& tens) { return as_var(tens); });
   m.def("derive", [](const ETensor& root, const ETensorsT& targets) { return tenncor::derive(root, targets); },
         "Return derivative of first tensor with respect to each target");

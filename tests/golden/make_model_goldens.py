@@ -14,8 +14,8 @@ REF = "/root/reference/models"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_models.json")
 NAMES = ["gd", "dqn", "dbn", "rnn"]
 # models/test/<name>.onnx + <name>.txt: the file and the PrettyEquation rendering the reference's own serializer tests compare
-# against (tenncor/test/test_serialize.cpp SaveGraph / LoadGraph)
-TEST_NAMES = ["eteq"]
+# against (tenncor/test/test_serialize.cpp and tenncor/serial/test/test_serialize.cpp, SaveGraph / LoadGraph)
+TEST_NAMES = ["eteq", "serial"]
 
 
 def main():

@@ -126,3 +126,52 @@ def test_save_graph(eteq_file, tmp_path):  # SERIALIZE.SaveGraph :72-129
     # and what we wrote loads back into the same graph
     _, ids = tc.load_model_ids(mine)
     assert stripped(line for name in NAMES for line in pretty(ids[name])) == WANT
+
+
+# ---------------------------------------------------------------- tenncor/serial/test/test_serialize.cpp: mixed types, placeholder, constants
+SERIAL = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_models.json")))["test_models"]["serial"]
+
+
+def serial_roots():
+    """the two sub-trees of SERIALIZE.SaveGraph :29-93; make_functor inserts the CASTs the mixed leaf types need"""
+    F = tc.egen.make_functor
+    zeros = lambda dtype, label: tc.variable(np.zeros((7, 3), dtype=dtype), label)  # noqa: E731  teq::Shape({3, 7})
+    osrc, osrc2 = zeros(np.float32, "osrc"), zeros(np.float64, "osrc2")
+    src = zeros(np.int32, "src")
+    src2 = tc.scalar_constant(23, [7, 3], "DOUBLE")
+    root1 = F("SUB", [src2, F("POW", [F("DIV", [F("NEG", [osrc]), F("ADD", [F("SIN", [src]), src])]), osrc2])])
+    s2src = tc.placeholder(np.zeros((7, 3), dtype=np.float32), "s2src")
+    s2src2, s2src3 = zeros(np.int32, "s2src2"), zeros(np.float64, "s2src3")
+    root2 = F("SUB", [s2src, F("MUL", [F("ABS", [s2src]), F("EXP", [s2src2]), F("NEG", [s2src3])])])
+    return root1, root2
+
+
+def typed(root):
+    from tests.test_backprop_golden import render_typed
+    return render_typed(root).split("\n")
+
+
+def test_serial_load_graph(tmp_path):  # SERIALIZE.LoadGraph, tenncor/serial/test/test_serialize.cpp:126-180
+    path = str(tmp_path / "serial.onnx")
+    with open(path, "wb") as f:
+        f.write(base64.b64decode(SERIAL["base64"]))
+    roots, ids = tc.load_model_ids(path)
+    assert len(roots) == 2 and "root1" in ids and "root2" in ids
+    got = stripped(line for name in ("root1", "root2") for line in typed(ids[name]))
+    assert got == stripped(SERIAL["txt"].split("\n"))
+    assert got == stripped(line for root in serial_roots() for line in typed(root))  # and the graph built here is that graph
+
+
+def test_serial_save_graph(tmp_path):  # SERIALIZE.SaveGraph :29-123
+    root1, root2 = serial_roots()
+    mine = str(tmp_path / "got_serial.onnx")
+    assert tc.save_to_file(mine, [root1, root2], {"root1": root1, "root2": root2})
+    global NAMES
+    keep, NAMES = NAMES, ("root1", "root2")
+    try:
+        want = canonical(tc.onnx_describe(base64.b64decode(SERIAL["base64"])))
+        got = canonical(tc.onnx_describe(open(mine, "rb").read()))
+    finally:
+        NAMES = keep
+    for section in ("name", "node", "initializer", "input", "output", "annotation"):  # serial::save_graph fills the graph only, no model header
+        assert got[section] == want[section], section
