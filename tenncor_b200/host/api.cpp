@@ -446,6 +446,33 @@ ETensor conv2d(const DimPairsT& kernel_hw, DimT in_ncol, DimT out_ncol, layr::In
   return conv2d(input, kernel, bias, zero_padding);
 }
 
+ETensor conv2d(const ETensor& input, DimT out_ncol, const DimPairsT& kernel_hw, layr::InitF kernel_init, layr::InitF bias_init,
+               const std::pair<DimPairsT, DimPairsT>& zero_padding, bool with_bias) {  // layer.yml:209-251: image must be [in, iwidth, iheight, ...]
+  auto dtype = (_GENERATED_DTYPE)input->get_meta().type_code();
+  if (!kernel_init) kernel_init = init::glorot_uniform(1, dtype);
+  VarptrT kernel = kernel_init(Shape({out_ncol, input->shape().at(0), kernel_hw.second, kernel_hw.first}), layr::weight_label);
+  VarptrT bias;
+  if (with_bias) {
+    if (!bias_init) bias_init = init::zeros(dtype);
+    bias = bias_init(Shape({out_ncol}), layr::bias_label);
+  }
+  return conv2d(input, kernel, bias, zero_padding);
+}
+
+ETensor conv2d(const ETensor& input, DimT out_ncol, const DimPairsT& kernel_hw, layr::InitF kernel_init, layr::InitF bias_init,
+               const std::string& padding, bool with_bias) {  // layer.yml:159-208
+  std::string zpadding;
+  std::transform(padding.begin(), padding.end(), std::back_inserter(zpadding), [](unsigned char c) { return std::tolower(c); });
+  std::pair<DimPairsT, DimPairsT> zero_padding{{0, 0}, {0, 0}};
+  if ("same" == zpadding) {
+    DimT xpad = kernel_hw.second / 2, ypad = kernel_hw.first / 2;
+    zero_padding = {{xpad, xpad}, {ypad, ypad}};
+  } else if ("valid" != zpadding) {
+    global::fatalf("unsupported padding type %s", padding.c_str());
+  }
+  return conv2d(input, out_ncol, kernel_hw, kernel_init, bias_init, zero_padding, with_bias);
+}
+
 static void check_seq_dim(RankT seq_dim) {
   if (seq_dim == 0) global::fatal("spliting input across 0th dimension... dense connection will not match");
 }

@@ -159,6 +159,10 @@ ETensor conv2d(const ETensor& input, const ETensor& kernel, const ETensor& bias 
 ETensor conv2d(const DimPairsT& kernel_hw, teq::DimT in_ncol, teq::DimT out_ncol, layr::InitF kernel_init = {}, layr::InitF bias_init = {},
                const std::pair<DimPairsT, DimPairsT>& zero_padding = {{0, 0}, {0, 0}}, bool with_bias = true,
                egen::_GENERATED_DTYPE dtype = egen::default_dtype);
+ETensor conv2d(const ETensor& input, teq::DimT out_ncol, const DimPairsT& kernel_hw, layr::InitF kernel_init, layr::InitF bias_init,
+               const std::pair<DimPairsT, DimPairsT>& zero_padding, bool with_bias = true);
+ETensor conv2d(const ETensor& input, teq::DimT out_ncol, const DimPairsT& kernel_hw, layr::InitF kernel_init, layr::InitF bias_init,
+               const std::string& padding, bool with_bias = true);
 ETensor rnn(const ETensor& input, const ETensor& init_state, const ETensor& cell, const layr::UnaryF& activation, teq::RankT seq_dim = 1);
 ETensor rnn(teq::DimT indim, teq::DimT hidden_dim, const layr::UnaryF& activation, teq::DimT nseq, layr::InitF kernel_init = {},
             layr::InitF bias_init = {}, teq::RankT seq_dim = 1, bool with_bias = true, egen::_GENERATED_DTYPE dtype = egen::default_dtype);

@@ -909,9 +909,19 @@ PYBIND11_MODULE(_tenncor, m) {
           py::arg("dtype") = py::none());
   lay.def("dense_on", [](const ETensor& input, const ETensor& kernel, const ETensor& bias) { return tenncor::layer::dense(input, kernel, bias); },
           py::arg("input"), py::arg("kernel"), py::arg("bias") = ETensor());
-  lay.def("conv2d", [wrap_init](tenncor::DimPairsT kernel_hw, DimT in_ncol, DimT out_ncol, py::object kinit, py::object binit) {
-    return tenncor::layer::conv2d(kernel_hw, in_ncol, out_ncol, wrap_init(kinit), wrap_init(binit));
-  }, py::arg("kernel_hw"), py::arg("in_ncol"), py::arg("out_ncol"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none());
+  using ZeroPadT = std::pair<tenncor::DimPairsT, tenncor::DimPairsT>;
+  lay.def("conv2d", [wrap_init](tenncor::DimPairsT kernel_hw, DimT in_ncol, DimT out_ncol, py::object kinit, py::object binit, ZeroPadT zero_padding,
+                                bool with_bias, py::object dtype) {
+    return tenncor::layer::conv2d(kernel_hw, in_ncol, out_ncol, wrap_init(kinit), wrap_init(binit), zero_padding, with_bias, parse_dtype(dtype));
+  }, py::arg("kernel_hw"), py::arg("in_ncol"), py::arg("out_ncol"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none(),
+          py::arg("zero_padding") = ZeroPadT{{0, 0}, {0, 0}}, py::arg("with_bias") = true, py::arg("dtype") = py::none());
+  lay.def("conv2d", [wrap_init](const ETensor& input, DimT out_ncol, tenncor::DimPairsT kernel_hw, py::object kinit, py::object binit, py::object padding,
+                                bool with_bias) {  // layer.yml:159-251: on an existing image, padding = "valid" | "same" | ((x0, x1), (y0, y1))
+    if (py::isinstance<py::str>(padding))
+      return tenncor::layer::conv2d(input, out_ncol, kernel_hw, wrap_init(kinit), wrap_init(binit), padding.cast<std::string>(), with_bias);
+    return tenncor::layer::conv2d(input, out_ncol, kernel_hw, wrap_init(kinit), wrap_init(binit), padding.cast<ZeroPadT>(), with_bias);
+  }, py::arg("input"), py::arg("out_ncol"), py::arg("kernel_hw"), py::arg("kernel_init") = py::none(), py::arg("bias_init") = py::none(),
+          py::arg("padding") = "valid", py::arg("with_bias") = true);
   lay.def("rnn", [wrap_init](DimT indim, DimT hidden_dim, layr::UnaryF activation, DimT nseq, py::object kinit, py::object binit, RankT seq_dim, py::object dtype) {
     return tenncor::layer::rnn(indim, hidden_dim, activation, nseq, wrap_init(kinit), wrap_init(binit), seq_dim, true, parse_dtype(dtype));
   }, py::arg("indim"), py::arg("hidden_dim"), py::arg("activation"), py::arg("nseq"), py::arg("kernel_init") = py::none(),

@@ -113,3 +113,44 @@ def test_init_xavier_uniform():  # INIT.UniformXavier :78-96
     bound = factor * np.sqrt(6.0 / (18 + 9))
     assert x.teq_shape()[:3] == [18, 9, 3] and str(x) == "ghi"
     assert np.abs(x.data()).max() < bound and np.abs(x.data()).max() > 0.8 * bound
+
+
+# ---------------------------------------------------------------- tenncor/test/test_layer.py
+def test_conv_conv_gru_link_shape():  # LAYRTest.test_gru :63-82 — two zero-padded conv2d layers feeding a gru split along rank 2
+    brain = tc.api.layer.link([
+        tc.api.layer.conv2d([5, 5], 1, 16, kernel_init=tc.api.init.xavier_normal(0.5), zero_padding=((2, 2), (2, 2))),
+        tc.api.layer.conv2d([5, 5], 16, 20, kernel_init=tc.api.init.xavier_normal(0.5), zero_padding=((2, 2), (2, 2))),
+        tc.api.layer.gru([2647, 20], 20, 128, seq_dim=2, kernel_init=tc.api.init.zeros(), bias_init=tc.api.init.zeros()),
+    ], tc.EVariable([128, 2647, 1], label="input"))
+    assert list(brain.shape()) == [128, 2647, 20]
+
+
+def test_conv2d_on_an_image():  # layer.yml:159-251 — conv2d(input, out_ncol, kernel_hw, ..., padding | zero_padding)
+    x = tc.EVariable([2, 9, 10, 4], label="x")                   # teq [4, 10, 9, 2], the image of API.Conv (test_api.cpp:2505-2531)
+    y = tc.api.layer.conv2d(x, 3, (6, 5))
+    assert y.teq_shape() == [3, 6, 4, 2, 1, 1, 1, 1]
+    kernel, bias = sorted(y.get_storage(), key=lambda v: -len(v.shape()))
+    assert kernel.teq_shape()[:4] == [3, 4, 5, 6] and bias.teq_shape()[0] == 3 and str(kernel) == "weight" and str(bias) == "bias"
+    assert tc.api.layer.conv2d(x, 3, (5, 5), padding="SAME").teq_shape() == [3, 10, 9, 2, 1, 1, 1, 1]
+    assert tc.api.layer.conv2d(x, 3, (5, 5), padding=((2, 2), (0, 0))).teq_shape() == [3, 10, 5, 2, 1, 1, 1, 1]
+    assert len(tc.api.layer.conv2d(x, 3, (5, 5), with_bias=False).get_storage()) == 1
+    with pytest.raises(Exception, match="unsupported padding type full"):
+        tc.api.layer.conv2d(x, 3, (5, 5), padding="full")
+
+
+def test_training_graph_survives_save_and_load(tmp_path):  # LAYRTest.test_context_save :26-61 — the whole apply_update graph, by its rendering
+    nunits, ninput, noutput, nbatch = 9, 10, 5, 10
+    train_err = tc.apply_update(
+        [tc.api.layer.link([
+            tc.api.layer.dense([ninput], [nunits], kernel_init=tc.api.init.xavier_uniform(), bias_init=tc.api.init.zeros()),
+            tc.api.layer.bind(tc.api.sigmoid),
+            tc.api.layer.dense([nunits], [noutput], kernel_init=tc.api.init.xavier_uniform(), bias_init=tc.api.init.zeros()),
+            tc.api.layer.bind(tc.api.sigmoid)])],
+        lambda err, leaves: tc.api.approx.sgd(err, leaves, learning_rate=0.9),
+        lambda models: tc.api.loss.mean_squared(tc.EVariable([nbatch, noutput]), models[0].connect(tc.EVariable([nbatch, ninput]))))
+    path = str(tmp_path / "layr_test.onnx")
+    assert tc.save_to_file(path, [train_err])
+    roots = tc.load_from_file(path)
+    assert len(roots) == 1
+    assert render_typed(roots[0]) == render_typed(train_err)
+    assert "ASSIGN_SUB" in render_typed(train_err)
