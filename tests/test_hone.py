@@ -1,6 +1,7 @@
 """hone pre-evaluation rewrites (tenncor/hone/src/duplicates.cpp, cstrules.hpp, optimize.cpp):
 duplicate merging is pure host logic and is checked here on CPU — the rewritten graph must evaluate (CPU oracle) to
-exactly the values of the original; constant folding evaluates on the device and is checked under -m gpu."""
+exactly the values of the original; constant folding evaluates on the device and is checked under -m gpu (the values of the three test_cstrules.cpp graphs in
+tests/test_zz_staged_gpu.py)."""
 import numpy as np
 import pytest
 
@@ -113,27 +114,6 @@ def test_which_functors_fold():
     noise = tc.api.random.rand_unif(lo, hi)
     # deviation kept on purpose: a random draw is not a constant (only the broadcast of the scalar 2 folds here)
     assert [t.opname() for t in tc.fold_candidates([noise * 2.0])] == ["EXTEND"]
-
-
-@pytest.mark.gpu
-def test_cstrules_goldens(gpu):
-    from tests.test_backprop_golden import render_typed, same_graph
-    lhs, typical, stop_at_var, identity = _cstrules_graphs()
-    (got,), _ = tc.optimize([typical])
-    assert same_graph(render_typed(got), "(constant:[107\\44\\180\\90\\193\\...]<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"), render_typed(got)
-    np.testing.assert_array_equal(got.data(), CST_B + 4 + CST_A + CST_B)
-    (got,), _ = tc.optimize([stop_at_var])
-    assert same_graph(render_typed(got),
-                      "(ADD<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
-                      "_`--(constant:[26\\19\\78\\42\\65\\...]<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
-                      "_`--(ADD<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
-                      "_____`--(variable:a<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
-                      "_____`--(constant:[22\\15\\74\\38\\61\\...]<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"), render_typed(got)
-    (got,), _ = tc.optimize([identity])
-    assert same_graph(render_typed(got),
-                      "(IDENTITY<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
-                      "_`--(constant:[26\\19\\78\\42\\65\\...]<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"
-                      "_`--(constant:[81\\25\\102\\48\\128\\...]<DOUBLE>[2\\3\\4\\1\\1\\1\\1\\1])\n"), render_typed(got)
 
 
 @pytest.mark.gpu
