@@ -149,9 +149,12 @@ def decode_env(data):
 
 # ---------------------------------------------------------------- the environment
 class DQNEnv(ecache.EnvManager):
-    def __init__(self, src_model, update_fn, max_exp=30000, train_interval=5, store_interval=5, explore_period=1000,
+    def __init__(self, src_model, update_fn, optimize_cfg="", max_exp=30000, train_interval=5, store_interval=5, explore_period=1000,
                  action_prob=0.05, mbatch_size=32, discount_rate=0.95, target_update_rate=0.01, clean_startup=False,
-                 usecase="", cachedir="/tmp"):
+                 usecase="", cachedir="/tmp", ctx=None):
+        """same parameters as the reference's DQNEnv (:52-60). `optimize_cfg`: the reference runs its json rule file over the context
+        (tc.optimize(cfg, ctx)); that file is not part of the repository, so a non-empty value asks for the code-defined hone passes
+        (duplicate merging, tc.optimize; host-side only) over the two graphs instead. `ctx` is accepted and unused (one context)."""
         self.max_exp = max_exp
         self.train_interval = train_interval
         self.store_interval = store_interval
@@ -177,6 +180,8 @@ class DQNEnv(ecache.EnvManager):
             self.rewards = tc.EVariable([mbatch_size], 0, "rewards")
             self.prediction_err = tc.api.identity(tc.apply_update(
                 [src_model, nxt_model], get_dqnupdate(update_fn, target_update_rate), get_dqnerror(self, discount_rate)))
+            if optimize_cfg:
+                (self.act_idx, self.prediction_err), _ = tc.optimize([self.act_idx, self.prediction_err], fold_constants=False)
 
         super().__init__(os.path.join(usecase, "dqn"), default_init=default_init, clean=clean_startup, cacheroot=cachedir)
         self.src_shape = self.src_outmask.shape()
