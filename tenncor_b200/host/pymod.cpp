@@ -246,6 +246,25 @@ PYBIND11_MODULE(_tenncor, m) {
         eteq::run({self}, to_set(ignored), max_version);
       }, py::arg("ignored") = ETensorsT{}, py::arg("max_version") = std::numeric_limits<size_t>::max(),
       "Evaluate on the device; the result stays in HBM (no host copy)")
+      .def("release_data", [](iTensor& self) {  // get_releasedata (eteq_ext.cpp:8-18): read through odata(), i.e. this read counts as one consumer
+        py::array out = to_array(self);
+        if (nullptr != dynamic_cast<iFunctor*>(&self)) { auto once = self.device().odata(); (void)once; }  // leaf storage has no lifetime to spend
+        return out;
+      }, "Host copy of the current data that spends one of the result's planned reads (a temporary is released after its last one)")
+      .def("release_get", [](TensptrT self, ETensorsT ignored, size_t max_version) {  // ETensor::calc_release (etens.hpp:165-176)
+        eteq::run({self}, to_set(ignored), max_version);
+        py::array out = to_array(*self);
+        { auto once = self->device().odata(); (void)once; }
+        return out;
+      }, py::arg("ignored") = ETensorsT{}, py::arg("max_version") = std::numeric_limits<size_t>::max(),
+      "Evaluate, return the result and release the target's buffer back to the arena")
+      .def("cache", [](iTensor& self) {  // Observable::cache_init (eteq_ext.cpp:163-170, functor.hpp:229-243)
+        if (nullptr == dynamic_cast<eigen::Observable*>(&self)) return;
+        if (auto op = dynamic_cast<cuda::DevOp*>(&self.device())) op->pin();
+      }, "Keep this functor's result across its consumers' reads (evaluations that name it in `ignored` read it as data)")
+      .def("tag", [](iTensor& self, const std::string& key, const std::string& val) {  // eteq_ext.cpp:193-201
+        if (auto f = dynamic_cast<iFunctor*>(&self)) f->add_attr(key, std::make_unique<marsh::String>(val));
+      }, py::arg("key"), py::arg("val"), "Attach a string attribute to a functor")
       .def("label", [](const iTensor& self) { return self.to_string(); }, "iTensor::to_string: a leaf's label / constant value, a functor's opcode name")
       .def("is_leaf", [](const iTensor& self) { return nullptr == dynamic_cast<const iFunctor*>(&self); })
       .def("usage", [](const iTensor& self) -> std::string {  // teq::get_usage_name (internal/teq/src/ileaf.cpp:12-35); "" for functors

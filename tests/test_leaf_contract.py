@@ -125,3 +125,25 @@ def test_subscriptions():  # OBSERVABLE.Subscriptions / CopyMove (internal/eigen
     other = tc.api.abs(lf)
     parent.update_child(other, 0)                               # re-pointing a reader moves its subscription
     assert obs.nsubs() == 0 and other.nsubs() == 1
+
+
+def test_etensor_tag_and_cache():  # ETensor.tag / .cache of the reference's python module (tenncor/python/eteq_ext.cpp:163-201)
+    lf = tc.variable(BIG.astype(np.float64), "leaf")
+    f = tc.api.sin(tc.api.neg(lf))
+    f.tag("recovery", "act_idx")
+    assert tc.dump_graph([f])[-1]["attrs"]["recovery"] == "act_idx"
+    lf.tag("ignored", "on a leaf")                               # only functors carry attributes
+    T = tc.testing
+    arg = f.args()[0]
+    T.mock_data(arg, 100)
+    T.stub_launch(f)
+    memory = T.CountingMemory()
+    f.cache()                                                    # Functor::cache_init: the result survives its planned reads
+    T.holder_assign(f, 1, memory)
+    ptr = T.holder_ptr(f)
+    T.holder_read(f)
+    T.holder_read(f)
+    assert T.holder_ptr(f) == ptr and [k for k, _, _ in memory.log()] == ["allocate"]
+    for name in ("release_data", "release_get", "get", "data", "calc"):
+        assert hasattr(f, name)
+    np.testing.assert_array_equal(lf.release_data(), BIG)        # on a leaf: a plain read
