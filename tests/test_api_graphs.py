@@ -154,3 +154,25 @@ def test_training_graph_survives_save_and_load(tmp_path):  # LAYRTest.test_conte
     assert len(roots) == 1
     assert render_typed(roots[0]) == render_typed(train_err)
     assert "ASSIGN_SUB" in render_typed(train_err)
+
+
+def test_python_module_shims():  # names the reference's scripts use beyond the API proper (tenncor/python/eteq_ext.cpp)
+    assert tc.Shape([2647, 20]) == [2647, 20] and repr(tc.Shape([3])) == "Shape([3])"
+    assert tc.TenncorAPI(tc.global_context) is tc.api and isinstance(tc.global_context, tc.Context)
+    assert tc.optimize("cfg/optimizations.json") is None        # the rule-file form: accepted, nothing to rewrite in place
+    a = tc.variable(np.ones((2, 3)), "a")
+    twice = tc.api.sin(a) * tc.api.sin(a)                        # two structurally equal functors
+    (merged,), stats = tc.optimize([twice], fold_constants=False)
+    assert stats["merged"] == 1 and merged.args()[0] == merged.args()[1]
+    import tenncor_b200.compat as compat
+    import sys
+    keep = {name: sys.modules.get(name) for name in ("tenncor", "extenncor", "dbg")}
+    try:
+        names = compat.install()
+        assert {"tenncor", "extenncor.dqn_trainer", "dbg.compare", "dbg.print"} <= set(names)
+        import tenncor
+        assert tenncor is tc
+    finally:
+        for name in list(sys.modules):
+            if name.split(".")[0] in keep and keep[name.split(".")[0]] is None:
+                del sys.modules[name]
