@@ -147,3 +147,14 @@ def test_etensor_tag_and_cache():  # ETensor.tag / .cache of the reference's pyt
     for name in ("release_data", "release_get", "get", "data", "calc"):
         assert hasattr(f, name)
     np.testing.assert_array_equal(lf.release_data(), BIG)        # on a leaf: a plain read
+
+
+def test_const_encoding_and_usage_names():  # LEAF.ConstEncoding / GetUsage (internal/teq/test/test_leaf.cpp:10-33)
+    data = np.arange(1, 9, dtype=np.float64)
+    assert str(tc.constant(data[:1].reshape(()))) == "1"
+    assert str(tc.constant(data[:4])) == "[1\\2\\3\\4]"
+    assert str(tc.constant(data.reshape(2, 4))) == "[1\\2\\3\\4\\5\\...]"          # teq::Shape({4, 2}): five shown, then an ellipsis
+    assert str(tc.constant(data[:5])) == "[1\\2\\3\\4\\5]"
+    assert tc.constant(data[:4]).usage() == "constant"
+    assert tc.variable(data[:4], "v").usage() == "variable"
+    assert tc.placeholder(data[:4], "p").usage() == "placeholder"
