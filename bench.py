@@ -41,9 +41,12 @@ WORKLOADS = {
     "c1w": dict(kind="mlp", ninput=1024, nhidden=1024, noutput=512, nbatch=8192),
     "c3": dict(kind="mlp", ninput=784, nhidden=1024, noutput=10, nbatch=8192, one_hot=True),
     "c2": dict(kind="rbm", nvisible=784, nhidden=64, nbatch=4096),
-    "c4a": dict(kind="lstm", vocab=128, hidden=1024, seq=128, batch=None),
-    "c4": dict(kind="lstm", vocab=128, hidden=1024, seq=128, batch=64),
-    "c4gru": dict(kind="gru", vocab=128, hidden=1024, seq=128, batch=64),
+    # learning rate: the demo's adagrad 0.1 (demo/lstm/latin_demo.py:120-122) on a NLL summed over 8192 tokens diverges at this size
+    # — the CPU oracle of the reference path reaches inf at step 3 and NaN at step 4 as well — so the batched
+    # configs train with 0.01, which stays finite; the arithmetic per step is identical
+    "c4a": dict(kind="lstm", vocab=128, hidden=1024, seq=128, batch=None, learning_rate=0.01),
+    "c4": dict(kind="lstm", vocab=128, hidden=1024, seq=128, batch=64, learning_rate=0.01),
+    "c4gru": dict(kind="gru", vocab=128, hidden=1024, seq=128, batch=64, learning_rate=0.01),
     "c5": dict(kind="dqn", nobs=10, nunits=9, nactions=9, nbatch=4096),
     # SURVEY §8a row a12 (CONV; not one of BASELINE's configs): one conv2d layer + sigmoid trained like gd_demo. The CPU oracle of the
     # reference's padded-rank formulation needs minutes per step at this size: run with --cpu-seconds 0 to skip that leg.
@@ -151,19 +154,24 @@ def dominant_kernel_roofline(cabi, name, w, peaks):
             B = w["batch"] or 1
             M, K, N = B, w["vocab"] + w["hidden"], w["hidden"]
             label = "tcr_gemm gate (B x (N+H))((N+H) x H) 3xTF32"
-        a = cabi.to_device(rng.uniform(-1, 1, M * K).astype(np.float32))
+        # rotate over enough (A, C) buffer sets that no launch finds its operands in the 126 MB L2 (the weights B stay hot, as in the step)
+        set_bytes = 4 * (M * K + M * N)
+        nsets = max(3, min(8, int(np.ceil(3 * 126e6 / set_bytes))))
         b = cabi.to_device(rng.uniform(-1, 1, K * N).astype(np.float32))
-        c = cabi.empty(M * N, np.float32)
+        sets = [(cabi.to_device(rng.uniform(-1, 1, M * K).astype(np.float32)), cabi.empty(M * N, np.float32)) for _ in range(nsets)]
         d = cabi.GemmDesc(m=M, n=N, k=K, batch=1, a_sm=K, a_sk=1, b_sk=N, b_sn=1, c_sm=N, c_sn=1, dtype=F, precision=cabi.GEMM_3XTF32)
-        call = lambda: cabi.check(lib.tcr_gemm(C.c_void_p(a.ptr), C.c_void_p(b.ptr), C.c_void_p(c.ptr), C.byref(d)))  # noqa: E731
 
-        def timed(iters=20):
-            for _ in range(3):
-                call()
+        def call(i):
+            a, c = sets[i % nsets]
+            cabi.check(lib.tcr_gemm(C.c_void_p(a.ptr), C.c_void_p(b.ptr), C.c_void_p(c.ptr), C.byref(d)))
+
+        def timed(iters=24):
+            for i in range(nsets):
+                call(i)
             cabi.sync()
             start()
-            for _ in range(iters):
-                call()
+            for i in range(iters):
+                call(i)
             return stop_ms() / iters
 
         ms = timed()
@@ -177,7 +185,8 @@ def dominant_kernel_roofline(cabi, name, w, peaks):
                 "frac": round(flops / ms / 1e9 / peak, 4), "traffic": None, "ms_per_launch": round(ms, 5),
                 "issued_mma_frac": round(3 * flops / ms / 1e9 / peak, 4),  # 3xTF32 issues 3 TF32 MMAs per algorithmic MMA
                 "tf32_variant": {"achieved": round(flops / ms_tf32 / 1e9, 2), "frac": round(flops / ms_tf32 / 1e9 / peak, 4), "ms_per_launch": round(ms_tf32, 5)},
-                "peak_source": "0.5 x measured bf16_tflops (MEASURED_PEAKS.json)" if "bf16_tflops" in peaks else "0.5 x fallback 1590"}
+                "peak_source": "0.5 x measured bf16_tflops (MEASURED_PEAKS.json)" if "bf16_tflops" in peaks else "0.5 x fallback 1590",
+                "buffers": "%d rotating (A, C) sets of %.0f MB: operands are not L2-resident between launches" % (nsets, set_bytes / 1e6)}
     # RBM: HBM-bound elementwise/RNG over [784, B]; DQN: the same kernel over [nobs, B] (latency-bound at that size)
     width = w.get("nvisible", w.get("nobs", 1))
     n = width * w["nbatch"]
@@ -197,10 +206,108 @@ def dominant_kernel_roofline(cabi, name, w, peaks):
             "peak_source": "measured hbm_gbs (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650"}
 
 
-def cpu_reference_steps(cfg, gen, budget_s, max_steps, target=None):
+def hbm_micro(cabi, peaks):
+    """The HBM half of the metric (M-ew at 2^26 and 2^28, M-red on [4096, 65536], M-lay), each case timed with CUDA
+    events on the library stream through the C-ABI: achieved = ALGORITHMIC bytes / time, frac = achieved / measured copy bandwidth.
+    Every operand set is larger than the 126 MB L2, or rotates over 8 disjoint copies when the case's own shape is smaller."""
+    lib = cabi.lib()
+    F = cabi.FLOAT
+    peak = peaks.get("hbm_gbs", 6650.0)
+    start, stop_ms = event_timer(cabi)
+    rng = np.random.default_rng(5)
+    n28 = 1 << 28
+    seed = cabi.to_device(rng.uniform(-4, 4, 1 << 24).astype(np.float32))
+    bufs = [cabi.empty(n28, np.float32) for _ in range(4)]
+    for k, buf in enumerate(bufs[:3]):  # fill by replication on the device (values only matter for range)
+        for j in range(16):
+            cabi.check(lib.tcr_d2d(C.c_void_p(buf.ptr + 4 * j * (1 << 24)), C.c_void_p(seed.ptr), C.c_size_t(4 << 24)))
+    a, b, c, out = bufs
+    # PROD needs values near 1: |x|/4 * 0.2 + 0.9
+    P = lambda x, off=0: C.c_void_p(x.ptr + 4 * off)  # noqa: E731
+    res = {}
+
+    def timeit(fn, iters):
+        for i in range(2):
+            fn(i)
+        cabi.sync()
+        start()
+        for i in range(iters):
+            fn(i)
+        return stop_ms() / iters
+
+    def rec(name, ms, nbytes):
+        gbps = nbytes / ms / 1e6
+        res[name] = {"GBps": round(gbps, 1), "frac": round(gbps / peak, 3), "ms": round(ms, 4)}
+
+    for log2n in (26, 28):
+        n = 1 << log2n
+        it = 10 if log2n == 26 else 5
+        rot = (lambda i: (i % 4) * n) if log2n == 26 else (lambda i: 0)
+        for op in ("EXP", "SIGMOID", "TANH"):
+            rec("ew_%s_2^%d" % (op, log2n), timeit(lambda i: cabi.check(lib.tcr_unary(cabi.OP[op], P(a, rot(i)), P(out, rot(i)), C.c_int64(n), F)), it), 8 * n)
+        for op in ("ADD", "MUL"):
+            rec("ew_%s_2^%d" % (op, log2n), timeit(lambda i: cabi.check(lib.tcr_binary(cabi.OP[op], P(a, rot(i)), P(b, rot(i)), P(out, rot(i)), C.c_int64(n), F)), it), 12 * n)
+        progs = [cabi.make_program(F, (n, 1, 1), [(a.ptr + 4 * rot(i), F, (0, 0, 0)), (b.ptr + 4 * rot(i), F, (0, 0, 0)), (c.ptr + 4 * rot(i), F, (0, 0, 0))],
+                                   [(out.ptr + 4 * rot(i), F, 0)], [(cabi.OP["MUL"], 0, 0, 1), (cabi.OP["ADD"], 0, 0, 2), (cabi.OP["SIGMOID"], 0, 0)]) for i in range(4)]
+        rec("ew_fused_sigmoid(a*b+c)_2^%d" % log2n, timeit(lambda i: cabi.check(lib.tcr_elementwise(C.byref(progs[i % 4]))), it), 16 * n)
+        rec("ew_ASSIGN_SUB_2^%d" % log2n, timeit(lambda i: cabi.check(lib.tcr_assign(cabi.OP["ASSIGN_SUB"], P(out, rot(i)), P(a, rot(i)), C.c_int64(n), F)), it), 12 * n)
+    H = 1024
+    progs = [cabi.make_program(F, (H, (1 << 26) // H, 1), [(a.ptr + (i << 28), F, (0, 0, 0)), (b.ptr, F, (0, 1, 0))], [(out.ptr + (i << 28), F, 0)],
+                               [(cabi.OP["ADD"], 0, 0, 1), (cabi.OP["SIGMOID"], 0, 0)]) for i in range(4)]
+    rec("ew_fused_sigmoid(x+bias[1024])_[1024,65536]", timeit(lambda i: cabi.check(lib.tcr_elementwise(C.byref(progs[i % 4]))), 10), 8 * (1 << 26) + 4 * H)
+    # reductions on [4096, 65536] (= 2^28 elements); PROD reads a tensor of values near 1
+    R0, R1 = 4096, 65536
+    shp = cabi.shape8([R0, R1])
+    near1 = [cabi.make_program(F, (n28, 1, 1), [(a.ptr, F, (0, 0, 0))], [(c.ptr, F, 0)],
+                               [(cabi.EW_CONST, 1, 0, 0, 0, 0.025), (cabi.OP["MUL"], 0, 0, 1), (cabi.EW_CONST, 1, 0, 0, 0, 1.0), (cabi.OP["ADD"], 0, 0, 1)])]
+    cabi.check(lib.tcr_elementwise(C.byref(near1[0])))  # c = 1 + a / 40 in [0.9, 1.1]
+    small = cabi.empty(R1, np.float32)
+    for op in ("REDUCE_SUM", "REDUCE_MAX", "REDUCE_MIN", "REDUCE_PROD"):
+        src = c if op == "REDUCE_PROD" else a
+        for mask, nm, nout in ((1, "dim0", R1), (2, "dim1", R0), (3, "full", 1)):
+            rec("%s_%s_[4096,65536]" % (op, nm), timeit(lambda i: cabi.check(lib.tcr_reduce(cabi.OP[op], P(src), P(small), shp, C.c_uint32(mask), F)), 5), 4 * (n28 + nout))
+    for dim, nm, nout in ((0, "dim0", R1), (1, "dim1", R0), (8, "flat", 1)):
+        rec("ARGMAX_%s_[4096,65536]" % nm, timeit(lambda i: cabi.check(lib.tcr_argmax(P(a), P(small), shp, dim, F)), 5), 4 * (n28 + nout))
+    # layout
+    side = 8192
+    order = (C.c_int32 * 8)(1, 0, 2, 3, 4, 5, 6, 7)
+    rec("PERMUTE10_[8192,8192]", timeit(lambda i: cabi.check(lib.tcr_permute(P(a, (i % 4) * side * side), P(out, (i % 4) * side * side), cabi.shape8([side, side]), order, 4)), 10), 8 * side * side)
+    bc = (C.c_int64 * 8)(1, 65536, 1, 1, 1, 1, 1, 1)
+    rec("EXTEND_[1024]->[1024,65536]", timeit(lambda i: cabi.check(lib.tcr_extend(P(a), P(out, (i % 4) << 26), cabi.shape8([1024]), bc, 4)), 10), 4 * 1024 * 65536 + 4096)
+    s3 = [1024, 128, 64]
+    m3 = 1024 * 128 * 64
+    offs = (C.c_int64 * 8)(0, 32, 0, 0, 0, 0, 0, 0)
+    exts = (C.c_int64 * 8)(1024, 64, 64, 1, 1, 1, 1, 1)
+    rec("SLICE_mid_[1024,128,64]", timeit(lambda i: cabi.check(lib.tcr_slice(P(a, (i % 8) * m3), P(out, (i % 8) * m3), cabi.shape8(s3), offs, exts, 4)), 16), 8 * (m3 // 2))
+    lo = (C.c_int64 * 8)(0, 16, 0, 0, 0, 0, 0, 0)
+    rec("PAD_mid_[1024,128,64]", timeit(lambda i: cabi.check(lib.tcr_pad(P(a, (i % 8) * m3), P(out, (i % 8) * 2 * m3), cabi.shape8(s3), lo, lo, 4)), 16), 4 * (m3 + 1024 * 160 * 64))
+    shp2 = (C.c_int64 * 16)(*(cabi.shape8(s3)[:] + cabi.shape8(s3)[:]))
+    tabs = [(C.c_void_p * 2)(a.ptr + 4 * (i % 8) * m3, b.ptr + 4 * (i % 8) * m3) for i in range(8)]
+    rec("CONCAT_axis1_[1024,128,64]x2", timeit(lambda i: cabi.check(lib.tcr_concat(tabs[i % 8], shp2, 2, P(out, (i % 8) * 2 * m3), 1, 4)), 16), 16 * m3)
+    res["_note"] = {"peak_GBps": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+                    "bytes": "algorithmic: 4*(inputs un-broadcast + outputs) per element (SURVEY.md §8d)",
+                    "cache": "operands exceed L2 (126 MB) or rotate over disjoint copies"}
+    del bufs, a, b, c, out, seed, small
+    return res
+
+
+def host_threads():
+    """Threads the CPU legs may use: every core the process is allowed to run on. torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers, which would silently throttle the BLAS inside the oracle, so the count is
+    set explicitly (threadpoolctl) instead of being inherited."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_steps(cfg, gen, budget_s, steps, warmup=1, target=None):
     """The oracle port of the reference's CPU path: node-by-node numpy evaluation of the dumped
-    graph (TravEvaluator order, one unfused op per functor, in-place ASSIGNs)."""
+    graph (TravEvaluator order, one unfused op per functor, in-place ASSIGNs). Runs `warmup` untimed and then `steps`
+    timed steps; a step that is too slow for that (c4: ~7 s) stops at `budget_s` with at least two timed steps.
+    Returns (seconds per step, timed steps, warm-up steps, BLAS threads)."""
     import tenncor_b200 as tc
+    from threadpoolctl import threadpool_limits, threadpool_info
     from oracle import tcr_oracle as orc  # cpu_baseline leg only: never on the product path
     orc.set_baseline_mode(True)
     target = cfg.train if target is None else target
@@ -211,17 +318,22 @@ def cpu_reference_steps(cfg, gen, budget_s, max_steps, target=None):
     feed_ids = tc.dump_ids([target] + list(cfg.feeds.values()), None)
     rng = np.random.default_rng(0)
     times = []
-    t_begin = time.perf_counter()
-    while len(times) < max_steps and (time.perf_counter() - t_begin < budget_s or len(times) < 2):
-        batch = gen(rng)
-        t0 = time.perf_counter()
-        for feed, arr in zip(cfg.feeds.values(), batch):
-            if feed_ids[feed] < len(tape) and tape[feed_ids[feed]]["kind"] == "leaf":  # inference does not read the labels
-                tape[feed_ids[feed]]["data"][...] = arr.reshape(-1)
-        orc.eval_tape(tape)
-        times.append(time.perf_counter() - t0)
-    steady = times[1:] if len(times) > 1 else times
-    return float(np.median(steady)), len(times)
+    nthreads = host_threads()
+    with threadpool_limits(limits=nthreads):
+        blas = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        t_begin = time.perf_counter()
+        for it in range(warmup + steps):
+            if it >= warmup + 2 and time.perf_counter() - t_begin > budget_s:
+                break
+            batch = gen(rng)
+            t0 = time.perf_counter()
+            for feed, arr in zip(cfg.feeds.values(), batch):
+                if feed_ids[feed] < len(tape) and tape[feed_ids[feed]]["kind"] == "leaf":  # inference does not read the labels
+                    tape[feed_ids[feed]]["data"][...] = arr.reshape(-1)
+            orc.eval_tape(tape)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    return float(np.mean(times)), len(times), warmup, (max(blas) if blas else 1)
 
 
 def e2e_entry(world, steps, pipelined_ms, serial_ms, h2d, d2h):
@@ -254,6 +366,8 @@ def main():
     ap.add_argument("--evaluator", default="plan", choices=["plan", "node"])
     ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "exact"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--extras", default="auto", choices=["auto", "none"],
+                    help="auto: the default c3 line also carries the LSTM sub-record (`workloads.c4`) and, at N = 1, the HBM micro-benchmarks (`micro`)")
     ap.add_argument("--mode", default="train", choices=["train", "inference"],
                     help="train: one apply_update step (the metric); inference: forward pass of the model only (BASELINE config 3 'inference+training')")
     args = ap.parse_args()
@@ -279,14 +393,14 @@ def main():
             return 0
         cfg, gen, w = build_config(args.workload)
         target = pick_target(cfg, args.mode)
-        med, nsteps = cpu_reference_steps(cfg, gen, budget_s=max(args.cpu_seconds, 10.0) * 4, max_steps=args.steps + args.warmup, target=target)
-        cores = os.cpu_count()
-        line = {"impl": "reference", "metric": metric, "value": round(1.0 / med, 4), "unit": "steps/s", "n_gpus": 0, "steps": nsteps,
-                "warmup": 1, "ms_per_step": round(med * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        sec, nsteps, nwarm, threads = cpu_reference_steps(cfg, gen, budget_s=max(args.cpu_seconds, 10.0) * 12, steps=args.steps, warmup=args.warmup, target=target)
+        sample = "%d timed full steps (after %d warm-up) of the same graph on the host: numpy oracle of the Eigen path, one thread per elementwise op, %d BLAS threads in GEMM" % (nsteps, nwarm, threads)
+        line = {"impl": "reference", "metric": metric, "value": round(1.0 / sec, 4), "unit": "steps/s", "n_gpus": args.gpus, "steps": nsteps,
+                "warmup": nwarm, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": dict(wdesc, desc=cfg.desc, batch_per_gpu=w.get("nbatch", w.get("batch"))),
-                "cpu_baseline": {"value": round(1.0 / med, 4), "unit": "steps/s", "cores": cores, "kind": "port",
-                                 "sample": "%d full steps of the same graph (numpy oracle: 1 thread per elementwise op, BLAS threads in GEMM)" % nsteps},
-                "e2e": {"value": round(1.0 / med, 4), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "cpu_baseline": {"value": round(1.0 / sec, 4), "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": round(1.0 / sec, 4), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "one host process evaluates one local batch per step regardless of --gpus (the reference's CPU path has no multi-device mode)"}
         print(json.dumps(line), flush=True)
         return 0
 
@@ -300,98 +414,157 @@ def main():
     cabi.init(local_rank)
     tc.set_evaluator(args.evaluator)
     tc.set_matmul_precision(args.precision)
+    dp_parity = None
     if world > 1:
-        ids = [tc.dp.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        mean_loss = WORKLOADS[args.workload]["kind"] in ("mlp", "rbm", "dqn", "conv")  # reduce_mean losses; the LSTM's NLL is a sum
-        tc.dp.init(rank, world, ids[0], mean_reduce=mean_loss)
-
-    cfg, gen, w = build_config(args.workload)
-    target = pick_target(cfg, args.mode)
-    rng = np.random.default_rng(1000 + rank)
-    feeds = list(cfg.feeds.values()) if args.mode == "train" else [cfg.feeds["x"]]  # inference reads no labels
-    host = [pinned_array(cabi, f.shape()) for f in feeds]
-    for buf, arr in zip(host, gen(rng)):
-        buf[...] = arr
-    h2d = int(sum(b.nbytes for b in host))
+        # sharded-vs-full-batch parity on this box's GPUs, before anything is timed (tests/test_dp_nccl_gpu.py is skipped on 1-GPU boxes)
+        from tools import dp_check
+        dp_parity = dp_check.run_check(dist, rank, world)  # initialises the communicator
+        if not dp_parity["ok"]:
+            if rank == 0:
+                sys.stderr.write("bench.py: data-parallel parity check failed: %s\n" % json.dumps(dp_parity))
+            return 4
 
     def barrier():
         tc.sync()
         if dist is not None:
             dist.barrier()
 
-    start, stop_ms = event_timer(cabi)
-
-    # resident: batch uploaded once, timed region = graph evaluation only
-    for f, buf in zip(feeds, host):
-        f.assign(buf)
-    for _ in range(args.warmup):
-        target.calc()
-        for f in feeds:
-            f.touch()  # new input version, data stays resident: the next step recomputes everything
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = cabi.lib().tcr_launch_count()
-    start()
-    for _ in range(args.steps):
-        for f in feeds:
-            f.touch()
-        target.calc()
-    ms_total = stop_ms()
-    launches = int(cabi.lib().tcr_launch_count() - launches0)
-    barrier()
-    plan = tc.plan_stats()
-
-    # end to end, serial: pinned host batch -> H2D -> step -> D2H of the loss, every step, one after the other
-    loss = None
-    for _ in range(args.warmup):
-        for f, buf in zip(feeds, host):
-            f.assign(buf)
-        loss = target.get()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for f, buf in zip(feeds, host):
-            f.assign(buf)
-        loss = target.get()
-    tc.sync()
-    e2e_serial_s = time.perf_counter() - t0
-    barrier()
-    # end to end, pipelined (the headline): the same per-step H2D of the batch and D2H of the loss, but the batch of
-    # step i+1 crosses PCIe on the copy stream (EVariable.prefetch) while step i computes; commit() swaps it in
-    for f, buf in zip(feeds, host):
-        f.prefetch(buf)
-    for _ in range(args.warmup):
-        for f in feeds:
-            f.commit()
-        for f, buf in zip(feeds, host):
-            f.prefetch(buf)
-        loss = target.get()
-    tc.sync()
-    tc.sync_prefetch()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for f in feeds:
-            f.commit()
-        for f, buf in zip(feeds, host):
-            f.prefetch(buf)
-        loss = target.get()
-    tc.sync()
-    tc.sync_prefetch()  # K copies were issued inside the timed region: all of them must have landed
-    e2e_s = time.perf_counter() - t0
-    barrier()
-    clocks = sampler.summary()
-    d2h = int(np.asarray(loss).nbytes)
-
-    if dist is not None:
+    def reduce_max(values):
+        if dist is None:
+            return [float(v) for v in values]
         import torch
-        t = torch.tensor([ms_total, e2e_s * 1e3, e2e_serial_s * 1e3], dtype=torch.float64)
+        t = torch.tensor(values, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms, e2e_serial_ms = float(t[0]), float(t[1]), float(t[2])
-    else:
-        e2e_ms, e2e_serial_ms = e2e_s * 1e3, e2e_serial_s * 1e3
+        return [float(v) for v in t]
+
+    def measure(name, steps, warmup, mode):
+        """resident + end-to-end timing of one workload; every rank takes part (collectives), results are max over ranks"""
+        if world > 1:
+            tc.dp.set_mean_reduce(WORKLOADS[name]["kind"] in ("mlp", "rbm", "dqn", "conv"))  # reduce_mean losses; the LSTM's NLL is a sum
+        cfg, gen, w = build_config(name)
+        target = pick_target(cfg, mode)
+        rng = np.random.default_rng(1000 + rank)
+        feeds = list(cfg.feeds.values()) if mode == "train" else [cfg.feeds["x"]]  # inference reads no labels
+        host = [pinned_array(cabi, f.shape()) for f in feeds]
+        for buf, arr in zip(host, gen(rng)):
+            buf[...] = arr
+        h2d = int(sum(b.nbytes for b in host))
+        start, stop_ms = event_timer(cabi)
+
+        # resident: batch uploaded once, timed region = graph evaluation only
+        for f, buf in zip(feeds, host):
+            f.assign(buf)
+        for _ in range(warmup):
+            target.calc()
+            for f in feeds:
+                f.touch()  # new input version, data stays resident: the next step recomputes everything
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = cabi.lib().tcr_launch_count()
+        start()
+        for _ in range(steps):
+            for f in feeds:
+                f.touch()
+            target.calc()
+        ms_total = stop_ms()
+        launches = int(cabi.lib().tcr_launch_count() - launches0)
+        barrier()
+        plan = tc.plan_stats()
+
+        # end to end, serial: pinned host batch -> H2D -> step -> D2H of the loss, every step, one after the other
+        loss = None
+        for _ in range(warmup):
+            for f, buf in zip(feeds, host):
+                f.assign(buf)
+            loss = target.get()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for f, buf in zip(feeds, host):
+                f.assign(buf)
+            loss = target.get()
+        tc.sync()
+        e2e_serial_s = time.perf_counter() - t0
+        barrier()
+        # end to end, pipelined (the headline): the same per-step H2D of the batch and D2H of the loss, but the batch of
+        # step i+1 crosses PCIe on the copy stream (EVariable.prefetch) while step i computes; commit() swaps it in
+        for f, buf in zip(feeds, host):
+            f.prefetch(buf)
+        for _ in range(warmup):
+            for f in feeds:
+                f.commit()
+            for f, buf in zip(feeds, host):
+                f.prefetch(buf)
+            loss = target.get()
+        tc.sync()
+        tc.sync_prefetch()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for f in feeds:
+                f.commit()
+            for f, buf in zip(feeds, host):
+                f.prefetch(buf)
+            loss = target.get()
+        tc.sync()
+        tc.sync_prefetch()  # K copies were issued inside the timed region: all of them must have landed
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        clocks = sampler.summary()
+        d2h = int(np.asarray(loss).nbytes)
+        ms_total, e2e_ms, e2e_serial_ms = reduce_max([ms_total, e2e_s * 1e3, e2e_serial_s * 1e3])
+        final_loss = float(np.asarray(loss).reshape(-1)[0])
+        # replicas must hold the same weights after the same all-reduced updates
+        replicas = None
+        if dist is not None and mode == "train":
+            sums = [float(np.asarray(v.data(), np.float64).sum()) for v in cfg.variables]
+            allsums = [None] * world
+            dist.all_gather_object(allsums, sums)
+            dev = max(abs(a - b) / (abs(b) + 1e-30) for other in allsums for a, b in zip(other, allsums[0]))
+            replicas = {"variables": len(sums), "max_rel_dev_of_checksums_vs_rank0": dev, "ok": bool(dev < 1e-6)}
+        finite = bool(np.isfinite(final_loss))
+        if dist is not None:
+            finite = bool(reduce_max([0.0 if finite else 1.0])[0] == 0.0)
+        return dict(cfg=cfg, gen=gen, w=w, target=target, ms_total=ms_total, launches=launches, plan=plan, e2e_ms=e2e_ms, e2e_serial_ms=e2e_serial_ms,
+                    h2d=h2d, d2h=d2h, final_loss=final_loss, finite=finite, clocks=clocks, replicas=replicas)
+
+    def sub_record(name, m, steps):
+        """compact record of a secondary workload (same timing rules) for the `workloads` key"""
+        w = m["w"]
+        ms_step = m["ms_total"] / steps
+        flops = m["cfg"].flops_per_step
+        rec = {"metric": "train steps/sec", "value": round(world * 1e3 / ms_step, 3), "unit": "steps/s", "ms_per_step": round(ms_step, 4), "steps": steps,
+               "config": dict({"workload": name}, **WORKLOADS[name], desc=m["cfg"].desc, batch_per_gpu=w.get("nbatch", w.get("batch")), matmul=args.precision),
+               "tflops": round(flops / ms_step / 1e9, 2), "launches_per_step": round(m["launches"] / steps, 1), "plan": m["plan"],
+               "e2e": e2e_entry(world, steps, m["e2e_ms"], m["e2e_serial_ms"], m["h2d"], m["d2h"]), "final_loss": m["final_loss"]}
+        if m["replicas"] is not None:
+            rec["replicas"] = m["replicas"]
+        return rec
+
+    main_m = measure(args.workload, args.steps, args.warmup, args.mode)
+    cfg, gen, w, target = main_m["cfg"], main_m["gen"], main_m["w"], main_m["target"]
+    rc = 0
+    if not main_m["finite"]:
+        sys.stderr.write("bench.py: final loss of %s is not finite (%r): the run is invalid\n" % (args.workload, main_m["final_loss"]))
+        rc = 5
+    if main_m["replicas"] is not None and not main_m["replicas"]["ok"]:
+        sys.stderr.write("bench.py: replicas diverged: %s\n" % json.dumps(main_m["replicas"]))
+        rc = 6
+
+    # the LSTM half of the metric ("gd MLP, LSTM"): a sub-record in the same line, same timing rules, fewer steps
+    extra = {}
+    extras = [] if args.extras == "none" or args.mode != "train" else [x for x in ("c4",) if x != args.workload and args.workload == "c3"]
+    for name in extras:
+        sub_steps = max(3, min(args.steps, 10))
+        m = measure(name, sub_steps, 3, "train")
+        extra[name] = sub_record(name, m, sub_steps)
+        if not m["finite"]:
+            sys.stderr.write("bench.py: final loss of %s is not finite (%r)\n" % (name, m["final_loss"]))
+            rc = 5
+        if m["replicas"] is not None and not m["replicas"]["ok"]:
+            rc = 6
+        del m
 
     if rank == 0:
         peaks = {}
@@ -399,25 +572,29 @@ def main():
         if os.path.exists(pk):
             peaks = json.load(open(pk))
         roof = dominant_kernel_roofline(cabi, args.workload, w, peaks)
-        try:  # DRAM traffic of the dominant kernel from the committed ncu capture (null when none was taken)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
+        try:  # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
             if tr:
                 roof["traffic"] = tr["bytes"]
                 roof["traffic_source"] = tr["source"]
         except Exception:
             pass
-        if args.cpu_seconds > 0:
-            med, nsteps = cpu_reference_steps(cfg, gen, budget_s=args.cpu_seconds, max_steps=20, target=target)
-            cpu_baseline = {"value": round(1.0 / med, 4), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
-                            "sample": "%d full steps of the same graph on the host (numpy oracle of the Eigen path)" % nsteps}
+        micro = None
+        if world == 1 and args.extras != "none" and args.workload == "c3":
+            micro = hbm_micro(cabi, peaks)
+        if args.cpu_seconds > 0 and world == 1:
+            sec, nsteps, nwarm, threads = cpu_reference_steps(cfg, gen, budget_s=args.cpu_seconds, steps=20, warmup=1, target=target)
+            cpu_baseline = {"value": round(1.0 / sec, 4), "unit": "steps/s", "cores": threads, "kind": "port",
+                            "sample": "%d full steps of the same graph on the host (numpy oracle of the Eigen path, %d BLAS threads)" % (nsteps, threads)}
         else:
-            cpu_baseline = None  # --cpu-seconds 0: the CPU leg was skipped on request
-        ms_step = ms_total / args.steps
+            cpu_baseline = None  # timed on rank 0 at N = 1 only (or skipped with --cpu-seconds 0)
+        ms_step = main_m["ms_total"] / args.steps
         # inference = forward only: a third of forward + both gradients for the GEMM-dominated models (approximate for c3, whose
         # first layer has no input gradient: 2*B*(in*hid + hid*out) exactly)
         flops_step = cfg.flops_per_step if args.mode == "train" else (2 * w["nbatch"] * (w["ninput"] * w["nhidden"] + w["nhidden"] * w["noutput"]) if "ninput" in w else cfg.flops_per_step // 3)
         line = {
-            "metric": metric, "value": round(world * 1e3 / ms_step, 3), "unit": "steps/s (sum over GPUs of per-GPU steps/s; each step = one local batch)",
+            "metric": metric, "value": round(world * 1e3 / ms_step, 3), "unit": "steps/s",
+            "unit_note": "sum over GPUs of per-GPU steps/s; each step = one local batch",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(wdesc, desc=cfg.desc, batch_per_gpu=w.get("nbatch", w.get("batch")), global_batch=(w.get("nbatch") or w.get("batch") or 1) * world,
@@ -425,19 +602,29 @@ def main():
                            cache="step working set %s L2 (126 MB); no flush" % ("exceeds" if args.workload in ("c3", "c1w", "c4", "c4gru", "c2", "conv") else "is resident in")),
             "samples_per_s": round(world * (w.get("nbatch") or w.get("batch") or 1) * 1e3 / ms_step, 1),
             "flops_per_step": flops_step, "tflops": round(flops_step / ms_step / 1e9, 2),
-            "clocks": clocks,
-            "e2e": e2e_entry(world, args.steps, e2e_ms, e2e_serial_ms, h2d, d2h),
-            "gpu_launches": launches, "launches_per_step": round(launches / args.steps, 1), "plan": plan,
+            "clocks": main_m["clocks"],
+            "e2e": e2e_entry(world, args.steps, main_m["e2e_ms"], main_m["e2e_serial_ms"], main_m["h2d"], main_m["d2h"]),
+            "gpu_launches": main_m["launches"], "launches_per_step": round(main_m["launches"] / args.steps, 1), "plan": main_m["plan"],
             "roofline": roof,
             "cpu_baseline": cpu_baseline,
-            "final_loss": float(np.asarray(loss).reshape(-1)[0]),
+            "final_loss": main_m["final_loss"],
         }
+        if extra:
+            line["workloads"] = extra
+        if micro is not None:
+            line["micro"] = micro
+        if dp_parity is not None:
+            line["dp_parity"] = dp_parity
+        if main_m["replicas"] is not None:
+            line["replicas"] = main_m["replicas"]
         print(json.dumps(line), flush=True)
+    del cfg, gen, target, main_m
     if dist is not None:
-        dist.barrier()  # rank 0 may still be in its CPU-baseline leg: leave together
+        dist.barrier()  # rank 0 may still be in its micro-benchmark leg: leave together
         tc.dp.shutdown()
         dist.destroy_process_group()
-    return 0
+    tc.shutdown()  # plans, graphs and the arena go before the interpreter tears the CUDA context down
+    return rc
 
 
 def _watchdog(seconds):
@@ -459,4 +646,4 @@ if __name__ == "__main__":
     rc = main()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(rc)  # skip interpreter teardown: nothing after the JSON line may block the launcher
+    sys.exit(rc)  # normal interpreter teardown (atexit hooks of the harness run); the watchdog above is the only hard exit

@@ -13,7 +13,6 @@ def install():
     aliases = {
         "tenncor": tenncor_b200,
         "extenncor": extenncor, "extenncor.dqn_trainer": extenncor.dqn_trainer, "extenncor.trainer_cache": extenncor.trainer_cache,
-        "extenncor.embed": extenncor.embed,
         "dbg": dbg, "dbg.compare": dbg.compare, "dbg.print": dbg.print,
     }
     for name, module in aliases.items():

@@ -48,10 +48,12 @@ int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
 // ring wraps (2^20 counters), and launches of different plans are ordered on the library stream.
 static int* g_counter_ring = nullptr;
 static size_t g_counter_pos = 0;
+static std::mutex g_counter_mu;
 constexpr size_t COUNTER_RING = 1u << 20;
 
 int* counter_ring_take(int n) {
   if (g_counter_ring == nullptr) return nullptr;
+  std::lock_guard<std::mutex> lk(g_counter_mu);
   if (n < 1) n = 1;
   if (g_counter_pos + (size_t)n > COUNTER_RING) g_counter_pos = 0;
   int* p = g_counter_ring + g_counter_pos;
@@ -114,6 +116,8 @@ int tcr_device_count(void) {
 int tcr_init(int device) {
   State& s = state();
   if (s.ready && s.device == device) return TCR_OK;
+  // the stream, the counter ring, the prefetch stream and every arena block belong to the device of the first init
+  TCR_ARG(!s.ready, "tcr_init: already initialised on device %d; call tcr_shutdown() before switching to device %d", s.device, device);
   int n = tcr_device_count();
   if (n <= 0) {
     set_error("tcr_init: no CUDA device visible (this back end has no CPU fallback)");
@@ -158,6 +162,11 @@ int tcr_shutdown(void) {
     g_copy_pending = g_commit_recorded = false;
   }
   tcr_arena_trim();
+  if (g_counter_ring) {
+    cudaFree(g_counter_ring);
+    g_counter_ring = nullptr;
+    g_counter_pos = 0;
+  }
   cudaStreamDestroy(s.stream);
   s.stream = nullptr;
   s.ready = false;

@@ -37,6 +37,7 @@ int rank() { return g_rank; }
 int size() { return g_size; }
 bool active() { return g_size > 1; }
 double scale() { return g_mean ? 1.0 / g_size : 1.0; }
+void set_mean_reduce(bool mean_reduce) { g_mean = mean_reduce; }
 
 layr::ETensorsT wrap_gradients(const layr::ETensorsT& grads) {
   if (!active()) return grads;

@@ -25,6 +25,8 @@ int rank();
 int size();
 bool active();
 double scale();
+/// gradients derived from now on are scaled by 1/nranks after the exchange (batch-mean losses) or left as sums
+void set_mean_reduce(bool mean_reduce);
 
 /// identity when no group is active; otherwise each gradient is wrapped in a marked IDENTITY
 layr::ETensorsT wrap_gradients(const layr::ETensorsT& grads);

@@ -922,6 +922,14 @@ struct Plan {
       for (size_t i = 0; i < nodes.size(); ++i) {
         PNode& n = nodes[i];
         if (!n.func || n.is_view) continue;
+        if (n.gemm_src >= 0 && nodes[n.gemm_src].conv < 0) {
+          // a fused GEMM step reads the product's operands (and its bias) as real buffers
+          for (int a : nodes[n.gemm_src].args) {
+            PNode& r = nodes[nodes[a].root];
+            if (r.is_extend) r.needs_mat = true;
+          }
+          if (n.gemm_bias >= 0 && nodes[nodes[n.gemm_bias].root].is_extend) nodes[nodes[n.gemm_bias].root].needs_mat = true;
+        }
         if (n.inlined || n.gemm_src >= 0) continue;  // absorbed into a GEMM epilogue: reads nothing itself
         bool ew_consumer = n.is_ew;
         for (size_t k = 0; k < n.args.size(); ++k) {

@@ -766,6 +766,12 @@ PYBIND11_MODULE(_tenncor, m) {
 
   // ---- back-end controls
   m.def("sync", [] { cuda::sync(); }, "Wait for all queued device work");
+  m.def("shutdown", [] {
+    if (tcr_stream() == nullptr) return;  // never initialised
+    cuda::drop_all_plans();
+    tcr_sync();
+    tcr_prefetch_sync();
+  }, "Destroy every cached plan (and its CUDA graph) and drain the device: call before the interpreter exits");
   m.def("launch_count", [] { return tcr_launch_count(); });
   m.def("sync_prefetch", [] { cuda::check(tcr_prefetch_sync(), "tcr_prefetch_sync"); }, "Wait for input copies started by EVariable.prefetch");
   m.def("set_matmul_precision", [](const std::string& p) {
@@ -1059,6 +1065,7 @@ PYBIND11_MODULE(_tenncor, m) {
   dpm.def("unique_id", [] { return py::bytes(dp::unique_id()); });
   dpm.def("init", [](int rank, int nranks, py::bytes id, bool mean_reduce) { dp::init(rank, nranks, std::string(id), mean_reduce); },
           py::arg("rank"), py::arg("nranks"), py::arg("id") = py::bytes(""), py::arg("mean_reduce") = true);
+  dpm.def("set_mean_reduce", &dp::set_mean_reduce, py::arg("mean_reduce"));
   dpm.def("shutdown", &dp::shutdown);
   dpm.def("rank", &dp::rank);
   dpm.def("size", &dp::size);

@@ -157,16 +157,3 @@ def _leaves(root):
             out.append(t)
         stack.extend(t.args())
     return out
-
-
-def test_embedding_pair():  # extenncor/embed.py: two dense layers over caller-visible kernels + vocabulary look-ups
-    from tenncor_b200.extenncor.embed import make_embedding, vdistance
-    words = ["natural", "language", "processing", "fun"]
-    emb = make_embedding(words, 3)
-    assert len(emb) == 4 and emb.onehot("processing") == [0, 0, 1, 0] and emb.onehot("absent") is None and emb.get_vec("absent") is None
-    kernels = [v for v in emb.embedding.get_storage() if str(v) == "to_vec"]
-    assert kernels == [emb.weight] and emb.weight.shape() == [4, 3]           # the layer trains the very variable the look-ups read
-    assert [str(v) for v in emb.exbedding.get_storage() if v.shape() == [3, 4]] == ["to_word"]
-    model = tc.api.layer.link([emb.embedding, emb.exbedding, tc.api.layer.bind(tc.api.softmax)])
-    assert model.connect(tc.variable(np.zeros(4, dtype=np.float64), "input")).shape() == [4]
-    assert abs(vdistance(np.array([1., 0.]), np.array([1., 1.])) - np.sqrt(0.5)) < 1e-12

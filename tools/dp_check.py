@@ -1,4 +1,5 @@
-"""Data-parallel parity on real GPUs (run under torchrun, one rank per GPU):
+"""Data-parallel parity on real GPUs (run under torchrun, one rank per GPU; also called by bench.py --gpus N before its
+timed region, because the pytest NCCL test is skipped on 1-GPU boxes):
 
 every rank trains the gd_demo-pattern MLP on its shard of a global batch with NCCL all-reduced
 gradients; rank 0 also trains a single-GPU replica on the WHOLE batch. With a reduce_mean loss and
@@ -15,25 +16,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    import torch.distributed as dist
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def run_check(dist, rank, world, dims=(64, 48, 16), per_gpu=96, steps=5):
+    """Must be called BEFORE tc.dp.init (the full-batch replica is built without a communicator); leaves the communicator
+    initialised with mean_reduce=True. Returns {"world", "weights_rel_err", "loss_rel_err", "ok"} on every rank."""
     import tenncor_b200 as tc
-    from tenncor_b200 import cabi, configs
-    os.environ["TCR_DEVICE"] = str(local)
-    cabi.init(local)
-    tc.set_evaluator("plan")
-    dims = (64, 48, 16)
-    per_gpu = 96
-    steps = 5
+    from tenncor_b200 import configs
     rng = np.random.default_rng(123)
     xs = rng.random((steps, per_gpu * world, dims[0]), dtype=np.float32)
     ys = rng.random((steps, per_gpu * world, dims[2]), dtype=np.float32)
 
-    # reference replica: the whole batch on this GPU, no communicator (built BEFORE dp.init)
+    # reference replica: the whole batch on this GPU, no communicator
     full = configs.mlp(dims[0], dims[1], dims[2], per_gpu * world, seed=7)
     full_losses = []
     for s in range(steps):
@@ -58,19 +50,34 @@ def main():
         worst = max(worst, float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30)))
     gathered = [None] * world
     dist.all_gather_object(gathered, (worst, losses))
-    ok = True
+    worst_all = max(g[0] for g in gathered)
+    # the returned loss is the post-update error on the LOCAL shard; its mean over ranks is the full-batch error
+    mean_losses = np.mean([g[1] for g in gathered], axis=0)
+    loss_err = float(np.max(np.abs(mean_losses - np.array(full_losses)) / np.abs(full_losses)))
+    ok = bool(worst_all < 1e-4 and loss_err < 1e-4)
+    return {"world": world, "weights_rel_err": worst_all, "loss_rel_err": loss_err, "ok": ok,
+            "what": "MLP %d-%d-%d, %d samples per rank, %d SGD steps: NCCL-sharded ranks vs one replica fed the whole batch" % (dims + (per_gpu, steps))}
+
+
+def main():
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import tenncor_b200 as tc
+    from tenncor_b200 import cabi
+    os.environ["TCR_DEVICE"] = str(local)
+    cabi.init(local)
+    tc.set_evaluator("plan")
+    res = run_check(dist, rank, world)
     if rank == 0:
-        worst_all = max(g[0] for g in gathered)
-        # the returned loss is the post-update error on the LOCAL shard; its mean over ranks is the full-batch error
-        mean_losses = np.mean([g[1] for g in gathered], axis=0)
-        loss_err = float(np.max(np.abs(mean_losses - np.array(full_losses)) / np.abs(full_losses)))
-        ok = worst_all < 1e-4 and loss_err < 1e-4
-        print(json.dumps({"world": world, "weights_rel_err": worst_all, "loss_rel_err": loss_err, "ok": ok}), flush=True)
+        print(json.dumps(res), flush=True)
     dist.barrier()
     tc.dp.shutdown()
     dist.destroy_process_group()
     sys.stdout.flush()
-    os._exit(0 if ok else 1)
+    sys.exit(0 if res["ok"] else 1)
 
 
 if __name__ == "__main__":
