@@ -311,6 +311,48 @@ typedef struct {
 
 int tcr_gemm(const void* a, const void* b, void* c, const tcr_gemm_desc* desc);
 
+/* Grouped / segmented product for small-batch recurrent steps (gemm_rnn.cu). For g < groups, s < segments:
+ *     out_g[m, n] = act_g( sum_s A_s[m, :] . B_{g,s}[:, n] + bias_g[n] )
+ * in ONE launch on the tensor cores (FLOAT, TF32 / 3xTF32). It is what the planner lowers these sub-graphs of the
+ * reference's unrolled recurrent layers to (cfg/tenncor/layer.yml:716-813):
+ *   - the gate products of one time step: CONTRACT(CONCAT(x_t, h_{t-1}), W_g) + EXTEND(b_g) through SIGMOID / TANH for every
+ *     gate g — groups = gates, segments = {x_t, h_{t-1}} (the CONCAT, operator.hpp:336-368, is never materialised),
+ *     b_trans = 0 (W_g is [K x n], n contiguous);
+ *   - the gradient reaching h_{t-1}: ADD over gates of CONTRACT(dpre_g, W_g) (backprop.hpp:269-359 + derive.cpp:49-51) —
+ *     groups = 1, segments = gates, b_trans = 1 (row j of W_g is column j of the product);
+ *   - optionally the LSTM cell update c_t = cand * in + c_{t-1} * forget, h_t = c_t * out (layer.yml:758-760) in the epilogue.
+ * A_s: [m x seg_k[s]] row-major with row pitch a_pitch[s]; B_{g,s}: b_trans == 0 -> [seg_k[s] x n] row-major, b_trans == 1 ->
+ * [n x seg_k[s]] row-major, row pitch b_pitch either way; out_g: [m x n] row-major, row pitch out_pitch. Pitches are in
+ * elements and multiples of 4, pointers 16-byte aligned (TMA). Split-K runs inside a thread-block cluster and is summed in a
+ * fixed order through distributed shared memory: deterministic, no workspace. */
+typedef struct {
+  int64_t m, n;
+  int32_t groups;   /* 1, 2 or 4 */
+  int32_t segments; /* 1..4; groups * segments <= 8 */
+  int64_t seg_k[4];
+  const void* a[4];
+  int64_t a_pitch[4];
+  const void* b[4][4]; /* [group][segment] */
+  int64_t b_pitch;
+  int32_t b_trans;
+  int32_t precision;   /* TCR_GEMM_TF32 | TCR_GEMM_3XTF32 */
+  const void* bias[4]; /* per group: n elements, or null */
+  int32_t act[4];      /* per group: 0 | TCR_EW_SIGMOID | TCR_EW_TANH */
+  void* out[4];        /* per group; may be null only when `cell` is set (activation not needed afterwards) */
+  int64_t out_pitch;
+  int32_t accumulate;  /* out += instead of out = */
+  int32_t cell;        /* 1: LSTM cell epilogue (groups == 4) */
+  int32_t role_cand, role_in, role_forget, role_out; /* which group is which gate */
+  const void* c_prev;  /* [m x n] pitch state_pitch, or null for a zero state */
+  void* c_out;
+  void* h_out;
+  int64_t state_pitch;
+} tcr_gemm_group_desc;
+
+int tcr_gemm_grouped(const tcr_gemm_group_desc* desc);
+/* host-only validation of everything but the pointers (the planner asks before it commits to this lowering) */
+int tcr_gemm_grouped_check(const tcr_gemm_group_desc* desc);
+
 /* General CONTRACT (operator.hpp:1069-1101, shape rule cfg/ops.yml:547-565): pairs
  * (a_rank, b_rank) are contracted; out dims = b-free (in order) then a-free. Used when
  * the operands cannot be viewed as strided matrices. */

@@ -46,7 +46,7 @@ SYMBOLS = [
     "tcr_graph_end", "tcr_graph_launch", "tcr_graph_destroy", "tcr_launch_count", "tcr_elementwise",
     "tcr_unary", "tcr_binary", "tcr_nnary", "tcr_select", "tcr_cast", "tcr_assign", "tcr_rand_unif", "tcr_rand_seed", "tcr_rand_unif_stream",
     "tcr_reduce", "tcr_argmax", "tcr_map_copy", "tcr_extend", "tcr_permute", "tcr_slice", "tcr_pad",
-    "tcr_stride", "tcr_scatter", "tcr_reverse", "tcr_concat", "tcr_gemm", "tcr_contract", "tcr_conv", "tcr_im2col", "tcr_col2im",
+    "tcr_stride", "tcr_scatter", "tcr_reverse", "tcr_concat", "tcr_gemm", "tcr_gemm_grouped", "tcr_gemm_grouped_check", "tcr_contract", "tcr_conv", "tcr_im2col", "tcr_col2im",
     "tcr_comm_unique_id", "tcr_comm_init", "tcr_comm_destroy", "tcr_comm_rank", "tcr_comm_size",
     "tcr_allreduce_sum",
 ]
@@ -89,6 +89,17 @@ class GemmDesc(C.Structure):
                 ("dtype", C.c_int32), ("precision", C.c_int32), ("epilogue", C.c_int32),
                 ("activation", C.c_int32), ("bias", C.c_void_p), ("accumulate", C.c_int32),
                 ("_pad", C.c_int32)]
+
+
+class GemmGroupDesc(C.Structure):
+    """tcr_gemm_group_desc (include/tcr_b200.h)"""
+    _fields_ = [("m", C.c_int64), ("n", C.c_int64), ("groups", C.c_int32), ("segments", C.c_int32),
+                ("seg_k", C.c_int64 * 4), ("a", C.c_void_p * 4), ("a_pitch", C.c_int64 * 4),
+                ("b", (C.c_void_p * 4) * 4), ("b_pitch", C.c_int64), ("b_trans", C.c_int32), ("precision", C.c_int32),
+                ("bias", C.c_void_p * 4), ("act", C.c_int32 * 4), ("out", C.c_void_p * 4), ("out_pitch", C.c_int64),
+                ("accumulate", C.c_int32), ("cell", C.c_int32),
+                ("role_cand", C.c_int32), ("role_in", C.c_int32), ("role_forget", C.c_int32), ("role_out", C.c_int32),
+                ("c_prev", C.c_void_p), ("c_out", C.c_void_p), ("h_out", C.c_void_p), ("state_pitch", C.c_int64)]
 
 
 _lib = None

@@ -1,0 +1,506 @@
+// gemm_rnn.cu — grouped / segmented fp32 product for SMALL-BATCH recurrent steps on the tcgen05 tensor cores.
+//
+// What it replaces. The reference unrolls layer.lstm / layer.gru (cfg/tenncor/layer.yml:716-813) into, per time step,
+//   4 x SIGMOID|TANH(ADD(CONTRACT(CONCAT(x_t, h_{t-1}), W_g), EXTEND(b_g)))          forward: one product per gate
+//   ADD(CONTRACT(dpre_g, W_g) for g in gates)                                         backward: sum of products
+// (internal/eigen/operator.hpp:1069-1139 for CONTRACT, :336-368 CONCAT, :716-731 n-ary ADD). With the batch as the only
+// "large" row extent (64 rows at BASELINE's C4), each of those is a weight-streaming product: 1152 x 1024 weights per gate
+// against 64 rows. The general GEMM kernels pad the batch to a 128-row tile and need a split-K workspace + second launch.
+//
+// This kernel computes, for up to 4 output groups g and up to 4 K-segments s,
+//     out_g[m, n] = act_g( sum_s A_s[m, :] . B_{g,s}[:, n] + bias_g[n] )         m = batch rows (any), n = units
+// in ONE launch:
+//   * roles are swapped on the tensor core: the weights are the MMA "A" operand (128 rows per CTA = `groups` row groups
+//     of 128/groups units each, so one CTA holds ALL gates of its units), the batch is the MMA "N" extent (64 per CTA);
+//   * K-segments have their own tensor maps: CONCAT(x_t, h_{t-1}) is never materialised (forward), and the sum over gates
+//     of the backward products is one accumulation in TMEM (backward);
+//   * split-K runs inside a thread-block CLUSTER (1,1,C): CTA c streams its share of the k-blocks, then the partial
+//     accumulators are exchanged through distributed shared memory (reduce-scatter over the batch columns, fixed order =>
+//     deterministic) — no workspace, no second kernel;
+//   * optional LSTM cell epilogue: c_t = cand * in + c_{t-1} * forget, h_t = c_t * out (layer.yml:758-760) computed by the
+//     CTA that owns all four gates of its units.
+// Pipeline per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (tcgen05.mma kind::tf32, 128 x 64 x 8, fp32 accumulator in
+// TMEM), warps 2-5 = 3xTF32 lo-part converters, then epilogue.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace tcr {
+
+int make_tf32_map(CUtensorMap* map, const float* base, int64_t dim0, int64_t dim1, int64_t pitch, uint32_t box0, uint32_t box1, bool mn_major);  // gemm_tc.cu
+
+namespace {
+
+constexpr int RM = 128, RN = 64, RK = 32;
+constexpr int W_TILE = RM * RK * 4;  // 16 KiB
+constexpr int X_TILE = RN * RK * 4;  // 8 KiB
+constexpr int THREADS = 192;
+constexpr int RED_BYTES = RM * RN * 4;        // 32 KiB: [src CTA][column][row]
+constexpr int CELL_BYTES = 4 * RN * 32 * 4;   // 32 KiB: [gate][column][unit <= 32]
+constexpr uint32_t SPIN_LIMIT = 1u << 28;
+
+struct alignas(64) RnnMaps {
+  CUtensorMap w[8];  // [group * nseg + segment]
+  CUtensorMap x[4];  // [segment]
+};
+
+struct RnnParams {
+  int64_t m, n;
+  int groups, rows_per_group, nseg;
+  int seg_kb_end[4];  // running count of k-blocks after segment s
+  int w_k0[4];        // k coordinate at which segment s starts inside its W map
+  int w_mn_major;     // 1: W element (k, n) has n contiguous (forward); 0: k contiguous (backward)
+  int kb_total, kb_per_cta;
+  float* out[4];
+  const float* bias[4];
+  int act[4];
+  int64_t out_pitch;
+  int accumulate;
+  int cell, role_cand, role_in, role_forget, role_out;
+  const float* c_prev;
+  float* c_out;
+  float* h_out;
+  int64_t state_pitch;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int a_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                           // accumulator F32
+  d |= 2u << 7;                           // A = TF32
+  d |= 2u << 10;                          // B = TF32
+  d |= (uint32_t)(a_mn_major & 1) << 15;  // A major
+  d |= (uint32_t)(RN >> 3) << 17;         // N
+  d |= (uint32_t)(RM >> 4) << 24;         // M
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float act_f(int act, float x) {
+  if (act == TCR_EW_SIGMOID) return __fdividef(1.0f, 1.0f + expf(-x));
+  if (act == TCR_EW_TANH) return tanhf(x);
+  return x;
+}
+
+template <int MODE>
+struct RnnCfg {
+  static constexpr int STAGES = MODE == 2 ? 3 : 4;
+  static constexpr int STAGE_BYTES = (MODE == 2 ? 2 : 1) * (W_TILE + X_TILE);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + RED_BYTES + CELL_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ RnnParams p) {
+  constexpr int STAGES = RnnCfg<MODE>::STAGES, STAGE_BYTES = RnnCfg<MODE>::STAGE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  float* red = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  float* cellbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + RED_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES + RED_BYTES + CELL_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* ready = bars + 2 * STAGES;
+  uint64_t* tmem_full = bars + 3 * STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_rank(), csize = cluster_size();
+  const int u0 = (int)blockIdx.x * p.rows_per_group;  // first unit (column of every out_g) of this CTA
+  const int m0 = (int)blockIdx.y * RN;                // first batch row
+  const int kb_begin = (int)crank * p.kb_per_cta;
+  const int num_kb = max(0, min(p.kb_per_cta, p.kb_total - kb_begin));
+
+  auto tile_w = [&](int s) { return smem + s * STAGE_BYTES; };
+  auto tile_x = [&](int s) { return smem + s * STAGE_BYTES + W_TILE; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&ready[s], 4);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(RN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  cluster_arrive();  // #1: "this CTA is running" — awaited before anybody writes into a peer's shared memory
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int chunks_per_group = 4 / p.groups;  // MN-major: the 128-row tile is four 32-unit chunks
+      for (int i = 0; i < num_kb; ++i) {
+        const int st = i % STAGES;
+        const uint32_t round = i / STAGES;
+        if (i >= STAGES) mbar_wait(&empty[st], (round - 1) & 1);
+        const int kbg = kb_begin + i;
+        int s = 0;
+        while (s + 1 < p.nseg && kbg >= p.seg_kb_end[s]) ++s;
+        const int kl = kbg - (s ? p.seg_kb_end[s - 1] : 0);
+        mbar_expect_tx(&full[st], W_TILE + X_TILE);
+        const int32_t wk = p.w_k0[s] + kl * RK;
+        if (p.w_mn_major) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int g = j / chunks_per_group, sub = j % chunks_per_group;
+            tma_load_2d(&maps.w[g * p.nseg + s], &full[st], tile_w(st) + j * 4096, u0 + 32 * sub, wk);  // [32 k][32 units]
+          }
+        } else {
+          for (int g = 0; g < p.groups; ++g)
+            tma_load_2d(&maps.w[g * p.nseg + s], &full[st], tile_w(st) + g * p.rows_per_group * 128, wk, u0);  // [rows][32 k]
+        }
+        tma_load_2d(&maps.x[s], &full[st], tile_x(st), kl * RK, m0);  // [64 batch rows][32 k]
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.w_mn_major);
+      const uint32_t a_lbo = p.w_mn_major ? 4096 : 16, a_sbo = p.w_mn_major ? 512 : 1024, a_kstep = p.w_mn_major ? 1024 : 32;
+      const uint32_t a_lt = p.w_mn_major ? 1 : 2;
+      uint32_t accumulate = 0;
+      for (int i = 0; i < num_kb; ++i) {
+        const int st = i % STAGES;
+        const uint32_t round = i / STAGES;
+        mbar_wait(MODE == 2 ? &ready[st] : &full[st], round & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(tile_w(st)), b_addr = smem_u32(tile_x(st));
+#pragma unroll
+        for (int k8 = 0; k8 < RK / 8; ++k8) {
+          const uint64_t da = make_desc(a_addr + k8 * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t db = make_desc(b_addr + k8 * 32, 16, 1024, 2);
+          if (MODE == 2) {
+            const uint64_t da_lo = make_desc(a_addr + (W_TILE + X_TILE) + k8 * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t db_lo = make_desc(b_addr + (W_TILE + X_TILE) + k8 * 32, 16, 1024, 2);
+            umma_tf32(tmem_base, da_lo, db, idesc, accumulate);  // small terms first
+            umma_tf32(tmem_base, da, db_lo, idesc, 1);
+            umma_tf32(tmem_base, da, db, idesc, 1);
+          } else {
+            umma_tf32(tmem_base, da, db, idesc, accumulate);
+          }
+          accumulate = 1;
+        }
+        umma_commit(&empty[st]);
+      }
+      umma_commit(tmem_full);
+    }
+    __syncwarp();
+  } else {
+    // ================= 3xTF32 converters (warps 2..5) =================
+    const int ct = threadIdx.x - 64;  // 0..127
+    if (MODE == 2) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int st = i % STAGES;
+        const uint32_t round = i / STAGES;
+        mbar_wait(&full[st], round & 1);
+        // the landed fp32 words are the hi operand as they are (the tensor core reads their top 19 bits); lo = x - hi
+        const uint4* src = reinterpret_cast<const uint4*>(tile_w(st));
+        uint4* dlo = reinterpret_cast<uint4*>(tile_w(st) + W_TILE + X_TILE);
+#pragma unroll 4
+        for (int e = ct; e < (W_TILE + X_TILE) / 16; e += 128) {
+          const uint4 v = src[e];
+          uint4 lo;
+          lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+          lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+          lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+          lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
+          dlo[e] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[st]);
+      }
+    }
+  }
+
+  // ================= exchange of the partial accumulators (reduce-scatter over batch columns) =================
+  const int nc = RN / (int)csize;  // batch columns this CTA finishes
+  cluster_wait();                  // #1: every CTA of the cluster has started
+  if (warp >= 2) {
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    float v[RN];
+    if (num_kb > 0) {
+      mbar_wait(tmem_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[half * 32 + j] = __uint_as_float(r[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < RN; ++j) v[j] = 0.f;
+    }
+    // column `col` belongs to CTA col / nc; it lands in that CTA's red[(my rank * nc + col % nc) * 128 + row]
+    const uint32_t red_local = smem_u32(red) + (uint32_t)(((int)crank * nc) * RM + row) * 4u;
+#pragma unroll
+    for (int col = 0; col < RN; ++col) {
+      const uint32_t dst_cta = (uint32_t)(col / nc);
+      const uint32_t addr = map_to_cta(red_local + (uint32_t)((col % nc) * RM) * 4u, dst_cta);
+      st_cluster_f32(addr, v[col]);
+    }
+  }
+  cluster_arrive();  // #2 (release): my partial sums are in their owners' shared memory
+  cluster_wait();    //    (acquire): everybody's are in mine
+
+  // ================= final sum, bias, activation, store (or LSTM cell) =================
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;  // W row of the tile
+    const int g = t / p.rows_per_group, ul = t % p.rows_per_group;
+    const int u = u0 + ul;
+    const bool u_ok = u < p.n;
+    const float bias = (u_ok && p.bias[g] != nullptr) ? p.bias[g][u] : 0.f;
+    const int act = p.act[g];
+    float* const out = p.out[g];
+    for (int j = 0; j < nc; ++j) {
+      const int b = m0 + (int)crank * nc + j;
+      float x = 0.f;
+      for (uint32_t src = 0; src < csize; ++src) x += red[((int)src * nc + j) * RM + t];
+      x = act_f(act, x + bias);
+      if (b < p.m && u_ok && out != nullptr) {
+        float* dst = out + (int64_t)b * p.out_pitch + u;
+        *dst = p.accumulate ? *dst + x : x;
+      }
+      if (p.cell) cellbuf[(g * RN + j) * 32 + ul] = x;
+    }
+    if (p.cell) {  // groups == 4, rows_per_group == 32
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int ul2 = t & 31;
+      const int u2 = u0 + ul2;
+      if (u2 < p.n) {
+        for (int j = t >> 5; j < nc; j += 4) {
+          const int b = m0 + (int)crank * nc + j;
+          if (b >= p.m) continue;
+          const float cand = cellbuf[(p.role_cand * RN + j) * 32 + ul2], in = cellbuf[(p.role_in * RN + j) * 32 + ul2];
+          const float forget = cellbuf[(p.role_forget * RN + j) * 32 + ul2], og = cellbuf[(p.role_out * RN + j) * 32 + ul2];
+          const int64_t at = (int64_t)b * p.state_pitch + u2;
+          const float cp = p.c_prev != nullptr ? p.c_prev[at] : 0.f;
+          const float c = __fadd_rn(__fmul_rn(cand, in), __fmul_rn(cp, forget));  // ADD(MUL(gate, in), MUL(state, forget)): no fma contraction
+          p.c_out[at] = c;
+          p.h_out[at] = c * og;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(RN));
+}
+
+int check_desc(const tcr_gemm_group_desc* d, bool need_device_ptrs) {
+  TCR_ARG(d != nullptr, "tcr_gemm_grouped: null descriptor");
+  TCR_ARG(d->m >= 1 && d->n >= 1, "tcr_gemm_grouped: empty output %lld x %lld", (long long)d->m, (long long)d->n);
+  TCR_ARG(d->groups == 1 || d->groups == 2 || d->groups == 4, "tcr_gemm_grouped: groups must be 1, 2 or 4 (got %d)", d->groups);
+  TCR_ARG(d->segments >= 1 && d->segments <= 4, "tcr_gemm_grouped: 1..4 K-segments (got %d)", d->segments);
+  TCR_ARG(d->groups * d->segments <= 8, "tcr_gemm_grouped: groups x segments <= 8");
+  TCR_ARG(d->precision == TCR_GEMM_TF32 || d->precision == TCR_GEMM_3XTF32, "tcr_gemm_grouped: tensor-core precisions only");
+  TCR_ARG(d->b_pitch > 0 && d->b_pitch % 4 == 0, "tcr_gemm_grouped: B row pitch must be a multiple of 4 elements (TMA)");
+  TCR_ARG(d->out_pitch >= d->n, "tcr_gemm_grouped: output pitch smaller than n");
+  for (int s = 0; s < d->segments; ++s) {
+    TCR_ARG(d->seg_k[s] >= 1, "tcr_gemm_grouped: empty K-segment %d", s);
+    TCR_ARG(d->a_pitch[s] >= d->seg_k[s] && d->a_pitch[s] % 4 == 0, "tcr_gemm_grouped: A pitch of segment %d must be >= K and a multiple of 4", s);
+    if (need_device_ptrs) {
+      TCR_ARG(d->a[s] != nullptr && (((uintptr_t)d->a[s]) & 15) == 0, "tcr_gemm_grouped: A segment %d must be 16-byte aligned", s);
+      for (int g = 0; g < d->groups; ++g)
+        TCR_ARG(d->b[g][s] != nullptr && (((uintptr_t)d->b[g][s]) & 15) == 0, "tcr_gemm_grouped: B[%d][%d] must be 16-byte aligned", g, s);
+    }
+  }
+  if (d->cell) {
+    TCR_ARG(d->groups == 4, "tcr_gemm_grouped: the LSTM cell epilogue needs the four gates in one launch");
+    const int roles = (1 << d->role_cand) | (1 << d->role_in) | (1 << d->role_forget) | (1 << d->role_out);
+    TCR_ARG(roles == 15, "tcr_gemm_grouped: gate roles must be a permutation of 0..3");
+    TCR_ARG(d->state_pitch >= d->n, "tcr_gemm_grouped: state pitch smaller than n");
+    if (need_device_ptrs) TCR_ARG(d->c_out != nullptr && d->h_out != nullptr, "tcr_gemm_grouped: cell outputs missing");
+  } else if (need_device_ptrs) {
+    for (int g = 0; g < d->groups; ++g) TCR_ARG(d->out[g] != nullptr, "tcr_gemm_grouped: output %d missing", g);
+  }
+  return TCR_OK;
+}
+
+template <int MODE>
+int launch_rnn(const RnnMaps& maps, const RnnParams& p, dim3 grid, int cluster) {
+  static bool configured = false;
+  if (!configured) {
+    TCR_CUDA(cudaFuncSetAttribute(gemm_rnn_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RnnCfg<MODE>::SMEM));
+    TCR_CUDA(cudaFuncSetAttribute(gemm_rnn_kernel<MODE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = RnnCfg<MODE>::SMEM;
+  cfg.stream = state().stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = (unsigned)cluster;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TCR_CUDA(cudaLaunchKernelEx(&cfg, gemm_rnn_kernel<MODE>, maps, p));
+  state().launches.fetch_add(1, std::memory_order_relaxed);
+  return TCR_OK;
+}
+
+}  // namespace
+
+}  // namespace tcr
+
+using namespace tcr;
+
+extern "C" {
+
+int tcr_gemm_grouped_check(const tcr_gemm_group_desc* d) { return check_desc(d, false); }
+
+int tcr_gemm_grouped(const tcr_gemm_group_desc* d) {
+  TCR_REQUIRE_DEVICE();
+  int rc = check_desc(d, true);
+  if (rc) return rc;
+  RnnMaps maps;
+  RnnParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.m = d->m;
+  p.n = d->n;
+  p.groups = d->groups;
+  p.rows_per_group = RM / d->groups;
+  p.nseg = d->segments;
+  p.w_mn_major = d->b_trans ? 0 : 1;
+  int kb = 0;
+  for (int s = 0; s < d->segments; ++s) {
+    kb += (int)ceil_div(d->seg_k[s], RK);
+    p.seg_kb_end[s] = kb;
+    p.w_k0[s] = 0;
+    // activations: dims {K_s, m}, box {32 k, 64 rows}; rows beyond m are zero-filled by the TMA unit
+    rc = make_tf32_map(&maps.x[s], (const float*)d->a[s], d->seg_k[s], d->m, d->a_pitch[s], RK, RN, false);
+    if (rc) return rc;
+    for (int g = 0; g < d->groups; ++g) {
+      CUtensorMap* wm = &maps.w[g * d->segments + s];
+      if (p.w_mn_major) rc = make_tf32_map(wm, (const float*)d->b[g][s], d->n, d->seg_k[s], d->b_pitch, 32, RK, true);  // [K_s][n], n contiguous
+      else rc = make_tf32_map(wm, (const float*)d->b[g][s], d->seg_k[s], d->n, d->b_pitch, RK, (uint32_t)p.rows_per_group, false);  // [n][K_s], k contiguous
+      if (rc) return rc;
+    }
+  }
+  p.kb_total = kb;
+  for (int g = 0; g < 4; ++g) {
+    p.out[g] = g < d->groups ? (float*)d->out[g] : nullptr;
+    p.bias[g] = g < d->groups ? (const float*)d->bias[g] : nullptr;
+    p.act[g] = g < d->groups ? d->act[g] : 0;
+  }
+  p.out_pitch = d->out_pitch;
+  p.accumulate = d->accumulate;
+  p.cell = d->cell;
+  p.role_cand = d->role_cand; p.role_in = d->role_in; p.role_forget = d->role_forget; p.role_out = d->role_out;
+  p.c_prev = (const float*)d->c_prev;
+  p.c_out = (float*)d->c_out;
+  p.h_out = (float*)d->h_out;
+  p.state_pitch = d->state_pitch;
+
+  const int64_t tiles = ceil_div(d->n, p.rows_per_group) * ceil_div(d->m, RN);
+  TCR_ARG(tiles <= 65535, "tcr_gemm_grouped: output too large for this kernel (%lld tiles)", (long long)tiles);
+  // cluster size = split-K factor: as many CTAs as fit one wave, at least two k-blocks each
+  static const int forced = std::getenv("TCR_RNN_CLUSTER") ? std::atoi(std::getenv("TCR_RNN_CLUSTER")) : 0;
+  const int sms = state().sm_count;
+  int cluster = 1;
+  for (int c = 2; c <= 16; c *= 2)
+    if (tiles * c <= sms && kb / c >= 2) cluster = c;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) cluster = forced;
+  while (cluster > 1 && kb < cluster) cluster /= 2;
+  p.kb_per_cta = (int)ceil_div(kb, cluster);
+  dim3 grid((unsigned)ceil_div(d->n, p.rows_per_group), (unsigned)ceil_div(d->m, RN), (unsigned)cluster);
+  return d->precision == TCR_GEMM_TF32 ? launch_rnn<1>(maps, p, grid, cluster) : launch_rnn<2>(maps, p, grid, cluster);
+}
+
+}  // extern "C"
