@@ -352,6 +352,8 @@ typedef struct {
 int tcr_gemm_grouped(const tcr_gemm_group_desc* desc);
 /* host-only validation of everything but the pointers (the planner asks before it commits to this lowering) */
 int tcr_gemm_grouped_check(const tcr_gemm_group_desc* desc);
+/* profiling aid (TCR_RNN_DEBUG=1): SM-clock stamps of the first CTA of the last tcr_gemm_grouped launch */
+int tcr_rnn_debug_read(long long out[16]);
 
 /* General CONTRACT (operator.hpp:1069-1101, shape rule cfg/ops.yml:547-565): pairs
  * (a_rank, b_rank) are contracted; out dims = b-free (in order) then a-free. Used when

@@ -64,7 +64,10 @@ struct RnnParams {
   float* c_out;
   float* h_out;
   int64_t state_pitch;
+  long long* dbg;  // TCR_RNN_DEBUG: SM-clock stamps of CTA (0,0,0), see tcr_rnn_debug_read
 };
+
+#define RNN_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -153,6 +156,138 @@ __device__ __forceinline__ float act_f(int act, float x) {
   return x;
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
+// Epilogue of one CTA of a cluster of CS = 64 / NC CTAs (warps 2..5, 128 threads; thread t owns accumulator row t):
+//   1. its 64 accumulator columns go to their owners: column c belongs to CTA c / NC and lands in that CTA's
+//      red[(sender * NC + c % NC) * 128 + t]  (st.shared::cluster, 128-byte coalesced per warp);
+//   2. cluster barrier (release / acquire);
+//   3. the NC columns this CTA owns are summed over the senders in rank order (deterministic), bias + activation are
+//      applied and the rows are stored; with the LSTM cell the four gate values of a (unit, batch row) meet through shared
+//      memory and c_t, h_t are written as well.
+// Everything that does not depend on the accumulator (bias, c_{t-1}) is fetched BEFORE waiting for it.
+template <int NC>
+__device__ __forceinline__ void rnn_epilogue(const RnnParams& p, uint64_t* tmem_full, uint32_t tmem_base, uint32_t red_s, uint32_t cell_s,
+                                             int num_kb, int u0, int m0, uint32_t crank) {
+  constexpr int CS = RN / NC;
+  constexpr int CELLS = NC >= 4 ? NC / 4 : 1;  // (unit, column) pairs per thread in the cell phase
+  const int t = threadIdx.x - 64, lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
+  const int row = 32 * q + lane;  // TMEM lane this thread reads (warp w may only touch lanes 32 (w % 4) ..)
+  // ---- operands of the final phase that are already in memory
+  const int g = t / p.rows_per_group, ul = t % p.rows_per_group;
+  const int u = u0 + ul;
+  const bool u_ok = u < p.n;
+  const float bias = (u_ok && p.bias[g] != nullptr) ? __ldg(p.bias[g] + u) : 0.f;
+  const int act = p.act[g];
+  float* const out = p.out[g];
+  const int b0 = m0 + (int)crank * NC;  // first batch row this CTA finishes
+  const int ul2 = t & 31, u2 = u0 + ul2;
+  float cprev[CELLS];
+#pragma unroll
+  for (int i = 0; i < CELLS; ++i) {
+    const int b = b0 + (t >> 5) + 4 * i;
+    cprev[i] = (p.cell && p.c_prev != nullptr && u2 < p.n && b < p.m) ? __ldg(p.c_prev + (int64_t)b * p.state_pitch + u2) : 0.f;
+  }
+  float old[NC];
+  if (p.accumulate) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) old[j] = (u_ok && b0 + j < p.m && out != nullptr) ? out[(int64_t)(b0 + j) * p.out_pitch + u] : 0.f;
+  }
+  // ---- 1. scatter the partial sums
+  {
+    float v[RN];
+    if (num_kb > 0) {
+      mbar_wait(tmem_full, 0);
+      if (threadIdx.x == 64) RNN_STAMP(6);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[half * 32 + j] = __uint_as_float(r[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < RN; ++j) v[j] = 0.f;
+    }
+    const uint32_t mine = red_s + (uint32_t)(((int)crank * NC) * RM + row) * 4u;
+    if (CS == 1) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) sts_f32(mine + (uint32_t)(j * RM) * 4u, v[j]);
+    } else {
+#pragma unroll
+      for (int dst = 0; dst < CS; ++dst) {
+        const uint32_t base = map_to_cta(mine, (uint32_t)dst);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) st_cluster_f32(base + (uint32_t)(j * RM) * 4u, v[dst * NC + j]);
+      }
+    }
+    if (threadIdx.x == 64) RNN_STAMP(7);
+  }
+  // ---- 2.
+  cluster_arrive();  // #2 (release): my partial sums are in their owners' shared memory
+  cluster_wait();    //    (acquire): everybody's are in mine
+  if (threadIdx.x == 64) RNN_STAMP(8);
+  // ---- 3. rows of the owned columns
+  float x[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) x[j] = 0.f;
+#pragma unroll
+  for (int src = 0; src < CS; ++src)
+#pragma unroll
+    for (int j = 0; j < NC; ++j) x[j] += lds_f32(red_s + (uint32_t)((src * NC + j) * RM + t) * 4u);
+  if (act == TCR_EW_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) x[j] = __fdividef(1.0f, 1.0f + expf(-(x[j] + bias)));
+  } else if (act == TCR_EW_TANH) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) x[j] = tanhf(x[j] + bias);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) x[j] += bias;
+  }
+  if (u_ok && out != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (b0 + j < p.m) out[(int64_t)(b0 + j) * p.out_pitch + u] = p.accumulate ? old[j] + x[j] : x[j];
+  }
+  if (p.cell) {  // groups == 4, rows_per_group == 32: gate g of unit ul, column j at cell[(g * NC + j) * 32 + ul]
+#pragma unroll
+    for (int j = 0; j < NC; ++j) sts_f32(cell_s + (uint32_t)((g * NC + j) * 32 + ul) * 4u, x[j]);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < CELLS; ++i) {
+      const int j = (t >> 5) + 4 * i;
+      const int b = b0 + j;
+      if (j < NC && u2 < p.n && b < p.m) {
+        const float cand = lds_f32(cell_s + (uint32_t)((p.role_cand * NC + j) * 32 + ul2) * 4u);
+        const float in = lds_f32(cell_s + (uint32_t)((p.role_in * NC + j) * 32 + ul2) * 4u);
+        const float forget = lds_f32(cell_s + (uint32_t)((p.role_forget * NC + j) * 32 + ul2) * 4u);
+        const float og = lds_f32(cell_s + (uint32_t)((p.role_out * NC + j) * 32 + ul2) * 4u);
+        const int64_t at = (int64_t)b * p.state_pitch + u2;
+        const float c = __fadd_rn(__fmul_rn(cand, in), __fmul_rn(cprev[i], forget));  // ADD(MUL(gate, in), MUL(state, forget)): no fma contraction
+        p.c_out[at] = c;
+        p.h_out[at] = c * og;
+      }
+    }
+  }
+}
+
 template <int MODE>
 struct RnnCfg {
   static constexpr int STAGES = MODE == 2 ? 3 : 4;
@@ -176,6 +311,7 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) RNN_STAMP(0);
   const uint32_t crank = cluster_rank(), csize = cluster_size();
   const int u0 = (int)blockIdx.x * p.rows_per_group;  // first unit (column of every out_g) of this CTA
   const int m0 = (int)blockIdx.y * RN;                // first batch row
@@ -185,6 +321,10 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
   auto tile_w = [&](int s) { return smem + s * STAGE_BYTES; };
   auto tile_x = [&](int s) { return smem + s * STAGE_BYTES + W_TILE; };
 
+  if (threadIdx.x == 32) {  // tensor maps live in kernel parameter space: fetch them now, not inside the first TMA
+    for (int i = 0; i < p.groups * p.nseg; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.w[i]) : "memory");
+    for (int i = 0; i < p.nseg; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.x[i]) : "memory");
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -202,6 +342,7 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) RNN_STAMP(1);
   cluster_arrive();  // #1: "this CTA is running" — awaited before anybody writes into a peer's shared memory
 
   if (warp == 0) {
@@ -229,7 +370,9 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
             tma_load_2d(&maps.w[g * p.nseg + s], &full[st], tile_w(st) + g * p.rows_per_group * 128, wk, u0);  // [rows][32 k]
         }
         tma_load_2d(&maps.x[s], &full[st], tile_x(st), kl * RK, m0);  // [64 batch rows][32 k]
+        if (i == 0) RNN_STAMP(2);
       }
+      RNN_STAMP(3);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -243,6 +386,7 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
         const int st = i % STAGES;
         const uint32_t round = i / STAGES;
         mbar_wait(MODE == 2 ? &ready[st] : &full[st], round & 1);
+        if (i == 0) RNN_STAMP(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_addr = smem_u32(tile_w(st)), b_addr = smem_u32(tile_x(st));
 #pragma unroll
@@ -263,6 +407,7 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
         umma_commit(&empty[st]);
       }
       umma_commit(tmem_full);
+      RNN_STAMP(5);
     }
     __syncwarp();
   } else {
@@ -293,91 +438,29 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
     }
   }
 
-  // ================= exchange of the partial accumulators (reduce-scatter over batch columns) =================
-  const int nc = RN / (int)csize;  // batch columns this CTA finishes
-  cluster_wait();                  // #1: every CTA of the cluster has started
+  // ================= exchange of the partial accumulators + final sum (see rnn_epilogue) =================
+  cluster_wait();  // #1: every CTA of the cluster has started
   if (warp >= 2) {
-    const int q = warp & 3;
-    const int row = 32 * q + lane;
-    float v[RN];
-    if (num_kb > 0) {
-      mbar_wait(tmem_full, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[half * 32 + j] = __uint_as_float(r[j]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < RN; ++j) v[j] = 0.f;
+    const uint32_t red_s = smem_u32(red), cell_s = smem_u32(cellbuf);
+    switch (csize) {
+      case 1: rnn_epilogue<64>(p, tmem_full, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
+      case 2: rnn_epilogue<32>(p, tmem_full, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
+      case 4: rnn_epilogue<16>(p, tmem_full, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
+      case 8: rnn_epilogue<8>(p, tmem_full, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
+      default: rnn_epilogue<4>(p, tmem_full, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
     }
-    // column `col` belongs to CTA col / nc; it lands in that CTA's red[(my rank * nc + col % nc) * 128 + row]
-    const uint32_t red_local = smem_u32(red) + (uint32_t)(((int)crank * nc) * RM + row) * 4u;
-#pragma unroll
-    for (int col = 0; col < RN; ++col) {
-      const uint32_t dst_cta = (uint32_t)(col / nc);
-      const uint32_t addr = map_to_cta(red_local + (uint32_t)((col % nc) * RM) * 4u, dst_cta);
-      st_cluster_f32(addr, v[col]);
-    }
+  } else {
+    cluster_arrive();  // #2
+    cluster_wait();
   }
-  cluster_arrive();  // #2 (release): my partial sums are in their owners' shared memory
-  cluster_wait();    //    (acquire): everybody's are in mine
-
-  // ================= final sum, bias, activation, store (or LSTM cell) =================
-  if (warp >= 2) {
-    const int t = threadIdx.x - 64;  // W row of the tile
-    const int g = t / p.rows_per_group, ul = t % p.rows_per_group;
-    const int u = u0 + ul;
-    const bool u_ok = u < p.n;
-    const float bias = (u_ok && p.bias[g] != nullptr) ? p.bias[g][u] : 0.f;
-    const int act = p.act[g];
-    float* const out = p.out[g];
-    for (int j = 0; j < nc; ++j) {
-      const int b = m0 + (int)crank * nc + j;
-      float x = 0.f;
-      for (uint32_t src = 0; src < csize; ++src) x += red[((int)src * nc + j) * RM + t];
-      x = act_f(act, x + bias);
-      if (b < p.m && u_ok && out != nullptr) {
-        float* dst = out + (int64_t)b * p.out_pitch + u;
-        *dst = p.accumulate ? *dst + x : x;
-      }
-      if (p.cell) cellbuf[(g * RN + j) * 32 + ul] = x;
-    }
-    if (p.cell) {  // groups == 4, rows_per_group == 32
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int ul2 = t & 31;
-      const int u2 = u0 + ul2;
-      if (u2 < p.n) {
-        for (int j = t >> 5; j < nc; j += 4) {
-          const int b = m0 + (int)crank * nc + j;
-          if (b >= p.m) continue;
-          const float cand = cellbuf[(p.role_cand * RN + j) * 32 + ul2], in = cellbuf[(p.role_in * RN + j) * 32 + ul2];
-          const float forget = cellbuf[(p.role_forget * RN + j) * 32 + ul2], og = cellbuf[(p.role_out * RN + j) * 32 + ul2];
-          const int64_t at = (int64_t)b * p.state_pitch + u2;
-          const float cp = p.c_prev != nullptr ? p.c_prev[at] : 0.f;
-          const float c = __fadd_rn(__fmul_rn(cand, in), __fmul_rn(cp, forget));  // ADD(MUL(gate, in), MUL(state, forget)): no fma contraction
-          p.c_out[at] = c;
-          p.h_out[at] = c * og;
-        }
-      }
-    }
-  }
+  if (threadIdx.x == 64) RNN_STAMP(9);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(RN));
+  if (threadIdx.x == 0) RNN_STAMP(10);
 }
+
+long long* g_rnn_dbg = nullptr;
 
 int check_desc(const tcr_gemm_group_desc* d, bool need_device_ptrs) {
   TCR_ARG(d != nullptr, "tcr_gemm_grouped: null descriptor");
@@ -445,6 +528,17 @@ extern "C" {
 
 int tcr_gemm_grouped_check(const tcr_gemm_group_desc* d) { return check_desc(d, false); }
 
+/* TCR_RNN_DEBUG=1: SM-clock stamps of CTA (0,0,0) of the last tcr_gemm_grouped launch (profiling aid, tools/rnn_gemm_bench.py):
+ * 0 entry, 1 set-up done, 2 first TMA issued, 3 last TMA issued, 4 first stage landed, 5 last MMA committed, 6 accumulator complete,
+ * 7 partial sums sent, 8 cluster exchange complete, 9 outputs stored, 10 exit */
+int tcr_rnn_debug_read(long long out[16]) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(g_rnn_dbg != nullptr, "tcr_rnn_debug_read: run with TCR_RNN_DEBUG=1");
+  TCR_CUDA(cudaStreamSynchronize(state().stream));
+  TCR_CUDA(cudaMemcpy(out, g_rnn_dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return TCR_OK;
+}
+
 int tcr_gemm_grouped(const tcr_gemm_group_desc* d) {
   TCR_REQUIRE_DEVICE();
   int rc = check_desc(d, true);
@@ -487,6 +581,12 @@ int tcr_gemm_grouped(const tcr_gemm_group_desc* d) {
   p.c_out = (float*)d->c_out;
   p.h_out = (float*)d->h_out;
   p.state_pitch = d->state_pitch;
+  static const bool debug = std::getenv("TCR_RNN_DEBUG") != nullptr;
+  if (debug && g_rnn_dbg == nullptr) {
+    TCR_CUDA(cudaMalloc(&g_rnn_dbg, 16 * sizeof(long long)));
+    TCR_CUDA(cudaMemset(g_rnn_dbg, 0, 16 * sizeof(long long)));
+  }
+  p.dbg = debug ? g_rnn_dbg : nullptr;
 
   const int64_t tiles = ceil_div(d->n, p.rows_per_group) * ceil_div(d->m, RN);
   TCR_ARG(tiles <= 65535, "tcr_gemm_grouped: output too large for this kernel (%lld tiles)", (long long)tiles);
