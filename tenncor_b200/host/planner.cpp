@@ -6,6 +6,8 @@
 #include "dp.hpp"
 #include <queue>
 #include <set>
+#include <map>
+#include <tuple>
 #include <algorithm>
 
 #include <cstdlib>
@@ -56,6 +58,8 @@ struct PNode {
   bool gemm_transposed = false;  // PERMUTE{1,0} of a GEMM: computed as (B^T A^T), no copy
   int64_t bucket_slot = -1;      // >= 0: this node's buffer is the gradient bucket at this byte offset
   int conv = -1;                 // >= 0: produced by the patch-gather + GEMM step `convs[conv]` (fuse_convs)
+  int stack = -1, stack_pos = 0;  // >= 0: the buffer is slab `stack_pos` of the plan-owned stack `stack` (fuse_recurrent_steps)
+  int alias_stack = -1;           // >= 0: the node IS that whole stack (an n-ary CONCAT whose operands were produced in place)
 };
 
 struct InputRef {
@@ -100,6 +104,23 @@ struct Step {
   bool member_in_place = false;
   size_t bucket_offset = 0;         // member: byte offset of its slot
   std::vector<int> bucket_members;  // flush: member step indices
+  // ---- recurrent-step fusion (fuse_recurrent_steps)
+  // grouped / K-segmented small-batch product (tcr_gemm_grouped): in = {A segments, B[group][segment], biases present, c_{t-1}}
+  bool group = false;
+  tcr_gemm_group_desc gd;
+  int g_bias_slot[4] = {-1, -1, -1, -1};  // index into `in` of the bias of group g
+  int g_cprev_slot = -1;
+  int g_out_nodes[4] = {-1, -1, -1, -1};  // node each group's result is stored to (-1: not stored)
+  int g_c_node = -1, g_h_node = -1;       // LSTM cell epilogue outputs
+  std::vector<int> extra_outs;            // nodes written besides out_node
+  std::vector<int> dep_nodes;             // nodes read through a stack base pointer: ordering / liveness only
+  // REDUCE over a stack of operands laid out back to back (the 128 per-step bias gradients as one reduction)
+  bool stack_reduce = false;
+  int red_op = 0;
+  uint32_t red_mask = 0;
+  int64_t red_shape[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+  int64_t pos = 0;  // ordering key of the stable topological re-sort
+  bool dead = false;
 };
 
 // One recognised conv2d composite (cfg/tenncor/nn.yml:48-98) or its kernel gradient
@@ -1065,16 +1086,581 @@ struct Plan {
     }
   }
 
+  // ---------------------------------------------------------------- recurrent-step fusion (step level)
+  // The reference unrolls layer.lstm / layer.gru / layer.rnn over time (cfg/tenncor/layer.yml:678-813) and teq::derive sums
+  // the per-step contributions of every shared weight with one n-ary ADD (internal/teq/src/derive.cpp:49-51). After
+  // build_steps() that is, per time step, four small GEMMs on the same operand, a CONCAT, four more GEMMs + an ADD + a SLICE for
+  // the gradient reaching h_{t-1}, and four weight-gradient GEMMs + four bias reductions whose results meet in 128-operand ADDs.
+  // This pass rewrites the STEP list (values are unchanged; the oracle still evaluates the unfused graph):
+  //   (1) sibling products  act(A . W_g + b_g), same A          -> ONE grouped launch (tcr_gemm_grouped); A = CONCAT(x, h)
+  //                                                                becomes two K-segments and the CONCAT step disappears when
+  //                                                                nobody else reads it
+  //   (2) ADD of products   sum_g (dpre_g . W_g^T) [+ SLICE]      -> ONE K-segmented launch producing only the sliced columns
+  //   (3) n-ary ADD of T weight-gradient products A_t^T . B_t     -> the operands are PLACED back to back (stacks) and the sum
+  //                                                                is ONE product with K = T . k
+  //   (4) n-ary ADD of T bias reductions                          -> ONE reduction over the stack
+  //   (5) n-ary CONCAT of T step outputs along the last rank      -> the producers write their slab of the result in place
+  // Steps keep (storage root, version) read / write sets taken from the original order; the rewritten list is re-sorted by a
+  // stable topological sort on those, so a merged step lands after everything any of its members waited for.
+  struct Stack {
+    std::vector<int> members;
+    size_t slab = 0;
+    void* base = nullptr;
+  };
+  std::vector<Stack> stacks;
+
+  struct Acc {
+    std::vector<std::pair<int, int>> rd, wr;
+  };
+
+  void step_reads(const Step& st, std::vector<int>& out) const {
+    out.clear();
+    if (st.kind == Step::BUCKET_FLUSH) return;
+    if (st.ew) for (auto& in : st.inputs) out.push_back(in.node);
+    else for (int in : st.in_nodes) out.push_back(in);
+    for (int d : st.dep_nodes) out.push_back(d);
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+  }
+
+  void step_writes(const Step& st, std::vector<int>& out) const {
+    out.clear();
+    if (st.kind == Step::BUCKET_FLUSH) return;
+    out.push_back(st.out_node);
+    for (int e : st.extra_outs) out.push_back(e);
+    const PNode& o = nodes[st.out_node];
+    if (is_assign(o.op)) out.push_back(nodes[o.args[0]].root);
+  }
+
+  struct GemmView {
+    bool ok = false;
+    tcr_gemm_desc d;
+    int a = -1, b = -1, bias = -1;
+    size_t a_off = 0, b_off = 0, bias_off = 0;
+  };
+
+  GemmView gemm_view(const Step& st) const {
+    GemmView v;
+    if (st.dead || st.kind != Step::NORMAL || st.ew || st.conv_fused || st.group || st.stack_reduce) return v;
+    const PNode& o = nodes[st.out_node];
+    if (st.gemm_fused) {
+      v.d = st.gemm;
+      if (st.in_nodes.size() > 2) { v.bias = st.in_nodes[2]; v.bias_off = st.in_offsets[2]; }
+    } else {
+      if (!st.holder || !st.holder->gemm() || (o.op != CONTRACT && o.op != MATMUL) || st.in_nodes.size() != 2) return v;
+      v.d = *st.holder->gemm();
+      v.d.epilogue = TCR_EPI_NONE;
+      v.d.activation = 0;
+    }
+    if (v.d.dtype != FLOAT || v.d.batch != 1 || v.d.accumulate) return v;
+    v.a = st.in_nodes[0]; v.a_off = st.in_offsets[0];
+    v.b = st.in_nodes[1]; v.b_off = st.in_offsets[1];
+    v.ok = true;
+    return v;
+  }
+
+  // operands 0..T-1 laid out back to back: all views of one buffer at base + i * slab, or distinct plan-owned results that can be
+  // (or already are) placed consecutively in a stack. check-only unless `commit`.
+  bool stack_operands(const std::vector<std::pair<int, size_t>>& refs, size_t slab, bool commit, int& base_node, size_t& base_off) {
+    if (refs.empty()) return false;
+    bool same_root = true;
+    for (size_t i = 0; i < refs.size(); ++i)
+      if (refs[i].first != refs[0].first || refs[i].second != refs[0].second + i * slab) same_root = false;
+    if (same_root) { base_node = refs[0].first; base_off = refs[0].second; return true; }
+    std::set<int> seen;
+    int sid = -2;
+    for (size_t i = 0; i < refs.size(); ++i) {
+      const PNode& n = nodes[refs[i].first];
+      if (refs[i].second != 0 || !n.func || n.exposed || n.is_view || is_assign(n.op) || n.step < 0 || n.bucket_slot >= 0 || n.conv >= 0 ||
+          n.alias_stack >= 0 || (size_t)n.n * type_size(n.dtype) != slab || !seen.insert(refs[i].first).second)
+        return false;
+      if (i == 0) sid = n.stack;
+      if (n.stack != sid) return false;
+      if (sid >= 0 && n.stack_pos != nodes[refs[0].first].stack_pos + (int)i) return false;
+    }
+    if (sid >= 0) {
+      base_node = stacks[sid].members[0];
+      base_off = (size_t)nodes[refs[0].first].stack_pos * slab;
+      return true;
+    }
+    if (commit) {
+      Stack st;
+      st.slab = slab;
+      for (size_t i = 0; i < refs.size(); ++i) {
+        st.members.push_back(refs[i].first);
+        nodes[refs[i].first].stack = (int)stacks.size();
+        nodes[refs[i].first].stack_pos = (int)i;
+      }
+      stacks.push_back(std::move(st));
+    }
+    base_node = refs[0].first;
+    base_off = 0;
+    return true;
+  }
+
+  void fuse_recurrent_steps() {
+    if (std::getenv("TCR_NO_RNN_FUSE") || precision == TCR_GEMM_EXACT) return;
+    const int ns = (int)steps.size();
+    if (ns < 4) return;
+    const std::vector<Step> original = steps;
+    std::vector<int> original_step_of(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) original_step_of[i] = nodes[i].step;
+    auto restore = [&] {
+      steps = original;
+      for (size_t i = 0; i < nodes.size(); ++i) { nodes[i].step = original_step_of[i]; nodes[i].stack = -1; nodes[i].alias_stack = -1; }
+      stacks.clear();
+    };
+    // ---- read / write sets with versions, from the original order
+    std::vector<Acc> acc(ns);
+    std::vector<std::vector<int>> readers(nodes.size());
+    {
+      std::unordered_map<int, int> ver;
+      std::vector<int> rd, wr;
+      for (int s = 0; s < ns; ++s) {
+        steps[s].pos = s;
+        step_reads(steps[s], rd);
+        step_writes(steps[s], wr);
+        for (int r : rd) { acc[s].rd.push_back({r, ver[r]}); readers[r].push_back(s); }
+        for (int w : wr) acc[s].wr.push_back({w, ++ver[w]});
+      }
+    }
+    auto merge_acc = [&](int into, int from) {
+      acc[into].rd.insert(acc[into].rd.end(), acc[from].rd.begin(), acc[from].rd.end());
+      acc[into].wr.insert(acc[into].wr.end(), acc[from].wr.begin(), acc[from].wr.end());
+    };
+    auto drop_node = [&](int s, int node) {  // `node` became internal to step s (or virtual)
+      auto& a = acc[s];
+      a.rd.erase(std::remove_if(a.rd.begin(), a.rd.end(), [&](const std::pair<int, int>& x) { return x.first == node; }), a.rd.end());
+      a.wr.erase(std::remove_if(a.wr.begin(), a.wr.end(), [&](const std::pair<int, int>& x) { return x.first == node; }), a.wr.end());
+    };
+    auto live_readers = [&](int node) {
+      std::vector<int> out;
+      for (int r : readers[node])
+        if (!steps[r].dead) out.push_back(r);
+      return out;
+    };
+    auto producer = [&](int node) -> int {
+      const PNode& n = nodes[node];
+      if (!n.func || n.step < 0 || n.step >= ns || steps[n.step].dead || steps[n.step].out_node != node) return -1;
+      return n.step;
+    };
+    auto plain_f32 = [&](int node) { return nodes[node].dtype == FLOAT; };
+    int n_fused = 0;
+
+    // ================= (1) sibling products sharing their A operand -> grouped launch =================
+    {
+      struct Key {
+        int a; size_t off; int64_t m, n, k, a_sm, b_sk;
+        bool operator<(const Key& o) const { return std::tie(a, off, m, n, k, a_sm, b_sk) < std::tie(o.a, o.off, o.m, o.n, o.k, o.a_sm, o.b_sk); }
+      };
+      std::map<Key, std::vector<int>> buckets;
+      for (int s = 0; s < ns; ++s) {
+        GemmView v = gemm_view(steps[s]);
+        if (!v.ok) continue;
+        const tcr_gemm_desc& d = v.d;
+        if (d.m > 128 || d.n < 32 || d.k < 32) continue;                                  // the small-batch kernel
+        if (d.a_sk != 1 || d.b_sn != 1 || d.c_sn != 1 || d.c_sm != d.n) continue;         // A row-major, B [k x n], C row-major
+        if (d.epilogue != TCR_EPI_NONE && d.epilogue != TCR_EPI_BIAS_N) continue;
+        if ((d.a_sm % 4) || (d.b_sk % 4) || (v.a_off % 16) || (v.b_off % 16)) continue;
+        buckets[Key{v.a, v.a_off, d.m, d.n, d.k, d.a_sm, d.b_sk}].push_back(s);
+      }
+      for (auto& kv : buckets) {
+        std::vector<int>& all = kv.second;
+        // the A operand as K-segments when it is a binary CONCAT along the fast rank that only products read
+        const Key& key = kv.first;
+        std::vector<std::pair<int, size_t>> segs = {{key.a, key.off}};
+        std::vector<int64_t> seg_k = {key.k}, seg_pitch = {key.a_sm};
+        int concat_step = -1;
+        {
+          const int ps = key.off == 0 ? producer(key.a) : -1;
+          if (ps >= 0) {
+            const Step& cs = steps[ps];
+            const PNode& cn = nodes[key.a];
+            if (!cs.ew && !cs.gemm_fused && cs.holder && cn.op == CONCAT && cs.in_nodes.size() == 2 && !cn.exposed && plain_f32(key.a) &&
+                eigen::unpack_rank(*cn.func) == 0) {
+              const PNode& x0 = nodes[cn.args[0]];
+              const PNode& x1 = nodes[cn.args[1]];
+              const int64_t k0 = x0.shape.at(0), k1 = x1.shape.at(0);
+              bool ok = k0 + k1 == key.k && key.a_sm == key.k && x0.n == k0 * key.m && x1.n == k1 * key.m && (k0 % 4) == 0 && (k1 % 4) == 0 &&
+                        (cs.in_offsets[0] % 16) == 0 && (cs.in_offsets[1] % 16) == 0 && x0.dtype == FLOAT && x1.dtype == FLOAT;
+              if (ok) {
+                segs = {{cs.in_nodes[0], cs.in_offsets[0]}, {cs.in_nodes[1], cs.in_offsets[1]}};
+                seg_k = {k0, k1};
+                seg_pitch = {k0, k1};
+                concat_step = ps;
+              }
+            }
+          }
+        }
+        if (all.size() < 2 && concat_step < 0) continue;
+        for (size_t at = 0; at < all.size();) {
+          const size_t left = all.size() - at;
+          const int G = left >= 4 ? 4 : left >= 2 ? 2 : 1;
+          if (G == 1 && concat_step < 0) { ++at; continue; }
+          std::vector<int> mem(all.begin() + at, all.begin() + at + G);
+          at += G;
+          const int keep = mem.back();
+          Step g;
+          g.group = true;
+          g.pos = steps[keep].pos;
+          g.out_node = steps[keep].out_node;
+          std::memset(&g.gd, 0, sizeof(g.gd));
+          tcr_gemm_group_desc& gd = g.gd;
+          gd.m = key.m; gd.n = key.n; gd.groups = G; gd.segments = (int)segs.size();
+          gd.b_pitch = key.b_sk; gd.b_trans = 0; gd.out_pitch = key.n;
+          for (size_t q = 0; q < segs.size(); ++q) {
+            gd.seg_k[q] = seg_k[q];
+            gd.a_pitch[q] = seg_pitch[q];
+            g.in_nodes.push_back(segs[q].first);
+            g.in_offsets.push_back(segs[q].second);
+          }
+          std::vector<GemmView> views;
+          for (int m : mem) views.push_back(gemm_view(steps[m]));
+          for (int gi = 0; gi < G; ++gi) {
+            size_t koff = 0;
+            for (size_t q = 0; q < segs.size(); ++q) {
+              g.in_nodes.push_back(views[gi].b);
+              g.in_offsets.push_back(views[gi].b_off + koff * (size_t)key.b_sk * sizeof(float));
+              koff += (size_t)seg_k[q];
+            }
+          }
+          for (int gi = 0; gi < G; ++gi) {
+            gd.act[gi] = views[gi].d.activation;
+            g.g_out_nodes[gi] = steps[mem[gi]].out_node;
+            if (views[gi].d.epilogue == TCR_EPI_BIAS_N && views[gi].bias >= 0) {
+              g.g_bias_slot[gi] = (int)g.in_nodes.size();
+              g.in_nodes.push_back(views[gi].bias);
+              g.in_offsets.push_back(views[gi].bias_off);
+            }
+            if (mem[gi] != keep) g.extra_outs.push_back(steps[mem[gi]].out_node);
+          }
+          gd.precision = TCR_GEMM_3XTF32;
+          if (tcr_gemm_grouped_check(&gd) != TCR_OK) continue;
+          // commit
+          for (int m : mem)
+            if (m != keep) { merge_acc(keep, m); steps[m].dead = true; }
+          if (concat_step >= 0) {
+            drop_node(keep, key.a);
+            acc[keep].rd.insert(acc[keep].rd.end(), acc[concat_step].rd.begin(), acc[concat_step].rd.end());
+          }
+          g.dead = false;
+          steps[keep] = std::move(g);
+          ++n_fused;
+        }
+        if (concat_step >= 0) {  // nobody reads the concatenation any more: it is never built
+          bool any = false;
+          std::vector<int> rd;
+          for (int r : live_readers(key.a)) {
+            step_reads(steps[r], rd);
+            if (std::find(rd.begin(), rd.end(), key.a) != rd.end()) any = true;
+          }
+          if (!any) steps[concat_step].dead = true;
+        }
+      }
+    }
+
+    // ================= (2) ADD of products (+ SLICE of the sum) -> one K-segmented launch =================
+    for (int s = 0; s < ns; ++s) {
+      Step& e = steps[s];
+      if (e.dead || !e.ew || e.kind != Step::NORMAL || e.prog.n_outputs != 1) continue;
+      const int nin = e.prog.n_inputs;
+      if (nin < 2 || nin > 4 || e.prog.n_instrs != nin - 1 || nodes[e.out_node].dtype != FLOAT || is_assign(nodes[e.out_node].op)) continue;
+      bool pure = true;
+      for (int k = 0; k < e.prog.n_instrs; ++k)
+        if (e.prog.instrs[k].op != TCR_EW_ADD) pure = false;
+      std::vector<int> prods;
+      std::vector<GemmView> views;
+      for (int k = 0; k < nin && pure; ++k) {
+        const InputRef& in = e.inputs[k];
+        const int ps = (in.mask == 0 && in.offset == 0 && in.dtype == FLOAT) ? producer(in.node) : -1;
+        if (ps < 0 || nodes[in.node].exposed || live_readers(in.node).size() != 1 || std::find(prods.begin(), prods.end(), ps) != prods.end()) { pure = false; break; }
+        GemmView v = gemm_view(steps[ps]);
+        if (!v.ok || v.d.epilogue != TCR_EPI_NONE || v.d.activation) { pure = false; break; }
+        const tcr_gemm_desc& d = v.d;
+        if (d.m > 128 || d.n < 32 || d.a_sk != 1 || d.b_sk != 1 || d.c_sn != 1 || d.c_sm != d.n || (d.a_sm % 4) || (d.b_sn % 4) || (v.a_off % 16) || (v.b_off % 16)) { pure = false; break; }
+        if (!views.empty() && (d.m != views[0].d.m || d.n != views[0].d.n || d.b_sn != views[0].d.b_sn)) { pure = false; break; }
+        prods.push_back(ps);
+        views.push_back(v);
+      }
+      if (!pure || (int)views.size() != nin) continue;
+      // every input must feed the sum exactly once: n - 1 ADDs over n distinct inputs is a sum of all of them iff each register 0..n-1 is consumed
+      int keep = s;
+      int64_t n_cols = views[0].d.n, col0 = 0;
+      int out_node = e.out_node;
+      // SLICE of the fast rank as the only reader: compute only those columns
+      {
+        std::vector<int> rs = live_readers(e.out_node);
+        if (rs.size() == 1 && !nodes[e.out_node].exposed) {
+          const Step& sl = steps[rs[0]];
+          const PNode& sn = nodes[sl.out_node];
+          if (!sl.ew && !sl.gemm_fused && !sl.group && sl.holder && sn.op == SLICE && sl.in_nodes.size() == 1 && sl.in_offsets[0] == 0 && sn.dtype == FLOAT) {
+            auto cuts = eigen::unpack_dimpairs(*sn.func);
+            const Shape whole = nodes[e.out_node].shape;
+            bool only_fast = true;
+            for (size_t r = 1; r < rank_cap; ++r) {
+              if (r < cuts.size() && (cuts[r].first != 0 || std::min<int64_t>(cuts[r].second, whole.at(r)) != (int64_t)whole.at(r))) only_fast = false;
+            }
+            if (only_fast && !cuts.empty() && (int64_t)whole.at(0) == n_cols) {
+              const int64_t lo = std::min<int64_t>(cuts[0].first, whole.at(0) - 1);
+              const int64_t len = std::min<int64_t>(cuts[0].second, whole.at(0) - lo);
+              if ((int64_t)sn.shape.at(0) == len && len >= 32 && (len % 4) == 0 && ((lo * views[0].d.b_sn * 4) % 16) == 0) {
+                col0 = lo; n_cols = len; keep = rs[0]; out_node = sl.out_node;
+              }
+            }
+          }
+        }
+      }
+      Step g;
+      g.group = true;
+      g.pos = steps[keep].pos;
+      g.out_node = out_node;
+      std::memset(&g.gd, 0, sizeof(g.gd));
+      tcr_gemm_group_desc& gd = g.gd;
+      gd.m = views[0].d.m; gd.n = n_cols; gd.groups = 1; gd.segments = nin;
+      gd.b_pitch = views[0].d.b_sn; gd.b_trans = 1; gd.out_pitch = n_cols;
+      for (int k = 0; k < nin; ++k) {
+        gd.seg_k[k] = views[k].d.k;
+        gd.a_pitch[k] = views[k].d.a_sm;
+        g.in_nodes.push_back(views[k].a);
+        g.in_offsets.push_back(views[k].a_off);
+      }
+      for (int k = 0; k < nin; ++k) {
+        g.in_nodes.push_back(views[k].b);
+        g.in_offsets.push_back(views[k].b_off + (size_t)col0 * (size_t)gd.b_pitch * sizeof(float));
+      }
+      g.g_out_nodes[0] = out_node;
+      gd.precision = TCR_GEMM_3XTF32;
+      if (tcr_gemm_grouped_check(&gd) != TCR_OK) continue;
+      const int sum_node = e.out_node;
+      if (keep != s) { merge_acc(keep, s); steps[s].dead = true; }
+      for (int ps : prods) { merge_acc(keep, ps); steps[ps].dead = true; }
+      for (int ps : prods) drop_node(keep, steps[ps].out_node);
+      if (keep != s) drop_node(keep, sum_node);
+      steps[keep] = std::move(g);
+      ++n_fused;
+    }
+
+    // ================= (3) n-ary ADD of weight-gradient products -> operands stacked, ONE product =================
+    // ================= (4) n-ary ADD of reductions               -> ONE reduction over the stack    =================
+    for (int pass = 0; pass < 2; ++pass)
+    for (int s = 0; s < ns; ++s) {
+      Step& x = steps[s];
+      if (x.dead || x.ew || x.gemm_fused || x.group || x.stack_reduce || x.kind != Step::NORMAL || !x.holder) continue;
+      const PNode& xn = nodes[x.out_node];
+      if (xn.op != ADD || xn.dtype != FLOAT || x.in_nodes.size() < 3) continue;
+      const int T = (int)x.in_nodes.size();
+      std::vector<int> prods;
+      bool ok = true;
+      for (int i = 0; i < T && ok; ++i) {
+        const int ps = x.in_offsets[i] == 0 ? producer(x.in_nodes[i]) : -1;
+        if (ps < 0 || nodes[x.in_nodes[i]].exposed || live_readers(x.in_nodes[i]).size() != 1 || std::find(prods.begin(), prods.end(), ps) != prods.end()) ok = false;
+        else prods.push_back(ps);
+      }
+      if (!ok) continue;
+      if (pass == 0) {
+        std::vector<GemmView> views;
+        for (int ps : prods) {
+          GemmView v = gemm_view(steps[ps]);
+          if (!v.ok || v.d.epilogue != TCR_EPI_NONE || v.d.activation) { ok = false; break; }
+          if (!views.empty()) {
+            const tcr_gemm_desc &d = v.d, &f = views[0].d;
+            if (d.m != f.m || d.n != f.n || d.k != f.k || d.a_sm != f.a_sm || d.a_sk != f.a_sk || d.b_sk != f.b_sk || d.b_sn != f.b_sn || d.c_sm != f.c_sm || d.c_sn != f.c_sn) { ok = false; break; }
+          }
+          views.push_back(v);
+        }
+        if (!ok) continue;
+        // canonical order: by the A operand's position in the graph (forward time order)
+        std::vector<int> order(T);
+        for (int i = 0; i < T; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int p, int q) { return std::make_pair(views[p].a, views[p].a_off) < std::make_pair(views[q].a, views[q].a_off); });
+        const tcr_gemm_desc& f = views[0].d;
+        const size_t a_slab = (size_t)f.k * (size_t)f.a_sk * sizeof(float), b_slab = (size_t)f.k * (size_t)f.b_sk * sizeof(float);
+        if (f.a_sk < f.m || f.b_sk < f.n) continue;  // K must be the slow extent of both operands
+        std::vector<std::pair<int, size_t>> ar, br;
+        for (int i : order) { ar.push_back({views[i].a, views[i].a_off}); br.push_back({views[i].b, views[i].b_off}); }
+        int an, bn;
+        size_t ao, bo;
+        if (!stack_operands(ar, a_slab, false, an, ao) || !stack_operands(br, b_slab, false, bn, bo)) continue;
+        stack_operands(ar, a_slab, true, an, ao);
+        stack_operands(br, b_slab, true, bn, bo);
+        Step g;
+        g.gemm_fused = true;
+        g.pos = x.pos;
+        g.out_node = x.out_node;
+        g.gemm = f;
+        g.gemm.k = f.k * T;
+        g.in_nodes = {an, bn};
+        g.in_offsets = {ao, bo};
+        for (auto& r : ar) g.dep_nodes.push_back(r.first);
+        for (auto& r : br) g.dep_nodes.push_back(r.first);
+        for (int ps : prods) { merge_acc(s, ps); drop_node(s, steps[ps].out_node); steps[ps].dead = true; }
+        steps[s] = std::move(g);
+        ++n_fused;
+      } else {
+        // reductions over rank 1 of [n, m] operands
+        uint32_t mask = 0;
+        std::vector<std::pair<int, size_t>> refs;
+        int64_t n0 = 0, m0 = 0;
+        int rop = 0;
+        for (int ps : prods) {
+          const Step& r = steps[ps];
+          const PNode& rn = nodes[r.out_node];
+          if (r.ew || r.gemm_fused || r.group || !r.holder || rn.op != REDUCE_SUM || r.in_nodes.size() != 1 || rn.dtype != FLOAT) { ok = false; break; }
+          uint32_t mk = 0;
+          for (RankT q : eigen::unpack_rankset(*rn.func))
+            if (q < rank_cap) mk |= 1u << q;
+          const PNode& in = nodes[rn.args[0]];
+          bool two_d = true;
+          for (int q = 2; q < rank_cap; ++q)
+            if (in.shape.at(q) != 1) two_d = false;
+          if (!two_d || mk != 2u || in.dtype != FLOAT) { ok = false; break; }
+          if (refs.empty()) { mask = mk; n0 = in.shape.at(0); m0 = in.shape.at(1); rop = rn.op; }
+          else if ((int64_t)in.shape.at(0) != n0 || (int64_t)in.shape.at(1) != m0) { ok = false; break; }
+          refs.push_back({r.in_nodes[0], r.in_offsets[0]});
+        }
+        if (!ok || refs.empty()) continue;
+        // order by stack position when the operands are stacked already, else by graph position
+        std::sort(refs.begin(), refs.end(), [&](const std::pair<int, size_t>& p, const std::pair<int, size_t>& q) {
+          const PNode &a = nodes[p.first], &b = nodes[q.first];
+          if (a.stack >= 0 && a.stack == b.stack) return a.stack_pos < b.stack_pos;
+          return p < q;
+        });
+        const size_t slab = (size_t)n0 * (size_t)m0 * sizeof(float);
+        int bn;
+        size_t bo;
+        if (!stack_operands(refs, slab, false, bn, bo)) continue;
+        stack_operands(refs, slab, true, bn, bo);
+        Step g;
+        g.stack_reduce = true;
+        g.pos = x.pos;
+        g.out_node = x.out_node;
+        g.red_op = rop;
+        g.red_mask = mask;
+        g.red_shape[0] = n0;
+        g.red_shape[1] = m0 * T;
+        g.in_nodes = {bn};
+        g.in_offsets = {bo};
+        for (auto& r : refs) g.dep_nodes.push_back(r.first);
+        for (int ps : prods) { merge_acc(s, ps); drop_node(s, steps[ps].out_node); steps[ps].dead = true; }
+        steps[s] = std::move(g);
+        ++n_fused;
+      }
+    }
+
+    // ================= (5) n-ary CONCAT of step outputs along the slowest rank -> produced in place =================
+    for (int s = 0; s < ns; ++s) {
+      Step& c = steps[s];
+      if (c.dead || c.ew || c.gemm_fused || c.group || c.stack_reduce || c.kind != Step::NORMAL || !c.holder) continue;
+      const PNode& cn = nodes[c.out_node];
+      if (cn.op != CONCAT || c.in_nodes.size() < 3 || cn.exposed) continue;
+      const int axis = (int)eigen::unpack_rank(*cn.func);
+      bool ok = axis < rank_cap;
+      for (int r = axis + 1; r < rank_cap && ok; ++r)
+        if (cn.shape.at(r) != 1) ok = false;
+      std::vector<std::pair<int, size_t>> refs;
+      for (size_t i = 0; i < c.in_nodes.size() && ok; ++i) {
+        const PNode& a = nodes[cn.args[i]];
+        if (a.shape.at(axis) != 1 || a.dtype != cn.dtype) ok = false;
+        refs.push_back({c.in_nodes[i], c.in_offsets[i]});
+      }
+      if (!ok) continue;
+      const size_t slab = (size_t)nodes[refs[0].first].n * type_size(cn.dtype);
+      int bn;
+      size_t bo;
+      bool same_root = true, fresh = true;
+      for (auto& r : refs) {
+        if (r.first != refs[0].first) same_root = false;
+        if (nodes[r.first].stack >= 0) fresh = false;  // only fresh stacks: the CONCAT's result must begin at the stack's base
+      }
+      if (same_root || !fresh || !stack_operands(refs, slab, false, bn, bo)) continue;
+      stack_operands(refs, slab, true, bn, bo);
+      const int sid = nodes[refs[0].first].stack;
+      nodes[c.out_node].alias_stack = sid;
+      // readers of the CONCAT now wait for the producers of its operands
+      for (int r : live_readers(c.out_node)) {
+        drop_node(r, c.out_node);
+        acc[r].rd.insert(acc[r].rd.end(), acc[s].rd.begin(), acc[s].rd.end());
+        for (auto& m : refs) steps[r].dep_nodes.push_back(m.first);
+      }
+      c.dead = true;
+      ++n_fused;
+    }
+    static const bool dbg = std::getenv("TCR_PLAN_DEBUG") != nullptr;
+    if (dbg) fprintf(stderr, "fuse_recurrent_steps: %d rewrites over %d steps\n", n_fused, ns);
+    if (n_fused == 0) { restore(); return; }
+
+    // ---- compact + stable topological re-sort on (root, version)
+    std::vector<int> live;
+    for (int s = 0; s < ns; ++s)
+      if (!steps[s].dead) live.push_back(s);
+    const int nl = (int)live.size();
+    std::map<std::pair<int, int>, int> writer;
+    std::map<std::pair<int, int>, std::vector<int>> readers_at;
+    for (int i = 0; i < nl; ++i) {
+      for (auto& w : acc[live[i]].wr) writer[w] = i;
+      for (auto& r : acc[live[i]].rd) readers_at[r].push_back(i);
+    }
+    std::vector<std::vector<int>> deps(nl);
+    bool broken = false;
+    for (int i = 0; i < nl && !broken; ++i) {
+      for (auto& r : acc[live[i]].rd) {
+        if (r.second == 0) continue;  // value from before the plan
+        auto w = writer.find(r);
+        if (w == writer.end()) {
+          if (std::getenv("TCR_PLAN_DEBUG")) fprintf(stderr, "  step %s reads %s v%d (op %s) which nobody writes\n", step_name(steps[live[i]]).c_str(), nodes[r.first].shape.to_string().c_str(), r.second, nodes[r.first].func ? egen::name_op((_GENERATED_OPCODE)nodes[r.first].op).c_str() : "leaf");
+          broken = true;
+          break;
+        }
+        if (w->second != i) deps[i].push_back(w->second);
+      }
+      for (auto& w : acc[live[i]].wr) {
+        if (w.second >= 2) {
+          auto pw = writer.find({w.first, w.second - 1});
+          if (pw != writer.end() && pw->second != i) deps[i].push_back(pw->second);
+        }
+        auto pr = readers_at.find({w.first, w.second - 1});
+        if (pr != readers_at.end())
+          for (int x : pr->second)
+            if (x != i) deps[i].push_back(x);
+      }
+    }
+    if (broken) { if (dbg) fprintf(stderr, "fuse_recurrent_steps: a read lost its writer, keeping the unfused plan\n"); restore(); return; }
+    std::vector<int> indeg(nl, 0);
+    std::vector<std::vector<int>> users(nl);
+    for (int i = 0; i < nl; ++i) {
+      std::sort(deps[i].begin(), deps[i].end());
+      deps[i].erase(std::unique(deps[i].begin(), deps[i].end()), deps[i].end());
+      for (int d : deps[i]) { users[d].push_back(i); ++indeg[i]; }
+    }
+    auto cmp = [&](int a, int b) { return steps[live[a]].pos > steps[live[b]].pos; };
+    std::priority_queue<int, std::vector<int>, decltype(cmp)> ready(cmp);
+    for (int i = 0; i < nl; ++i)
+      if (indeg[i] == 0) ready.push(i);
+    std::vector<int> order;
+    while (!ready.empty()) {
+      const int i = ready.top();
+      ready.pop();
+      order.push_back(i);
+      for (int u : users[i])
+        if (--indeg[u] == 0) ready.push(u);
+    }
+    if ((int)order.size() != nl) { if (dbg) fprintf(stderr, "fuse_recurrent_steps: cycle (%d of %d sorted), keeping the unfused plan\n", (int)order.size(), nl); restore(); return; }  // a merge closed a cycle: keep the unfused plan
+    std::vector<Step> sorted;
+    sorted.reserve(nl);
+    for (int i : order) sorted.push_back(std::move(steps[live[i]]));
+    steps = std::move(sorted);
+    for (auto& n : nodes) n.step = -1;
+    std::vector<int> wr;
+    for (size_t s = 0; s < steps.size(); ++s) {
+      nodes[steps[s].out_node].step = (int)s;
+      for (int e : steps[s].extra_outs) nodes[e].step = (int)s;
+    }
+  }
+
   // Reads / write of a step in terms of storage roots (before buffers exist)
   void step_access(const Step& st, std::vector<int>& reads, std::vector<int>& writes) const {
-    reads.clear();
-    writes.clear();
-    if (st.ew) for (auto& in : st.inputs) reads.push_back(in.node);
-    else for (int in : st.in_nodes) reads.push_back(in);
-    const PNode& out = nodes[st.out_node];
-    writes.push_back(st.out_node);
-    // an ASSIGN updates the variable's storage AND is what readers of the updated value name
-    if (is_assign(out.op)) writes.push_back(nodes[out.args[0]].root);
+    step_reads(st, reads);
+    step_writes(st, writes);
   }
 
   // Data-parallel plans: put every all-reduced gradient in one flat bucket and exchange it with ONE
@@ -1199,9 +1785,17 @@ struct Plan {
       Step& st = steps[s];
       if (st.ew) for (auto& in : st.inputs) last_use[in.node] = (int)s;
       else for (int in : st.in_nodes) last_use[in] = (int)s;
+      for (int d : st.dep_nodes) last_use[d] = (int)s;
     }
     for (auto& n : nodes)
       if (!n.func) n.ptr = leaf_ptr(n);
+    // stacks: operands that one fused step reads back to back live in ONE plan-owned buffer for the whole plan
+    for (auto& stk : stacks) {
+      stk.base = alloc_owned(stk.slab * stk.members.size());
+      for (int m : stk.members) nodes[m].ptr = (char*)stk.base + (size_t)nodes[m].stack_pos * stk.slab;
+    }
+    for (auto& n : nodes)
+      if (n.alias_stack >= 0) n.ptr = stacks[n.alias_stack].base;
     if (bucket_bytes > 0) {
       bucket = alloc_owned(bucket_bytes);
       check(tcr_memset(bucket, 0, bucket_bytes), "tcr_memset");  // the 16-byte padding between slots stays zero
@@ -1211,8 +1805,8 @@ struct Plan {
         if (st.kind != Step::BUCKET_MEMBER) continue;
         PNode& in = nodes[st.in_nodes[0]];
         PNode& out = nodes[st.out_node];
-        if (in.func && in.step >= 0 && !in.exposed && !is_assign(in.op) && last_use[st.in_nodes[0]] == (int)s &&
-            steps[in.step].kind == Step::NORMAL && in.n == out.n && in.dtype == out.dtype) {
+        if (in.func && in.step >= 0 && !in.exposed && !is_assign(in.op) && last_use[st.in_nodes[0]] == (int)s && in.stack < 0 &&
+            steps[in.step].out_node == st.in_nodes[0] && steps[in.step].kind == Step::NORMAL && in.n == out.n && in.dtype == out.dtype) {
           in.bucket_slot = (int64_t)st.bucket_offset;
           st.member_in_place = true;
         }
@@ -1220,11 +1814,40 @@ struct Plan {
     }
     std::multimap<size_t, void*> pool;  // plan-local free list: buffers are reused once their last reader has run
     std::vector<std::vector<int>> dying(steps.size());
+    auto place_pooled = [&](int node, size_t s) {
+      PNode& o = nodes[node];
+      size_t bytes = (size_t)o.n * type_size(o.dtype);
+      size_t bucket = bytes < 512 ? 512 : bytes;
+      auto it = pool.lower_bound(bucket);
+      if (it != pool.end() && it->first <= bucket * 2) {
+        o.ptr = it->second;
+        pool.erase(it);
+      } else {
+        o.ptr = alloc_owned(bucket);
+      }
+      int lu = last_use[node];
+      if (lu >= (int)s) dying[lu].push_back(node);
+      else dying[s].push_back(node);  // never read: reusable right after
+    };
     for (size_t s = 0; s < steps.size(); ++s) {
       Step& st = steps[s];
       PNode& out = nodes[st.out_node];
+      for (int e : st.extra_outs) {  // further results of a grouped launch
+        PNode& eo = nodes[e];
+        if (eo.stack >= 0) continue;
+        if (eo.exposed) {
+          auto op = dynamic_cast<DevOp*>(eo.holder);
+          if (!op) global::fatalf("planner: target %s cannot hold data", eo.tens->to_string().c_str());
+          eo.ptr = op->ensure_buffer(1, memory);
+          bound.push_back({e, eo.ptr});
+        } else {
+          place_pooled(e, s);
+        }
+      }
       if (st.kind == Step::BUCKET_FLUSH) {
         continue;  // owns nothing
+      } else if (out.stack >= 0 && st.kind == Step::NORMAL) {
+        // placed above: slab of a stack
       } else if (st.kind == Step::BUCKET_MEMBER) {
         out.ptr = (char*)bucket + st.bucket_offset;  // lives for the whole plan, never pooled
       } else if (out.bucket_slot >= 0) {
@@ -1260,18 +1883,7 @@ struct Plan {
         if (lu >= (int)s) dying[lu].push_back(st.out_node);
         else dying[s].push_back(st.out_node);
       } else {
-        size_t bytes = (size_t)out.n * type_size(out.dtype);
-        size_t bucket = bytes < 512 ? 512 : bytes;
-        auto it = pool.lower_bound(bucket);
-        if (it != pool.end() && it->first <= bucket * 2) {
-          out.ptr = it->second;
-          pool.erase(it);
-        } else {
-          out.ptr = alloc_owned(bucket);
-        }
-        int lu = last_use[st.out_node];
-        if (lu >= (int)s) dying[lu].push_back(st.out_node);
-        else dying[s].push_back(st.out_node);  // never read: reusable right after
+        place_pooled(st.out_node, s);
       }
       for (int d : dying[s]) {
         PNode& dn = nodes[d];
@@ -1300,6 +1912,22 @@ struct Plan {
           if (!in.ptr) global::fatalf("planner: input %s of %s was never materialised", in.tens->to_string().c_str(), out.tens->to_string().c_str());
           st.in.push_back((const char*)in.ptr + st.in_offsets[k]);
         }
+        if (st.group) {
+          tcr_gemm_group_desc& gd = st.gd;
+          size_t k = 0;
+          for (int q = 0; q < gd.segments; ++q) gd.a[q] = st.in[k++];
+          for (int g = 0; g < gd.groups; ++g)
+            for (int q = 0; q < gd.segments; ++q) gd.b[g][q] = st.in[k++];
+          for (int g = 0; g < gd.groups; ++g) {
+            gd.bias[g] = st.g_bias_slot[g] >= 0 ? st.in[st.g_bias_slot[g]] : nullptr;
+            gd.out[g] = st.g_out_nodes[g] >= 0 ? nodes[st.g_out_nodes[g]].ptr : nullptr;
+          }
+          if (gd.cell) {
+            gd.c_prev = st.g_cprev_slot >= 0 ? st.in[st.g_cprev_slot] : nullptr;
+            gd.c_out = nodes[st.g_c_node].ptr;
+            gd.h_out = nodes[st.g_h_node].ptr;
+          }
+        }
       }
     }
   }
@@ -1311,7 +1939,13 @@ struct Plan {
     } else if (st.kind == Step::BUCKET_MEMBER) {
       if (!st.member_in_place) check(tcr_d2d(st.out, st.in[0], (size_t)nodes[st.out_node].n * type_size(nodes[st.out_node].dtype)), "tcr_d2d");
     } else if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
-    else if (st.conv_dimg) {
+    else if (st.group) {
+      tcr_gemm_group_desc d = st.gd;
+      d.precision = gemm_precision();
+      check(tcr_gemm_grouped(&d), "tcr_gemm_grouped");
+    } else if (st.stack_reduce) {
+      check(tcr_reduce(st.red_op, st.in[0], st.out, st.red_shape, st.red_mask, FLOAT), "tcr_reduce");
+    } else if (st.conv_dimg) {
       tcr_gemm_desc d = st.gemm;
       d.precision = gemm_precision();
       check(tcr_gemm(st.in[0], st.in[1], st.conv_cols, &d), "tcr_gemm");
@@ -1364,6 +1998,7 @@ struct Plan {
       };
       if (st.ew) for (auto& in : st.inputs) read(nodes[in.node].ptr);
       else for (int in : st.in_nodes) read(nodes[in].ptr);
+      for (int dn : st.dep_nodes) read(nodes[dn].ptr);
       auto write = [&](const void* out) {
         auto w = last_writer.find(out);
         if (w != last_writer.end()) d.push_back(w->second);
@@ -1379,6 +2014,7 @@ struct Plan {
         for (int m : st.bucket_members) write(nodes[steps[m].out_node].ptr);
       } else {
         write(nodes[st.out_node].ptr);
+        for (int e : st.extra_outs) write(nodes[e].ptr);
       }
       // collectives (one communicator) and RAND_UNIF (one generator state) keep program order on lane 0
       const bool collective = st.kind == Step::BUCKET_FLUSH ||
@@ -1456,6 +2092,7 @@ struct Plan {
     }
     fuse();
     build_steps();
+    fuse_recurrent_steps();
     bucket_gradients();
     if (lower_only) return;
     assign_buffers();
@@ -1503,6 +2140,13 @@ struct Plan {
     std::string what = egen::name_op((_GENERATED_OPCODE)o.op);
     if (st.kind == Step::BUCKET_MEMBER) return what + " -> bucket";
     if (st.ew) return what + " fused(" + std::to_string(st.prog.n_instrs) + " instr, " + std::to_string(st.prog.n_inputs) + " in)";
+    if (st.group) {
+      std::string k;
+      for (int q = 0; q < st.gd.segments; ++q) k += (q ? "+" : "") + std::to_string(st.gd.seg_k[q]);
+      return std::string(st.gd.b_trans ? "GEMM-SUM" : "GEMM-GROUP") + (st.gd.cell ? "+cell" : "") + " x" + std::to_string(st.gd.groups) + " m" + std::to_string(st.gd.m) + " n" +
+             std::to_string(st.gd.n) + " k" + k;
+    }
+    if (st.stack_reduce) return what + "-STACK(" + std::to_string(st.dep_nodes.size()) + ")";
     const std::string mnk = " m" + std::to_string(st.gemm.m) + " n" + std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
     if (st.conv_fused)
       return st.conv_dimg ? "CONV2D-dX GEMM+col2im" + mnk : std::string(st.conv_grad ? "CONV2D-dK" : "CONV2D") + " im2col+GEMM" + (st.gemm.epilogue ? "+bias" : "") + (st.gemm.activation ? "+act" : "") + mnk;

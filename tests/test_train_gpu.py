@@ -97,6 +97,31 @@ def test_recurrent_training_matches_oracle(gpu, kind, batch, evaluator):
         tc.set_evaluator("plan")
 
 
+@pytest.mark.parametrize("kind,batch,seq", [("lstm", 8, 10), ("lstm", 70, 3), ("gru", 8, 10), ("lstm", None, 10)])
+def test_recurrent_training_with_step_fusion_matches_oracle(gpu, kind, batch, seq):
+    """sizes at which the planner's recurrent-step fusion applies (grouped gate products, K-segmented sums, stacked weight
+    gradients: units >= 32, more than 8 time steps for the n-ary ADDs): same oracle, same tolerance as the unfused plans"""
+    tc.set_evaluator("plan")
+    vocab, hidden = 32, 64
+    cfg = configs.recurrent(kind, vocab=vocab, hidden=hidden, seq=seq, batch=batch, learning_rate=0.05)
+    if kind == "lstm" and batch is not None:
+        plan = tc.describe_plan([cfg.train])
+        assert any(s.startswith("GEMM-GROUP x4") for s in plan) and any(s.startswith("GEMM-SUM") for s in plan), plan[:40]
+    sess = OracleSession([cfg.train])
+    rng = np.random.default_rng(5)
+    for step in range(3):
+        x, y = configs.recurrent_batch(rng, cfg.feeds, vocab)
+        cfg.feeds["x"].assign(x)
+        cfg.feeds["y"].assign(y)
+        sess.assign(cfg.feeds["x"], x)
+        sess.assign(cfg.feeds["y"], y)
+        loss = cfg.train.get()
+        want = sess.run()[0]
+        assert rel_err(loss, want) < 1e-4, (step, loss, want)
+    for v in cfg.variables:
+        assert rel_err(v.data(), sess.leaf_value(v)) < 5e-4
+
+
 def test_rbm_training_statistics(gpu):
     """RAND_UNIF streams differ from the reference's std::default_random_engine by design
     (SURVEY.md §2a): CD-1 is checked statistically — the reconstruction error falls."""
