@@ -1359,6 +1359,117 @@ struct Plan {
       }
     }
 
+    // ================= (1b) LSTM cell update in the epilogue of the grouped gate launch =================
+    // state = ADD(MUL(gate, in), MUL(state, forget)); hidden = MUL(state, output) (cfg/tenncor/layer.yml:758-760): when the four
+    // operands are the four results of one grouped launch, the CTA that holds all gates of a unit computes both on the spot.
+    for (int s = 0; s < ns; ++s) {
+      if (steps[s].dead || !steps[s].group || steps[s].gd.groups != 4 || steps[s].gd.b_trans || steps[s].gd.cell) continue;
+      int gate_of[4];
+      for (int g = 0; g < 4; ++g) gate_of[g] = steps[s].g_out_nodes[g];
+      auto which_gate = [&](int arg) {
+        const PNode& a = nodes[arg];
+        if (a.offset != 0) return -1;
+        for (int g = 0; g < 4; ++g)
+          if (a.root == gate_of[g]) return g;
+        return -1;
+      };
+      // E1: the state update, an elementwise step reading gates of this launch
+      int e1 = -1, e2 = -1, role_f = -1, role_o = -1, cprev = -2;
+      size_t cprev_off = 0;
+      int pair[2] = {-1, -1};
+      for (int r : live_readers(gate_of[0])) {
+        const Step& e = steps[r];
+        if (!e.ew || e.kind != Step::NORMAL) continue;
+        const int c = e.out_node;
+        const PNode& cn = nodes[c];
+        auto mem = members.find(c);
+        if (cn.op != ADD || cn.args.size() != 2 || cn.dtype != FLOAT || mem == members.end() || mem->second.size() != 3) continue;
+        const PNode &p = nodes[nodes[cn.args[0]].root], &q = nodes[nodes[cn.args[1]].root];
+        if (!p.func || !q.func || p.op != MUL || q.op != MUL || p.args.size() != 2 || q.args.size() != 2 || !p.inlined || !q.inlined || p.region != c || q.region != c) continue;
+        const int leaf[4] = {p.args[0], p.args[1], q.args[0], q.args[1]};
+        int g4[4], n_gate = 0, other = -1;
+        for (int k = 0; k < 4; ++k) {
+          g4[k] = which_gate(leaf[k]);
+          if (g4[k] >= 0) ++n_gate;
+          else other = k;
+        }
+        if (n_gate != 3) continue;
+        bool distinct = true;
+        for (int a = 0; a < 4; ++a)
+          for (int b = a + 1; b < 4; ++b)
+            if (g4[a] >= 0 && g4[a] == g4[b]) distinct = false;
+        if (!distinct) continue;
+        const PNode& on = nodes[leaf[other]];
+        if (on.has_scalar) {
+          if (on.scalar != 0.0) continue;
+          cprev = -1;  // zero state
+        } else {
+          if (on.n != cn.n || on.dtype != FLOAT || on.is_extend) continue;
+          cprev = on.root;
+          cprev_off = on.offset;
+        }
+        role_f = g4[other ^ 1];                       // the gate multiplied with the previous state
+        pair[0] = g4[(other < 2) ? 2 : 0];            // the other product: candidate x input gate (commutative)
+        pair[1] = g4[(other < 2) ? 3 : 1];
+        role_o = 6 - role_f - pair[0] - pair[1];
+        e1 = r;
+        break;
+      }
+      if (e1 < 0) continue;
+      const int c = steps[e1].out_node;
+      for (int r : live_readers(c)) {
+        const Step& e = steps[r];
+        if (!e.ew || e.kind != Step::NORMAL) continue;
+        const int h = e.out_node;
+        const PNode& hn = nodes[h];
+        auto mem = members.find(h);
+        if (hn.op != MUL || hn.args.size() != 2 || hn.dtype != FLOAT || mem == members.end() || mem->second.size() != 1) continue;
+        const PNode &x = nodes[hn.args[0]], &y = nodes[hn.args[1]];
+        const bool cx = x.root == c && x.offset == 0, cy = y.root == c && y.offset == 0;
+        if (cx == cy) continue;
+        if (which_gate(cx ? hn.args[1] : hn.args[0]) != role_o) continue;
+        e2 = r;
+        break;
+      }
+      if (e2 < 0 || nodes[c].n != steps[s].gd.m * steps[s].gd.n) continue;
+      const int h = steps[e2].out_node;
+      Step& g = steps[s];
+      tcr_gemm_group_desc trial = g.gd;
+      trial.cell = 1;
+      trial.role_cand = pair[0]; trial.role_in = pair[1]; trial.role_forget = role_f; trial.role_out = role_o;
+      trial.state_pitch = trial.n;
+      if (tcr_gemm_grouped_check(&trial) != TCR_OK) continue;
+      g.gd = trial;
+      if (cprev >= 0) {
+        g.g_cprev_slot = (int)g.in_nodes.size();
+        g.in_nodes.push_back(cprev);
+        g.in_offsets.push_back(cprev_off);
+      }
+      g.g_c_node = c;
+      g.g_h_node = h;
+      merge_acc(s, e1);
+      merge_acc(s, e2);
+      steps[e1].dead = true;
+      steps[e2].dead = true;
+      // a gate nobody else reads is not stored
+      g.extra_outs.clear();
+      g.out_node = h;
+      g.extra_outs.push_back(c);
+      for (int k = 0; k < 4; ++k) {
+        bool read = nodes[gate_of[k]].exposed;
+        std::vector<int> rd;
+        for (int r : live_readers(gate_of[k])) {
+          if (r == s) continue;
+          step_reads(steps[r], rd);
+          if (std::find(rd.begin(), rd.end(), gate_of[k]) != rd.end()) read = true;
+        }
+        if (read) g.extra_outs.push_back(gate_of[k]);
+        else { g.g_out_nodes[k] = -1; drop_node(s, gate_of[k]); }
+      }
+      g.pos = std::max(g.pos, steps[e2].pos);
+      ++n_fused;
+    }
+
     // ================= (2) ADD of products (+ SLICE of the sum) -> one K-segmented launch =================
     for (int s = 0; s < ns; ++s) {
       Step& e = steps[s];
