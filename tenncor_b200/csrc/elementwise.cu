@@ -168,6 +168,7 @@ __device__ __forceinline__ void st16(T* p, const Vec<T>& r) {
 // mode: 0 = unary/binary cwise, 1 = in-place assign flavour handled by caller through pointers.
 template <typename T, int OP, int NIN>
 __global__ void __launch_bounds__(256) ew_direct_kernel(const T* a, const T* b, const T* c, T* out, int64_t n) {
+  TCR_PDL_ENTER();
   constexpr int N = Vec<T>::N;
   constexpr int UNROLL = 2;
   const int64_t nvec = n / N;
@@ -319,6 +320,7 @@ template <typename T> struct VmCfg { static constexpr int THREADS = sizeof(T) ==
 // the cost of a VM instruction two shared loads, one uniform opcode branch and one store.
 template <typename T, bool ALIGNED, typename I>
 __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_constant__ VmParams p) {
+  TCR_PDL_ENTER();
   constexpr int THREADS = VmCfg<T>::THREADS;
   __shared__ V4<T> regs[TCR_EW_NREGS][THREADS];
   const I n = (I)p.n;
@@ -579,6 +581,7 @@ __device__ __noinline__ void chain_store_general(void* out, int dtype, uint32_t 
 
 template <typename T, int CH>
 __global__ void __launch_bounds__(256, 4) ew_chain_kernel(const __grid_constant__ ChainParams p) {
+  TCR_PDL_ENTER();
   constexpr int THREADS = 256;
   using I = uint32_t;
   extern __shared__ __align__(16) unsigned char chain_smem[];
@@ -930,13 +933,16 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2])
 // device lets a captured CUDA graph draw fresh numbers at every replay (the kernel reads the offset,
 // a one-thread kernel behind it advances it), in the same sequence an eager run produces.
 __device__ uint64_t g_rand_state[2];
-__global__ void rand_seed_kernel(uint64_t seed, uint64_t offset) { g_rand_state[0] = seed; g_rand_state[1] = offset; }
-__global__ void rand_advance_kernel(uint64_t n) { g_rand_state[1] += n; }
+__global__ void rand_seed_kernel(uint64_t seed, uint64_t offset) {
+  TCR_PDL_ENTER(); g_rand_state[0] = seed; g_rand_state[1] = offset; }
+__global__ void rand_advance_kernel(uint64_t n) {
+  TCR_PDL_ENTER(); g_rand_state[1] += n; }
 
 template <typename T, bool STREAM = false>
 __global__ void __launch_bounds__(256) rand_unif_kernel(const T* __restrict__ lo, const T* __restrict__ hi,
                                                         T* __restrict__ out, int64_t n, uint64_t seed,
                                                         uint64_t offset) {
+  TCR_PDL_ENTER();
   if (STREAM) {
     seed = g_rand_state[0];
     offset = g_rand_state[1];
@@ -968,17 +974,20 @@ __global__ void __launch_bounds__(256) rand_unif_kernel(const T* __restrict__ lo
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n) {
+  TCR_PDL_ENTER();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (TO)in[i];
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) scale_kernel(T* __restrict__ buf, int64_t n, double s) {
+  TCR_PDL_ENTER();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] = (T)((double)buf[i] * s);
 }
 template <>
 __global__ void __launch_bounds__(256) scale_kernel<float>(float* __restrict__ buf, int64_t n, double s) {
+  TCR_PDL_ENTER();
   const float fs = (float)s;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] *= fs;

@@ -30,6 +30,7 @@ constexpr int BM = 64, BN = 64, BK = 16;
 template <typename T>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C,
                                                         const __grid_constant__ tcr_gemm_desc d) {
+  TCR_PDL_ENTER();
   __shared__ T As[BK][BM + 4];
   __shared__ T Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -109,6 +110,7 @@ struct ContractDesc {
 template <typename T>
 __global__ void __launch_bounds__(256) contract_generic_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                                                T* __restrict__ out, const __grid_constant__ ContractDesc d) {
+  TCR_PDL_ENTER();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < d.n_out; o += stride) {
     int64_t t = o, aoff = 0, boff = 0;
@@ -135,6 +137,7 @@ struct ConvDesc {
 template <typename T>
 __global__ void __launch_bounds__(256) conv_generic_kernel(const T* __restrict__ img, const T* __restrict__ kern,
                                                            T* __restrict__ out, const __grid_constant__ ConvDesc d) {
+  TCR_PDL_ENTER();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < d.n_out; o += stride) {
     int64_t t = o, base = 0;

@@ -38,6 +38,9 @@ constexpr int RM = 128, RN = 64, RK = 32;
 constexpr int W_TILE = RM * RK * 4;  // 16 KiB
 constexpr int X_TILE = RN * RK * 4;  // 8 KiB
 constexpr int THREADS = 192;
+constexpr int NACC = 1;  // TMEM accumulators used round-robin by the k-steps of a k-block and summed in the epilogue. Measured: 4 independent
+                         // accumulators do not speed the MMAs up (the ~83 cycles per 128 x 64 x 8 MMA are not an accumulator dependency) and
+                         // cost ~300 cycles of extra TMEM loads, so one is used.
 constexpr int RED_BYTES = RM * RN * 4;        // 32 KiB: [src CTA][column][row]
 constexpr int CELL_BYTES = 4 * RN * 32 * 4;   // 32 KiB: [gate][column][unit <= 32]
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
@@ -64,6 +67,7 @@ struct RnnParams {
   float* c_out;
   float* h_out;
   int64_t state_pitch;
+  int dbg_mode;    // TCR_RNN_EXPERIMENT: 1 = no MMAs (TMA only), 2 = no TMA loads (MMAs on whatever shared memory holds), 4 = X tile not loaded
   long long* dbg;  // TCR_RNN_DEBUG: SM-clock stamps of CTA (0,0,0), see tcr_rnn_debug_read
 };
 
@@ -206,9 +210,12 @@ __device__ __forceinline__ void rnn_epilogue(const RnnParams& p, uint64_t* tmem_
       if (threadIdx.x == 64) RNN_STAMP(6);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int j = 0; j < RN; ++j) v[j] = 0.f;
+#pragma unroll
+      for (int part = 0; part < 2 * NACC; ++part) {  // NACC accumulators x two 32-column halves
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * 32);
+        const int half = part & 1;
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((part >> 1) * RN + half * 32);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -219,7 +226,7 @@ __device__ __forceinline__ void rnn_epilogue(const RnnParams& p, uint64_t* tmem_
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[half * 32 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[half * 32 + j] += __uint_as_float(r[j]);
       }
     } else {
 #pragma unroll
@@ -335,79 +342,115 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(RN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(RN * NACC));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  TCR_PDL_ENTER();  // everything above touched no global memory: the previous kernel may still be running
   if (threadIdx.x == 0) RNN_STAMP(1);
   cluster_arrive();  // #1: "this CTA is running" — awaited before anybody writes into a peer's shared memory
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      const int chunks_per_group = 4 / p.groups;  // MN-major: the 128-row tile is four 32-unit chunks
-      for (int i = 0; i < num_kb; ++i) {
-        const int st = i % STAGES;
-        const uint32_t round = i / STAGES;
-        if (i >= STAGES) mbar_wait(&empty[st], (round - 1) & 1);
-        const int kbg = kb_begin + i;
-        int s = 0;
-        while (s + 1 < p.nseg && kbg >= p.seg_kb_end[s]) ++s;
-        const int kl = kbg - (s ? p.seg_kb_end[s - 1] : 0);
-        mbar_expect_tx(&full[st], W_TILE + X_TILE);
-        const int32_t wk = p.w_k0[s] + kl * RK;
-        if (p.w_mn_major) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int g = j / chunks_per_group, sub = j % chunks_per_group;
-            tma_load_2d(&maps.w[g * p.nseg + s], &full[st], tile_w(st) + j * 4096, u0 + 32 * sub, wk);  // [32 k][32 units]
-          }
-        } else {
-          for (int g = 0; g < p.groups; ++g)
-            tma_load_2d(&maps.w[g * p.nseg + s], &full[st], tile_w(st) + g * p.rows_per_group * 128, wk, u0);  // [rows][32 k]
-        }
-        tma_load_2d(&maps.x[s], &full[st], tile_x(st), kl * RK, m0);  // [64 batch rows][32 k]
-        if (i == 0) RNN_STAMP(2);
+    // One lane per box: lanes 0..3 fetch the weight boxes, lane 4 the activation tile; lane 0 also arms the barrier. (One thread
+    // issuing five TMAs with their address arithmetic cost ~950 cycles per k-block: the loop was bound by that thread, not by L2.)
+    {
+      // per-lane constants of the weight box this lane fetches
+      const int chunks_per_group = 4 / p.groups;
+      int my_map = 0, c0 = 0, c1 = 0;         // tensor-map index (without the segment), fixed coordinates
+      uint32_t my_off = 0;                    // byte offset of the box inside the weight tile
+      bool w_lane = false;
+      if (p.w_mn_major) {                      // four [32 k][32 units] boxes
+        w_lane = lane < 4;
+        const int g = lane / chunks_per_group, sub = lane % chunks_per_group;
+        my_map = g * p.nseg;
+        c0 = u0 + 32 * sub;
+        my_off = (uint32_t)lane * 4096u;
+      } else {                                 // one [rows_per_group][32 k] box per group
+        w_lane = lane < p.groups;
+        my_map = lane * p.nseg;
+        c1 = u0;
+        my_off = (uint32_t)(lane * p.rows_per_group) * 128u;
       }
-      RNN_STAMP(3);
+      const bool x_lane = lane == 4 && !(p.dbg_mode & 4);
+      const uint32_t tx_bytes = (p.dbg_mode & 4) ? W_TILE : W_TILE + X_TILE;
+      int seg = 0, kl = kb_begin;  // segment of the current k-block and its index inside the segment
+      while (seg + 1 < p.nseg && kb_begin >= p.seg_kb_end[seg]) ++seg;
+      if (seg > 0) kl = kb_begin - p.seg_kb_end[seg - 1];
+      int st = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < num_kb; ++i) {
+        if (i >= STAGES && lane < 5) mbar_wait(&empty[st], phase ^ 1);
+        if (p.dbg_mode & 2) {
+          if (lane == 0) mbar_arrive(&full[st]);
+        } else {
+          if (lane == 0) mbar_expect_tx(&full[st], tx_bytes);
+          const int32_t wk = kl * RK;
+          uint8_t* const wt = tile_w(st);
+          if (w_lane) {
+            if (p.w_mn_major) tma_load_2d(&maps.w[my_map + seg], &full[st], wt + my_off, c0, wk);
+            else tma_load_2d(&maps.w[my_map + seg], &full[st], wt + my_off, wk, c1);
+          }
+          if (x_lane) tma_load_2d(&maps.x[seg], &full[st], wt + W_TILE, wk, m0);
+        }
+        if (i == 0 && lane == 0) RNN_STAMP(2);
+        ++kl;
+        if (seg + 1 < p.nseg && kb_begin + i + 1 >= p.seg_kb_end[seg]) { ++seg; kl = 0; }
+        if (++st == STAGES) { st = 0; phase ^= 1; }
+      }
+      if (lane == 0) RNN_STAMP(3);
     }
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // The whole warp runs the loop (uniform control flow keeps the descriptor arithmetic in uniform registers, which is where
+    // UTCHMMA reads its operands from); one elected lane issues. Descriptors are (constant fields | address >> 4), so the loop
+    // adds precomputed 16-byte-unit offsets instead of re-encoding them. Measured per MMA issued by a lone divergent thread:
+    // ~83 cycles of issue against a 32-cycle execution floor (128 x 64 x 8).
+    {
       const uint32_t idesc = make_idesc(p.w_mn_major);
       const uint32_t a_lbo = p.w_mn_major ? 4096 : 16, a_sbo = p.w_mn_major ? 512 : 1024, a_kstep = p.w_mn_major ? 1024 : 32;
       const uint32_t a_lt = p.w_mn_major ? 1 : 2;
-      uint32_t accumulate = 0;
+      const uint64_t a_base = make_desc(smem_u32(smem), a_lbo, a_sbo, a_lt);            // weight tile of stage 0
+      const uint64_t b_base = make_desc(smem_u32(smem) + W_TILE, 16, 1024, 2);           // activation tile of stage 0
+      const uint64_t a_step = a_kstep >> 4, b_step = 32 >> 4, stage_step = STAGE_BYTES >> 4, lo_step = (W_TILE + X_TILE) >> 4;
+      const bool issuer = lane == 0;
+      int st = 0;
+      uint32_t phase = 0;
+      uint64_t da0 = a_base, db0 = b_base;
       for (int i = 0; i < num_kb; ++i) {
-        const int st = i % STAGES;
-        const uint32_t round = i / STAGES;
-        mbar_wait(MODE == 2 ? &ready[st] : &full[st], round & 1);
-        if (i == 0) RNN_STAMP(4);
+        mbar_wait(MODE == 2 ? &ready[st] : &full[st], phase);
+        if (i == 0 && issuer) RNN_STAMP(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_u32(tile_w(st)), b_addr = smem_u32(tile_x(st));
+        if (p.dbg_mode & 1) {
+          if (issuer) mbar_arrive(&empty[st]);
+        } else {
+          const uint32_t acc = i != 0;
+          if (issuer) {
 #pragma unroll
-        for (int k8 = 0; k8 < RK / 8; ++k8) {
-          const uint64_t da = make_desc(a_addr + k8 * a_kstep, a_lbo, a_sbo, a_lt);
-          const uint64_t db = make_desc(b_addr + k8 * 32, 16, 1024, 2);
-          if (MODE == 2) {
-            const uint64_t da_lo = make_desc(a_addr + (W_TILE + X_TILE) + k8 * a_kstep, a_lbo, a_sbo, a_lt);
-            const uint64_t db_lo = make_desc(b_addr + (W_TILE + X_TILE) + k8 * 32, 16, 1024, 2);
-            umma_tf32(tmem_base, da_lo, db, idesc, accumulate);  // small terms first
-            umma_tf32(tmem_base, da, db_lo, idesc, 1);
-            umma_tf32(tmem_base, da, db, idesc, 1);
-          } else {
-            umma_tf32(tmem_base, da, db, idesc, accumulate);
+            for (int k8 = 0; k8 < RK / 8; ++k8)  // k-step k8 accumulates into accumulator k8: consecutive MMAs are independent
+              umma_tf32(tmem_base + (k8 % NACC) * RN, (MODE == 2 ? lo_step : 0) + da0 + k8 * a_step, db0 + k8 * b_step, idesc, acc | (uint32_t)(k8 >= NACC));  // 3xTF32: small terms first
+            if (MODE == 2) {
+#pragma unroll
+              for (int k8 = 0; k8 < RK / 8; ++k8) umma_tf32(tmem_base + (k8 % NACC) * RN, da0 + k8 * a_step, db0 + k8 * b_step + lo_step, idesc, 1);
+#pragma unroll
+              for (int k8 = 0; k8 < RK / 8; ++k8) umma_tf32(tmem_base + (k8 % NACC) * RN, da0 + k8 * a_step, db0 + k8 * b_step, idesc, 1);
+            }
+            umma_commit(&empty[st]);
           }
-          accumulate = 1;
+          __syncwarp();
         }
-        umma_commit(&empty[st]);
+        da0 += stage_step;
+        db0 += stage_step;
+        if (++st == STAGES) { st = 0; phase ^= 1; da0 = a_base; db0 = b_base; }
       }
-      umma_commit(tmem_full);
-      RNN_STAMP(5);
+      if (issuer) {
+        if (p.dbg_mode & 1) mbar_arrive(tmem_full); else umma_commit(tmem_full);
+        RNN_STAMP(5);
+      }
     }
     __syncwarp();
   } else {
@@ -456,7 +499,7 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
   if (threadIdx.x == 64) RNN_STAMP(9);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(RN));
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(RN * NACC));
   if (threadIdx.x == 0) RNN_STAMP(10);
 }
 
@@ -506,13 +549,15 @@ int launch_rnn(const RnnMaps& maps, const RnnParams& p, dim3 grid, int cluster) 
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = RnnCfg<MODE>::SMEM;
   cfg.stream = state().stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = (unsigned)cluster;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   TCR_CUDA(cudaLaunchKernelEx(&cfg, gemm_rnn_kernel<MODE>, maps, p));
   state().launches.fetch_add(1, std::memory_order_relaxed);
   return TCR_OK;
@@ -587,6 +632,8 @@ int tcr_gemm_grouped(const tcr_gemm_group_desc* d) {
     TCR_CUDA(cudaMemset(g_rnn_dbg, 0, 16 * sizeof(long long)));
   }
   p.dbg = debug ? g_rnn_dbg : nullptr;
+  static const int experiment = std::getenv("TCR_RNN_EXPERIMENT") ? std::atoi(std::getenv("TCR_RNN_EXPERIMENT")) : 0;
+  p.dbg_mode = experiment;
 
   const int64_t tiles = ceil_div(d->n, p.rows_per_group) * ceil_div(d->m, RN);
   TCR_ARG(tiles <= 65535, "tcr_gemm_grouped: output too large for this kernel (%lld tiles)", (long long)tiles);
@@ -594,7 +641,7 @@ int tcr_gemm_grouped(const tcr_gemm_group_desc* d) {
   static const int forced = std::getenv("TCR_RNN_CLUSTER") ? std::atoi(std::getenv("TCR_RNN_CLUSTER")) : 0;
   const int sms = state().sm_count;
   int cluster = 1;
-  for (int c = 2; c <= 16; c *= 2)
+  for (int c = 2; c <= 8; c *= 2)  // 16 (non-portable) measured slower than 8 on the 64 x 1024 x 4096 sum (20.5 vs 15.6 us)
     if (tiles * c <= sms && kb / c >= 2) cluster = c;
   if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) cluster = forced;
   while (cluster > 1 && kb < cluster) cluster /= 2;

@@ -55,6 +55,7 @@ template <> __device__ __forceinline__ int64_t sk_shfl_down(int64_t v, int o) { 
 template <typename T>
 __global__ void __launch_bounds__(256) skinny_rk_kernel(const T* __restrict__ X, const T* __restrict__ Y, T* __restrict__ C,
                                                         const __grid_constant__ SkinnyDesc d) {
+  TCR_PDL_ENTER();
   constexpr int KC = 128, RPW = 4;
   __shared__ T ysm[SK_MAX][KC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(256) skinny_rk_kernel(const T* __restrict__ X,
 template <typename T>
 __global__ void __launch_bounds__(256) skinny_rs_kernel(const T* __restrict__ X, const T* __restrict__ Y, T* __restrict__ C,
                                                         T* __restrict__ ws, int64_t kchunk, const __grid_constant__ SkinnyDesc d) {
+  TCR_PDL_ENTER();
   const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t k0 = (int64_t)blockIdx.y * kchunk, k1 = k0 + kchunk < d.K ? k0 + kchunk : d.K;
   __shared__ T ysm[SK_MAX][64];
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(256) skinny_rs_kernel(const T* __restrict__ X,
 template <typename T>
 __global__ void __launch_bounds__(256) skinny_rs_reduce_kernel(const T* __restrict__ ws, T* __restrict__ C, int splits,
                                                                const __grid_constant__ SkinnyDesc d) {
+  TCR_PDL_ENTER();
   __shared__ T part[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t lblocks = (d.L + 31) / 32;
@@ -180,6 +183,7 @@ __global__ void __launch_bounds__(256) skinny_rs_reduce_kernel(const T* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) small_k_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C,
                                                       const __grid_constant__ tcr_gemm_desc d) {
+  TCR_PDL_ENTER();
   __shared__ T a_sm[64][SK_MAX];
   const int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const bool n_ok = n < d.n;
@@ -225,6 +229,7 @@ template <typename T> struct alignas(16) SkVec { T v[16 / sizeof(T)]; };
 template <typename T, int SP>
 __global__ void __launch_bounds__(256, (SP * sizeof(T) <= 48 ? 2 : 1)) skinny_rk2_kernel(const T* __restrict__ X, const T* __restrict__ Y, T* __restrict__ C,
                                                          int kc, const __grid_constant__ SkinnyDesc d) {
+  TCR_PDL_ENTER();
   constexpr int V = 16 / sizeof(T), RPW = 4, KSTEP = 32 * V;
   extern __shared__ __align__(16) unsigned char sk_smem[];
   T* ysm = reinterpret_cast<T*>(sk_smem);
@@ -297,6 +302,7 @@ __global__ void __launch_bounds__(256, (SP * sizeof(T) <= 48 ? 2 : 1)) skinny_rk
 template <typename T, int SP>
 __global__ void __launch_bounds__(256) skinny_rs2_kernel(const T* __restrict__ X, const T* __restrict__ Y, T* __restrict__ C,
                                                          T* __restrict__ ws, int64_t kchunk, const __grid_constant__ SkinnyDesc d) {
+  TCR_PDL_ENTER();
   constexpr int V = 16 / sizeof(T), KS = 128, U = 8;
   __shared__ __align__(16) T ysm[KS * SP];
   const int64_t l = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V;
@@ -356,6 +362,7 @@ __global__ void __launch_bounds__(256) skinny_rs2_kernel(const T* __restrict__ X
 template <typename T, int KP>
 __global__ void __launch_bounds__(256) small_k2_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C,
                                                        const __grid_constant__ tcr_gemm_desc d) {
+  TCR_PDL_ENTER();
   constexpr int V = 16 / sizeof(T);
   __shared__ __align__(16) T a_sm[64 * KP];
   const int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -400,6 +407,7 @@ __global__ void __launch_bounds__(256) small_k2_kernel(const T* __restrict__ A, 
 template <typename T, int KP>
 __global__ void __launch_bounds__(256) small_kn_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C,
                                                        const __grid_constant__ tcr_gemm_desc d) {
+  TCR_PDL_ENTER();
   __shared__ T b_sm[KP][SK_MAX];
   for (int e = threadIdx.x; e < KP * SK_MAX; e += 256) {
     const int k = e / SK_MAX, n = e % SK_MAX;

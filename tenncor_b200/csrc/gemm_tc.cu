@@ -176,6 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  TCR_PDL_ENTER();  // everything above touched no global memory: the previous kernel may still be running
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -416,6 +417,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 // deterministic split-K: out(m,n) = epilogue(sum_z ws[z][m][n])
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, TcParams p) {
+  TCR_PDL_ENTER();
   const int64_t total = p.m * p.n, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t m = i / p.n, n = i % p.n;

@@ -185,6 +185,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   cluster_sync();  // the peer's barriers exist before anyone arrives on them remotely
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  TCR_PDL_ENTER();  // everything above touched no global memory: the previous kernel may still be running
 
   // work item -> tile coordinates and k range
   auto decode = [&](int item, int64_t& m0, int64_t& n0, int& kb0, int& nkb, int& split) {
@@ -420,6 +421,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 }
 
 __global__ void __launch_bounds__(256) splitk2_reduce_kernel(const float* __restrict__ ws, int splits, Tc2Params p) {
+  TCR_PDL_ENTER();
   const int64_t total = p.m * p.n, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t m = i / p.n, n = i % p.n;
@@ -447,13 +449,15 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Params& p,
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM;
   cfg.stream = state().stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   TCR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<MODE>, ma, mb, p));
   state().launches.fetch_add(1, std::memory_order_relaxed);
   return TCR_OK;

@@ -24,6 +24,7 @@ struct Im2colDesc {
 
 // generic form: one thread per 16-byte group of a row, 64-bit coordinate arithmetic (any size)
 __global__ void __launch_bounds__(256) im2col_kernel(const uint32_t* __restrict__ img, uint4* __restrict__ cols, Im2colDesc d) {
+  TCR_PDL_ENTER();
   const int64_t total = d.rows * d.pitch4;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = t / d.pitch4, g = t - row * d.pitch4;
@@ -63,6 +64,7 @@ constexpr int IM_ROWS = 32;
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) im2col_tiled_kernel(const uint32_t* __restrict__ img, uint4* __restrict__ cols, Im2colDesc d) {
+  TCR_PDL_ENTER();
   extern __shared__ int32_t woff[];  // [pitch4 * 4] window offsets (-1: zero fill), then IM_ROWS row bases
   const int pitch4 = (int)d.pitch4;
   int32_t* base = woff + pitch4 * 4;
@@ -139,6 +141,7 @@ constexpr int C2I_MAX_SLIDE = 4;
 // consecutive columns of the same rows: one 16-byte load per term and a quarter of the instructions per byte.
 template <bool VEC>
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ cols, float* __restrict__ img, Col2imDesc d) {
+  TCR_PDL_ENTER();
   extern __shared__ int32_t table[];  // n_combo x (C2I_MAX_SLIDE window coordinates + column offset)
   constexpr int TW = C2I_MAX_SLIDE + 1;
   for (int c = threadIdx.x; c < d.n_combo; c += blockDim.x) {

@@ -34,6 +34,7 @@ struct MapPlan {
 
 template <typename E, typename I, bool CHECK>
 __global__ void __launch_bounds__(256) map_copy_kernel(const E* __restrict__ in, E* __restrict__ out, const __grid_constant__ MapPlan p) {
+  TCR_PDL_ENTER();
   const I n = (I)p.n_out;
   const I stride = (I)gridDim.x * blockDim.x;
   for (I o = (I)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += stride) {
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(256) map_copy_kernel(const E* __restrict__ in,
 // out[j + B*(i + A*c)] = in[i + A*(j + B*c)]  (in is [A, B, C], out is [B, A, C])
 template <typename E>
 __global__ void __launch_bounds__(256) transpose_kernel(const E* __restrict__ in, E* __restrict__ out, int64_t A, int64_t B) {
+  TCR_PDL_ENTER();
   __shared__ E tile[32][33];
   const int64_t c = blockIdx.z;
   const E* src = in + c * A * B;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const E* __restrict__ in
 // in is [A (fast), B, C]: tile = 16*V elements along A x 64 along B; out is [B (fast), A, C].
 template <typename E>
 __global__ void __launch_bounds__(256) transpose_vec_kernel(const E* __restrict__ in, E* __restrict__ out, int64_t A, int64_t B) {
+  TCR_PDL_ENTER();
   constexpr int V = 16 / sizeof(E), TA = 16 * V, TB = 64;
   __shared__ E tile[TB][TA + 1];
   struct alignas(16) Vec { E v[V]; };
@@ -131,6 +134,7 @@ struct ConcatArgs {
 template <typename E>
 __global__ void __launch_bounds__(256) concat_one_kernel(const E* __restrict__ in, E* __restrict__ out, int64_t inner,
                                                          int64_t ext, int64_t outer, int64_t off, int64_t out_ext) {
+  TCR_PDL_ENTER();
   const int64_t n = inner * ext * outer, stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t row = inner * ext;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(256) concat_one_kernel(const E* __restrict__ i
 template <typename E>
 __global__ void __launch_bounds__(256) concat_pair_kernel(const E* __restrict__ a, const E* __restrict__ b, E* __restrict__ out,
                                                           int64_t row0, int64_t row1, int64_t outer) {
+  TCR_PDL_ENTER();
   const int64_t row = row0 + row1, n = row * outer, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int64_t r = i % row, o = i / row;
@@ -154,6 +159,7 @@ __global__ void __launch_bounds__(256) concat_pair_kernel(const E* __restrict__ 
 template <typename E>
 __global__ void __launch_bounds__(256) concat_many_kernel(const __grid_constant__ ConcatArgs a, E* __restrict__ out,
                                                           int64_t inner, int64_t outer, int k0, int total) {
+  TCR_PDL_ENTER();
   const int64_t per = inner * outer, n = per * a.n, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     int64_t ii = i % inner, t = i / inner;

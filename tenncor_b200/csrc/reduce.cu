@@ -68,6 +68,7 @@ __device__ __forceinline__ T block_reduce(T v) {
 template <typename T, int OP>
 __global__ void __launch_bounds__(256) reduce_rows_block(const T* __restrict__ in, T* __restrict__ out, int64_t R,
                                                          int64_t chunk, int S, int64_t Kout) {
+  TCR_PDL_ENTER();
   const int s = blockIdx.x;
   // grid.y walks the kept rows (any count: 65536 rows of 4096 is a SURVEY §8d case)
   for (int64_t ko = blockIdx.y; ko < Kout; ko += gridDim.y) {
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256) reduce_rows_block(const T* __restrict__ i
 template <typename T, int OP>
 __global__ void __launch_bounds__(256) reduce_rows_warp(const T* __restrict__ in, T* __restrict__ out, int64_t R,
                                                         int64_t Kout) {
+  TCR_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const int64_t warps_per_grid = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t ko = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ko < Kout; ko += warps_per_grid) {
@@ -127,6 +129,7 @@ __global__ void __launch_bounds__(256) reduce_rows_warp(const T* __restrict__ in
 template <typename T, int OP>
 __global__ void __launch_bounds__(256) reduce_cols(const T* __restrict__ in, T* __restrict__ out, int64_t Kin,
                                                    int64_t R, int64_t chunk, int S) {
+  TCR_PDL_ENTER();
   __shared__ T tile[8][33];
   const int64_t ki = (int64_t)blockIdx.x * 32 + threadIdx.x;
   const int s = blockIdx.y;
@@ -165,6 +168,7 @@ struct GenericDesc {
 
 template <typename T, int OP>
 __global__ void __launch_bounds__(256) reduce_generic(const T* __restrict__ in, T* __restrict__ out, GenericDesc d) {
+  TCR_PDL_ENTER();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < d.n_out; o += stride) {
     int64_t base = 0, t = o;
@@ -326,6 +330,7 @@ __device__ __forceinline__ ValIdx<T> vi_warp(ValIdx<T> x) {
 // element(r) = in[ki + Kin*(r + R*ko)]. Kin == 1: one warp per row; else one thread per (ki, ko).
 template <typename T>
 __global__ void __launch_bounds__(256) argmax_warp(const T* __restrict__ in, T* __restrict__ out, int64_t R, int64_t Kout) {
+  TCR_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t ko = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ko < Kout; ko += wpg) {
@@ -340,6 +345,7 @@ __global__ void __launch_bounds__(256) argmax_warp(const T* __restrict__ in, T* 
 template <typename T>
 __global__ void __launch_bounds__(256) argmax_cols(const T* __restrict__ in, T* __restrict__ out, int64_t Kin, int64_t R,
                                                    int64_t Kout) {
+  TCR_PDL_ENTER();
   const int64_t total = Kin * Kout, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += stride) {
     int64_t ki = o % Kin, ko = o / Kin;
@@ -361,6 +367,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) argmax_cols_split(const T* __restrict__ in, const int64_t* __restrict__ pidx, T* __restrict__ out_val,
                                                          int64_t* __restrict__ out_idx, T* __restrict__ out_final, int64_t Kin, int64_t R,
                                                          int64_t chunk, int S) {
+  TCR_PDL_ENTER();
   __shared__ T sv[8][33];
   __shared__ int64_t si[8][33];
   const int64_t ki = (int64_t)blockIdx.x * 32 + threadIdx.x;
@@ -390,6 +397,7 @@ __global__ void __launch_bounds__(256) argmax_cols_split(const T* __restrict__ i
 // flat: pass 1 -> per-block (val, idx); pass 2 (single block) -> out
 template <typename T>
 __global__ void __launch_bounds__(256) argmax_flat1(const T* __restrict__ in, int64_t n, T* __restrict__ pv, int64_t* __restrict__ pi) {
+  TCR_PDL_ENTER();
   __shared__ T sv[8];
   __shared__ int64_t si[8];
   ValIdx<T> best{Lim<T>::lo(), INT64_MAX};
@@ -408,6 +416,7 @@ __global__ void __launch_bounds__(256) argmax_flat1(const T* __restrict__ in, in
 
 template <typename T>
 __global__ void __launch_bounds__(256) argmax_flat2(const T* __restrict__ pv, const int64_t* __restrict__ pi, int nparts, T* __restrict__ out) {
+  TCR_PDL_ENTER();
   __shared__ T sv[8];
   __shared__ int64_t si[8];
   ValIdx<T> best{Lim<T>::lo(), INT64_MAX};

@@ -41,6 +41,11 @@ int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
   return TCR_ERR_CUDA;
 }
 
+bool pdl_enabled() {
+  static const bool on = !(std::getenv("TCR_PDL") && std::atoi(std::getenv("TCR_PDL")) == 0);
+  return on;
+}
+
 // ---------------------------------------------------------------- ticket counters
 // Self-resetting per-tile arrival counters for kernels that finish a split reduction in their last
 // CTA. A launch takes a fresh range of a zero-initialised ring; ranges baked into captured graphs stay

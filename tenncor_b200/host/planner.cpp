@@ -1251,7 +1251,8 @@ struct Plan {
     {
       struct Key {
         int a; size_t off; int64_t m, n, k, a_sm, b_sk;
-        bool operator<(const Key& o) const { return std::tie(a, off, m, n, k, a_sm, b_sk) < std::tie(o.a, o.off, o.m, o.n, o.k, o.a_sm, o.b_sk); }
+        int b_version;  // products reading their weights before / after an in-place update belong to different launches
+        bool operator<(const Key& o) const { return std::tie(a, off, m, n, k, a_sm, b_sk, b_version) < std::tie(o.a, o.off, o.m, o.n, o.k, o.a_sm, o.b_sk, o.b_version); }
       };
       std::map<Key, std::vector<int>> buckets;
       for (int s = 0; s < ns; ++s) {
@@ -1262,7 +1263,10 @@ struct Plan {
         if (d.a_sk != 1 || d.b_sn != 1 || d.c_sn != 1 || d.c_sm != d.n) continue;         // A row-major, B [k x n], C row-major
         if (d.epilogue != TCR_EPI_NONE && d.epilogue != TCR_EPI_BIAS_N) continue;
         if ((d.a_sm % 4) || (d.b_sk % 4) || (v.a_off % 16) || (v.b_off % 16)) continue;
-        buckets[Key{v.a, v.a_off, d.m, d.n, d.k, d.a_sm, d.b_sk}].push_back(s);
+        int b_version = 0;
+        for (auto& r : acc[s].rd)
+          if (r.first == v.b) b_version = r.second;
+        buckets[Key{v.a, v.a_off, d.m, d.n, d.k, d.a_sm, d.b_sk, b_version}].push_back(s);
       }
       for (auto& kv : buckets) {
         std::vector<int>& all = kv.second;
@@ -1754,6 +1758,21 @@ struct Plan {
       order.push_back(i);
       for (int u : users[i])
         if (--indeg[u] == 0) ready.push(u);
+    }
+    if ((int)order.size() != nl && dbg) {
+      // walk unsorted predecessors until a step repeats
+      std::vector<int> seen(nl, 0);
+      int cur = -1;
+      for (int i = 0; i < nl; ++i)
+        if (indeg[i] > 0) { cur = i; break; }
+      for (int hop = 0; hop < 40 && cur >= 0; ++hop) {
+        fprintf(stderr, "  [%d] %s %s\n", (int)steps[live[cur]].pos, step_name(steps[live[cur]]).c_str(), nodes[steps[live[cur]].out_node].shape.to_string().c_str());
+        if (seen[cur]++) break;
+        int nxt = -1;
+        for (int d : deps[cur])
+          if (indeg[d] > 0) { nxt = d; break; }
+        cur = nxt;
+      }
     }
     if ((int)order.size() != nl) { if (dbg) fprintf(stderr, "fuse_recurrent_steps: cycle (%d of %d sorted), keeping the unfused plan\n", (int)order.size(), nl); restore(); return; }  // a merge closed a cycle: keep the unfused plan
     std::vector<Step> sorted;
