@@ -287,6 +287,10 @@ enum { TCR_GEMM_EXACT = 0, /* SIMT FMA in the element type (fp32/fp64/int32) */
        TCR_GEMM_3XTF32 = 2 /* tcgen05 kind::tf32, 3-pass split for fp32-grade accuracy */ };
 
 enum { TCR_EPI_NONE = 0, TCR_EPI_BIAS_N = 1 /* + bias[n] */, TCR_EPI_BIAS_M = 2 /* + bias[m] */ };
+/* post-operation on the product, applied last: the chain-rule factor the reference's SIGMOID / TANH gradient rules multiply onto the
+ * upstream gradient (tenncor/eteq/backprop.hpp:136-142: MUL(MUL(s, SUB(1, s)), sup), MUL(SUB(1, SQUARE(t)), sup)) when `sup` is this
+ * product. `aux` has the layout of C. Only products with k <= 16, unit column stride and n % 4 == 0 accept it (TCR_ERR_UNSUPPORTED else). */
+enum { TCR_POST_NONE = 0, TCR_POST_MUL_DSIGMOID = 1 /* c *= aux * (1 - aux) */, TCR_POST_MUL_DTANH = 2 /* c *= 1 - aux^2 */ };
 
 /* C[m,n] (+)= sum_k A(m,k) * B(k,n), fully strided operands:
  *   A(m,k) = a[m*a_sm + k*a_sk + batch*a_sb], likewise B(k,n), C(m,n).
@@ -306,7 +310,8 @@ typedef struct {
   int32_t activation;  /* 0 or TCR_EW_SIGMOID / TCR_EW_TANH applied after bias */
   const void* bias;
   int32_t accumulate;  /* C += (beta = 1) instead of C = */
-  int32_t _pad;
+  int32_t post_op;     /* TCR_POST_* */
+  const void* aux;     /* operand of post_op */
 } tcr_gemm_desc;
 
 int tcr_gemm(const void* a, const void* b, void* c, const tcr_gemm_desc* desc);

@@ -36,6 +36,7 @@ OP = {n: i for i, n in enumerate(OPCODES)}
 EW_MOV, EW_CONST = 64, 65
 GEMM_EXACT, GEMM_TF32, GEMM_3XTF32 = 0, 1, 2
 EPI_NONE, EPI_BIAS_N, EPI_BIAS_M = 0, 1, 2
+POST_NONE, POST_MUL_DSIGMOID, POST_MUL_DTANH = 0, 1, 2
 
 # every symbol include/tcr_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [
@@ -88,7 +89,7 @@ class GemmDesc(C.Structure):
                 ("c_sm", C.c_int64), ("c_sn", C.c_int64), ("c_sb", C.c_int64),
                 ("dtype", C.c_int32), ("precision", C.c_int32), ("epilogue", C.c_int32),
                 ("activation", C.c_int32), ("bias", C.c_void_p), ("accumulate", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("post_op", C.c_int32), ("aux", C.c_void_p)]
 
 
 class GemmGroupDesc(C.Structure):

@@ -174,6 +174,10 @@ int tcr_gemm(const void* a, const void* b, void* c, const tcr_gemm_desc* desc) {
     if (rc) return rc;
     if (handled) return TCR_OK;
   }
+  if (desc->post_op != TCR_POST_NONE) {
+    set_error("tcr_gemm: post_op is only implemented for products with k <= 16 (the small-K streaming kernel)");
+    return TCR_ERR_UNSUPPORTED;
+  }
   if (desc->precision != TCR_GEMM_EXACT) {
     TCR_ARG(desc->dtype == TCR_FLOAT, "tcr_gemm: tensor-core precisions are fp32 only");
     bool handled = false;

@@ -12,6 +12,8 @@
 //   small_k    K <= 16: every output is a short dot product         (4 outputs per thread)
 #include <cstdlib>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tcr {
@@ -237,6 +239,20 @@ __global__ void __launch_bounds__(256, (SP * sizeof(T) <= 48 ? 2 : 1)) skinny_rk
   const bool single = d.K <= kc;
   auto stage = [&](int64_t kb) {
     const int64_t kw = d.K - kb < kc ? d.K - kb : kc;
+    if (d.y_ss == 1 && d.y_sk == d.S) {
+      // the small operand is one contiguous [K][S] block (a dense layer's weights, S = its output width)
+      // a thread takes whole k rows: S consecutive elements each (independent loads, no division), written down the columns
+      const T* src = Y + kb * d.y_sk;
+      const int S = (int)d.S;
+      for (int k = threadIdx.x; k < kc; k += 256) {
+        T v[SP];
+#pragma unroll
+        for (int s2 = 0; s2 < SP; ++s2) v[s2] = (s2 < S && k < kw) ? src[(int64_t)k * S + s2] : T(0);
+#pragma unroll
+        for (int s2 = 0; s2 < SP; ++s2) ysm[s2 * kc + k] = v[s2];
+      }
+      return;
+    }
     // (no div/mod by the run-time chunk length: this loop runs SP*kc/256 times per thread)
 #pragma unroll 1
     for (int s = 0; s < SP; ++s) {
@@ -248,13 +264,18 @@ __global__ void __launch_bounds__(256, (SP * sizeof(T) <= 48 ? 2 : 1)) skinny_rk
     stage(0);
     __syncthreads();
   }
-  for (int64_t row_base = (int64_t)blockIdx.x * 32; row_base < d.L; row_base += (int64_t)gridDim.x * 32) {
+  // every block owns an equal share of the 32-row groups' worth of work in units of 4 rows (one warp pass): a grid of whole
+  // waves with 32-row blocks left 40 % of the SMs with half the work of the others
+  const int64_t quads = (d.L + RPW - 1) / RPW;
+  const int64_t q_begin = quads * blockIdx.x / gridDim.x, q_end = quads * (blockIdx.x + 1) / gridDim.x;
+  for (int64_t row_base = q_begin * RPW; row_base < q_end * RPW; row_base += 32) {
     T acc[RPW][SP];
 #pragma unroll
     for (int r = 0; r < RPW; ++r)
 #pragma unroll
       for (int s = 0; s < SP; ++s) acc[r][s] = T(0);
     const int64_t l0 = row_base + warp * RPW;
+    const int64_t l_end = q_end * RPW < d.L ? q_end * RPW : d.L;  // rows past the block's share belong to the next block
     for (int64_t kb = 0; kb < d.K; kb += kc) {
       if (!single) {
         __syncthreads();
@@ -268,7 +289,7 @@ __global__ void __launch_bounds__(256, (SP * sizeof(T) <= 48 ? 2 : 1)) skinny_rk
         SkVec<T> x[RPW];
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
-          if (k < kw && l0 + r < d.L) x[r] = *reinterpret_cast<const SkVec<T>*>(X + (l0 + r) * d.x_sl + kb + k);
+          if (k < kw && l0 + r < l_end) x[r] = *reinterpret_cast<const SkVec<T>*>(X + (l0 + r) * d.x_sl + kb + k);
           else
 #pragma unroll
             for (int e = 0; e < V; ++e) x[r].v[e] = T(0);
@@ -290,10 +311,138 @@ __global__ void __launch_bounds__(256, (SP * sizeof(T) <= 48 ? 2 : 1)) skinny_rk
         T v = acc[r][s];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += sk_shfl_down(v, o);
-        if (lane == 0 && l0 + r < d.L && s < d.S) sk_store<T>(d, C, l0 + r, s, v);
+        if (lane == 0 && l0 + r < l_end && s < d.S) sk_store<T>(d, C, l0 + r, s, v);
       }
     }
   }
+}
+
+// fp32, X K-major with 16-byte aligned rows, K % 4 == 0 and the whole small operand in shared memory (SP * K * 4 <= 96 KB).
+// ncu on the 8192 x 10 x 1024 output layer (profiles/r2_ncu_skinny.md) showed skinny_rk2 latency-bound, not bandwidth-bound:
+// 33.5 MB in 28 us, 1.2-1.5 IPC at 21 % occupancy, every warp walking the same sequence of dependent phases (stage the small
+// operand -> barrier -> four rounds of load 4 rows / wait / FMA -> shuffle -> store) with ~one 4-row group per warp, so no
+// phase overlapped another. Here a warp owns TWO rows and issues all of their loads (up to 8 k-steps = 16 x 16 bytes per
+// lane) BEFORE the block stages the small operand and synchronises: one exposed memory latency instead of five.
+template <int SP>
+__global__ void __launch_bounds__(256, 2) skinny_rk3_kernel(const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ C,
+                                                            int kc, const __grid_constant__ SkinnyDesc d) {
+  TCR_PDL_ENTER();
+  constexpr int RPW = 2, PF = 8;  // rows per warp pass, k-steps prefetched per row
+  extern __shared__ __align__(16) unsigned char sk_smem[];
+  float* ysm = reinterpret_cast<float*>(sk_smem);  // [SP][kc], zero padded in s and k
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K = (int)d.K, S = (int)d.S;
+  const int steps = (K + 127) / 128;  // lanes beyond K in the last step read zeros from ysm: clamp their x address instead of predicating
+  const int64_t pairs = (d.L + RPW - 1) / RPW;
+  const int64_t p_begin = pairs * blockIdx.x / gridDim.x, p_end = pairs * (blockIdx.x + 1) / gridDim.x;
+  bool staged = false;
+  for (int64_t pr = p_begin + warp; pr < p_end || !staged; pr += 8) {
+    const bool active = pr < p_end;
+    const float* xr[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      int64_t row = pr * RPW + r;
+      if (row > d.L - 1) row = d.L - 1;  // clamped: computed twice, stored once
+      xr[r] = X + row * d.x_sl;
+    }
+    float acc[RPW][SP];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int s2 = 0; s2 < SP; ++s2) acc[r][s2] = 0.f;
+    for (int k0 = 0; k0 < steps; k0 += PF) {
+      float4 x[PF][RPW];
+      if (active) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+          int koff = (k0 + u) * 128 + lane * 4;
+          if (koff > K - 4) koff = K - 4;  // past the end (last ragged step or u beyond `steps`): any valid address, multiplied by zeros
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) x[u][r] = __ldg(reinterpret_cast<const float4*>(xr[r] + koff));
+        }
+      }
+      if (!staged) {  // first pass: the small operand is staged while the big operand's loads are in flight
+        if (d.y_ss == 1 && d.y_sk == d.S) {  // contiguous [K][S] weights: whole rows per thread, independent loads
+          for (int k = threadIdx.x; k < kc; k += 256) {
+            float v[SP];
+#pragma unroll
+            for (int s2 = 0; s2 < SP; ++s2) v[s2] = (s2 < S && k < K) ? Y[(int64_t)k * S + s2] : 0.f;
+#pragma unroll
+            for (int s2 = 0; s2 < SP; ++s2) ysm[s2 * kc + k] = v[s2];
+          }
+        } else {
+          for (int e = threadIdx.x; e < SP * kc; e += 256) {
+            const int s2 = e / kc, k = e - s2 * kc;
+            ysm[e] = (s2 < S && k < K) ? Y[s2 * d.y_ss + k * d.y_sk] : 0.f;
+          }
+        }
+        __syncthreads();
+        staged = true;
+      }
+      if (active) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+          if (k0 + u < steps) {
+            const float* yp = ysm + (k0 + u) * 128 + lane * 4;  // zero beyond K
+#pragma unroll
+            for (int s2 = 0; s2 < SP; ++s2) {
+              const float4 y = *reinterpret_cast<const float4*>(yp + s2 * kc);
+#pragma unroll
+              for (int r = 0; r < RPW; ++r) {
+                float a = acc[r][s2];
+                a = fmaf(x[u][r].x, y.x, a);
+                a = fmaf(x[u][r].y, y.y, a);
+                a = fmaf(x[u][r].z, y.z, a);
+                a = fmaf(x[u][r].w, y.w, a);
+                acc[r][s2] = a;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (!active) continue;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+#pragma unroll
+      for (int s2 = 0; s2 < SP; ++s2) {
+        float v = acc[r][s2];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[r][s2] = v;
+      }
+    }
+    // every lane holds every sum: lane (r * SP + s2) stores element (row r, column s2)
+    float mine = 0.f;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int s2 = 0; s2 < SP; ++s2)
+        if (lane == r * SP + s2) mine = acc[r][s2];
+    if (lane < RPW * SP) {
+      const int r = lane / SP, s2 = lane % SP;
+      const int64_t row = pr * RPW + r;
+      if (row < d.L && s2 < S) sk_store<float>(d, C, row, s2, mine);
+    }
+  }
+}
+
+template <int SP>
+static int launch_rk3(const float* X, const float* Y, float* C, const SkinnyDesc& d) {
+  const int kc = (int)(ceil_div(d.K, 128) * 128);
+  const size_t smem = (size_t)SP * kc * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    TCR_CUDA(cudaFuncSetAttribute(skinny_rk3_kernel<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  const int64_t pairs = ceil_div(d.L, 2);
+  int64_t want = pairs / 8 < 1 ? 1 : pairs / 8;  // at least one pass of the 8 warps per block
+  const int64_t cap = (int64_t)state().sm_count * 2;
+  const int grid = (int)(want < cap ? want : cap);
+  TCR_LAUNCH((skinny_rk3_kernel<SP>), grid, 256, smem, X, Y, C, kc, d);
+  TCR_CHECK_LAUNCH();
+  return TCR_OK;
 }
 
 // X L-major (x_sl == 1), 16-byte aligned rows of L, L % V == 0: a thread owns V consecutive l,
@@ -402,6 +551,79 @@ __global__ void __launch_bounds__(256) small_k2_kernel(const T* __restrict__ A, 
 }
 
 
+// K <= 16, wide output with unit column stride, fp32: a thread owns FOUR consecutive columns (B(:, n..n+3) in registers) and
+// walks 32 rows staged in shared memory; every store is 16 bytes (the 4-byte-store form above issues four times the
+// instructions per byte and reached 2.2 TB/s writing the 33.5 MB input gradient of the 1024 -> 10 layer). Optional post-op:
+// multiply by the activation's derivative read from `aux` — the dX product of a dense layer and the SIGMOID / TANH gradient
+// rule behind it in ONE pass over memory instead of write + read + read + write.
+template <int KP>
+__global__ void __launch_bounds__(256) small_k4_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                                       const __grid_constant__ tcr_gemm_desc d) {
+  TCR_PDL_ENTER();
+  constexpr int RB = 32;
+  __shared__ __align__(16) float a_sm[RB * KP];
+  const int64_t n = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  const bool n_ok = n < d.n;  // n % 4 == 0: all four columns or none
+  const float* bias = (const float*)d.bias;
+  const float* aux = (const float*)d.aux;
+  float b[KP][4];
+#pragma unroll
+  for (int k = 0; k < KP; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) b[k][e] = (n_ok && k < d.k) ? B[k * d.b_sk + (n + e) * d.b_sn] : 0.f;
+  float bn[4] = {0.f, 0.f, 0.f, 0.f};
+  if (n_ok && d.epilogue == TCR_EPI_BIAS_N)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bn[e] = bias[n + e];
+  for (int64_t m0 = (int64_t)blockIdx.y * RB; m0 < d.m; m0 += (int64_t)gridDim.y * RB) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < RB * KP; e += 256) {
+      const int mm = e / KP, k = e % KP;
+      a_sm[e] = (m0 + mm < d.m && k < d.k) ? A[(m0 + mm) * d.a_sm + k * d.a_sk] : 0.f;
+    }
+    __syncthreads();
+    if (!n_ok) continue;
+    const int rows = d.m - m0 < RB ? (int)(d.m - m0) : RB;
+    for (int mb = 0; mb < rows; mb += 8) {
+    float4 xs[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)  // eight 16-byte loads in flight per thread before any arithmetic
+      xs[u] = (d.post_op && mb + u < rows) ? __ldg(reinterpret_cast<const float4*>(aux + (m0 + mb + u) * d.c_sm + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int mm = mb + u;
+      if (mm >= rows) break;
+      const int64_t m = m0 + mm;
+      const float4 x = xs[u];
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < KP; k += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(a_sm + mm * KP + k);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] += a.x * b[k][e] + a.y * b[k + 1][e] + a.z * b[k + 2][e] + a.w * b[k + 3][e];
+      }
+      float* dst = C + m * d.c_sm + n;
+      if (d.accumulate) {
+        const float4 o = *reinterpret_cast<const float4*>(dst);
+        v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+      }
+      const float bm = d.epilogue == TCR_EPI_BIAS_M ? bias[m] : 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[e] += bn[e] + bm;
+        if (d.activation) v[e] = sk_act<float>(d.activation, v[e]);
+      }
+      if (d.post_op == TCR_POST_MUL_DSIGMOID) {
+        v[0] *= x.x * (1.f - x.x); v[1] *= x.y * (1.f - x.y); v[2] *= x.z * (1.f - x.z); v[3] *= x.w * (1.f - x.w);
+      } else if (d.post_op == TCR_POST_MUL_DTANH) {
+        v[0] *= 1.f - x.x * x.x; v[1] *= 1.f - x.y * x.y; v[2] *= 1.f - x.z * x.z; v[3] *= 1.f - x.w * x.w;
+      }
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    }
+  }
+}
+
 // K <= 16 and a narrow output (n <= 16, e.g. the 10-9-9 DQN layers at replay batch 4096): a thread
 // owns one row m; B (k x n) sits in shared memory and is read by broadcast
 template <typename T, int KP>
@@ -448,7 +670,12 @@ static int launch_rk2(const T* X, const T* Y, T* C, const SkinnyDesc& d) {
     TCR_CUDA(cudaFuncSetAttribute(skinny_rk2_kernel<T, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured = true;
   }
-  int grid = wave_grid(d.L, 32, 2);
+  // two blocks per SM, each with an equal share of the 4-row groups (a block stages the small operand once, so few large
+  // blocks; at least four row groups each so that the staging is amortised)
+  const int64_t quads = ceil_div(d.L, 4);
+  int64_t want = quads / 4 < 1 ? 1 : quads / 4;
+  const int64_t cap = (int64_t)state().sm_count * 2;
+  int grid = (int)(want < cap ? want : cap);
   TCR_LAUNCH((skinny_rk2_kernel<T, SP>), grid, 256, smem, X, Y, C, (int)kc, d);
   TCR_CHECK_LAUNCH();
   return TCR_OK;
@@ -502,6 +729,14 @@ static int run_skinny(const T* X, const T* Y, T* C, const SkinnyDesc& d) {
   static const int vec = std::getenv("TCR_SKINNY_VEC") ? std::atoi(std::getenv("TCR_SKINNY_VEC")) : 1;
   if (vec && d.x_sk == 1 && d.K >= 64 && (d.K % V) == 0 && aligned16<T>(X, d.x_sl)) {
     int rc = TCR_OK;
+    if constexpr (std::is_same<T, float>::value) {
+      static const int lean = std::getenv("TCR_SKINNY_RK3") ? std::atoi(std::getenv("TCR_SKINNY_RK3")) : 1;
+      const int64_t sp = d.S <= 4 ? 4 : d.S <= 8 ? 8 : d.S <= 12 ? 12 : 16;
+      if (lean && sp * ceil_div(d.K, 128) * 128 * 4 <= 96 * 1024 && d.K < (1 << 24)) {
+        TCR_SK_SP(d.S, rc = (launch_rk3<SP>(X, Y, C, d)));
+        return rc;
+      }
+    }
     TCR_SK_SP(d.S, rc = (launch_rk2<T, SP>(X, Y, C, d)));
     return rc;
   }
@@ -551,7 +786,23 @@ int gemm_skinny_dispatch(const void* a, const void* b, void* c, const tcr_gemm_d
     if (gy > 4096) gy = 4096;
     dim3 grid((unsigned)ceil_div(d->n, 256), (unsigned)gy);
     static const int vec = std::getenv("TCR_SKINNY_VEC") ? std::atoi(std::getenv("TCR_SKINNY_VEC")) : 1;
-    if (vec && d->n <= SK_MAX && d->m >= 256) {
+    const bool k4 = d->dtype == TCR_FLOAT && d->c_sn == 1 && (d->n % 4) == 0 && (d->c_sm % 4) == 0 && d->n >= 64 && ((((uintptr_t)c) & 15) == 0) &&
+                    (!d->post_op || ((((uintptr_t)d->aux) & 15) == 0));
+    if (d->post_op && !k4) {
+      set_error("tcr_gemm: post_op needs an fp32 product with k <= 16, unit column stride, n %% 4 == 0 and 16-byte aligned C / aux");
+      return TCR_ERR_UNSUPPORTED;
+    }
+    if (vec && k4) {
+      int64_t gy4 = ceil_div(d->m, 32);
+      if (gy4 > 65535) gy4 = 65535;
+      dim3 grid4((unsigned)ceil_div(d->n, 1024), (unsigned)gy4);
+      const float *fa = (const float*)a, *fb = (const float*)b;
+      float* fc = (float*)c;
+      if (d->k <= 4) TCR_LAUNCH((small_k4_kernel<4>), grid4, 256, 0, fa, fb, fc, *d);
+      else if (d->k <= 8) TCR_LAUNCH((small_k4_kernel<8>), grid4, 256, 0, fa, fb, fc, *d);
+      else if (d->k <= 12) TCR_LAUNCH((small_k4_kernel<12>), grid4, 256, 0, fa, fb, fc, *d);
+      else TCR_LAUNCH((small_k4_kernel<16>), grid4, 256, 0, fa, fb, fc, *d);
+    } else if (vec && d->n <= SK_MAX && d->m >= 256) {
       int g1 = wave_grid(d->m, 256, 4);
       TCR_DISPATCH_COMPUTE(d->dtype, T, {
         if (d->k <= 4) TCR_LAUNCH((small_kn_kernel<T, 4>), g1, 256, 0, (const T*)a, (const T*)b, (T*)c, *d);

@@ -42,7 +42,9 @@ int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 bool pdl_enabled() {
-  static const bool on = !(std::getenv("TCR_PDL") && std::atoi(std::getenv("TCR_PDL")) == 0);
+  // opt-in (TCR_PDL=1): measured gain is ~1 us per dependent launch in a captured chain (C4: 8.91 -> 8.83 ms per step), and
+  // Nsight Compute 2025.2 crashes the application (SIGSEGV) when kernels carry the programmatic-serialization attribute
+  static const bool on = std::getenv("TCR_PDL") && std::atoi(std::getenv("TCR_PDL")) != 0;
   return on;
 }
 

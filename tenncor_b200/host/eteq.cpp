@@ -456,6 +456,7 @@ void typed_exec(egen::_GENERATED_OPCODE opcode, egen::_GENERATED_DTYPE dtype, ei
       break;
     case MATMUL: {
       tcr_gemm_desc d;
+      std::memset(&d, 0, sizeof(d));
       matmul_as_gemm(in[0]->shape(), in[1]->shape(), d);
       d.dtype = dtype;
       op([=](void* o, const std::vector<const void*>& a) {
@@ -469,6 +470,7 @@ void typed_exec(egen::_GENERATED_OPCODE opcode, egen::_GENERATED_DTYPE dtype, ei
       auto pairs = eigen::unpack_rankpairs(attrib);
       Shape ashape = in[0]->shape(), bshape = in[1]->shape();
       tcr_gemm_desc d;
+      std::memset(&d, 0, sizeof(d));
       if (contract_as_gemm(ashape, bshape, pairs, d)) {
         d.dtype = dtype;
         op([=](void* o, const std::vector<const void*>& a) {

@@ -121,6 +121,7 @@ struct Step {
   int64_t red_shape[8] = {1, 1, 1, 1, 1, 1, 1, 1};
   int64_t pos = 0;  // ordering key of the stable topological re-sort
   bool dead = false;
+  int gemm_aux_slot = -1;  // index into `in` of the operand of the product's post-op (activation derivative)
 };
 
 // One recognised conv2d composite (cfg/tenncor/nn.yml:48-98) or its kernel gradient
@@ -1201,7 +1202,7 @@ struct Plan {
   void fuse_recurrent_steps() {
     if (std::getenv("TCR_NO_RNN_FUSE") || precision == TCR_GEMM_EXACT) return;
     const int ns = (int)steps.size();
-    if (ns < 4) return;
+    if (ns < 3) return;
     const std::vector<Step> original = steps;
     std::vector<int> original_step_of(nodes.size());
     for (size_t i = 0; i < nodes.size(); ++i) original_step_of[i] = nodes[i].step;
@@ -1246,6 +1247,57 @@ struct Plan {
     };
     auto plain_f32 = [&](int node) { return nodes[node].dtype == FLOAT; };
     int n_fused = 0;
+
+    // ================= (0) activation-derivative factor folded into the product that feeds it =================
+    // backprop.hpp:136-142: d SIGMOID = MUL(MUL(s, SUB(1, s)), sup), d TANH = MUL(SUB(1, SQUARE(t)), sup). When `sup` is a small-K
+    // product (the input gradient of a narrow dense layer: K = its output width) the factor is applied while the product is
+    // written: one pass over the [batch x hidden] gradient instead of write, read twice, write.
+    for (int s = 0; s < ns; ++s) {
+      Step& e = steps[s];
+      if (e.dead || !e.ew || e.kind != Step::NORMAL || e.prog.n_outputs != 1 || e.prog.n_inputs != 2) continue;
+      const int n0 = e.out_node;
+      const PNode& o = nodes[n0];
+      auto mem = members.find(n0);
+      if (o.op != MUL || o.args.size() != 2 || o.dtype != FLOAT || is_assign(o.op) || mem == members.end() || mem->second.size() != 3) continue;
+      const PNode& loc = nodes[nodes[o.args[0]].root];
+      const PNode& sup = nodes[o.args[1]];
+      if (!loc.func || !loc.inlined || loc.region != n0 || sup.offset != 0 || nodes[sup.root].n != o.n) continue;
+      int post = 0, aux = -1;
+      auto is_one = [&](int a) { return nodes[a].has_scalar && nodes[a].scalar == 1.0; };
+      auto plain = [&](int a) { const PNode& x = nodes[a]; return (!x.has_scalar && x.offset == 0 && x.n == o.n && x.dtype == FLOAT && !x.is_extend) ? x.root : -1; };
+      if (loc.op == MUL && loc.args.size() == 2) {  // s * (1 - s)
+        const int sv = plain(loc.args[0]);
+        const PNode& sb = nodes[nodes[loc.args[1]].root];
+        if (sv >= 0 && sb.func && sb.op == SUB && sb.inlined && sb.region == n0 && sb.args.size() == 2 && is_one(sb.args[0]) && plain(sb.args[1]) == sv) { post = TCR_POST_MUL_DSIGMOID; aux = sv; }
+      } else if (loc.op == SUB && loc.args.size() == 2 && is_one(loc.args[0])) {  // 1 - t^2
+        const PNode& sq = nodes[nodes[loc.args[1]].root];
+        if (sq.func && sq.op == SQUARE && sq.inlined && sq.region == n0 && sq.args.size() == 1) {
+          const int tv = plain(sq.args[0]);
+          if (tv >= 0) { post = TCR_POST_MUL_DTANH; aux = tv; }
+        }
+      }
+      if (!post) continue;
+      const int ps = producer(sup.root);
+      if (ps < 0 || nodes[sup.root].exposed || live_readers(sup.root).size() != 1) continue;
+      GemmView v = gemm_view(steps[ps]);
+      if (!v.ok || v.d.k > 16 || v.d.c_sn != 1 || v.d.c_sm != v.d.n || (v.d.n % 4) || v.d.n < 64 || v.d.m * v.d.n != o.n || v.d.post_op) continue;
+      if (v.d.m * v.d.n < 4096) continue;
+      Step g = steps[ps];
+      g.gemm_fused = true;
+      g.holder = nullptr;
+      g.gemm = v.d;
+      g.gemm.post_op = post;
+      g.gemm_aux_slot = (int)g.in_nodes.size();
+      g.in_nodes.push_back(aux);
+      g.in_offsets.push_back(0);
+      g.out_node = n0;
+      g.pos = e.pos;
+      merge_acc(s, ps);
+      drop_node(s, sup.root);
+      steps[ps].dead = true;
+      steps[s] = std::move(g);
+      ++n_fused;
+    }
 
     // ================= (1) sibling products sharing their A operand -> grouped launch =================
     {
@@ -2089,7 +2141,8 @@ struct Plan {
     } else if (st.gemm_fused) {
       tcr_gemm_desc d = st.gemm;
       d.precision = d.dtype == FLOAT ? gemm_precision() : TCR_GEMM_EXACT;
-      d.bias = st.in.size() > 2 ? st.in[2] : nullptr;
+      d.bias = (d.epilogue != TCR_EPI_NONE && st.in.size() > 2) ? st.in[2] : nullptr;
+      d.aux = st.gemm_aux_slot >= 0 ? st.in[st.gemm_aux_slot] : nullptr;
       check(tcr_gemm(st.in[0], st.in[1], st.out, &d), "tcr_gemm");
     } else st.holder->launch_with(st.out, st.in);
   }
@@ -2280,6 +2333,7 @@ struct Plan {
     const std::string mnk = " m" + std::to_string(st.gemm.m) + " n" + std::to_string(st.gemm.n) + " k" + std::to_string(st.gemm.k);
     if (st.conv_fused)
       return st.conv_dimg ? "CONV2D-dX GEMM+col2im" + mnk : std::string(st.conv_grad ? "CONV2D-dK" : "CONV2D") + " im2col+GEMM" + (st.gemm.epilogue ? "+bias" : "") + (st.gemm.activation ? "+act" : "") + mnk;
+    if (st.gemm_fused && st.gemm.post_op) return std::string("GEMM*") + (st.gemm.post_op == TCR_POST_MUL_DSIGMOID ? "dsigmoid" : "dtanh") + mnk;
     if (st.gemm_fused && st.in_nodes.size() == 2) return "GEMM^T" + mnk;
     if (st.gemm_fused) return "GEMM+bias" + std::string(st.gemm.activation ? "+act" : "") + mnk;
     return what;
