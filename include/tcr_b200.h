@@ -397,8 +397,16 @@ int tcr_comm_init(int rank, int nranks, const char id[TCR_COMM_ID_BYTES]);
 int tcr_comm_destroy(void);
 int tcr_comm_rank(void);
 int tcr_comm_size(void); /* 1 when no communicator */
-/* in-place SUM all-reduce followed by `scale` (1/nranks for mean-type losses) */
+/* in-place SUM all-reduce followed by `scale` (1/nranks for mean-type losses). FLOAT buffers inside the symmetric region
+ * (tcr_comm_symm_alloc) are exchanged by ONE kernel over NVLink peer memory (allreduce_p2p.cu: every rank maps every peer's
+ * region through CUDA IPC; one-shot below 512 KB, reduce-scatter + all-gather above; rank-order sums, bit-identical on all
+ * ranks); everything else goes through ncclAllReduce. */
 int tcr_allreduce_sum(void* buf, int64_t n, int dtype, double scale);
+/* Symmetric region: memory every peer can address. Ranks must allocate the same sizes in the same order (the planner does: all
+ * ranks build the same plan). TCR_ERR_UNSUPPORTED when no peer path exists or the region is full: use tcr_alloc + NCCL then. */
+int tcr_comm_symm_alloc(void** out, size_t bytes);
+int tcr_comm_symm_reset(void); /* forget every symmetric allocation (call on all ranks together, with no plan alive) */
+int tcr_comm_p2p_ready(void);  /* 1 when the peer-memory path is active */
 
 #ifdef __cplusplus
 }

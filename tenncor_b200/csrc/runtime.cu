@@ -545,6 +545,7 @@ typedef int (*fn_get_uid)(nccl_uid*);
 typedef int (*fn_comm_init)(nccl_comm*, int, nccl_uid, int);
 typedef int (*fn_comm_destroy)(nccl_comm);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, nccl_comm, cudaStream_t);
 typedef const char* (*fn_errstr)(int);
 
 static struct {
@@ -553,6 +554,7 @@ static struct {
   fn_comm_init comm_init = nullptr;
   fn_comm_destroy comm_destroy = nullptr;
   fn_allreduce allreduce = nullptr;
+  fn_allgather allgather = nullptr;
   fn_errstr errstr = nullptr;
   nccl_comm comm = nullptr;
   int rank = 0, size = 1;
@@ -573,6 +575,7 @@ static int nccl_load() {
   g_nccl.comm_init = (fn_comm_init)dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.comm_destroy = (fn_comm_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.allgather = (fn_allgather)dlsym(g_nccl.lib, "ncclAllGather");
   g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
   if (!g_nccl.get_uid || !g_nccl.comm_init || !g_nccl.comm_destroy || !g_nccl.allreduce) {
     set_error("NCCL: missing symbols in libnccl");
@@ -585,6 +588,33 @@ static int nccl_fail(int rc, const char* what) {
   set_error("NCCL error %d (%s) in %s", rc, g_nccl.errstr ? g_nccl.errstr(rc) : "?", what);
   return TCR_ERR_NCCL;
 }
+
+}  // extern "C" (reopened below)
+
+namespace tcr {
+int p2p_setup(int rank, int nranks);  // allreduce_p2p.cu
+void p2p_teardown();
+bool p2p_allreduce(void* buf, int64_t n, int dtype, double scale, int* rc);
+
+// set-up helper: every rank contributes `bytes`, everybody receives all of them in rank order (host buffers)
+int nccl_allgather_bytes(const void* mine, void* all, size_t bytes) {
+  if (!g_nccl.comm || !g_nccl.allgather) { set_error("NCCL all-gather unavailable"); return TCR_ERR_NCCL; }
+  const size_t n = (size_t)g_nccl.size;
+  char *dsend = nullptr, *drecv = nullptr;
+  TCR_CUDA(cudaMalloc(&dsend, bytes));
+  TCR_CUDA(cudaMalloc(&drecv, bytes * n));
+  TCR_CUDA(cudaMemcpy(dsend, mine, bytes, cudaMemcpyHostToDevice));
+  int e = g_nccl.allgather(dsend, drecv, bytes, /*ncclInt8*/ 0, g_nccl.comm, state().stream);
+  if (e) { cudaFree(dsend); cudaFree(drecv); return nccl_fail(e, "ncclAllGather"); }
+  TCR_CUDA(cudaStreamSynchronize(state().stream));
+  TCR_CUDA(cudaMemcpy(all, drecv, bytes * n, cudaMemcpyDeviceToHost));
+  cudaFree(dsend);
+  cudaFree(drecv);
+  return TCR_OK;
+}
+}  // namespace tcr
+
+extern "C" {
 
 int tcr_comm_unique_id(char id[TCR_COMM_ID_BYTES]) {
   int rc = nccl_load();
@@ -609,12 +639,13 @@ int tcr_comm_init(int rank, int nranks, const char id[TCR_COMM_ID_BYTES]) {
   if (e) return nccl_fail(e, "ncclCommInitRank");
   g_nccl.rank = rank;
   g_nccl.size = nranks;
-  return TCR_OK;
+  return p2p_setup(rank, nranks);  // peer-memory exchange path (allreduce_p2p.cu); NCCL remains the fallback
 }
 
 int tcr_comm_destroy(void) {
   if (g_nccl.comm) {
     if (state().stream) cudaStreamSynchronize(state().stream);
+    p2p_teardown();
     g_nccl.comm_destroy(g_nccl.comm);
     g_nccl.comm = nullptr;
   }
@@ -632,6 +663,8 @@ int tcr_allreduce_sum(void* buf, int64_t n, int dtype, double scale) {
   TCR_REQUIRE_DEVICE();
   if (n <= 0) return TCR_OK;
   if (g_nccl.comm != nullptr && g_nccl.size > 1) {
+    int prc = TCR_OK;
+    if (p2p_allreduce(buf, n, dtype, scale, &prc)) return prc;  // NVLink peer-memory kernel, scale included
     int nccl_type;
     switch (dtype) {  // ncclDataType_t
       case TCR_FLOAT: nccl_type = 7; break;

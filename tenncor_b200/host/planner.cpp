@@ -1979,7 +1979,10 @@ struct Plan {
     for (auto& n : nodes)
       if (n.alias_stack >= 0) n.ptr = stacks[n.alias_stack].base;
     if (bucket_bytes > 0) {
-      bucket = alloc_owned(bucket_bytes);
+      // inside the symmetric region when there is a peer path: the exchange is then one kernel over NVLink peer memory
+      void* symm = nullptr;
+      if (tcr_comm_symm_alloc(&symm, bucket_bytes) == TCR_OK && symm != nullptr) bucket = symm;
+      else bucket = alloc_owned(bucket_bytes);
       check(tcr_memset(bucket, 0, bucket_bytes), "tcr_memset");  // the 16-byte padding between slots stays zero
       // a gradient read only by its exchange is produced straight into its slot
       for (size_t s = 0; s < steps.size(); ++s) {

@@ -35,7 +35,7 @@ def test_struct_layouts_match_header(built):
     assert C.sizeof(cabi.EwOutput) == 16
     assert C.sizeof(cabi.EwProgram) == 16 + 24 + 8 * 16 + 4 * 16 + 32 * 16
     assert C.sizeof(cabi.MapDesc) == 8 * 8 * 5 + 8 * 4
-    assert C.sizeof(cabi.GemmDesc) == 13 * 8 + 4 * 4 + 8 + 8
+    assert C.sizeof(cabi.GemmDesc) == 13 * 8 + 4 * 4 + 8 + 8 + 8  # + post_op (in the old pad) + aux pointer
 
 
 def test_no_cpu_fallback_without_device(built):
