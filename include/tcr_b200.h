@@ -208,6 +208,11 @@ typedef struct {
 } tcr_ew_program;
 
 int tcr_elementwise(const tcr_ew_program* prog);
+/* Map-reduce form: output 0 of the program is not stored but SUMMED over all elements into out[0] (element of the compute type,
+ * FLOAT / DOUBLE), then post_op is applied: 0 none, 1 out /= post_imm, 2 out *= post_imm. One launch replaces the reference's
+ * elementwise chain + REDUCE_SUM over every rank + scalar DIV of a loss (cfg/tenncor/loss.yml:21-39 -> core.yml:1090-1096:
+ * SUB, SQUARE, REDUCE_SUM, DIV by a constant element count). Deterministic: block partials in block order. */
+int tcr_elementwise_reduce(const tcr_ew_program* prog, void* out, int post_op, double post_imm);
 
 /* Convenience single-op forms (same kernels, program of length 1). */
 int tcr_unary(int opcode, const void* in, void* out, int64_t n, int dtype);

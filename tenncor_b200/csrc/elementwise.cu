@@ -274,6 +274,12 @@ struct VmParams {
   VmInput in[TCR_EW_MAX_INPUTS];
   tcr_ew_output out[TCR_EW_MAX_OUTPUTS];
   tcr_ew_instr ins[TCR_EW_MAX_INSTRS];
+  // map-reduce form (tcr_elementwise_reduce): output 0 is not stored but summed over all elements
+  void* red_out;       // one element of the compute type
+  void* red_partial;   // gridDim.x elements
+  int* red_counter;    // ticket, zero between launches (self-resetting)
+  int32_t red_post;    // 0 none, 1 divide by red_imm, 2 multiply by red_imm
+  double red_imm;
 };
 
 template <typename T>
@@ -318,11 +324,15 @@ template <typename T> struct VmCfg { static constexpr int THREADS = sizeof(T) ==
 // operand fetch is an LDS.128 with a computed address instead of a branch tree over
 // hardware registers, which keeps the kernel at ~40 registers (full occupancy) and makes
 // the cost of a VM instruction two shared loads, one uniform opcode branch and one store.
-template <typename T, bool ALIGNED, typename I>
+template <typename T> __device__ __forceinline__ T shfl_down_any(T v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
+template <> __device__ __forceinline__ int64_t shfl_down_any(int64_t v, int o) { return (int64_t)__shfl_down_sync(0xffffffffu, (long long)v, o); }
+
+template <typename T, bool ALIGNED, typename I, bool RED = false>
 __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_constant__ VmParams p) {
   TCR_PDL_ENTER();
   constexpr int THREADS = VmCfg<T>::THREADS;
   __shared__ V4<T> regs[TCR_EW_NREGS][THREADS];
+  T red_acc = T(0);  // RED: this thread's share of the sum of output 0
   const I n = (I)p.n;
   const I nchunks = (n + VM_V - 1) / VM_V;
   const I stride = (I)gridDim.x * THREADS;
@@ -415,7 +425,13 @@ __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_c
       regs[ins.dst][threadIdx.x] = d;
     }
     // ---- store outputs
-    for (int k = 0; k < p.n_outputs; ++k) {
+    if (RED) {
+      const V4<T> y = regs[p.out[0].reg][threadIdx.x];
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v)
+        if (base + v < n) red_acc += y.v[v];
+    }
+    for (int k = RED ? 1 : 0; k < p.n_outputs; ++k) {
       const tcr_ew_output& o = p.out[k];
       V4<T> y = regs[o.reg][threadIdx.x];
       if (ALIGNED && full && o.dtype == DTypeOf<T>::value) {
@@ -426,6 +442,39 @@ __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_c
 #pragma unroll
         for (int v = 0; v < VM_V; ++v)
           if (base + v < n) store_any<T>(o.ptr, o.dtype, base + v, y.v[v]);
+      }
+    }
+  }
+  if (RED) {
+    // block sum in a fixed order (shuffle tree, then warp order), one partial per block; the last block to arrive adds the
+    // partials in block order and applies the post-op: deterministic for a given grid, one launch
+    __shared__ T warp_sum[THREADS / 32];
+    __shared__ int last_block;
+    T v = red_acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += shfl_down_any<T>(v, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      T b = T(0);
+      for (int w = 0; w < THREADS / 32; ++w) b += warp_sum[w];
+      ((T*)p.red_partial)[blockIdx.x] = b;
+      __threadfence();
+      const int ticket = atomicAdd(p.red_counter, 1);
+      last_block = ticket == (int)gridDim.x - 1;
+      if (last_block) *p.red_counter = 0;
+    }
+    __syncthreads();
+    if (last_block && threadIdx.x < 32) {
+      __threadfence();
+      T t = T(0);
+      for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) t += __ldcg((const T*)p.red_partial + b);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += shfl_down_any<T>(t, o);
+      if (threadIdx.x == 0) {
+        if (p.red_post == 1) t = t / (T)p.red_imm;
+        else if (p.red_post == 2) t = t * (T)p.red_imm;
+        *(T*)p.red_out = t;
       }
     }
   }
@@ -440,8 +489,16 @@ static int op_arity(int op) {
   return -1;
 }
 
+int* counter_ring_take(int n);  // runtime.cu
+
+struct VmReduce {
+  void* out = nullptr;
+  int post = 0;
+  double imm = 0;
+};
+
 template <typename T>
-static int run_vm(const tcr_ew_program* prog) {
+static int run_vm(const tcr_ew_program* prog, const VmReduce* red = nullptr) {
   VmParams p;
   memset(&p, 0, sizeof(p));
   p.n_inputs = prog->n_inputs;
@@ -467,6 +524,11 @@ static int run_vm(const tcr_ew_program* prog) {
     if ((p.in[k].mode == 0 || (p.in[k].mode == 3 && !b0)) && !aligned16(in.ptr)) aligned = false;
   }
   for (int k = 0; k < prog->n_outputs; ++k) {
+    if (red != nullptr && k == 0) {  // summed, not stored
+      TCR_ARG(prog->outputs[0].reg < TCR_EW_NREGS, "tcr_elementwise_reduce: output register out of range");
+      p.out[0] = prog->outputs[0];
+      continue;
+    }
     TCR_ARG(prog->outputs[k].ptr != nullptr, "tcr_elementwise: output %d is null", k);
     TCR_ARG(prog->outputs[k].reg < TCR_EW_NREGS, "tcr_elementwise: output %d register out of range", k);
     TCR_ARG(dtype_size(prog->outputs[k].dtype) != 0, "tcr_elementwise: output %d has bad dtype", k);
@@ -480,10 +542,31 @@ static int run_vm(const tcr_ew_program* prog) {
             "tcr_elementwise: instr %d register out of range", k);
     p.ins[k] = ins;
   }
-  if (p.n == 0) return TCR_OK;
+  if (p.n == 0 && red == nullptr) return TCR_OK;
   constexpr int THREADS = VmCfg<T>::THREADS;
   int grid = wave_grid(ceil_div(p.n, VM_V), THREADS, sizeof(T) == 4 ? 6 : 6);
   const bool small = p.n < (1ll << 31);
+  if (red != nullptr) {
+    void* partial = nullptr;
+    int rc = tcr_alloc(&partial, sizeof(T) * (size_t)grid);
+    if (rc) return rc;
+    p.red_out = red->out;
+    p.red_partial = partial;
+    p.red_counter = counter_ring_take(1);
+    TCR_ARG(p.red_counter != nullptr, "tcr_elementwise_reduce: no ticket counters (tcr_init not called?)");
+    p.red_post = red->post;
+    p.red_imm = red->imm;
+    if (small) {
+      if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, uint32_t, true>), grid, THREADS, 0, p);
+      else TCR_LAUNCH((ew_vm_kernel<T, false, uint32_t, true>), grid, THREADS, 0, p);
+    } else {
+      if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, int64_t, true>), grid, THREADS, 0, p);
+      else TCR_LAUNCH((ew_vm_kernel<T, false, int64_t, true>), grid, THREADS, 0, p);
+    }
+    tcr_free(partial);
+    TCR_CHECK_LAUNCH();
+    return TCR_OK;
+  }
   if (small) {
     if (aligned) TCR_LAUNCH((ew_vm_kernel<T, true, uint32_t>), grid, THREADS, 0, p);
     else TCR_LAUNCH((ew_vm_kernel<T, false, uint32_t>), grid, THREADS, 0, p);
@@ -1038,6 +1121,23 @@ int tcr_elementwise(const tcr_ew_program* prog) {
     return run_vm<T>(prog);
   });
   return TCR_OK;
+}
+
+int tcr_elementwise_reduce(const tcr_ew_program* prog, void* out, int post_op, double post_imm) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(prog != nullptr && out != nullptr, "tcr_elementwise_reduce: null argument");
+  TCR_ARG(prog->n_inputs >= 0 && prog->n_inputs <= TCR_EW_MAX_INPUTS, "tcr_elementwise_reduce: bad n_inputs %d", prog->n_inputs);
+  TCR_ARG(prog->n_outputs >= 1 && prog->n_outputs <= TCR_EW_MAX_OUTPUTS, "tcr_elementwise_reduce: bad n_outputs %d", prog->n_outputs);
+  TCR_ARG(prog->n_instrs >= 0 && prog->n_instrs <= TCR_EW_MAX_INSTRS, "tcr_elementwise_reduce: bad n_instrs %d", prog->n_instrs);
+  TCR_ARG(post_op >= 0 && post_op <= 2, "tcr_elementwise_reduce: bad post_op %d", post_op);
+  TCR_ARG(prog->dtype == TCR_FLOAT || prog->dtype == TCR_DOUBLE, "tcr_elementwise_reduce: floating-point programs only");
+  TCR_ARG(prog->outputs[0].dtype == prog->dtype, "tcr_elementwise_reduce: the summed output has the compute type");
+  VmReduce red;
+  red.out = out;
+  red.post = post_op;
+  red.imm = post_imm;
+  if (prog->dtype == TCR_FLOAT) return run_vm<float>(prog, &red);
+  return run_vm<double>(prog, &red);
 }
 
 static void prog1(tcr_ew_program* p, int op, int nin, const void* a, const void* b, const void* c, void* out,
