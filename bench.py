@@ -39,7 +39,10 @@ WORKLOADS = {
     # name: (builder kwargs, description)
     "c1": dict(kind="mlp", ninput=10, nhidden=9, noutput=5, nbatch=3),
     "c1w": dict(kind="mlp", ninput=1024, nhidden=1024, noutput=512, nbatch=8192),
-    "c3": dict(kind="mlp", ninput=784, nhidden=1024, noutput=10, nbatch=8192, one_hot=True),
+    # c3 feeds UINT8 pixels (the way MNIST is stored) and casts them on the device with the reference's own CAST (tenncor/eteq/caster.hpp),
+    # both arms evaluate that same graph; c3f is the float-input form of round 1
+    "c3": dict(kind="mlp", ninput=784, nhidden=1024, noutput=10, nbatch=8192, one_hot=True, pixels=True),
+    "c3f": dict(kind="mlp", ninput=784, nhidden=1024, noutput=10, nbatch=8192, one_hot=True),
     "c2": dict(kind="rbm", nvisible=784, nhidden=64, nbatch=4096),
     # learning rate: the demo's adagrad 0.1 (demo/lstm/latin_demo.py:120-122) on a NLL summed over 8192 tokens diverges at this size
     # — the CPU oracle of the reference path reaches inf at step 3 and NaN at step 4 as well. 0.01 survives the ~50 steps
@@ -446,7 +449,7 @@ def main():
         target = pick_target(cfg, mode)
         rng = np.random.default_rng(1000 + rank)
         feeds = list(cfg.feeds.values()) if mode == "train" else [cfg.feeds["x"]]  # inference reads no labels
-        host = [pinned_array(cabi, f.shape()) for f in feeds]
+        host = [pinned_array(cabi, f.shape(), np.dtype(f.dtype())) for f in feeds]
         for buf, arr in zip(host, gen(rng)):
             buf[...] = arr
         h2d = int(sum(b.nbytes for b in host))

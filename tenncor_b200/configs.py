@@ -13,10 +13,16 @@ import tenncor_b200 as tc
 Config = namedtuple("Config", "name train feeds model variables flops_per_step desc")
 
 
-def mlp(ninput=10, nhidden=9, noutput=5, nbatch=3, learning_rate=0.9, seed=0, name="C1"):
-    """dense -> sigmoid -> dense -> sigmoid, MSE, SGD (demo/gd_demo.py:55-71, demo/gd_demo.cpp:100-168)."""
+def mlp(ninput=10, nhidden=9, noutput=5, nbatch=3, learning_rate=0.9, seed=0, name="C1", pixels=False):
+    """dense -> sigmoid -> dense -> sigmoid, MSE, SGD (demo/gd_demo.py:55-71, demo/gd_demo.cpp:100-168).
+    pixels=True: the input variable holds UINT8 pixels (how MNIST is stored) and the graph starts with the reference's own
+    CAST to float and a scale by 1/255 (tenncor/eteq/caster.hpp:10-44): a quarter of the host -> device bytes per step."""
     tc.seed(seed)
-    train_input = tc.EVariable([nbatch, ninput], 0, "train_input")
+    if pixels:
+        feed_input = tc.EVariable([nbatch, ninput], 0, "train_input", dtype="uint8")
+        train_input = tc.api.cast(feed_input, "float32") * (1.0 / 255.0)
+    else:
+        feed_input = train_input = tc.EVariable([nbatch, ninput], 0, "train_input")
     train_exout = tc.EVariable([nbatch, noutput], 0, "train_exout")
     model = tc.api.layer.link([
         tc.api.layer.dense([ninput], [nhidden]),
@@ -30,15 +36,19 @@ def mlp(ninput=10, nhidden=9, noutput=5, nbatch=3, learning_rate=0.9, seed=0, na
         lambda models: tc.api.loss.mean_squared(train_exout, models[0].connect(train_input)))
     # grad wrt the first layer's input is not built (internal/teq/src/derive.cpp:151-159)
     flops = 4 * nbatch * ninput * nhidden + 6 * nbatch * nhidden * noutput
-    return Config(name, train, {"x": train_input, "y": train_exout}, model, model.get_storage(), flops,
-                  "MLP %d-%d-%d sigmoid, MSE, SGD %.2g, batch %d" % (ninput, nhidden, noutput, learning_rate, nbatch))
+    return Config(name, train, {"x": feed_input, "y": train_exout}, model, model.get_storage(), flops,
+                  "MLP %d-%d-%d sigmoid, MSE, SGD %.2g, batch %d%s" % (ninput, nhidden, noutput, learning_rate, nbatch,
+                                                                      ", uint8 pixel input cast on the device" if pixels else ""))
 
 
 def mlp_batch(rng, cfg_feeds, one_hot=False):
     """synthetic batch: x ~ U[0,1); y = pairwise mean of x (gd_demo batch_generate) or one-hot."""
     x_shape = cfg_feeds["x"].shape()
     y_shape = cfg_feeds["y"].shape()
-    x = rng.random(x_shape, dtype=np.float32)
+    if cfg_feeds["x"].dtype() == np.uint8:
+        x = rng.integers(0, 256, x_shape, dtype=np.uint8)
+    else:
+        x = rng.random(x_shape, dtype=np.float32)
     if one_hot or x_shape[1] != 2 * y_shape[1]:
         y = np.zeros(y_shape, dtype=np.float32)
         y[np.arange(y_shape[0]), rng.integers(0, y_shape[1], y_shape[0])] = 1

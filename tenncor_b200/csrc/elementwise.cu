@@ -357,6 +357,11 @@ __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_c
             *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
             *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
           }
+        } else if (ALIGNED && full && in.dtype == TCR_UINT8 && (reinterpret_cast<uintptr_t>(in.ptr) & 3) == 0) {
+          // byte inputs (image pixels cast on the device): one 32-bit load per chunk
+          const uint32_t w = *reinterpret_cast<const uint32_t*>((const uint8_t*)in.ptr + base);
+#pragma unroll
+          for (int v = 0; v < VM_V; ++v) x.v[v] = (T)((w >> (8 * v)) & 0xffu);
         } else {
 #pragma unroll
           for (int v = 0; v < VM_V; ++v) x.v[v] = (base + v < n) ? load_any<T>(in.ptr, in.dtype, base + v) : T(0);

@@ -11,7 +11,15 @@
 //     main loop of tile i+1, and barrier setup / TMEM allocation happen once per launch;
 //   * keeps the 3xTF32 hi/lo split in shared memory (converter warps write only `lo`; the tensor core
 //     truncates the raw tile to its `hi` part), 3 MMAs per k-step;
-//   * supports split-K work items (weight gradients: K = batch) with a deterministic second pass.
+//   * supports split-K work items (weight gradients: K = batch) with a deterministic second pass;
+//   * stream-K when the tile count does not fill whole waves (8192 x 1024: 128 tiles on 74 pairs = 1.73 waves): the tiles x
+//     k-blocks are dealt to the pairs as contiguous ranges of equal length, so a pair computes the last k-blocks of one tile, whole
+//     tiles, and the first k-blocks of another. The pair holding a tile's FIRST k-blocks owns it; the next pair computes the rest
+//     first thing in its walk, leaves the raw accumulator in a workspace slot and raises a flag per epilogue warp; the owner
+//     reaches that tile last, adds the partial (own + partial, a fixed order) and runs the epilogue. Nobody waits on a chain.
+//     (Cutting N instead was measured and rejected: with the lo-part conversion and both operand tiles re-read by three MMAs per
+//     k-step the kernel sits at ~1500 of 2196 cycles per k-block of shared-memory traffic, so a 192-column piece costs 0.85 and
+//     a 128-column piece 0.72 of a 256-column one, profiles/r2_tc2_nslice.md.)
 //
 // Warp roles (per CTA):  w0 TMA producer | w1 MMA issuer (leader CTA only) | w2 TMEM alloc + TF32
 // forwarder | w3 idle | 3xTF32: w4-7 converters, w8-11 epilogue | TF32: w4-7 epilogue.
@@ -23,6 +31,7 @@
 //   tempty[b] leader, 8 arrivals (4 epilogue warps x 2 CTAs) : accumulator b drained
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -44,6 +53,30 @@ struct Tc2Params {
   int epilogue, activation, accumulate;
   int a_mn_major, b_mn_major;
   int tiles_m, tiles_n, splits, kb_per_split;  // work item = (tile_m, tile_n, split); split-K partials go to c + split*m*n
+  int streamk;                                 // 1: pairs walk equal ranges of tiles x k-blocks (splits == 1)
+  float* sk_ws;                                // [pair][256][256] raw partial of the pair's head fragment
+  int* sk_flags;                               // [pair][8]: one per (CTA, epilogue warp), zero between launches
+  long long* dbg;                              // TCR_TC2_TRACE: [pair][8] globaltimer stamps (see gemm_tc2_dispatch)
+};
+
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC2_STAMP(slot) do { if (p.dbg != nullptr && leader && lane == 0) p.dbg[cluster_id * 8 + (slot)] = globaltimer_ns(); } while (0)
+
+// first (tile, k-block) unit of pair c. No snapping to tile edges: moving a boundary by 2-3 k-blocks to avoid a short fragment
+// costs more balance (3 us on the busiest pair at 8192 x 1024 x 784) than the fragment does
+__host__ __device__ inline int64_t tc2_sk_boundary(int64_t T, int c, int C, int total_kb) {
+  (void)total_kb;
+  return T * c / C;
+}
+
+struct Tc2Piece {
+  int64_t m0, n0;
+  int kb0, nkb, split;
+  int kind;  // 0 whole k range of its work item; 1 head fragment (contributor: partial to the workspace); 2 tail fragment (owner: adds the next pair's partial)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -187,25 +220,63 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   TCR_PDL_ENTER();  // everything above touched no global memory: the previous kernel may still be running
 
-  // work item -> tile coordinates and k range
-  auto decode = [&](int item, int64_t& m0, int64_t& n0, int& kb0, int& nkb, int& split) {
-    split = item % p.splits;
-    int t = item / p.splits;
+  // the pair's walk over its pieces, identical in every warp role
+  const int64_t sk_total = (int64_t)p.tiles_m * p.tiles_n * total_kb;
+  // stream-K: the range [sk_begin, sk_end) of (tile, k-block) units is walked as  head fragment, tail fragment, whole tiles.  The
+  // tail (owned) comes second so that its epilogue — which waits for the next pair's head — hides under the whole tiles, and
+  // the un-overlapped last epilogue is an ordinary one.
+  const int64_t sk_begin = p.streamk ? tc2_sk_boundary(sk_total, cluster_id, num_clusters, total_kb) : 0;
+  const int64_t sk_end = p.streamk ? tc2_sk_boundary(sk_total, cluster_id + 1, num_clusters, total_kb) : 0;
+  const int64_t sk_first_full = (sk_begin + total_kb - 1) / total_kb, sk_full_end = sk_end / total_kb;  // tile indices
+  const int sk_head = sk_begin < sk_first_full * total_kb ? 1 : 0, sk_tail = sk_full_end * total_kb < sk_end ? 1 : 0;
+  const int64_t walk_begin = p.streamk ? 0 : cluster_id;
+  const int64_t walk_end = p.streamk ? sk_head + sk_tail + (sk_full_end - sk_first_full) : num_items;
+  auto next_piece = [&](int64_t& cur, Tc2Piece& pc) -> bool {
+    if (cur >= walk_end) return false;
+    int t;
+    if (!p.streamk) {
+      const int item = (int)cur;
+      cur += num_clusters;
+      pc.split = item % p.splits;
+      t = item / p.splits;
+      pc.kb0 = pc.split * p.kb_per_split;
+      pc.nkb = min(p.kb_per_split, total_kb - pc.kb0);
+      pc.kind = 0;
+    } else {
+      const int j = (int)cur++;
+      pc.split = 0;
+      if (j < sk_head) {
+        t = (int)(sk_begin / total_kb);
+        pc.kb0 = (int)(sk_begin - (int64_t)t * total_kb);
+        pc.nkb = total_kb - pc.kb0;
+        pc.kind = 1;
+      } else if (j < sk_head + sk_tail) {
+        t = (int)sk_full_end;
+        pc.kb0 = 0;
+        pc.nkb = (int)(sk_end - sk_full_end * total_kb);
+        pc.kind = 2;
+      } else {
+        t = (int)(sk_first_full + (j - sk_head - sk_tail));
+        pc.kb0 = 0;
+        pc.nkb = total_kb;
+        pc.kind = 0;
+      }
+    }
     const int tn = t % p.tiles_n, tm = t / p.tiles_n;
-    m0 = (int64_t)tm * 256;
-    n0 = (int64_t)tn * 256;
-    kb0 = split * p.kb_per_split;
-    nkb = min(p.kb_per_split, total_kb - kb0);
+    pc.m0 = (int64_t)tm * 256;
+    pc.n0 = (int64_t)tn * 256;
+    return true;
   };
+  Tc2Piece pc;
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
+    TC2_STAMP(0);
     if (lane == 0) {
       uint32_t it = 0;  // global k-block counter -> stage / phase
-      for (int item = cluster_id; item < num_items; item += num_clusters) {
-        int64_t m0, n0; int kb0, nkb, split;
-        decode(item, m0, n0, kb0, nkb, split);
-        const int32_t am = (int32_t)(m0 + 128 * rank), bn = (int32_t)(n0 + 128 * rank);
+      for (int64_t cur = walk_begin; next_piece(cur, pc);) {
+        const int kb0 = pc.kb0, nkb = pc.nkb;
+        const int32_t am = (int32_t)(pc.m0 + 128 * rank), bn = (int32_t)(pc.n0 + 128 * rank);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t use = it / STAGES;
@@ -233,9 +304,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const uint32_t b_lbo = p.b_mn_major ? 4096 : 16, b_sbo = p.b_mn_major ? 512 : 1024, b_kstep = p.b_mn_major ? 1024 : 32;
       const uint32_t a_lt = p.a_mn_major ? 1 : 2, b_lt = p.b_mn_major ? 1 : 2;
       uint32_t it = 0, tile_it = 0;
-      for (int item = cluster_id; item < num_items; item += num_clusters, ++tile_it) {
-        int64_t m0, n0; int kb0, nkb, split;
-        decode(item, m0, n0, kb0, nkb, split);
+      for (int64_t cur = walk_begin; next_piece(cur, pc); ++tile_it) {
+        const int nkb = pc.nkb;
         const uint32_t b = tile_it & 1, buse = tile_it >> 1;
         mbar_wait(&tempty[b], (buse & 1) ^ 1);  // epilogues of both CTAs drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -266,14 +336,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         umma2_commit(&tfull[b]);
       }
+      TC2_STAMP(1);  // last MMA issued
     }
   } else if (warp == 2 && MODE == 1) {
     // ================= TF32 forwarder: local "tiles landed" -> leader's ready barrier =================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int item = cluster_id; item < num_items; item += num_clusters) {
-        int64_t m0, n0; int kb0, nkb, split;
-        decode(item, m0, n0, kb0, nkb, split);
+      for (int64_t cur = walk_begin; next_piece(cur, pc);) {
+        const int nkb = pc.nkb;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&full[s], (it / STAGES) & 1);
@@ -285,9 +355,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ================= 3xTF32 converters: lo = x - trunc_tf32(x) =================
     const int ct = threadIdx.x - C::CONV_WARP0 * 32;  // 0..127
     uint32_t it = 0;
-    for (int item = cluster_id; item < num_items; item += num_clusters) {
-      int64_t m0, n0; int kb0, nkb, split;
-      decode(item, m0, n0, kb0, nkb, split);
+    for (int64_t cur = walk_begin; next_piece(cur, pc);) {
+      const int nkb = pc.nkb;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % STAGES;
         mbar_wait(&full[s], (it / STAGES) & 1);
@@ -312,18 +381,87 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ================= epilogue: TMEM -> registers -> global (both CTAs, own 128 rows) =================
     const int q = warp & 3;
     uint32_t tile_it = 0;
-    for (int item = cluster_id; item < num_items; item += num_clusters, ++tile_it) {
-      int64_t m0, n0; int kb0, nkb, split;
-      decode(item, m0, n0, kb0, nkb, split);
+    float* const my_stage = epi_stage + (warp - C::EPI_WARP0) * (32 * EPI_PITCH);
+    for (int64_t cur = walk_begin; next_piece(cur, pc); ++tile_it) {
+      const int64_t m0 = pc.m0, n0 = pc.n0;
+      const int split = pc.split;
       const uint32_t b = tile_it & 1, buse = tile_it >> 1;
       mbar_wait(&tfull[b], buse & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (pc.kind == 1) {
+        // ---- stream-K contributor: this warp's 32 rows of the raw accumulator go to the pair's workspace slot, then its flag rises
+        float* slot = p.sk_ws + (int64_t)cluster_id * (256 * 256) + (int64_t)(128 * rank + 32 * q) * 256;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          __syncwarp();
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * BN + c * 32);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(my_stage + lane * EPI_PITCH + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          __syncwarp();
+          const int sub = lane >> 3, col = (lane & 7) * 4;
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 4) {
+            const int row = rr + sub;
+            __stcg(reinterpret_cast<float4*>(slot + row * 256 + c * 32 + col), *reinterpret_cast<const float4*>(my_stage + row * EPI_PITCH + col));
+          }
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + cluster_id * 8 + 4 * (int)rank + q), "r"(1) : "memory");
+        }
+        if (q == 0) TC2_STAMP(2);  // head partial published
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tempty[b], 0);
+        continue;
+      }
+      const float* partial = nullptr;
+      if (pc.kind == 2) {
+        // ---- stream-K owner: the next pair computed the tile's remaining k-blocks at the start of its walk
+        int* flag = p.sk_flags + (cluster_id + 1) * 8 + 4 * (int)rank + q;
+        if (q == 0) TC2_STAMP(3);  // owner: accumulator complete, waiting for the partial
+        if (lane == 0) {
+          int seen = 0;
+          uint32_t spins = 0;
+          while (true) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+            if (seen) break;
+            if (++spins > SPIN_LIMIT) __trap();
+          }
+          *flag = 0;  // nobody else reads it: ready for the next launch
+        }
+        __syncwarp();
+        if (q == 0) TC2_STAMP(4);
+        partial = p.sk_ws + (int64_t)(cluster_id + 1) * (256 * 256) + (int64_t)(128 * rank + 32 * q) * 256;  // this warp's 32 rows
+      }
       float* c_out = p.c + (p.splits > 1 ? (int64_t)split * p.m * p.n : 0);
       const int64_t m = m0 + 128 * rank + 32 * q + lane;
       const bool m_ok = m < p.m;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         __syncwarp();
+        if (partial != nullptr) {
+          // the other pair's partial of this chunk: four full 128-byte row segments per load instruction, through the staging tile
+          const int sub = lane >> 3, col = (lane & 7) * 4;
+          float4 pv[8];
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 4) pv[rr / 4] = __ldcg(reinterpret_cast<const float4*>(partial + (rr + sub) * 256 + c * 32 + col));
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 4) *reinterpret_cast<float4*>(my_stage + (rr + sub) * EPI_PITCH + col) = pv[rr / 4];
+          __syncwarp();
+        }
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * BN + c * 32);
         asm volatile(
@@ -341,6 +479,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (partial != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(my_stage + lane * EPI_PITCH + j);
+            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+          }
+          __syncwarp();  // the staging tile is rewritten below
+        }
         // fast path (warp-uniform): unit-stride, 16-byte aligned rows, whole 32-column chunk inside C.
         // Rows are exchanged through shared memory so every store instruction writes four full
         // 128-byte row segments instead of 32 scattered 16-byte pieces.
@@ -373,7 +519,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
             }
           }
-          float* stage = epi_stage + (warp - C::EPI_WARP0) * (32 * EPI_PITCH);
+          float* stage = my_stage;
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -414,6 +560,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       if (lane == 0) mbar_arrive_cluster(&tempty[b], 0);  // this warp's quarter of accumulator b is free
     }
   }
+  if (warp == C::EPI_WARP0) TC2_STAMP(5);  // epilogue done
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   cluster_sync();  // the leader's MMAs read the peer's shared memory: nobody leaves early
@@ -468,6 +615,8 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Params& p,
 int make_tf32_map(CUtensorMap* map, const float* base, int64_t dim0, int64_t dim1, int64_t pitch, uint32_t box0, uint32_t box1, bool mn_major);  // gemm_tc.cu
 
 // 2-CTA path: returns handled = false when the problem should go to the single-CTA kernel
+int* counter_ring_take(int n);  // runtime.cu
+
 int gemm_tc2_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc* d, int a_mn, int b_mn, int64_t a_pitch, int64_t b_pitch, bool* handled) {
   *handled = false;
   static const int enabled = std::getenv("TCR_GEMM_2CTA") ? std::atoi(std::getenv("TCR_GEMM_2CTA")) : 1;
@@ -490,6 +639,7 @@ int gemm_tc2_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc
   p.tiles_n = (int)ceil_div(d->n, 256);
   const int total_kb = (int)ceil_div(d->k, BK);
   const int pairs = state().sm_count / 2;
+  static const int cap = std::getenv("TCR_TC2_CLUSTERS") ? std::atoi(std::getenv("TCR_TC2_CLUSTERS")) : 0;  // experiment knob
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
   int splits = 1;
   if (tiles * 2 <= pairs && total_kb >= 16) {
@@ -502,6 +652,39 @@ int gemm_tc2_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc
   p.kb_per_split = (int)ceil_div(total_kb, splits);
   splits = (int)ceil_div(total_kb, p.kb_per_split);
   p.splits = splits;
+  p.streamk = 0;
+  p.sk_ws = nullptr;
+  p.sk_flags = nullptr;
+  p.dbg = nullptr;
+  static const bool trace = std::getenv("TCR_TC2_TRACE") != nullptr;  // eager launches only: the dispatch synchronises and prints
+  static long long* trace_buf = nullptr;
+  if (trace) {
+    if (!trace_buf) TCR_CUDA(cudaMalloc(&trace_buf, sizeof(long long) * 8 * 80));
+    TCR_CUDA(cudaMemsetAsync(trace_buf, 0, sizeof(long long) * 8 * 80, state().stream));
+    p.dbg = trace_buf;
+  }
+  void* sk_ws = nullptr;
+  static const int sk_enabled = std::getenv("TCR_TC2_STREAMK") ? std::atoi(std::getenv("TCR_TC2_STREAMK")) : 1;
+  if (sk_enabled && splits == 1 && tiles > pairs && total_kb >= 8) {
+    // whole waves of tiles cost ceil(tiles / pairs) tile-lengths; equal ranges cost tiles / pairs (+ a fragment's overheads).
+    // Every range must be at least one tile long so that a tile is shared by two pairs at most. Measured (profiles/r2_tc2_streamk.md):
+    // the gain is far below the MMA count saved on the busiest pair — 4096^3: -13.5 % k-blocks, -4 % time; 8192 x 1024 x 784:
+    // -13.5 % k-blocks, +1 % time — because with every pair busy to the end the per-k-block time rises from ~0.95-1.0 to 1.08 us
+    // (the trace shows all pairs resident from t = 0 and nobody waiting: the 3-MMA main loop is at the chip's sustained
+    // tensor rate, not at a per-pair schedule limit). Hence the 12 % threshold: C3's first layer keeps the plain two-wave walk.
+    const double share = (double)tiles * total_kb / pairs;
+    const double waves = (double)ceil_div(tiles, (int64_t)pairs) * total_kb;
+    if (share >= total_kb + 1 && waves > 1.12 * (share + 3) && (cap <= 0 || cap >= pairs)) {
+      int* flags = counter_ring_take(8 * (pairs + 1));
+      if (flags != nullptr) {
+        rc = tcr_alloc(&sk_ws, sizeof(float) * 256 * 256 * (size_t)pairs);
+        if (rc) return rc;
+        p.streamk = 1;
+        p.sk_ws = (float*)sk_ws;
+        p.sk_flags = flags;
+      }
+    }
+  }
   void* ws = nullptr;
   Tc2Params pk = p;
   if (splits > 1) {
@@ -512,10 +695,28 @@ int gemm_tc2_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc
   }
   const int64_t items = tiles * splits;
   int num_clusters = (int)(items < pairs ? items : pairs);
-  static const int cap = std::getenv("TCR_TC2_CLUSTERS") ? std::atoi(std::getenv("TCR_TC2_CLUSTERS")) : 0;  // experiment knob
   if (cap > 0 && num_clusters > cap) num_clusters = cap;
+  static const bool dbg = std::getenv("TCR_TC2_DEBUG") != nullptr;
+  if (dbg)
+    fprintf(stderr, "tc2: %lld x %lld x %lld %s tiles=%lld splits=%d kb/split=%d pairs=%d streamk=%d\n", (long long)d->m, (long long)d->n, (long long)d->k,
+            d->precision == TCR_GEMM_TF32 ? "tf32" : "3xtf32", (long long)tiles, splits, p.kb_per_split, num_clusters, p.streamk);
   rc = d->precision == TCR_GEMM_TF32 ? launch_tc2<1>(ma, mb, pk, num_clusters) : launch_tc2<2>(ma, mb, pk, num_clusters);
+  if (sk_ws) tcr_free(sk_ws);
   if (rc) return rc;
+  if (trace) {
+    static long long host[8 * 80];
+    TCR_CUDA(cudaStreamSynchronize(state().stream));
+    TCR_CUDA(cudaMemcpy(host, trace_buf, sizeof(host), cudaMemcpyDeviceToHost));
+    long long t0 = 0;
+    for (int c = 0; c < num_clusters; ++c)
+      if (host[c * 8] && (!t0 || host[c * 8] < t0)) t0 = host[c * 8];
+    fprintf(stderr, "tc2 trace (us since the first pair started): pair start lastMMA headPublished ownerWait ownerGo epilogueDone\n");
+    for (int c = 0; c < num_clusters; ++c) {
+      fprintf(stderr, "  %2d", c);
+      for (int k = 0; k < 6; ++k) fprintf(stderr, " %8.2f", host[c * 8 + k] ? (host[c * 8 + k] - t0) * 1e-3 : -1.0);
+      fprintf(stderr, "\n");
+    }
+  }
   if (splits > 1) {
     int grid = wave_grid(d->m * d->n, 256, 8);
     TCR_LAUNCH(splitk2_reduce_kernel, grid, 256, 0, (const float*)ws, splits, p);

@@ -122,6 +122,10 @@ struct Step {
   int64_t pos = 0;  // ordering key of the stable topological re-sort
   bool dead = false;
   int gemm_aux_slot = -1;  // index into `in` of the operand of the product's post-op (activation derivative)
+  // map-reduce (tcr_elementwise_reduce): the program's output is summed over every element into `out`, then scaled
+  bool ew_reduce = false;
+  int red_post = 0;
+  double red_imm = 0;
 };
 
 // One recognised conv2d composite (cfg/tenncor/nn.yml:48-98) or its kernel gradient
@@ -216,7 +220,8 @@ struct Plan {
         if (src.has_scalar) { n.has_scalar = true; n.scalar = src.scalar; }
       } else if (is_ew_op(n.op) && has_compute_kernels(n.dtype)) {
         n.is_ew = true;
-        if (n.op == CAST && !has_compute_kernels(nodes[n.args[0]].dtype)) n.is_ew = false;
+        // a CAST from a storage-only type (UINT8 pixels, INT16 ...) into a compute type converts at load inside the program that
+        // consumes it (tenncor/eteq/caster.hpp:10-44 static_casts element-wise, as load_any does): no separate CAST launch
       }
     }
   }
@@ -395,11 +400,9 @@ struct Plan {
       ins.a = (uint8_t)ra; ins.b = (uint8_t)rb; ins.c = (uint8_t)rc;
       ins.imm = x.imm;
     }
-    p.dtype = rn.op == CAST ? nodes[rn.args[0]].dtype : rn.dtype;
-    if (is_assign(rn.op)) p.dtype = rn.dtype;
+    // a CAST root converts at load (from any storage type): compute in the OUTPUT type so that the store is a plain copy
+    p.dtype = rn.dtype;
     if (!has_compute_kernels((_GENERATED_DTYPE)p.dtype)) return false;
-    // a CAST root converts at load: compute in the OUTPUT type so that the store is a plain copy
-    if (rn.op == CAST) p.dtype = rn.dtype;
     p.n_inputs = (int)g.inputs.size();
     p.n_outputs = 1;
     p.n_instrs = ninstr;
@@ -993,7 +996,8 @@ struct Plan {
         PNode& an = nodes[a];
         if (!an.is_ew || an.inlined || an.exposed || is_assign(an.op) || an.region != a) continue;
         if (an.consumers.size() != 1 || an.n != x.n || an.dtype != x.dtype) continue;
-        if (an.op == CAST) continue;
+        // a CAST joins its consumer's program when that program computes in the CAST's output type: its operand is never a
+        // member (see above), so the conversion is exactly the typed load of that operand
         if (crosses_assign(a, (int)i)) continue;
         // tentatively merge
         std::vector<int> moved = members[a];
@@ -1297,6 +1301,56 @@ struct Plan {
       steps[ps].dead = true;
       steps[s] = std::move(g);
       ++n_fused;
+    }
+
+    // ================= (0b) loss chains: REDUCE_SUM over every rank of an elementwise result [/ constant] =================
+    // cfg/tenncor/loss.yml:21-39 -> core.yml:1090-1096: mean_squared = DIV(REDUCE_SUM(SQUARE(SUB(a, b))), count). The elementwise
+    // program sums its own output (deterministic block-order partials) and applies the scalar division: one launch, and the
+    // [batch x out] intermediate is never written.
+    if (!std::getenv("TCR_NO_LOSS_FUSE"))
+    for (int s = 0; s < ns; ++s) {
+      Step& r = steps[s];
+      if (r.dead || r.ew || r.kind != Step::NORMAL || r.gemm_fused || r.conv_fused || r.group || r.stack_reduce || !r.holder) continue;
+      const int rnode = r.out_node;
+      const PNode& rn = nodes[rnode];
+      if (rn.op != REDUCE_SUM || rn.n != 1 || (rn.dtype != FLOAT && rn.dtype != DOUBLE) || r.in_nodes.size() != 1 || r.in_offsets[0] != 0) continue;
+      const int x = r.in_nodes[0];
+      const int ps = producer(x);
+      if (ps < 0 || nodes[x].exposed || nodes[x].stack >= 0 || live_readers(x).size() != 1 || nodes[rn.args[0]].n != nodes[x].n) continue;
+      const Step& e = steps[ps];
+      if (!e.ew || e.kind != Step::NORMAL || e.ew_reduce || e.prog.n_outputs != 1 || is_assign(nodes[x].op) || nodes[x].dtype != rn.dtype || e.prog.dtype != (int)rn.dtype ||
+          e.prog.outputs[0].dtype != (int)rn.dtype)
+        continue;
+      Step f = e;
+      f.ew_reduce = true;
+      f.out_node = rnode;
+      f.pos = r.pos;
+      merge_acc(s, ps);
+      drop_node(s, x);
+      steps[ps].dead = true;
+      steps[s] = std::move(f);
+      ++n_fused;
+      // the scalar that follows: DIV / MUL of the sum by a constant (reduce_mean's count)
+      if (rn.exposed) continue;
+      const std::vector<int> rd = live_readers(rnode);
+      if (rd.size() != 1) continue;
+      const int sd = rd[0];
+      const Step& d = steps[sd];
+      if (sd <= s || !d.ew || d.kind != Step::NORMAL || d.ew_reduce || d.prog.n_outputs != 1 || d.prog.n_inputs != 1 || d.prog.n_instrs != 2 || d.inputs.size() != 1 ||
+          d.inputs[0].node != rnode || d.inputs[0].offset != 0 || nodes[d.out_node].n != 1 || nodes[d.out_node].dtype != rn.dtype || is_assign(nodes[d.out_node].op) ||
+          d.prog.dtype != (int)rn.dtype)
+        continue;
+      const tcr_ew_instr &i0 = d.prog.instrs[0], &i1 = d.prog.instrs[1];
+      if (i0.op != TCR_EW_CONST || (i1.op != DIV && i1.op != MUL) || i1.a != 0 || i1.b != i0.dst || i0.dst == 0 || d.prog.outputs[0].reg != i1.dst) continue;
+      Step g = steps[s];
+      g.red_post = i1.op == DIV ? 1 : 2;
+      g.red_imm = i0.imm;
+      g.out_node = d.out_node;
+      g.pos = d.pos;
+      merge_acc(sd, s);
+      drop_node(sd, rnode);
+      steps[s].dead = true;
+      steps[sd] = std::move(g);
     }
 
     // ================= (1) sibling products sharing their A operand -> grouped launch =================
@@ -2089,6 +2143,7 @@ struct Plan {
           st.prog.inputs[k].ptr = (const char*)in.ptr + st.inputs[k].offset;
         }
         st.prog.outputs[0].ptr = out.ptr;
+        st.out = out.ptr;
       } else {
         st.out = out.ptr;
         if (st.conv_fused) st.conv_cols = alloc_owned((size_t)st.conv_rows * (size_t)st.conv_pitch * sizeof(float));
@@ -2123,7 +2178,8 @@ struct Plan {
             "tcr_allreduce_sum");
     } else if (st.kind == Step::BUCKET_MEMBER) {
       if (!st.member_in_place) check(tcr_d2d(st.out, st.in[0], (size_t)nodes[st.out_node].n * type_size(nodes[st.out_node].dtype)), "tcr_d2d");
-    } else if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
+    } else if (st.ew_reduce) check(tcr_elementwise_reduce(&st.prog, st.out, st.red_post, st.red_imm), "tcr_elementwise_reduce");
+    else if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
     else if (st.group) {
       tcr_gemm_group_desc d = st.gd;
       d.precision = gemm_precision();
@@ -2325,6 +2381,7 @@ struct Plan {
     const PNode& o = nodes[st.out_node];
     std::string what = egen::name_op((_GENERATED_OPCODE)o.op);
     if (st.kind == Step::BUCKET_MEMBER) return what + " -> bucket";
+    if (st.ew_reduce) return std::string("SUM") + (st.red_post == 1 ? "/c" : st.red_post == 2 ? "*c" : "") + " of fused(" + std::to_string(st.prog.n_instrs) + " instr, " + std::to_string(st.prog.n_inputs) + " in)";
     if (st.ew) return what + " fused(" + std::to_string(st.prog.n_instrs) + " instr, " + std::to_string(st.prog.n_inputs) + " in)";
     if (st.group) {
       std::string k;

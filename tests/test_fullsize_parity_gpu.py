@@ -36,10 +36,12 @@ def _train_and_compare(cfg, gen, steps, tol_loss, tol_var):
     assert max(worst.values()) < tol_var, worst
 
 
-def test_c3_full_size_three_steps_match_oracle(gpu):
+@pytest.mark.parametrize("pixels", [False, True])
+def test_c3_full_size_three_steps_match_oracle(gpu, pixels):
+    """pixels: the bench's form — a UINT8 input variable, CAST + scale on the device (tenncor/eteq/caster.hpp:10-44)."""
     tc.set_evaluator("plan")
     tc.set_matmul_precision("3xtf32")
-    cfg = configs.mlp(784, 1024, 10, 8192, name="c3")
+    cfg = configs.mlp(784, 1024, 10, 8192, name="c3", pixels=pixels)
     _train_and_compare(cfg, lambda rng: configs.mlp_batch(rng, cfg.feeds, one_hot=True), steps=3, tol_loss=1e-4, tol_var=1e-4)
 
 

@@ -105,3 +105,25 @@ def test_single_cta_kernel_still_correct_in_subprocess(gpu):
     env = dict(os.environ, TCR_GEMM_2CTA="0")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("precision", [1, 2], ids=["tf32", "3xtf32"])
+@pytest.mark.parametrize("M,N,K,ta,tb", [(5120, 1024, 784, 0, 0), (4864, 1000, 520, 1, 0), (19200, 260, 300, 0, 1), (2560, 7680, 256, 1, 1)],
+                         ids=["80-tiles", "ragged-n", "ragged-mnk", "300-tiles"])
+def test_stream_k_tiles_shared_by_two_pairs(gpu, M, N, K, ta, tb, precision):
+    """More 256 x 256 tiles than CTA pairs and not a multiple of them: the pairs walk equal (tile, k-block) ranges and a tile's
+    accumulator is the sum of two pairs' partials (csrc/gemm_tc2.cu). Same bounds as the un-split product, bit-identical on
+    repeats (fixed order own + partial, flags reset for the next launch), bias + activation applied once by the owner."""
+    rng = np.random.default_rng(M + N + K)
+    A = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+    B = rng.uniform(-1, 1, (K, N)).astype(np.float32)
+    want = A.astype(np.float64) @ B.astype(np.float64)
+    S = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)
+    bound = S * (2.0 ** -10 if precision == 1 else (2.0 ** -19 + K * 2.0 ** -23))
+    got = run_gemm(gpu, A, B, ta, tb, precision)
+    assert np.all(np.abs(got - want) <= bound + 1e-30)
+    for _ in range(2):
+        np.testing.assert_array_equal(run_gemm(gpu, A, B, ta, tb, precision), got)
+    bias = rng.uniform(-1, 1, N).astype(np.float32)
+    got = run_gemm(gpu, A, B, ta, tb, 2, bias=bias, epi=gpu.EPI_BIAS_N, act=gpu.OP["SIGMOID"])
+    assert np.all(np.abs(got - 1 / (1 + np.exp(-(want + bias)))) <= 0.25 * S * (2.0 ** -19 + K * 2.0 ** -23) + 2e-6)  # |sigmoid'| <= 1/4
