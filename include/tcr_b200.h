@@ -213,6 +213,34 @@ int tcr_elementwise(const tcr_ew_program* prog);
  * elementwise chain + REDUCE_SUM over every rank + scalar DIV of a loss (cfg/tenncor/loss.yml:21-39 -> core.yml:1090-1096:
  * SUB, SQUARE, REDUCE_SUM, DIV by a constant element count). Deterministic: block partials in block order. */
 int tcr_elementwise_reduce(const tcr_ew_program* prog, void* out, int post_op, double post_imm);
+/* `count` (<= 8) programs of one compute type over the SAME iteration space (equal dims products) in one launch, evaluated
+ * in order per element: a program may read, un-broadcast and at the same index, what an earlier one of the call stored.
+ * Replaces a chain of elementwise functors whose intermediate results have several readers each (every one of them would be a
+ * separate Eigen assignment in the reference: internal/eigen/device.hpp:555-570 calls one per functor).
+ * keep[k] = 0 (keep may be NULL = keep all): the result of program k is read only by later programs of this call and is not
+ * written to memory (its output pointer still names it). All inputs that come from memory are fetched before the first program
+ * runs; results travel between programs through shared memory. */
+int tcr_elementwise_multi(const tcr_ew_program* progs, int count, const uint8_t* keep);
+
+/* Backward through one time step of a gated recurrent cell, float32, one launch (a hand-written form of the multi launch above
+ * for the shape backprop.hpp:136-142 gives the derivative graph of cfg/tenncor/layer.yml:716-768, every operation rounded on its
+ * own like the separate functors):
+ *     s   = s_a + s_b                                     gradient reaching the cell's output: two contributions
+ *     c   = (c_x * c_y) + (c_z * s)                       gradient of the state: what the next step passes down + this step's
+ *     out_k = (x_k * (1 - x_k)) * (y_k * v_k)             SIGMOID gate   (kind 1)
+ *     out_k = (1 - x_k * x_k)   * (y_k * v_k)             TANH gate      (kind 2)        v_k = s (sel 0) or c (sel 1)
+ * s / c are stored only when their pointer is not NULL. */
+typedef struct {
+  int64_t n;
+  const void *s_a, *s_b;
+  const void *c_x, *c_y, *c_z;
+  void *s_out, *c_out;
+  int32_t n_gates;                 /* <= 6 */
+  int32_t kind[6], sel[6];
+  const void *x[6], *y[6];
+  void* out[6];
+} tcr_cell_backward_desc;
+int tcr_cell_backward(const tcr_cell_backward_desc* desc);
 
 /* Convenience single-op forms (same kernels, program of length 1). */
 int tcr_unary(int opcode, const void* in, void* out, int64_t n, int dtype);

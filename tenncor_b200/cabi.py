@@ -44,7 +44,7 @@ SYMBOLS = [
     "tcr_sync", "tcr_alloc", "tcr_free", "tcr_arena_stats", "tcr_arena_trim", "tcr_host_alloc",
     "tcr_host_free", "tcr_h2d", "tcr_h2d_prefetch", "tcr_prefetch_commit", "tcr_prefetch_sync", "tcr_d2h", "tcr_d2d", "tcr_memset", "tcr_event_create",
     "tcr_event_destroy", "tcr_event_record", "tcr_event_elapsed_ms", "tcr_graph_begin", "tcr_graph_lane", "tcr_graph_record", "tcr_graph_wait",
-    "tcr_graph_end", "tcr_graph_launch", "tcr_graph_destroy", "tcr_launch_count", "tcr_elementwise", "tcr_elementwise_reduce",
+    "tcr_graph_end", "tcr_graph_launch", "tcr_graph_destroy", "tcr_launch_count", "tcr_elementwise", "tcr_elementwise_reduce", "tcr_elementwise_multi", "tcr_cell_backward",
     "tcr_unary", "tcr_binary", "tcr_nnary", "tcr_select", "tcr_cast", "tcr_assign", "tcr_rand_unif", "tcr_rand_seed", "tcr_rand_unif_stream",
     "tcr_reduce", "tcr_argmax", "tcr_map_copy", "tcr_extend", "tcr_permute", "tcr_slice", "tcr_pad",
     "tcr_stride", "tcr_scatter", "tcr_reverse", "tcr_concat", "tcr_gemm", "tcr_gemm_grouped", "tcr_gemm_grouped_check", "tcr_rnn_debug_read", "tcr_contract", "tcr_conv", "tcr_im2col", "tcr_col2im",
@@ -90,6 +90,13 @@ class GemmDesc(C.Structure):
                 ("dtype", C.c_int32), ("precision", C.c_int32), ("epilogue", C.c_int32),
                 ("activation", C.c_int32), ("bias", C.c_void_p), ("accumulate", C.c_int32),
                 ("post_op", C.c_int32), ("aux", C.c_void_p)]
+
+
+class CellBackwardDesc(C.Structure):
+    """tcr_cell_backward_desc (include/tcr_b200.h)"""
+    _fields_ = [("n", C.c_int64), ("s_a", C.c_void_p), ("s_b", C.c_void_p), ("c_x", C.c_void_p), ("c_y", C.c_void_p), ("c_z", C.c_void_p),
+                ("s_out", C.c_void_p), ("c_out", C.c_void_p), ("n_gates", C.c_int32), ("kind", C.c_int32 * 6), ("sel", C.c_int32 * 6),
+                ("x", C.c_void_p * 6), ("y", C.c_void_p * 6), ("out", C.c_void_p * 6)]
 
 
 class GemmGroupDesc(C.Structure):

@@ -327,129 +327,148 @@ template <typename T> struct VmCfg { static constexpr int THREADS = sizeof(T) ==
 template <typename T> __device__ __forceinline__ T shfl_down_any(T v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
 template <> __device__ __forceinline__ int64_t shfl_down_any(int64_t v, int o) { return (int64_t)__shfl_down_sync(0xffffffffu, (long long)v, o); }
 
+// The register machine in three pieces: one input of one chunk (VM_V consecutive elements) from memory, the instruction list over
+// the shared-memory register file (register r of this thread at regs[r * TH + threadIdx.x]), the outputs of one chunk to memory.
+template <typename T, bool ALIGNED, typename I>
+__device__ __forceinline__ V4<T> vm_load(const VmParams& p, const VmInput& in, const I ch) {
+  const I n = (I)p.n;
+  const I d0 = (I)p.d0, d1 = (I)p.d1;
+  const I base = ch * VM_V;
+  const bool full = base + VM_V <= n;
+  V4<T> x;
+  if (in.mode == 1) {
+    T s = load_any<T>(in.ptr, in.dtype, 0);
+#pragma unroll
+    for (int v = 0; v < VM_V; ++v) x.v[v] = s;
+  } else if (in.mode == 0) {
+    if (ALIGNED && full && in.dtype == DTypeOf<T>::value) {
+      const T* src = (const T*)in.ptr + base;
+      if (sizeof(T) == 4) {
+        *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
+      } else {
+        *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
+        *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
+      }
+    } else if (ALIGNED && full && in.dtype == TCR_UINT8 && (reinterpret_cast<uintptr_t>(in.ptr) & 3) == 0) {
+      // byte inputs (image pixels cast on the device): one 32-bit load per chunk
+      const uint32_t w = *reinterpret_cast<const uint32_t*>((const uint8_t*)in.ptr + base);
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) x.v[v] = (T)((w >> (8 * v)) & 0xffu);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) x.v[v] = (base + v < n) ? load_any<T>(in.ptr, in.dtype, base + v) : T(0);
+    }
+  } else if (in.mode == 3) {
+    // 3-segment broadcast with D0 % 4 == 0: the chunk stays inside one run of segment 0
+    const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
+    I i0 = base % d0, t = base / d0, i1 = t % d1, i2 = t / d1;
+    I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
+    if (in.bcast[0]) {
+      T s = load_any<T>(in.ptr, in.dtype, j);
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) x.v[v] = s;
+    } else if (ALIGNED && in.dtype == DTypeOf<T>::value) {
+      const T* src = (const T*)in.ptr + j;
+      *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
+      if (sizeof(T) == 8) *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) x.v[v] = load_any<T>(in.ptr, in.dtype, j + v);
+    }
+  } else {
+    const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
+#pragma unroll
+    for (int v = 0; v < VM_V; ++v) {
+      I i = base + v;
+      if (i >= n) { x.v[v] = T(0); continue; }
+      I i0 = i % d0, t = i / d0, i1 = t % d1, i2 = t / d1;
+      I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
+      x.v[v] = load_any<T>(in.ptr, in.dtype, j);
+    }
+  }
+  return x;
+}
+
+template <typename T, int TH>
+__device__ __forceinline__ void vm_exec(const VmParams& p, V4<T>* regs) {
+  for (int pc = 0; pc < p.n_instrs; ++pc) {
+    const tcr_ew_instr& ins = p.ins[pc];
+    const int op = ins.op;
+    V4<T> a = regs[ins.a * TH + threadIdx.x], d;
+    if (op >= TCR_EW_POW && op <= TCR_EW_GT) {
+      V4<T> b = regs[ins.b * TH + threadIdx.x];
+      switch (op) {
+#define VMB(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d.v[v] = vm_bin<T, OP>(a.v[v], b.v[v]); break;
+        VMB(TCR_EW_ADD) VMB(TCR_EW_SUB) VMB(TCR_EW_MUL) VMB(TCR_EW_DIV) VMB(TCR_EW_POW) VMB(TCR_EW_MIN)
+        VMB(TCR_EW_MAX) VMB(TCR_EW_EQ) VMB(TCR_EW_NEQ) VMB(TCR_EW_LT) VMB(TCR_EW_GT)
+#undef VMB
+        default: d = a;
+      }
+    } else if (op == TCR_EW_CONST) {
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) d.v[v] = (T)ins.imm;
+    } else if (op == TCR_EW_SELECT) {
+      V4<T> b = regs[ins.b * TH + threadIdx.x], c = regs[ins.c * TH + threadIdx.x];
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) d.v[v] = (a.v[v] != T(0)) ? b.v[v] : c.v[v];
+    } else {
+      switch (op) {
+#define VMU(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d.v[v] = vm_un<T, OP>(a.v[v]); break;
+        VMU(TCR_EW_SIGMOID) VMU(TCR_EW_TANH) VMU(TCR_EW_EXP) VMU(TCR_EW_NEG) VMU(TCR_EW_SQUARE) VMU(TCR_EW_LOG)
+        VMU(TCR_EW_SQRT) VMU(TCR_EW_ABS) VMU(TCR_EW_SIN) VMU(TCR_EW_COS) VMU(TCR_EW_TAN) VMU(TCR_EW_ROUND)
+        VMU(TCR_EW_CUBE)
+#undef VMU
+        default: d = a;  // MOV
+      }
+    }
+    regs[ins.dst * TH + threadIdx.x] = d;
+  }
+}
+
+template <typename T, bool ALIGNED, typename I, bool RED, int TH>
+__device__ __forceinline__ void vm_store(const VmParams& p, V4<T>* regs, const I ch, T& red_acc) {
+  const I n = (I)p.n;
+  const I base = ch * VM_V;
+  const bool full = base + VM_V <= n;
+  if (RED) {
+    const V4<T> y = regs[p.out[0].reg * TH + threadIdx.x];
+#pragma unroll
+    for (int v = 0; v < VM_V; ++v)
+      if (base + v < n) red_acc += y.v[v];
+  }
+  for (int k = RED ? 1 : 0; k < p.n_outputs; ++k) {
+    const tcr_ew_output& o = p.out[k];
+    V4<T> y = regs[o.reg * TH + threadIdx.x];
+    if (ALIGNED && full && o.dtype == DTypeOf<T>::value) {
+      T* dst = (T*)o.ptr + base;
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(y.v);
+      if (sizeof(T) == 8) *reinterpret_cast<uint4*>(dst + 2) = *reinterpret_cast<const uint4*>(y.v + 2);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v)
+        if (base + v < n) store_any<T>(o.ptr, o.dtype, base + v, y.v[v]);
+    }
+  }
+}
+
+// one chunk of one program: load, execute, store
+template <typename T, bool ALIGNED, typename I, bool RED>
+__device__ __forceinline__ void vm_chunk(const VmParams& p, V4<T>* regs, const I ch, T& red_acc) {
+  constexpr int TH = VmCfg<T>::THREADS;
+  for (int k = 0; k < p.n_inputs; ++k) regs[k * TH + threadIdx.x] = vm_load<T, ALIGNED, I>(p, p.in[k], ch);
+  vm_exec<T, TH>(p, regs);
+  vm_store<T, ALIGNED, I, RED, TH>(p, regs, ch, red_acc);
+}
+
 template <typename T, bool ALIGNED, typename I, bool RED = false>
 __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_constant__ VmParams p) {
   TCR_PDL_ENTER();
   constexpr int THREADS = VmCfg<T>::THREADS;
-  __shared__ V4<T> regs[TCR_EW_NREGS][THREADS];
+  __shared__ V4<T> regs[TCR_EW_NREGS * THREADS];
   T red_acc = T(0);  // RED: this thread's share of the sum of output 0
-  const I n = (I)p.n;
-  const I nchunks = (n + VM_V - 1) / VM_V;
+  const I nchunks = ((I)p.n + VM_V - 1) / VM_V;
   const I stride = (I)gridDim.x * THREADS;
-  const I d0 = (I)p.d0, d1 = (I)p.d1;
-  for (I ch = (I)blockIdx.x * THREADS + threadIdx.x; ch < nchunks; ch += stride) {
-    const I base = ch * VM_V;
-    const bool full = base + VM_V <= n;
-    // ---- load inputs into registers 0..n_inputs-1
-    for (int k = 0; k < p.n_inputs; ++k) {
-      V4<T> x;
-      const VmInput& in = p.in[k];
-      if (in.mode == 1) {
-        T s = load_any<T>(in.ptr, in.dtype, 0);
-#pragma unroll
-        for (int v = 0; v < VM_V; ++v) x.v[v] = s;
-      } else if (in.mode == 0) {
-        if (ALIGNED && full && in.dtype == DTypeOf<T>::value) {
-          const T* src = (const T*)in.ptr + base;
-          if (sizeof(T) == 4) {
-            *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
-          } else {
-            *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
-            *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
-          }
-        } else if (ALIGNED && full && in.dtype == TCR_UINT8 && (reinterpret_cast<uintptr_t>(in.ptr) & 3) == 0) {
-          // byte inputs (image pixels cast on the device): one 32-bit load per chunk
-          const uint32_t w = *reinterpret_cast<const uint32_t*>((const uint8_t*)in.ptr + base);
-#pragma unroll
-          for (int v = 0; v < VM_V; ++v) x.v[v] = (T)((w >> (8 * v)) & 0xffu);
-        } else {
-#pragma unroll
-          for (int v = 0; v < VM_V; ++v) x.v[v] = (base + v < n) ? load_any<T>(in.ptr, in.dtype, base + v) : T(0);
-        }
-      } else if (in.mode == 3) {
-        // 3-segment broadcast with D0 % 4 == 0: the chunk stays inside one run of segment 0
-        const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
-        I i0 = base % d0, t = base / d0, i1 = t % d1, i2 = t / d1;
-        I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
-        if (in.bcast[0]) {
-          T s = load_any<T>(in.ptr, in.dtype, j);
-#pragma unroll
-          for (int v = 0; v < VM_V; ++v) x.v[v] = s;
-        } else if (ALIGNED && in.dtype == DTypeOf<T>::value) {
-          const T* src = (const T*)in.ptr + j;
-          *reinterpret_cast<uint4*>(x.v) = *reinterpret_cast<const uint4*>(src);
-          if (sizeof(T) == 8) *reinterpret_cast<uint4*>(x.v + 2) = *reinterpret_cast<const uint4*>(src + 2);
-        } else {
-#pragma unroll
-          for (int v = 0; v < VM_V; ++v) x.v[v] = load_any<T>(in.ptr, in.dtype, j + v);
-        }
-      } else {
-        const I e0 = in.bcast[0] ? 1 : d0, e1 = in.bcast[1] ? 1 : d1;
-#pragma unroll
-        for (int v = 0; v < VM_V; ++v) {
-          I i = base + v;
-          if (i >= n) { x.v[v] = T(0); continue; }
-          I i0 = i % d0, t = i / d0, i1 = t % d1, i2 = t / d1;
-          I j = (in.bcast[0] ? 0 : i0) + e0 * ((in.bcast[1] ? 0 : i1) + e1 * (in.bcast[2] ? 0 : i2));
-          x.v[v] = load_any<T>(in.ptr, in.dtype, j);
-        }
-      }
-      regs[k][threadIdx.x] = x;
-    }
-    // ---- execute
-    for (int pc = 0; pc < p.n_instrs; ++pc) {
-      const tcr_ew_instr& ins = p.ins[pc];
-      const int op = ins.op;
-      V4<T> a = regs[ins.a][threadIdx.x], d;
-      if (op >= TCR_EW_POW && op <= TCR_EW_GT) {
-        V4<T> b = regs[ins.b][threadIdx.x];
-        switch (op) {
-#define VMB(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d.v[v] = vm_bin<T, OP>(a.v[v], b.v[v]); break;
-          VMB(TCR_EW_ADD) VMB(TCR_EW_SUB) VMB(TCR_EW_MUL) VMB(TCR_EW_DIV) VMB(TCR_EW_POW) VMB(TCR_EW_MIN)
-          VMB(TCR_EW_MAX) VMB(TCR_EW_EQ) VMB(TCR_EW_NEQ) VMB(TCR_EW_LT) VMB(TCR_EW_GT)
-#undef VMB
-          default: d = a;
-        }
-      } else if (op == TCR_EW_CONST) {
-#pragma unroll
-        for (int v = 0; v < VM_V; ++v) d.v[v] = (T)ins.imm;
-      } else if (op == TCR_EW_SELECT) {
-        V4<T> b = regs[ins.b][threadIdx.x], c = regs[ins.c][threadIdx.x];
-#pragma unroll
-        for (int v = 0; v < VM_V; ++v) d.v[v] = (a.v[v] != T(0)) ? b.v[v] : c.v[v];
-      } else {
-        switch (op) {
-#define VMU(OP) case OP: _Pragma("unroll") for (int v = 0; v < VM_V; ++v) d.v[v] = vm_un<T, OP>(a.v[v]); break;
-          VMU(TCR_EW_SIGMOID) VMU(TCR_EW_TANH) VMU(TCR_EW_EXP) VMU(TCR_EW_NEG) VMU(TCR_EW_SQUARE) VMU(TCR_EW_LOG)
-          VMU(TCR_EW_SQRT) VMU(TCR_EW_ABS) VMU(TCR_EW_SIN) VMU(TCR_EW_COS) VMU(TCR_EW_TAN) VMU(TCR_EW_ROUND)
-          VMU(TCR_EW_CUBE)
-#undef VMU
-          default: d = a;  // MOV
-        }
-      }
-      regs[ins.dst][threadIdx.x] = d;
-    }
-    // ---- store outputs
-    if (RED) {
-      const V4<T> y = regs[p.out[0].reg][threadIdx.x];
-#pragma unroll
-      for (int v = 0; v < VM_V; ++v)
-        if (base + v < n) red_acc += y.v[v];
-    }
-    for (int k = RED ? 1 : 0; k < p.n_outputs; ++k) {
-      const tcr_ew_output& o = p.out[k];
-      V4<T> y = regs[o.reg][threadIdx.x];
-      if (ALIGNED && full && o.dtype == DTypeOf<T>::value) {
-        T* dst = (T*)o.ptr + base;
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(y.v);
-        if (sizeof(T) == 8) *reinterpret_cast<uint4*>(dst + 2) = *reinterpret_cast<const uint4*>(y.v + 2);
-      } else {
-#pragma unroll
-        for (int v = 0; v < VM_V; ++v)
-          if (base + v < n) store_any<T>(o.ptr, o.dtype, base + v, y.v[v]);
-      }
-    }
-  }
+  for (I ch = (I)blockIdx.x * THREADS + threadIdx.x; ch < nchunks; ch += stride) vm_chunk<T, ALIGNED, I, RED>(p, regs, ch, red_acc);
   if (RED) {
     // block sum in a fixed order (shuffle tree, then warp order), one partial per block; the last block to arrive adds the
     // partials in block order and applies the post-op: deterministic for a given grid, one launch
@@ -485,6 +504,128 @@ __global__ void __launch_bounds__(VmCfg<T>::THREADS) ew_vm_kernel(const __grid_c
   }
 }
 
+// Several programs over the SAME iteration space in one launch: a thread runs program 0, 1, ... on its chunk before moving to
+// the next chunk. A later program may read what an earlier one stored at the same index (the thread's own stores are visible
+// to it), which is how a chain of elementwise results that each have several readers — the LSTM cell's backward: dh, dc and
+// four gate pre-activation gradients (tenncor/eteq/backprop.hpp:136-142 over cfg/tenncor/layer.yml:716-768) — becomes one launch
+// without a register machine wide enough to hold all of them at once.
+constexpr int VM_MULTI_MAX = 8;
+constexpr int VM_MULTI_THREADS = 128;
+struct VmMulti {
+  int32_t count;
+  int32_t n_ext;                                          // inputs read from memory, over all programs
+  // where input j of program k comes from: >= 0 slot of the prefetched external inputs; < 0: output 0 of program -(src + 1)
+  int16_t src[VM_MULTI_MAX][TCR_EW_MAX_INPUTS];
+  uint8_t store[VM_MULTI_MAX];                            // 0: nobody outside the launch reads this program's result
+  VmParams p[VM_MULTI_MAX];
+};
+
+// Dynamic shared memory: [n_ext + count][THREADS] chunks. Every input that comes from memory is fetched first, for all programs
+// at once (one memory round trip for the launch instead of one per program); a program's result stays in its forward slot for
+// the programs after it and goes to memory only if somebody outside the launch reads it.
+template <typename T, bool ALIGNED>
+__global__ void __launch_bounds__(VM_MULTI_THREADS) ew_vm_multi_kernel(const __grid_constant__ VmMulti pm) {
+  TCR_PDL_ENTER();
+  constexpr int TH = VM_MULTI_THREADS;
+  __shared__ V4<T> regs[TCR_EW_NREGS * TH];
+  extern __shared__ __align__(16) uint8_t vm_multi_dyn[];
+  V4<T>* ext = reinterpret_cast<V4<T>*>(vm_multi_dyn);
+  V4<T>* fwd = ext + pm.n_ext * TH;
+  T unused = T(0);
+  const uint32_t nchunks = ((uint32_t)pm.p[0].n + VM_V - 1) / VM_V;
+  const uint32_t stride = gridDim.x * TH;
+  for (uint32_t ch = blockIdx.x * TH + threadIdx.x; ch < nchunks; ch += stride) {
+    const bool full = (ch + 1) * VM_V <= (uint32_t)pm.p[0].n;
+    for (int k = 0; k < pm.count; ++k)
+      for (int j = 0; j < pm.p[k].n_inputs; ++j) {
+        const int sl = pm.src[k][j];
+        if (sl < 0) continue;
+        const VmInput& in = pm.p[k].in[j];
+        if (ALIGNED && full && in.mode == 0 && in.dtype == DTypeOf<T>::value) {
+          // whole, aligned, already of the compute type: global -> shared without a register in between, so all of these are in
+          // flight together (a load followed by its own shared store would serialise the launch on one L2 latency per input)
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ext[sl * TH + threadIdx.x]);
+          const T* src = (const T*)in.ptr + (size_t)ch * VM_V;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+          if (sizeof(T) == 8) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 2) : "memory");
+        } else {
+          ext[sl * TH + threadIdx.x] = vm_load<T, ALIGNED, uint32_t>(pm.p[k], in, ch);
+        }
+      }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    for (int k = 0; k < pm.count; ++k) {
+      const VmParams& p = pm.p[k];
+      for (int j = 0; j < p.n_inputs; ++j) {
+        const int sl = pm.src[k][j];
+        regs[j * TH + threadIdx.x] = sl >= 0 ? ext[sl * TH + threadIdx.x] : fwd[(-sl - 1) * TH + threadIdx.x];
+      }
+      vm_exec<T, TH>(p, regs);
+      fwd[k * TH + threadIdx.x] = regs[p.out[0].reg * TH + threadIdx.x];
+      if (pm.store[k]) vm_store<T, ALIGNED, uint32_t, false, TH>(p, regs, ch, unused);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ gated-cell backward (tcr_cell_backward)
+struct CellBwdParams {
+  uint32_t n;
+  int32_t n_gates;
+  const float *s_a, *s_b, *c_x, *c_y, *c_z;
+  float *s_out, *c_out;
+  int32_t kind[6], sel[6];
+  const float *x[6], *y[6];
+  float* out[6];
+};
+
+template <int V>
+struct CellVec { float v[V]; };
+template <int V> __device__ __forceinline__ CellVec<V> cell_ld(const float* p, uint32_t i) {
+  CellVec<V> r;
+  if (V == 4) *reinterpret_cast<float4*>(r.v) = *reinterpret_cast<const float4*>(p + i);
+  else r.v[0] = p[i];
+  return r;
+}
+template <int V> __device__ __forceinline__ void cell_st(float* p, uint32_t i, const CellVec<V>& r) {
+  if (V == 4) *reinterpret_cast<float4*>(p + i) = *reinterpret_cast<const float4*>(r.v);
+  else p[i] = r.v[0];
+}
+
+// every product / sum is a separately rounded operation (__fmul_rn / __fadd_rn keep ptxas from contracting them into FMAs):
+// the results are bit-identical to the chain of single-functor launches
+template <int V>
+__global__ void __launch_bounds__(128) cell_backward_kernel(const __grid_constant__ CellBwdParams p) {
+  TCR_PDL_ENTER();
+  const uint32_t i = (blockIdx.x * 128u + threadIdx.x) * V;
+  if (i >= p.n) return;
+  // all loads first: one memory round trip for the launch
+  const CellVec<V> sa = cell_ld<V>(p.s_a, i), sb = cell_ld<V>(p.s_b, i), cx = cell_ld<V>(p.c_x, i), cy = cell_ld<V>(p.c_y, i), cz = cell_ld<V>(p.c_z, i);
+  CellVec<V> gx[6], gy[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    if (k < p.n_gates) { gx[k] = cell_ld<V>(p.x[k], i); gy[k] = cell_ld<V>(p.y[k], i); }
+  CellVec<V> s, c;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    s.v[v] = __fadd_rn(sa.v[v], sb.v[v]);
+    c.v[v] = __fadd_rn(__fmul_rn(cx.v[v], cy.v[v]), __fmul_rn(cz.v[v], s.v[v]));
+  }
+  if (p.s_out != nullptr) cell_st<V>(p.s_out, i, s);
+  if (p.c_out != nullptr) cell_st<V>(p.c_out, i, c);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    if (k >= p.n_gates) break;
+    CellVec<V> o;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float x = gx[k].v[v];
+      const float local = p.kind[k] == 1 ? __fmul_rn(x, __fsub_rn(1.0f, x)) : __fsub_rn(1.0f, __fmul_rn(x, x));
+      o.v[v] = __fmul_rn(local, __fmul_rn(gy[k].v[v], p.sel[k] ? c.v[v] : s.v[v]));
+    }
+    cell_st<V>(p.out[k], i, o);
+  }
+}
+
 static int op_arity(int op) {
   if (op >= TCR_EW_ABS && op <= TCR_EW_CUBE) return 1;
   if (op >= TCR_EW_POW && op <= TCR_EW_GT) return 2;
@@ -502,9 +643,8 @@ struct VmReduce {
   double imm = 0;
 };
 
-template <typename T>
-static int run_vm(const tcr_ew_program* prog, const VmReduce* red = nullptr) {
-  VmParams p;
+// tcr_ew_program -> kernel parameters; `aligned` is cleared when a vector access would be misaligned
+static int fill_vm(const tcr_ew_program* prog, VmParams& p, bool& aligned, const VmReduce* red) {
   memset(&p, 0, sizeof(p));
   p.n_inputs = prog->n_inputs;
   p.n_outputs = prog->n_outputs;
@@ -512,7 +652,6 @@ static int run_vm(const tcr_ew_program* prog, const VmReduce* red = nullptr) {
   p.d0 = prog->dims[0];
   p.d1 = prog->dims[1];
   p.n = prog->dims[0] * prog->dims[1] * prog->dims[2];
-  bool aligned = true;
   for (int k = 0; k < prog->n_inputs; ++k) {
     const tcr_ew_input& in = prog->inputs[k];
     TCR_ARG(in.ptr != nullptr, "tcr_elementwise: input %d is null", k);
@@ -547,6 +686,15 @@ static int run_vm(const tcr_ew_program* prog, const VmReduce* red = nullptr) {
             "tcr_elementwise: instr %d register out of range", k);
     p.ins[k] = ins;
   }
+  return TCR_OK;
+}
+
+template <typename T>
+static int run_vm(const tcr_ew_program* prog, const VmReduce* red = nullptr) {
+  VmParams p;
+  bool aligned = true;
+  int frc = fill_vm(prog, p, aligned, red);
+  if (frc) return frc;
   if (p.n == 0 && red == nullptr) return TCR_OK;
   constexpr int THREADS = VmCfg<T>::THREADS;
   int grid = wave_grid(ceil_div(p.n, VM_V), THREADS, sizeof(T) == 4 ? 6 : 6);
@@ -647,6 +795,18 @@ template <typename T>
 __device__ __noinline__ V4<T> chain_load_general(const void* ptr, int dtype, bool b0, bool b1, bool b2, uint32_t base, uint32_t n,
                                                  uint32_t d0, uint32_t d1) {
   V4<T> x;
+  if (!b0 && !b1 && !b2 && base + VM_V <= n) {
+    // un-broadcast leaf of another element type (a CAST folded into its consumer): no index arithmetic; byte pixels in one load
+    if (dtype == TCR_UINT8 && (reinterpret_cast<uintptr_t>(ptr) & 3) == 0) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>((const uint8_t*)ptr + base);
+#pragma unroll
+      for (int v = 0; v < VM_V; ++v) x.v[v] = (T)((w >> (8 * v)) & 0xffu);
+      return x;
+    }
+#pragma unroll
+    for (int v = 0; v < VM_V; ++v) x.v[v] = load_any<T>(ptr, dtype, base + v);
+    return x;
+  }
   const uint32_t e0 = b0 ? 1 : d0, e1 = b1 ? 1 : d1;
 #pragma unroll 1
   for (int v = 0; v < VM_V; ++v) {
@@ -1085,6 +1245,47 @@ __global__ void __launch_bounds__(256) scale_kernel<float>(float* __restrict__ b
 
 using namespace tcr;
 
+template <typename T>
+static int run_vm_multi(const tcr_ew_program* progs, int count, const uint8_t* keep) {
+  static VmMulti pm;  // 7 KB: not on the stack; launches are serialised by the caller (one library stream)
+  pm.count = count;
+  pm.n_ext = 0;
+  bool aligned = true;
+  for (int k = 0; k < count; ++k) {
+    int rc = fill_vm(&progs[k], pm.p[k], aligned, nullptr);
+    if (rc) return rc;
+    pm.store[k] = keep == nullptr || keep[k] != 0;
+    for (int j = 0; j < progs[k].n_inputs; ++j) {
+      const VmInput& in = pm.p[k].in[j];
+      int from = -1;
+      // the value an earlier program of this launch computes: same address, whole, same element type
+      for (int q = k - 1; q >= 0 && from < 0; --q)
+        if (in.mode == 0 && in.ptr == progs[q].outputs[0].ptr && in.dtype == progs[q].outputs[0].dtype && in.dtype == progs[k].dtype) from = q;
+      pm.src[k][j] = from >= 0 ? (int16_t)(-(from + 1)) : (int16_t)pm.n_ext++;
+    }
+  }
+  for (int k = 0; k < count; ++k)
+    for (int q = 0; q < k; ++q)
+      for (int j = 0; j < progs[k].n_inputs; ++j) {
+        // a BROADCAST or re-typed read of an earlier result cannot be served by this thread's own stores
+        const VmInput& in = pm.p[k].in[j];
+        TCR_ARG(!(in.ptr == progs[q].outputs[0].ptr && pm.src[k][j] >= 0), "tcr_elementwise_multi: program %d reads program %d's result broadcast or re-typed", k, q);
+      }
+  if (pm.p[0].n == 0) return TCR_OK;
+  const size_t dyn = sizeof(V4<T>) * (size_t)VM_MULTI_THREADS * (size_t)(pm.n_ext + count);
+  static size_t configured[2] = {0, 0};
+  if (dyn > 48 * 1024 - sizeof(V4<T>) * TCR_EW_NREGS * VM_MULTI_THREADS && dyn > configured[aligned]) {
+    if (aligned) TCR_CUDA(cudaFuncSetAttribute(ew_vm_multi_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    else TCR_CUDA(cudaFuncSetAttribute(ew_vm_multi_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    configured[aligned] = dyn;
+  }
+  const int grid = wave_grid(ceil_div(pm.p[0].n, VM_V), VM_MULTI_THREADS, 3);
+  if (aligned) TCR_LAUNCH((ew_vm_multi_kernel<T, true>), grid, VM_MULTI_THREADS, dyn, pm);
+  else TCR_LAUNCH((ew_vm_multi_kernel<T, false>), grid, VM_MULTI_THREADS, dyn, pm);
+  TCR_CHECK_LAUNCH();
+  return TCR_OK;
+}
+
 extern "C" {
 
 int tcr_elementwise(const tcr_ew_program* prog) {
@@ -1125,6 +1326,56 @@ int tcr_elementwise(const tcr_ew_program* prog) {
     if (try_chain<T>(prog, &rc)) return rc;
     return run_vm<T>(prog);
   });
+  return TCR_OK;
+}
+
+int tcr_elementwise_multi(const tcr_ew_program* progs, int count, const uint8_t* keep) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(progs != nullptr && count >= 1 && count <= VM_MULTI_MAX, "tcr_elementwise_multi: 1..%d programs (got %d)", VM_MULTI_MAX, count);
+  if (count == 1) return tcr_elementwise(progs);
+  const int64_t n = progs[0].dims[0] * progs[0].dims[1] * progs[0].dims[2];
+  TCR_ARG(n < (1ll << 31), "tcr_elementwise_multi: iteration space too large");
+  for (int k = 0; k < count; ++k) {
+    const tcr_ew_program& q = progs[k];
+    TCR_ARG(q.n_inputs >= 0 && q.n_inputs <= TCR_EW_MAX_INPUTS && q.n_outputs >= 1 && q.n_outputs <= TCR_EW_MAX_OUTPUTS && q.n_instrs >= 0 &&
+                q.n_instrs <= TCR_EW_MAX_INSTRS, "tcr_elementwise_multi: program %d has bad counts", k);
+    TCR_ARG(q.dtype == progs[0].dtype, "tcr_elementwise_multi: program %d computes in another type", k);
+    TCR_ARG(q.dims[0] * q.dims[1] * q.dims[2] == n, "tcr_elementwise_multi: program %d has another iteration space", k);
+  }
+  switch (progs[0].dtype) {
+    case TCR_FLOAT: return run_vm_multi<float>(progs, count, keep);
+    case TCR_DOUBLE: return run_vm_multi<double>(progs, count, keep);
+    case TCR_INT32: return run_vm_multi<int32_t>(progs, count, keep);
+    case TCR_INT64: return run_vm_multi<int64_t>(progs, count, keep);
+    default: set_error("tcr_elementwise_multi: no compute kernels for dtype %d", progs[0].dtype); return TCR_ERR_ARG;
+  }
+}
+
+int tcr_cell_backward(const tcr_cell_backward_desc* d) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(d != nullptr && d->n >= 0 && d->n < (1ll << 31), "tcr_cell_backward: bad element count");
+  TCR_ARG(d->n_gates >= 0 && d->n_gates <= 6, "tcr_cell_backward: 0..6 gates (got %d)", d->n_gates);
+  TCR_ARG(d->s_a && d->s_b && d->c_x && d->c_y && d->c_z, "tcr_cell_backward: null operand");
+  CellBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = (uint32_t)d->n;
+  p.n_gates = d->n_gates;
+  p.s_a = (const float*)d->s_a; p.s_b = (const float*)d->s_b;
+  p.c_x = (const float*)d->c_x; p.c_y = (const float*)d->c_y; p.c_z = (const float*)d->c_z;
+  p.s_out = (float*)d->s_out; p.c_out = (float*)d->c_out;
+  bool vec = (d->n % 4) == 0 && aligned16(d->s_a) && aligned16(d->s_b) && aligned16(d->c_x) && aligned16(d->c_y) && aligned16(d->c_z) &&
+             aligned16(d->s_out) && aligned16(d->c_out);
+  for (int k = 0; k < d->n_gates; ++k) {
+    TCR_ARG(d->kind[k] == 1 || d->kind[k] == 2, "tcr_cell_backward: gate %d has kind %d (1 SIGMOID, 2 TANH)", k, d->kind[k]);
+    TCR_ARG(d->x[k] && d->y[k] && d->out[k], "tcr_cell_backward: gate %d has a null pointer", k);
+    p.kind[k] = d->kind[k]; p.sel[k] = d->sel[k] ? 1 : 0;
+    p.x[k] = (const float*)d->x[k]; p.y[k] = (const float*)d->y[k]; p.out[k] = (float*)d->out[k];
+    vec = vec && aligned16(d->x[k]) && aligned16(d->y[k]) && aligned16(d->out[k]);
+  }
+  if (d->n == 0) return TCR_OK;
+  if (vec) TCR_LAUNCH(cell_backward_kernel<4>, (int)ceil_div(d->n / 4, (int64_t)128), 128, 0, p);
+  else TCR_LAUNCH(cell_backward_kernel<1>, (int)ceil_div(d->n, (int64_t)128), 128, 0, p);
+  TCR_CHECK_LAUNCH();
   return TCR_OK;
 }
 

@@ -126,6 +126,17 @@ struct Step {
   bool ew_reduce = false;
   int red_post = 0;
   double red_imm = 0;
+  // several elementwise programs over one iteration space in one launch (tcr_elementwise_multi, merge_elementwise_steps): program k
+  // reads multi_inputs[k] and stores node multi_outs[k]; `inputs` holds the reads that come from outside the step
+  bool multi = false;
+  std::vector<tcr_ew_program> multi_progs;
+  std::vector<std::vector<InputRef>> multi_inputs;
+  std::vector<int> multi_outs;
+  std::vector<uint8_t> multi_keep;  // 0: the result is read only by later programs of the launch and is not written to memory
+  // the multi launch has the shape of a gated cell's backward step (match_cell_backward): program 0 = s, 1 = c, then the gates
+  bool cell_bwd = false;
+  int cb_c[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // (program, input) of c_x, c_y, c_z
+  int cb_kind[6] = {0, 0, 0, 0, 0, 0}, cb_sel[6] = {0, 0, 0, 0, 0, 0}, cb_x[6] = {0, 0, 0, 0, 0, 0}, cb_y[6] = {0, 0, 0, 0, 0, 0};  // gate k = program k + 2; x / y input slots
 };
 
 // One recognised conv2d composite (cfg/tenncor/nn.yml:48-98) or its kernel gradient
@@ -1893,6 +1904,212 @@ struct Plan {
     }
   }
 
+  // ---------------------------------------------------------------- elementwise steps over one iteration space -> one launch
+  // After region building every elementwise result with more than one reader is its own launch. Backward through an unrolled
+  // LSTM / GRU cell (tenncor/eteq/backprop.hpp:136-142 over cfg/tenncor/layer.yml:716-813) is, per time step, a chain of six such
+  // results on the critical path (dh, dc, four gate pre-activation gradients), each ~5 us of launch latency for 256 KB of data.
+  // Steps of equal iteration space that are adjacent in the (already topologically sorted) list are merged into one
+  // tcr_elementwise_multi launch: programs run in list order per element, a later one reads an earlier one's result at the same
+  // index. A step joins when (a) what it reads from the group is un-broadcast, whole and of the same size, and (b) no step lying
+  // between the group's first member and it touches anything the group reads or writes — then every member can slide down to
+  // the last member's position without crossing a dependency.
+  // ---- symbolic form of a register-machine program (independent of the register allocation)
+  struct Sym {
+    int kind = 0;  // 0 input, 1 constant, 2 operation
+    int op = 0, a = -1, b = -1, input = -1;
+    double imm = 0;
+  };
+  static bool symbolic(const tcr_ew_program& q, std::vector<Sym>& ex, int& root) {
+    int reg[NREGS];
+    for (int r = 0; r < NREGS; ++r) reg[r] = -1;
+    ex.clear();
+    for (int k = 0; k < q.n_inputs; ++k) { Sym e; e.kind = 0; e.input = k; ex.push_back(e); reg[k] = k; }
+    for (int i = 0; i < q.n_instrs; ++i) {
+      const tcr_ew_instr& ins = q.instrs[i];
+      Sym e;
+      if (ins.op == TCR_EW_CONST) { e.kind = 1; e.imm = ins.imm; }
+      else if (ins.op == TCR_EW_MOV) { if (reg[ins.a] < 0) return false; reg[ins.dst] = reg[ins.a]; continue; }
+      else if (is_unary(ins.op)) { e.kind = 2; e.op = ins.op; e.a = reg[ins.a]; if (e.a < 0) return false; }
+      else if (is_binary(ins.op) || ins.op == ADD || ins.op == MUL) { e.kind = 2; e.op = ins.op; e.a = reg[ins.a]; e.b = reg[ins.b]; if (e.a < 0 || e.b < 0) return false; }
+      else return false;
+      ex.push_back(e);
+      reg[ins.dst] = (int)ex.size() - 1;
+    }
+    root = reg[q.outputs[0].reg];
+    return root >= 0;
+  }
+
+  // Backward through one step of a gated cell as the derivative rules emit it (backprop.hpp:136-142):  s = a + b,
+  // c = x*y + z*s, gates (x (1 - x)) * (y v) or (1 - x^2) * (y v) with v = s | c. Matched on expression trees modulo the
+  // commutativity of ADD / MUL (bitwise commutative in IEEE arithmetic), so the hand-written kernel gives the same bits.
+  bool match_cell_backward(Step& m) {
+    const int count = (int)m.multi_progs.size();
+    if (count < 3 || count > 8) return false;
+    for (int k = 0; k < count; ++k) {
+      const tcr_ew_program& q = m.multi_progs[k];
+      if (q.dtype != FLOAT || q.outputs[0].dtype != FLOAT || q.n_outputs != 1) return false;
+      for (auto& in : m.multi_inputs[k])
+        if (in.mask != 0 || in.dtype != FLOAT || nodes[in.node].has_scalar) return false;
+    }
+    auto is_result_of = [&](int prog, int input, int producer) {
+      const InputRef& r = m.multi_inputs[prog][input];
+      return r.node == m.multi_outs[producer] && r.offset == 0;
+    };
+    std::vector<Sym> ex;
+    int root = -1;
+    auto leaf = [&](int e) { return e >= 0 && ex[e].kind == 0 ? ex[e].input : -1; };
+    auto is_op = [&](int e, int op) { return e >= 0 && ex[e].kind == 2 && ex[e].op == op; };
+    auto is_one = [&](int e) { return e >= 0 && ex[e].kind == 1 && ex[e].imm == 1.0; };
+    // program 0: s = a + b
+    if (!symbolic(m.multi_progs[0], ex, root) || !is_op(root, ADD) || leaf(ex[root].a) < 0 || leaf(ex[root].b) < 0 || leaf(ex[root].a) == leaf(ex[root].b)) return false;
+    if (m.multi_progs[0].n_inputs != 2) return false;
+    // program 1: c = x*y + z*s
+    if (!symbolic(m.multi_progs[1], ex, root) || !is_op(root, ADD) || !is_op(ex[root].a, MUL) || !is_op(ex[root].b, MUL)) return false;
+    {
+      int l[4] = {leaf(ex[ex[root].a].a), leaf(ex[ex[root].a].b), leaf(ex[ex[root].b].a), leaf(ex[ex[root].b].b)};
+      int s_at = -1;
+      for (int k = 0; k < 4; ++k) {
+        if (l[k] < 0) return false;
+        if (is_result_of(1, l[k], 0)) { if (s_at >= 0) return false; s_at = k; }
+      }
+      if (s_at < 0) return false;
+      const int z = l[s_at ^ 1], x = l[(s_at < 2) ? 2 : 0], y = l[(s_at < 2) ? 3 : 1];
+      m.cb_c[0][0] = 1; m.cb_c[0][1] = x;
+      m.cb_c[1][0] = 1; m.cb_c[1][1] = y;
+      m.cb_c[2][0] = 1; m.cb_c[2][1] = z;
+    }
+    // gates
+    for (int k = 2; k < count; ++k) {
+      if (!symbolic(m.multi_progs[k], ex, root) || !is_op(root, MUL)) return false;
+      int local = ex[root].a, up = ex[root].b;
+      auto local_kind = [&](int e, int& x) {
+        if (is_op(e, MUL)) {  // x * (1 - x)
+          for (int sw = 0; sw < 2; ++sw) {
+            const int xe = sw ? ex[e].b : ex[e].a, se = sw ? ex[e].a : ex[e].b;
+            if (leaf(xe) >= 0 && is_op(se, SUB) && is_one(ex[se].a) && leaf(ex[se].b) == leaf(xe)) { x = leaf(xe); return 1; }
+          }
+        } else if (is_op(e, SUB) && is_one(ex[e].a) && is_op(ex[e].b, SQUARE) && leaf(ex[ex[e].b].a) >= 0) {  // 1 - x^2
+          x = leaf(ex[ex[e].b].a);
+          return 2;
+        }
+        return 0;
+      };
+      int x = -1;
+      int kind = local_kind(local, x);
+      if (!kind) { std::swap(local, up); kind = local_kind(local, x); }
+      if (!kind || !is_op(up, MUL)) return false;
+      int y = leaf(ex[up].a), v = leaf(ex[up].b);
+      if (y < 0 || v < 0) return false;
+      auto which = [&](int input) { return is_result_of(k, input, 0) ? 0 : is_result_of(k, input, 1) ? 1 : -1; };
+      if (which(v) < 0) std::swap(y, v);
+      if (which(v) < 0 || which(y) >= 0 || which(x) >= 0) return false;
+      m.cb_kind[k - 2] = kind; m.cb_sel[k - 2] = which(v); m.cb_x[k - 2] = x; m.cb_y[k - 2] = y;
+    }
+    m.cell_bwd = true;
+    return true;
+  }
+
+  void merge_elementwise_steps() {
+    if (std::getenv("TCR_NO_EW_MERGE")) return;
+    const int ns = (int)steps.size();
+    if (ns < 2) return;
+    constexpr int MAX_MEMBERS = 8, WINDOW = 12;
+    auto candidate = [&](const Step& e) {
+      return e.ew && !e.ew_reduce && !e.multi && !e.dead && e.kind == Step::NORMAL && e.prog.n_outputs == 1 && e.extra_outs.empty() && e.dep_nodes.empty() &&
+             !is_assign(nodes[e.out_node].op) && nodes[e.out_node].offset == 0 && nodes[e.out_node].root == e.out_node &&
+             e.prog.dims[0] * e.prog.dims[1] * e.prog.dims[2] < (1ll << 31);
+    };
+    std::vector<std::vector<int>> node_readers(nodes.size());  // steps reading each storage root
+    {
+      std::vector<int> tmp;
+      for (int s = 0; s < ns; ++s) {
+        if (steps[s].dead) continue;
+        step_reads(steps[s], tmp);
+        for (int x : tmp) node_readers[x].push_back(s);
+      }
+    }
+    std::vector<int> group, between;
+    std::vector<int> g_reads, g_writes;  // storage roots
+    std::vector<int> rd, wr;
+    int n_merged = 0;
+    auto contains = [](const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+    auto close = [&] {
+      if (group.size() >= 2) {
+        const int last = group.back();
+        Step m = steps[last];
+        m.multi = true;
+        std::vector<InputRef> outside;
+        for (int g : group) {
+          const Step& e = steps[g];
+          m.multi_progs.push_back(e.prog);
+          m.multi_inputs.push_back(e.inputs);
+          m.multi_outs.push_back(e.out_node);
+          bool outside_reader = nodes[e.out_node].exposed;
+          for (int r : node_readers[e.out_node])
+            if (!contains(group, r)) outside_reader = true;
+          m.multi_keep.push_back(outside_reader ? 1 : 0);
+          for (auto& in : e.inputs)
+            if (!contains(g_writes, in.node) && std::find(outside.begin(), outside.end(), in) == outside.end()) outside.push_back(in);
+          if (g != last) { m.extra_outs.push_back(e.out_node); steps[g].dead = true; }
+        }
+        m.inputs = outside;
+        if (!std::getenv("TCR_NO_CELL_BWD")) match_cell_backward(m);
+        steps[last] = std::move(m);
+        ++n_merged;
+      }
+      group.clear(); between.clear(); g_reads.clear(); g_writes.clear();
+    };
+    for (int s = 0; s < ns; ++s) {
+      const Step& e = steps[s];
+      if (e.dead) continue;
+      if (!candidate(e)) {
+        if (!group.empty()) {
+          between.push_back(s);
+          if ((int)between.size() > WINDOW) close();
+        }
+        continue;
+      }
+      bool join = !group.empty() && (int)group.size() < MAX_MEMBERS;
+      if (join) {
+        const Step& f = steps[group.front()];
+        join = f.prog.dtype == e.prog.dtype && f.prog.dims[0] == e.prog.dims[0] && f.prog.dims[1] == e.prog.dims[1] && f.prog.dims[2] == e.prog.dims[2];
+      }
+      if (join)  // (a) reads from the group are whole and un-broadcast
+        for (auto& in : e.inputs)
+          if (contains(g_writes, in.node) && (in.mask != 0 || in.offset != 0 || nodes[in.node].n != nodes[e.out_node].n || nodes[in.node].dtype != nodes[e.out_node].dtype)) join = false;
+      if (join) {  // (b) nothing in between touches the group's data, nor this step's
+        step_reads(e, rd);
+        for (int b : between) {
+          std::vector<int> brd, bwr;
+          step_reads(steps[b], brd);
+          step_writes(steps[b], bwr);
+          for (int x : brd) if (contains(g_writes, x)) join = false;
+          for (int x : bwr) if (contains(g_writes, x) || contains(g_reads, x) || x == e.out_node) join = false;  // (this step itself stays behind them)
+          if (steps[b].kind != Step::NORMAL) join = false;  // gradient exchange: keep its place
+        }
+      }
+      if (!join) close();
+      group.push_back(s);
+      step_reads(e, rd);
+      for (int x : rd) if (!contains(g_reads, x)) g_reads.push_back(x);
+      g_writes.push_back(e.out_node);
+      // steps skipped so far stay "between" the group's first member and whatever joins next
+    }
+    close();
+    if (n_merged == 0) return;
+    std::vector<Step> kept;
+    kept.reserve(steps.size());
+    for (auto& st : steps)
+      if (!st.dead) kept.push_back(std::move(st));
+    steps = std::move(kept);
+    for (auto& n : nodes) n.step = -1;
+    for (size_t k = 0; k < steps.size(); ++k) {
+      if (steps[k].kind == Step::BUCKET_FLUSH) continue;
+      nodes[steps[k].out_node].step = (int)k;
+      for (int e : steps[k].extra_outs) nodes[e].step = (int)k;
+    }
+  }
+
   // Reads / write of a step in terms of storage roots (before buffers exist)
   void step_access(const Step& st, std::vector<int>& reads, std::vector<int>& writes) const {
     step_reads(st, reads);
@@ -2136,7 +2353,17 @@ struct Plan {
     for (auto& st : steps) {
       if (st.kind == Step::BUCKET_FLUSH) continue;
       PNode& out = nodes[st.out_node];
-      if (st.ew) {
+      if (st.multi) {
+        for (size_t q = 0; q < st.multi_progs.size(); ++q) {
+          for (size_t k = 0; k < st.multi_inputs[q].size(); ++k) {
+            PNode& in = nodes[st.multi_inputs[q][k].node];
+            if (!in.ptr) global::fatalf("planner: input %s of %s was never materialised", in.tens->to_string().c_str(), out.tens->to_string().c_str());
+            st.multi_progs[q].inputs[k].ptr = (const char*)in.ptr + st.multi_inputs[q][k].offset;
+          }
+          st.multi_progs[q].outputs[0].ptr = nodes[st.multi_outs[q]].ptr;
+        }
+        st.out = out.ptr;
+      } else if (st.ew) {
         for (size_t k = 0; k < st.inputs.size(); ++k) {
           PNode& in = nodes[st.inputs[k].node];
           if (!in.ptr) global::fatalf("planner: input %s of %s was never materialised", in.tens->to_string().c_str(), out.tens->to_string().c_str());
@@ -2178,7 +2405,29 @@ struct Plan {
             "tcr_allreduce_sum");
     } else if (st.kind == Step::BUCKET_MEMBER) {
       if (!st.member_in_place) check(tcr_d2d(st.out, st.in[0], (size_t)nodes[st.out_node].n * type_size(nodes[st.out_node].dtype)), "tcr_d2d");
-    } else if (st.ew_reduce) check(tcr_elementwise_reduce(&st.prog, st.out, st.red_post, st.red_imm), "tcr_elementwise_reduce");
+    } else if (st.cell_bwd) {
+      tcr_cell_backward_desc d;
+      std::memset(&d, 0, sizeof(d));
+      const int count = (int)st.multi_progs.size();
+      d.n = nodes[st.out_node].n;
+      d.s_a = st.multi_progs[0].inputs[0].ptr;
+      d.s_b = st.multi_progs[0].inputs[1].ptr;
+      d.c_x = st.multi_progs[st.cb_c[0][0]].inputs[st.cb_c[0][1]].ptr;
+      d.c_y = st.multi_progs[st.cb_c[1][0]].inputs[st.cb_c[1][1]].ptr;
+      d.c_z = st.multi_progs[st.cb_c[2][0]].inputs[st.cb_c[2][1]].ptr;
+      d.s_out = st.multi_keep[0] ? st.multi_progs[0].outputs[0].ptr : nullptr;
+      d.c_out = st.multi_keep[1] ? st.multi_progs[1].outputs[0].ptr : nullptr;
+      d.n_gates = count - 2;
+      for (int k = 0; k < count - 2; ++k) {
+        d.kind[k] = st.cb_kind[k];
+        d.sel[k] = st.cb_sel[k];
+        d.x[k] = st.multi_progs[k + 2].inputs[st.cb_x[k]].ptr;
+        d.y[k] = st.multi_progs[k + 2].inputs[st.cb_y[k]].ptr;
+        d.out[k] = st.multi_progs[k + 2].outputs[0].ptr;
+      }
+      check(tcr_cell_backward(&d), "tcr_cell_backward");
+    } else if (st.multi) check(tcr_elementwise_multi(st.multi_progs.data(), (int)st.multi_progs.size(), st.multi_keep.data()), "tcr_elementwise_multi");
+    else if (st.ew_reduce) check(tcr_elementwise_reduce(&st.prog, st.out, st.red_post, st.red_imm), "tcr_elementwise_reduce");
     else if (st.ew) check(tcr_elementwise(&st.prog), "tcr_elementwise");
     else if (st.group) {
       tcr_gemm_group_desc d = st.gd;
@@ -2335,6 +2584,7 @@ struct Plan {
     fuse();
     build_steps();
     fuse_recurrent_steps();
+    merge_elementwise_steps();
     bucket_gradients();
     if (lower_only) return;
     assign_buffers();
@@ -2381,6 +2631,12 @@ struct Plan {
     const PNode& o = nodes[st.out_node];
     std::string what = egen::name_op((_GENERATED_OPCODE)o.op);
     if (st.kind == Step::BUCKET_MEMBER) return what + " -> bucket";
+    if (st.cell_bwd) return "CELL-BACKWARD(" + std::to_string(st.multi_progs.size() - 2) + " gates, " + std::to_string(st.inputs.size()) + " in)";
+    if (st.multi) {
+      int instrs = 0;
+      for (auto& q : st.multi_progs) instrs += q.n_instrs;
+      return what + " multi(" + std::to_string(st.multi_progs.size()) + " programs, " + std::to_string(instrs) + " instr, " + std::to_string(st.inputs.size()) + " in)";
+    }
     if (st.ew_reduce) return std::string("SUM") + (st.red_post == 1 ? "/c" : st.red_post == 2 ? "*c" : "") + " of fused(" + std::to_string(st.prog.n_instrs) + " instr, " + std::to_string(st.prog.n_inputs) + " in)";
     if (st.ew) return what + " fused(" + std::to_string(st.prog.n_instrs) + " instr, " + std::to_string(st.prog.n_inputs) + " in)";
     if (st.group) {
@@ -2408,7 +2664,8 @@ struct Plan {
       PNode& o = nodes[st.out_node];
       StepTiming t;
       t.what = o.tens->to_string();
-      if (st.ew) t.what += " fused(" + std::to_string(st.prog.n_instrs) + " instr, " + std::to_string(st.prog.n_inputs) + " in)";
+      if (st.multi || st.ew_reduce) t.what = step_name(st);
+      else if (st.ew) t.what += " fused(" + std::to_string(st.prog.n_instrs) + " instr, " + std::to_string(st.prog.n_inputs) + " in)";
       t.shape = o.shape.to_string();
       t.bytes = (size_t)o.n * type_size(o.dtype);
       if (st.ew) {
@@ -2505,7 +2762,32 @@ std::vector<std::string> describe_plan(const TensSetT& targets) {
   Plan plan;
   plan.build(targets, {}, nullptr, true);
   std::vector<std::string> out;
-  for (auto& st : plan.steps) out.push_back(plan.step_name(st) + " " + (st.kind == Step::BUCKET_FLUSH ? std::string() : plan.nodes[st.out_node].shape.to_string()));
+  const bool verbose = std::getenv("TCR_PLAN_VERBOSE") != nullptr;
+  for (auto& st : plan.steps) {
+    std::string line = plan.step_name(st) + " " + (st.kind == Step::BUCKET_FLUSH ? std::string() : plan.nodes[st.out_node].shape.to_string());
+    if (verbose && st.kind != Step::BUCKET_FLUSH) {
+      // storage roots read and written, and the program of an elementwise step: what a fusion pass would have to merge
+      line += "  -> n" + std::to_string(st.out_node);
+      for (int e : st.extra_outs) line += ",n" + std::to_string(e);
+      line += "  <-";
+      if (st.ew) {
+        for (auto& in : st.inputs) line += " n" + std::to_string(in.node) + (in.offset ? "+" + std::to_string(in.offset) : "") + (in.mask ? "/b" + std::to_string(in.mask) : "");
+        line += "  {";
+        for (int k = 0; k < st.prog.n_instrs; ++k) {
+          const tcr_ew_instr& ins = st.prog.instrs[k];
+          line += " r" + std::to_string(ins.dst) + "=";
+          if (ins.op == TCR_EW_CONST) line += std::to_string(ins.imm);
+          else if (ins.op == TCR_EW_MOV) line += "r" + std::to_string(ins.a);
+          else line += egen::name_op((_GENERATED_OPCODE)ins.op) + "(r" + std::to_string(ins.a) + ",r" + std::to_string(ins.b) + ")";
+        }
+        line += " } out r" + std::to_string(st.prog.outputs[0].reg);
+      } else {
+        for (size_t k = 0; k < st.in_nodes.size(); ++k) line += " n" + std::to_string(st.in_nodes[k]) + (st.in_offsets[k] ? "+" + std::to_string(st.in_offsets[k]) : "");
+        for (int dnode : st.dep_nodes) line += " ~n" + std::to_string(dnode);
+      }
+    }
+    out.push_back(line);
+  }
   return out;
 }
 
