@@ -312,6 +312,15 @@ int tcr_reverse(const void* in, void* out, const int64_t shape[8], uint32_t reve
 /* CONCAT along `axis` (operator.hpp:336-368): binary concatenation of arbitrary axis
  * extents, or n-ary where every arg has extent 1 along axis. `shapes` = nargs x 8. */
 int tcr_concat(const void* const* args, const int64_t* shapes, int nargs, void* out, int axis, int elem_size);
+/* `count` strided 2-D copies (rows x row_bytes, byte pitches) in one launch. CONCAT along any rank is one such copy per operand
+ * (rows = product of the ranks above the axis, row_bytes = that operand's run along and below it): the per-time-step CONCATs of
+ * an unrolled recurrent layer (operator.hpp:336-368, one Eigen assignment each) become one launch. */
+typedef struct {
+  void* dst;
+  const void* src;
+  int64_t row_bytes, rows, dst_pitch, src_pitch;
+} tcr_copy2d_item;
+int tcr_copy2d_batched(const tcr_copy2d_item* items, int count);
 
 /* ------------------------------------------------------------- contractions */
 

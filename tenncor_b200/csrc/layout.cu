@@ -7,6 +7,8 @@
 // go through a 32x32 shared-memory tile so that both the read and the write coalesce.
 #include <vector>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace tcr {
@@ -126,6 +128,32 @@ __global__ void __launch_bounds__(256) transpose_vec_kernel(const E* __restrict_
 }
 
 // concat: copy one argument (shape [inner, ext, outer]) into out at axis offset `off`
+// Many strided 2-D copies in one launch (blockIdx.y = item): the [x_t | h_{t-1}] operands of every time step of an unrolled
+// recurrent layer (cfg/tenncor/layer.yml:716-813 builds one CONCAT per step) are laid down after the forward pass in one go.
+constexpr int COPY2D_MAX = 512;
+struct Copy2dItemDev {
+  char* dst;
+  const char* src;
+  uint32_t row_bytes, rows;
+  int64_t dst_pitch, src_pitch;
+};
+struct Copy2dBatch {
+  int32_t count;
+  Copy2dItemDev it[COPY2D_MAX];
+};
+template <typename V>
+__global__ void __launch_bounds__(256) copy2d_batched_kernel(const __grid_constant__ Copy2dBatch b) {
+  TCR_PDL_ENTER();
+  const Copy2dItemDev& it = b.it[blockIdx.y];
+  const uint32_t per_row = it.row_bytes / (uint32_t)sizeof(V);
+  const uint32_t total = per_row * it.rows;
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+    const uint32_t r = i / per_row, c = i - r * per_row;
+    *reinterpret_cast<V*>(it.dst + (int64_t)r * it.dst_pitch + (int64_t)c * sizeof(V)) =
+        *reinterpret_cast<const V*>(it.src + (int64_t)r * it.src_pitch + (int64_t)c * sizeof(V));
+  }
+}
+
 struct ConcatArgs {
   const void* ptr[32];
   int n;
@@ -398,6 +426,37 @@ int tcr_reverse(const void* in, void* out, const int64_t shape[8], uint32_t reve
   for (int k = 0; k < 8; ++k)
     if ((reverse_mask >> k) & 1u) { d.mul[k] = -1; d.add[k] = shape[k] - 1; }
   return tcr_map_copy(in, out, &d, elem_size);
+}
+
+int tcr_copy2d_batched(const tcr_copy2d_item* items, int count) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(items != nullptr && count >= 0, "tcr_copy2d_batched: bad arguments");
+  for (int k0 = 0; k0 < count; k0 += COPY2D_MAX) {
+    static Copy2dBatch b;  // 16 KB: not on the stack
+    b.count = count - k0 < COPY2D_MAX ? count - k0 : COPY2D_MAX;
+    bool vec = true;
+    int64_t most = 0;
+    for (int k = 0; k < b.count; ++k) {
+      const tcr_copy2d_item& it = items[k0 + k];
+      TCR_ARG(it.dst != nullptr && it.src != nullptr && it.row_bytes >= 0 && it.rows >= 0 && it.row_bytes < (1ll << 31) && it.rows < (1ll << 31),
+              "tcr_copy2d_batched: item %d is malformed", k0 + k);
+      b.it[k].dst = (char*)it.dst; b.it[k].src = (const char*)it.src;
+      b.it[k].row_bytes = (uint32_t)it.row_bytes; b.it[k].rows = (uint32_t)it.rows;
+      b.it[k].dst_pitch = it.dst_pitch; b.it[k].src_pitch = it.src_pitch;
+      vec = vec && ((((uintptr_t)it.dst | (uintptr_t)it.src | (uintptr_t)it.dst_pitch | (uintptr_t)it.src_pitch | (uintptr_t)it.row_bytes) & 15) == 0);
+      most = std::max<int64_t>(most, it.row_bytes * it.rows);
+    }
+    if (most == 0) continue;
+    const int unit = vec ? 16 : 1;
+    int per_item = (int)ceil_div(most / unit, (int64_t)(256 * 8));
+    if (per_item < 1) per_item = 1;
+    if (per_item > 64) per_item = 64;
+    dim3 grid((unsigned)per_item, (unsigned)b.count);
+    if (vec) TCR_LAUNCH((copy2d_batched_kernel<uint4>), grid, 256, 0, b);
+    else TCR_LAUNCH((copy2d_batched_kernel<uint8_t>), grid, 256, 0, b);
+  }
+  TCR_CHECK_LAUNCH();
+  return TCR_OK;
 }
 
 int tcr_concat(const void* const* args, const int64_t* shapes, int nargs, void* out, int axis, int elem_size) {

@@ -134,6 +134,11 @@ struct Step {
   std::vector<int> multi_outs;
   std::vector<uint8_t> multi_keep;  // 0: the result is read only by later programs of the launch and is not written to memory
   // the multi launch has the shape of a gated cell's backward step (match_cell_backward): program 0 = s, 1 = c, then the gates
+  // several CONCAT steps as one batched 2-D copy launch (batch_concat_steps): item k copies into node copy_dst[k] at byte copy_off[k]
+  bool copy_batch = false;
+  std::vector<tcr_copy2d_item> copy_items;
+  std::vector<int> copy_dst, copy_src;
+  std::vector<size_t> copy_dst_off, copy_src_off;
   bool cell_bwd = false;
   int cb_c[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // (program, input) of c_x, c_y, c_z
   int cb_kind[6] = {0, 0, 0, 0, 0, 0}, cb_sel[6] = {0, 0, 0, 0, 0, 0}, cb_x[6] = {0, 0, 0, 0, 0, 0}, cb_y[6] = {0, 0, 0, 0, 0, 0};  // gate k = program k + 2; x / y input slots
@@ -2110,6 +2115,102 @@ struct Plan {
     }
   }
 
+  // ---------------------------------------------------------------- CONCAT steps -> one batched copy
+  // An unrolled recurrent layer builds CONCAT(x_t, h_{t-1}) per time step (cfg/tenncor/layer.yml:716-813). The gate products read
+  // x_t and h_{t-1} as K-segments, so those CONCATs are needed only by the weight-gradient product at the end of the backward
+  // pass: every one of them slides down to the position of the last (same commutation rule as merge_elementwise_steps) and they
+  // run as ONE tcr_copy2d_batched launch instead of T launches of ~4.5 us.
+  void batch_concat_steps() {
+    if (std::getenv("TCR_NO_CONCAT_BATCH")) return;
+    const int ns = (int)steps.size();
+    auto candidate = [&](const Step& e) {
+      if (e.ew || e.dead || e.kind != Step::NORMAL || e.gemm_fused || e.conv_fused || e.group || e.stack_reduce || e.multi || !e.holder || !e.extra_outs.empty() ||
+          !e.dep_nodes.empty())
+        return false;
+      const PNode& o = nodes[e.out_node];
+      if (o.op != CONCAT || o.exposed || e.in_nodes.size() < 2 || o.root != e.out_node || o.offset != 0) return false;
+      if (e.in_nodes.size() > 2)  // group concat: every operand has extent one along the axis (operator.hpp:336-368)
+        for (int a : o.args)
+          if (nodes[a].shape.at(eigen::unpack_rank(*o.func)) != 1) return false;
+      return true;
+    };
+    auto contains = [](const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+    std::vector<int> group, between, g_reads, g_writes, rd, brd, bwr;
+    int n_merged = 0;
+    auto close = [&] {
+      if (group.size() >= 2) {
+        const int last = group.back();
+        Step m = steps[last];
+        m.copy_batch = true;
+        m.holder = nullptr;
+        m.in_nodes.clear();
+        m.in_offsets.clear();
+        for (int g : group) {
+          const Step& e = steps[g];
+          const PNode& o = nodes[e.out_node];
+          const int axis = eigen::unpack_rank(*o.func);
+          const size_t es = type_size(o.dtype);
+          int64_t inner = 1, outer = 1;
+          for (int r = 0; r < axis; ++r) inner *= o.shape.at(r);
+          for (int r = axis + 1; r < rank_cap; ++r) outer *= o.shape.at(r);
+          const int64_t out_row = inner * o.shape.at(axis) * (int64_t)es;
+          int64_t at = 0;
+          for (size_t k = 0; k < e.in_nodes.size(); ++k) {
+            const int64_t row = inner * nodes[o.args[k]].shape.at(axis) * (int64_t)es;
+            tcr_copy2d_item it;
+            it.dst = nullptr; it.src = nullptr;
+            it.row_bytes = row; it.rows = outer; it.dst_pitch = out_row; it.src_pitch = row;
+            m.copy_items.push_back(it);
+            m.copy_dst.push_back(e.out_node); m.copy_dst_off.push_back((size_t)at);
+            m.copy_src.push_back(e.in_nodes[k]); m.copy_src_off.push_back(e.in_offsets[k]);
+            m.in_nodes.push_back(e.in_nodes[k]); m.in_offsets.push_back(e.in_offsets[k]);
+            at += row;
+          }
+          if (g != last) { m.extra_outs.push_back(e.out_node); steps[g].dead = true; }
+        }
+        steps[last] = std::move(m);
+        ++n_merged;
+      }
+      group.clear(); between.clear(); g_reads.clear(); g_writes.clear();
+    };
+    for (int s = 0; s < ns; ++s) {
+      const Step& e = steps[s];
+      if (e.dead) continue;
+      if (!candidate(e)) { if (!group.empty()) between.push_back(s); continue; }
+      bool join = !group.empty() && group.size() < 240;
+      if (join) {
+        for (int in : e.in_nodes) if (contains(g_writes, in)) join = false;  // a CONCAT of CONCATs keeps its own launch
+        // the between-steps seen so far were checked when earlier members joined; the new ones since then:
+        for (int b : between) {
+          step_reads(steps[b], brd);
+          step_writes(steps[b], bwr);
+          for (int x : brd) if (contains(g_writes, x)) join = false;
+          for (int x : bwr) if (contains(g_writes, x) || contains(g_reads, x)) join = false;
+          if (steps[b].kind != Step::NORMAL) join = false;
+        }
+      }
+      if (!join) close();
+      else between.clear();  // verified against the group; later members add reads that these (earlier) steps cannot have written after them
+      group.push_back(s);
+      step_reads(e, rd);
+      for (int x : rd) if (!contains(g_reads, x)) g_reads.push_back(x);
+      g_writes.push_back(e.out_node);
+    }
+    close();
+    if (n_merged == 0) return;
+    std::vector<Step> kept;
+    kept.reserve(steps.size());
+    for (auto& st : steps)
+      if (!st.dead) kept.push_back(std::move(st));
+    steps = std::move(kept);
+    for (auto& n : nodes) n.step = -1;
+    for (size_t k = 0; k < steps.size(); ++k) {
+      if (steps[k].kind == Step::BUCKET_FLUSH) continue;
+      nodes[steps[k].out_node].step = (int)k;
+      for (int e : steps[k].extra_outs) nodes[e].step = (int)k;
+    }
+  }
+
   // Reads / write of a step in terms of storage roots (before buffers exist)
   void step_access(const Step& st, std::vector<int>& reads, std::vector<int>& writes) const {
     step_reads(st, reads);
@@ -2379,6 +2480,11 @@ struct Plan {
           if (!in.ptr) global::fatalf("planner: input %s of %s was never materialised", in.tens->to_string().c_str(), out.tens->to_string().c_str());
           st.in.push_back((const char*)in.ptr + st.in_offsets[k]);
         }
+        if (st.copy_batch)
+          for (size_t k = 0; k < st.copy_items.size(); ++k) {
+            st.copy_items[k].dst = (char*)nodes[st.copy_dst[k]].ptr + st.copy_dst_off[k];
+            st.copy_items[k].src = (const char*)nodes[st.copy_src[k]].ptr + st.copy_src_off[k];
+          }
         if (st.group) {
           tcr_gemm_group_desc& gd = st.gd;
           size_t k = 0;
@@ -2405,6 +2511,8 @@ struct Plan {
             "tcr_allreduce_sum");
     } else if (st.kind == Step::BUCKET_MEMBER) {
       if (!st.member_in_place) check(tcr_d2d(st.out, st.in[0], (size_t)nodes[st.out_node].n * type_size(nodes[st.out_node].dtype)), "tcr_d2d");
+    } else if (st.copy_batch) {
+      check(tcr_copy2d_batched(st.copy_items.data(), (int)st.copy_items.size()), "tcr_copy2d_batched");
     } else if (st.cell_bwd) {
       tcr_cell_backward_desc d;
       std::memset(&d, 0, sizeof(d));
@@ -2517,6 +2625,18 @@ struct Plan {
       std::sort(d.begin(), d.end());
       d.erase(std::unique(d.begin(), d.end()), d.end());
     }
+    // A plan that is one long dependent chain (an unrolled recurrent layer: ~520 of C4's 569 steps) gains nothing from lanes and
+    // pays for the cross-lane event nodes of the few steps beside it (C4: 6.89 ms on 4 lanes, 6.74 ms on one): with fewer than
+    // 1.25 steps per step of the longest chain everything is captured on lane 0.
+    {
+      std::vector<int> depth(ns, 1);
+      int longest = 1;
+      for (int s = 0; s < ns; ++s) {
+        for (int dstep : deps[s]) depth[s] = std::max(depth[s], depth[dstep] + 1);
+        longest = std::max(longest, depth[s]);
+      }
+      if (!std::getenv("TCR_GRAPH_LANES") && ns >= 64 && (double)ns < 1.25 * (double)longest) return;
+    }
     std::vector<int> lane_tail(n_lanes, -1);  // last step captured on each lane
     for (int s = 0; s < ns; ++s) {
       Step& st = steps[s];
@@ -2585,6 +2705,7 @@ struct Plan {
     build_steps();
     fuse_recurrent_steps();
     merge_elementwise_steps();
+    batch_concat_steps();
     bucket_gradients();
     if (lower_only) return;
     assign_buffers();
@@ -2631,6 +2752,7 @@ struct Plan {
     const PNode& o = nodes[st.out_node];
     std::string what = egen::name_op((_GENERATED_OPCODE)o.op);
     if (st.kind == Step::BUCKET_MEMBER) return what + " -> bucket";
+    if (st.copy_batch) return "CONCAT-BATCH(" + std::to_string(1 + st.extra_outs.size()) + ")";
     if (st.cell_bwd) return "CELL-BACKWARD(" + std::to_string(st.multi_progs.size() - 2) + " gates, " + std::to_string(st.inputs.size()) + " in)";
     if (st.multi) {
       int instrs = 0;

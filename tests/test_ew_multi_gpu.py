@@ -114,3 +114,25 @@ def test_cell_backward_is_bit_identical_to_the_separate_functors(gpu, n):
     np.testing.assert_array_equal(gpu.to_host(outs["s"], n, np.float32), np.full(n, 3.0, np.float32))  # NULL s_out: not stored
     for k in range(3):
         np.testing.assert_array_equal(gpu.to_host(outs["o%d" % k], n, np.float32), want[k])
+
+
+def test_copy2d_batched_lays_down_concats(gpu):
+    """CONCAT(x_t, h_t) for several t as one launch of strided 2-D copies (operator.hpp:336-368 semantics per pair)."""
+    rng = np.random.default_rng(2)
+    T, B, KX, KH = 5, 7, 12, 20  # rows of 48 / 80 bytes: 16-byte path; second case below is unaligned
+    for kx, kh in ((KX, KH), (3, 5)):
+        xs = rng.uniform(-1, 1, (T, B, kx)).astype(np.float32)
+        hs = rng.uniform(-1, 1, (T, B, kh)).astype(np.float32)
+        dx, dh = gpu.to_device(xs), gpu.to_device(hs)
+        out = gpu.to_device(np.zeros((T, B, kx + kh), np.float32))
+
+        class Item(C.Structure):
+            _fields_ = [("dst", C.c_void_p), ("src", C.c_void_p), ("row_bytes", C.c_int64), ("rows", C.c_int64), ("dst_pitch", C.c_int64), ("src_pitch", C.c_int64)]
+        items = (Item * (2 * T))()
+        for t in range(T):
+            base = out.ptr + 4 * t * B * (kx + kh)
+            items[2 * t] = Item(base, dx.ptr + 4 * t * B * kx, 4 * kx, B, 4 * (kx + kh), 4 * kx)
+            items[2 * t + 1] = Item(base + 4 * kx, dh.ptr + 4 * t * B * kh, 4 * kh, B, 4 * (kx + kh), 4 * kh)
+        gpu.check(gpu.lib().tcr_copy2d_batched(items, 2 * T))
+        got = gpu.to_host(out, T * B * (kx + kh), np.float32).reshape(T, B, kx + kh)
+        np.testing.assert_array_equal(got, np.concatenate([xs, hs], axis=2))

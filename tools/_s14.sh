@@ -1,5 +1,4 @@
-timeout 600 python -m pytest tests/test_ew_multi_gpu.py tests/test_train_gpu.py tests/test_fullsize_parity_gpu.py -m gpu -x -q 2>&1 | tail -3
+for c in fwd bwd; do TCR_RNN_DEBUG=1 timeout 100 python tools/rnn_gemm_bench.py $c 2 2>&1 | tail -2; done
 run() { timeout 200 python bench.py --workload $1 --steps $2 --warmup 3 --cpu-seconds 0 --extras none 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['launches_per_step'], d['e2e']['ms_per_step'], d['final_loss'])"; }
 echo c4; run c4 5
-echo c4 lanes1; TCR_GRAPH_LANES=1 run c4 5
-echo c4gru; run c4gru 5
+echo c3; run c3 20
