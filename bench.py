@@ -230,10 +230,25 @@ def hbm_micro(cabi, peaks):
     P = lambda x, off=0: C.c_void_p(x.ptr + 4 * off)  # noqa: E731
     res = {}
 
-    def timeit(fn, iters):
+    def timeit(fn, iters, graph=False):
+        """graph=True: the launches are captured once and replayed — for kernels of a few microseconds, where the host's launch rate
+        (ctypes + cudaLaunchKernel, ~5 us) and not the device would otherwise be what is measured"""
         for i in range(2):
             fn(i)
         cabi.sync()
+        if graph:
+            g = C.c_void_p()
+            cabi.check(lib.tcr_graph_begin())
+            for i in range(iters):
+                fn(i)
+            cabi.check(lib.tcr_graph_end(C.byref(g)))
+            cabi.check(lib.tcr_graph_launch(g))
+            cabi.sync()
+            start()
+            cabi.check(lib.tcr_graph_launch(g))
+            ms = stop_ms() / iters
+            cabi.check(lib.tcr_graph_destroy(g))
+            return ms
         start()
         for i in range(iters):
             fn(i)
@@ -275,22 +290,23 @@ def hbm_micro(cabi, peaks):
     # layout
     side = 8192
     order = (C.c_int32 * 8)(1, 0, 2, 3, 4, 5, 6, 7)
-    rec("PERMUTE10_[8192,8192]", timeit(lambda i: cabi.check(lib.tcr_permute(P(a, (i % 4) * side * side), P(out, (i % 4) * side * side), cabi.shape8([side, side]), order, 4)), 10), 8 * side * side)
+    rec("PERMUTE10_[8192,8192]", timeit(lambda i: cabi.check(lib.tcr_permute(P(a, (i % 4) * side * side), P(out, (i % 4) * side * side), cabi.shape8([side, side]), order, 4)), 10, graph=True), 8 * side * side)
     bc = (C.c_int64 * 8)(1, 65536, 1, 1, 1, 1, 1, 1)
-    rec("EXTEND_[1024]->[1024,65536]", timeit(lambda i: cabi.check(lib.tcr_extend(P(a), P(out, (i % 4) << 26), cabi.shape8([1024]), bc, 4)), 10), 4 * 1024 * 65536 + 4096)
+    rec("EXTEND_[1024]->[1024,65536]", timeit(lambda i: cabi.check(lib.tcr_extend(P(a), P(out, (i % 4) << 26), cabi.shape8([1024]), bc, 4)), 10, graph=True), 4 * 1024 * 65536 + 4096)
     s3 = [1024, 128, 64]
     m3 = 1024 * 128 * 64
     offs = (C.c_int64 * 8)(0, 32, 0, 0, 0, 0, 0, 0)
     exts = (C.c_int64 * 8)(1024, 64, 64, 1, 1, 1, 1, 1)
-    rec("SLICE_mid_[1024,128,64]", timeit(lambda i: cabi.check(lib.tcr_slice(P(a, (i % 8) * m3), P(out, (i % 8) * m3), cabi.shape8(s3), offs, exts, 4)), 16), 8 * (m3 // 2))
+    rec("SLICE_mid_[1024,128,64]", timeit(lambda i: cabi.check(lib.tcr_slice(P(a, (i % 8) * m3), P(out, (i % 8) * m3), cabi.shape8(s3), offs, exts, 4)), 16, graph=True), 8 * (m3 // 2))
     lo = (C.c_int64 * 8)(0, 16, 0, 0, 0, 0, 0, 0)
-    rec("PAD_mid_[1024,128,64]", timeit(lambda i: cabi.check(lib.tcr_pad(P(a, (i % 8) * m3), P(out, (i % 8) * 2 * m3), cabi.shape8(s3), lo, lo, 4)), 16), 4 * (m3 + 1024 * 160 * 64))
+    rec("PAD_mid_[1024,128,64]", timeit(lambda i: cabi.check(lib.tcr_pad(P(a, (i % 8) * m3), P(out, (i % 8) * 2 * m3), cabi.shape8(s3), lo, lo, 4)), 16, graph=True), 4 * (m3 + 1024 * 160 * 64))
     shp2 = (C.c_int64 * 16)(*(cabi.shape8(s3)[:] + cabi.shape8(s3)[:]))
     tabs = [(C.c_void_p * 2)(a.ptr + 4 * (i % 8) * m3, b.ptr + 4 * (i % 8) * m3) for i in range(8)]
-    rec("CONCAT_axis1_[1024,128,64]x2", timeit(lambda i: cabi.check(lib.tcr_concat(tabs[i % 8], shp2, 2, P(out, (i % 8) * 2 * m3), 1, 4)), 16), 16 * m3)
+    rec("CONCAT_axis1_[1024,128,64]x2", timeit(lambda i: cabi.check(lib.tcr_concat(tabs[i % 8], shp2, 2, P(out, (i % 8) * 2 * m3), 1, 4)), 16, graph=True), 16 * m3)
     res["_note"] = {"peak_GBps": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                     "bytes": "algorithmic: 4*(inputs un-broadcast + outputs) per element (SURVEY.md §8d)",
-                    "cache": "operands exceed L2 (126 MB) or rotate over disjoint copies"}
+                    "cache": "operands exceed L2 (126 MB) or rotate over disjoint copies",
+                    "timing": "CUDA events on the library stream; layout cases (< 0.1 ms per launch) are captured in one CUDA graph and replayed"}
     del bufs, a, b, c, out, seed, small
     return res
 

@@ -567,6 +567,55 @@ __global__ void __launch_bounds__(VM_MULTI_THREADS) ew_vm_multi_kernel(const __g
   }
 }
 
+// ------------------------------------------------------------------ byte pixels -> float (CAST [* constant])
+// The input of an image model arrives as UINT8 and is cast (and scaled by 1/255) on the device (tenncor/eteq/caster.hpp:10-44 +
+// a MUL by a constant): 16 pixels per thread, one 16-byte load and four 16-byte stores, instead of four byte loads per thread.
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t n, float scale, int scaled) {
+  TCR_PDL_ENTER();
+  const int64_t nvec = n / 16, stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += stride) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    const uint32_t word[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 f;
+      f.x = (float)(word[q] & 0xffu); f.y = (float)((word[q] >> 8) & 0xffu); f.z = (float)((word[q] >> 16) & 0xffu); f.w = (float)(word[q] >> 24);
+      if (scaled) { f.x = __fmul_rn(f.x, scale); f.y = __fmul_rn(f.y, scale); f.z = __fmul_rn(f.z, scale); f.w = __fmul_rn(f.w, scale); }
+      reinterpret_cast<float4*>(out)[i * 4 + q] = f;
+    }
+  }
+  for (int64_t i = nvec * 16 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+    const float f = (float)in[i];
+    out[i] = scaled ? __fmul_rn(f, scale) : f;
+  }
+}
+
+// program == (float)u8 [* c] ?  (registers traced symbolically: 0 unknown, 1 the input, 2 a constant, 3 input * constant)
+static bool match_pixel_cast(const tcr_ew_program* prog, float* scale, int* scaled) {
+  if (prog->dtype != TCR_FLOAT || prog->n_inputs != 1 || prog->n_outputs != 1 || prog->n_instrs > 4) return false;
+  const tcr_ew_input& in = prog->inputs[0];
+  if (in.dtype != TCR_UINT8 || prog->outputs[0].dtype != TCR_FLOAT) return false;
+  if ((in.bcast[0] && prog->dims[0] > 1) || (in.bcast[1] && prog->dims[1] > 1) || (in.bcast[2] && prog->dims[2] > 1)) return false;
+  int kind[TCR_EW_NREGS] = {0};
+  float cst[TCR_EW_NREGS] = {0};
+  kind[0] = 1;
+  for (int i = 0; i < prog->n_instrs; ++i) {
+    const tcr_ew_instr& ins = prog->instrs[i];
+    if (ins.dst >= TCR_EW_NREGS || ins.a >= TCR_EW_NREGS || ins.b >= TCR_EW_NREGS) return false;
+    if (ins.op == TCR_EW_CONST) { kind[ins.dst] = 2; cst[ins.dst] = (float)ins.imm; }
+    else if (ins.op == TCR_EW_MOV) { const int k = kind[ins.a]; const float c = cst[ins.a]; kind[ins.dst] = k; cst[ins.dst] = c; }
+    else if (ins.op == TCR_EW_MUL && ((kind[ins.a] == 1 && kind[ins.b] == 2) || (kind[ins.a] == 2 && kind[ins.b] == 1))) {
+      const float c = kind[ins.a] == 2 ? cst[ins.a] : cst[ins.b];
+      kind[ins.dst] = 3; cst[ins.dst] = c;
+    } else return false;
+  }
+  const int r = prog->outputs[0].reg;
+  if (r >= TCR_EW_NREGS || (kind[r] != 1 && kind[r] != 3)) return false;
+  *scaled = kind[r] == 3;
+  *scale = cst[r];
+  return aligned16(in.ptr) && aligned16(prog->outputs[0].ptr);
+}
+
 // ------------------------------------------------------------------ gated-cell backward (tcr_cell_backward)
 struct CellBwdParams {
   uint32_t n;
@@ -1319,6 +1368,18 @@ int tcr_elementwise(const tcr_ew_program* prog) {
         if (ar == 2) return direct_binary<T>(ins.op, a, b, out, n);
         return launch_direct<T, TCR_EW_SELECT, 3>(a, b, c, out, n);
       });
+    }
+  }
+  {
+    float scale = 1.f;
+    int scaled = 0;
+    if (match_pixel_cast(prog, &scale, &scaled)) {
+      const int64_t n = prog->dims[0] * prog->dims[1] * prog->dims[2];
+      if (n == 0) return TCR_OK;
+      const int grid = wave_grid(ceil_div(n, (int64_t)16), 256, 8);
+      TCR_LAUNCH(u8_to_f32_kernel, grid, 256, 0, (const uint8_t*)prog->inputs[0].ptr, (float*)prog->outputs[0].ptr, n, scale, scaled);
+      TCR_CHECK_LAUNCH();
+      return TCR_OK;
     }
   }
   TCR_DISPATCH_COMPUTE(prog->dtype, T, {

@@ -154,6 +154,43 @@ __global__ void __launch_bounds__(256) copy2d_batched_kernel(const __grid_consta
   }
 }
 
+// SLICE / PAD along ONE rank (the recurrent layers' per-step slices, conv2d's zero border along a fresh rank): the tensor is
+// `outer` rows; an output row is [zeros lo | data | zeros hi] of a window of the input row. 16-byte vectors, one division per vector
+// (tcr_map_copy spends a div/mod chain over eight ranks per element: 49-52 % of the copy bandwidth on [1024,128,64]).
+__global__ void __launch_bounds__(256) row_window_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t out_row, uint32_t lo, uint32_t data,
+                                                          int64_t in_row, int64_t in_off, int64_t total) {
+  TCR_PDL_ENTER();
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / out_row;
+    const uint32_t c = (uint32_t)(i - r * out_row);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (c >= lo && c - lo < data) v = in[r * in_row + in_off + (c - lo)];
+    out[i] = v;
+  }
+}
+
+// one rank differs between the two shapes -> (outer rows, bytes per row below and along that rank); false otherwise
+static bool single_rank(const int64_t a[8], const int64_t b[8], int* rank) {
+  int found = -1;
+  for (int k = 0; k < 8; ++k)
+    if (a[k] != b[k]) { if (found >= 0) return false; found = k; }
+  *rank = found;
+  return found >= 0;
+}
+static bool launch_row_window(const void* in, void* out, const int64_t in_shape[8], int rank, int64_t window_off, int64_t window, int64_t lo, int64_t hi, int elem_size) {
+  int64_t inner = elem_size, outer = 1;
+  for (int k = 0; k < rank; ++k) inner *= in_shape[k];
+  for (int k = rank + 1; k < 8; ++k) outer *= in_shape[k];
+  const int64_t in_row = inner * in_shape[rank], off = inner * window_off, data = inner * window, lo_b = inner * lo, out_row = inner * (lo + window + hi);
+  if (((in_row | off | data | lo_b | out_row) & 15) != 0 || (((uintptr_t)in | (uintptr_t)out) & 15) != 0) return false;
+  if (out_row / 16 >= (1ll << 32) || outer * out_row == 0) return false;
+  const int64_t total = outer * out_row / 16;
+  const int grid = wave_grid(total, 256, 8);
+  TCR_LAUNCH(row_window_kernel, grid, 256, 0, (const uint4*)in, (uint4*)out, (uint32_t)(out_row / 16), (uint32_t)(lo_b / 16), (uint32_t)(data / 16), in_row / 16, off / 16, total);
+  return true;
+}
+
 struct ConcatArgs {
   const void* ptr[32];
   int n;
@@ -381,6 +418,14 @@ int tcr_slice(const void* in, void* out, const int64_t in_shape[8], const int64_
   tcr_map_desc d;
   for (int k = 0; k < 8; ++k)
     TCR_ARG(offsets[k] >= 0 && extents[k] >= 1 && offsets[k] + extents[k] <= in_shape[k], "tcr_slice: box out of range at rank %d", k);
+  {
+    int rank = -1;
+    TCR_REQUIRE_DEVICE();
+    if (single_rank(in_shape, extents, &rank) && launch_row_window(in, out, in_shape, rank, offsets[rank], extents[rank], 0, 0, elem_size)) {
+      TCR_CHECK_LAUNCH();
+      return TCR_OK;
+    }
+  }
   identity_desc(&d, in_shape, extents);
   for (int k = 0; k < 8; ++k) d.add[k] = offsets[k];
   return tcr_map_copy(in, out, &d, elem_size);
@@ -392,6 +437,14 @@ int tcr_pad(const void* in, void* out, const int64_t in_shape[8], const int64_t 
   for (int k = 0; k < 8; ++k) {
     TCR_ARG(pad_lo[k] >= 0 && pad_hi[k] >= 0, "tcr_pad: negative padding");
     out_shape[k] = in_shape[k] + pad_lo[k] + pad_hi[k];
+  }
+  {
+    int rank = -1;
+    TCR_REQUIRE_DEVICE();
+    if (single_rank(in_shape, out_shape, &rank) && launch_row_window(in, out, in_shape, rank, 0, in_shape[rank], pad_lo[rank], pad_hi[rank], elem_size)) {
+      TCR_CHECK_LAUNCH();
+      return TCR_OK;
+    }
   }
   identity_desc(&d, in_shape, out_shape);
   for (int k = 0; k < 8; ++k) d.add[k] = -pad_lo[k];

@@ -157,6 +157,62 @@ __global__ void __launch_bounds__(256) reduce_cols(const T* __restrict__ in, T* 
   }
 }
 
+// 16-byte variant of reduce_cols for 4-byte elements: a thread owns FOUR adjacent kept columns, a warp reads 512 contiguous
+// bytes of a row (128-byte reads at a 16 KB row stride ran at 50 % of the copy bandwidth on [4096, 65536]).
+// block = (32, 8); grid = (ceil(Kin/128), S, Kout)
+template <typename T, int OP>
+__global__ void __launch_bounds__(256) reduce_cols_v4(const T* __restrict__ in, T* __restrict__ out, int64_t Kin, int64_t R, int64_t chunk, int S) {
+  static_assert(sizeof(T) == 4, "16-byte loads of four elements");
+  TCR_PDL_ENTER();
+  struct alignas(16) Q { T v[4]; };
+  __shared__ Q tile[8][33];
+  const int64_t ki = ((int64_t)blockIdx.x * 32 + threadIdx.x) * 4;
+  const int s = blockIdx.y;
+  const int64_t ko = blockIdx.z;
+  const int64_t lo = (int64_t)s * chunk, hi = lo + chunk < R ? lo + chunk : R;
+  Q acc, a1;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) acc.v[v] = a1.v[v] = Red<T, OP>::init();
+  if (ki < Kin) {
+    const T* base = in + ki + Kin * (R * ko);
+    int64_t r = lo + threadIdx.y;
+    for (; r + 24 < hi; r += 32) {
+      const Q x0 = *reinterpret_cast<const Q*>(base + Kin * r), x1 = *reinterpret_cast<const Q*>(base + Kin * (r + 8)),
+              x2 = *reinterpret_cast<const Q*>(base + Kin * (r + 16)), x3 = *reinterpret_cast<const Q*>(base + Kin * (r + 24));
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        acc.v[v] = Red<T, OP>::op(acc.v[v], Red<T, OP>::op(x0.v[v], x1.v[v]));
+        a1.v[v] = Red<T, OP>::op(a1.v[v], Red<T, OP>::op(x2.v[v], x3.v[v]));
+      }
+    }
+    for (; r < hi; r += 8) {
+      const Q x = *reinterpret_cast<const Q*>(base + Kin * r);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc.v[v] = Red<T, OP>::op(acc.v[v], x.v[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc.v[v] = Red<T, OP>::op(acc.v[v], a1.v[v]);
+  }
+  tile[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && ki < Kin) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc.v[v] = Red<T, OP>::op(acc.v[v], tile[y][threadIdx.x].v[v]);
+    *reinterpret_cast<Q*>(out + ki + Kin * ((int64_t)s + (int64_t)S * ko)) = acc;
+  }
+}
+
+template <typename T, int OP, bool FOUR = sizeof(T) == 4>
+struct ColsV4 {
+  static void launch(dim3 grid, const T* in, T* out, int64_t Kin, int64_t R, int64_t chunk, int S) { TCR_LAUNCH((reduce_cols_v4<T, OP>), grid, dim3(32, 8), 0, in, out, Kin, R, chunk, S); }
+};
+template <typename T, int OP>
+struct ColsV4<T, OP, false> {
+  static void launch(dim3, const T*, T*, int64_t, int64_t, int64_t, int) {}
+};
+
 // ---- generic: arbitrary mask, one thread per output element
 struct GenericDesc {
   int64_t shape[8];
@@ -233,7 +289,9 @@ template <typename T, int OP>
 static int run_cols(const T* in, T* out, int64_t Kin, int64_t R, int64_t Kout) {
   State& st = state();
   TCR_ARG(Kout <= 65535, "tcr_reduce: kept-outer extent %lld exceeds grid.z", (long long)Kout);
-  int64_t bx = ceil_div(Kin, 32);
+  // four columns per thread when the rows are 16-byte aligned runs of 4-byte elements
+  const bool v4 = sizeof(T) == 4 && (Kin % 4) == 0 && Kin >= 128 && ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
+  int64_t bx = ceil_div(Kin, v4 ? 128 : 32);
   int64_t base_blocks = bx * Kout;
   int64_t want = (int64_t)st.sm_count * 8;
   int64_t S = 1;
@@ -247,14 +305,16 @@ static int run_cols(const T* in, T* out, int64_t Kin, int64_t R, int64_t Kout) {
   int64_t chunk = ceil_div(R, S);
   S = ceil_div(R, chunk);
   if (S == 1) {
-    TCR_LAUNCH((reduce_cols<T, OP>), dim3((unsigned)bx, 1, (unsigned)Kout), dim3(32, 8), 0, in, out, Kin, R, chunk, 1);
+    if (v4) ColsV4<T, OP>::launch(dim3((unsigned)bx, 1, (unsigned)Kout), in, out, Kin, R, chunk, 1);
+    else TCR_LAUNCH((reduce_cols<T, OP>), dim3((unsigned)bx, 1, (unsigned)Kout), dim3(32, 8), 0, in, out, Kin, R, chunk, 1);
     TCR_CHECK_LAUNCH();
     return TCR_OK;
   }
   void* part = nullptr;
   int rc = tcr_alloc(&part, sizeof(T) * (size_t)(Kin * S * Kout));
   if (rc) return rc;
-  TCR_LAUNCH((reduce_cols<T, OP>), dim3((unsigned)bx, (unsigned)S, (unsigned)Kout), dim3(32, 8), 0, in, (T*)part, Kin, R, chunk, (int)S);
+  if (v4) ColsV4<T, OP>::launch(dim3((unsigned)bx, (unsigned)S, (unsigned)Kout), in, (T*)part, Kin, R, chunk, (int)S);
+  else TCR_LAUNCH((reduce_cols<T, OP>), dim3((unsigned)bx, (unsigned)S, (unsigned)Kout), dim3(32, 8), 0, in, (T*)part, Kin, R, chunk, (int)S);
   TCR_CHECK_LAUNCH();
   rc = run_cols<T, OP>((const T*)part, out, Kin, S, Kout);
   tcr_free(part);

@@ -136,3 +136,20 @@ def test_copy2d_batched_lays_down_concats(gpu):
         gpu.check(gpu.lib().tcr_copy2d_batched(items, 2 * T))
         got = gpu.to_host(out, T * B * (kx + kh), np.float32).reshape(T, B, kx + kh)
         np.testing.assert_array_equal(got, np.concatenate([xs, hs], axis=2))
+
+
+@pytest.mark.parametrize("n", [8192 * 784, 1000003, 17, 5])
+def test_pixel_cast_and_scale(gpu, n):
+    """(float)u8 * c — CAST of a UINT8 variable (tenncor/eteq/caster.hpp:10-44) folded into the MUL that scales it: bit-exact."""
+    F, OP = gpu.FLOAT, gpu.OP
+    rng = np.random.default_rng(n)
+    px = rng.integers(0, 256, n, dtype=np.uint8)
+    dpx, out = gpu.to_device(px), gpu.empty(n, np.float32)
+    c = np.float32(1.0 / 255.0)
+    prog = gpu.make_program(F, (n, 1, 1), [(dpx.ptr, gpu.UINT8, (0, 0, 0))], [(out.ptr, F, 0)],
+                            [(gpu.EW_MOV, 1, 0), (gpu.EW_CONST, 2, 0, 0, 0, float(c)), (OP["MUL"], 0, 1, 2)])
+    gpu.check(gpu.lib().tcr_elementwise(C.byref(prog)))
+    np.testing.assert_array_equal(gpu.to_host(out, n, np.float32), px.astype(np.float32) * c)
+    prog = gpu.make_program(F, (n, 1, 1), [(dpx.ptr, gpu.UINT8, (0, 0, 0))], [(out.ptr, F, 1)], [(gpu.EW_MOV, 1, 0)])
+    gpu.check(gpu.lib().tcr_elementwise(C.byref(prog)))
+    np.testing.assert_array_equal(gpu.to_host(out, n, np.float32), px.astype(np.float32))
