@@ -510,6 +510,16 @@ PYBIND11_MODULE(_tenncor, m) {
   eg.def("grad_add", [](const ETensorsT& elems) { return eteq::DerivativeFuncs().add(elems); });
   eg.def("is_commutative", [](const std::string& opname) { return egen::is_commutative(egen::get_op(opname)); });
   eg.def("is_idempotent", [](const std::string& opname) { return egen::is_idempotent(egen::get_op(opname)); });
+  eg.def("dtypes", [] {
+    // (name, bytes per element, conversion precision rank) in enum order, as tools/egen/plugins/dtypes.py generates them from the type file
+    std::vector<std::tuple<std::string, size_t, size_t>> out;
+    for (int t = 1; t < egen::_N_GENERATED_DTYPES; ++t) {
+      auto dt = (egen::_GENERATED_DTYPE)t;
+      out.push_back({egen::name_type(dt), (size_t)egen::type_size(dt), (size_t)egen::type_precision(dt)});
+    }
+    return out;
+  });
+  eg.def("default_dtype", [] { return egen::name_type(egen::default_dtype); });
   eg.def("opcodes", [] {
     std::vector<std::string> out;
     for (int op = 1; op < egen::_N_GENERATED_OPCODES; ++op) out.push_back(egen::name_op((egen::_GENERATED_OPCODE)op));
