@@ -397,6 +397,16 @@ typedef struct {
 } tcr_gemm_group_desc;
 
 int tcr_gemm_grouped(const tcr_gemm_group_desc* desc);
+/* `count` CONSECUTIVE TIME STEPS of a recurrent layer in ONE launch: descs[t] is the gate launch of step t (cell = 1), step
+ * t + 1 reads h_out of step t as one of its A segments and c_out of step t as its c_prev; weights, biases and extents are
+ * those of descs[0]. The CTAs stay resident over the whole sequence (tensor maps, barriers and TMEM set up once, weight tiles
+ * of step t + 1 prefetched during the epilogue of step t) and meet at a grid barrier between steps — the reference runs
+ * 4 x seq Eigen contractions + their elementwise tails one after the other (cfg/tenncor/layer.yml:716-768). prepare() builds
+ * the per-step tables in device memory once (not capturable); launch() is one kernel launch (capturable); all clusters must fit
+ * the device at once (prepare fails otherwise, and the caller keeps the per-step launches). */
+int tcr_gemm_grouped_seq_prepare(const tcr_gemm_group_desc* descs, int count, void** handle);
+int tcr_gemm_grouped_seq_launch(void* handle);
+int tcr_gemm_grouped_seq_destroy(void* handle);
 /* host-only validation of everything but the pointers (the planner asks before it commits to this lowering) */
 int tcr_gemm_grouped_check(const tcr_gemm_group_desc* desc);
 /* profiling aid (TCR_RNN_DEBUG=1): SM-clock stamps of the first CTA of the last tcr_gemm_grouped launch */

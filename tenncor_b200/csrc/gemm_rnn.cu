@@ -25,6 +25,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -69,6 +70,22 @@ struct RnnParams {
   int64_t state_pitch;
   int dbg_mode;    // TCR_RNN_EXPERIMENT: 1 = no MMAs (TMA only), 2 = no TMA loads (MMAs on whatever shared memory holds), 4 = X tile not loaded
   long long* dbg;  // TCR_RNN_DEBUG: SM-clock stamps of CTA (0,0,0), see tcr_rnn_debug_read
+};
+
+// One launch over T consecutive time steps (tcr_gemm_grouped_seq_*): what differs from step to step
+struct alignas(64) RnnStep {
+  float* out[4];
+  const float* c_prev;
+  float* c_out;
+  float* h_out;
+};
+struct RnnSeq {
+  const CUtensorMap* xmaps;  // [T][nseg] activation maps in device memory
+  const RnnStep* steps;      // [T]
+  int T;
+  uint32_t dep_segs;         // bit s: segment s of step t reads what step t - 1 wrote (h_{t-1}): its loads wait for the grid barrier
+  unsigned* bar;             // [0] arrivals (monotonic over the launch), [1] CTAs that finished; both zero between launches
+  unsigned num_ctas;
 };
 
 #define RNN_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[slot] = clock64(); } while (0)
@@ -176,8 +193,8 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("
 //      memory and c_t, h_t are written as well.
 // Everything that does not depend on the accumulator (bias, c_{t-1}) is fetched BEFORE waiting for it.
 template <int NC>
-__device__ __forceinline__ void rnn_epilogue(const RnnParams& p, uint64_t* tmem_full, uint32_t tmem_base, uint32_t red_s, uint32_t cell_s,
-                                             int num_kb, int u0, int m0, uint32_t crank) {
+__device__ __forceinline__ void rnn_epilogue(const RnnParams& p, const RnnStep& sp, uint64_t* tmem_full, uint32_t full_parity, uint64_t* tmem_empty,
+                                             uint32_t tmem_base, uint32_t red_s, uint32_t cell_s, int num_kb, int u0, int m0, uint32_t crank) {
   constexpr int CS = RN / NC;
   constexpr int CELLS = NC >= 4 ? NC / 4 : 1;  // (unit, column) pairs per thread in the cell phase
   const int t = threadIdx.x - 64, lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
@@ -188,14 +205,15 @@ __device__ __forceinline__ void rnn_epilogue(const RnnParams& p, uint64_t* tmem_
   const bool u_ok = u < p.n;
   const float bias = (u_ok && p.bias[g] != nullptr) ? __ldg(p.bias[g] + u) : 0.f;
   const int act = p.act[g];
-  float* const out = p.out[g];
+  float* const out = sp.out[g];
   const int b0 = m0 + (int)crank * NC;  // first batch row this CTA finishes
   const int ul2 = t & 31, u2 = u0 + ul2;
   float cprev[CELLS];
 #pragma unroll
   for (int i = 0; i < CELLS; ++i) {
     const int b = b0 + (t >> 5) + 4 * i;
-    cprev[i] = (p.cell && p.c_prev != nullptr && u2 < p.n && b < p.m) ? __ldg(p.c_prev + (int64_t)b * p.state_pitch + u2) : 0.f;
+    // plain load (not the read-only path): in a multi-step launch this is what the same thread stored one step earlier
+    cprev[i] = (p.cell && sp.c_prev != nullptr && u2 < p.n && b < p.m) ? sp.c_prev[(int64_t)b * p.state_pitch + u2] : 0.f;
   }
   float old[NC];
   if (p.accumulate) {
@@ -206,7 +224,7 @@ __device__ __forceinline__ void rnn_epilogue(const RnnParams& p, uint64_t* tmem_
   {
     float v[RN];
     if (num_kb > 0) {
-      mbar_wait(tmem_full, 0);
+      mbar_wait(tmem_full, full_parity);
       if (threadIdx.x == 64) RNN_STAMP(6);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -227,6 +245,11 @@ __device__ __forceinline__ void rnn_epilogue(const RnnParams& p, uint64_t* tmem_
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[half * 32 + j] += __uint_as_float(r[j]);
+      }
+      if (tmem_empty != nullptr) {  // multi-step launch: the accumulator may be overwritten by the next step's first MMA
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty);
       }
     } else {
 #pragma unroll
@@ -288,8 +311,8 @@ __device__ __forceinline__ void rnn_epilogue(const RnnParams& p, uint64_t* tmem_
         const float og = lds_f32(cell_s + (uint32_t)((p.role_out * NC + j) * 32 + ul2) * 4u);
         const int64_t at = (int64_t)b * p.state_pitch + u2;
         const float c = __fadd_rn(__fmul_rn(cand, in), __fmul_rn(cprev[i], forget));  // ADD(MUL(gate, in), MUL(state, forget)): no fma contraction
-        p.c_out[at] = c;
-        p.h_out[at] = c * og;
+        sp.c_out[at] = c;
+        sp.h_out[at] = c * og;
       }
     }
   }
@@ -302,9 +325,20 @@ struct RnnCfg {
   static constexpr int SMEM = STAGES * STAGE_BYTES + RED_BYTES + CELL_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int MODE>
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// SEQ = false: one product (tcr_gemm_grouped). SEQ = true: T dependent time steps in ONE launch (tcr_gemm_grouped_seq_*): the
+// CTAs stay resident, barriers / TMEM / tensor maps are set up once, every role keeps its ring position across steps, and
+// between steps the grid meets at a counter in global memory — the epilogue threads of a CTA publish their h_t rows and
+// arrive, the one lane that fetches activation tiles waits before its first load of a segment that reads h_{t-1} (weight
+// tiles of the next step are already on their way by then). All CTAs must be co-resident (checked by the host).
+template <int MODE, bool SEQ>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ RnnParams p) {
+gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ RnnParams p, const __grid_constant__ RnnSeq sq) {
   constexpr int STAGES = RnnCfg<MODE>::STAGES, STAGE_BYTES = RnnCfg<MODE>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -315,7 +349,8 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
   uint64_t* empty = bars + STAGES;
   uint64_t* ready = bars + 2 * STAGES;
   uint64_t* tmem_full = bars + 3 * STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 1);
+  uint64_t* tmem_empty = bars + 3 * STAGES + 1;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) RNN_STAMP(0);
@@ -324,13 +359,14 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
   const int m0 = (int)blockIdx.y * RN;                // first batch row
   const int kb_begin = (int)crank * p.kb_per_cta;
   const int num_kb = max(0, min(p.kb_per_cta, p.kb_total - kb_begin));
+  const int T = SEQ ? sq.T : 1;
 
   auto tile_w = [&](int s) { return smem + s * STAGE_BYTES; };
-  auto tile_x = [&](int s) { return smem + s * STAGE_BYTES + W_TILE; };
 
   if (threadIdx.x == 32) {  // tensor maps live in kernel parameter space: fetch them now, not inside the first TMA
     for (int i = 0; i < p.groups * p.nseg; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.w[i]) : "memory");
-    for (int i = 0; i < p.nseg; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.x[i]) : "memory");
+    if (!SEQ)
+      for (int i = 0; i < p.nseg; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.x[i]) : "memory");
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -339,6 +375,7 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
       mbar_init(&ready[s], 4);
     }
     mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -377,31 +414,52 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
       }
       const bool x_lane = lane == 4 && !(p.dbg_mode & 4);
       const uint32_t tx_bytes = (p.dbg_mode & 4) ? W_TILE : W_TILE + X_TILE;
-      int seg = 0, kl = kb_begin;  // segment of the current k-block and its index inside the segment
-      while (seg + 1 < p.nseg && kb_begin >= p.seg_kb_end[seg]) ++seg;
-      if (seg > 0) kl = kb_begin - p.seg_kb_end[seg - 1];
-      int st = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < num_kb; ++i) {
-        if (i >= STAGES && lane < 5) mbar_wait(&empty[st], phase ^ 1);
-        if (p.dbg_mode & 2) {
-          if (lane == 0) mbar_arrive(&full[st]);
-        } else {
-          if (lane == 0) mbar_expect_tx(&full[st], tx_bytes);
-          const int32_t wk = kl * RK;
-          uint8_t* const wt = tile_w(st);
-          if (w_lane) {
-            if (p.w_mn_major) tma_load_2d(&maps.w[my_map + seg], &full[st], wt + my_off, c0, wk);
-            else tma_load_2d(&maps.w[my_map + seg], &full[st], wt + my_off, wk, c1);
+      uint32_t it = 0;  // k-blocks issued by this CTA so far, over all steps: ring position
+      for (int t = 0; t < T; ++t) {
+        int seg = 0, kl = kb_begin;  // segment of the current k-block and its index inside the segment
+        while (seg + 1 < p.nseg && kb_begin >= p.seg_kb_end[seg]) ++seg;
+        if (seg > 0) kl = kb_begin - p.seg_kb_end[seg - 1];
+        bool met = !SEQ || t == 0;  // step 0 reads what was there before the launch
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int st = (int)(it % STAGES);
+          const uint32_t phase = (it / STAGES) & 1u;
+          if (it >= (uint32_t)STAGES && lane < 5) mbar_wait(&empty[st], phase ^ 1);
+          if (p.dbg_mode & 2) {
+            if (lane == 0) mbar_arrive(&full[st]);
+          } else {
+            if (lane == 0) mbar_expect_tx(&full[st], tx_bytes);
+            const int32_t wk = kl * RK;
+            uint8_t* const wt = tile_w(st);
+            if (w_lane) {
+              if (p.w_mn_major) tma_load_2d(&maps.w[my_map + seg], &full[st], wt + my_off, c0, wk);
+              else tma_load_2d(&maps.w[my_map + seg], &full[st], wt + my_off, wk, c1);
+            }
+            if (x_lane) {
+              if (SEQ && !met && ((sq.dep_segs >> seg) & 1u)) {
+                // every CTA has published its rows of h_{t-1}: arrivals >= t * CTAs (the weight boxes of this stage, and of the
+                // stages behind it, are already in flight)
+                const unsigned target = (unsigned)t * sq.num_ctas;
+                uint32_t spins = 0;
+                while (ld_acquire_gpu(sq.bar) < target)
+                  if (++spins > SPIN_LIMIT) __trap();
+                asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores of other SMs -> this TMA read
+                met = true;
+              }
+              tma_load_2d(SEQ ? &sq.xmaps[t * p.nseg + seg] : &maps.x[seg], &full[st], wt + W_TILE, wk, m0);
+            }
           }
-          if (x_lane) tma_load_2d(&maps.x[seg], &full[st], wt + W_TILE, wk, m0);
+          if (t == 0 && i == 0 && lane == 0) RNN_STAMP(2);
+          ++kl;
+          if (seg + 1 < p.nseg && kb_begin + i + 1 >= p.seg_kb_end[seg]) { ++seg; kl = 0; }
         }
-        if (i == 0 && lane == 0) RNN_STAMP(2);
-        ++kl;
-        if (seg + 1 < p.nseg && kb_begin + i + 1 >= p.seg_kb_end[seg]) { ++seg; kl = 0; }
-        if (++st == STAGES) { st = 0; phase ^= 1; }
+        if (t == 0 && lane == 0) RNN_STAMP(3);
+        if (SEQ) {  // the cluster barrier of this step's exchange counts every thread of the cluster
+          __syncwarp();
+          if (t == 0) cluster_wait();  // #1
+          cluster_arrive();
+          cluster_wait();
+        }
       }
-      if (lane == 0) RNN_STAMP(3);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -421,78 +479,110 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
       int st = 0;
       uint32_t phase = 0;
       uint64_t da0 = a_base, db0 = b_base;
-      for (int i = 0; i < num_kb; ++i) {
-        mbar_wait(MODE == 2 ? &ready[st] : &full[st], phase);
-        if (i == 0 && issuer) RNN_STAMP(4);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (p.dbg_mode & 1) {
-          if (issuer) mbar_arrive(&empty[st]);
-        } else {
-          const uint32_t acc = i != 0;
-          if (issuer) {
-#pragma unroll
-            for (int k8 = 0; k8 < RK / 8; ++k8)  // k-step k8 accumulates into accumulator k8: consecutive MMAs are independent
-              umma_tf32(tmem_base + (k8 % NACC) * RN, (MODE == 2 ? lo_step : 0) + da0 + k8 * a_step, db0 + k8 * b_step, idesc, acc | (uint32_t)(k8 >= NACC));  // 3xTF32: small terms first
-            if (MODE == 2) {
-#pragma unroll
-              for (int k8 = 0; k8 < RK / 8; ++k8) umma_tf32(tmem_base + (k8 % NACC) * RN, da0 + k8 * a_step, db0 + k8 * b_step + lo_step, idesc, 1);
-#pragma unroll
-              for (int k8 = 0; k8 < RK / 8; ++k8) umma_tf32(tmem_base + (k8 % NACC) * RN, da0 + k8 * a_step, db0 + k8 * b_step, idesc, 1);
-            }
-            umma_commit(&empty[st]);
-          }
-          __syncwarp();
+      for (int t = 0; t < T; ++t) {
+        if (SEQ && t > 0) {  // the epilogue has read the previous step's accumulator out of TMEM
+          mbar_wait(tmem_empty, (uint32_t)(t - 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        da0 += stage_step;
-        db0 += stage_step;
-        if (++st == STAGES) { st = 0; phase ^= 1; da0 = a_base; db0 = b_base; }
-      }
-      if (issuer) {
-        if (p.dbg_mode & 1) mbar_arrive(tmem_full); else umma_commit(tmem_full);
-        RNN_STAMP(5);
+        for (int i = 0; i < num_kb; ++i) {
+          mbar_wait(MODE == 2 ? &ready[st] : &full[st], phase);
+          if (t == 0 && i == 0 && issuer) RNN_STAMP(4);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (p.dbg_mode & 1) {
+            if (issuer) mbar_arrive(&empty[st]);
+          } else {
+            const uint32_t acc = i != 0;
+            if (issuer) {
+#pragma unroll
+              for (int k8 = 0; k8 < RK / 8; ++k8)  // k-step k8 accumulates into accumulator k8: consecutive MMAs are independent
+                umma_tf32(tmem_base + (k8 % NACC) * RN, (MODE == 2 ? lo_step : 0) + da0 + k8 * a_step, db0 + k8 * b_step, idesc, acc | (uint32_t)(k8 >= NACC));  // 3xTF32: small terms first
+              if (MODE == 2) {
+#pragma unroll
+                for (int k8 = 0; k8 < RK / 8; ++k8) umma_tf32(tmem_base + (k8 % NACC) * RN, da0 + k8 * a_step, db0 + k8 * b_step + lo_step, idesc, 1);
+#pragma unroll
+                for (int k8 = 0; k8 < RK / 8; ++k8) umma_tf32(tmem_base + (k8 % NACC) * RN, da0 + k8 * a_step, db0 + k8 * b_step, idesc, 1);
+              }
+              umma_commit(&empty[st]);
+            }
+            __syncwarp();
+          }
+          da0 += stage_step;
+          db0 += stage_step;
+          if (++st == STAGES) { st = 0; phase ^= 1; da0 = a_base; db0 = b_base; }
+        }
+        if (issuer) {
+          if (p.dbg_mode & 1) mbar_arrive(tmem_full); else umma_commit(tmem_full);
+          if (t == 0) RNN_STAMP(5);
+        }
+        if (SEQ) {
+          __syncwarp();
+          if (t == 0) cluster_wait();  // #1
+          cluster_arrive();
+          cluster_wait();
+        }
       }
     }
     __syncwarp();
   } else {
-    // ================= 3xTF32 converters (warps 2..5) =================
+    // ================= 3xTF32 converters (warps 2..5), then the epilogue of the step =================
     const int ct = threadIdx.x - 64;  // 0..127
-    if (MODE == 2) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int st = i % STAGES;
-        const uint32_t round = i / STAGES;
-        mbar_wait(&full[st], round & 1);
-        // the landed fp32 words are the hi operand as they are (the tensor core reads their top 19 bits); lo = x - hi
-        const uint4* src = reinterpret_cast<const uint4*>(tile_w(st));
-        uint4* dlo = reinterpret_cast<uint4*>(tile_w(st) + W_TILE + X_TILE);
+    const uint32_t red_s = smem_u32(red), cell_s = smem_u32(cellbuf);
+    uint32_t it = 0;
+    for (int t = 0; t < T; ++t) {
+      if (MODE == 2) {
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int st = (int)(it % STAGES);
+          const uint32_t round = it / STAGES;
+          mbar_wait(&full[st], round & 1);
+          // the landed fp32 words are the hi operand as they are (the tensor core reads their top 19 bits); lo = x - hi
+          const uint4* src = reinterpret_cast<const uint4*>(tile_w(st));
+          uint4* dlo = reinterpret_cast<uint4*>(tile_w(st) + W_TILE + X_TILE);
 #pragma unroll 4
-        for (int e = ct; e < (W_TILE + X_TILE) / 16; e += 128) {
-          const uint4 v = src[e];
-          uint4 lo;
-          lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
-          lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
-          lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
-          lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
-          dlo[e] = lo;
+          for (int e = ct; e < (W_TILE + X_TILE) / 16; e += 128) {
+            const uint4 v = src[e];
+            uint4 lo;
+            lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+            lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+            lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+            lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
+            dlo[e] = lo;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[st]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ready[st]);
+      }
+      // ---- exchange of the partial accumulators + final sum (see rnn_epilogue)
+      if (t == 0) cluster_wait();  // #1: every CTA of the cluster has started
+      RnnStep sp;
+      if (SEQ) {
+        sp = sq.steps[t];
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) sp.out[g] = p.out[g];
+        sp.c_prev = p.c_prev; sp.c_out = p.c_out; sp.h_out = p.h_out;
+      }
+      uint64_t* const te = SEQ ? tmem_empty : nullptr;
+      const uint32_t par = (uint32_t)t & 1u;
+      switch (csize) {
+        case 1: rnn_epilogue<64>(p, sp, tmem_full, par, te, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
+        case 2: rnn_epilogue<32>(p, sp, tmem_full, par, te, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
+        case 4: rnn_epilogue<16>(p, sp, tmem_full, par, te, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
+        case 8: rnn_epilogue<8>(p, sp, tmem_full, par, te, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
+        default: rnn_epilogue<4>(p, sp, tmem_full, par, te, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
+      }
+      if (SEQ && t + 1 < T) {
+        // this CTA's rows of h_t (and c_t, the gate activations) are stored: publish them and arrive at the grid barrier
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          __threadfence();
+          atomicAdd(sq.bar, 1u);
+        }
       }
     }
   }
-
-  // ================= exchange of the partial accumulators + final sum (see rnn_epilogue) =================
-  cluster_wait();  // #1: every CTA of the cluster has started
-  if (warp >= 2) {
-    const uint32_t red_s = smem_u32(red), cell_s = smem_u32(cellbuf);
-    switch (csize) {
-      case 1: rnn_epilogue<64>(p, tmem_full, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
-      case 2: rnn_epilogue<32>(p, tmem_full, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
-      case 4: rnn_epilogue<16>(p, tmem_full, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
-      case 8: rnn_epilogue<8>(p, tmem_full, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
-      default: rnn_epilogue<4>(p, tmem_full, tmem_base, red_s, cell_s, num_kb, u0, m0, crank); break;
-    }
-  } else {
+  if (!SEQ && warp < 2) {
+    cluster_wait();    // #1
     cluster_arrive();  // #2
     cluster_wait();
   }
@@ -500,6 +590,15 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(RN * NACC));
+  if (SEQ && threadIdx.x == 0) {
+    // the last CTA to finish leaves both counters at zero for the next launch (everybody has passed every barrier by then)
+    __threadfence();
+    if (atomicAdd(sq.bar + 1, 1u) == sq.num_ctas - 1) {
+      sq.bar[0] = 0;
+      sq.bar[1] = 0;
+      __threadfence();
+    }
+  }
   if (threadIdx.x == 0) RNN_STAMP(10);
 }
 
@@ -535,12 +634,12 @@ int check_desc(const tcr_gemm_group_desc* d, bool need_device_ptrs) {
   return TCR_OK;
 }
 
-template <int MODE>
-int launch_rnn(const RnnMaps& maps, const RnnParams& p, dim3 grid, int cluster) {
+template <int MODE, bool SEQ>
+int launch_rnn(const RnnMaps& maps, const RnnParams& p, const RnnSeq& sq, dim3 grid, int cluster, bool check_residency = false) {
   static bool configured = false;
   if (!configured) {
-    TCR_CUDA(cudaFuncSetAttribute(gemm_rnn_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RnnCfg<MODE>::SMEM));
-    TCR_CUDA(cudaFuncSetAttribute(gemm_rnn_kernel<MODE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    TCR_CUDA(cudaFuncSetAttribute(gemm_rnn_kernel<MODE, SEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, RnnCfg<MODE>::SMEM));
+    TCR_CUDA(cudaFuncSetAttribute(gemm_rnn_kernel<MODE, SEQ>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured = true;
   }
   cudaLaunchConfig_t cfg;
@@ -558,10 +657,83 @@ int launch_rnn(const RnnMaps& maps, const RnnParams& p, dim3 grid, int cluster) 
   attr[0].val.clusterDim.z = (unsigned)cluster;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  TCR_CUDA(cudaLaunchKernelEx(&cfg, gemm_rnn_kernel<MODE>, maps, p));
+  if (check_residency) {
+    // the grid barrier of the multi-step kernel needs every cluster on the machine at once
+    int max_clusters = 0;
+    cfg.numAttrs = 1;
+    TCR_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, gemm_rnn_kernel<MODE, SEQ>, &cfg));
+    const int64_t need = (int64_t)grid.x * grid.y;
+    TCR_ARG(max_clusters >= need, "tcr_gemm_grouped_seq: %lld clusters of %d CTAs do not fit the device at once (%d)", (long long)need, cluster, max_clusters);
+    return TCR_OK;
+  }
+  TCR_CUDA(cudaLaunchKernelEx(&cfg, gemm_rnn_kernel<MODE, SEQ>, maps, p, sq));
   state().launches.fetch_add(1, std::memory_order_relaxed);
   return TCR_OK;
 }
+
+// everything of a launch that does not change from time step to time step
+int build_common(const tcr_gemm_group_desc* d, RnnMaps& maps, RnnParams& p, dim3& grid, int& cluster, bool with_x_maps) {
+  std::memset(&p, 0, sizeof(p));
+  p.m = d->m;
+  p.n = d->n;
+  p.groups = d->groups;
+  p.rows_per_group = RM / d->groups;
+  p.nseg = d->segments;
+  p.w_mn_major = d->b_trans ? 0 : 1;
+  int kb = 0, rc = TCR_OK;
+  for (int s = 0; s < d->segments; ++s) {
+    kb += (int)ceil_div(d->seg_k[s], RK);
+    p.seg_kb_end[s] = kb;
+    p.w_k0[s] = 0;
+    if (with_x_maps) {
+      // activations: dims {K_s, m}, box {32 k, 64 rows}; rows beyond m are zero-filled by the TMA unit
+      rc = make_tf32_map(&maps.x[s], (const float*)d->a[s], d->seg_k[s], d->m, d->a_pitch[s], RK, RN, false);
+      if (rc) return rc;
+    }
+    for (int g = 0; g < d->groups; ++g) {
+      CUtensorMap* wm = &maps.w[g * d->segments + s];
+      if (p.w_mn_major) rc = make_tf32_map(wm, (const float*)d->b[g][s], d->n, d->seg_k[s], d->b_pitch, 32, RK, true);  // [K_s][n], n contiguous
+      else rc = make_tf32_map(wm, (const float*)d->b[g][s], d->seg_k[s], d->n, d->b_pitch, RK, (uint32_t)p.rows_per_group, false);  // [n][K_s], k contiguous
+      if (rc) return rc;
+    }
+  }
+  p.kb_total = kb;
+  for (int g = 0; g < 4; ++g) {
+    p.out[g] = g < d->groups ? (float*)d->out[g] : nullptr;
+    p.bias[g] = g < d->groups ? (const float*)d->bias[g] : nullptr;
+    p.act[g] = g < d->groups ? d->act[g] : 0;
+  }
+  p.out_pitch = d->out_pitch;
+  p.accumulate = d->accumulate;
+  p.cell = d->cell;
+  p.role_cand = d->role_cand; p.role_in = d->role_in; p.role_forget = d->role_forget; p.role_out = d->role_out;
+  p.c_prev = (const float*)d->c_prev;
+  p.c_out = (float*)d->c_out;
+  p.h_out = (float*)d->h_out;
+  p.state_pitch = d->state_pitch;
+  const int64_t tiles = ceil_div(d->n, p.rows_per_group) * ceil_div(d->m, RN);
+  TCR_ARG(tiles <= 65535, "tcr_gemm_grouped: output too large for this kernel (%lld tiles)", (long long)tiles);
+  // cluster size = split-K factor: as many CTAs as fit one wave, at least two k-blocks each
+  static const int forced = std::getenv("TCR_RNN_CLUSTER") ? std::atoi(std::getenv("TCR_RNN_CLUSTER")) : 0;
+  const int sms = state().sm_count;
+  cluster = 1;
+  for (int c = 2; c <= 8; c *= 2)  // 16 (non-portable) measured slower than 8 on the 64 x 1024 x 4096 sum (20.5 vs 15.6 us)
+    if (tiles * c <= sms && kb / c >= 2) cluster = c;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) cluster = forced;
+  while (cluster > 1 && kb < cluster) cluster /= 2;
+  p.kb_per_cta = (int)ceil_div(kb, cluster);
+  grid = dim3((unsigned)ceil_div(d->n, p.rows_per_group), (unsigned)ceil_div(d->m, RN), (unsigned)cluster);
+  return TCR_OK;
+}
+
+struct SeqHandle {
+  RnnMaps maps;
+  RnnParams p;
+  RnnSeq sq;
+  dim3 grid;
+  int cluster = 1, precision = 0;
+  void* dev = nullptr;  // one allocation: [x maps][steps][2 counters]
+};
 
 }  // namespace
 
@@ -590,42 +762,10 @@ int tcr_gemm_grouped(const tcr_gemm_group_desc* d) {
   if (rc) return rc;
   RnnMaps maps;
   RnnParams p;
-  std::memset(&p, 0, sizeof(p));
-  p.m = d->m;
-  p.n = d->n;
-  p.groups = d->groups;
-  p.rows_per_group = RM / d->groups;
-  p.nseg = d->segments;
-  p.w_mn_major = d->b_trans ? 0 : 1;
-  int kb = 0;
-  for (int s = 0; s < d->segments; ++s) {
-    kb += (int)ceil_div(d->seg_k[s], RK);
-    p.seg_kb_end[s] = kb;
-    p.w_k0[s] = 0;
-    // activations: dims {K_s, m}, box {32 k, 64 rows}; rows beyond m are zero-filled by the TMA unit
-    rc = make_tf32_map(&maps.x[s], (const float*)d->a[s], d->seg_k[s], d->m, d->a_pitch[s], RK, RN, false);
-    if (rc) return rc;
-    for (int g = 0; g < d->groups; ++g) {
-      CUtensorMap* wm = &maps.w[g * d->segments + s];
-      if (p.w_mn_major) rc = make_tf32_map(wm, (const float*)d->b[g][s], d->n, d->seg_k[s], d->b_pitch, 32, RK, true);  // [K_s][n], n contiguous
-      else rc = make_tf32_map(wm, (const float*)d->b[g][s], d->seg_k[s], d->n, d->b_pitch, RK, (uint32_t)p.rows_per_group, false);  // [n][K_s], k contiguous
-      if (rc) return rc;
-    }
-  }
-  p.kb_total = kb;
-  for (int g = 0; g < 4; ++g) {
-    p.out[g] = g < d->groups ? (float*)d->out[g] : nullptr;
-    p.bias[g] = g < d->groups ? (const float*)d->bias[g] : nullptr;
-    p.act[g] = g < d->groups ? d->act[g] : 0;
-  }
-  p.out_pitch = d->out_pitch;
-  p.accumulate = d->accumulate;
-  p.cell = d->cell;
-  p.role_cand = d->role_cand; p.role_in = d->role_in; p.role_forget = d->role_forget; p.role_out = d->role_out;
-  p.c_prev = (const float*)d->c_prev;
-  p.c_out = (float*)d->c_out;
-  p.h_out = (float*)d->h_out;
-  p.state_pitch = d->state_pitch;
+  dim3 grid;
+  int cluster = 1;
+  rc = build_common(d, maps, p, grid, cluster, true);
+  if (rc) return rc;
   static const bool debug = std::getenv("TCR_RNN_DEBUG") != nullptr;
   if (debug && g_rnn_dbg == nullptr) {
     TCR_CUDA(cudaMalloc(&g_rnn_dbg, 16 * sizeof(long long)));
@@ -634,20 +774,95 @@ int tcr_gemm_grouped(const tcr_gemm_group_desc* d) {
   p.dbg = debug ? g_rnn_dbg : nullptr;
   static const int experiment = std::getenv("TCR_RNN_EXPERIMENT") ? std::atoi(std::getenv("TCR_RNN_EXPERIMENT")) : 0;
   p.dbg_mode = experiment;
+  RnnSeq none;
+  std::memset(&none, 0, sizeof(none));
+  return d->precision == TCR_GEMM_TF32 ? launch_rnn<1, false>(maps, p, none, grid, cluster) : launch_rnn<2, false>(maps, p, none, grid, cluster);
+}
 
-  const int64_t tiles = ceil_div(d->n, p.rows_per_group) * ceil_div(d->m, RN);
-  TCR_ARG(tiles <= 65535, "tcr_gemm_grouped: output too large for this kernel (%lld tiles)", (long long)tiles);
-  // cluster size = split-K factor: as many CTAs as fit one wave, at least two k-blocks each
-  static const int forced = std::getenv("TCR_RNN_CLUSTER") ? std::atoi(std::getenv("TCR_RNN_CLUSTER")) : 0;
-  const int sms = state().sm_count;
-  int cluster = 1;
-  for (int c = 2; c <= 8; c *= 2)  // 16 (non-portable) measured slower than 8 on the 64 x 1024 x 4096 sum (20.5 vs 15.6 us)
-    if (tiles * c <= sms && kb / c >= 2) cluster = c;
-  if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) cluster = forced;
-  while (cluster > 1 && kb < cluster) cluster /= 2;
-  p.kb_per_cta = (int)ceil_div(kb, cluster);
-  dim3 grid((unsigned)ceil_div(d->n, p.rows_per_group), (unsigned)ceil_div(d->m, RN), (unsigned)cluster);
-  return d->precision == TCR_GEMM_TF32 ? launch_rnn<1>(maps, p, grid, cluster) : launch_rnn<2>(maps, p, grid, cluster);
+int tcr_gemm_grouped_seq_prepare(const tcr_gemm_group_desc* descs, int count, void** handle) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(descs != nullptr && handle != nullptr && count >= 2 && count <= 4096, "tcr_gemm_grouped_seq_prepare: 2..4096 steps");
+  *handle = nullptr;
+  const tcr_gemm_group_desc& d0 = descs[0];
+  uint32_t dep = 0;
+  for (int t = 0; t < count; ++t) {
+    const tcr_gemm_group_desc& d = descs[t];
+    int rc = check_desc(&d, true);
+    if (rc) return rc;
+    TCR_ARG(d.cell == 1 && d.accumulate == 0, "tcr_gemm_grouped_seq_prepare: steps carry the cell epilogue and do not accumulate");
+    bool same = d.m == d0.m && d.n == d0.n && d.groups == d0.groups && d.segments == d0.segments && d.b_pitch == d0.b_pitch && d.b_trans == d0.b_trans &&
+                d.precision == d0.precision && d.out_pitch == d0.out_pitch && d.state_pitch == d0.state_pitch && d.role_cand == d0.role_cand &&
+                d.role_in == d0.role_in && d.role_forget == d0.role_forget && d.role_out == d0.role_out;
+    for (int s = 0; s < d0.segments && same; ++s) {
+      same = d.seg_k[s] == d0.seg_k[s] && d.a_pitch[s] == d0.a_pitch[s];
+      for (int g = 0; g < d0.groups && same; ++g) same = d.b[g][s] == d0.b[g][s];
+    }
+    for (int g = 0; g < d0.groups && same; ++g) same = d.bias[g] == d0.bias[g] && d.act[g] == d0.act[g];
+    TCR_ARG(same, "tcr_gemm_grouped_seq_prepare: step %d differs from step 0 in more than its activations and outputs", t);
+    if (t > 0) {
+      // which segments read the previous step's h; the state must be the previous step's c (the same thread re-reads what it stored)
+      uint32_t mine = 0;
+      for (int s = 0; s < d.segments; ++s)
+        if (d.a[s] == descs[t - 1].h_out) mine |= 1u << s;
+      TCR_ARG(t == 1 || mine == dep, "tcr_gemm_grouped_seq_prepare: step %d chains through other segments than step 1", t);
+      dep = mine;
+      TCR_ARG(d.c_prev == descs[t - 1].c_out, "tcr_gemm_grouped_seq_prepare: step %d does not continue the state of step %d", t, t - 1);
+      for (int s = 0; s < d.segments; ++s)
+        for (int q = 0; q < t - 1; ++q)
+          TCR_ARG(d.a[s] != descs[q].h_out && d.a[s] != descs[q].c_out, "tcr_gemm_grouped_seq_prepare: step %d reads the output of step %d", t, q);
+    }
+  }
+  TCR_ARG(dep != 0, "tcr_gemm_grouped_seq_prepare: the steps are not chained");
+  SeqHandle* h = new SeqHandle();
+  int rc = build_common(&d0, h->maps, h->p, h->grid, h->cluster, false);
+  if (rc) { delete h; return rc; }
+  h->precision = d0.precision;
+  const size_t maps_bytes = sizeof(CUtensorMap) * (size_t)count * d0.segments, steps_bytes = sizeof(RnnStep) * (size_t)count;
+  std::vector<CUtensorMap> xm((size_t)count * d0.segments);
+  std::vector<RnnStep> st((size_t)count);
+  for (int t = 0; t < count; ++t) {
+    const tcr_gemm_group_desc& d = descs[t];
+    for (int s = 0; s < d.segments; ++s) {
+      rc = make_tf32_map(&xm[(size_t)t * d.segments + s], (const float*)d.a[s], d.seg_k[s], d.m, d.a_pitch[s], RK, RN, false);
+      if (rc) { delete h; return rc; }
+    }
+    for (int g = 0; g < 4; ++g) st[t].out[g] = g < d.groups ? (float*)d.out[g] : nullptr;
+    st[t].c_prev = (const float*)d.c_prev;
+    st[t].c_out = (float*)d.c_out;
+    st[t].h_out = (float*)d.h_out;
+  }
+  char* dev = nullptr;
+  if (cudaMalloc(&dev, maps_bytes + steps_bytes + 256) != cudaSuccess) { delete h; set_error("tcr_gemm_grouped_seq_prepare: out of device memory"); return TCR_ERR_CUDA; }
+  h->dev = dev;
+  cudaMemcpy(dev, xm.data(), maps_bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(dev + maps_bytes, st.data(), steps_bytes, cudaMemcpyHostToDevice);
+  cudaMemset(dev + maps_bytes + steps_bytes, 0, 256);
+  h->sq.xmaps = reinterpret_cast<const CUtensorMap*>(dev);
+  h->sq.steps = reinterpret_cast<const RnnStep*>(dev + maps_bytes);
+  h->sq.T = count;
+  h->sq.dep_segs = dep;
+  h->sq.bar = reinterpret_cast<unsigned*>(dev + maps_bytes + steps_bytes);
+  h->sq.num_ctas = h->grid.x * h->grid.y * h->grid.z;
+  rc = h->precision == TCR_GEMM_TF32 ? launch_rnn<1, true>(h->maps, h->p, h->sq, h->grid, h->cluster, true)
+                                     : launch_rnn<2, true>(h->maps, h->p, h->sq, h->grid, h->cluster, true);
+  if (rc) { cudaFree(dev); delete h; return rc; }
+  *handle = h;
+  return TCR_OK;
+}
+
+int tcr_gemm_grouped_seq_launch(void* handle) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(handle != nullptr, "tcr_gemm_grouped_seq_launch: null handle");
+  SeqHandle* h = (SeqHandle*)handle;
+  return h->precision == TCR_GEMM_TF32 ? launch_rnn<1, true>(h->maps, h->p, h->sq, h->grid, h->cluster) : launch_rnn<2, true>(h->maps, h->p, h->sq, h->grid, h->cluster);
+}
+
+int tcr_gemm_grouped_seq_destroy(void* handle) {
+  if (handle == nullptr) return TCR_OK;
+  SeqHandle* h = (SeqHandle*)handle;
+  if (h->dev) cudaFree(h->dev);
+  delete h;
+  return TCR_OK;
 }
 
 }  // extern "C"

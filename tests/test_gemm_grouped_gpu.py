@@ -179,3 +179,16 @@ def test_deterministic(gpu):
     again = run_grouped(gpu, A, B, None, [0] * 4, 0, 2)
     for x, y in zip(first, again):
         assert np.array_equal(x, y)
+
+
+def test_sequence_launch_is_bit_identical_to_per_step_launches(gpu):
+    """tcr_gemm_grouped_seq_*: 12 chained LSTM gate steps in ONE resident launch (grid barrier between steps) give the bits of 12
+    separate tcr_gemm_grouped launches, on repeated launches too (the barrier counters reset themselves); tools/rnn_seq_check.py
+    is the full-size (128 steps, hidden 1024) form with timings."""
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for prec in ("1", "2"):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "rnn_seq_check.py"), "12", prec, "48", "32", "256"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and '"bit_identical": true' in r.stdout, (r.stdout[-600:], r.stderr[-600:])
