@@ -246,14 +246,14 @@ __device__ __forceinline__ void rnn_epilogue(const RnnParams& p, const RnnStep& 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[half * 32 + j] += __uint_as_float(r[j]);
       }
-      if (tmem_empty != nullptr) {  // multi-step launch: the accumulator may be overwritten by the next step's first MMA
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty);
-      }
     } else {
 #pragma unroll
       for (int j = 0; j < RN; ++j) v[j] = 0.f;
+    }
+    if (tmem_empty != nullptr) {  // multi-step launch: the accumulator may be overwritten by the next step's first MMA
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
     }
     const uint32_t mine = red_s + (uint32_t)(((int)crank * NC) * RM + row) * 4u;
     if (CS == 1) {
@@ -297,6 +297,7 @@ __device__ __forceinline__ void rnn_epilogue(const RnnParams& p, const RnnStep& 
       if (b0 + j < p.m) out[(int64_t)(b0 + j) * p.out_pitch + u] = p.accumulate ? old[j] + x[j] : x[j];
   }
   if (p.cell) {  // groups == 4, rows_per_group == 32: gate g of unit ul, column j at cell[(g * NC + j) * 32 + ul]
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the cell buffer IS the reduce buffer: everybody has read its sums out of it
 #pragma unroll
     for (int j = 0; j < NC; ++j) sts_f32(cell_s + (uint32_t)((g * NC + j) * 32 + ul) * 4u, x[j]);
     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -320,9 +321,14 @@ __device__ __forceinline__ void rnn_epilogue(const RnnParams& p, const RnnStep& 
 
 template <int MODE>
 struct RnnCfg {
-  static constexpr int STAGES = MODE == 2 ? 3 : 4;
+  // The main loop is bound by the turn-around of a ring stage (TMA land ~1160 cycles + lo-part conversion + 12 MMAs + commit,
+  // ~2750 cycles), not by the MMAs (384 cycles per k-block): a k-block costs turn-around / STAGES. A fourth 48 KB stage fits
+  // in 3xTF32 once the cell-exchange buffer shares the (already consumed) reduce buffer: 3 stages ~1000 cycles per k-block.
+  static constexpr int STAGES = MODE == 2 ? 4 : 6;
   static constexpr int STAGE_BYTES = (MODE == 2 ? 2 : 1) * (W_TILE + X_TILE);
-  static constexpr int SMEM = STAGES * STAGE_BYTES + RED_BYTES + CELL_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + RED_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(CELL_BYTES <= RED_BYTES, "the cell buffer lives inside the reduce buffer");
+  static_assert(SMEM <= 232448, "dynamic shared memory of one CTA");
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
@@ -343,8 +349,8 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* red = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  float* cellbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + RED_BYTES);
-  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES + RED_BYTES + CELL_BYTES);
+  float* cellbuf = red;  // reused once every thread has summed its columns out of `red` (bar.sync in rnn_epilogue)
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES + RED_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* ready = bars + 2 * STAGES;
