@@ -1335,6 +1335,119 @@ static int run_vm_multi(const tcr_ew_program* progs, int count, const uint8_t* k
   return TCR_OK;
 }
 
+// ------------------------------------------------------------------ vector-along-segment-0 broadcast: out = un(bin(x, v))
+// `x OP EXTEND(v)` (+ one unary) where v spans segment 0 and repeats over every row — a dense layer's bias + activation when it is
+// not a GEMM epilogue (cfg/tenncor/layer.yml dense: CONTRACT, EXTEND, ADD). A thread keeps its 16 bytes of v in registers and
+// streams rows: no index arithmetic and no per-element interpreter step, four 16-byte loads in flight per thread. The chain
+// interpreter ran this shape at 0.45 of the copy bandwidth (issue-bound). Values are those of the separate functors (same
+// Ops<T> bodies, each result rounded).
+__device__ __forceinline__ float rowvec_unary(int un, float a) {
+  switch (un) {
+#define RVU(OP) case OP: return vm_un<float, OP>(a);
+    RVU(TCR_EW_SIGMOID) RVU(TCR_EW_TANH) RVU(TCR_EW_EXP) RVU(TCR_EW_NEG) RVU(TCR_EW_SQUARE) RVU(TCR_EW_LOG)
+    RVU(TCR_EW_SQRT) RVU(TCR_EW_ABS) RVU(TCR_EW_ROUND) RVU(TCR_EW_CUBE)
+#undef RVU
+    default: return a;
+  }
+}
+template <int BIN, bool REV>
+__global__ void __launch_bounds__(256) ew_rowvec_kernel(const float* x, const float* __restrict__ vec, float* out, uint32_t d0v,
+                                                        uint32_t colblocks, uint32_t rows_per_block, int64_t rows, int un) {
+  TCR_PDL_ENTER();
+  constexpr int U = 4;
+  const uint32_t cb = blockIdx.x % colblocks, rb = blockIdx.x / colblocks, nrb = gridDim.x / colblocks;
+  uint32_t col, lane;
+  if (rows_per_block == 1) { col = cb * 256u + threadIdx.x; lane = 0; }
+  else { col = threadIdx.x % d0v; lane = threadIdx.x / d0v; }
+  if (col >= d0v) return;
+  const Vec<float> b = ld16(vec + 4 * (size_t)col);
+  const int64_t rstride = (int64_t)nrb * rows_per_block;
+  int64_t r = (int64_t)rb * rows_per_block + lane;
+  auto apply = [&](Vec<float>& v) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v.v[k] = REV ? vm_bin<float, BIN>(b.v[k], v.v[k]) : vm_bin<float, BIN>(v.v[k], b.v[k]);
+    if (un != TCR_EW_NOP) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v.v[k] = rowvec_unary(un, v.v[k]);
+    }
+  };
+  for (; r + (U - 1) * rstride < rows; r += U * rstride) {
+    Vec<float> v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = ld16(x + 4 * ((r + u * rstride) * d0v + col));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      apply(v[u]);
+      st16(out + 4 * ((r + u * rstride) * d0v + col), v[u]);
+    }
+  }
+  for (; r < rows; r += rstride) {
+    Vec<float> v = ld16(x + 4 * (r * d0v + col));
+    apply(v);
+    st16(out + 4 * (r * d0v + col), v);
+  }
+}
+
+// true when the program is `un(bin(full, vector))` over floats and was launched (or failed to launch: *rc)
+static bool try_rowvec(const tcr_ew_program* prog, int* rc) {
+  static const int enabled = std::getenv("TCR_EW_ROWVEC") ? std::atoi(std::getenv("TCR_EW_ROWVEC")) : 1;
+  if (!enabled || prog->dtype != TCR_FLOAT || prog->n_inputs != 2 || prog->n_outputs != 1 || prog->n_instrs < 1 || prog->n_instrs > 2) return false;
+  if (prog->outputs[0].dtype != TCR_FLOAT || prog->inputs[0].dtype != TCR_FLOAT || prog->inputs[1].dtype != TCR_FLOAT) return false;
+  const int64_t d0 = prog->dims[0], rows = prog->dims[1] * prog->dims[2];
+  if (d0 < 4 || (d0 & 3) || rows < 2 || d0 * rows < (1 << 15) || d0 / 4 >= (1ll << 31)) return false;
+  const int64_t d0v = d0 / 4;
+  if (d0v < 256 && 256 % d0v != 0) return false;
+  int full = -1, vec = -1;
+  for (int k = 0; k < 2; ++k) {
+    const tcr_ew_input& in = prog->inputs[k];
+    const bool b0 = in.bcast[0] != 0, b1 = in.bcast[1] && prog->dims[1] > 1, b2 = in.bcast[2] && prog->dims[2] > 1;
+    const bool rep1 = b1 || prog->dims[1] == 1, rep2 = b2 || prog->dims[2] == 1;
+    if (!b0 && !b1 && !b2) full = k;
+    else if (!b0 && rep1 && rep2) vec = k;
+  }
+  if (full < 0 || vec < 0) return false;
+  const tcr_ew_instr& i0 = prog->instrs[0];
+  if (!((i0.a == full && i0.b == vec) || (i0.a == vec && i0.b == full))) return false;
+  const bool rev = i0.a == vec;
+  int un = TCR_EW_NOP;
+  uint8_t result = i0.dst;
+  if (prog->n_instrs == 2) {
+    const tcr_ew_instr& i1 = prog->instrs[1];
+    if (i1.a != result) return false;
+    switch (i1.op) {
+      case TCR_EW_SIGMOID: case TCR_EW_TANH: case TCR_EW_EXP: case TCR_EW_NEG: case TCR_EW_SQUARE: case TCR_EW_LOG:
+      case TCR_EW_SQRT: case TCR_EW_ABS: case TCR_EW_ROUND: case TCR_EW_CUBE: break;
+      default: return false;
+    }
+    un = i1.op;
+    result = i1.dst;
+  }
+  if (prog->outputs[0].reg != result) return false;
+  const float* x = (const float*)prog->inputs[full].ptr;
+  const float* v = (const float*)prog->inputs[vec].ptr;
+  float* out = (float*)prog->outputs[0].ptr;
+  if (!aligned16(x) || !aligned16(v) || !aligned16(out)) return false;
+  if ((const char*)v < (const char*)out + 4 * d0 * rows && (const char*)out < (const char*)v + 4 * d0) return false;  // vector inside the output
+  const uint32_t colblocks = d0v >= 256 ? (uint32_t)ceil_div(d0v, 256) : 1u, rpb = d0v >= 256 ? 1u : (uint32_t)(256 / d0v);
+  int64_t nrb = ceil_div(rows, (int64_t)rpb * 4);
+  const int64_t cap = std::max<int64_t>(1, (int64_t)state().sm_count * 8 / colblocks);
+  if (nrb > cap) nrb = cap;
+  const int grid = (int)(nrb * colblocks);
+#define RV_LAUNCH(OP)                                                                                                                \
+  case OP:                                                                                                                           \
+    if (rev) TCR_LAUNCH((ew_rowvec_kernel<OP, true>), grid, 256, 0, x, v, out, (uint32_t)d0v, colblocks, rpb, rows, un);              \
+    else TCR_LAUNCH((ew_rowvec_kernel<OP, false>), grid, 256, 0, x, v, out, (uint32_t)d0v, colblocks, rpb, rows, un);                 \
+    break;
+  switch (i0.op) {
+    RV_LAUNCH(TCR_EW_ADD) RV_LAUNCH(TCR_EW_SUB) RV_LAUNCH(TCR_EW_MUL) RV_LAUNCH(TCR_EW_DIV) RV_LAUNCH(TCR_EW_MIN) RV_LAUNCH(TCR_EW_MAX)
+    default: return false;
+  }
+#undef RV_LAUNCH
+  const cudaError_t e = cudaPeekAtLastError();
+  *rc = e == cudaSuccess ? TCR_OK : fail_cuda(e, "kernel launch", __FILE__, __LINE__);
+  return true;
+}
+
 extern "C" {
 
 int tcr_elementwise(const tcr_ew_program* prog) {
@@ -1381,6 +1494,10 @@ int tcr_elementwise(const tcr_ew_program* prog) {
       TCR_CHECK_LAUNCH();
       return TCR_OK;
     }
+  }
+  {
+    int rc = TCR_OK;
+    if (try_rowvec(prog, &rc)) return rc;
   }
   TCR_DISPATCH_COMPUTE(prog->dtype, T, {
     int rc = TCR_OK;

@@ -68,7 +68,7 @@ struct RnnParams {
   float* c_out;
   float* h_out;
   int64_t state_pitch;
-  int dbg_mode;    // TCR_RNN_EXPERIMENT: 1 = no MMAs (TMA only), 2 = no TMA loads (MMAs on whatever shared memory holds), 4 = X tile not loaded
+  int dbg_mode;    // TCR_RNN_EXPERIMENT: 1 = no MMAs (TMA only), 2 = no TMA loads (MMAs on whatever shared memory holds), 4 = X tile not loaded, 8 = no lo-part conversion, 16 = lo parts of the activation tile only
   long long* dbg;  // TCR_RNN_DEBUG: SM-clock stamps of CTA (0,0,0), see tcr_rnn_debug_read
 };
 
@@ -543,8 +543,10 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
           // the landed fp32 words are the hi operand as they are (the tensor core reads their top 19 bits); lo = x - hi
           const uint4* src = reinterpret_cast<const uint4*>(tile_w(st));
           uint4* dlo = reinterpret_cast<uint4*>(tile_w(st) + W_TILE + X_TILE);
+          // timing experiments (results are wrong): 8 = no conversion at all, 16 = only the activation tile is converted
+          const int e_begin = (p.dbg_mode & 8) ? (W_TILE + X_TILE) / 16 : (p.dbg_mode & 16) ? W_TILE / 16 : 0;
 #pragma unroll 4
-          for (int e = ct; e < (W_TILE + X_TILE) / 16; e += 128) {
+          for (int e = e_begin + ct; e < (W_TILE + X_TILE) / 16; e += 128) {
             const uint4 v = src[e];
             uint4 lo;
             lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));

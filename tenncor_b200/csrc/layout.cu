@@ -157,16 +157,31 @@ __global__ void __launch_bounds__(256) copy2d_batched_kernel(const __grid_consta
 // SLICE / PAD along ONE rank (the recurrent layers' per-step slices, conv2d's zero border along a fresh rank): the tensor is
 // `outer` rows; an output row is [zeros lo | data | zeros hi] of a window of the input row. 16-byte vectors, one division per vector
 // (tcr_map_copy spends a div/mod chain over eight ranks per element: 49-52 % of the copy bandwidth on [1024,128,64]).
+template <typename I>
 __global__ void __launch_bounds__(256) row_window_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t out_row, uint32_t lo, uint32_t data,
-                                                          int64_t in_row, int64_t in_off, int64_t total) {
+                                                          int64_t in_row, int64_t in_off, int64_t total_) {
   TCR_PDL_ENTER();
-  const int64_t stride = (int64_t)gridDim.x * 256;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
-    const int64_t r = i / out_row;
-    const uint32_t c = (uint32_t)(i - r * out_row);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (c >= lo && c - lo < data) v = in[r * in_row + in_off + (c - lo)];
-    out[i] = v;
+  // I = uint32_t whenever the vector count allows it (a 64-bit division is ~10x the instructions of a 32-bit one, and a 16 MB
+  // slice is only a few vectors per thread); four vectors in flight per thread
+  constexpr int U = 4;
+  const I total = (I)total_, stride = (I)gridDim.x * 256;
+  for (I i0 = (I)blockIdx.x * 256 + threadIdx.x; i0 < total; i0 += U * stride) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const I i = i0 + (I)u * stride;
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (i < total) {
+        const I r = i / out_row;
+        const uint32_t c = (uint32_t)(i - r * out_row);
+        if (c >= lo && c - lo < data) v[u] = in[(int64_t)r * in_row + in_off + (c - lo)];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const I i = i0 + (I)u * stride;
+      if (i < total) out[i] = v[u];
+    }
   }
 }
 
@@ -186,8 +201,12 @@ static bool launch_row_window(const void* in, void* out, const int64_t in_shape[
   if (((in_row | off | data | lo_b | out_row) & 15) != 0 || (((uintptr_t)in | (uintptr_t)out) & 15) != 0) return false;
   if (out_row / 16 >= (1ll << 32) || outer * out_row == 0) return false;
   const int64_t total = outer * out_row / 16;
-  const int grid = wave_grid(total, 256, 8);
-  TCR_LAUNCH(row_window_kernel, grid, 256, 0, (const uint4*)in, (uint4*)out, (uint32_t)(out_row / 16), (uint32_t)(lo_b / 16), (uint32_t)(data / 16), in_row / 16, off / 16, total);
+  const int grid = wave_grid(ceil_div(total, 4), 256, 8);
+  // i0 + 3 * stride must not wrap: stride <= 148 * 8 * 256
+  if (total < (1ll << 32) - (1ll << 22))
+    TCR_LAUNCH(row_window_kernel<uint32_t>, grid, 256, 0, (const uint4*)in, (uint4*)out, (uint32_t)(out_row / 16), (uint32_t)(lo_b / 16), (uint32_t)(data / 16), in_row / 16, off / 16, total);
+  else
+    TCR_LAUNCH(row_window_kernel<int64_t>, grid, 256, 0, (const uint4*)in, (uint4*)out, (uint32_t)(out_row / 16), (uint32_t)(lo_b / 16), (uint32_t)(data / 16), in_row / 16, off / 16, total);
   return true;
 }
 

@@ -462,7 +462,35 @@ __global__ void __launch_bounds__(256) argmax_flat1(const T* __restrict__ in, in
   __shared__ int64_t si[8];
   ValIdx<T> best{Lim<T>::lo(), INT64_MAX};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) best = vi_better(best, ValIdx<T>{in[i], i});
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t done = 0;
+  if (sizeof(T) == 4 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    // 16-byte loads, four vectors in flight per thread. A thread meets its elements in increasing index order, so a strict `>`
+    // keeps the lowest index of equal maxima without comparing indices; the `== ... && none yet` arm lets a tensor made of the
+    // lowest representable value (or of -inf) still name its first element (NaN never wins, as in vi_better).
+    struct alignas(16) Q { T v[4]; };
+    const Q* in4 = reinterpret_cast<const Q*>(in);
+    const int64_t nvec = n / 4;
+    int64_t i = tid;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+      const Q q0 = in4[i], q1 = in4[i + stride], q2 = in4[i + 2 * stride], q3 = in4[i + 3 * stride];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) if (q0.v[v] > best.v || (q0.v[v] == best.v && best.i == INT64_MAX)) { best.v = q0.v[v]; best.i = 4 * i + v; }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) if (q1.v[v] > best.v || (q1.v[v] == best.v && best.i == INT64_MAX)) { best.v = q1.v[v]; best.i = 4 * (i + stride) + v; }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) if (q2.v[v] > best.v || (q2.v[v] == best.v && best.i == INT64_MAX)) { best.v = q2.v[v]; best.i = 4 * (i + 2 * stride) + v; }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) if (q3.v[v] > best.v || (q3.v[v] == best.v && best.i == INT64_MAX)) { best.v = q3.v[v]; best.i = 4 * (i + 3 * stride) + v; }
+    }
+    for (; i < nvec; i += stride) {
+      const Q q = in4[i];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) if (q.v[v] > best.v || (q.v[v] == best.v && best.i == INT64_MAX)) { best.v = q.v[v]; best.i = 4 * i + v; }
+    }
+    done = nvec * 4;
+  }
+  for (int64_t i = done + tid; i < n; i += stride) best = vi_better(best, ValIdx<T>{in[i], i});
   best = vi_warp(best);
   if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best.v; si[threadIdx.x >> 5] = best.i; }
   __syncthreads();

@@ -155,6 +155,49 @@ def test_fused_program_with_broadcast(gpu, dims, bc):
     np.testing.assert_allclose(got2, 0.5 * t, rtol=FP32_RTOL, atol=1e-6)
 
 
+@pytest.mark.parametrize("d0,rows,binop,rev,un", [
+    (1024, 67, "ADD", False, "SIGMOID"),     # dense bias + activation: one column block, rows with a ragged tail of the 4-row unroll
+    (64, 1031, "ADD", True, "TANH"),         # 16 vectors per row: 16 row lanes per block
+    (2048 + 512, 33, "MUL", False, None),    # three column blocks, the last one partial
+    (256, 300, "SUB", True, "EXP"),          # vector - x
+    (128, 512, "DIV", False, "SQUARE"),
+    (4096, 9, "MAX", False, "NEG"),
+])
+def test_vector_broadcast_program_matches_separate_functors(gpu, d0, rows, binop, rev, un):
+    """un(bin(x, EXTEND(v))) with v along segment 0 takes ew_rowvec_kernel; values are bit-identical to the functors run one by one
+    over the materialised broadcast (internal/eigen/operator.hpp:159-173 materialises it), also when the result overwrites x."""
+    rng = np.random.default_rng(d0 + rows)
+    lib = gpu.lib()
+    n = d0 * rows
+    x = rng.uniform(-2, 2, n).astype(np.float32)
+    v = rng.uniform(0.5, 2, d0).astype(np.float32)
+    dx, dv, out = gpu.to_device(x), gpu.to_device(v), gpu.empty(n, np.float32)
+    OPC = gpu.OP
+    ins = [(dx.ptr, gpu.FLOAT, (0, 0, 0)), (dv.ptr, gpu.FLOAT, (0, 1, 0))]
+    instrs = [(OPC[binop], 2, 1, 0) if rev else (OPC[binop], 2, 0, 1)]
+    if un:
+        instrs.append((OPC[un], 3, 2))
+    reg = 3 if un else 2
+    launches = lib.tcr_launch_count()
+    prog = gpu.make_program(gpu.FLOAT, (d0, rows, 1), ins, [(out.ptr, gpu.FLOAT, reg)], instrs)
+    gpu.check(lib.tcr_elementwise(C.byref(prog)))
+    assert lib.tcr_launch_count() == launches + 1
+    got = gpu.to_host(out, n, np.float32)
+    # the separate functors over the materialised broadcast
+    dfull = gpu.to_device(np.tile(v, rows))
+    t = gpu.empty(n, np.float32)
+    a, b = (dfull, dx) if rev else (dx, dfull)
+    gpu.check(lib.tcr_binary(OPC[binop], C.c_void_p(a.ptr), C.c_void_p(b.ptr), C.c_void_p(t.ptr), C.c_int64(n), gpu.FLOAT))
+    if un:
+        gpu.check(lib.tcr_unary(OPC[un], C.c_void_p(t.ptr), C.c_void_p(t.ptr), C.c_int64(n), gpu.FLOAT))
+    want = gpu.to_host(t, n, np.float32)
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    # in place: the result replaces x
+    prog = gpu.make_program(gpu.FLOAT, (d0, rows, 1), ins, [(dx.ptr, gpu.FLOAT, reg)], instrs)
+    gpu.check(lib.tcr_elementwise(C.byref(prog)))
+    np.testing.assert_array_equal(gpu.to_host(dx, n, np.float32).view(np.uint32), want.view(np.uint32))
+
+
 def test_program_mixed_dtype_cast_and_inplace(gpu):
     rng = np.random.default_rng(5)
     lib = gpu.lib()
@@ -236,6 +279,20 @@ def test_argmax_with_ties(gpu, dt, shape, dim):
     np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("fill", [-np.inf, float(np.finfo(np.float32).min)], ids=["-inf", "lowest"])
+def test_argmax_flat_of_a_tensor_of_lowest_values(gpu, fill):
+    """every element equals the reduction's identity: the answer is still the first index (Eigen argmax keeps the first maximum)"""
+    n = (1 << 18) + 3
+    x = np.full(n, fill, np.float32)
+    s8 = orc.full_shape([n])
+    got, _ = opcheck.gpu_run(gpu, "ARGMAX", [x], [s8], {"rank": 8})
+    assert float(np.asarray(got).reshape(-1)[0]) == 0.0
+    x[12345] = fill if np.isinf(fill) else 0.0
+    x[777] = np.nan  # never wins
+    got, _ = opcheck.gpu_run(gpu, "ARGMAX", [x], [s8], {"rank": 8})
+    assert float(np.asarray(got).reshape(-1)[0]) == (0.0 if np.isinf(fill) else 12345.0)
+
+
 LAYOUT = [
     ("EXTEND", [7, 1, 5], {"dimensions": [1, 6]}),
     ("EXTEND", [1], {"dimensions": [33, 9]}),
@@ -252,6 +309,8 @@ LAYOUT = [
     ("SLICE", [5, 4], {"dimension_pairs": [[100, 1]]}),
     ("PAD", [5, 4, 3], {"dimension_pairs": [[1, 2], [0, 0], [2, 0]]}),
     ("PAD", [64, 1, 6], {"dimension_pairs": [[0, 0], [3, 6]]}),
+    ("SLICE", [1024, 128, 40], {"dimension_pairs": [[0, 1024], [32, 64]]}),   # row_window_kernel over several unrolled iterations
+    ("PAD", [1024, 128, 24], {"dimension_pairs": [[0, 0], [16, 16]]}),
     ("STRIDE", [10, 9], {"dimensions": [2, 3]}),
     ("SCATTER", [5, 3], {"dimensions": [2, 3], "shape": [10, 9]}),
     ("SCATTER", [5, 3], {"dimensions": [2, 3], "shape": [9, 7]}),
