@@ -451,7 +451,7 @@ int tcr_comm_rank(void);
 int tcr_comm_size(void); /* 1 when no communicator */
 /* in-place SUM all-reduce followed by `scale` (1/nranks for mean-type losses). FLOAT buffers inside the symmetric region
  * (tcr_comm_symm_alloc) are exchanged by ONE kernel over NVLink peer memory (allreduce_p2p.cu: every rank maps every peer's
- * region through CUDA IPC; one-shot below 512 KB, reduce-scatter + all-gather above; rank-order sums, bit-identical on all
+ * region through CUDA IPC; one-shot below 512 KB; above, every rank pulls and sums its slice and pushes it to all peers; rank-order sums, bit-identical on all
  * ranks); everything else goes through ncclAllReduce. */
 int tcr_allreduce_sum(void* buf, int64_t n, int dtype, double scale);
 /* Symmetric region: memory every peer can address. Ranks must allocate the same sizes in the same order (the planner does: all

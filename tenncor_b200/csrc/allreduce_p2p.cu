@@ -6,8 +6,8 @@
 // call is latency-bound — 73 us at 8 ranks for 3.26 MB, the whole loss of weak-scaling efficiency. Here every rank maps
 // every peer's bucket (CUDA IPC) and ONE kernel does the exchange with plain loads and stores through NVSwitch:
 //   one-shot (<= 512 KB) : barrier; every rank reads all peers' buckets and sums them in rank order; barrier
-//   two-shot             : barrier; rank r sums slice r of every peer's bucket into its own slice r (reduce-scatter);
-//                          barrier; rank r copies slice p from rank p for every p (all-gather); barrier
+//   two-shot             : barrier; rank r pulls slice r of every bucket, sums it and pushes the result into every bucket
+//                          (reduce-scatter by loads, all-gather by stores); barrier
 // Sums run in rank order on every rank, so all ranks hold bit-identical results (replicated optimiser state stays consistent)
 // and repeated runs are deterministic. The post-reduction scale (1 / ranks for batch-mean losses) is applied in the same pass.
 // Barriers are per-block flag exchanges in the peers' memory (st / ld at system scope), epochs live in device memory so a
@@ -97,53 +97,41 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_p2p_kernel(const __grid_
     p2p_barrier(p, 1, epoch);  // no peer reads my bucket any more
     if (tid < nvec) *reinterpret_cast<float4*>(p.data[p.rank] + 4 * tid) = acc;
   } else {
+    // rank r owns slice r: it PULLS that slice from every bucket (all ranks' loads of a vector are in flight together: one trip
+    // through NVSwitch, ~1-2 us, per U vectors instead of one per rank), sums in rank order, and PUSHES the result into every
+    // bucket — stores need no round trip, so the all-gather costs no second latency and no third barrier: an element of slice r in
+    // a peer's bucket is read and then overwritten by the same thread of rank r, nobody else touches it.
     const int64_t per = (nvec + p.size - 1) / p.size;  // vectors per slice
-    // reduce-scatter: my slice
-    {
-      const int64_t lo = per * p.rank, hi = lo + per < nvec ? lo + per : nvec;
-      float* out = p.data[p.rank];
-      constexpr int U = 4;  // vectors in flight per peer per thread: a peer load takes ~1 us through NVSwitch
-      for (int64_t i0 = lo + tid; i0 < hi; i0 += nthr * U) {
-        float4 acc[U];
+    const int64_t lo = per * p.rank, hi = lo + per < nvec ? lo + per : nvec;
+    constexpr int U = 2;
+    for (int64_t i0 = lo + tid; i0 < hi; i0 += nthr * U) {
+      float4 v[MAX_RANKS][U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int64_t i = i0 + u * nthr;
-          acc[u] = i < hi ? ld_peer(p.data[0] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int r = 1; r < p.size; ++r) {
-          float4 v[U];
+      for (int r = 0; r < MAX_RANKS; ++r) {
+        if (r < p.size) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int64_t i = i0 + u * nthr;
-            v[u] = i < hi ? ld_peer(p.data[r] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[r][u] = i < hi ? ld_peer(p.data[r] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-#pragma unroll
-          for (int u = 0; u < U; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
         }
+      }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int64_t i = i0 + u * nthr;
-          if (i < hi) *reinterpret_cast<float4*>(out + 4 * i) = make_float4(acc[u].x * p.scale, acc[u].y * p.scale, acc[u].z * p.scale, acc[u].w * p.scale);
+      for (int u = 0; u < U; ++u) {
+        float4 acc = v[0][u];
+#pragma unroll
+        for (int r = 1; r < MAX_RANKS; ++r)
+          if (r < p.size) { acc.x += v[r][u].x; acc.y += v[r][u].y; acc.z += v[r][u].z; acc.w += v[r][u].w; }
+        acc = make_float4(acc.x * p.scale, acc.y * p.scale, acc.z * p.scale, acc.w * p.scale);
+        const int64_t i = i0 + u * nthr;
+        if (i < hi) {
+#pragma unroll
+          for (int r = 0; r < MAX_RANKS; ++r)
+            if (r < p.size) *reinterpret_cast<float4*>(p.data[r] + 4 * i) = acc;
         }
       }
     }
-    p2p_barrier(p, 1, epoch);  // every slice is final in its owner's bucket
-    // all-gather: slice q from rank q
-    float* out = p.data[p.rank];
-    for (int q = 0; q < p.size; ++q) {
-      if (q == p.rank) continue;
-      const int64_t lo = per * q, hi = lo + per < nvec ? lo + per : nvec;
-      const float* src = p.data[q];
-      for (int64_t i0 = lo + tid; i0 < hi; i0 += nthr * 4) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = i0 + u * nthr < hi ? ld_peer(src + 4 * (i0 + u * nthr)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (i0 + u * nthr < hi) *reinterpret_cast<float4*>(out + 4 * (i0 + u * nthr)) = v[u];
-      }
-    }
-    p2p_barrier(p, 2, epoch);  // nobody reads my bucket any more: the next step may overwrite it
+    p2p_barrier(p, 1, epoch);  // every slice has arrived in every bucket
   }
   if (threadIdx.x == 0) p.sig[p.rank]->epoch[blockIdx.x] = epoch;
 }

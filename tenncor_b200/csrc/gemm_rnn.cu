@@ -38,7 +38,8 @@ namespace {
 constexpr int RM = 128, RN = 64, RK = 32;
 constexpr int W_TILE = RM * RK * 4;  // 16 KiB
 constexpr int X_TILE = RN * RK * 4;  // 8 KiB
-constexpr int THREADS = 192;
+constexpr int THREADS = 256;
+constexpr int PRODUCERS = 3;  // warps 0, 6, 7: a warp issues the five boxes of a k-block in ~700 cycles (ELECT + R2UR round trip per lane), so k-blocks are dealt to three of them
 constexpr int NACC = 1;  // TMEM accumulators used round-robin by the k-steps of a k-block and summed in the epilogue. Measured: 4 independent
                          // accumulators do not speed the MMAs up (the ~83 cycles per 128 x 64 x 8 MMA are not an accumulator dependency) and
                          // cost ~300 cycles of extra TMEM loads, so one is used.
@@ -360,7 +361,9 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) RNN_STAMP(0);
-  const uint32_t crank = cluster_rank(), csize = cluster_size();
+  // the cluster is (1, 1, C) and the grid is C deep: rank and size are blockIdx.z / gridDim.z, which — unlike the %cluster_*
+  // registers read through inline assembly — the compiler knows to be warp-uniform
+  const uint32_t crank = blockIdx.z, csize = gridDim.z;
   const int u0 = (int)blockIdx.x * p.rows_per_group;  // first unit (column of every out_g) of this CTA
   const int m0 = (int)blockIdx.y * RN;                // first batch row
   const int kb_begin = (int)crank * p.kb_per_cta;
@@ -396,8 +399,9 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
   if (threadIdx.x == 0) RNN_STAMP(1);
   cluster_arrive();  // #1: "this CTA is running" — awaited before anybody writes into a peer's shared memory
 
-  if (warp == 0) {
-    // ================= TMA producer =================
+  if (warp == 0 || warp >= 6) {
+    // ================= TMA producers =================
+    const uint32_t pw = warp == 0 ? 0u : (uint32_t)(warp - 5);  // k-block `it` (counted over all steps) belongs to producer it % PRODUCERS
     // One lane per box: lanes 0..3 fetch the weight boxes, lane 4 the activation tile; lane 0 also arms the barrier. (One thread
     // issuing five TMAs with their address arithmetic cost ~950 cycles per k-block: the loop was bound by that thread, not by L2.)
     {
@@ -427,10 +431,12 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
         if (seg > 0) kl = kb_begin - p.seg_kb_end[seg - 1];
         bool met = !SEQ || t == 0;  // step 0 reads what was there before the launch
         for (int i = 0; i < num_kb; ++i, ++it) {
+          const bool mine = it % PRODUCERS == pw;
           const int st = (int)(it % STAGES);
           const uint32_t phase = (it / STAGES) & 1u;
-          if (it >= (uint32_t)STAGES && lane < 5) mbar_wait(&empty[st], phase ^ 1);
-          if (p.dbg_mode & 2) {
+          if (mine && it >= (uint32_t)STAGES && lane < 5) mbar_wait(&empty[st], phase ^ 1);
+          if (!mine) {
+          } else if (p.dbg_mode & 2) {
             if (lane == 0) mbar_arrive(&full[st]);
           } else {
             if (lane == 0) mbar_expect_tx(&full[st], tx_bytes);
@@ -454,11 +460,11 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
               tma_load_2d(SEQ ? &sq.xmaps[t * p.nseg + seg] : &maps.x[seg], &full[st], wt + W_TILE, wk, m0);
             }
           }
-          if (t == 0 && i == 0 && lane == 0) RNN_STAMP(2);
+          if (t == 0 && i == 0 && lane == 0 && pw == 0) RNN_STAMP(2);
           ++kl;
           if (seg + 1 < p.nseg && kb_begin + i + 1 >= p.seg_kb_end[seg]) { ++seg; kl = 0; }
         }
-        if (t == 0 && lane == 0) RNN_STAMP(3);
+        if (t == 0 && lane == 0 && pw == (uint32_t)((it - 1) % PRODUCERS) && num_kb > 0) RNN_STAMP(3);
         if (SEQ) {  // the cluster barrier of this step's exchange counts every thread of the cluster
           __syncwarp();
           if (t == 0) cluster_wait();  // #1
@@ -589,7 +595,7 @@ gemm_rnn_kernel(const __grid_constant__ RnnMaps maps, const __grid_constant__ Rn
       }
     }
   }
-  if (!SEQ && warp < 2) {
+  if (!SEQ && (warp < 2 || warp >= 6)) {
     cluster_wait();    // #1
     cluster_arrive();  // #2
     cluster_wait();
