@@ -116,6 +116,7 @@ int tcr_memset(void* dst, int byte, size_t bytes);
 int tcr_event_create(void** out);
 int tcr_event_destroy(void* ev);
 int tcr_event_record(void* ev);
+int tcr_event_sync(void* ev); /* wait for the work queued before the record (a deferred tcr_d2h: read the host buffer after this) */
 int tcr_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on stop */
 
 /* CUDA-graph capture of a launch sequence (replaces the per-node host traversal of

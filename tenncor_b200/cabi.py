@@ -43,7 +43,7 @@ SYMBOLS = [
     "tcr_init", "tcr_shutdown", "tcr_last_error", "tcr_device_count", "tcr_sm_count", "tcr_stream",
     "tcr_sync", "tcr_alloc", "tcr_free", "tcr_arena_stats", "tcr_arena_trim", "tcr_host_alloc",
     "tcr_host_free", "tcr_h2d", "tcr_h2d_prefetch", "tcr_prefetch_commit", "tcr_prefetch_sync", "tcr_d2h", "tcr_d2d", "tcr_memset", "tcr_event_create",
-    "tcr_event_destroy", "tcr_event_record", "tcr_event_elapsed_ms", "tcr_graph_begin", "tcr_graph_lane", "tcr_graph_record", "tcr_graph_wait",
+    "tcr_event_destroy", "tcr_event_record", "tcr_event_sync", "tcr_event_elapsed_ms", "tcr_graph_begin", "tcr_graph_lane", "tcr_graph_record", "tcr_graph_wait",
     "tcr_graph_end", "tcr_graph_launch", "tcr_graph_destroy", "tcr_launch_count", "tcr_elementwise", "tcr_elementwise_reduce", "tcr_elementwise_multi", "tcr_cell_backward",
     "tcr_unary", "tcr_binary", "tcr_nnary", "tcr_select", "tcr_cast", "tcr_assign", "tcr_rand_unif", "tcr_rand_seed", "tcr_rand_unif_stream",
     "tcr_reduce", "tcr_argmax", "tcr_map_copy", "tcr_extend", "tcr_permute", "tcr_slice", "tcr_pad",

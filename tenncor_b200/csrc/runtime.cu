@@ -356,6 +356,12 @@ int tcr_event_record(void* ev) {
   return TCR_OK;
 }
 
+int tcr_event_sync(void* ev) {
+  TCR_REQUIRE_DEVICE();
+  TCR_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
+  return TCR_OK;
+}
+
 int tcr_event_elapsed_ms(void* start, void* stop, float* ms) {
   TCR_REQUIRE_DEVICE();
   TCR_CUDA(cudaEventSynchronize((cudaEvent_t)stop));

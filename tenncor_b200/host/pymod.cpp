@@ -98,6 +98,60 @@ static py::array to_array(iTensor& tens) {
   return out;
 }
 
+// A result on its way to the host: ETensor.get_later() queues the device -> pinned-host copy behind the evaluation and returns at once,
+// so the host can launch the next step while this one computes; result() waits for the copy (not for anything queued after it).
+// The reference's session loop reads the error of every iteration synchronously (tenncor/pyutils: sess.update_target + get);
+// on a device that read would idle the GPU for one host round trip per step.
+struct PendingRead {
+  void* host = nullptr;
+  void* event = nullptr;
+  size_t bytes = 0;
+  egen::_GENERATED_DTYPE dtype = egen::BAD_TYPE;
+  std::vector<py::ssize_t> shape;
+  bool waited = false;
+  PendingRead() = default;
+  PendingRead(const PendingRead&) = delete;
+  PendingRead& operator=(const PendingRead&) = delete;
+  ~PendingRead() {
+    if (event) { tcr_event_sync(event); tcr_event_destroy(event); }
+    if (host) pool().emplace_back(bytes, host);
+  }
+  // pinned staging buffers are kept for reuse (cudaHostAlloc costs more than a training step)
+  static std::vector<std::pair<size_t, void*>>& pool() {
+    static auto* p = new std::vector<std::pair<size_t, void*>>();
+    return *p;
+  }
+  static void* take(size_t bytes) {
+    auto& p = pool();
+    for (size_t i = 0; i < p.size(); ++i)
+      if (p[i].first == bytes) { void* h = p[i].second; p.erase(p.begin() + i); return h; }
+    void* h = nullptr;
+    cuda::check(tcr_host_alloc(&h, bytes ? bytes : 1), "tcr_host_alloc");
+    return h;
+  }
+  py::array result() {
+    if (!waited) { cuda::check(tcr_event_sync(event), "tcr_event_sync"); waited = true; }
+    py::array out(dtype2np(dtype), shape);
+    std::memcpy(out.mutable_data(), host, bytes);
+    return out;
+  }
+};
+
+static std::unique_ptr<PendingRead> read_later(iTensor& tens) {
+  void* dev = tens.device().device_data();
+  if (nullptr == dev) global::fatalf("%s has no device data: evaluate it first", tens.to_string().c_str());
+  std::unique_ptr<PendingRead> r(new PendingRead());
+  r->dtype = (egen::_GENERATED_DTYPE)tens.get_meta().type_code();
+  r->bytes = tens.shape().n_elems() * egen::type_size(r->dtype);
+  DimsT ps = c2pshape(tens.shape());
+  r->shape.assign(ps.begin(), ps.end());
+  r->host = PendingRead::take(r->bytes);
+  cuda::check(tcr_event_create(&r->event), "tcr_event_create");
+  cuda::check(tcr_d2h(r->host, dev, r->bytes), "tcr_d2h");
+  cuda::check(tcr_event_record(r->event), "tcr_event_record");
+  return r;
+}
+
 static TensSetT to_set(const ETensorsT& ts) {
   TensSetT out;
   for (auto& t : ts) out.emplace(t.get());
@@ -224,6 +278,10 @@ PYBIND11_MODULE(_tenncor, m) {
   m.doc() = "tenncor_b200 host module: TEQ functor graphs evaluated on B200 (sm_100a)";
   py::register_exception<global::FatalError>(m, "FatalError", PyExc_RuntimeError);
 
+  py::class_<PendingRead>(m, "PendingRead")
+      .def("result", &PendingRead::result, "Wait for the queued device -> host copy and return the value as a numpy array")
+      .def("done", [](PendingRead& self) { return self.waited; });
+
   py::class_<iTensor, TensptrT> etens(m, "ETensor");
   etens.def("__str__", [](const iTensor& self) { return self.to_string(); })
       .def("__hash__", [](const iTensor& self) { return (size_t)&self; })
@@ -242,6 +300,12 @@ PYBIND11_MODULE(_tenncor, m) {
         return to_array(*self);
       }, py::arg("ignored") = ETensorsT{}, py::arg("max_version") = std::numeric_limits<size_t>::max(),
       "Evaluate on the device and return the result as a numpy array")
+      .def("get_later", [](TensptrT self, ETensorsT ignored, size_t max_version) {
+        eteq::run({self}, to_set(ignored), max_version);
+        return read_later(*self);
+      }, py::arg("ignored") = ETensorsT{}, py::arg("max_version") = std::numeric_limits<size_t>::max(),
+      "Evaluate on the device and queue the copy of the result to pinned host memory; returns a PendingRead whose result() waits for "
+      "that copy only — the host is free to launch the next step meanwhile")
       .def("calc", [](TensptrT self, ETensorsT ignored, size_t max_version) {
         eteq::run({self}, to_set(ignored), max_version);
       }, py::arg("ignored") = ETensorsT{}, py::arg("max_version") = std::numeric_limits<size_t>::max(),

@@ -44,3 +44,34 @@ def test_assign_from_a_device_array(gpu):
         x.assign(src.double())
     with pytest.raises(Exception, match="shaped"):
         x.assign(src[:2].contiguous())
+
+
+def test_get_later_reads_every_step_one_step_behind(gpu):
+    """ETensor.get_later: the copy to pinned host memory is queued behind the evaluation and the host goes on launching; result()
+    returns what get() would have returned at that point, also when the variable has been overwritten since (the copy is ordered
+    on the device before the next step's work)."""
+    rng = np.random.default_rng(2)
+    x = tc.EVariable([64, 33], 0, "x")
+    w = tc.variable(rng.uniform(-1, 1, (33, 9)).astype(np.float32), "w")
+    y = tc.api.reduce_sum(tc.api.tanh(tc.api.matmul(x, w)))
+    batches = [rng.uniform(-1, 1, (64, 33)).astype(np.float32) for _ in range(6)]
+    want = []
+    for b in batches:
+        x.assign(b)
+        want.append(np.array(y.get()))
+    pending, got = None, []
+    for b in batches:
+        x.assign(b)
+        nxt = y.get_later()
+        if pending is not None:
+            assert pending.done() is False
+            got.append(pending.result())
+            assert pending.done() is True
+        pending = nxt
+    got.append(pending.result())
+    got.append(pending.result())  # a second result() returns the same value
+    for a, b in zip(got, want + want[-1:]):
+        assert a.shape == b.shape and a.dtype == b.dtype
+        np.testing.assert_array_equal(a, b)
+    with pytest.raises(Exception, match="no device data"):
+        tc.api.exp(x + 1.0).__cuda_array_interface__
