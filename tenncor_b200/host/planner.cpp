@@ -7,6 +7,8 @@
 #include <queue>
 #include <set>
 #include <map>
+#include <unordered_map>
+#include <limits>
 #include <tuple>
 #include <algorithm>
 
@@ -2371,10 +2373,26 @@ struct Plan {
     }
     std::multimap<size_t, void*> pool;  // plan-local free list: buffers are reused once their last reader has run
     std::vector<std::vector<int>> dying(steps.size());
+    // A plan that updates no variable (inference, metrics) keeps every result in its own buffer, like the reference keeps every
+    // functor's data (internal/eigen/device.hpp): a later evaluation re-runs only what a changed leaf reaches (stale_steps) and
+    // reads everything else where it was left. Training plans are stale from top to bottom after every step (the ASSIGNs bump the
+    // variables), so they recycle buffers by lifetime instead. TCR_PLAN_KEEP_MB bounds the memory spent on keeping (default 4096).
+    bool keep_all = bucket_bytes == 0 && std::getenv("TCR_NO_PARTIAL") == nullptr;
+    {
+      size_t total = 0;
+      for (auto& st : steps) {
+        if (st.kind != Step::NORMAL || is_assign(nodes[st.out_node].op)) { keep_all = false; break; }
+        total += (size_t)nodes[st.out_node].n * type_size(nodes[st.out_node].dtype);
+        for (int e : st.extra_outs) total += (size_t)nodes[e].n * type_size(nodes[e].dtype);
+      }
+      const char* cap = std::getenv("TCR_PLAN_KEEP_MB");
+      if (total > (size_t)(cap ? std::atoll(cap) : 4096) << 20) keep_all = false;
+    }
     auto place_pooled = [&](int node, size_t s) {
       PNode& o = nodes[node];
       size_t bytes = (size_t)o.n * type_size(o.dtype);
       size_t bucket = bytes < 512 ? 512 : bytes;
+      if (keep_all) { o.ptr = alloc_owned(bucket); return; }
       auto it = pool.lower_bound(bucket);
       if (it != pool.end() && it->first <= bucket * 2) {
         o.ptr = it->second;
@@ -2709,6 +2727,7 @@ struct Plan {
     bucket_gradients();
     if (lower_only) return;
     assign_buffers();
+    prepare_partial();
     n_launch_steps = steps.size();
     // RAND_UNIF reads and advances the device-resident generator state: graph replays draw fresh numbers
     use_graph = std::getenv("TCR_NO_GRAPH") == nullptr && !steps.empty();
@@ -2823,10 +2842,102 @@ struct Plan {
     return out;
   }
 
+  // ---------------------------------------------------------------- re-evaluation of the stale part only
+  // The reference recomputes a functor only when a child carries a newer version (tenncor/eteq/functor.hpp:246-269,
+  // internal/eigen/device.hpp:555-570). The plan keeps, per functor, the version its own buffers hold (`seen_version`: versions are
+  // global, another plan or the node evaluator may have bumped them without touching this plan's private buffers), and runs only
+  // the steps that write a stale functor — plus the producers of operands whose buffer was recycled for another result since
+  // (assign_buffers pools by lifetime), found by walking the steps backwards. When every step is needed the captured graph replays.
+  std::vector<size_t> seen_version;     // per node; functors only
+  std::vector<char> shared_buffer;      // per node: its buffer also holds another step's result at some point of a run
+  std::vector<std::vector<int>> node_writers;  // per node: the steps that write it (a variable updated in place has several)
+  size_t steps_run_last = 0;
+  bool partial_ok = false;
+
+  void prepare_partial() {
+    seen_version.assign(nodes.size(), (size_t)-1);
+    shared_buffer.assign(nodes.size(), 0);
+    partial_ok = std::getenv("TCR_NO_PARTIAL") == nullptr;
+    std::unordered_map<const void*, int> writers;
+    std::vector<int> wr;
+    node_writers.assign(nodes.size(), {});
+    for (size_t k = 0; k < steps.size(); ++k) {
+      const Step& st = steps[k];
+      if (st.kind != Step::NORMAL) { partial_ok = false; continue; }  // gradient exchange: every rank runs the same launches
+      step_writes(st, wr);
+      for (int q : st.multi_outs) wr.push_back(q);
+      std::sort(wr.begin(), wr.end());
+      wr.erase(std::unique(wr.begin(), wr.end()), wr.end());
+      std::set<const void*> ptrs;  // an ASSIGN names its variable's storage twice (result node and variable): one writer
+      for (int w : wr) { ptrs.insert(nodes[w].ptr); node_writers[w].push_back((int)k); }
+      for (const void* q : ptrs) ++writers[q];
+    }
+    for (auto& st : steps) {
+      if (st.kind != Step::NORMAL) continue;
+      step_writes(st, wr);
+      for (int w : wr)
+        if (writers[nodes[w].ptr] > 1 || nodes[w].stack >= 0 || nodes[w].alias_stack >= 0 || nodes[w].bucket_slot >= 0) shared_buffer[w] = 1;
+    }
+  }
+
+  // steps to launch for this evaluation: empty = nothing is stale, size == steps.size() = everything
+  void stale_steps(std::vector<int>& todo) {
+    todo.clear();
+    const int ns = (int)steps.size();
+    std::vector<char> stale(nodes.size(), 0), needed(ns, 0);
+    bool any = false;
+    for (int i : functor_order)
+      if (nodes[i].func->get_meta().state_version() != seen_version[i]) { stale[i] = 1; any = true; }
+    if (!any) return;
+    std::vector<int> wr, rd;
+    for (int s = 0; s < ns; ++s) {
+      step_writes(steps[s], wr);
+      for (int w : wr) if (stale[w]) needed[s] = 1;
+      for (int q : steps[s].multi_outs) if (stale[q]) needed[s] = 1;
+    }
+    for (int s = ns - 1; s >= 0; --s) {
+      if (!needed[s]) continue;
+      step_reads(steps[s], rd);
+      if (steps[s].multi)
+        for (auto& ins : steps[s].multi_inputs) for (auto& in : ins) rd.push_back(in.node);
+      for (int r0 : rd) {
+        const int r = nodes[r0].root >= 0 ? nodes[r0].root : r0;  // a view reads its base
+        if (!shared_buffer[r] && !shared_buffer[r0]) continue;
+        for (int base : {r, r0})
+          for (int producer : node_writers[base])
+            if (producer < s) needed[producer] = 1;
+      }
+    }
+    for (int s = 0; s < ns; ++s) if (needed[s]) todo.push_back(s);
+  }
+
+  void mark_seen() {
+    for (int i : functor_order) seen_version[i] = nodes[i].func->get_meta().state_version();
+  }
+
   void run(size_t max_version) {
     bool changed = propagate_versions(max_version);
-    if (has_run && !changed && !always_run) return;
-    if (steps.empty()) { has_run = true; return; }
+    steps_run_last = 0;
+    std::vector<int> todo;
+    const bool consider_partial = partial_ok && has_run && !always_run && max_version == std::numeric_limits<size_t>::max();
+    if (consider_partial) {
+      stale_steps(todo);
+      if (todo.empty()) return;
+      if (todo.size() < steps.size()) {
+        if (uses_rand) eteq::rng_flush();
+        for (int s : todo) launch_one(steps[s]);
+        for (auto& n : nodes)
+          if (n.exposed && n.holder) n.holder->mark_device_dirty();
+        mark_seen();
+        steps_run_last = todo.size();
+        ++g_stats.partial_runs;
+        return;
+      }
+    } else if (has_run && !changed && !always_run) {
+      return;
+    }
+    if (steps.empty()) { has_run = true; mark_seen(); return; }
+    steps_run_last = steps.size();
     if (uses_rand) eteq::rng_flush();  // a seed() since the last run must reach the device before a replay
     if (use_graph && has_run) {
       if (!graph) {
@@ -2849,6 +2960,7 @@ struct Plan {
     for (auto& n : nodes)
       if (n.exposed && n.holder) n.holder->mark_device_dirty();
     has_run = true;
+    mark_seen();
   }
 };
 
@@ -2957,6 +3069,7 @@ void PlanEvaluator::evaluate(iDevice& device, const TensSetT& targets, const Ten
   g_stats.launches = plan.n_launch_steps;
   g_stats.graph = plan.graph != nullptr;
   g_stats.cached = cache_->plans.size();
+  g_stats.steps_run = plan.steps_run_last;
 }
 
 }  // namespace cuda

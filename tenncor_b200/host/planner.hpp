@@ -23,6 +23,8 @@ struct PlanStats {
   size_t launches = 0;  // kernel launches of one run
   bool graph = false;   // replayed as a CUDA graph
   size_t cached = 0;    // plans alive in the cache
+  size_t steps_run = 0;      // steps launched by the last evaluate() (0: nothing was stale)
+  size_t partial_runs = 0;   // evaluations of this process that re-ran only the stale part of a plan
 };
 
 PlanStats last_plan_stats();

@@ -860,6 +860,7 @@ PYBIND11_MODULE(_tenncor, m) {
     auto s = cuda::last_plan_stats();
     py::dict d;
     d["nodes"] = s.nodes; d["steps"] = s.steps; d["launches_per_run"] = s.launches; d["graph"] = s.graph; d["plans_cached"] = s.cached;
+    d["steps_run"] = s.steps_run; d["partial_runs"] = s.partial_runs;
     return d;
   });
   m.def("describe_plan", [](const ETensorsT& targets) {
