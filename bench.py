@@ -483,10 +483,12 @@ def main():
         sampler.start()
         launches0 = cabi.lib().tcr_launch_count()
         start()
+        t_host = time.perf_counter()
         for _ in range(steps):
             for f in feeds:
                 f.touch()
             target.calc()
+        host_ms = (time.perf_counter() - t_host) * 1e3  # the calls have returned, the device is still working: host cost of K evaluations
         ms_total = stop_ms()
         launches = int(cabi.lib().tcr_launch_count() - launches0)
         barrier()
@@ -554,7 +556,7 @@ def main():
         finite = bool(np.isfinite(final_loss))
         if dist is not None:
             finite = bool(reduce_max([0.0 if finite else 1.0])[0] == 0.0)
-        return dict(cfg=cfg, gen=gen, w=w, target=target, ms_total=ms_total, launches=launches, plan=plan, e2e_ms=e2e_ms, e2e_serial_ms=e2e_serial_ms,
+        return dict(cfg=cfg, gen=gen, w=w, target=target, ms_total=ms_total, host_ms=host_ms, launches=launches, plan=plan, e2e_ms=e2e_ms, e2e_serial_ms=e2e_serial_ms,
                     h2d=h2d, d2h=d2h, final_loss=final_loss, finite=finite, clocks=clocks, replicas=replicas)
 
     def sub_record(name, m, steps):
@@ -565,6 +567,7 @@ def main():
         rec = {"metric": "train steps/sec", "value": round(world * 1e3 / ms_step, 3), "unit": "steps/s", "ms_per_step": round(ms_step, 4), "steps": steps,
                "config": dict({"workload": name}, **WORKLOADS[name], desc=m["cfg"].desc, batch_per_gpu=w.get("nbatch", w.get("batch")), matmul=args.precision),
                "tflops": round(flops / ms_step / 1e9, 2), "launches_per_step": round(m["launches"] / steps, 1), "plan": m["plan"],
+               "host_ms_per_step": round(m["host_ms"] / steps, 4),
                "e2e": e2e_entry(world, steps, m["e2e_ms"], m["e2e_serial_ms"], m["h2d"], m["d2h"]), "final_loss": m["final_loss"]}
         if m["replicas"] is not None:
             rec["replicas"] = m["replicas"]
@@ -633,6 +636,7 @@ def main():
             "clocks": main_m["clocks"],
             "e2e": e2e_entry(world, args.steps, main_m["e2e_ms"], main_m["e2e_serial_ms"], main_m["h2d"], main_m["d2h"]),
             "gpu_launches": main_m["launches"], "launches_per_step": round(main_m["launches"] / args.steps, 1), "plan": main_m["plan"],
+            "host_ms_per_step": round(main_m["host_ms"] / args.steps, 4),
             "roofline": roof,
             "cpu_baseline": cpu_baseline,
             "final_loss": main_m["final_loss"],

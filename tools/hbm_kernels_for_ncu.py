@@ -32,5 +32,18 @@ prog = cabi.make_program(F, (8192 * 784, 1, 1), [(px.ptr, cabi.UINT8, (0, 0, 0))
                          [(cabi.EW_MOV, 1, 0), (cabi.EW_CONST, 2, 0, 0, 0, 1.0 / 255.0), (cabi.OP["MUL"], 0, 1, 2)])
 for _ in range(2):
     cabi.check(lib.tcr_elementwise(C.byref(prog)))
+# round 2, session 3: vector-broadcast elementwise, flat ARGMAX with 16-byte loads, SLICE through the row-window kernel
+bias = cabi.to_device(rng.uniform(-1, 1, 1024).astype(np.float32))
+big = cabi.empty(1 << 26, np.float32)
+prog2 = cabi.make_program(F, (1024, (1 << 26) // 1024, 1), [(a.ptr, F, (0, 0, 0)), (bias.ptr, F, (0, 1, 0))], [(big.ptr, F, 0)],
+                          [(cabi.OP["ADD"], 0, 0, 1), (cabi.OP["SIGMOID"], 0, 0)])
+for _ in range(2):
+    cabi.check(lib.tcr_elementwise(C.byref(prog2)))
+for _ in range(2):
+    cabi.check(lib.tcr_argmax(C.c_void_p(a.ptr), C.c_void_p(small.ptr), shp, 8, F))
+offs = (C.c_int64 * 8)(0, 32, 0, 0, 0, 0, 0, 0)
+exts = (C.c_int64 * 8)(1024, 64, 64, 1, 1, 1, 1, 1)
+for _ in range(2):
+    cabi.check(lib.tcr_slice(C.c_void_p(a.ptr), C.c_void_p(out.ptr), cabi.shape8(s3), offs, exts, 4))
 cabi.sync()
 print("ok")
