@@ -433,6 +433,15 @@ int tcr_conv(const void* image, const void* kernel, void* out, const int64_t img
  * instead of operator.hpp:1143-1187's scalar slide over a mostly-zero rank. 4-byte elements. */
 int tcr_im2col(const void* image, void* cols, const int64_t img_shape[8], const int64_t win_shape[8],
                int64_t row_pitch, int elem_size);
+/* tcr_im2col + tcr_gemm(cols, b, c) WITHOUT the patch matrix in memory (implicit GEMM): the tensor-core kernel's producer warp gathers
+ * each 128-row x 32-k tile of `cols` straight from the image with cp.async into the shared-memory arrangement the MMA reads, so the
+ * matrix (9x the image for a 3 x 3 window) is neither written nor re-read. `desc` describes the product as if `a` were the patch
+ * matrix with row pitch k (a_sm / a_sk are ignored); bias / activation epilogues as in tcr_gemm. Eligible views: image [C, W, H,
+ * images...], window [C, kw, kh, 1...] with (kw * C) % 32 == 0, FLOAT, TF32 / 3xTF32. Anything else returns TCR_ERR_UNSUPPORTED
+ * without launching (callers keep the two-call form). Replaces the reference's scalar slide over a padded rank for conv2d
+ * (internal/eigen/operator.hpp:1143-1187 under cfg/tenncor/nn.yml:48-98). */
+int tcr_gemm_patches(const void* image, const void* b, void* c, const tcr_gemm_desc* desc, const int64_t img_shape[8],
+                     const int64_t win_shape[8]);
 /* Adjoint of tcr_im2col (the conv2d image gradient: cols = upstream . kernel^T on the tensor cores, then this):
  * image[u] = sum over window coordinates w with a valid position u - w of cols[position(u - w)][w]. Every image
  * element is written (zero where no window reaches). Terms are added in a fixed order: deterministic. FLOAT only. */

@@ -47,7 +47,7 @@ SYMBOLS = [
     "tcr_graph_end", "tcr_graph_launch", "tcr_graph_destroy", "tcr_launch_count", "tcr_elementwise", "tcr_elementwise_reduce", "tcr_elementwise_multi", "tcr_cell_backward",
     "tcr_unary", "tcr_binary", "tcr_nnary", "tcr_select", "tcr_cast", "tcr_assign", "tcr_rand_unif", "tcr_rand_seed", "tcr_rand_unif_stream",
     "tcr_reduce", "tcr_argmax", "tcr_map_copy", "tcr_extend", "tcr_permute", "tcr_slice", "tcr_pad",
-    "tcr_stride", "tcr_scatter", "tcr_reverse", "tcr_concat", "tcr_copy2d_batched", "tcr_gemm", "tcr_gemm_grouped", "tcr_gemm_grouped_check", "tcr_gemm_grouped_seq_prepare", "tcr_gemm_grouped_seq_launch", "tcr_gemm_grouped_seq_destroy", "tcr_rnn_debug_read", "tcr_contract", "tcr_conv", "tcr_im2col", "tcr_col2im",
+    "tcr_stride", "tcr_scatter", "tcr_reverse", "tcr_concat", "tcr_copy2d_batched", "tcr_gemm", "tcr_gemm_grouped", "tcr_gemm_grouped_check", "tcr_gemm_grouped_seq_prepare", "tcr_gemm_grouped_seq_launch", "tcr_gemm_grouped_seq_destroy", "tcr_rnn_debug_read", "tcr_contract", "tcr_conv", "tcr_im2col", "tcr_gemm_patches", "tcr_col2im",
     "tcr_comm_unique_id", "tcr_comm_init", "tcr_comm_destroy", "tcr_comm_rank", "tcr_comm_size",
     "tcr_allreduce_sum", "tcr_comm_symm_alloc", "tcr_comm_symm_reset", "tcr_comm_p2p_ready",
 ]

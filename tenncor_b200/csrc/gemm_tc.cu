@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -43,6 +44,13 @@ struct TcParams {
   int a_mn_major, b_mn_major;  // 0: K-major (K contiguous), 1: MN-major (M / N contiguous)
   int kb_per_split;            // k-blocks handled by one blockIdx.z (split-K); partial tiles go to `c` + z*m*n
   int raw_hi;                  // 3xTF32: leave the landed tile untouched (the tensor core truncates it to tf32 = hi) and only write lo
+  // GATHER: A is the patch matrix of a conv2d that is never written to memory (tcr_gemm_patches). Row `pos` = valid window position
+  // (x, y, image) of an image [C, W, H, images] (C fastest); column k = c + C * (kx + kw * ky): for a fixed ky the kw * C values
+  // are contiguous in the image, so with (kw * C) % 32 == 0 every 32-k block of a row is 128 contiguous bytes
+  const float* g_img;
+  int g_c, g_w, g_h;           // image extents (elements)
+  int g_pw, g_ph;              // valid positions along x / y
+  int g_run;                   // kw * C: contiguous run of one window row (elements)
   // fused split-K reduction: the last CTA of a tile to finish (ticket counter) sums the partial tiles
   // in split order and applies the epilogue — deterministic, and no second launch
   int* counters;               // one per output tile, zero between launches (self-resetting); null = separate reduce kernel
@@ -134,7 +142,7 @@ __device__ __forceinline__ float act_f(int act, float x) {
 }
 
 // MODE 1: TF32 (STAGES x 32 KiB), MODE 2: 3xTF32 (STAGES x 64 KiB)
-template <int MODE, int STAGES>
+template <int MODE, int STAGES, bool GATHER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -161,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], GATHER ? 33 : 1);  // GATHER: + one arrival per lane of the producer warp when its cp.async copies have landed
       mbar_init(&empty[s], 1);
       mbar_init(&ready[s], 4);  // one arrival per converter warp
     }
@@ -178,7 +186,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   TCR_PDL_ENTER();  // everything above touched no global memory: the previous kernel may still be running
 
-  if (warp == 0) {
+  if (GATHER && warp == 0) {
+    // ================= producer: B tile by TMA, A tile gathered from the image =================
+    // lane l owns rows l, l + 32, l + 64, l + 96 of the tile: their 128-byte k-block is copied with 8 x cp.async (16 bytes) into the
+    // SWIZZLE_128B arrangement the TMA would have produced (16-byte chunk j of row r sits at chunk j ^ (r & 7)); rows beyond the
+    // last position are zero-filled (src-size 0)
+    const float* rowp[4];
+    uint32_t rowok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t pos = m0 + lane + 32 * i;
+      rowok[i] = pos < p.m ? 16u : 0u;
+      const int64_t q = pos < p.m ? pos : 0;
+      const int64_t x = q % p.g_pw, t = q / p.g_pw, y = t % p.g_ph, img = t / p.g_ph;
+      rowp[i] = p.g_img + (int64_t)p.g_c * (x + (int64_t)p.g_w * (y + (int64_t)p.g_h * img));
+    }
+    const int64_t row_stride = (int64_t)p.g_w * p.g_c;  // one image row down
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t round = kb / STAGES;
+      if (kb >= STAGES) mbar_wait(&empty[s], (round - 1) & 1);
+      const int32_t k0 = (kb_begin + kb) * BK;
+      if (lane == 0) {
+        mbar_expect_tx(&full[s], TILE_BYTES);
+        if (!p.b_mn_major) {
+          tma_load_2d(&map_b, &full[s], tile_b(s), k0, (int32_t)n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_2d(&map_b, &full[s], tile_b(s) + j * 4096, (int32_t)n0 + 32 * j, k0);
+        }
+      }
+      const int ky = k0 / p.g_run;
+      const int64_t off = (int64_t)ky * row_stride + (k0 - ky * p.g_run);
+      const uint32_t tile = smem_u32(tile_a(s));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t r = (uint32_t)lane + 32u * i;
+        const float* src = rowp[i] + off;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+          const uint32_t dst = tile + r * 128u + ((j ^ (r & 7u)) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src + 4 * j), "r"(rowok[i]) : "memory");
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[s])) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -218,6 +272,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int s = kb % STAGES;
         const uint32_t round = kb / STAGES;
         mbar_wait(MODE == 2 ? &ready[s] : &full[s], round & 1);
+        if (GATHER && MODE != 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async writes (generic proxy) -> MMA operand reads
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_addr = smem_u32(tile_a(s)), b_addr = smem_u32(tile_b(s));
 #pragma unroll
@@ -468,17 +523,17 @@ int make_map(CUtensorMap* map, const float* base, int64_t dim0, int64_t dim1, in
   return TCR_OK;
 }
 
-template <int MODE, int STAGES>
+template <int MODE, int STAGES, bool GATHER = false>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int splits) {
   constexpr int STAGE_BYTES = (MODE == 2 ? 4 : 2) * TILE_BYTES;
   constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool configured = false;
   if (!configured) {
-    TCR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    TCR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, STAGES, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(p.n, BN), (unsigned)ceil_div(p.m, BM), (unsigned)splits);
-  TCR_LAUNCH((gemm_tc_kernel<MODE, STAGES>), grid, NUM_THREADS, SMEM, ma, mb, p);
+  TCR_LAUNCH((gemm_tc_kernel<MODE, STAGES, GATHER>), grid, NUM_THREADS, SMEM, ma, mb, p);
   TCR_CHECK_LAUNCH();
   return TCR_OK;
 }
@@ -528,7 +583,7 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
     if (rc) return rc;
     rc = b_mn ? make_map(&mb, bp, d->n, d->k, b_pitch, 32, 32, true) : make_map(&mb, bp, d->k, d->n, b_pitch, 32, 128, false);
     if (rc) return rc;
-    TcParams p;
+    TcParams p = TcParams();
     p.m = d->m; p.n = d->n; p.k = d->k;
     p.c_sm = d->c_sm; p.c_sn = d->c_sn;
     p.c = (float*)c + bi * d->c_sb;
@@ -603,4 +658,50 @@ int gemm_tc_dispatch(const void* a, const void* b, void* c, const tcr_gemm_desc*
   return TCR_OK;
 }
 
+// The conv2d composite's forward product with the patch matrix gathered inside the kernel (see TcParams::g_*). Returns
+// TCR_ERR_UNSUPPORTED (nothing launched) when the view or the operands do not fit: the caller keeps tcr_im2col + tcr_gemm.
+int gemm_tc_patches(const void* image, const void* b, void* c, const tcr_gemm_desc* d, const int64_t img[8], const int64_t win[8]) {
+  auto unsupported = [](const char* why) { set_error("tcr_gemm_patches: %s", why); return TCR_ERR_UNSUPPORTED; };
+  if (d->dtype != TCR_FLOAT || d->batch != 1 || d->accumulate || d->post_op) return unsupported("fp32, one problem, no accumulation / post-op");
+  if (d->precision != TCR_GEMM_TF32 && d->precision != TCR_GEMM_3XTF32) return unsupported("tensor-core precisions only");
+  for (int r = 3; r < 8; ++r)
+    if (win[r] != 1) return unsupported("the window covers channels, x and y only");
+  const int64_t C = img[0], W = img[1], H = img[2], kw = win[1], kh = win[2];
+  int64_t images = 1;
+  for (int r = 3; r < 8; ++r) images *= img[r];
+  if (win[0] != C || kw > W || kh > H) return unsupported("the window spans every channel");
+  const int64_t run = kw * C, K = run * kh, pw = W - kw + 1, ph = H - kh + 1, M = pw * ph * images;
+  if (run % BK != 0 || C % 4 != 0) return unsupported("kw * channels must be a multiple of 32");
+  if (d->k != K || d->m != M) return unsupported("product extents do not match the patch view");
+  if (W * C >= (1ll << 31) || M >= (1ll << 31) || (((uintptr_t)image) & 15) != 0) return unsupported("image too large or misaligned");
+  const bool b_k = d->b_sk == 1 || d->k == 1, b_n = d->b_sn == 1 || d->n == 1;
+  if (!(b_k || b_n)) return unsupported("kernel operand is strided in both ranks");
+  const int b_mn = !(d->b_sk == 1) && b_n ? 1 : (b_k ? 0 : 1);
+  const int64_t b_pitch = b_mn ? d->b_sk : d->b_sn;
+  if ((((uintptr_t)b) & 15) != 0 || b_pitch <= 0 || (b_pitch % 4) != 0 || b_pitch < (b_mn ? d->n : d->k)) return unsupported("kernel operand not addressable by TMA");
+  CUtensorMap ma, mb;
+  std::memset(&ma, 0, sizeof(ma));
+  int rc = b_mn ? make_map(&mb, (const float*)b, d->n, d->k, b_pitch, 32, 32, true) : make_map(&mb, (const float*)b, d->k, d->n, b_pitch, 32, 128, false);
+  if (rc) return rc;
+  TcParams p = TcParams();
+  p.m = M; p.n = d->n; p.k = K;
+  p.c_sm = d->c_sm; p.c_sn = d->c_sn;
+  p.c = (float*)c;
+  p.bias = (const float*)d->bias;
+  p.epilogue = d->epilogue; p.activation = d->activation; p.accumulate = 0;
+  p.a_mn_major = 0; p.b_mn_major = b_mn;
+  p.raw_hi = 1;
+  p.kb_per_split = (int)(K / BK);
+  p.g_img = (const float*)image;
+  p.g_c = (int)C; p.g_w = (int)W; p.g_h = (int)H; p.g_pw = (int)pw; p.g_ph = (int)ph; p.g_run = (int)run;
+  return d->precision == TCR_GEMM_TF32 ? launch_tc<1, 3, true>(ma, mb, p, 1) : launch_tc<2, 3, true>(ma, mb, p, 1);
+}
+
 }  // namespace tcr
+
+extern "C" int tcr_gemm_patches(const void* image, const void* b, void* c, const tcr_gemm_desc* desc, const int64_t img_shape[8],
+                                const int64_t win_shape[8]) {
+  TCR_REQUIRE_DEVICE();
+  TCR_ARG(image && b && c && desc && img_shape && win_shape, "tcr_gemm_patches: null argument");
+  return tcr::gemm_tc_patches(image, b, c, desc, img_shape, win_shape);
+}

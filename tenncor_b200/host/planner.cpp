@@ -2567,10 +2567,18 @@ struct Plan {
       check(tcr_gemm(st.in[0], st.in[1], st.conv_cols, &d), "tcr_gemm");
       check(tcr_col2im(st.conv_cols, (char*)st.out + st.conv_out_offset, st.conv_img, st.conv_win, st.conv_pitch, FLOAT), "tcr_col2im");
     } else if (st.conv_fused) {
-      check(tcr_im2col(st.in[0], st.conv_cols, st.conv_img, st.conv_win, st.conv_pitch, (int)sizeof(float)), "tcr_im2col");
       tcr_gemm_desc d = st.gemm;
       d.precision = gemm_precision();
       d.bias = st.in.size() > 2 ? st.in[2] : nullptr;
+      // forward product: the kernel gathers the patch tiles itself when the view allows it (tcr_gemm_patches); the patch matrix is
+      // written only for the shapes it declines (few channels, windows over other ranks) and for the kernel gradient
+      static const bool implicit = std::getenv("TCR_NO_IMPLICIT_CONV") == nullptr;
+      if (implicit && !st.conv_grad && st.conv_pitch == d.k) {
+        const int rc = tcr_gemm_patches(st.in[0], st.in[1], st.out, &d, st.conv_img, st.conv_win);
+        if (rc == TCR_OK) return;
+        if (rc != TCR_ERR_UNSUPPORTED) check(rc, "tcr_gemm_patches");
+      }
+      check(tcr_im2col(st.in[0], st.conv_cols, st.conv_img, st.conv_win, st.conv_pitch, (int)sizeof(float)), "tcr_im2col");
       check(tcr_gemm(st.conv_cols, st.in[1], st.out, &d), "tcr_gemm");
     } else if (st.gemm_fused) {
       tcr_gemm_desc d = st.gemm;

@@ -152,3 +152,59 @@ def test_conv_plan_is_fused_and_graph_replayed(gpu):
     assert sum(n.startswith("CONV2D im2col+GEMM") for n in names) == 4, names
     assert sum(n.startswith("CONV2D-dK") for n in names) == 2, names
     assert sum(n.startswith("CONV2D-dX") for n in names) == 1, names
+
+
+@pytest.mark.parametrize("precision", [1, 2], ids=["tf32", "3xtf32"])
+@pytest.mark.parametrize("img_shape,win,cout,act", [
+    ([32, 10, 9, 4], [32, 3, 3, 1], 24, "TANH"),     # 224 positions: the second row tile is zero-filled past row 96; 24 of 128 columns
+    ([64, 34, 34, 8], [64, 3, 3, 1], 64, None),      # the conv bench layer at batch 8: 8192 positions, K = 576
+    ([8, 12, 11, 3], [8, 4, 2, 1], 40, "SIGMOID"),   # run = 32: one k-block per window row
+    ([32, 6, 5, 2, 3], [32, 1, 1, 1, 1], 16, None),  # 1 x 1 window, two batch ranks
+], ids=["ragged", "bench", "run32", "pointwise"])
+def test_gemm_patches_matches_the_materialised_patch_matrix(gpu, img_shape, win, cout, act, precision):
+    """tcr_gemm_patches (implicit GEMM: patch tiles gathered by the kernel's producer warp) against float64 over the numpy patch matrix
+    (bounds of tests/test_gemm_tc_gpu.py) and against tcr_im2col + tcr_gemm on the device."""
+    rng = np.random.default_rng(int(np.prod(img_shape)) + cout)
+    lib = gpu.lib()
+    s8 = list(img_shape) + [1] * (8 - len(img_shape))
+    w8 = list(win) + [1] * (8 - len(win))
+    img = rng.uniform(-1, 1, int(np.prod(s8))).astype(np.float32)
+    cols = _im2col(img, s8, w8)
+    m, k = cols.shape
+    kern = (rng.uniform(-1, 1, (k, cout)) * 0.2).astype(np.float32)
+    bias = rng.uniform(-1, 1, cout).astype(np.float32)
+    pre = cols.astype(np.float64) @ kern.astype(np.float64) + bias.astype(np.float64)
+    S = np.abs(cols).astype(np.float64) @ np.abs(kern).astype(np.float64)
+    want = np.tanh(pre) if act == "TANH" else 1 / (1 + np.exp(-pre)) if act == "SIGMOID" else pre
+    tol = S * (2.0 ** -10 if precision == 1 else (2.0 ** -19 + k * 2.0 ** -23)) + 2e-6
+    dimg, dk, db = gpu.to_device(img), gpu.to_device(kern), gpu.to_device(bias)
+    out = gpu.to_device(np.full(m * cout, 9.0, np.float32))
+    d = gpu.GemmDesc()
+    d.m, d.n, d.k, d.batch = m, cout, k, 1
+    d.a_sm, d.a_sk, d.b_sk, d.b_sn, d.c_sm, d.c_sn = k, 1, cout, 1, cout, 1
+    d.dtype, d.precision, d.epilogue, d.activation, d.bias = gpu.FLOAT, precision, 1, (gpu.OP[act] if act else 0), db.ptr
+    launches = lib.tcr_launch_count()
+    gpu.check(lib.tcr_gemm_patches(C.c_void_p(dimg.ptr), C.c_void_p(dk.ptr), C.c_void_p(out.ptr), C.byref(d), gpu.shape8(s8), gpu.shape8(w8)))
+    assert lib.tcr_launch_count() == launches + 1  # one kernel, no patch matrix
+    got = gpu.to_host(out, m * cout, np.float32).reshape(m, cout).astype(np.float64)
+    assert np.all(np.abs(got - want) <= tol), float(np.abs(got - want).max())
+    # the two-call form on the device
+    dcols = gpu.empty(m * k, np.float32)
+    gpu.check(lib.tcr_im2col(C.c_void_p(dimg.ptr), C.c_void_p(dcols.ptr), gpu.shape8(s8), gpu.shape8(w8), C.c_int64(k), 4))
+    out2 = gpu.empty(m * cout, np.float32)
+    gpu.check(lib.tcr_gemm(C.c_void_p(dcols.ptr), C.c_void_p(dk.ptr), C.c_void_p(out2.ptr), C.byref(d)))
+    two = gpu.to_host(out2, m * cout, np.float32).reshape(m, cout).astype(np.float64)
+    assert np.all(np.abs(got - two) <= 2 * tol)
+
+
+def test_gemm_patches_declines_views_it_cannot_gather(gpu):
+    lib = gpu.lib()
+    s8, w8 = [3, 10, 9, 4, 1, 1, 1, 1], [3, 3, 2, 1, 1, 1, 1, 1]  # kw * C = 9
+    d = gpu.GemmDesc()
+    d.m, d.n, d.k, d.batch = 8 * 8 * 4, 16, 18, 1
+    d.b_sk, d.b_sn, d.c_sm, d.c_sn = 16, 1, 16, 1
+    d.dtype, d.precision = gpu.FLOAT, 2
+    buf = gpu.empty(1 << 16, np.float32)
+    launches = lib.tcr_launch_count()
+    rc = lib.tcr_gemm_patches(C.c_void_p(buf.ptr), C.c_void_p(buf.ptr), C.c_void_p(buf.ptr), C.byref(d), gpu.shape8(s8), gpu.shape8(w8))
+    assert rc == 6 and lib.tcr_launch_count() == launches  # TCR_ERR_UNSUPPORTED, nothing launched
