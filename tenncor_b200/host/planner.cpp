@@ -2888,15 +2888,15 @@ struct Plan {
     }
   }
 
-  // steps to launch for this evaluation: empty = nothing is stale, size == steps.size() = everything
-  void stale_steps(std::vector<int>& todo) {
+  // steps to launch for this evaluation (size == steps.size() = everything); false = no functor of the plan is stale
+  bool stale_steps(std::vector<int>& todo) {
     todo.clear();
     const int ns = (int)steps.size();
     std::vector<char> stale(nodes.size(), 0), needed(ns, 0);
     bool any = false;
     for (int i : functor_order)
       if (nodes[i].func->get_meta().state_version() != seen_version[i]) { stale[i] = 1; any = true; }
-    if (!any) return;
+    if (!any) return false;
     std::vector<int> wr, rd;
     for (int s = 0; s < ns; ++s) {
       step_writes(steps[s], wr);
@@ -2917,6 +2917,7 @@ struct Plan {
       }
     }
     for (int s = 0; s < ns; ++s) if (needed[s]) todo.push_back(s);
+    return true;
   }
 
   void mark_seen() {
@@ -2929,16 +2930,15 @@ struct Plan {
     std::vector<int> todo;
     const bool consider_partial = partial_ok && has_run && !always_run && max_version == std::numeric_limits<size_t>::max();
     if (consider_partial) {
-      stale_steps(todo);
-      if (todo.empty()) return;
-      if (todo.size() < steps.size()) {
+      if (!stale_steps(todo)) return;
+      if (todo.size() < steps.size()) {  // possibly none: only views of leaves are stale — their holders still learn about it below
         if (uses_rand) eteq::rng_flush();
         for (int s : todo) launch_one(steps[s]);
         for (auto& n : nodes)
           if (n.exposed && n.holder) n.holder->mark_device_dirty();
         mark_seen();
         steps_run_last = todo.size();
-        ++g_stats.partial_runs;
+        if (!todo.empty()) ++g_stats.partial_runs;
         return;
       }
     } else if (has_run && !changed && !always_run) {
