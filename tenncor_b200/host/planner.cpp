@@ -2872,6 +2872,9 @@ struct Plan {
     for (size_t k = 0; k < steps.size(); ++k) {
       const Step& st = steps[k];
       if (st.kind != Step::NORMAL) { partial_ok = false; continue; }  // gradient exchange: every rank runs the same launches
+      // A plan that updates variables is stale from top to bottom after every run (the ASSIGNs bump what everything reads); the few
+      // steps that are not (constant sub-expressions) are cheaper to replay inside the captured graph than to launch the rest eagerly
+      if (is_assign(nodes[st.out_node].op)) partial_ok = false;
       step_writes(st, wr);
       for (int q : st.multi_outs) wr.push_back(q);
       std::sort(wr.begin(), wr.end());
