@@ -38,3 +38,15 @@ def test_c4_training_step_is_one_product_and_one_cell_launch_per_time_step():
     assert kinds["GEMM^T"] == 5                  # four gate weight gradients with K = seq x batch, one for the output layer
     assert kinds["CONCAT"] + kinds.get("CONCAT-BATCH(127)", 0) + kinds.get("CONCAT-BATCH(128)", 0) <= 2
     assert not any(_kind(s) in ("PERMUTE", "SLICE", "EXTEND") for s in plan)
+
+
+def test_gru_training_step_groups_its_gate_products():
+    """cfg/tenncor/layer.yml:770-813: update and reset gates share their operands (one grouped launch per time step and pass), the
+    candidate reads the reset hidden state and gets its own; the per-step CONCATs leave the chain as batched copies."""
+    cfg = configs.recurrent("gru", vocab=128, hidden=1024, seq=128, batch=64, learning_rate=0.001)
+    plan = tc.describe_plan([cfg.train])
+    kinds = collections.Counter(_kind(s) for s in plan)
+    assert len(plan) <= 1750, len(plan)
+    assert kinds["GEMM-GROUP"] == 512 and kinds["GEMM-SUM"] == 127 and kinds["ADD-STACK(128)"] == 3
+    assert sum(v for k, v in kinds.items() if k.startswith("CONCAT-BATCH")) == 2 and kinds["CONCAT"] == 0
+    assert kinds["PERMUTE"] == 0 and kinds["EXTEND"] == 0
